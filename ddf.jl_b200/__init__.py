@@ -1,0 +1,16 @@
+"""ddf.jl_b200 -- B200-native (sm_100a) implementation of DDF.jl's discrete
+exterior calculus operator hot path, behind the reference's own call surface.
+
+Import as ``import ddf.jl_b200 as ddf`` (the ``ddf/`` shim at the repo root maps
+the dotted name onto this directory).  All compute runs in libddf_b200.so
+(hand-written CUDA, C ABI in include/ddf_b200.h); there is no CPU fallback.
+"""
+from ._lib import DDFError, LIB_PATH, load  # noqa: F401
+from .core import (Context, Dl, Fun, Manifold, Op, Pr, default_context, op_from_csc, op_from_diag,  # noqa: F401
+                   rand_fun, set_default_context, unit_fun, zero_fun)
+from .manifoldops import (boundary, boundary_of, coderiv, coderiv_of, delaunay_mesh, deriv, deriv_of,  # noqa: F401
+                          hodge, hodge_of, integral, invhodge, invhodge_of, isboundary,
+                          large_hypercube_manifold, laplace, laplace_of, one, refined_manifold,
+                          refined_simplex_manifold, regular_simplex, sample, simplex_manifold, zero)
+from .wave import wave, wave_dt, wave_leapfrog, wave_rhs, wave_step_bytes  # noqa: F401
+from . import dist  # noqa: F401

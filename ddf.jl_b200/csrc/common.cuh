@@ -1,0 +1,172 @@
+// common.cuh -- shared host-side plumbing of libddf_b200 (handles, error state,
+// device allocation accounting, launch counting).  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/ddf_b200.h"
+
+#define DDF_MAXD 5            // topology (assembly, d_k) up to D = 5 like the reference tests
+#define DDF_MAXC 3            // geometry kernels are written for C <= 3 (BASELINE configs are 2D/3D)
+
+// chop threshold of the Op constructor: abs2(f) < sqrt(eps(Float64)^3)  (src/Ops.jl:52,57)
+#define DDF_CHOP_ABS2 3.308722450212111e-24
+
+void ddf_set_error(const char* fmt, ...);
+
+#define DDF_FAIL(...)              \
+  do {                             \
+    ddf_set_error(__VA_ARGS__);    \
+    return 1;                      \
+  } while (0)
+
+#define DDF_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) {                                                  \
+      ddf_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,        \
+                    cudaGetErrorString(_e));                                  \
+      return 1;                                                               \
+    }                                                                         \
+  } while (0)
+
+#define DDF_CHECK(expr)            \
+  do {                             \
+    int _r = (expr);               \
+    if (_r != 0) return _r;        \
+  } while (0)
+
+#define DDF_TRY_BEGIN try {
+#define DDF_TRY_END                                        \
+  }                                                        \
+  catch (const std::exception& e) {                        \
+    ddf_set_error("exception: %s", e.what());              \
+    return 1;                                              \
+  }                                                        \
+  catch (...) {                                            \
+    ddf_set_error("unknown exception");                    \
+    return 1;                                              \
+  }
+
+struct ddf_ctx {
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;     // compute stream
+  cudaStream_t comm_stream = nullptr;  // halo / NCCL stream
+  cudaEvent_t ev_tic = nullptr, ev_toc = nullptr, ev_a = nullptr, ev_b = nullptr;
+  int64_t bytes_in_use = 0;
+  int64_t launches = 0;
+  // scratch for reductions
+  double* red_dev = nullptr;         // small device buffer
+  double* red_host = nullptr;        // pinned
+  // L2 flush buffer
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  // NCCL (dlopen'ed lazily)
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+int ddf_dev_alloc(ddf_ctx* ctx, void** p, size_t bytes);
+void ddf_dev_free(ddf_ctx* ctx, void* p, size_t bytes);
+
+// RAII-ish device buffer tied to a ctx (not thread safe; one ctx per thread)
+template <typename T>
+struct DevBuf {
+  ddf_ctx* ctx = nullptr;
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  int alloc(ddf_ctx* c, size_t count) {
+    release();
+    ctx = c;
+    n = count;
+    if (count == 0) { p = nullptr; return 0; }
+    return ddf_dev_alloc(c, (void**)&p, count * sizeof(T));
+  }
+  void release() {
+    if (p) ddf_dev_free(ctx, p, n * sizeof(T));
+    p = nullptr;
+    n = 0;
+  }
+  void swap(DevBuf& o) {
+    std::swap(ctx, o.ctx); std::swap(p, o.p); std::swap(n, o.n);
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+struct ddf_vec {
+  ddf_ctx* ctx = nullptr;
+  DevBuf<double> d;
+  int64_t n = 0;
+};
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// grid helper: 1-D launch with 64-bit element counts
+static inline int grid_for(int64_t n, int per_block, int* grid) {
+  int64_t g = ceil_div64(n, per_block);
+  if (g > 0x7fffffffLL) { ddf_set_error("grid too large"); return 1; }
+  *grid = (int)(g > 0 ? g : 1);
+  return 0;
+}
+
+#define DDF_LAUNCH_CHECK(ctx)                                                   \
+  do {                                                                          \
+    (ctx)->launches++;                                                          \
+    cudaError_t _e = cudaGetLastError();                                        \
+    if (_e != cudaSuccess) {                                                    \
+      ddf_set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__,      \
+                    cudaGetErrorString(_e));                                    \
+      return 1;                                                                 \
+    }                                                                           \
+  } while (0)
+
+// ---------------------------------------------------------------- PTX helpers
+// streaming (read-once) 128-bit index load: bypass L1 allocation so the L1 stays
+// free for the x-gather.
+__device__ __forceinline__ int4 ld_stream_int4(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int2 ld_stream_int2(const int2* p) {
+  int2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];"
+               : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int ld_stream_int(const int* p) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double ld_stream_f64(const double* p) {
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+               : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+// streaming (write-once) stores: evict-first so the outputs do not push the
+// gathered x out of L2.
+__device__ __forceinline__ void st_stream_f64x2(double2* p, double a, double b) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void st_stream_f64(double* p, double a) {
+  asm volatile("st.global.cs.f64 [%0], %1;" :: "l"(p), "d"(a) : "memory");
+}

@@ -1,0 +1,350 @@
+// core.cu -- context, error state, device allocation accounting, cochain
+// vectors (Fun.values, src/Funs.jl:16-31) with their axpy-class arithmetic
+// (src/Funs.jl:156-188, src/SparseOps.jl:108-119) and reductions
+// (ManifoldOps.jl:150-164; norms used at examples/wave.jl:127,162).
+#include "common.cuh"
+#include "mesh.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void ddf_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* ddf_last_error(void) { return g_err; }
+extern "C" int ddf_version(void) { return 100; }
+
+int ddf_dev_alloc(ddf_ctx* ctx, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) return 0;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ddf_set_error("cudaMalloc(%zu bytes) failed: %s (in use: %lld bytes)", bytes,
+                  cudaGetErrorString(e), (long long)ctx->bytes_in_use);
+    return 1;
+  }
+  ctx->bytes_in_use += (int64_t)bytes;
+  return 0;
+}
+
+void ddf_dev_free(ddf_ctx* ctx, void* p, size_t bytes) {
+  if (!p) return;
+  cudaFree(p);
+  if (ctx) ctx->bytes_in_use -= (int64_t)bytes;
+}
+
+extern "C" int ddf_ctx_create(int device, ddf_ctx** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    DDF_FAIL("no CUDA device available (%s); libddf_b200 has no CPU fallback",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  if (device < 0 || device >= ndev) DDF_FAIL("device %d out of range (have %d)", device, ndev);
+  cudaDeviceProp prop;
+  DDF_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    DDF_FAIL("device %d is sm_%d%d; libddf_b200 is built for sm_100a only (no fallback)", device,
+             prop.major, prop.minor);
+  DDF_CUDA(cudaSetDevice(device));
+  ddf_ctx* c = new ddf_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  DDF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  DDF_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  DDF_CUDA(cudaEventCreate(&c->ev_tic));
+  DDF_CUDA(cudaEventCreate(&c->ev_toc));
+  DDF_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+  DDF_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+  DDF_CHECK(ddf_dev_alloc(c, (void**)&c->red_dev, 4096 * sizeof(double)));
+  DDF_CUDA(cudaMallocHost((void**)&c->red_host, 4096 * sizeof(double)));
+  *out = c;
+  return 0;
+  DDF_TRY_END
+}
+
+extern "C" int ddf_ctx_destroy(ddf_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  ddf_comm_destroy(c);
+  if (c->flush_buf) ddf_dev_free(c, c->flush_buf, c->flush_bytes);
+  ddf_dev_free(c, c->red_dev, 4096 * sizeof(double));
+  cudaFreeHost(c->red_host);
+  cudaEventDestroy(c->ev_tic);
+  cudaEventDestroy(c->ev_toc);
+  cudaEventDestroy(c->ev_a);
+  cudaEventDestroy(c->ev_b);
+  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->comm_stream);
+  delete c;
+  return 0;
+}
+
+extern "C" int ddf_sync(ddf_ctx* c) {
+  DDF_CUDA(cudaSetDevice(c->device));
+  DDF_CUDA(cudaStreamSynchronize(c->stream));
+  DDF_CUDA(cudaStreamSynchronize(c->comm_stream));
+  return 0;
+}
+
+extern "C" int ddf_ctx_bytes_in_use(ddf_ctx* c, int64_t* out) { *out = c->bytes_in_use; return 0; }
+extern "C" int ddf_ctx_launch_count(ddf_ctx* c, int64_t* out) { *out = c->launches; return 0; }
+
+extern "C" int ddf_timer_tic(ddf_ctx* c) {
+  DDF_CUDA(cudaEventRecord(c->ev_tic, c->stream));
+  return 0;
+}
+extern "C" int ddf_timer_toc(ddf_ctx* c, double* ms) {
+  DDF_CUDA(cudaEventRecord(c->ev_toc, c->stream));
+  DDF_CUDA(cudaEventSynchronize(c->ev_toc));
+  float f = 0;
+  DDF_CUDA(cudaEventElapsedTime(&f, c->ev_tic, c->ev_toc));
+  *ms = (double)f;
+  return 0;
+}
+
+__global__ void k_fill_u32(uint32_t* p, size_t n, uint32_t v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v + (uint32_t)i;
+}
+
+extern "C" int ddf_flush_l2(ddf_ctx* c) {
+  DDF_TRY_BEGIN
+  if (!c->flush_buf) {
+    c->flush_bytes = (size_t)512 << 20;   // 512 MiB > 126 MB L2
+    DDF_CHECK(ddf_dev_alloc(c, &c->flush_buf, c->flush_bytes));
+  }
+  k_fill_u32<<<c->sm_count * 8, 256, 0, c->stream>>>((uint32_t*)c->flush_buf, c->flush_bytes / 4, 1u);
+  DDF_LAUNCH_CHECK(c);
+  return 0;
+  DDF_TRY_END
+}
+
+// ------------------------------------------------------------------ vectors
+extern "C" int ddf_vec_create(ddf_ctx* ctx, int64_t n, ddf_vec** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  if (n < 0) DDF_FAIL("negative vector length");
+  ddf_vec* v = new ddf_vec();
+  v->ctx = ctx;
+  v->n = n;
+  if (v->d.alloc(ctx, (size_t)n)) { delete v; return 1; }
+  if (n) DDF_CUDA(cudaMemsetAsync(v->d.p, 0, n * sizeof(double), ctx->stream));
+  *out = v;
+  return 0;
+  DDF_TRY_END
+}
+extern "C" int ddf_vec_destroy(ddf_vec* v) {
+  if (!v) return 0;
+  cudaStreamSynchronize(v->ctx->stream);
+  delete v;
+  return 0;
+}
+extern "C" int ddf_vec_length(ddf_vec* v, int64_t* out) { *out = v->n; return 0; }
+
+extern "C" int ddf_vec_upload(ddf_vec* v, const double* host) {
+  if (v->n == 0) return 0;
+  DDF_CUDA(cudaMemcpyAsync(v->d.p, host, v->n * sizeof(double), cudaMemcpyHostToDevice, v->ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(v->ctx->stream));   // host pointer is borrowed for the call only
+  return 0;
+}
+extern "C" int ddf_vec_download(ddf_vec* v, double* host) {
+  if (v->n == 0) return 0;
+  DDF_CUDA(cudaMemcpyAsync(host, v->d.p, v->n * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return 0;
+}
+
+__global__ void k_fill(double* __restrict__ p, int64_t n, double a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = a;
+}
+extern "C" int ddf_vec_fill(ddf_vec* v, double a) {
+  if (v->n == 0) return 0;
+  int grid;
+  DDF_CHECK(grid_for(v->n, 256, &grid));
+  k_fill<<<grid, 256, 0, v->ctx->stream>>>(v->d.p, v->n, a);
+  DDF_LAUNCH_CHECK(v->ctx);
+  return 0;
+}
+extern "C" int ddf_vec_copy(ddf_vec* dst, ddf_vec* src) {
+  if (dst->n != src->n) DDF_FAIL("vec_copy: length mismatch %lld vs %lld", (long long)dst->n, (long long)src->n);
+  if (dst->n == 0) return 0;
+  DDF_CUDA(cudaMemcpyAsync(dst->d.p, src->d.p, dst->n * sizeof(double), cudaMemcpyDeviceToDevice, dst->ctx->stream));
+  return 0;
+}
+
+// z = a x + b y, two doubles per thread (128-bit accesses)
+__global__ void k_axpby(double a, const double* __restrict__ x, double b, const double* __restrict__ y,
+                        double* __restrict__ z, int64_t n) {
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    double2 xv = *reinterpret_cast<const double2*>(x + i);
+    double2 r;
+    if (y) {
+      double2 yv = *reinterpret_cast<const double2*>(y + i);
+      // separate roundings like Julia's broadcast a*x + b*y (no contraction)
+      r.x = __dadd_rn(__dmul_rn(a, xv.x), __dmul_rn(b, yv.x));
+      r.y = __dadd_rn(__dmul_rn(a, xv.y), __dmul_rn(b, yv.y));
+    } else {
+      r.x = __dmul_rn(a, xv.x);
+      r.y = __dmul_rn(a, xv.y);
+    }
+    *reinterpret_cast<double2*>(z + i) = r;
+  } else if (i < n) {
+    z[i] = y ? __dadd_rn(__dmul_rn(a, x[i]), __dmul_rn(b, y[i])) : __dmul_rn(a, x[i]);
+  }
+}
+extern "C" int ddf_vec_axpby(double a, ddf_vec* x, double b, ddf_vec* y, ddf_vec* z) {
+  if (x->n != z->n || (y && y->n != z->n)) DDF_FAIL("vec_axpby: length mismatch");
+  if (z->n == 0) return 0;
+  int grid;
+  DDF_CHECK(grid_for(ceil_div64(z->n, 2), 256, &grid));
+  k_axpby<<<grid, 256, 0, z->ctx->stream>>>(a, x->d.p, b, y ? y->d.p : nullptr, z->d.p, z->n);
+  DDF_LAUNCH_CHECK(z->ctx);
+  return 0;
+}
+
+__global__ void k_mul(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ z, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) z[i] = x[i] * y[i];
+}
+extern "C" int ddf_vec_mul(ddf_vec* x, ddf_vec* y, ddf_vec* z) {
+  if (x->n != z->n || y->n != z->n) DDF_FAIL("vec_mul: length mismatch");
+  if (z->n == 0) return 0;
+  int grid;
+  DDF_CHECK(grid_for(z->n, 256, &grid));
+  k_mul<<<grid, 256, 0, z->ctx->stream>>>(x->d.p, y->d.p, z->d.p, z->n);
+  DDF_LAUNCH_CHECK(z->ctx);
+  return 0;
+}
+
+__global__ void k_div(const double* __restrict__ x, double a, double* __restrict__ z, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) z[i] = __ddiv_rn(x[i], a);
+}
+extern "C" int ddf_vec_div(ddf_vec* x, double a, ddf_vec* z) {
+  if (x->n != z->n) DDF_FAIL("vec_div: length mismatch");
+  if (z->n == 0) return 0;
+  int grid;
+  DDF_CHECK(grid_for(z->n, 256, &grid));
+  k_div<<<grid, 256, 0, z->ctx->stream>>>(x->d.p, a, z->d.p, z->n);
+  DDF_LAUNCH_CHECK(z->ctx);
+  return 0;
+}
+
+// counter-based uniform [0,1): splitmix64 of (seed, i) -> 53-bit mantissa
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void k_rand(double* __restrict__ p, int64_t n, uint64_t seed) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint64_t r = splitmix64(seed * 0xD1342543DE82EF95ull + (uint64_t)i);
+    p[i] = (double)(r >> 11) * (1.0 / 9007199254740992.0);
+  }
+}
+extern "C" int ddf_vec_rand(ddf_vec* v, uint64_t seed) {
+  if (v->n == 0) return 0;
+  int grid;
+  DDF_CHECK(grid_for(v->n, 256, &grid));
+  k_rand<<<grid, 256, 0, v->ctx->stream>>>(v->d.p, v->n, seed);
+  DDF_LAUNCH_CHECK(v->ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------ reductions
+// Two-stage deterministic reduction: fixed grid, each block reduces a contiguous
+// chunk in a fixed order, the (<= 1024) partials are combined on the host in
+// index order.  mode: 0 sum(x), 1 sum|x|, 2 sum x^2, 3 max|x|, 4 sum x*y, 5 min(x)
+template <int MODE>
+__global__ void k_reduce(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+                         double* __restrict__ partial) {
+  __shared__ double sm[32];
+  double acc = (MODE == 5) ? INFINITY : 0.0;
+  int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  int64_t lo = (int64_t)blockIdx.x * per;
+  int64_t hi = lo + per < n ? lo + per : n;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    double v = x[i];
+    if (MODE == 0) acc += v;
+    else if (MODE == 1) acc += fabs(v);
+    else if (MODE == 2) acc += v * v;
+    else if (MODE == 3) acc = fmax(acc, fabs(v));
+    else if (MODE == 4) acc += v * y[i];
+    else acc = fmin(acc, v);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    double o = __shfl_down_sync(0xffffffffu, acc, off);
+    if (MODE == 3) acc = fmax(acc, o);
+    else if (MODE == 5) acc = fmin(acc, o);
+    else acc += o;
+  }
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) sm[w] = acc;
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    acc = lane < nw ? sm[lane] : ((MODE == 5) ? INFINITY : 0.0);
+    for (int off = 16; off > 0; off >>= 1) {
+      double o = __shfl_down_sync(0xffffffffu, acc, off);
+      if (MODE == 3) acc = fmax(acc, o);
+      else if (MODE == 5) acc = fmin(acc, o);
+      else acc += o;
+    }
+    if (lane == 0) partial[blockIdx.x] = acc;
+  }
+}
+
+int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n, double* out) {
+  if (n == 0) { *out = (mode == 5) ? INFINITY : 0.0; return 0; }
+  int grid = (int)(ceil_div64(n, 4096) < 1024 ? ceil_div64(n, 4096) : 1024);
+  switch (mode) {
+    case 0: k_reduce<0><<<grid, 256, 0, c->stream>>>(x, y, n, c->red_dev); break;
+    case 1: k_reduce<1><<<grid, 256, 0, c->stream>>>(x, y, n, c->red_dev); break;
+    case 2: k_reduce<2><<<grid, 256, 0, c->stream>>>(x, y, n, c->red_dev); break;
+    case 3: k_reduce<3><<<grid, 256, 0, c->stream>>>(x, y, n, c->red_dev); break;
+    case 4: k_reduce<4><<<grid, 256, 0, c->stream>>>(x, y, n, c->red_dev); break;
+    default: k_reduce<5><<<grid, 256, 0, c->stream>>>(x, y, n, c->red_dev); break;
+  }
+  DDF_LAUNCH_CHECK(c);
+  DDF_CUDA(cudaMemcpyAsync(c->red_host, c->red_dev, grid * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  DDF_CUDA(cudaStreamSynchronize(c->stream));
+  double acc = (mode == 5) ? INFINITY : 0.0;
+  for (int i = 0; i < grid; i++) {
+    if (mode == 3) acc = acc > c->red_host[i] ? acc : c->red_host[i];
+    else if (mode == 5) acc = acc < c->red_host[i] ? acc : c->red_host[i];
+    else acc += c->red_host[i];
+  }
+  *out = acc;
+  return 0;
+}
+
+extern "C" int ddf_vec_norm(ddf_vec* v, int kind, double* out) {
+  double r = 0;
+  if (kind == DDF_NORM_INF) { DDF_CHECK(ddf_reduce(v->ctx, 3, v->d.p, nullptr, v->n, &r)); }
+  else if (kind == DDF_NORM_1) { DDF_CHECK(ddf_reduce(v->ctx, 1, v->d.p, nullptr, v->n, &r)); }
+  else if (kind == DDF_NORM_2) { DDF_CHECK(ddf_reduce(v->ctx, 2, v->d.p, nullptr, v->n, &r)); r = sqrt(r); }
+  else DDF_FAIL("vec_norm: unknown kind %d", kind);
+  *out = r;
+  return 0;
+}
+extern "C" int ddf_vec_dot(ddf_vec* x, ddf_vec* y, double* out) {
+  if (x->n != y->n) DDF_FAIL("vec_dot: length mismatch");
+  return ddf_reduce(x->ctx, 4, x->d.p, y->d.p, x->n, out);
+}
+extern "C" int ddf_vec_sum(ddf_vec* x, double* out) {
+  return ddf_reduce(x->ctx, 0, x->d.p, nullptr, x->n, out);
+}

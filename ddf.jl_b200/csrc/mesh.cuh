@@ -1,0 +1,65 @@
+// mesh.cuh -- device-resident manifold (src/Manifolds.jl:37-101 restated as flat
+// int32 tables).  Layout in HBM (all 0-based):
+//   simp[R]  : n_R x (R+1) int32, row-major, vertices ascending   (_simplices[R]; index-only, ZeroOrOne.jl:43-68)
+//   bnd[R]   : n_R x (R+1) int32, row-major, face ids ascending   (_boundaries[R] columns; the +-1 values are
+//              implicit: entry p (0-based) carries sign (-1)^(R+p), constant for every column)
+//              bnd[1] aliases simp[1] (the faces of an edge are its vertices)
+//   brow_ptr[R], bcol[R] : CSR of d_R by rows (face -> parents ascending), parent id | sign bit 31
+//   vol[R], dualvol[R], cc[R] : geometry (Float64)
+#pragma once
+#include "common.cuh"
+
+struct ddf_mesh {
+  ddf_ctx* ctx = nullptr;
+  int D = 0, C = 0;
+  int64_t n[DDF_MAXD + 1] = {0};         // nsimplices per rank R
+  bool assembled = false;
+  bool has_geometry = false;
+  bool weighted = true;
+
+  DevBuf<int32_t> simp[DDF_MAXD + 1];    // R >= 1 (R = 0 is the identity table)
+  DevBuf<int32_t> bnd[DDF_MAXD + 1];     // R >= 2 owns; R == 1 aliases simp[1]
+  DevBuf<uint32_t> brow_ptr[DDF_MAXD + 1];  // n_{R-1}+1 offsets into bcol[R]
+  DevBuf<uint32_t> bcol[DDF_MAXD + 1];      // (R+1) n_R entries: parent | (negative ? 1u<<31 : 0)
+
+  DevBuf<double> coords;                 // V x C row-major
+  DevBuf<double> weights;                // V
+  DevBuf<double> vol[DDF_MAXD + 1];
+  DevBuf<double> dualvol[DDF_MAXD + 1];
+  DevBuf<double> cc[DDF_MAXD + 1];       // dual coords n_R x C (R >= 1; R = 0 is coords)
+  DevBuf<uint8_t> isbnd[DDF_MAXD + 1];   // R < D
+  bool has_isbnd = false;
+  // diagonal operator payloads, built lazily by ops.cu
+  DevBuf<double> star[DDF_MAXD + 1];     // dualvol ./ vol   (hodge(Pr,R),   ManifoldOps.jl:67)
+  DevBuf<double> istar[DDF_MAXD + 1];    // vol ./ dualvol   (invhodge(Dl,R), ManifoldOps.jl:81)
+  DevBuf<double> isbnd_d[DDF_MAXD + 1];  // 0.0 / 1.0 mask   (isboundary,    ManifoldOps.jl:34)
+
+  // wave / Laplacian working set (built lazily by wave.cu): the assembled
+  // L = laplace(Pr,0) = delta_1 d_0 in row-CSR with the diagonal split off.
+  // Row i's neighbours are the other endpoints of its incident edges in edge-id
+  // order == ascending vertex order, so adj_ptr aliases brow_ptr[1].
+  bool has_wave = false;
+  DevBuf<int32_t> adj_nbr;               // 2E  neighbour vertex j
+  DevBuf<double> adj_l;                  // 2E  L[i,j] = fl(ih0[i] * star1[e])   (chopped -> 0)
+  DevBuf<double> ldiag;                  // V   L[i,i] = sequential sum over incident edges of -L[i,j]
+  DevBuf<double> utmp;                   // V   ping-pong buffer of the fused step
+
+  // slab halo of the distributed wave step (comm.cu): vertex planes along the
+  // slowest axis; the first halo_lo / last halo_hi planes are ghosts owned by rank-1 / rank+1
+  int64_t halo_plane = 0, halo_lo = 0, halo_hi = 0;
+
+  // hypercube generator parameters (slab meshes of the distributed wave step)
+  bool is_hypercube = false;
+  int64_t nelts[DDF_MAXD] = {0};
+  int64_t hdiv = 0, z0 = 0;
+
+  const int32_t* bnd_table(int R) const { return R == 1 ? simp[1].p : bnd[R].p; }
+};
+
+// implemented in mesh.cu
+int ddf_mesh_require_assembled(ddf_mesh* m);
+// implemented in geometry.cu
+int ddf_mesh_require_geometry(ddf_mesh* m);
+int ddf_mesh_require_isboundary(ddf_mesh* m);
+// implemented in wave.cu
+int ddf_mesh_require_wave(ddf_mesh* m);

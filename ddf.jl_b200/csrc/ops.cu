@@ -1,0 +1,1166 @@
+// ops.cu -- DEC operators (src/ManifoldOps.jl), the Op ring (src/Ops.jl) and
+// Op*Fun (src/Ops.jl:273-276 -> SparseArrays `mul!`), as device kernels.
+//
+// Kernels (all HBM-bound, Float64, integer +-1 coefficients never stored):
+//   K2 k_apply_fixed<W>   y = d_k x for the primal derivative d_k = adjoint(d_{k+1}
+//        boundary) (ManifoldOps.jl:46).  The reference holds Adjoint{Int8,CSC}; the
+//        parent CSC's columns are the rows of d_k, all of width W = k+2 with the
+//        constant sign pattern (-1)^(k+1+p).  One thread owns 4 consecutive rows:
+//        W 128-bit streaming index loads, 4W independent gathers in flight, the
+//        sum per row in the reference's order (tmp = 0; tmp += v_j x[c_j], j ascending),
+//        two 128-bit streaming stores.  Bit-exact with the oracle.
+//   K3 k_apply_csrsign    y = d_R x for boundary / dual derivative (plain CSC in the
+//        reference: zero y, scatter by ascending column == per-row sequential sum over
+//        ascending parents).  Row-CSR with the sign in bit 31 of the column index.
+//   K4 diagonal Hodge stars fused as prologue (x[c]*pre[c]) / epilogue (post[r]*sum)
+//        of K2/K3, or k_apply_diag when they stand alone.
+//   k_apply_csrf64        arbitrary assembled Float64 operators (ddf_op_from_csc),
+//        separately rounded multiply and add in ascending-column order (bit-exact
+//        with SparseArrays' CSC `mul!`).
+#include <cub/cub.cuh>
+
+#include <memory>
+
+#include "mesh.cuh"
+
+int ddf_laplace0_apply(ddf_mesh* m, const double* x, double* y);   // wave.cu
+
+enum OpKind { OPK_ZERO = 0, OPK_FIXED, OPK_CSRSIGN, OPK_DIAG, OPK_CSRF64, OPK_LAPLACE0, OPK_CHAIN, OPK_SUM };
+
+struct OpNode;
+typedef std::shared_ptr<OpNode> OpRef;
+
+struct OpNode {
+  OpKind kind = OPK_ZERO;
+  ddf_ctx* ctx = nullptr;
+  ddf_mesh* mesh = nullptr;       // borrowed (FIXED / CSRSIGN / LAPLACE0 / mesh diagonals)
+  int64_t nrows = 0, ncols = 0;
+  // FIXED / CSRSIGN: boundary level R (tables live in the mesh)
+  int R = 0;
+  // DIAG: y = sign * diag .* x ; diag == nullptr means the identity scaled by `scale`
+  const double* diag = nullptr;
+  DevBuf<double> diag_own;
+  double scale = 1.0;             // DIAG identity scale / CHAIN scalar
+  // CSRF64
+  DevBuf<uint32_t> rowptr;
+  DevBuf<int32_t> col;
+  DevBuf<double> val;
+  int64_t nnz = 0;
+  // CHAIN (factors left to right) / SUM (coef, term)
+  std::vector<OpRef> factors;
+  std::vector<double> coefs;
+  // scratch vectors reused across applies
+  std::vector<std::unique_ptr<DevBuf<double>>> temps;
+};
+
+struct ddf_op {
+  OpRef node;
+};
+
+// shallow clone of a leaf node (payload pointers are borrowed; the source is kept
+// alive through `factors`)
+static OpRef clone_leaf(const OpRef& src) {
+  OpRef o = std::make_shared<OpNode>();
+  o->kind = src->kind; o->ctx = src->ctx; o->mesh = src->mesh;
+  o->nrows = src->nrows; o->ncols = src->ncols; o->R = src->R;
+  o->diag = src->diag; o->scale = src->scale;
+  o->factors.push_back(src);
+  return o;
+}
+
+static ddf_op* wrap(OpRef n) {
+  ddf_op* o = new ddf_op();
+  o->node = n;
+  return o;
+}
+
+// ======================================================================= kernels
+template <int W, bool PRE, bool POST>
+__global__ void __launch_bounds__(256)
+k_apply_fixed(const int32_t* __restrict__ tab, int64_t nrows, int first_negative, const double* __restrict__ x,
+              const double* __restrict__ pre, const double* __restrict__ post, double alpha,
+              double* __restrict__ y) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r0 = t * 4;
+  if (r0 >= nrows) return;
+  if (r0 + 3 < nrows) {
+    int idx[4 * W];
+    const int4* tp = reinterpret_cast<const int4*>(tab) + t * W;
+#pragma unroll
+    for (int q = 0; q < W; q++) {
+      int4 v = ld_stream_int4(tp + q);
+      idx[4 * q + 0] = v.x; idx[4 * q + 1] = v.y; idx[4 * q + 2] = v.z; idx[4 * q + 3] = v.w;
+    }
+    double xv[4 * W];
+#pragma unroll
+    for (int q = 0; q < 4 * W; q++) xv[q] = __ldg(x + idx[q]);
+    if (PRE) {
+#pragma unroll
+      for (int q = 0; q < 4 * W; q++) xv[q] = __dmul_rn(__ldg(pre + idx[q]), xv[q]);
+    }
+    double acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      double a = 0.0;                                   // tmp = zero(eltype(C))
+#pragma unroll
+      for (int p = 0; p < W; p++) {
+        const bool neg = ((p & 1) != 0) != (first_negative != 0);
+        a = neg ? __dsub_rn(a, xv[r * W + p]) : __dadd_rn(a, xv[r * W + p]);
+      }
+      acc[r] = a;
+    }
+    if (POST) {
+      const double2 p0 = ld_stream_f64x2(reinterpret_cast<const double2*>(post + r0));
+      const double2 p1 = ld_stream_f64x2(reinterpret_cast<const double2*>(post + r0 + 2));
+      acc[0] = __dmul_rn(p0.x, acc[0]); acc[1] = __dmul_rn(p0.y, acc[1]);
+      acc[2] = __dmul_rn(p1.x, acc[2]); acc[3] = __dmul_rn(p1.y, acc[3]);
+    }
+    if (alpha != 1.0) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) acc[r] = __dmul_rn(alpha, acc[r]);
+    }
+    st_stream_f64x2(reinterpret_cast<double2*>(y + r0), acc[0], acc[1]);
+    st_stream_f64x2(reinterpret_cast<double2*>(y + r0 + 2), acc[2], acc[3]);
+  } else {
+    for (int64_t r = r0; r < nrows; r++) {
+      double a = 0.0;
+#pragma unroll
+      for (int p = 0; p < W; p++) {
+        const int c = tab[r * W + p];
+        double v = x[c];
+        if (PRE) v = __dmul_rn(pre[c], v);
+        const bool neg = ((p & 1) != 0) != (first_negative != 0);
+        a = neg ? __dsub_rn(a, v) : __dadd_rn(a, v);
+      }
+      if (POST) a = __dmul_rn(post[r], a);
+      if (alpha != 1.0) a = __dmul_rn(alpha, a);
+      y[r] = a;
+    }
+  }
+}
+
+// Row-CSR with sign bit; one thread per row, sequential ascending-parent sum.
+template <bool PRE, bool POST>
+__global__ void __launch_bounds__(256)
+k_apply_csrsign(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, int64_t nrows,
+                const double* __restrict__ x, const double* __restrict__ pre, const double* __restrict__ post,
+                double alpha, double* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const uint32_t lo = rowptr[i], hi = rowptr[i + 1];
+  double a = 0.0;
+  for (uint32_t p = lo; p < hi; p++) {
+    const uint32_t cw = __ldg(col + p);
+    const uint32_t c = cw & 0x7fffffffu;
+    double v = __ldg(x + c);
+    if (PRE) v = __dmul_rn(__ldg(pre + c), v);
+    a = (cw >> 31) ? __dsub_rn(a, v) : __dadd_rn(a, v);
+  }
+  if (POST) a = __dmul_rn(post[i], a);
+  if (alpha != 1.0) a = __dmul_rn(alpha, a);
+  y[i] = a;
+}
+
+__global__ void k_apply_diag(const double* __restrict__ d, double sign_or_scale, const double* __restrict__ x,
+                             double* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = d ? __dmul_rn(d[i], x[i]) : x[i];
+  if (sign_or_scale != 1.0) v = __dmul_rn(sign_or_scale, v);
+  y[i] = v;
+}
+
+__global__ void k_apply_csrf64(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                               const double* __restrict__ val, int64_t nrows, const double* __restrict__ x,
+                               double alpha, double* __restrict__ y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const uint32_t lo = rowptr[i], hi = rowptr[i + 1];
+  double a = 0.0;
+  for (uint32_t p = lo; p < hi; p++) a = __dadd_rn(a, __dmul_rn(__ldg(val + p), __ldg(x + __ldg(col + p))));
+  if (alpha != 1.0) a = __dmul_rn(alpha, a);
+  y[i] = a;
+}
+
+// ================================================================ kernel launchers
+static int launch_fixed(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, int first_negative, const double* x,
+                        const double* pre, const double* post, double alpha, double* y) {
+  if (nrows == 0) return 0;
+  int grid;
+  DDF_CHECK(grid_for(ceil_div64(nrows, 4), 256, &grid));
+#define DDF_FIXED_CASE(WW)                                                                                          \
+  case WW:                                                                                                          \
+    if (pre && post) k_apply_fixed<WW, true, true><<<grid, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, pre, post, alpha, y); \
+    else if (pre) k_apply_fixed<WW, true, false><<<grid, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, pre, post, alpha, y);   \
+    else if (post) k_apply_fixed<WW, false, true><<<grid, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, pre, post, alpha, y);  \
+    else k_apply_fixed<WW, false, false><<<grid, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, pre, post, alpha, y);           \
+    break;
+  switch (W) {
+    DDF_FIXED_CASE(2)
+    DDF_FIXED_CASE(3)
+    DDF_FIXED_CASE(4)
+    DDF_FIXED_CASE(5)
+    DDF_FIXED_CASE(6)
+    default: DDF_FAIL("apply: unsupported fixed width %d", W);
+  }
+#undef DDF_FIXED_CASE
+  DDF_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+static int launch_csrsign(ddf_ctx* ctx, const uint32_t* rowptr, const uint32_t* col, int64_t nrows, const double* x,
+                          const double* pre, const double* post, double alpha, double* y) {
+  if (nrows == 0) return 0;
+  int grid;
+  DDF_CHECK(grid_for(nrows, 256, &grid));
+  if (pre && post) k_apply_csrsign<true, true><<<grid, 256, 0, ctx->stream>>>(rowptr, col, nrows, x, pre, post, alpha, y);
+  else if (pre) k_apply_csrsign<true, false><<<grid, 256, 0, ctx->stream>>>(rowptr, col, nrows, x, pre, post, alpha, y);
+  else if (post) k_apply_csrsign<false, true><<<grid, 256, 0, ctx->stream>>>(rowptr, col, nrows, x, pre, post, alpha, y);
+  else k_apply_csrsign<false, false><<<grid, 256, 0, ctx->stream>>>(rowptr, col, nrows, x, pre, post, alpha, y);
+  DDF_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+static int launch_diag(ddf_ctx* ctx, const double* d, double s, const double* x, double* y, int64_t n) {
+  if (n == 0) return 0;
+  int grid;
+  DDF_CHECK(grid_for(n, 256, &grid));
+  k_apply_diag<<<grid, 256, 0, ctx->stream>>>(d, s, x, y, n);
+  DDF_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// ======================================================== mesh diagonal payloads
+__global__ void k_ratio(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __ddiv_rn(a[i], b[i]);
+}
+__global__ void k_mask_to_double(const uint8_t* __restrict__ m, double* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = m[i] ? 1.0 : 0.0;
+}
+
+int ddf_mesh_require_star(ddf_mesh* m, int R) {
+  DDF_CHECK(ddf_mesh_require_geometry(m));
+  if (m->star[R].p || m->n[R] == 0) return 0;
+  DDF_CHECK(m->star[R].alloc(m->ctx, m->n[R]));
+  DDF_CHECK(m->istar[R].alloc(m->ctx, m->n[R]));
+  int grid;
+  DDF_CHECK(grid_for(m->n[R], 256, &grid));
+  k_ratio<<<grid, 256, 0, m->ctx->stream>>>(m->dualvol[R].p, m->vol[R].p, m->star[R].p, m->n[R]);    // dualvol ./ vol
+  DDF_LAUNCH_CHECK(m->ctx);
+  k_ratio<<<grid, 256, 0, m->ctx->stream>>>(m->vol[R].p, m->dualvol[R].p, m->istar[R].p, m->n[R]);   // vol ./ dualvol
+  DDF_LAUNCH_CHECK(m->ctx);
+  return 0;
+}
+
+static int bitsign(int b) { return (b & 1) ? -1 : 1; }
+
+// ============================================================== op constructors
+static OpRef make_node(ddf_mesh* m, OpKind k, int64_t nr, int64_t nc) {
+  OpRef n = std::make_shared<OpNode>();
+  n->kind = k;
+  n->ctx = m->ctx;
+  n->mesh = m;
+  n->nrows = nr;
+  n->ncols = nc;
+  return n;
+}
+
+// the matrix d_R (n_{R-1} x n_R) as an operator: row-CSR with sign bits
+static OpRef node_boundary_matrix(ddf_mesh* m, int R) {
+  OpRef n = make_node(m, OPK_CSRSIGN, m->n[R - 1], m->n[R]);
+  n->R = R;
+  return n;
+}
+// its transpose (n_R x n_{R-1}): fixed-width rows
+static OpRef node_boundary_transpose(ddf_mesh* m, int R) {
+  OpRef n = make_node(m, OPK_FIXED, m->n[R], m->n[R - 1]);
+  n->R = R;
+  return n;
+}
+
+extern "C" int ddf_op_boundary(ddf_mesh* m, int P, int R, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  DDF_CHECK(ddf_mesh_require_assembled(m));
+  if (P == DDF_PR) {
+    if (!(0 < R && R <= m->D)) DDF_FAIL("boundary(Pr,R): need 0 < R <= D (ManifoldOps.jl:18)");
+    *out = wrap(node_boundary_matrix(m, R));
+  } else {
+    if (!(0 <= R && R < m->D)) DDF_FAIL("boundary(Dl,R): need 0 <= R < D (ManifoldOps.jl:23)");
+    *out = wrap(node_boundary_transpose(m, R + 1));
+  }
+  return 0;
+  DDF_TRY_END
+}
+
+extern "C" int ddf_op_deriv(ddf_mesh* m, int P, int R, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  DDF_CHECK(ddf_mesh_require_assembled(m));
+  const int s = P == DDF_PR ? 1 : -1;
+  if (!(0 <= R && R <= m->D) || !(0 <= R + s && R + s <= m->D))
+    DDF_FAIL("deriv(P,R): need 0 <= R <= D and 0 <= R+s <= D (ManifoldOps.jl:43-44)");
+  // adjoint(boundary(P, R+s)): Pr -> transpose of d_{R+1}; Dl -> adjoint(transpose d_R) = d_R
+  if (P == DDF_PR) *out = wrap(node_boundary_transpose(m, R + 1));
+  else *out = wrap(node_boundary_matrix(m, R));
+  return 0;
+  DDF_TRY_END
+}
+
+static int node_hodge(ddf_mesh* m, int P, int R, bool inverse, OpRef* out) {
+  if (!(0 <= R && R <= m->D)) DDF_FAIL("hodge/invhodge: need 0 <= R <= D");
+  DDF_CHECK(ddf_mesh_require_star(m, R));
+  OpRef n = make_node(m, OPK_DIAG, m->n[R], m->n[R]);
+  // hodge(Pr) = dualvol./vol ; invhodge(Dl) = vol./dualvol ;
+  // hodge(Dl) = s*invhodge(Dl) ; invhodge(Pr) = s*hodge(Pr), s = (-1)^(R(D-R))  (ManifoldOps.jl:58-100)
+  const int s = bitsign(R * (m->D - R));
+  if (!inverse) {
+    if (P == DDF_PR) { n->diag = m->star[R].p; n->scale = 1.0; }
+    else { n->diag = m->istar[R].p; n->scale = s; }
+  } else {
+    if (P == DDF_DL) { n->diag = m->istar[R].p; n->scale = 1.0; }
+    else { n->diag = m->star[R].p; n->scale = s; }
+  }
+  *out = n;
+  return 0;
+}
+
+extern "C" int ddf_op_hodge(ddf_mesh* m, int P, int R, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  OpRef n;
+  DDF_CHECK(node_hodge(m, P, R, false, &n));
+  *out = wrap(n);
+  return 0;
+  DDF_TRY_END
+}
+extern "C" int ddf_op_invhodge(ddf_mesh* m, int P, int R, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  OpRef n;
+  DDF_CHECK(node_hodge(m, P, R, true, &n));
+  *out = wrap(n);
+  return 0;
+  DDF_TRY_END
+}
+
+static OpRef chain_of(std::vector<OpRef> f, double scalar) {
+  OpRef n = std::make_shared<OpNode>();
+  n->kind = OPK_CHAIN;
+  n->ctx = f[0]->ctx;
+  n->mesh = f[0]->mesh;
+  n->nrows = f.front()->nrows;
+  n->ncols = f.back()->ncols;
+  n->scale = scalar;
+  // flatten nested chains
+  for (auto& g : f) {
+    if (g->kind == OPK_CHAIN) {
+      n->scale *= g->scale;
+      for (auto& h : g->factors) n->factors.push_back(h);
+    } else {
+      n->factors.push_back(g);
+    }
+  }
+  return n;
+}
+
+static int node_coderiv(ddf_mesh* m, int P, int R, OpRef* out) {
+  const int dR = P == DDF_PR ? 1 : -1;
+  if (!(0 <= R && R <= m->D) || !(0 <= R - dR && R - dR <= m->D))
+    DDF_FAIL("coderiv(P,R): need 0 <= R <= D and 0 <= R-dR <= D (ManifoldOps.jl:114-115)");
+  DDF_CHECK(ddf_mesh_require_assembled(m));
+  // bitsign(R) * invhodge(!P, R-dR) * deriv(!P, R) * hodge(P, R)   (ManifoldOps.jl:117-120)
+  OpRef ih, d, h;
+  DDF_CHECK(node_hodge(m, P == DDF_PR ? DDF_DL : DDF_PR, R - dR, true, &ih));
+  DDF_CHECK(node_hodge(m, P, R, false, &h));
+  if (P == DDF_PR) d = node_boundary_matrix(m, R);          // deriv(Dl,R) = d_R   (n_{R-1} x n_R)
+  else d = node_boundary_transpose(m, R + 1);                // deriv(Pr,R) = d_{R+1}^T
+  OpRef ihs = clone_leaf(ih);                                // fold bitsign(R) into the left diagonal (exact)
+  ihs->factors.clear();
+  ihs->scale = ih->scale * bitsign(R);
+  *out = chain_of({ihs, d, h}, 1.0);
+  return 0;
+}
+
+extern "C" int ddf_op_coderiv(ddf_mesh* m, int P, int R, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  OpRef n;
+  DDF_CHECK(node_coderiv(m, P, R, &n));
+  *out = wrap(n);
+  return 0;
+  DDF_TRY_END
+}
+
+extern "C" int ddf_op_laplace(ddf_mesh* m, int P, int R, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  if (!(0 <= R && R <= m->D)) DDF_FAIL("laplace(P,R): need 0 <= R <= D");
+  DDF_CHECK(ddf_mesh_require_assembled(m));
+  const int dR = P == DDF_PR ? 1 : -1;
+  if (P == DDF_PR && R == 0 && m->D >= 1) {
+    // delta_1 d_0 = -star0^-1 d0^T star1 d0 : fused vertex-adjacency kernel (wave.cu)
+    DDF_CHECK(ddf_mesh_require_wave(m));
+    *out = wrap(make_node(m, OPK_LAPLACE0, m->n[0], m->n[0]));
+    return 0;
+  }
+  OpRef sum = std::make_shared<OpNode>();
+  sum->kind = OPK_SUM;
+  sum->ctx = m->ctx;
+  sum->mesh = m;
+  sum->nrows = sum->ncols = m->n[R];
+  if (0 <= R - dR && R - dR <= m->D) {          // deriv(P, R-dR) * coderiv(P, R)
+    OpRef cd;
+    DDF_CHECK(node_coderiv(m, P, R, &cd));
+    OpRef d = P == DDF_PR ? node_boundary_transpose(m, R) /* d_{R-1} = d_R^T table */
+                          : node_boundary_matrix(m, R + 1) /* deriv(Dl,R+1) = d_{R+1} */;
+    sum->factors.push_back(chain_of({d, cd}, 1.0));
+    sum->coefs.push_back(1.0);
+  }
+  if (0 <= R + dR && R + dR <= m->D) {          // coderiv(P, R+dR) * deriv(P, R)
+    OpRef cd;
+    DDF_CHECK(node_coderiv(m, P, R + dR, &cd));
+    OpRef d = P == DDF_PR ? node_boundary_transpose(m, R + 1) : node_boundary_matrix(m, R);
+    sum->factors.push_back(chain_of({cd, d}, 1.0));
+    sum->coefs.push_back(1.0);
+  }
+  if (sum->factors.empty()) { sum->kind = OPK_ZERO; }
+  *out = wrap(sum);
+  return 0;
+  DDF_TRY_END
+}
+
+extern "C" int ddf_op_isboundary(ddf_mesh* m, int P, int R, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  if (P != DDF_PR) DDF_FAIL("isboundary: only defined for Pr (ManifoldOps.jl:31)");
+  if (!(0 <= R && R < m->D)) DDF_FAIL("isboundary(Pr,R): need 0 <= R < D (ManifoldOps.jl:32)");
+  DDF_CHECK(ddf_mesh_require_isboundary(m));
+  if (!m->isbnd_d[R].p && m->n[R]) {
+    DDF_CHECK(m->isbnd_d[R].alloc(m->ctx, m->n[R]));
+    int grid;
+    DDF_CHECK(grid_for(m->n[R], 256, &grid));
+    k_mask_to_double<<<grid, 256, 0, m->ctx->stream>>>(m->isbnd[R].p, m->isbnd_d[R].p, m->n[R]);
+    DDF_LAUNCH_CHECK(m->ctx);
+  }
+  OpRef n = make_node(m, OPK_DIAG, m->n[R], m->n[R]);
+  n->diag = m->isbnd_d[R].p;
+  *out = wrap(n);
+  return 0;
+  DDF_TRY_END
+}
+
+extern "C" int ddf_op_identity(ddf_mesh* m, int R, double a, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  if (!(0 <= R && R <= m->D)) DDF_FAIL("identity: R out of range");
+  if (R != 0 && R != m->D) DDF_CHECK(ddf_mesh_require_assembled(m));
+  OpRef n = make_node(m, OPK_DIAG, m->n[R], m->n[R]);
+  n->diag = nullptr;
+  n->scale = a;
+  *out = wrap(n);
+  return 0;
+  DDF_TRY_END
+}
+
+extern "C" int ddf_op_zero(ddf_mesh* m, int R1, int R2, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  if (!(0 <= R1 && R1 <= m->D && 0 <= R2 && R2 <= m->D)) DDF_FAIL("zero: R out of range");
+  DDF_CHECK(ddf_mesh_require_assembled(m));
+  *out = wrap(make_node(m, OPK_ZERO, m->n[R1], m->n[R2]));
+  return 0;
+  DDF_TRY_END
+}
+
+extern "C" int ddf_op_from_diag(ddf_ctx* ctx, int64_t n, const double* diag, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  OpRef o = std::make_shared<OpNode>();
+  o->kind = OPK_DIAG;
+  o->ctx = ctx;
+  o->nrows = o->ncols = n;
+  DDF_CHECK(o->diag_own.alloc(ctx, n));
+  if (n) {
+    DDF_CUDA(cudaMemcpyAsync(o->diag_own.p, diag, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  o->diag = o->diag_own.p;
+  *out = wrap(o);
+  return 0;
+  DDF_TRY_END
+}
+
+// ---------------------------------------------------- CSC (reference storage) -> CSR
+__global__ void k_expand_cols(const int64_t* __restrict__ colptr, int64_t ncols, int32_t* __restrict__ colidx) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncols) return;
+  for (int64_t p = colptr[j] - 1; p < colptr[j + 1] - 1; p++) colidx[p] = (int32_t)j;
+}
+__global__ void k_rows_to_keys(const int64_t* __restrict__ rowval, int64_t nnz, uint32_t* __restrict__ keys,
+                               uint32_t* __restrict__ idx) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nnz) { keys[p] = (uint32_t)(rowval[p] - 1); idx[p] = (uint32_t)p; }
+}
+__global__ void k_gather_csr(const uint32_t* __restrict__ idx, const int32_t* __restrict__ colidx,
+                             const double* __restrict__ nzval, int64_t nnz, int32_t* __restrict__ col,
+                             double* __restrict__ val) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nnz) { col[p] = colidx[idx[p]]; val[p] = nzval[idx[p]]; }
+}
+// rowptr[r] = first position whose key >= r (keys sorted)
+__global__ void k_lower_bound(const uint32_t* __restrict__ keys, int64_t nnz, int64_t nrows, uint32_t* __restrict__ rowptr) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > nrows) return;
+  int64_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < (uint32_t)r) lo = mid + 1; else hi = mid;
+  }
+  rowptr[r] = (uint32_t)lo;
+}
+
+extern "C" int ddf_op_from_csc(ddf_ctx* ctx, int64_t nrows, int64_t ncols, const int64_t* colptr,
+                               const int64_t* rowval, const double* nzval, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  if (nrows >= 0x7fffffffLL || ncols >= 0x7fffffffLL) DDF_FAIL("from_csc: dimension >= 2^31");
+  const int64_t nnz = colptr[ncols] - 1;
+  if (nnz < 0 || nnz >= 0xffffffffLL) DDF_FAIL("from_csc: nnz %lld unsupported", (long long)nnz);
+  DDF_CUDA(cudaSetDevice(ctx->device));
+  OpRef o = std::make_shared<OpNode>();
+  o->kind = OPK_CSRF64;
+  o->ctx = ctx;
+  o->nrows = nrows;
+  o->ncols = ncols;
+  o->nnz = nnz;
+  DDF_CHECK(o->rowptr.alloc(ctx, nrows + 1));
+  DDF_CHECK(o->col.alloc(ctx, nnz));
+  DDF_CHECK(o->val.alloc(ctx, nnz));
+  if (nnz == 0) {
+    DDF_CUDA(cudaMemsetAsync(o->rowptr.p, 0, (nrows + 1) * 4, ctx->stream));
+    *out = wrap(o);
+    return 0;
+  }
+  DevBuf<int64_t> dcolptr, drowval;
+  DevBuf<double> dval;
+  DevBuf<int32_t> colidx;
+  DevBuf<uint32_t> k0, k1, i0, i1;
+  DevBuf<uint8_t> temp;
+  DDF_CHECK(dcolptr.alloc(ctx, ncols + 1));
+  DDF_CHECK(drowval.alloc(ctx, nnz));
+  DDF_CHECK(dval.alloc(ctx, nnz));
+  DDF_CHECK(colidx.alloc(ctx, nnz));
+  DDF_CHECK(k0.alloc(ctx, nnz)); DDF_CHECK(k1.alloc(ctx, nnz));
+  DDF_CHECK(i0.alloc(ctx, nnz)); DDF_CHECK(i1.alloc(ctx, nnz));
+  DDF_CUDA(cudaMemcpyAsync(dcolptr.p, colptr, (ncols + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  DDF_CUDA(cudaMemcpyAsync(drowval.p, rowval, nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+  DDF_CUDA(cudaMemcpyAsync(dval.p, nzval, nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int grid;
+  DDF_CHECK(grid_for(ncols, 256, &grid));
+  k_expand_cols<<<grid, 256, 0, ctx->stream>>>(dcolptr.p, ncols, colidx.p);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CHECK(grid_for(nnz, 256, &grid));
+  k_rows_to_keys<<<grid, 256, 0, ctx->stream>>>(drowval.p, nnz, k0.p, i0.p);
+  DDF_LAUNCH_CHECK(ctx);
+  int bits = 1;
+  while (((int64_t)1 << bits) < nrows) bits++;
+  cub::DoubleBuffer<uint32_t> dk(k0.p, k1.p), di(i0.p, i1.p);
+  size_t tb = 0;
+  DDF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, di, nnz, 0, bits, ctx->stream));
+  DDF_CHECK(temp.alloc(ctx, tb));
+  DDF_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, tb, dk, di, nnz, 0, bits, ctx->stream));   // stable: columns stay ascending
+  ctx->launches += (bits + 7) / 8 + 1;
+  k_gather_csr<<<grid, 256, 0, ctx->stream>>>(di.Current(), colidx.p, dval.p, nnz, o->col.p, o->val.p);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CHECK(grid_for(nrows + 1, 256, &grid));
+  k_lower_bound<<<grid, 256, 0, ctx->stream>>>(dk.Current(), nnz, nrows, o->rowptr.p);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = wrap(o);
+  return 0;
+  DDF_TRY_END
+}
+
+extern "C" int ddf_op_destroy(ddf_op* op) {
+  if (!op) return 0;
+  if (op->node && op->node->ctx) cudaStreamSynchronize(op->node->ctx->stream);
+  delete op;
+  return 0;
+}
+extern "C" int ddf_op_shape(ddf_op* op, int64_t* nrows, int64_t* ncols) {
+  *nrows = op->node->nrows;
+  *ncols = op->node->ncols;
+  return 0;
+}
+
+// ==================================================================== Op algebra
+extern "C" int ddf_op_compose(ddf_op* A, ddf_op* B, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  if (A->node->ncols != B->node->nrows)
+    DDF_FAIL("compose: inner dimensions differ (%lld vs %lld)", (long long)A->node->ncols, (long long)B->node->nrows);
+  if (A->node->kind == OPK_ZERO || B->node->kind == OPK_ZERO) {
+    OpRef z = std::make_shared<OpNode>();
+    z->kind = OPK_ZERO; z->ctx = A->node->ctx; z->mesh = A->node->mesh;
+    z->nrows = A->node->nrows; z->ncols = B->node->ncols;
+    *out = wrap(z);
+    return 0;
+  }
+  *out = wrap(chain_of({A->node, B->node}, 1.0));
+  return 0;
+  DDF_TRY_END
+}
+
+__global__ void k_diag_combine(const double* __restrict__ a, double sa, const double* __restrict__ b, double sb,
+                               double coef, double* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // Diagonal(a) + coef*Diagonal(b); identity payloads have null pointers
+  double va = a ? __dmul_rn(sa, a[i]) : sa;
+  double vb = b ? __dmul_rn(sb, b[i]) : sb;
+  out[i] = __dadd_rn(va, __dmul_rn(coef, vb));
+}
+
+extern "C" int ddf_op_add(ddf_op* A, double b, ddf_op* B, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  OpRef a = A->node, bb = B->node;
+  if (a->nrows != bb->nrows || a->ncols != bb->ncols) DDF_FAIL("add: shapes differ");
+  if (a->kind == OPK_DIAG && bb->kind == OPK_DIAG) {     // Diagonal +- Diagonal stays diagonal (exact same arithmetic)
+    OpRef o = std::make_shared<OpNode>();
+    o->kind = OPK_DIAG; o->ctx = a->ctx; o->mesh = a->mesh; o->nrows = a->nrows; o->ncols = a->ncols;
+    DDF_CHECK(o->diag_own.alloc(a->ctx, a->nrows));
+    if (a->nrows) {
+      int grid;
+      DDF_CHECK(grid_for(a->nrows, 256, &grid));
+      k_diag_combine<<<grid, 256, 0, a->ctx->stream>>>(a->diag, a->scale, bb->diag, bb->scale, b, o->diag_own.p, a->nrows);
+      DDF_LAUNCH_CHECK(a->ctx);
+    }
+    o->diag = o->diag_own.p;
+    o->scale = 1.0;
+    // keep payload owners alive
+    o->factors.push_back(a);
+    o->factors.push_back(bb);
+    *out = wrap(o);
+    return 0;
+  }
+  OpRef s = std::make_shared<OpNode>();
+  s->kind = OPK_SUM; s->ctx = a->ctx; s->mesh = a->mesh; s->nrows = a->nrows; s->ncols = a->ncols;
+  auto push = [&](OpRef t, double c) {
+    if (t->kind == OPK_ZERO) return;
+    if (t->kind == OPK_SUM) {
+      for (size_t i = 0; i < t->factors.size(); i++) { s->factors.push_back(t->factors[i]); s->coefs.push_back(c * t->coefs[i]); }
+    } else { s->factors.push_back(t); s->coefs.push_back(c); }
+  };
+  push(a, 1.0);
+  push(bb, b);
+  if (s->factors.empty()) s->kind = OPK_ZERO;
+  *out = wrap(s);
+  return 0;
+  DDF_TRY_END
+}
+
+extern "C" int ddf_op_scale(double a, ddf_op* A, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  OpRef n = A->node;
+  if (n->kind == OPK_ZERO) { *out = wrap(n); return 0; }
+  if (n->kind == OPK_DIAG && (n->diag == nullptr || a == 1.0 || a == -1.0)) {
+    OpRef o = clone_leaf(n);          // keeps an owned payload alive
+    o->scale = n->scale * a;          // exact for +-1 and for the scaled identity
+    *out = wrap(o);
+    return 0;
+  }
+  if (n->kind == OPK_DIAG) {          // a * Diagonal(d) = Diagonal(a*d), one rounding per entry like the reference
+    OpRef o = std::make_shared<OpNode>();
+    o->kind = OPK_DIAG; o->ctx = n->ctx; o->mesh = n->mesh; o->nrows = n->nrows; o->ncols = n->ncols;
+    DDF_CHECK(o->diag_own.alloc(n->ctx, n->nrows));
+    if (n->nrows) {
+      int grid;
+      DDF_CHECK(grid_for(n->nrows, 256, &grid));
+      k_diag_combine<<<grid, 256, 0, n->ctx->stream>>>(nullptr, 0.0, n->diag, n->scale, a, o->diag_own.p, n->nrows);
+      DDF_LAUNCH_CHECK(n->ctx);
+    }
+    o->diag = o->diag_own.p;
+    o->factors.push_back(n);
+    *out = wrap(o);
+    return 0;
+  }
+  *out = wrap(chain_of({n}, a));
+  return 0;
+  DDF_TRY_END
+}
+
+static int transpose_csrf64(OpRef src, OpRef* out);
+
+static int adjoint_node(OpRef n, OpRef* out) {
+  switch (n->kind) {
+    case OPK_ZERO: {
+      OpRef o = clone_leaf(n);
+      o->factors.clear();
+      std::swap(o->nrows, o->ncols);
+      *out = o;
+      return 0;
+    }
+    case OPK_FIXED: *out = node_boundary_matrix(n->mesh, n->R); return 0;
+    case OPK_CSRSIGN: *out = node_boundary_transpose(n->mesh, n->R); return 0;
+    case OPK_DIAG: *out = n; return 0;
+    case OPK_CSRF64: return transpose_csrf64(n, out);
+    case OPK_LAPLACE0: ddf_set_error("adjoint of the fused Laplacian is not available; use coderiv/deriv factors"); return 1;
+    case OPK_CHAIN: {
+      std::vector<OpRef> f;
+      for (auto it = n->factors.rbegin(); it != n->factors.rend(); ++it) {
+        OpRef a;
+        DDF_CHECK(adjoint_node(*it, &a));
+        f.push_back(a);
+      }
+      *out = chain_of(f, n->scale);
+      return 0;
+    }
+    case OPK_SUM: {
+      OpRef s = std::make_shared<OpNode>();
+      s->kind = OPK_SUM; s->ctx = n->ctx; s->mesh = n->mesh; s->nrows = n->ncols; s->ncols = n->nrows;
+      for (size_t i = 0; i < n->factors.size(); i++) {
+        OpRef a;
+        DDF_CHECK(adjoint_node(n->factors[i], &a));
+        s->factors.push_back(a);
+        s->coefs.push_back(n->coefs[i]);
+      }
+      *out = s;
+      return 0;
+    }
+  }
+  return 1;
+}
+
+extern "C" int ddf_op_adjoint(ddf_op* A, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  OpRef o;
+  DDF_CHECK(adjoint_node(A->node, &o));
+  *out = wrap(o);
+  return 0;
+  DDF_TRY_END
+}
+
+// ====================================================================== Op * Fun
+static double* temp_of(OpNode* n, size_t slot, int64_t len) {
+  while (n->temps.size() <= slot) n->temps.emplace_back(new DevBuf<double>());
+  DevBuf<double>* b = n->temps[slot].get();
+  if ((int64_t)b->n < len) {
+    if (b->alloc(n->ctx, (size_t)len)) return nullptr;
+  }
+  return b->p;
+}
+
+static int apply_node(OpNode* n, const double* x, double* y);
+
+static bool is_sparse_leaf(const OpRef& f) { return f->kind == OPK_FIXED || f->kind == OPK_CSRSIGN; }
+
+// sparse leaf with optional fused diagonals.  A diagonal payload with scale != 1
+// cannot be fused bit-identically unless the scale is +-1 (sign flips commute with
+// rounding), which is all the DEC operators ever produce.
+static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpNode* post, double alpha, double* y) {
+  ddf_mesh* m = f->mesh;
+  const double* pre_d = pre ? pre->diag : nullptr;
+  const double* post_d = post ? post->diag : nullptr;
+  double a = alpha;
+  if (pre) a *= pre->scale;
+  if (post) a *= post->scale;
+  if (f->kind == OPK_FIXED) {
+    const int W = f->R + 1;
+    return launch_fixed(f->ctx, m->bnd_table(f->R), W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
+  }
+  return launch_csrsign(f->ctx, m->brow_ptr[f->R].p, m->bcol[f->R].p, f->nrows, x, pre_d, post_d, a, y);
+}
+
+static bool fusable_diag(const OpRef& f) {
+  return f->kind == OPK_DIAG && f->diag != nullptr && (f->scale == 1.0 || f->scale == -1.0);
+}
+
+static int apply_chain(OpNode* n, const double* x, double* y) {
+  // evaluate right to left; stage = [post-diag] sparse [pre-diag]  or a lone factor
+  const int nf = (int)n->factors.size();
+  int i = nf - 1;
+  const double* cur = x;
+  size_t slot = 0;
+  while (i >= 0) {
+    int next_i;
+    const OpNode *pre = nullptr, *post = nullptr;
+    OpNode* core;
+    if (fusable_diag(n->factors[i]) && i - 1 >= 0 && is_sparse_leaf(n->factors[i - 1])) {
+      pre = n->factors[i].get();
+      core = n->factors[i - 1].get();
+      next_i = i - 2;
+    } else {
+      core = n->factors[i].get();
+      next_i = i - 1;
+    }
+    if ((core->kind == OPK_FIXED || core->kind == OPK_CSRSIGN) && next_i >= 0 && fusable_diag(n->factors[next_i])) {
+      post = n->factors[next_i].get();
+      next_i--;
+    }
+    const bool last = next_i < 0;
+    const double alpha = last ? n->scale : 1.0;
+    double* dst = last ? y : temp_of(n, slot++ & 1, core->nrows);
+    if (!dst) return 1;
+    if (core->kind == OPK_FIXED || core->kind == OPK_CSRSIGN) {
+      DDF_CHECK(apply_sparse(core, cur, pre, post, alpha, dst));
+    } else {
+      DDF_CHECK(apply_node(core, cur, dst));
+      if (alpha != 1.0) DDF_CHECK(launch_diag(n->ctx, nullptr, alpha, dst, dst, core->nrows));
+    }
+    cur = dst;
+    i = next_i;
+  }
+  return 0;
+}
+
+__global__ void k_axpy_inplace(double c, const double* __restrict__ t, double* __restrict__ y, int64_t n, int first) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = c == 1.0 ? t[i] : __dmul_rn(c, t[i]);
+  y[i] = first ? v : __dadd_rn(y[i], v);
+}
+
+static int apply_node(OpNode* n, const double* x, double* y) {
+  ddf_ctx* ctx = n->ctx;
+  switch (n->kind) {
+    case OPK_ZERO:
+      if (n->nrows) DDF_CUDA(cudaMemsetAsync(y, 0, n->nrows * sizeof(double), ctx->stream));
+      return 0;
+    case OPK_FIXED:
+    case OPK_CSRSIGN: return apply_sparse(n, x, nullptr, nullptr, 1.0, y);
+    case OPK_DIAG: return launch_diag(ctx, n->diag, n->scale, x, y, n->nrows);
+    case OPK_CSRF64: {
+      if (!n->nrows) return 0;
+      int grid;
+      DDF_CHECK(grid_for(n->nrows, 256, &grid));
+      k_apply_csrf64<<<grid, 256, 0, ctx->stream>>>(n->rowptr.p, n->col.p, n->val.p, n->nrows, x, 1.0, y);
+      DDF_LAUNCH_CHECK(ctx);
+      return 0;
+    }
+    case OPK_LAPLACE0: return ddf_laplace0_apply(n->mesh, x, y);
+    case OPK_CHAIN: return apply_chain(n, x, y);
+    case OPK_SUM: {
+      // terms are evaluated into a scratch vector and accumulated in order
+      for (size_t t = 0; t < n->factors.size(); t++) {
+        double* tmp = temp_of(n, 2, n->nrows);
+        if (!tmp && n->nrows) return 1;
+        DDF_CHECK(apply_node(n->factors[t].get(), x, tmp));
+        if (n->nrows) {
+          int grid;
+          DDF_CHECK(grid_for(n->nrows, 256, &grid));
+          k_axpy_inplace<<<grid, 256, 0, ctx->stream>>>(n->coefs[t], tmp, y, n->nrows, t == 0 ? 1 : 0);
+          DDF_LAUNCH_CHECK(ctx);
+        }
+      }
+      return 0;
+    }
+  }
+  return 1;
+}
+
+extern "C" int ddf_op_apply(ddf_op* A, ddf_vec* x, ddf_vec* y) {
+  DDF_TRY_BEGIN
+  OpNode* n = A->node.get();
+  if (x->n != n->ncols) DDF_FAIL("apply: x has length %lld, operator has %lld columns", (long long)x->n, (long long)n->ncols);
+  if (y->n != n->nrows) DDF_FAIL("apply: y has length %lld, operator has %lld rows", (long long)y->n, (long long)n->nrows);
+  if (x == y) DDF_FAIL("apply: x and y must not alias");
+  return apply_node(n, x->d.p, y->d.p);
+  DDF_TRY_END
+}
+
+// ============================================================ assembled export
+// Materialise an operator as a device COO list in CSC order (col ascending, row
+// ascending within a column) with the Op constructor's chop (Ops.jl:44-58).
+struct Coo {
+  DevBuf<int32_t> row, col;
+  DevBuf<double> val;
+  int64_t nnz = 0;
+};
+
+// d_R^T (FIXED, n_R x n_{R-1}): CSC columns are faces -> parents = the row-CSR of d_R
+__global__ void k_coo_from_rowcsr(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ colw, int64_t nfaces,
+                                  const double* __restrict__ dl, double sl, const double* __restrict__ dr, double sr,
+                                  int32_t* __restrict__ row, int32_t* __restrict__ col, double* __restrict__ val,
+                                  int transpose) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nfaces) return;
+  for (uint32_t p = rowptr[f]; p < rowptr[f + 1]; p++) {
+    const uint32_t cw = colw[p];
+    const int32_t j = (int32_t)(cw & 0x7fffffffu);
+    double v = (cw >> 31) ? -1.0 : 1.0;
+    // matrix entry M[j, f] (transpose == 1: M = d_R^T) ; left diag indexed by row, right by column
+    const int32_t r = transpose ? j : (int32_t)f, c = transpose ? (int32_t)f : j;
+    if (dl || sl != 1.0) { v = __dmul_rn(dl ? __dmul_rn(sl, dl[r]) : sl, v); if (v * v < DDF_CHOP_ABS2) v = 0.0; }
+    if (dr || sr != 1.0) v = __dmul_rn(v, dr ? __dmul_rn(sr, dr[c]) : sr);
+    row[p] = r; col[p] = c; val[p] = v;
+  }
+}
+// d_R (CSRSIGN, n_{R-1} x n_R): CSC columns are simplices -> faces = the fixed-width table
+__global__ void k_coo_from_table(const int32_t* __restrict__ tab, int64_t nsimp, int W, int first_negative,
+                                 const double* __restrict__ dl, double sl, const double* __restrict__ dr, double sr,
+                                 int32_t* __restrict__ row, int32_t* __restrict__ col, double* __restrict__ val) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nsimp) return;
+  for (int p = 0; p < W; p++) {
+    const int32_t f = tab[j * W + p];
+    double v = (((p & 1) != 0) != (first_negative != 0)) ? -1.0 : 1.0;
+    if (dl || sl != 1.0) { v = __dmul_rn(dl ? __dmul_rn(sl, dl[f]) : sl, v); if (v * v < DDF_CHOP_ABS2) v = 0.0; }
+    if (dr || sr != 1.0) v = __dmul_rn(v, dr ? __dmul_rn(sr, dr[j]) : sr);
+    row[j * W + p] = f; col[j * W + p] = (int32_t)j; val[j * W + p] = v;
+  }
+}
+__global__ void k_coo_diag(const double* __restrict__ d, double s, int64_t n, int32_t* __restrict__ row,
+                           int32_t* __restrict__ col, double* __restrict__ val) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  row[i] = col[i] = (int32_t)i;
+  val[i] = d ? __dmul_rn(s, d[i]) : s;
+}
+__global__ void k_chop_flags(const double* __restrict__ val, int64_t nnz, double thr, uint8_t* __restrict__ keep) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nnz) keep[p] = (val[p] * val[p] < thr) ? 0 : 1;    // abs2(f) < eps34sq  (Ops.jl:52)
+}
+
+static int coo_alloc(ddf_ctx* ctx, Coo& c, int64_t nnz) {
+  c.nnz = nnz;
+  DDF_CHECK(c.row.alloc(ctx, nnz));
+  DDF_CHECK(c.col.alloc(ctx, nnz));
+  DDF_CHECK(c.val.alloc(ctx, nnz));
+  return 0;
+}
+
+static int coo_chop(ddf_ctx* ctx, Coo& c) {
+  if (c.nnz == 0) return 0;
+  DevBuf<uint8_t> keep, temp;
+  DevBuf<int64_t> nsel;
+  Coo o;
+  DDF_CHECK(keep.alloc(ctx, c.nnz));
+  DDF_CHECK(nsel.alloc(ctx, 1));
+  DDF_CHECK(coo_alloc(ctx, o, c.nnz));
+  int grid;
+  DDF_CHECK(grid_for(c.nnz, 256, &grid));
+  const double thr = DDF_CHOP_ABS2;
+  k_chop_flags<<<grid, 256, 0, ctx->stream>>>(c.val.p, c.nnz, thr, keep.p);
+  DDF_LAUNCH_CHECK(ctx);
+  size_t tb = 0, tb2 = 0, tb3 = 0;
+  DDF_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, c.row.p, keep.p, o.row.p, nsel.p, c.nnz, ctx->stream));
+  DDF_CUDA(cub::DeviceSelect::Flagged(nullptr, tb2, c.val.p, keep.p, o.val.p, nsel.p, c.nnz, ctx->stream));
+  tb3 = tb > tb2 ? tb : tb2;
+  DDF_CHECK(temp.alloc(ctx, tb3));
+  DDF_CUDA(cub::DeviceSelect::Flagged(temp.p, tb3, c.row.p, keep.p, o.row.p, nsel.p, c.nnz, ctx->stream));
+  DDF_CUDA(cub::DeviceSelect::Flagged(temp.p, tb3, c.col.p, keep.p, o.col.p, nsel.p, c.nnz, ctx->stream));
+  DDF_CUDA(cub::DeviceSelect::Flagged(temp.p, tb3, c.val.p, keep.p, o.val.p, nsel.p, c.nnz, ctx->stream));
+  ctx->launches += 3;
+  int64_t h = 0;
+  DDF_CUDA(cudaMemcpyAsync(&h, nsel.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  o.nnz = h;
+  c.row.swap(o.row); c.col.swap(o.col); c.val.swap(o.val);
+  c.nnz = h;
+  return 0;
+}
+
+__global__ void k_csr_to_coo(const uint32_t* __restrict__ rowptr, int64_t nrows, int32_t* __restrict__ row) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  for (uint32_t p = rowptr[i]; p < rowptr[i + 1]; p++) row[p] = (int32_t)i;
+}
+__global__ void k_gather_i32(const uint32_t* __restrict__ idx, const int32_t* __restrict__ src, int64_t n, int32_t* __restrict__ dst) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[p] = src[idx[p]];
+}
+__global__ void k_gather_f64(const uint32_t* __restrict__ idx, const double* __restrict__ src, int64_t n, double* __restrict__ dst) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[p] = src[idx[p]];
+}
+__global__ void k_iota_u32(uint32_t* __restrict__ p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t)i;
+}
+__global__ void k_i32_to_u32(const int32_t* __restrict__ s, uint32_t* __restrict__ d, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = (uint32_t)s[i];
+}
+
+// stable sort of a row-major COO by column -> CSC order
+static int coo_sort_by_col(ddf_ctx* ctx, Coo& c, int64_t ncols) {
+  if (c.nnz == 0) return 0;
+  DevBuf<uint32_t> k0, k1, i0, i1;
+  DevBuf<uint8_t> temp;
+  DDF_CHECK(k0.alloc(ctx, c.nnz)); DDF_CHECK(k1.alloc(ctx, c.nnz));
+  DDF_CHECK(i0.alloc(ctx, c.nnz)); DDF_CHECK(i1.alloc(ctx, c.nnz));
+  int grid;
+  DDF_CHECK(grid_for(c.nnz, 256, &grid));
+  k_i32_to_u32<<<grid, 256, 0, ctx->stream>>>(c.col.p, k0.p, c.nnz);
+  DDF_LAUNCH_CHECK(ctx);
+  k_iota_u32<<<grid, 256, 0, ctx->stream>>>(i0.p, c.nnz);
+  DDF_LAUNCH_CHECK(ctx);
+  int bits = 1;
+  while (((int64_t)1 << bits) < ncols) bits++;
+  cub::DoubleBuffer<uint32_t> dk(k0.p, k1.p), di(i0.p, i1.p);
+  size_t tb = 0;
+  DDF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, di, c.nnz, 0, bits, ctx->stream));
+  DDF_CHECK(temp.alloc(ctx, tb));
+  DDF_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, tb, dk, di, c.nnz, 0, bits, ctx->stream));
+  ctx->launches += (bits + 7) / 8 + 1;
+  Coo o;
+  DDF_CHECK(coo_alloc(ctx, o, c.nnz));
+  k_gather_i32<<<grid, 256, 0, ctx->stream>>>(di.Current(), c.row.p, c.nnz, o.row.p);
+  k_gather_i32<<<grid, 256, 0, ctx->stream>>>(di.Current(), c.col.p, c.nnz, o.col.p);
+  k_gather_f64<<<grid, 256, 0, ctx->stream>>>(di.Current(), c.val.p, c.nnz, o.val.p);
+  ctx->launches += 3;
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  c.row.swap(o.row); c.col.swap(o.col); c.val.swap(o.val);
+  return 0;
+}
+
+static int transpose_csrf64(OpRef src, OpRef* out) {
+  ddf_ctx* ctx = src->ctx;
+  OpRef o = std::make_shared<OpNode>();
+  o->kind = OPK_CSRF64; o->ctx = ctx; o->mesh = src->mesh;
+  o->nrows = src->ncols; o->ncols = src->nrows; o->nnz = src->nnz;
+  DDF_CHECK(o->rowptr.alloc(ctx, o->nrows + 1));
+  DDF_CHECK(o->col.alloc(ctx, o->nnz));
+  DDF_CHECK(o->val.alloc(ctx, o->nnz));
+  if (o->nnz == 0) {
+    DDF_CUDA(cudaMemsetAsync(o->rowptr.p, 0, (o->nrows + 1) * 4, ctx->stream));
+    *out = o;
+    return 0;
+  }
+  Coo c;
+  DDF_CHECK(coo_alloc(ctx, c, src->nnz));
+  int grid;
+  DDF_CHECK(grid_for(src->nrows, 256, &grid));
+  k_csr_to_coo<<<grid, 256, 0, ctx->stream>>>(src->rowptr.p, src->nrows, c.row.p);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CUDA(cudaMemcpyAsync(c.col.p, src->col.p, src->nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  DDF_CUDA(cudaMemcpyAsync(c.val.p, src->val.p, src->nnz * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  DDF_CHECK(coo_sort_by_col(ctx, c, src->ncols));
+  // transposed CSR: rows = old columns (sorted), cols = old rows
+  DDF_CUDA(cudaMemcpyAsync(o->col.p, c.row.p, o->nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  DDF_CUDA(cudaMemcpyAsync(o->val.p, c.val.p, o->nnz * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  DevBuf<uint32_t> keys;
+  DDF_CHECK(keys.alloc(ctx, o->nnz));
+  DDF_CHECK(grid_for(o->nnz, 256, &grid));
+  k_i32_to_u32<<<grid, 256, 0, ctx->stream>>>(c.col.p, keys.p, o->nnz);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CHECK(grid_for(o->nrows + 1, 256, &grid));
+  k_lower_bound<<<grid, 256, 0, ctx->stream>>>(keys.p, o->nnz, o->nrows, o->rowptr.p);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = o;
+  return 0;
+}
+
+int ddf_laplace0_to_coo(ddf_mesh* m, DevBuf<int32_t>& row, DevBuf<int32_t>& col, DevBuf<double>& val, int64_t* nnz);  // wave.cu
+
+// materialise node -> Coo in CSC order, chopped
+static int materialise(OpNode* n, Coo& c) {
+  ddf_ctx* ctx = n->ctx;
+  ddf_mesh* m = n->mesh;
+  int grid;
+  // pattern [DIAG] sparse [DIAG] (also a bare sparse leaf / bare diagonal)
+  const OpNode *dl = nullptr, *dr = nullptr, *core = nullptr;
+  if (n->kind == OPK_FIXED || n->kind == OPK_CSRSIGN) core = n;
+  else if (n->kind == OPK_CHAIN && n->scale == 1.0) {
+    std::vector<OpNode*> f;
+    for (auto& g : n->factors) f.push_back(g.get());
+    size_t a = 0, b = f.size();
+    if (a < b && f[a]->kind == OPK_DIAG) dl = f[a++];
+    if (a < b && f[b - 1]->kind == OPK_DIAG && b - 1 > a) dr = f[--b];
+    if (b - a == 1 && (f[a]->kind == OPK_FIXED || f[a]->kind == OPK_CSRSIGN)) core = f[a];
+    else { dl = dr = nullptr; }
+  }
+  if (core) {
+    const int R = core->R;
+    const int64_t nnz = m->n[R] * (R + 1);
+    DDF_CHECK(coo_alloc(ctx, c, nnz));
+    if (nnz) {
+      const double* pl = dl ? dl->diag : nullptr; const double sl = dl ? dl->scale : 1.0;
+      const double* pr = dr ? dr->diag : nullptr; const double sr = dr ? dr->scale : 1.0;
+      if (core->kind == OPK_FIXED) {
+        DDF_CHECK(grid_for(m->n[R - 1], 256, &grid));
+        k_coo_from_rowcsr<<<grid, 256, 0, ctx->stream>>>(m->brow_ptr[R].p, m->bcol[R].p, m->n[R - 1], pl, sl, pr, sr,
+                                                         c.row.p, c.col.p, c.val.p, 1);
+      } else {
+        DDF_CHECK(grid_for(m->n[R], 256, &grid));
+        k_coo_from_table<<<grid, 256, 0, ctx->stream>>>(m->bnd_table(R), m->n[R], R + 1, R & 1, pl, sl, pr, sr, c.row.p,
+                                                        c.col.p, c.val.p);
+      }
+      DDF_LAUNCH_CHECK(ctx);
+    }
+    // NB: the reference chops after each product; with |entries| = |dl*dr| a second chop
+    // after the first product can only differ when |dl| alone is below threshold -- apply both.
+    return coo_chop(ctx, c);
+  }
+  if (n->kind == OPK_DIAG) {
+    DDF_CHECK(coo_alloc(ctx, c, n->nrows));
+    if (n->nrows) {
+      DDF_CHECK(grid_for(n->nrows, 256, &grid));
+      k_coo_diag<<<grid, 256, 0, ctx->stream>>>(n->diag, n->scale, n->nrows, c.row.p, c.col.p, c.val.p);
+      DDF_LAUNCH_CHECK(ctx);
+    }
+    return 0;     // Diagonal is not an AbstractSparseMatrix: dnz leaves it alone (Ops.jl:40)
+  }
+  if (n->kind == OPK_ZERO) return coo_alloc(ctx, c, 0);
+  if (n->kind == OPK_CSRF64) {
+    DDF_CHECK(coo_alloc(ctx, c, n->nnz));
+    if (n->nnz) {
+      DDF_CHECK(grid_for(n->nrows, 256, &grid));
+      k_csr_to_coo<<<grid, 256, 0, ctx->stream>>>(n->rowptr.p, n->nrows, c.row.p);
+      DDF_LAUNCH_CHECK(ctx);
+      DDF_CUDA(cudaMemcpyAsync(c.col.p, n->col.p, n->nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      DDF_CUDA(cudaMemcpyAsync(c.val.p, n->val.p, n->nnz * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      DDF_CHECK(coo_sort_by_col(ctx, c, n->ncols));
+    }
+    return coo_chop(ctx, c);
+  }
+  if (n->kind == OPK_LAPLACE0) {
+    DDF_CHECK(ddf_laplace0_to_coo(m, c.row, c.col, c.val, &c.nnz));
+    return coo_chop(ctx, c);
+  }
+  ddf_set_error("to_csc: assembled export is implemented for deriv/boundary, hodge, coderiv (diag*sparse*diag), "
+                "laplace(Pr,0) and from_csc operators; general Op*Op SpGEMM is a next-row item (SURVEY 8f N3)");
+  return 1;
+}
+
+extern "C" int ddf_op_to_csc(ddf_op* A, int64_t* nnz, int64_t* colptr, int64_t* rowval, double* nzval) {
+  DDF_TRY_BEGIN
+  OpNode* n = A->node.get();
+  ddf_ctx* ctx = n->ctx;
+  Coo c;
+  DDF_CHECK(materialise(n, c));
+  *nnz = c.nnz;
+  if (!colptr) return 0;
+  // colptr by lower bound over the sorted column keys
+  DevBuf<uint32_t> keys, cp;
+  DDF_CHECK(cp.alloc(ctx, n->ncols + 1));
+  int grid;
+  if (c.nnz) {
+    DDF_CHECK(keys.alloc(ctx, c.nnz));
+    DDF_CHECK(grid_for(c.nnz, 256, &grid));
+    k_i32_to_u32<<<grid, 256, 0, ctx->stream>>>(c.col.p, keys.p, c.nnz);
+    DDF_LAUNCH_CHECK(ctx);
+  }
+  DDF_CHECK(grid_for(n->ncols + 1, 256, &grid));
+  k_lower_bound<<<grid, 256, 0, ctx->stream>>>(keys.p, c.nnz, n->ncols, cp.p);
+  DDF_LAUNCH_CHECK(ctx);
+  std::vector<uint32_t> hcp(n->ncols + 1);
+  std::vector<int32_t> hrow(c.nnz);
+  DDF_CUDA(cudaMemcpyAsync(hcp.data(), cp.p, (n->ncols + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (c.nnz) {
+    DDF_CUDA(cudaMemcpyAsync(hrow.data(), c.row.p, c.nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DDF_CUDA(cudaMemcpyAsync(nzval, c.val.p, c.nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int64_t j = 0; j <= n->ncols; j++) colptr[j] = (int64_t)hcp[j] + 1;
+  for (int64_t p = 0; p < c.nnz; p++) rowval[p] = (int64_t)hrow[p] + 1;
+  return 0;
+  DDF_TRY_END
+}

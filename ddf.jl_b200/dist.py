@@ -1,0 +1,103 @@
+"""Multi-GPU layer: one process per GPU, slabs along the slowest grid axis, ghost
+planes exchanged with ncclSend/ncclRecv over NVLink.
+
+The reference has no parallel code at all ("Parallelism strategies:
+none"); this partitions the path's independent units (rows = simplices) by
+simplex ranges.  Host-side logic here is pure Python so that it can be tested
+with the gloo backend on CPU (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+GHOST_CELLS = 2   # ghost cell layers per interior slab face: even, so the mirrored Kuhn blocks keep their parity
+
+
+@dataclass
+class Slab:
+    """This rank's part of a `large_hypercube` mesh cut along the last axis."""
+    rank: int
+    nranks: int
+    z_own_lo: int          # first owned vertex plane (global index)
+    z_own_hi: int          # one past the last owned vertex plane
+    z_cell_lo: int         # first local cell layer (global index, even)
+    z_cell_hi: int         # one past the last local cell layer
+    plane: int             # vertices per plane
+    ghost_lo: int          # ghost vertex planes below the owned range
+    ghost_hi: int          # ghost vertex planes above the owned range
+
+    @property
+    def nz_cells(self) -> int:
+        return self.z_cell_hi - self.z_cell_lo
+
+    @property
+    def n_local_planes(self) -> int:
+        return self.nz_cells + 1
+
+    @property
+    def own_rows(self):
+        return self.ghost_lo * self.plane, (self.n_local_planes - self.ghost_hi) * self.plane
+
+
+def partition_slabs(nz_cells: int, nranks: int, plane: int) -> List[Slab]:
+    """Cut `nz_cells` cell layers (even) into `nranks` contiguous slabs of even
+    thickness.  Rank r owns vertex planes [Z_r, Z_{r+1}); the last rank also owns the
+    top plane.  Every interior slab face is padded by GHOST_CELLS cell layers so the
+    full star (all incident cells) of every owned vertex is local: geometry and the
+    Laplacian rows of owned vertices are then identical to the undivided mesh."""
+    if nz_cells % 2:
+        raise ValueError("nz_cells must be even (ManifoldConstructors.jl:208)")
+    blocks = nz_cells // 2
+    if nranks > blocks:
+        raise ValueError(f"cannot cut {nz_cells} cell layers into {nranks} slabs of even thickness")
+    base, extra = divmod(blocks, nranks)
+    cuts = [0]
+    for r in range(nranks):
+        cuts.append(cuts[-1] + 2 * (base + (1 if r < extra else 0)))
+    slabs = []
+    for r in range(nranks):
+        lo, hi = cuts[r], cuts[r + 1]
+        g_lo = GHOST_CELLS if r > 0 else 0
+        g_hi = GHOST_CELLS if r < nranks - 1 else 0
+        own_hi = hi if r < nranks - 1 else hi + 1           # the last rank owns the top vertex plane
+        slabs.append(Slab(rank=r, nranks=nranks, z_own_lo=lo, z_own_hi=own_hi, z_cell_lo=lo - g_lo,
+                          z_cell_hi=hi + g_hi, plane=plane, ghost_lo=g_lo,
+                          ghost_hi=(g_hi + 1) if r < nranks - 1 else 0))
+    return slabs
+
+
+def init_comm(ctx, group=None):
+    """Create the NCCL communicator of `ctx` from an initialised torch.distributed
+    process group (any backend; only used to broadcast the 128-byte unique id)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        ctx.rank, ctx.nranks = 0, 1
+        return
+    if rank == 0:
+        uid = ctx.comm_unique_id()
+    else:
+        uid = bytes(128)
+    obj = [uid]
+    dist.broadcast_object_list(obj, src=0, group=group)
+    ctx.comm_init(world, rank, obj[0])
+
+
+def slab_hypercube(D: int, nelts: Sequence[int], ctx, rank: Optional[int] = None, nranks: Optional[int] = None):
+    """This rank's slab of large_hypercube_manifold(Val(D); nelts) as a device mesh
+    with global coordinates and weights (hdiv = nelts[0]; the reference requires all
+    nelts equal, ManifoldConstructors.jl:262 -- slabs relax that along the last axis
+    only).  Returns (Manifold, Slab)."""
+    from .manifoldops import large_hypercube_manifold
+    rank = ctx.rank if rank is None else rank
+    nranks = ctx.nranks if nranks is None else nranks
+    plane = int(np.prod([n + 1 for n in nelts[:-1]])) if D > 1 else 1
+    slab = partition_slabs(int(nelts[-1]), nranks, plane)[rank]
+    local = list(nelts[:-1]) + [slab.nz_cells]
+    mfd = large_hypercube_manifold(D, local, ctx=ctx, hdiv=int(nelts[0]), z0=slab.z_cell_lo)
+    mfd.set_halo(plane, slab.ghost_lo, slab.ghost_hi)
+    return mfd, slab

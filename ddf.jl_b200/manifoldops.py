@@ -1,0 +1,215 @@
+"""DEC operators and manifold constructors, mirroring the reference's call surface.
+
+  deriv / boundary / isboundary     src/ManifoldOps.jl:17-49
+  hodge / invhodge                  src/ManifoldOps.jl:58-105
+  coderiv / laplace                 src/ManifoldOps.jl:110-146
+  integral / dot                    src/ManifoldOps.jl:150-164
+  sample (R = 0)                    src/Continuum.jl:124-158
+  simplex_manifold / refined_manifold / large_hypercube_manifold
+                                    src/ManifoldConstructors.jl:30-74,521-529,196-284
+Same names, argument meaning and error behaviour (the reference's `@assert`s on
+R ranges become DDFError).  `Val(P), Val(R)` become plain arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from ._lib import DDFError, call
+from .core import Context, Dl, Fun, Manifold, Op, Pr, _P, default_context
+
+
+def _op(fn: str, mfd: Manifold, P, R, P1, R1, P2, R2) -> Op:
+    h = C.c_void_p()
+    call(fn, mfd._h, _P(P), int(R), C.byref(h))
+    return Op(mfd, P1, R1, P2, R2, h)
+
+
+# ------------------------------------------------------------ topological operators
+def boundary(P, R: int, mfd: Manifold) -> Op:
+    """boundary(Val(P), Val(R), mfd) (ManifoldOps.jl:17-26)."""
+    if P:
+        return _op("ddf_op_boundary", mfd, P, R, Pr, R - 1, Pr, R)
+    return _op("ddf_op_boundary", mfd, P, R, Dl, R + 1, Dl, R)
+
+
+def isboundary(P, R: int, mfd: Manifold) -> Op:
+    """isboundary(Val(Pr), Val(R), mfd) (ManifoldOps.jl:31-35)."""
+    return _op("ddf_op_isboundary", mfd, P, R, Pr, R, Pr, R)
+
+
+def deriv(P, R: int, mfd: Manifold) -> Op:
+    """deriv(Val(P), Val(R), mfd) (ManifoldOps.jl:40-47)."""
+    s = 1 if P else -1
+    return _op("ddf_op_deriv", mfd, P, R, P, R + s, P, R)
+
+
+# --------------------------------------------------------------- geometric operators
+def hodge(P, R: int, mfd: Manifold) -> Op:
+    """hodge(Val(P), Val(R), mfd) (ManifoldOps.jl:58-68, 84-91)."""
+    mfd._geometry()
+    return _op("ddf_op_hodge", mfd, P, R, not P, R, P, R)
+
+
+def invhodge(P, R: int, mfd: Manifold) -> Op:
+    """invhodge(Val(P), Val(R), mfd) (ManifoldOps.jl:71-82, 93-100)."""
+    mfd._geometry()
+    return _op("ddf_op_invhodge", mfd, P, R, not P, R, P, R)
+
+
+def coderiv(P, R: int, mfd: Manifold) -> Op:
+    """coderiv(Val(P), Val(R), mfd) (ManifoldOps.jl:110-121)."""
+    mfd._geometry()
+    dR = 1 if P else -1
+    return _op("ddf_op_coderiv", mfd, P, R, P, R - dR, P, R)
+
+
+def laplace(P, R: int, mfd: Manifold) -> Op:
+    """laplace(Val(P), Val(R), mfd) (ManifoldOps.jl:128-144)."""
+    mfd._geometry()
+    return _op("ddf_op_laplace", mfd, P, R, P, R, P, R)
+
+
+def one(P, R: int, mfd: Manifold, a: float = 1.0) -> Op:
+    """one(Op{D,P,R,P,R}, mfd) (Ops.jl:216-220), optionally scaled."""
+    h = C.c_void_p()
+    call("ddf_op_identity", mfd._h, int(R), float(a), C.byref(h))
+    return Op(mfd, P, R, P, R, h)
+
+
+def zero(P1, R1, P2, R2, mfd: Manifold) -> Op:
+    """zero(Op{D,P1,R1,P2,R2}, mfd) (Ops.jl:152-157)."""
+    h = C.c_void_p()
+    call("ddf_op_zero", mfd._h, int(R1), int(R2), C.byref(h))
+    return Op(mfd, P1, R1, P2, R2, h)
+
+
+# convenience forms acting on a Fun (ManifoldOps.jl:28,49,102-105,123,146)
+def _apply(opfn, f: Fun) -> Fun:
+    return opfn(f.P, f.R, f.manifold) * f
+
+
+def boundary_of(f: Fun) -> Fun:
+    return _apply(boundary, f)
+
+
+def deriv_of(f: Fun) -> Fun:
+    return _apply(deriv, f)
+
+
+def hodge_of(f: Fun) -> Fun:
+    return _apply(hodge, f)
+
+
+def invhodge_of(f: Fun) -> Fun:
+    return _apply(invhodge, f)
+
+
+def coderiv_of(f: Fun) -> Fun:
+    return _apply(coderiv, f)
+
+
+def laplace_of(f: Fun) -> Fun:
+    return _apply(laplace, f)
+
+
+def integral(f: Fun) -> float:
+    """integral(f) for (Pr, D)- and (Dl, 0)-cochains (ManifoldOps.jl:150-151)."""
+    if not ((f.P and f.R == f.manifold.D) or ((not f.P) and f.R == 0)):
+        raise DDFError("integral: defined for Fun{D,Pr,D} and Fun{D,Dl,0} (ManifoldOps.jl:150-151)")
+    return f.sum()
+
+
+# ------------------------------------------------------------------------- sampling
+_FIELDS = {"wave": 0, "readme": 1, "poisson_rho": 2}
+
+
+def sample(mfd: Manifold, f, P=Pr, R: int = 0) -> Fun:
+    """sample(Fun{D,Pr,0,...}, f, mfd) (Continuum.jl:124-158; R = 0 only, like the
+    reference's assert at :130).  `f` is one of the example fields evaluated on the
+    device ("wave", "readme", "poisson_rho") or a callable coords(V,C) -> values(V)
+    evaluated on the host (the reference also evaluates `f` on the host)."""
+    if not P or R != 0:
+        raise DDFError("sample: only P == Pr and R == 0 (Continuum.jl:127-130)")
+    out = Fun(mfd, Pr, 0)
+    if isinstance(f, str):
+        call("ddf_vec_sample", mfd._h, _FIELDS[f], out._h)
+    else:
+        out.upload(np.asarray(f(mfd.get_coords()), dtype=np.float64))
+    return out
+
+
+# --------------------------------------------------------------------- constructors
+def regular_simplex(D: int) -> np.ndarray:
+    """Coordinates of the regular D-simplex with edge length 1
+    (ManifoldConstructors.jl:50-74).  Host side: mesh *input*."""
+    N = D + 1
+    s = np.zeros((N, D))
+    if D > 0:
+        s0 = regular_simplex(D - 1)
+        z = 1.0 if D == 1 else math.sqrt(1 - float(np.sum(s0[0] ** 2)))
+        z0 = -z / (D + 1)
+        for n in range(N - 1):
+            s[n, :D - 1] = s0[n]
+            s[n, D - 1] = z0
+        s[N - 1, D - 1] = z + z0
+    return s
+
+
+def simplex_manifold(D: int, ctx: Optional[Context] = None) -> Manifold:
+    """simplex_manifold(Val(D), Float64; optimize_mesh=false) (ManifoldConstructors.jl:30-40)."""
+    coords = regular_simplex(D).reshape(D + 1, D)
+    simp = np.arange(D + 1, dtype=np.int64)[None, :]
+    return Manifold.from_simplices("simplex manifold", simp, coords, ctx=ctx)
+
+
+def delaunay_mesh(coords: np.ndarray) -> np.ndarray:
+    """delaunay_mesh(coords) (Meshing.jl:19-49): the reference calls
+    scipy.spatial.Delaunay through Delaunay.jl/PyCall; so does this."""
+    from scipy.spatial import Delaunay
+    if coords.shape[1] == 1:
+        order = np.argsort(coords[:, 0], kind="stable")
+        return np.stack([order[:-1], order[1:]], axis=1).astype(np.int64)
+    return np.asarray(Delaunay(coords).simplices, dtype=np.int64)
+
+
+def refined_manifold(mfd0: Manifold) -> Manifold:
+    """refined_manifold(mfd0; optimize_mesh=false) (ManifoldConstructors.jl:521-529):
+    old vertices + edge midpoints in edge-id order (Meshing.jl:127-146), Delaunay,
+    zero weights.  Host-side mesh input; the face assembly runs on the device."""
+    if mfd0.D == 0:
+        return mfd0
+    coords = mfd0.get_coords()
+    edges = mfd0.get_simplices(1)
+    mid = (coords[edges[:, 0]] + coords[edges[:, 1]]) / 2
+    newc = np.concatenate([coords, mid], axis=0)
+    return Manifold.from_simplices("refined " + mfd0.name, delaunay_mesh(newc), newc, ctx=mfd0.ctx)
+
+
+def refined_simplex_manifold(D: int, levels: int = 1, ctx: Optional[Context] = None) -> Manifold:
+    m = simplex_manifold(D, ctx)
+    for _ in range(levels):
+        m = refined_manifold(m)
+    return m
+
+
+def large_hypercube_manifold(D: int, nelts: Optional[Sequence[int]] = None, ctx: Optional[Context] = None,
+                             hdiv: int = 0, z0: int = 0, assemble: bool = True) -> Manifold:
+    """large_hypercube_manifold(Val(D), Float64; nelts, optimize_mesh=false)
+    (ManifoldConstructors.jl:196-284), generated on the device."""
+    ctx = ctx or default_context()
+    if nelts is None:
+        nelts = (2,) * D
+    ne = np.ascontiguousarray(nelts, dtype=np.int64)
+    if len(ne) != D:
+        raise DDFError("large_hypercube_manifold: nelts must have D entries")
+    h = C.c_void_p()
+    call("ddf_mesh_create_hypercube", ctx._h, int(D), ne.ctypes.data_as(C.POINTER(C.c_int64)), int(hdiv), int(z0),
+         C.byref(h))
+    m = Manifold(h, ctx, "large hypercube manifold")
+    if assemble:
+        call("ddf_mesh_assemble", h)
+    return m

@@ -1,0 +1,71 @@
+"""Scalar wave equation driver, mirroring `Wave.wave(Val(D), levels)` of
+examples/wave.jl:25-170 on the device.
+
+The reference integrates dU = F U with fixed-step Tsit5 (wave.jl:134).  This
+module provides (i) the drop-in right-hand side `wave_rhs` (= `mul!(dU, F, U)`,
+wave.jl:98-100) and (ii) the fused leapfrog step north_star asks for, on the same
+operators (L, 1-B) and the same dt = min edge length / 2 (wave.jl:106,118).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from ._lib import call
+from .core import Fun, Manifold, Pr
+from .manifoldops import large_hypercube_manifold, sample
+
+
+def wave_dt(mfd: Manifold) -> float:
+    mfd._geometry()
+    out = C.c_double()
+    call("ddf_wave_dt", mfd._h, C.byref(out))
+    return out.value
+
+
+def wave_rhs(mfd: Manifold, u: Fun, udot: Fun):
+    """(du, dudot) = F * [u; udot]  (examples/wave.jl:87-100)."""
+    mfd._geometry()
+    du, dudot = Fun(mfd, Pr, 0), Fun(mfd, Pr, 0)
+    call("ddf_wave_rhs", mfd._h, u._h, udot._h, du._h, dudot._h)
+    return du, dudot
+
+
+def wave_leapfrog(mfd: Manifold, u: Fun, v: Fun, dt: float, nsteps: int):
+    """In-place fused leapfrog: v += dt (1-b).(L u); u += dt (1-b).v, `nsteps` times."""
+    mfd._geometry()
+    if mfd.ctx.nranks > 1:
+        call("ddf_wave_leapfrog_dist", mfd._h, u._h, v._h, float(dt), int(nsteps))
+    else:
+        call("ddf_wave_leapfrog", mfd._h, u._h, v._h, float(dt), int(nsteps))
+    return u, v
+
+
+def wave_step_bytes(mfd: Manifold):
+    a, b = C.c_int64(), C.c_int64()
+    call("ddf_wave_step_bytes", mfd._h, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def wave(D: int, levels: int, ctx=None, t1: float = 0.875):
+    """`Wave.wave(Val(D), levels)` with the leapfrog integrator: mesh n = 2^levels
+    (wave.jl:32-34), u0 = prod sinpi(x_d), udot0 = 0 (wave.jl:42-58), integrate to
+    t1 (the last `saveat` time of wave.jl:116 is 0.875) and return the error norm
+    sqrt(|u - u_exact|^2 / length) of wave.jl:156-163."""
+    n = 2 ** levels
+    mfd = large_hypercube_manifold(D, (n,) * D, ctx=ctx)
+    u = sample(mfd, "wave")
+    v = Fun(mfd, Pr, 0)
+    dt = wave_dt(mfd)
+    nsteps = int(round(t1 / dt))
+    omega = math.sqrt(D)
+    # staggered start: v lives at half steps in leapfrog; v(dt/2) ~ v0 + dt/2 * L u0
+    # (symplectic-Euler form used here keeps v at integer steps; first-order in the start-up)
+    wave_leapfrog(mfd, u, v, dt, nsteps)
+    t = nsteps * dt
+    coords = mfd.get_coords()
+    exact = math.cos(math.pi * omega * t) * np.prod(np.sin(np.pi * coords), axis=1)
+    e = u.values - exact
+    return float(np.sqrt(np.sum(e * e) / len(e))), mfd

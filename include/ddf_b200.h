@@ -1,0 +1,205 @@
+/* ddf_b200.h -- C ABI of libddf_b200.so: a B200 (sm_100a) CUDA implementation of
+ * DDF.jl's discrete-exterior-calculus operator hot path.
+ *
+ * The reference (eschnett/DDF.jl, pure Julia) has no FFI seam of its own; the seam
+ * is Julia multiple dispatch on the container inside `Op.values` (src/Ops.jl:18-34)
+ * and `Fun.values` (src/Funs.jl:16-31), with examples/wave-gpu.jl:22-34,121-126 as
+ * the precedent (swap the array type, overload `mul!`).  Every entry point below
+ * names the reference interface it replaces (file:line under /root/reference).
+ * The Julia binding a maintainer would add is shown in INTEGRATION.md; the Python
+ * ctypes binding used by the tests is ddf.jl_b200/_lib.py.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; the message is
+ *    available from ddf_last_error() (thread-local).  Nothing throws or exits.
+ *  - handles are opaque and library-owned; *_destroy releases device memory.
+ *  - host pointers are borrowed for the duration of the call only.
+ *  - indices cross the ABI as the reference stores them: int64, 1-based, CSC
+ *    (colptr[n+1], rowval[nnz], nzval[nnz]); on the device they are 0-based int32.
+ *  - one ctx == one GPU == one process rank (torch.distributed-style launch);
+ *    multi-GPU meshes are slabs joined by NCCL halos (ddf_comm_*, ddf_halo_*).
+ *  - there is NO CPU fallback: without an sm_100 device ddf_ctx_create fails.
+ */
+#ifndef DDF_B200_H
+#define DDF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+typedef struct ddf_ctx ddf_ctx;
+typedef struct ddf_mesh ddf_mesh;
+typedef struct ddf_vec ddf_vec;
+typedef struct ddf_op ddf_op;
+
+/* PrimalDual (src/Manifolds.jl: `@enum PrimalDual Pr Dl`, `!Pr == Dl`). */
+enum { DDF_PR = 1, DDF_DL = 0 };
+/* DualKind (src/Manifolds.jl: BarycentricDuals / CircumcentricDuals). Only the
+ * circumcentric kind is implemented (the barycentric code path of the reference
+ * is dead: called with the wrong arity at Manifolds.jl:649-652). */
+enum { DDF_DUAL_BARYCENTRIC = 0, DDF_DUAL_CIRCUMCENTRIC = 1 };
+/* norms for ddf_vec_norm (LinearAlgebra.norm(x, p); examples/wave.jl:127,162) */
+enum { DDF_NORM_1 = 1, DDF_NORM_2 = 2, DDF_NORM_INF = 0 };
+
+const char* ddf_last_error(void);
+int ddf_version(void);
+
+/* ------------------------------------------------------------------ context */
+int ddf_ctx_create(int device, ddf_ctx** out);
+int ddf_ctx_destroy(ddf_ctx* ctx);
+int ddf_sync(ddf_ctx* ctx);
+/* bytes currently held by the library on this ctx's device */
+int ddf_ctx_bytes_in_use(ddf_ctx* ctx, int64_t* out);
+/* CUDA-event timing on the library stream (bench.py's roofline timer):
+ * tic records an event, toc records another, synchronises and returns ms. */
+int ddf_timer_tic(ddf_ctx* ctx);
+int ddf_timer_toc(ddf_ctx* ctx, double* ms);
+/* number of kernels the library has launched on this ctx since creation */
+int ddf_ctx_launch_count(ddf_ctx* ctx, int64_t* out);
+/* overwrite a >L2-sized scratch buffer (bench hygiene between timed launches) */
+int ddf_flush_l2(ddf_ctx* ctx);
+
+/* ------------------------------------------------------------------- meshes */
+/* Manifold outer constructor input (src/Manifolds.jl:319-330): the top-simplex
+ * table `simplicesD::SparseOp{0,D,One}` as CSC (nvertices x nsimplices, D+1 rows
+ * per column, index-only), vertex coordinates (C x V column-major == V rows of C
+ * doubles) and vertex weights. */
+int ddf_mesh_create(ddf_ctx* ctx, int D, int C, int64_t nvertices,
+                    int64_t nsimplices, const int64_t* colptr,
+                    const int64_t* rowval, const double* coords,
+                    const double* weights, ddf_mesh** out);
+/* large_hypercube_manifold (src/ManifoldConstructors.jl:196-284) generated on the
+ * device, same simplex order / vertex numbering / coords / level weights.
+ * `hdiv` > 0 generalises the reference's equal-nelts assert (:262): coordinates
+ * are i/hdiv and weights levelweight/hdiv^2 (slab meshes of BASELINE config 5);
+ * hdiv == 0 reproduces the reference (requires all nelts equal).
+ * `z0`: offset (in cells) of this slab along the last axis -- added to the last
+ * coordinate before the division, so slab meshes share global coordinates. */
+int ddf_mesh_create_hypercube(ddf_ctx* ctx, int D, const int64_t* nelts,
+                              int64_t hdiv, int64_t z0, ddf_mesh** out);
+int ddf_mesh_destroy(ddf_mesh* mesh);
+/* calc_faces_boundaries for R = D..1 (src/Manifolds.jl:361-368, :717-768):
+ * lexicographic face ranking + signed boundary matrices, bit-exact. */
+int ddf_mesh_assemble(ddf_mesh* mesh);
+/* nsimplices(mfd, R) */
+int ddf_mesh_nsimplices(ddf_mesh* mesh, int R, int64_t* out);
+int ddf_mesh_dims(ddf_mesh* mesh, int* D, int* C);
+/* get_simplices(mfd, R).op (src/Manifolds.jl:434-441): colptr[n_R+1], rowval[(R+1) n_R] */
+int ddf_mesh_get_simplices_csc(ddf_mesh* mesh, int R, int64_t* colptr, int64_t* rowval);
+/* get_boundaries(mfd, R).op (src/Manifolds.jl:443-450): n_{R-1} x n_R, Int8 values */
+int ddf_mesh_get_boundary_csc(ddf_mesh* mesh, int R, int64_t* colptr,
+                              int64_t* rowval, int8_t* nzval);
+/* calc_volumes / weighted calc_dualcoords / circumcentric calc_dualvolumes
+ * (src/Manifolds.jl:834-855, :896-913, :1160-1223) for all R. */
+int ddf_mesh_geometry(ddf_mesh* mesh, int dualkind, int use_weighted_duals);
+int ddf_mesh_get_coords(ddf_mesh* mesh, double* out /* V*C */);
+int ddf_mesh_get_weights(ddf_mesh* mesh, double* out /* V */);
+int ddf_mesh_get_volumes(ddf_mesh* mesh, int R, double* out);
+int ddf_mesh_get_dualvolumes(ddf_mesh* mesh, int R, double* out);
+int ddf_mesh_get_dualcoords(ddf_mesh* mesh, int R, double* out /* n_R*C */);
+/* get_isboundary(mfd, R) as a 0/1 byte mask (src/Manifolds.jl:510-550) */
+int ddf_mesh_get_isboundary(ddf_mesh* mesh, int R, uint8_t* out);
+
+/* ------------------------------------------------------------------ cochains */
+/* Fun{D,P,R}.values (src/Funs.jl:16-31): a device vector of n doubles. */
+int ddf_vec_create(ddf_ctx* ctx, int64_t n, ddf_vec** out);
+int ddf_vec_destroy(ddf_vec* v);
+int ddf_vec_length(ddf_vec* v, int64_t* out);
+int ddf_vec_upload(ddf_vec* v, const double* host);
+int ddf_vec_download(ddf_vec* v, double* host);
+int ddf_vec_fill(ddf_vec* v, double a);
+int ddf_vec_copy(ddf_vec* dst, ddf_vec* src);
+/* sample(Fun{D,Pr,0}, f, mfd) for the fields of the examples, evaluated at the
+ * vertex coordinates on the device (src/Continuum.jl:124-158, R = 0):
+ * kind 0: prod_d sinpi(x_d)  (examples/wave.jl:45 at t=0)
+ * kind 1: sin(x1) cos(x2)    (README.md:63-65)
+ * kind 2: poisson.jl Gaussian rho (examples/poisson.jl:85-92) */
+int ddf_vec_sample(ddf_mesh* mesh, int kind, ddf_vec* out);
+/* uniform [0,1) pseudo-random fill (Funs.jl:80-84 `rand`), counter-based, seeded */
+int ddf_vec_rand(ddf_vec* v, uint64_t seed);
+/* z = a*x + b*y  (Funs.jl:156-188: +, -, scalar *, /); z may alias x or y; y may be NULL when b == 0 */
+int ddf_vec_axpby(double a, ddf_vec* x, double b, ddf_vec* y, ddf_vec* z);
+/* z = x / a (Funs.jl:186-188) */
+int ddf_vec_div(ddf_vec* x, double a, ddf_vec* z);
+/* z = x .* y */
+int ddf_vec_mul(ddf_vec* x, ddf_vec* y, ddf_vec* z);
+int ddf_vec_norm(ddf_vec* v, int kind, double* out);
+int ddf_vec_dot(ddf_vec* x, ddf_vec* y, double* out);
+int ddf_vec_sum(ddf_vec* x, double* out);
+
+/* ----------------------------------------------------------------- operators */
+/* Each returns a new op handle (src/ManifoldOps.jl).  P is DDF_PR / DDF_DL. */
+int ddf_op_boundary(ddf_mesh* mesh, int P, int R, ddf_op** out);   /* ManifoldOps.jl:17-26  */
+int ddf_op_deriv(ddf_mesh* mesh, int P, int R, ddf_op** out);      /* ManifoldOps.jl:40-47  */
+int ddf_op_hodge(ddf_mesh* mesh, int P, int R, ddf_op** out);      /* ManifoldOps.jl:58-68,84-91 */
+int ddf_op_invhodge(ddf_mesh* mesh, int P, int R, ddf_op** out);   /* ManifoldOps.jl:71-82,93-100 */
+int ddf_op_coderiv(ddf_mesh* mesh, int P, int R, ddf_op** out);    /* ManifoldOps.jl:110-121 */
+int ddf_op_laplace(ddf_mesh* mesh, int P, int R, ddf_op** out);    /* ManifoldOps.jl:128-144 */
+int ddf_op_isboundary(ddf_mesh* mesh, int P, int R, ddf_op** out); /* ManifoldOps.jl:31-35  */
+int ddf_op_identity(ddf_mesh* mesh, int R, double a, ddf_op** out);/* Ops.jl:216-220 `one`, scaled */
+int ddf_op_zero(ddf_mesh* mesh, int R1, int R2, ddf_op** out);     /* Ops.jl:152-157 `zero` */
+/* arbitrary Op from the reference's storage: SparseMatrixCSC{Float64,Int} */
+int ddf_op_from_csc(ddf_ctx* ctx, int64_t nrows, int64_t ncols, const int64_t* colptr,
+                    const int64_t* rowval, const double* nzval, ddf_op** out);
+/* Diagonal{Float64} */
+int ddf_op_from_diag(ddf_ctx* ctx, int64_t n, const double* diag, ddf_op** out);
+int ddf_op_destroy(ddf_op* op);
+int ddf_op_shape(ddf_op* op, int64_t* nrows, int64_t* ncols);
+/* Op*Op (Ops.jl:228-232): lazy product C = A*B (applied right to left, diagonal
+ * factors fused into the neighbouring sparse kernel) */
+int ddf_op_compose(ddf_op* A, ddf_op* B, ddf_op** out);
+/* A + b*B (Ops.jl:186-196) */
+int ddf_op_add(ddf_op* A, double b, ddf_op* B, ddf_op** out);
+/* a*A (Ops.jl:198-212) */
+int ddf_op_scale(double a, ddf_op* A, ddf_op** out);
+/* adjoint(A) (Ops.jl:258-260) */
+int ddf_op_adjoint(ddf_op* A, ddf_op** out);
+/* Op*Fun (Ops.jl:273-276): y = A x */
+int ddf_op_apply(ddf_op* A, ddf_vec* x, ddf_vec* y);
+/* Assembled export in the reference's storage, with the Op constructor's
+ * dnz/chop applied (Ops.jl:36-58).  Call with NULL arrays to query nnz. */
+int ddf_op_to_csc(ddf_op* A, int64_t* nnz, int64_t* colptr, int64_t* rowval, double* nzval);
+
+/* ---------------------------------------------------------------------- wave */
+/* examples/wave.jl:87-100: dU = F U, i.e. du = (E-B) udot, dudot = (E-B)(L u). */
+int ddf_wave_rhs(ddf_mesh* mesh, ddf_vec* u, ddf_vec* udot, ddf_vec* du, ddf_vec* dudot);
+/* examples/wave.jl:106,118: dt = minimum(vol_1)/2 */
+int ddf_wave_dt(ddf_mesh* mesh, double* dt);
+/* north_star's fused leapfrog on the same operators (not in the reference):
+ *   v += dt (1-b) .* (L u);  u += dt (1-b) .* v     repeated nsteps times,
+ * one kernel per step, L applied matrix-free from the vertex adjacency. */
+int ddf_wave_leapfrog(ddf_mesh* mesh, ddf_vec* u, ddf_vec* v, double dt, int nsteps);
+/* one leapfrog step timed alone is exposed through ddf_timer_*; the algorithmic
+ * byte count of a step (E*16 + V*41) is returned here for reporting */
+int ddf_wave_step_bytes(ddf_mesh* mesh, int64_t* algorithmic, int64_t* format_bytes);
+
+/* --------------------------------------------------------- multi-GPU (NCCL) */
+/* ncclGetUniqueId: 128 bytes, created on rank 0 and broadcast by the host side */
+int ddf_comm_unique_id(void* id128);
+int ddf_comm_init(ddf_ctx* ctx, int nranks, int rank, const void* id128);
+int ddf_comm_destroy(ddf_ctx* ctx);
+/* Slab decomposition of the distributed wave step: this rank's
+ * mesh is a slab along the slowest axis with `plane` vertices per plane; its first
+ * `ghost_lo` and last `ghost_hi` vertex planes are ghosts owned by rank-1 / rank+1
+ * (0 at the domain ends).  Owned rows are the planes in between. */
+int ddf_mesh_set_halo(ddf_mesh* mesh, int64_t plane, int64_t ghost_lo, int64_t ghost_hi);
+/* fused leapfrog on the owned rows + one-plane halo exchange of u per step with
+ * ncclSend/ncclRecv to rank-1 / rank+1, overlapped with the interior rows. */
+int ddf_wave_leapfrog_dist(ddf_mesh* mesh, ddf_vec* u, ddf_vec* v, double dt, int nsteps);
+/* halo exchange of a vertex cochain alone (fills the ghost planes next to the owned rows) */
+int ddf_halo_exchange(ddf_mesh* mesh, ddf_vec* u);
+/* sum / max all-reduce of a host scalar across ranks (norms, CFL minimum) */
+int ddf_comm_allreduce(ddf_ctx* ctx, double* value, int op /* 0 sum, 1 max, 2 min */);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDF_B200_H */

@@ -1,0 +1,390 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on
+the same inputs.  Integer / index work must be bit-exact; Float64 operator
+arithmetic is bit-exact given identical geometry and within 1e-12 relative end to
+end (north_star's tolerance; the geometry kernels evaluate the third-party
+DifferentialForms / StaticArrays algebra in a different order).
+
+Mirrors the reference's test strategy (test/test-manifolds.jl, test-manifoldops.jl,
+test-ops.jl): manifold zoo x algebraic identities, plus element-wise comparison
+with the oracle that the reference cannot offer.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import ddf_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12   # north_star: "Float64 results must match ... within 1e-12 relative"
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = max(np.max(np.abs(b)) if b.size else 0.0, 1e-300)
+    return float(np.max(np.abs(a - b)) / scale) if a.size else 0.0
+
+
+def make_pair(ddf, ctx, kind):
+    """(oracle manifold, device manifold) built from the same input."""
+    if kind.startswith("kuhn"):
+        D, n = int(kind[4]), int(kind.split("n")[-1])
+        om = o.large_hypercube_manifold(D, (n,) * D)
+        dm = ddf.large_hypercube_manifold(D, (n,) * D, ctx=ctx)      # on-device generator
+        return om, dm
+    if kind.startswith("refined"):
+        D, lv = int(kind[7]), int(kind.split("l")[-1])
+        om = o.refined_simplex_manifold(D, lv)
+        dm = ddf.Manifold.from_simplices(om.name, om.simplices[om.D], om.coords, om.weights, ctx=ctx)
+        return om, dm
+    if kind.startswith("simplex"):
+        D = int(kind[7])
+        om = o.simplex_manifold(D)
+        dm = ddf.Manifold.from_simplices(om.name, om.simplices[om.D], om.coords, om.weights, ctx=ctx)
+        return om, dm
+    if kind == "kuhn3slab":
+        om = o.large_hypercube_manifold(3, (4, 4, 6), h_div=4)
+        dm = ddf.large_hypercube_manifold(3, (4, 4, 6), ctx=ctx, hdiv=4)
+        return om, dm
+    raise KeyError(kind)
+
+
+ZOO = ["kuhn1n4", "kuhn2n4", "kuhn2n16", "kuhn3n2", "kuhn3n4", "kuhn3n8", "refined2l1", "refined2l4", "refined3l1",
+       "simplex1", "simplex2", "simplex3", "kuhn3slab"]
+GEO_ZOO = ["kuhn1n4", "kuhn2n4", "kuhn2n16", "kuhn3n4", "kuhn3n8", "refined2l4", "simplex2", "simplex3", "kuhn3slab"]
+
+
+@pytest.fixture(scope="module")
+def pairs(ddf, ctx):
+    cache = {}
+
+    def get(kind):
+        if kind not in cache:
+            cache[kind] = make_pair(ddf, ctx, kind)
+        return cache[kind]
+    return get
+
+
+# ------------------------------------------------------------------ A1/A2 assembly
+@pytest.mark.parametrize("kind", ZOO)
+def test_assembly_bit_exact(pairs, kind):
+    om, dm = pairs(kind)
+    for R in range(om.D + 1):
+        assert dm.nsimplices(R) == om.nsimplices(R)
+        colptr, rowval = dm.get_simplices_csc(R)
+        ocp, orv = o.simplices_julia_csc(om.simplices[R])
+        assert np.array_equal(colptr, ocp) and np.array_equal(rowval, orv), f"simplices R={R}"
+    for R in range(1, om.D + 1):
+        colptr, rowval, nzval = dm.get_boundaries_csc(R)
+        ocp, orv, onz = o.to_julia_csc(om.boundaries[R])
+        assert np.array_equal(colptr, ocp), f"boundary colptr R={R}"
+        assert np.array_equal(rowval, orv), f"boundary rowval R={R}"
+        assert np.array_equal(nzval, onz) and nzval.dtype == np.int8, f"boundary nzval R={R}"
+
+
+def test_generator_matches_oracle_tables(ddf, ctx):
+    for D, n in ((2, 6), (3, 4)):
+        simp, coords, weights = o.large_hypercube_tables(D, (n,) * D)
+        dm = ddf.large_hypercube_manifold(D, (n,) * D, ctx=ctx)
+        assert np.array_equal(dm.get_simplices(D), simp)          # same simplex ORDER, not just the same set
+        assert np.array_equal(dm.get_coords(), coords)
+        assert np.array_equal(dm.get_weights(), weights)
+
+
+def test_uploaded_equals_generated(ddf, ctx):
+    simp, coords, weights = o.large_hypercube_tables(3, (4, 4, 4))
+    a = ddf.Manifold.from_simplices("up", simp, coords, weights, ctx=ctx)
+    b = ddf.large_hypercube_manifold(3, (4, 4, 4), ctx=ctx)
+    for R in range(1, 4):
+        for x, y in zip(a.get_boundaries_csc(R), b.get_boundaries_csc(R)):
+            assert np.array_equal(x, y)
+
+
+def test_dd_zero_on_device(ddf, ctx, pairs):
+    """d_{k+1} d_k x == 0 exactly for integer-valued x (test-manifoldops.jl:60-68)."""
+    for kind in ("kuhn3n4", "refined2l4", "simplex3"):
+        om, dm = pairs(kind)
+        rng = np.random.default_rng(0)
+        for k in range(om.D - 1):
+            x = ddf.Fun(dm, ddf.Pr, k, rng.integers(-50, 50, om.nsimplices(k)).astype(np.float64))
+            y = ddf.deriv(ddf.Pr, k + 1, dm) * (ddf.deriv(ddf.Pr, k, dm) * x)
+            assert not np.any(y.values)
+        for k in range(om.D, 1, -1):
+            x = ddf.Fun(dm, ddf.Pr, k, rng.integers(-50, 50, om.nsimplices(k)).astype(np.float64))
+            y = ddf.boundary(ddf.Pr, k - 1, dm) * (ddf.boundary(ddf.Pr, k, dm) * x)
+            assert not np.any(y.values)
+
+
+# --------------------------------------------------------------------- A3/A4 apply
+@pytest.mark.parametrize("kind", ZOO)
+def test_deriv_apply_bit_exact(ddf, pairs, kind):
+    om, dm = pairs(kind)
+    rng = np.random.default_rng(1)
+    for k in range(om.D):
+        x = rng.standard_normal(om.nsimplices(k))
+        y = (ddf.deriv(ddf.Pr, k, dm) * ddf.Fun(dm, ddf.Pr, k, x)).values
+        assert np.array_equal(y, o.apply_deriv(o.Pr, k, om, x)), f"primal d_{k}"
+    for k in range(1, om.D + 1):
+        x = rng.standard_normal(om.nsimplices(k))
+        y = (ddf.deriv(ddf.Dl, k, dm) * ddf.Fun(dm, ddf.Dl, k, x)).values
+        assert np.array_equal(y, o.apply_deriv(o.Dl, k, om, x)), f"dual d_{k}"
+        yb = (ddf.boundary(ddf.Pr, k, dm) * ddf.Fun(dm, ddf.Pr, k, x)).values
+        assert np.array_equal(yb, o.spmv_csc(om.boundaries[k], x))
+    for k in range(om.D):
+        x = rng.standard_normal(om.nsimplices(k))
+        yb = (ddf.boundary(ddf.Dl, k, dm) * ddf.Fun(dm, ddf.Dl, k, x)).values
+        assert np.array_equal(yb, o.spmv_adjoint_csc(om.boundaries[k + 1], x))
+
+
+def test_deriv_apply_ragged_sizes(ddf, ctx):
+    """rows % 4 != 0 exercises the scalar tail of the 4-rows-per-thread kernel."""
+    for n in (2, 6, 10):
+        om = o.large_hypercube_manifold(2, (n, n))
+        dm = ddf.large_hypercube_manifold(2, (n, n), ctx=ctx)
+        rng = np.random.default_rng(n)
+        for k in range(2):
+            x = rng.standard_normal(om.nsimplices(k))
+            y = (ddf.deriv(ddf.Pr, k, dm) * ddf.Fun(dm, ddf.Pr, k, x)).values
+            assert np.array_equal(y, o.apply_deriv(o.Pr, k, om, x))
+
+
+# ------------------------------------------------------------------- A5-A8 geometry
+@pytest.mark.parametrize("kind", GEO_ZOO)
+def test_geometry_parity(pairs, kind):
+    om, dm = pairs(kind)
+    for R in range(om.D + 1):
+        assert relerr(dm.get_volumes(R), o.calc_volumes(om, R)) <= RTOL, f"vol R={R}"
+        assert relerr(dm.get_dualcoords(R), o.calc_dualcoords(om, R)) <= 1e-11, f"dualcoords R={R}"
+        dv, odv = dm.get_dualvolumes(R), o.calc_dualvolumes(om, R)
+        assert relerr(dv, odv) <= 1e-11, f"dualvol R={R}"
+    assert np.all(dm.get_volumes(0) == 1) and np.all(dm.get_dualvolumes(om.D) == 1)
+
+
+@pytest.mark.parametrize("kind", GEO_ZOO)
+def test_isboundary_bit_exact(pairs, kind):
+    om, dm = pairs(kind)
+    for R in range(om.D):
+        assert np.array_equal(dm.get_isboundary(R), o.calc_isboundary(om, R)), f"isboundary R={R}"
+
+
+def with_device_geometry(om, dm):
+    """Give the oracle the device's vol / dualvol so that the OPERATOR arithmetic
+    can be compared bit for bit (geometry itself is compared in test_geometry_parity)."""
+    for R in range(om.D + 1):
+        om._cache[("vol", R)] = dm.get_volumes(R)
+        om._cache[("dualvol", R, True)] = dm.get_dualvolumes(R)
+    return om
+
+
+@pytest.mark.parametrize("kind", ["kuhn2n4", "kuhn3n4", "refined2l4", "simplex3"])
+def test_hodge_apply_bit_exact(ddf, pairs, kind):
+    om, dm = pairs(kind)
+    om = with_device_geometry(om, dm)
+    rng = np.random.default_rng(2)
+    for R in range(om.D + 1):
+        x = rng.standard_normal(om.nsimplices(R))
+        for P in (o.Pr, o.Dl):
+            y = (ddf.hodge(P, R, dm) * ddf.Fun(dm, P, R, x)).values
+            assert np.array_equal(y, o.hodge_diag(P, R, om) * x)
+            y = (ddf.invhodge(P, R, dm) * ddf.Fun(dm, P, R, x)).values
+            assert np.array_equal(y, o.invhodge_diag(P, R, om) * x)
+
+
+# ---------------------------------------------------------- A9 coderiv / laplace
+@pytest.mark.parametrize("kind", ["kuhn2n4", "kuhn3n4", "refined2l4", "simplex3", "kuhn3slab"])
+def test_coderiv_assembled_bit_exact(ddf, pairs, kind):
+    om, dm = pairs(kind)
+    om = with_device_geometry(om, dm)
+    for P in (o.Pr, o.Dl):
+        dR = 1 if P else -1
+        for R in range(om.D + 1):
+            if not (0 <= R - dR <= om.D):
+                continue
+            A = ddf.coderiv(P, R, dm).to_csc()
+            B = o.coderiv(P, R, om)
+            assert A.shape == B.shape
+            assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices), (P, R)
+            assert np.array_equal(A.data, B.data), (P, R)
+
+
+@pytest.mark.parametrize("kind", ["kuhn2n4", "kuhn2n16", "kuhn3n4", "refined2l4", "simplex3", "kuhn3slab"])
+def test_laplace0_bit_exact(ddf, pairs, kind):
+    om, dm = pairs(kind)
+    om = with_device_geometry(om, dm)
+    L = o.laplace(o.Pr, 0, om)
+    A = ddf.laplace(ddf.Pr, 0, dm).to_csc()
+    assert np.array_equal(A.indptr, L.indptr) and np.array_equal(A.indices, L.indices)
+    assert np.array_equal(A.data, L.data)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(om.nsimplices(0))
+    y = (ddf.laplace(ddf.Pr, 0, dm) * ddf.Fun(dm, ddf.Pr, 0, x)).values
+    assert np.array_equal(y, o.spmv_csc(L, x))
+
+
+@pytest.mark.parametrize("kind", ["kuhn2n4", "kuhn3n4", "refined2l4"])
+def test_laplace_end_to_end_tolerance(ddf, pairs, kind):
+    """Independent geometry on both sides: 1e-12-class agreement (north_star)."""
+    om, dm = pairs(kind)
+    om._cache.clear()
+    L = o.laplace(o.Pr, 0, om)
+    u = o.wave_u0(om.coords) if kind.startswith("kuhn") else o.readme_field(om.coords)
+    y = (ddf.laplace(ddf.Pr, 0, dm) * ddf.Fun(dm, ddf.Pr, 0, u)).values
+    assert relerr(y, o.spmv_csc(L, u)) <= 1e-11
+
+
+@pytest.mark.parametrize("kind", ["kuhn2n4", "kuhn3n4", "simplex3"])
+def test_laplace_general_R(ddf, pairs, kind):
+    """laplace(P,R) for R > 0 (both terms), lazily composed on the device, against the
+    oracle's assembled operator (association differs: tolerance)."""
+    om, dm = pairs(kind)
+    om = with_device_geometry(om, dm)
+    rng = np.random.default_rng(4)
+    for P in (o.Pr, o.Dl):
+        for R in range(om.D + 1):
+            if P and R == 0:
+                continue
+            x = rng.standard_normal(om.nsimplices(R))
+            y = (ddf.laplace(P, R, dm) * ddf.Fun(dm, P, R, x)).values
+            ref = o.spmv_csc(o.laplace(P, R, om), x)
+            assert relerr(y, ref) <= 1e-12, (P, R)
+
+
+# ------------------------------------------------------------------ Op / Fun algebra
+def test_op_fun_algebra(ddf, pairs):
+    """Ring / vector-space laws of test-ops.jl:183-260 and test-funs.jl on the device."""
+    om, dm = pairs("kuhn3n4")
+    rng = np.random.default_rng(5)
+    f = ddf.Fun(dm, ddf.Pr, 0, rng.integers(-9, 9, om.nsimplices(0)).astype(float))
+    g = ddf.Fun(dm, ddf.Pr, 0, rng.integers(-9, 9, om.nsimplices(0)).astype(float))
+    d0, d1 = ddf.deriv(ddf.Pr, 0, dm), ddf.deriv(ddf.Pr, 1, dm)
+    assert (d0 * (f + g)) == (d0 * f + d0 * g)                  # A*(f+g) == A*f + A*g  (integers: exact)
+    assert ((d1 * d0) * f) == (d1 * (d0 * f))                   # (F*A)*f == F*(A*f)
+    assert ((2.0 * d0) * f) == (2.0 * (d0 * f))
+    assert ((d0 + d0) * f) == ((2.0 * d0) * f)
+    assert ((d0 - d0) * f).norm(np.inf) == 0
+    assert (-(d0)) * f == (d0 * (-f))
+    assert (f - g) + g == f and (f * 2.0) / 2.0 == f
+    assert d0.adjoint().shape == (om.nsimplices(0), om.nsimplices(1))
+    h = ddf.Fun(dm, ddf.Pr, 1, rng.integers(-9, 9, om.nsimplices(1)).astype(float))
+    # <d0 f, h> == <f, d0' h> exactly on integers
+    assert (d0 * f).dot(h) == f.dot(d0.adjoint() * h)
+    E, B = ddf.one(ddf.Pr, 0, dm), ddf.isboundary(ddf.Pr, 0, dm)
+    m = 1.0 - om_isb(om)
+    assert np.array_equal(((E - B) * f).values, m * f.values)   # wave.jl:93
+    with pytest.raises(ddf.DDFError):
+        d1 * f                                                   # type mismatch (R)
+    with pytest.raises(ddf.DDFError):
+        ddf.deriv(ddf.Pr, om.D, dm)                              # @assert 0 <= R+s <= D
+
+
+def om_isb(om):
+    return o.calc_isboundary(om, 0).astype(np.float64)
+
+
+def test_from_csc_bit_exact(ddf, pairs):
+    om, dm = pairs("kuhn2n4")
+    rng = np.random.default_rng(6)
+    n0, n1 = om.nsimplices(0), om.nsimplices(1)
+    A = sp.random(n1, n0, density=0.2, random_state=7, format="csc")
+    op = ddf.op_from_csc(dm, ddf.Pr, 1, ddf.Pr, 0, A)
+    x = rng.standard_normal(n0)
+    y = (op * ddf.Fun(dm, ddf.Pr, 0, x)).values
+    assert np.array_equal(y, o.spmv_csc(A, x))
+    B = op.to_csc()
+    A.sort_indices()
+    assert np.array_equal(B.indptr, A.indptr) and np.array_equal(B.indices, A.indices) and np.array_equal(B.data, A.data)
+    yt = (op.adjoint() * ddf.Fun(dm, ddf.Pr, 1, rng.standard_normal(n1))).values
+    assert yt.shape == (n0,)
+
+
+def test_export_deriv_and_hodge(ddf, pairs):
+    om, dm = pairs("kuhn3n4")
+    for k in range(om.D):
+        A = ddf.deriv(ddf.Pr, k, dm).to_csc()
+        B = o.deriv(o.Pr, k, om).astype(np.float64)
+        B.sort_indices()
+        assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
+        A = ddf.deriv(ddf.Dl, k + 1, dm).to_csc()
+        B = o.deriv(o.Dl, k + 1, om).astype(np.float64)
+        B.sort_indices()
+        assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
+
+
+# ------------------------------------------------------------------------ A10 wave
+@pytest.mark.parametrize("kind", ["kuhn2n4", "kuhn2n16", "kuhn3n4", "kuhn3n8"])
+def test_wave_rhs_and_leapfrog_bit_exact(ddf, pairs, kind):
+    om, dm = pairs(kind)
+    om = with_device_geometry(om, dm)
+    u0 = o.wave_u0(om.coords)
+    rng = np.random.default_rng(8)
+    v0 = rng.standard_normal(len(u0))
+    du, dv = ddf.wave_rhs(dm, ddf.Fun(dm, ddf.Pr, 0, u0), ddf.Fun(dm, ddf.Pr, 0, v0))
+    odu, odv = o.wave_rhs(om, u0, v0)
+    assert np.array_equal(du.values, odu) and np.array_equal(dv.values, odv)
+    dt = ddf.wave_dt(dm)
+    assert dt == o.wave_dt(om)
+    u, v = ddf.Fun(dm, ddf.Pr, 0, u0), ddf.Fun(dm, ddf.Pr, 0, np.zeros_like(u0))
+    ddf.wave_leapfrog(dm, u, v, dt, 7)
+    ou, ov = o.wave_leapfrog(om, u0, np.zeros_like(u0), dt, 7)
+    assert np.array_equal(u.values, ou) and np.array_equal(v.values, ov)
+
+
+def test_wave_sample_and_convergence(ddf, ctx):
+    """Device-sampled initial data and second-order convergence of the leapfrog
+    solution (the oracle restatement of wave.jl is second order)."""
+    errs = []
+    for lv in (3, 4, 5):
+        e, mfd = ddf.wave(2, lv, ctx=ctx, t1=0.5)
+        errs.append(e)
+    assert errs[1] < errs[0] / 2.5 and errs[2] < errs[1] / 2.5, errs
+    m = ddf.large_hypercube_manifold(2, (8, 8), ctx=ctx)
+    assert relerr(ddf.sample(m, "wave").values, o.wave_u0(m.get_coords())) < 1e-14
+    assert relerr(ddf.sample(m, "readme").values, o.readme_field(m.get_coords())) < 1e-14
+    assert relerr(ddf.sample(m, "poisson_rho").values, o.poisson_rho(m.get_coords())) < 1e-13
+
+
+# --------------------------------------------------------- size-independent checks
+def test_large_mesh_properties(ddf, ctx):
+    """3D Kuhn n=64 (1.57e6 tets): closed-form counts, dd = 0, volume sums,
+    d applied to coordinate functions, L(1) = 0 on interior rows."""
+    n = 64
+    m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
+    assert [m.nsimplices(R) for R in range(4)] == [(n + 1) ** 3, 7 * n ** 3 + 9 * n ** 2 + 3 * n,
+                                                   12 * n ** 3 + 6 * n ** 2, 6 * n ** 3]
+    rng = np.random.default_rng(9)
+    x = ddf.Fun(m, ddf.Pr, 0, rng.integers(-99, 99, m.nsimplices(0)).astype(float))
+    d0, d1, d2 = (ddf.deriv(ddf.Pr, k, m) for k in range(3))
+    assert (d1 * (d0 * x)).norm(np.inf) == 0
+    y = ddf.Fun(m, ddf.Pr, 1, rng.integers(-99, 99, m.nsimplices(1)).astype(float))
+    assert (d2 * (d1 * y)).norm(np.inf) == 0
+    assert abs(m.get_volumes(3).sum() - 1) < 1e-12 and abs(m.get_dualvolumes(0).sum() - 1) < 1e-12
+    for R in range(4):
+        assert m.get_dualvolumes(R).min() > 0
+    one = ddf.Fun(m, ddf.Pr, 0, np.ones(m.nsimplices(0)))
+    L1 = (ddf.laplace(ddf.Pr, 0, m) * one).values
+    scale = n * n
+    assert np.max(np.abs(L1)) <= 1e-12 * scale * 64
+    # linearity of the fused step: leapfrog(a u) == a leapfrog(u) for a power of two
+    u0 = ddf.sample(m, "wave")
+    u1, v1 = u0.copy(), ddf.Fun(m, ddf.Pr, 0)
+    u2, v2 = u0 * 4.0, ddf.Fun(m, ddf.Pr, 0)
+    dt = ddf.wave_dt(m)
+    ddf.wave_leapfrog(m, u1, v1, dt, 5)
+    ddf.wave_leapfrog(m, u2, v2, dt, 5)
+    assert np.array_equal(u2.values, 4.0 * u1.values)
+
+
+def test_empty_and_tiny(ddf, ctx):
+    """Edge cases of the reference's zoo: a single simplex per D and ragged tails."""
+    for D in (1, 2, 3):
+        om = o.simplex_manifold(D)
+        dm = ddf.Manifold.from_simplices("s", om.simplices[D], om.coords, ctx=ctx)
+        for R in range(D + 1):
+            assert dm.nsimplices(R) == len(list(__import__("itertools").combinations(range(D + 1), R + 1)))
+    with pytest.raises(ddf.DDFError):
+        ddf.Manifold.from_simplices("bad", np.array([[0, 0, 1]]), np.zeros((2, 2)), ctx=ctx)   # repeated vertex
+    with pytest.raises(ddf.DDFError):
+        ddf.Manifold.from_simplices("bad", np.array([[0, 1, 5]]), np.zeros((3, 2)), ctx=ctx)   # out of range
+    with pytest.raises(ddf.DDFError):
+        ddf.large_hypercube_manifold(2, (3, 3), ctx=ctx)                                        # odd nelts
