@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DEC operator hot path (BASELINE.json metric:
+"cochain DOF updates/sec and achieved HBM GB/s for d_k / star_k SpMV").
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (restated, see below)
+
+A "step" = one pass of the hot path over one batch of synthetic cochains on the 3D
+Kuhn mesh of BASELINE config 4 (large_hypercube n=256: 1.0066e8 tets):
+    y1 = d0 x0,  y2 = d1 x1,  y3 = d2 x2,  z_k = star_k x_k  (k = 0..3)
+N > 1: weak scaling -- one C4-sized z-slab per GPU (+2 ghost cell layers per interior
+face); the d_k/star_k applies need no collective, the fused wave step
+(reported in "wave") exchanges one ghost plane per neighbour per step over NCCL.
+
+The reference arm: DDF.jl is Julia and cannot run here (no julia binary, no network),
+so `--impl reference` times oracle/ddf_oracle.c -- a C restatement of Julia
+SparseArrays' `mul!` loops on the reference's own storage (Int64 CSC + Int8/Float64
+values), single-threaded like Julia's sparse mul! -- on a bounded sample (3D Kuhn
+n=64) of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cochain DOF updates/sec (d_k + star_k apply, 3D Kuhn mesh)"
+UNIT = "DOF/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dk_bytes(n_rows, n_cols, k):
+    """Algorithmic bytes of y = d_k x: rows*(4(k+2)+8) + 8*cols."""
+    return n_rows * (4 * (k + 2) + 8) + 8 * n_cols
+
+
+def owned_counts(ddf, ctx, nelts_xy, slab, local_counts):
+    """k-simplices owned by this rank = those whose smallest vertex lies in an owned plane.
+    Counted from two tiny auxiliary meshes: one 2-layer slab and one in-plane 2D mesh."""
+    if slab is None:
+        return list(local_counts)
+    two = ddf.large_hypercube_manifold(3, tuple(nelts_xy) + (2,), ctx=ctx, hdiv=nelts_xy[0])
+    flat = ddf.large_hypercube_manifold(2, tuple(nelts_xy), ctx=ctx)
+    c2 = [two.nsimplices(k) for k in range(4)]
+    p = [flat.nsimplices(k) for k in range(3)] + [0]
+    two.close()
+    flat.close()
+
+    def S(L, k):        # k-simplices of a slab with L cell layers
+        return p[k] + (L // 2) * (c2[k] - p[k])
+    L = slab.z_own_hi - slab.z_own_lo - (1 if slab.rank == slab.nranks - 1 else 0)
+    out = []
+    for k in range(4):
+        own = S(L, k) - p[k]
+        if slab.rank == slab.nranks - 1:
+            own += p[k]
+        out.append(own)
+    return out
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_reference_pass(n_ref, seconds_target, threads_omp=False):
+    """Time the C restatement of the reference's CPU path on a bounded sample: 3D Kuhn n=n_ref,
+    the same 7 operator applications, reference storage.  Returns dict(value, unit, cores, kind, sample)."""
+    import c_oracle
+    import ddf_oracle as o
+    t0 = time.time()
+    simp, coords, weights = o.large_hypercube_tables(3, (n_ref,) * 3)
+    tables = {3: simp}
+    csc = {}
+    for R in (3, 2, 1):
+        faces, cp, rv, nz = c_oracle.calc_faces_boundaries(tables[R])
+        tables[R - 1] = faces
+        csc[R] = (cp, rv, nz)
+    t_asm = time.time() - t0
+    n = [coords.shape[0]] + [tables[R].shape[0] for R in (1, 2, 3)]
+    rng = np.random.default_rng(0)
+    x = [rng.random(nk) for nk in n]
+    # the diagonal's values do not change the cost of Diagonal*Vector; use the oracle's real stars where cheap
+    star = [rng.random(nk) + 0.5 for nk in n]
+    dof = 2 * (n[1] + n[2] + n[3]) + n[0]
+
+    def one_pass():
+        for k in range(3):
+            cp, rv, nz = csc[k + 1]
+            c_oracle.spmv_adjoint_csc_i8(cp, rv, nz, x[k], omp=threads_omp)
+        for k in range(4):
+            c_oracle.diag_mul(star[k], x[k])
+
+    one_pass()
+    t1 = time.time()
+    reps = 0
+    while True:
+        one_pass()
+        reps += 1
+        el = time.time() - t1
+        if el >= seconds_target or reps >= 200:
+            break
+    per = el / reps
+    return {"value": dof / per, "unit": UNIT, "cores": (os.cpu_count() if threads_omp else 1), "kind": "port",
+            "sample": f"3D Kuhn n={n_ref} ({n[3]} tets, {dof} DOF/step), {reps} passes in {el:.1f}s, C restatement of "
+                      f"SparseArrays mul! on Int64-CSC/Int8 storage; assembly restatement took {t_asm:.1f}s",
+            "ms_per_step": per * 1e3, "dof_per_step": dof}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # warmup W passes + K timed steps, each step a bounded sample (n=64)
+    import c_oracle
+    c_oracle.load()
+    res = cpu_reference_pass(args.n_ref, seconds_target=min(60.0, 2.0 * max(args.steps, 1)))
+    omp = cpu_reference_pass(args.n_ref, seconds_target=5.0, threads_omp=True)
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D Kuhn large_hypercube n={args.n_ref} bounded sample of config 4 "
+                                   "(d0,d1,d2 + star0..3 apply)", "reference_runnable": False,
+                       "note": "DDF.jl is Julia; no julia binary in the image -> C restatement of its SparseArrays "
+                               "mul! loops on the reference's storage, 1 thread like Julia's sparse mul!"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "omp_allcores_crosscheck": {"value": omp["value"], "cores": omp["cores"]},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import ddf.jl_b200 as ddf
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    N = args.gpus
+    if world != N:
+        if N == 1 and world == 1:
+            pass
+        else:
+            raise SystemExit(f"--gpus {N} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {N}")
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if N > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = ddf.Context(local_rank)
+    ddf.set_default_context(ctx)
+    if N > 1:
+        ddf.dist.init_comm(ctx)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n = args.n
+    t_setup0 = time.time()
+    slab = None
+    if N == 1:
+        mfd = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx, assemble=False)
+    else:
+        mfd, slab = ddf.dist.slab_hypercube(3, (n, n, n * N), ctx)
+    ctx.sync()
+    ctx.tic()
+    ddf._lib.call("ddf_mesh_assemble", mfd._h)
+    asm_ms = ctx.toc()
+    mfd._geometry()
+    ctx.sync()
+    cnt = [mfd.nsimplices(k) for k in range(4)]
+    own = owned_counts(ddf, ctx, (n, n), slab, cnt)
+    d = [ddf.deriv(ddf.Pr, k, mfd) for k in range(3)]
+    h = [ddf.hodge(ddf.Pr, k, mfd) for k in range(4)]
+    x = [ddf.rand_fun(mfd, ddf.Pr, k, seed=k + 1) for k in range(4)]
+    y = [ddf.Fun(mfd, ddf.Pr, k + 1) for k in range(3)]
+    z = [ddf.Fun(mfd, ddf.Dl, k) for k in range(4)]
+    setup_s = time.time() - t_setup0
+
+    def step(record=None):
+        for k in range(3):
+            if record is not None and k == 1:
+                ctx.event_record(record)
+            d[k].apply(x[k], y[k])
+            if record is not None and k == 1:
+                ctx.event_record(record + 1)
+        for k in range(4):
+            h[k].apply(x[k], z[k])
+
+    K, W = args.steps, args.warmup
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ctx.tic()
+    for s in range(K):
+        step(record=2 * s)
+    ms_total = ctx.toc()
+    barrier()
+    launches = ctx.launch_count() - l0
+    ms_step = max_over_ranks(ms_total / K)
+    d1_ms = float(np.mean([ctx.event_elapsed(2 * s, 2 * s + 1) for s in range(K)]))
+    d1_ms = max_over_ranks(d1_ms)
+    dof_local = 2 * (own[1] + own[2] + own[3]) + own[0]
+    dof_total = sum_over_ranks(float(dof_local))
+    value = dof_total / (ms_step * 1e-3)
+
+    # per-operator breakdown (each timed alone, back to back, inputs >> L2)
+    breakdown = {}
+    peak, peak_src = load_peaks()
+
+    def time_op(fn, reps):
+        fn()
+        ctx.sync()
+        ctx.tic()
+        for _ in range(reps):
+            fn()
+        return ctx.toc() / reps
+    for k in range(3):
+        ms = time_op(lambda k=k: d[k].apply(x[k], y[k]), K)
+        b = dk_bytes(cnt[k + 1], cnt[k], k)
+        breakdown[f"d{k}"] = {"ms": ms, "GBps": b / ms * 1e-6, "frac": b / ms * 1e-6 / peak, "bytes": b}
+    for k in range(4):
+        ms = time_op(lambda k=k: h[k].apply(x[k], z[k]), K)
+        b = 24 * cnt[k]
+        breakdown[f"star{k}"] = {"ms": ms, "GBps": b / ms * 1e-6, "frac": b / ms * 1e-6 / peak, "bytes": b}
+
+    # fused wave step (leapfrog; halo exchange over NCCL when N > 1)
+    u = ddf.sample(mfd, "wave")
+    v = ddf.Fun(mfd, ddf.Pr, 0)
+    dt = ddf.wave_dt(mfd)
+    if N > 1:
+        dt = ctx.allreduce(dt, "min")
+    ddf.wave_leapfrog(mfd, u, v, dt, W)
+    barrier()
+    ctx.tic()
+    ddf.wave_leapfrog(mfd, u, v, dt, K)
+    wave_ms = max_over_ranks(ctx.toc() / K)
+    barrier()
+    alg, fmt = ddf.wave_step_bytes(mfd)
+    if slab is not None:     # owned share of the local slab
+        frac_own = own[0] / cnt[0]
+        alg, fmt = int(alg * frac_own), int(fmt * frac_own)
+    unorm = u.norm(np.inf)
+    wave = {"ms_per_step": wave_ms, "vertex_updates_per_s": sum_over_ranks(float(own[0])) / (wave_ms * 1e-3),
+            "algorithmic_bytes": alg, "format_bytes": fmt, "GBps": alg / wave_ms * 1e-6,
+            "frac": alg / wave_ms * 1e-6 / peak, "dt": dt, "u_inf_after": unorm}
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hx = [torch.empty(c, dtype=torch.float64).pin_memory() for c in cnt]
+        for k in range(4):
+            hx[k].copy_(torch.from_numpy(np.random.default_rng(k).random(cnt[k])))
+        hy = [torch.empty(cnt[k + 1], dtype=torch.float64).pin_memory() for k in range(3)]
+        hz = [torch.empty(c, dtype=torch.float64).pin_memory() for c in cnt]
+        C = __import__("ctypes")
+
+        def ptr(t):
+            return C.cast(t.data_ptr(), C.POINTER(C.c_double))
+
+        def e2e_step():
+            for k in range(4):
+                ddf._lib.call("ddf_vec_upload", x[k]._h, ptr(hx[k]))
+            for k in range(3):
+                d[k].apply(x[k], y[k])
+                ddf._lib.call("ddf_vec_download", y[k]._h, ptr(hy[k]))
+            for k in range(4):
+                h[k].apply(x[k], z[k])
+                ddf._lib.call("ddf_vec_download", z[k]._h, ptr(hz[k]))
+        e2e_step()
+        barrier()
+        Ke = max(1, min(K, args.e2e_steps))
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            e2e_step()
+        ctx.sync()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) / Ke * 1e3)
+        barrier()
+        h2d = 8 * sum(cnt)
+        d2h = 8 * (cnt[1] + cnt[2] + cnt[3] + sum(cnt))
+        e2e = {"value": dof_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": Ke,
+               "api": "ddf_vec_upload -> ddf_op_apply -> ddf_vec_download (pinned host buffers)"}
+
+    cpu = None
+    if rank == 0 and N == 1 and not args.no_cpu:
+        cpu = cpu_reference_pass(args.n_ref, seconds_target=12.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        d1_bytes = dk_bytes(cnt[2], cnt[1], 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 4: 3D Kuhn large_hypercube n={n}"
+                                   + (f" per GPU, z-slabs of {n * N} layers over {N} GPUs (config 5 weak scaling)" if N > 1 else "")
+                                   + ": y=d_k x (k=0,1,2) and star_k x (k=0..3), Float64",
+                       "nsimplices_local": cnt, "dof_per_step": int(dof_total),
+                       "l2_hygiene": "inputs larger than L2 (index tables 0.9-2.4 GB, vectors 0.14-1.6 GB vs 126 MB L2)",
+                       "parallelism": "none" if N == 1 else f"z-slabs x{N}, no collective in d_k/star_k apply; "
+                                                            "NCCL send/recv halo in the wave step"},
+            "roofline": {"bound": "hbm", "kernel": "k_apply_fixed<3> (y = d1 x)", "achieved": d1_bytes / d1_ms * 1e-6,
+                         "peak": peak, "unit": "GB/s", "frac": d1_bytes / d1_ms * 1e-6 / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(d1_bytes),
+                         "ms_per_launch": d1_ms, "frac_of_nominal_8TBs": d1_bytes / d1_ms * 1e-6 / 8000.0},
+            "breakdown": breakdown, "wave": wave, "assembly_ms": asm_ms, "setup_s": setup_s,
+            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
+            "hbm_bytes_in_use": ctx.bytes_in_use(),
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="cells per axis (per GPU along z)")
+    ap.add_argument("--n-ref", type=int, default=64, help="cells per axis of the CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

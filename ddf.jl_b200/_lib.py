@@ -40,6 +40,8 @@ SIGNATURES = {
     "ddf_timer_tic": [_P],
     "ddf_timer_toc": [_P, _f64p],
     "ddf_ctx_launch_count": [_P, _i64p],
+    "ddf_event_record": [_P, _int],
+    "ddf_event_elapsed": [_P, _int, _int, _f64p],
     "ddf_flush_l2": [_P],
     "ddf_mesh_create": [_P, _int, _int, _i64, _i64, _i64p, _i64p, _f64p, _f64p, _PP],
     "ddf_mesh_create_hypercube": [_P, _int, _i64p, _i64, _i64, _PP],

@@ -64,6 +64,14 @@ class Context:
         call("ddf_timer_toc", self._h, C.byref(out))
         return out.value
 
+    def event_record(self, slot: int):
+        call("ddf_event_record", self._h, int(slot))
+
+    def event_elapsed(self, a: int, b: int) -> float:
+        out = C.c_double()
+        call("ddf_event_elapsed", self._h, int(a), int(b), C.byref(out))
+        return out.value
+
     def flush_l2(self):
         call("ddf_flush_l2", self._h)
 

@@ -60,6 +60,7 @@ struct ddf_ctx {
   cudaStream_t stream = nullptr;     // compute stream
   cudaStream_t comm_stream = nullptr;  // halo / NCCL stream
   cudaEvent_t ev_tic = nullptr, ev_toc = nullptr, ev_a = nullptr, ev_b = nullptr;
+  std::vector<cudaEvent_t> events;   // numbered timing events (ddf_event_record)
   int64_t bytes_in_use = 0;
   int64_t launches = 0;
   // scratch for reductions

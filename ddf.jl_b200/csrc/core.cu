@@ -111,6 +111,23 @@ extern "C" int ddf_timer_toc(ddf_ctx* c, double* ms) {
   return 0;
 }
 
+extern "C" int ddf_event_record(ddf_ctx* c, int slot) {
+  if (slot < 0 || slot >= 4096) DDF_FAIL("event_record: slot out of range");
+  if (c->events.size() <= (size_t)slot) c->events.resize(slot + 1, nullptr);
+  if (!c->events[slot]) DDF_CUDA(cudaEventCreate(&c->events[slot]));
+  DDF_CUDA(cudaEventRecord(c->events[slot], c->stream));
+  return 0;
+}
+extern "C" int ddf_event_elapsed(ddf_ctx* c, int a, int b, double* ms) {
+  if (a < 0 || b < 0 || (size_t)a >= c->events.size() || (size_t)b >= c->events.size() || !c->events[a] || !c->events[b])
+    DDF_FAIL("event_elapsed: slot not recorded");
+  DDF_CUDA(cudaEventSynchronize(c->events[b]));
+  float f = 0;
+  DDF_CUDA(cudaEventElapsedTime(&f, c->events[a], c->events[b]));
+  *ms = (double)f;
+  return 0;
+}
+
 __global__ void k_fill_u32(uint32_t* p, size_t n, uint32_t v) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;

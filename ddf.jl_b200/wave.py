@@ -61,8 +61,10 @@ def wave(D: int, levels: int, ctx=None, t1: float = 0.875):
     dt = wave_dt(mfd)
     nsteps = int(round(t1 / dt))
     omega = math.sqrt(D)
-    # staggered start: v lives at half steps in leapfrog; v(dt/2) ~ v0 + dt/2 * L u0
-    # (symplectic-Euler form used here keeps v at integer steps; first-order in the start-up)
+    # leapfrog staggering: the step is v^{n+1/2} = v^{n-1/2} + dt L u^n; u^{n+1} = u^n + dt v^{n+1/2},
+    # so start from v^{-1/2} = v0 - dt/2 (1-b) L u0 (second order overall)
+    _, dv0 = wave_rhs(mfd, u, v)
+    v = v - dv0 * (dt / 2)
     wave_leapfrog(mfd, u, v, dt, nsteps)
     t = nsteps * dt
     coords = mfd.get_coords()

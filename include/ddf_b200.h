@@ -59,6 +59,10 @@ int ddf_ctx_bytes_in_use(ddf_ctx* ctx, int64_t* out);
  * tic records an event, toc records another, synchronises and returns ms. */
 int ddf_timer_tic(ddf_ctx* ctx);
 int ddf_timer_toc(ddf_ctx* ctx, double* ms);
+/* numbered CUDA events on the library stream (0 <= slot < 4096): record without
+ * synchronising, read the elapsed time between two recorded slots later */
+int ddf_event_record(ddf_ctx* ctx, int slot);
+int ddf_event_elapsed(ddf_ctx* ctx, int slot_a, int slot_b, double* ms);
 /* number of kernels the library has launched on this ctx since creation */
 int ddf_ctx_launch_count(ddf_ctx* ctx, int64_t* out);
 /* overwrite a >L2-sized scratch buffer (bench hygiene between timed launches) */

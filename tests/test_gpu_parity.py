@@ -28,7 +28,7 @@ def relerr(a, b):
 
 def make_pair(ddf, ctx, kind):
     """(oracle manifold, device manifold) built from the same input."""
-    if kind.startswith("kuhn"):
+    if kind.startswith("kuhn") and kind != "kuhn3slab":
         D, n = int(kind[4]), int(kind.split("n")[-1])
         om = o.large_hypercube_manifold(D, (n,) * D)
         dm = ddf.large_hypercube_manifold(D, (n,) * D, ctx=ctx)      # on-device generator
@@ -155,7 +155,9 @@ def test_geometry_parity(pairs, kind):
     om, dm = pairs(kind)
     for R in range(om.D + 1):
         assert relerr(dm.get_volumes(R), o.calc_volumes(om, R)) <= RTOL, f"vol R={R}"
-        assert relerr(dm.get_dualcoords(R), o.calc_dualcoords(om, R)) <= 1e-11, f"dualcoords R={R}"
+        # positions: error relative to the mesh extent (a circumcentre may sit at the origin)
+        ext = float(np.max(np.abs(om.coords))) or 1.0
+        assert np.max(np.abs(dm.get_dualcoords(R) - o.calc_dualcoords(om, R))) <= 1e-12 * ext, f"dualcoords R={R}"
         dv, odv = dm.get_dualvolumes(R), o.calc_dualvolumes(om, R)
         assert relerr(dv, odv) <= 1e-11, f"dualvol R={R}"
     assert np.all(dm.get_volumes(0) == 1) and np.all(dm.get_dualvolumes(om.D) == 1)
