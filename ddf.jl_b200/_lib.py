@@ -43,6 +43,7 @@ SIGNATURES = {
     "ddf_event_record": [_P, _int],
     "ddf_event_elapsed": [_P, _int, _int, _f64p],
     "ddf_flush_l2": [_P],
+    "ddf_set_tuning": [C.c_char_p, _int],
     "ddf_mesh_create": [_P, _int, _int, _i64, _i64, _i64p, _i64p, _f64p, _f64p, _PP],
     "ddf_mesh_create_hypercube": [_P, _int, _i64p, _i64, _i64, _PP],
     "ddf_mesh_destroy": [_P],

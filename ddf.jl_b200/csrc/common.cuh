@@ -137,31 +137,78 @@ static inline int grid_for(int64_t n, int per_block, int* grid) {
 // free for the x-gather.
 __device__ __forceinline__ int4 ld_stream_int4(const int4* p) {
   int4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.s32 {%0,%1,%2,%3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.L2::128B.v4.s32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ int2 ld_stream_int2(const int2* p) {
   int2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];"
+  asm("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];"
                : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
 __device__ __forceinline__ int ld_stream_int(const int* p) {
   int r;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
   return r;
 }
 __device__ __forceinline__ double ld_stream_f64(const double* p) {
   double r;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
   return r;
 }
 __device__ __forceinline__ double2 ld_stream_f64x2(const double2* p) {
   double2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
                : "=d"(r.x), "=d"(r.y) : "l"(p));
   return r;
+}
+// L2 eviction-priority policies (createpolicy, sm_80+): the gathered cochain x is
+// re-used by neighbouring rows -> evict_last; index tables and outputs are touched
+// once -> evict_first, so they do not push x out of the 126 MB L2.
+__device__ __forceinline__ uint64_t make_policy_evict_last() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t make_policy_evict_first() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double ld_keep_f64(const double* p, uint64_t pol) {
+  double r;
+  asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ int ld_keep_s32(const int* p, uint64_t pol) {
+  int r;
+  asm("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ int4 ld_stream_int4_hint(const int4* p, uint64_t pol) {
+  int4 r;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ int4 ld_l1_int4_hint(const int4* p, uint64_t pol) {
+  int4 r;
+  asm("ld.global.nc.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ double2 ld_stream_f64x2_hint(const double2* p, uint64_t pol) {
+  double2 r;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+               : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void st_hint_f64x2(double2* p, double a, double b, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" :: "l"(p), "d"(a), "d"(b), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint_f64(double* p, double a, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(a), "l"(pol) : "memory");
 }
 // streaming (write-once) stores: evict-first so the outputs do not push the
 // gathered x out of L2.

@@ -39,9 +39,10 @@ struct ddf_mesh {
   // Row i's neighbours are the other endpoints of its incident edges in edge-id
   // order == ascending vertex order, so adj_ptr aliases brow_ptr[1].
   bool has_wave = false;
-  DevBuf<int32_t> adj_nbr;               // 2E  neighbour vertex j
-  DevBuf<double> adj_l;                  // 2E  L[i,j] = fl(ih0[i] * star1[e])   (chopped -> 0)
-  DevBuf<double> ldiag;                  // V   L[i,i] = sequential sum over incident edges of -L[i,j]
+  DevBuf<uint32_t> adj_ptr;              // V+1 row offsets (diagonal inline, chopped entries removed)
+  DevBuf<int32_t> adj_nbr;               // nnz column j, ascending within a row
+  DevBuf<double> adj_l;                  // nnz L[i,j] = fl(ih0[i] * star1[e]); L[i,i] = sequential sum of -L[i,j]
+  int64_t adj_nnz = 0;
   DevBuf<double> utmp;                   // V   ping-pong buffer of the fused step
 
   // slab halo of the distributed wave step (comm.cu): vertex planes along the

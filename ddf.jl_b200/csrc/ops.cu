@@ -82,21 +82,23 @@ k_apply_fixed(const int32_t* __restrict__ tab, int64_t nrows, int first_negative
               double* __restrict__ y) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t r0 = t * 4;
+  const uint64_t pol_keep = make_policy_evict_last();     // gathered x: keep in L2
+  const uint64_t pol_stream = make_policy_evict_first();  // index table / outputs: touched once
   if (r0 >= nrows) return;
   if (r0 + 3 < nrows) {
     int idx[4 * W];
     const int4* tp = reinterpret_cast<const int4*>(tab) + t * W;
 #pragma unroll
     for (int q = 0; q < W; q++) {
-      int4 v = ld_stream_int4(tp + q);
+      int4 v = ld_l1_int4_hint(tp + q, pol_stream);   // L1-allocating: the W loads of a thread share sectors
       idx[4 * q + 0] = v.x; idx[4 * q + 1] = v.y; idx[4 * q + 2] = v.z; idx[4 * q + 3] = v.w;
     }
     double xv[4 * W];
 #pragma unroll
-    for (int q = 0; q < 4 * W; q++) xv[q] = __ldg(x + idx[q]);
+    for (int q = 0; q < 4 * W; q++) xv[q] = ld_keep_f64(x + idx[q], pol_keep);
     if (PRE) {
 #pragma unroll
-      for (int q = 0; q < 4 * W; q++) xv[q] = __dmul_rn(__ldg(pre + idx[q]), xv[q]);
+      for (int q = 0; q < 4 * W; q++) xv[q] = __dmul_rn(ld_keep_f64(pre + idx[q], pol_keep), xv[q]);
     }
     double acc[4];
 #pragma unroll
@@ -110,8 +112,8 @@ k_apply_fixed(const int32_t* __restrict__ tab, int64_t nrows, int first_negative
       acc[r] = a;
     }
     if (POST) {
-      const double2 p0 = ld_stream_f64x2(reinterpret_cast<const double2*>(post + r0));
-      const double2 p1 = ld_stream_f64x2(reinterpret_cast<const double2*>(post + r0 + 2));
+      const double2 p0 = ld_stream_f64x2_hint(reinterpret_cast<const double2*>(post + r0), pol_stream);
+      const double2 p1 = ld_stream_f64x2_hint(reinterpret_cast<const double2*>(post + r0 + 2), pol_stream);
       acc[0] = __dmul_rn(p0.x, acc[0]); acc[1] = __dmul_rn(p0.y, acc[1]);
       acc[2] = __dmul_rn(p1.x, acc[2]); acc[3] = __dmul_rn(p1.y, acc[3]);
     }
@@ -119,8 +121,8 @@ k_apply_fixed(const int32_t* __restrict__ tab, int64_t nrows, int first_negative
 #pragma unroll
       for (int r = 0; r < 4; r++) acc[r] = __dmul_rn(alpha, acc[r]);
     }
-    st_stream_f64x2(reinterpret_cast<double2*>(y + r0), acc[0], acc[1]);
-    st_stream_f64x2(reinterpret_cast<double2*>(y + r0 + 2), acc[2], acc[3]);
+    st_hint_f64x2(reinterpret_cast<double2*>(y + r0), acc[0], acc[1], pol_stream);
+    st_hint_f64x2(reinterpret_cast<double2*>(y + r0 + 2), acc[2], acc[3], pol_stream);
   } else {
     for (int64_t r = r0; r < nrows; r++) {
       double a = 0.0;
@@ -182,12 +184,163 @@ __global__ void k_apply_csrf64(const uint32_t* __restrict__ rowptr, const int32_
   y[i] = a;
 }
 
+extern int g_tune_wave;   // wave.cu
+extern int g_tune_fixed;
+extern "C" int ddf_set_tuning(const char* key, int value) {
+  if (!strcmp(key, "fixed")) g_tune_fixed = value;
+  else if (!strcmp(key, "wave")) g_tune_wave = value;
+  else DDF_FAIL("set_tuning: unknown key %s", key);
+  return 0;
+}
+
+// ------------------------------------------------------------- tuning variants
+// Experimental variants of the plain (no fused diagonal) fixed-width kernel, selected
+// with ddf_set_tuning("fixed", v).  All produce bit-identical results.
+//   1: L2 eviction-priority hints (gathers evict_last, streams evict_first)
+//   2: 1 + index loads allocate in L1
+//   3: 1 + warp-coalesced index loads transposed through shared memory
+//   4: 1 + persistent blocks with the next tile's indices prefetched
+int g_tune_fixed = 0;
+
+template <int W>
+__device__ __forceinline__ void fixed_rows4(const int* idx, const double* __restrict__ x, uint64_t pol_keep,
+                                            uint64_t pol_stream, int first_negative, double* __restrict__ y,
+                                            int64_t r0) {
+  double xv[4 * W];
+#pragma unroll
+  for (int q = 0; q < 4 * W; q++) xv[q] = ld_keep_f64(x + idx[q], pol_keep);
+  double acc[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    double a = 0.0;
+#pragma unroll
+    for (int p = 0; p < W; p++) {
+      const bool neg = ((p & 1) != 0) != (first_negative != 0);
+      a = neg ? __dsub_rn(a, xv[r * W + p]) : __dadd_rn(a, xv[r * W + p]);
+    }
+    acc[r] = a;
+  }
+  st_hint_f64x2(reinterpret_cast<double2*>(y + r0), acc[0], acc[1], pol_stream);
+  st_hint_f64x2(reinterpret_cast<double2*>(y + r0 + 2), acc[2], acc[3], pol_stream);
+}
+
+template <int W>
+__device__ __forceinline__ void fixed_tail(const int32_t* __restrict__ tab, const double* __restrict__ x,
+                                           int first_negative, double* __restrict__ y, int64_t r0, int64_t nrows) {
+  for (int64_t r = r0; r < nrows; r++) {
+    double a = 0.0;
+#pragma unroll
+    for (int p = 0; p < W; p++) {
+      const double v = x[tab[r * W + p]];
+      const bool neg = ((p & 1) != 0) != (first_negative != 0);
+      a = neg ? __dsub_rn(a, v) : __dadd_rn(a, v);
+    }
+    y[r] = a;
+  }
+}
+
+template <int W, int VAR>
+__global__ void __launch_bounds__(256)
+k_apply_fixed_x(const int32_t* __restrict__ tab, int64_t nrows, int first_negative, const double* __restrict__ x,
+                double* __restrict__ y) {
+  const uint64_t pol_keep = make_policy_evict_last();
+  const uint64_t pol_stream = make_policy_evict_first();
+  if (VAR == 1 || VAR == 2) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r0 = t * 4;
+    if (r0 >= nrows) return;
+    if (r0 + 3 < nrows) {
+      int idx[4 * W];
+      const int4* tp = reinterpret_cast<const int4*>(tab) + t * W;
+#pragma unroll
+      for (int q = 0; q < W; q++) {
+        int4 v = VAR == 1 ? ld_stream_int4_hint(tp + q, pol_stream) : ld_l1_int4_hint(tp + q, pol_stream);
+        idx[4 * q + 0] = v.x; idx[4 * q + 1] = v.y; idx[4 * q + 2] = v.z; idx[4 * q + 3] = v.w;
+      }
+      fixed_rows4<W>(idx, x, pol_keep, pol_stream, first_negative, y, r0);
+    } else {
+      fixed_tail<W>(tab, x, first_negative, y, r0, nrows);
+    }
+  } else if (VAR == 3) {
+    // a warp owns 128 consecutive rows = 32*W int4 of indices: W fully coalesced 512-byte loads,
+    // transposed through shared memory so that lane l ends up with rows 4l..4l+3
+    __shared__ int4 sm[8][32 * W];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warp_row0 = ((int64_t)blockIdx.x * 8 + w) * 128;
+    if (warp_row0 >= nrows) return;
+    const int64_t r0 = warp_row0 + lane * 4;
+    if (warp_row0 + 127 < nrows) {
+      const int4* tp = reinterpret_cast<const int4*>(tab) + (warp_row0 / 4) * W;
+#pragma unroll
+      for (int q = 0; q < W; q++) sm[w][q * 32 + lane] = ld_stream_int4_hint(tp + q * 32 + lane, pol_stream);
+      __syncwarp();
+      int idx[4 * W];
+#pragma unroll
+      for (int q = 0; q < W; q++) {
+        int4 v = sm[w][lane * W + q];
+        idx[4 * q + 0] = v.x; idx[4 * q + 1] = v.y; idx[4 * q + 2] = v.z; idx[4 * q + 3] = v.w;
+      }
+      fixed_rows4<W>(idx, x, pol_keep, pol_stream, first_negative, y, r0);
+    } else if (r0 < nrows) {
+      fixed_tail<W>(tab, x, first_negative, y, r0, r0 + 4 < nrows ? r0 + 4 : nrows);
+    }
+  } else {
+    // VAR 4: persistent blocks; the indices of the next tile are in flight while this tile gathers
+    const int64_t ntiles = (nrows / 4);                 // full 4-row groups
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int4 nxt[W];
+    if (t < ntiles) {
+      const int4* tp = reinterpret_cast<const int4*>(tab) + t * W;
+#pragma unroll
+      for (int q = 0; q < W; q++) nxt[q] = ld_stream_int4_hint(tp + q, pol_stream);
+    }
+    for (; t < ntiles; t += stride) {
+      int idx[4 * W];
+#pragma unroll
+      for (int q = 0; q < W; q++) {
+        idx[4 * q + 0] = nxt[q].x; idx[4 * q + 1] = nxt[q].y; idx[4 * q + 2] = nxt[q].z; idx[4 * q + 3] = nxt[q].w;
+      }
+      if (t + stride < ntiles) {
+        const int4* tp = reinterpret_cast<const int4*>(tab) + (t + stride) * W;
+#pragma unroll
+        for (int q = 0; q < W; q++) nxt[q] = ld_stream_int4_hint(tp + q, pol_stream);
+      }
+      fixed_rows4<W>(idx, x, pol_keep, pol_stream, first_negative, y, t * 4);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) fixed_tail<W>(tab, x, first_negative, y, ntiles * 4, nrows);
+  }
+}
+
+template <int W>
+static void launch_fixed_x(ddf_ctx* ctx, int var, const int32_t* tab, int64_t nrows, int first_negative,
+                           const double* x, double* y) {
+  const int grid4 = (int)ceil_div64(ceil_div64(nrows, 4), 256);
+  switch (var) {
+    case 1: k_apply_fixed_x<W, 1><<<grid4, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
+    case 2: k_apply_fixed_x<W, 2><<<grid4, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
+    case 3: k_apply_fixed_x<W, 3><<<(int)ceil_div64(nrows, 1024), 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
+    default: {
+      int g = ctx->sm_count * 8;
+      if (g > grid4) g = grid4;
+      k_apply_fixed_x<W, 4><<<g, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y);
+    }
+  }
+}
+
 // ================================================================ kernel launchers
 static int launch_fixed(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, int first_negative, const double* x,
                         const double* pre, const double* post, double alpha, double* y) {
   if (nrows == 0) return 0;
   int grid;
   DDF_CHECK(grid_for(ceil_div64(nrows, 4), 256, &grid));
+  if (g_tune_fixed > 0 && !pre && !post && alpha == 1.0 && W >= 2 && W <= 4) {
+    if (W == 2) launch_fixed_x<2>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
+    else if (W == 3) launch_fixed_x<3>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
+    else launch_fixed_x<4>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
+    DDF_LAUNCH_CHECK(ctx);
+    return 0;
+  }
 #define DDF_FIXED_CASE(WW)                                                                                          \
   case WW:                                                                                                          \
     if (pre && post) k_apply_fixed<WW, true, true><<<grid, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, pre, post, alpha, y); \

@@ -6,43 +6,72 @@
 // (Ops.jl:228-232), chopping after every product (Ops.jl:44-58):
 //     delta[i,e] = fl((-ih0[i] * s_ie) * star1[e]),   L[i,j] = delta[i,e] * d0[e,j],
 //     L[i,i]    = sequential sum over incident edges e ascending of delta[i,e]*d0[e,i].
-// k_build_laplace0 reproduces exactly those roundings into a row-CSR with the
-// diagonal split off.  Because edge ids are lexicographic ranks of (a,b), the
+// k_build_laplace0 reproduces exactly those roundings into a row-CSR (adj_ptr,
+// adj_nbr, adj_l) with the diagonal entry stored inline at its sorted position and
+// chopped entries removed.  Because edge ids are lexicographic ranks of (a,b), the
 // incident edges of vertex i in id order are its neighbours in ascending vertex
 // order -- the reference's CSC `mul!` (zero y; scatter by ascending column) is
-// therefore the per-row sum: incoming neighbours, diagonal, outgoing neighbours,
-// with separately rounded multiply and add.  All kernels below use that order, so
-// L*u, the wave right-hand side and the leapfrog step are bit-exact with the oracle.
+// therefore the per-row sequential sum over the stored entries, with separately
+// rounded multiply and add.  All kernels below sum in that order, so L*u, the wave
+// right-hand side and the leapfrog step are bit-exact with the oracle.
+//
+// Row kernels are warp-cooperative ("row streaming"): a warp owns 32 consecutive
+// rows; their entries are one contiguous range of the CSR arrays, loaded with fully
+// coalesced 128/256-byte requests, every lane issues its u-gathers back to back
+// (14 independent gathers per lane on the 3D Kuhn mesh), the products go to shared
+// memory and each lane then adds up its own row in order.
+#include <cub/cub.cuh>
+
 #include "mesh.cuh"
 
 int ddf_mesh_require_star(ddf_mesh* m, int R);   // ops.cu
 int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n, double* out);   // core.cu
 
+int g_tune_wave = 0;
+
+// pass 1 (count) / pass 2 (fill) of the assembly of L rows
+template <bool FILL>
 __global__ void k_build_laplace0(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ colw,
                                  const int32_t* __restrict__ edges, const double* __restrict__ ih0,
-                                 const double* __restrict__ star1, int64_t nv, int32_t* __restrict__ nbr,
-                                 double* __restrict__ lval, double* __restrict__ ldiag) {
+                                 const double* __restrict__ star1, int64_t nv, uint32_t* __restrict__ counts,
+                                 const uint32_t* __restrict__ adj_ptr, int32_t* __restrict__ nbr,
+                                 double* __restrict__ lval) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nv) return;
   const double ih = ih0[i];
+  const bool ih_kept = !(ih * ih < DDF_CHOP_ABS2);   // chop of the (bitsign * invhodge) * deriv entries (+-ih)
+  // the diagonal: first touch assigns, later touches add (SparseArrays spmatmul), edges ascending
   double diag = 0.0;
   bool first = true;
-  const bool ih_kept = !(ih * ih < DDF_CHOP_ABS2);   // chop of (bitsign * invhodge) * deriv  entries (+-ih)
+  uint32_t kept = 0;
+  for (uint32_t p = rowptr[i]; p < rowptr[i + 1]; p++) {
+    const uint32_t e = colw[p] & 0x7fffffffu;
+    double l = ih_kept ? __dmul_rn(ih, star1[e]) : 0.0;     // |delta[i,e]| = L[i,j]
+    if (l * l < DDF_CHOP_ABS2) l = 0.0;                     // chop(delta) and chop(L) act on the same magnitude
+    if (l != 0.0) {
+      diag = first ? -l : __dadd_rn(diag, -l);
+      first = false;
+      kept++;
+    }
+  }
+  const bool diag_kept = !first && !(diag * diag < DDF_CHOP_ABS2);
+  if (!FILL) {
+    counts[i] = kept + (diag_kept ? 1u : 0u);
+    return;
+  }
+  uint32_t out = adj_ptr[i];
+  bool diag_done = !diag_kept;
   for (uint32_t p = rowptr[i]; p < rowptr[i + 1]; p++) {
     const uint32_t cw = colw[p];
     const uint32_t e = cw & 0x7fffffffu;
-    const bool i_is_first = (cw >> 31) != 0;        // d_1[a,e] = -1
-    nbr[p] = i_is_first ? edges[2 * (size_t)e + 1] : edges[2 * (size_t)e];
-    double l = ih_kept ? __dmul_rn(ih, star1[e]) : 0.0;   // |delta[i,e]|
-    if (l * l < DDF_CHOP_ABS2) l = 0.0;                   // chop(delta), then chop(L) on the same magnitude
-    lval[p] = l;                                           // L[i,j] = +l for both orientations
-    if (l != 0.0) {                                        // diagonal: first touch assigns, later touches add
-      diag = first ? -l : __dadd_rn(diag, -l);
-      first = false;
-    }
+    const bool i_is_first = (cw >> 31) != 0;                // d_1[a,e] = -1
+    const int32_t j = i_is_first ? edges[2 * (size_t)e + 1] : edges[2 * (size_t)e];
+    double l = ih_kept ? __dmul_rn(ih, star1[e]) : 0.0;
+    if (l * l < DDF_CHOP_ABS2) l = 0.0;
+    if (!diag_done && j > i) { nbr[out] = (int32_t)i; lval[out] = diag; out++; diag_done = true; }
+    if (l != 0.0) { nbr[out] = j; lval[out] = l; out++; }
   }
-  if (diag * diag < DDF_CHOP_ABS2) diag = 0.0;
-  ldiag[i] = diag;
+  if (!diag_done) { nbr[out] = (int32_t)i; lval[out] = diag; }
 }
 
 int ddf_mesh_require_wave(ddf_mesh* m) {
@@ -52,91 +81,211 @@ int ddf_mesh_require_wave(ddf_mesh* m) {
   DDF_CHECK(ddf_mesh_require_star(m, 1));
   DDF_CHECK(ddf_mesh_require_isboundary(m));
   ddf_ctx* ctx = m->ctx;
-  const int64_t nv = m->n[0], ne = m->n[1];
-  DDF_CHECK(m->adj_nbr.alloc(ctx, 2 * ne));
-  DDF_CHECK(m->adj_l.alloc(ctx, 2 * ne));
-  DDF_CHECK(m->ldiag.alloc(ctx, nv));
-  if (nv) {
-    int grid;
-    DDF_CHECK(grid_for(nv, 256, &grid));
-    k_build_laplace0<<<grid, 256, 0, ctx->stream>>>(m->brow_ptr[1].p, m->bcol[1].p, m->simp[1].p, m->istar[0].p,
-                                                    m->star[1].p, nv, m->adj_nbr.p, m->adj_l.p, m->ldiag.p);
-    DDF_LAUNCH_CHECK(ctx);
+  const int64_t nv = m->n[0];
+  DDF_CHECK(m->adj_ptr.alloc(ctx, nv + 1));
+  if (nv == 0) {
+    DDF_CUDA(cudaMemsetAsync(m->adj_ptr.p, 0, 4, ctx->stream));
+    m->adj_nnz = 0;
+    m->has_wave = true;
+    return 0;
   }
+  int grid;
+  DDF_CHECK(grid_for(nv, 256, &grid));
+  DevBuf<uint32_t> counts;
+  DevBuf<uint8_t> temp;
+  DDF_CHECK(counts.alloc(ctx, nv + 1));
+  DDF_CUDA(cudaMemsetAsync(counts.p + nv, 0, 4, ctx->stream));
+  k_build_laplace0<false><<<grid, 256, 0, ctx->stream>>>(m->brow_ptr[1].p, m->bcol[1].p, m->simp[1].p, m->istar[0].p,
+                                                         m->star[1].p, nv, counts.p, nullptr, nullptr, nullptr);
+  DDF_LAUNCH_CHECK(ctx);
+  size_t tb = 0;
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, counts.p, m->adj_ptr.p, nv + 1, ctx->stream));
+  DDF_CHECK(temp.alloc(ctx, tb));
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, counts.p, m->adj_ptr.p, nv + 1, ctx->stream));
+  ctx->launches++;
+  uint32_t nnz = 0;
+  DDF_CUDA(cudaMemcpyAsync(&nnz, m->adj_ptr.p + nv, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  m->adj_nnz = nnz;
+  DDF_CHECK(m->adj_nbr.alloc(ctx, nnz));
+  DDF_CHECK(m->adj_l.alloc(ctx, nnz));
+  k_build_laplace0<true><<<grid, 256, 0, ctx->stream>>>(m->brow_ptr[1].p, m->bcol[1].p, m->simp[1].p, m->istar[0].p,
+                                                        m->star[1].p, nv, nullptr, m->adj_ptr.p, m->adj_nbr.p,
+                                                        m->adj_l.p);
+  DDF_LAUNCH_CHECK(ctx);
   m->has_wave = true;
   return 0;
 }
 
-// (L u)_i in the reference's summation order
-__device__ __forceinline__ double row_laplace(int64_t i, const uint32_t* __restrict__ rowptr,
-                                              const int32_t* __restrict__ nbr, const double* __restrict__ lval,
-                                              const double* __restrict__ ldiag, const double* __restrict__ u,
-                                              double ui) {
-  const uint32_t lo = rowptr[i], hi = rowptr[i + 1];
-  const double d = ldiag[i];
-  double acc = 0.0;
-  bool diag_done = (d == 0.0);
-  for (uint32_t p = lo; p < hi; p++) {
-    const int32_t j = __ldg(nbr + p);
-    const double l = __ldg(lval + p);
-    if (!diag_done && j > i) {
-      acc = __dadd_rn(acc, __dmul_rn(d, ui));
-      diag_done = true;
-    }
-    if (l != 0.0) acc = __dadd_rn(acc, __dmul_rn(l, __ldg(u + j)));
+// ---------------------------------------------------------------- row kernels
+// MODE 0: y = L u            MODE 1: wave rhs (du, dudot)          MODE 2: leapfrog step
+struct RowArgs {
+  const uint32_t* rowptr;
+  const int32_t* nbr;
+  const double* lval;
+  const uint8_t* isb;
+  const double* u;
+  const double* udot;   // MODE 1 input
+  double* out0;         // MODE 0: y ; MODE 1: du    ; MODE 2: v (in/out)
+  double* out1;         //            MODE 1: dudot ; MODE 2: unew
+  double dt;
+  int64_t row0, row1;
+};
+
+template <int MODE>
+__device__ __forceinline__ void row_epilogue(const RowArgs& a, int64_t i, double lu, uint64_t pol_stream) {
+  if (MODE == 0) {
+    st_hint_f64(a.out0 + i, lu, pol_stream);
+  } else if (MODE == 1) {
+    const double m = a.isb[i] ? 0.0 : 1.0;
+    a.out0[i] = __dmul_rn(m, a.udot[i]);
+    a.out1[i] = __dmul_rn(m, lu);
+  } else {
+    const double m = a.isb[i] ? 0.0 : 1.0;
+    const double vn = __dadd_rn(a.out0[i], __dmul_rn(a.dt, __dmul_rn(m, lu)));
+    a.out0[i] = vn;
+    a.out1[i] = __dadd_rn(a.u[i], __dmul_rn(a.dt, __dmul_rn(m, vn)));
   }
-  if (!diag_done) acc = __dadd_rn(acc, __dmul_rn(d, ui));
-  return acc;
 }
 
-__global__ void __launch_bounds__(256)
-k_laplace0(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, const double* __restrict__ lval,
-           const double* __restrict__ ldiag, const double* __restrict__ u, double* __restrict__ y, int64_t nv) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nv) return;
-  y[i] = row_laplace(i, rowptr, nbr, lval, ldiag, u, u[i]);
+// variant 1: one thread per row (baseline)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_rows_thread(RowArgs a) {
+  const int64_t i = a.row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.row1) return;
+  const uint64_t pol_stream = make_policy_evict_first();
+  const uint64_t pol_keep = make_policy_evict_last();
+  double acc = 0.0;
+  const uint32_t lo = a.rowptr[i], hi = a.rowptr[i + 1];
+  // batches of 8 entries: 8 index + 8 value loads, then 8 gathers in flight, then the ordered sum
+  for (uint32_t p = lo; p < hi; p += 8) {
+    int j[8];
+    double l[8], uu[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const bool ok = p + q < hi;
+      j[q] = ok ? __ldg(a.nbr + p + q) : (int)i;
+      l[q] = ok ? __ldg(a.lval + p + q) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) uu[q] = ld_keep_f64(a.u + j[q], pol_keep);
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (p + q < hi) acc = __dadd_rn(acc, __dmul_rn(l[q], uu[q]));
+  }
+  row_epilogue<MODE>(a, i, acc, pol_stream);
 }
 
-int ddf_laplace0_apply(ddf_mesh* m, const double* x, double* y) {
-  DDF_CHECK(ddf_mesh_require_wave(m));
-  if (!m->n[0]) return 0;
-  int grid;
-  DDF_CHECK(grid_for(m->n[0], 256, &grid));
-  k_laplace0<<<grid, 256, 0, m->ctx->stream>>>(m->brow_ptr[1].p, m->adj_nbr.p, m->adj_l.p, m->ldiag.p, x, y, m->n[0]);
+// default: warp-cooperative row streaming
+#define DDF_ROW_CAP 512       // products staged per warp and chunk (4 KB)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_rows_warp(RowArgs a) {
+  __shared__ double sm[8][DDF_ROW_CAP];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t r0 = a.row0 + ((int64_t)blockIdx.x * 8 + w) * 32;
+  if (r0 >= a.row1) return;
+  const uint64_t pol_keep = make_policy_evict_last();
+  const uint64_t pol_stream = make_policy_evict_first();
+  const int64_t i = r0 + lane;
+  const bool active = i < a.row1;
+  const int64_t ic = active ? i : a.row1 - 1;
+  const uint32_t lo = a.rowptr[ic];
+  const uint32_t hi = active ? a.rowptr[ic + 1] : lo;
+  const uint32_t wlo = __shfl_sync(0xffffffffu, lo, 0);
+  uint32_t whi = hi;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, off));
+  double acc = 0.0;
+  double* s = sm[w];
+  for (uint32_t base = wlo; base < whi; base += DDF_ROW_CAP) {
+    const uint32_t cend = min(base + (uint32_t)DDF_ROW_CAP, whi);
+    // coalesced loads of the warp's entries, gathers issued back to back
+    for (uint32_t k0 = base + lane; k0 < cend; k0 += 32 * 4) {
+      int j[4];
+      double l[4], uu[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint32_t k = k0 + 32 * q;
+        const bool ok = k < cend;
+        j[q] = ok ? ld_stream_int(a.nbr + k) : (int)ic;
+        l[q] = ok ? ld_stream_f64(a.lval + k) : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) uu[q] = ld_keep_f64(a.u + j[q], pol_keep);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint32_t k = k0 + 32 * q;
+        if (k < cend) s[k - base] = __dmul_rn(l[q], uu[q]);
+      }
+    }
+    __syncwarp();
+    const uint32_t sb = max(lo, base), se = min(hi, cend);
+    for (uint32_t q = sb; q < se; q++) acc = __dadd_rn(acc, s[q - base]);
+    __syncwarp();
+  }
+  if (active) row_epilogue<MODE>(a, i, acc, pol_stream);
+}
+
+template <int MODE>
+static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
+  const int64_t n = a.row1 - a.row0;
+  if (n <= 0) return 0;
+  a.rowptr = m->adj_ptr.p;
+  a.nbr = m->adj_nbr.p;
+  a.lval = m->adj_l.p;
+  a.isb = m->isbnd[0].p;
+  if (g_tune_wave != 2 && g_tune_wave != 3) {   // default: one thread per row (measured faster than the staged variant)
+    int grid;
+    DDF_CHECK(grid_for(n, 256, &grid));
+    k_rows_thread<MODE><<<grid, 256, 0, stream>>>(a);
+  } else {
+    int grid;
+    DDF_CHECK(grid_for(n, 256, &grid));       // 8 warps x 32 rows per block
+    // the staging buffer must not eat the L1 that serves the u-gathers: cap the shared-memory carveout
+    static int carve_set[3] = {-1, -1, -1};
+    const int carve = g_tune_wave == 2 ? 50 : (g_tune_wave == 3 ? -1 : 25);
+    if (carve_set[MODE] != carve) {
+      DDF_CUDA(cudaFuncSetAttribute(k_rows_warp<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      carve_set[MODE] = carve;
+    }
+    k_rows_warp<MODE><<<grid, 256, 0, stream>>>(a);
+  }
   DDF_LAUNCH_CHECK(m->ctx);
   return 0;
 }
 
-// assembled L as COO in CSC order (column j: incoming rows, j, outgoing rows)
+int ddf_laplace0_apply(ddf_mesh* m, const double* x, double* y) {
+  DDF_CHECK(ddf_mesh_require_wave(m));
+  RowArgs a{};
+  a.u = x;
+  a.out0 = y;
+  a.row0 = 0;
+  a.row1 = m->n[0];
+  return launch_rows<0>(m, m->ctx->stream, a);
+}
+
+// assembled L as COO in CSC order.  Column j of L holds L[i,j] for the neighbours i of j:
+// the value stored in ROW i at column j.
 __global__ void k_laplace0_coo(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
-                               const double* __restrict__ lval, const double* __restrict__ ldiag,
-                               const uint32_t* __restrict__ colw, int64_t nv, int32_t* __restrict__ row,
+                               const double* __restrict__ lval, int64_t nv, int32_t* __restrict__ row,
                                int32_t* __restrict__ col, double* __restrict__ val) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nv) return;
-  // L[i,j] for the neighbours i of j equals fl(ih0[i]*star1[e]) = the value stored in ROW i for edge e;
-  // find it through the edge: row i stores it at the position of e in i's incidence list.
-  size_t out = (size_t)rowptr[j] + (size_t)j;
-  bool diag_done = false;
+  // the pattern is symmetric (L[i,j] kept <=> L[j,i] kept only if both ih are kept; handle the general
+  // case by searching row i for column j and writing 0 when it is absent -- chopped later)
   for (uint32_t p = rowptr[j]; p < rowptr[j + 1]; p++) {
     const int32_t i = nbr[p];
-    if (!diag_done && i > j) {
-      row[out] = (int32_t)j; col[out] = (int32_t)j; val[out] = ldiag[j]; out++;
-      diag_done = true;
-    }
-    const uint32_t e = colw[p] & 0x7fffffffu;
     double v = 0.0;
     for (uint32_t q = rowptr[i]; q < rowptr[i + 1]; q++)
-      if ((colw[q] & 0x7fffffffu) == e) { v = lval[q]; break; }
-    row[out] = i; col[out] = (int32_t)j; val[out] = v; out++;
+      if (nbr[q] == (int32_t)j) { v = lval[q]; break; }
+    row[p] = i; col[p] = (int32_t)j; val[p] = v;
   }
-  if (!diag_done) { row[out] = (int32_t)j; col[out] = (int32_t)j; val[out] = ldiag[j]; }
 }
 
 int ddf_laplace0_to_coo(ddf_mesh* m, DevBuf<int32_t>& row, DevBuf<int32_t>& col, DevBuf<double>& val, int64_t* nnz) {
   DDF_CHECK(ddf_mesh_require_wave(m));
   ddf_ctx* ctx = m->ctx;
-  const int64_t n = 2 * m->n[1] + m->n[0];
+  const int64_t n = m->adj_nnz;
   *nnz = n;
   DDF_CHECK(row.alloc(ctx, n));
   DDF_CHECK(col.alloc(ctx, n));
@@ -144,38 +293,26 @@ int ddf_laplace0_to_coo(ddf_mesh* m, DevBuf<int32_t>& row, DevBuf<int32_t>& col,
   if (!m->n[0]) return 0;
   int grid;
   DDF_CHECK(grid_for(m->n[0], 256, &grid));
-  k_laplace0_coo<<<grid, 256, 0, ctx->stream>>>(m->brow_ptr[1].p, m->adj_nbr.p, m->adj_l.p, m->ldiag.p, m->bcol[1].p,
-                                                m->n[0], row.p, col.p, val.p);
+  k_laplace0_coo<<<grid, 256, 0, ctx->stream>>>(m->adj_ptr.p, m->adj_nbr.p, m->adj_l.p, m->n[0], row.p, col.p, val.p);
   DDF_LAUNCH_CHECK(ctx);
   return 0;
 }
 
 // examples/wave.jl:87-100: du = (E-B) udot ; dudot = (E-B) (L u)
-__global__ void __launch_bounds__(256)
-k_wave_rhs(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, const double* __restrict__ lval,
-           const double* __restrict__ ldiag, const uint8_t* __restrict__ isb, const double* __restrict__ u,
-           const double* __restrict__ udot, double* __restrict__ du, double* __restrict__ dudot, int64_t nv) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nv) return;
-  const double m = isb[i] ? 0.0 : 1.0;
-  const double lu = row_laplace(i, rowptr, nbr, lval, ldiag, u, u[i]);
-  du[i] = __dmul_rn(m, udot[i]);
-  dudot[i] = __dmul_rn(m, lu);
-}
-
 extern "C" int ddf_wave_rhs(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, ddf_vec* du, ddf_vec* dudot) {
   DDF_TRY_BEGIN
   DDF_CHECK(ddf_mesh_require_wave(m));
   const int64_t nv = m->n[0];
   if (u->n != nv || udot->n != nv || du->n != nv || dudot->n != nv) DDF_FAIL("wave_rhs: vectors must have length n0=%lld", (long long)nv);
   if (du == u || dudot == u) DDF_FAIL("wave_rhs: outputs must not alias u");
-  if (!nv) return 0;
-  int grid;
-  DDF_CHECK(grid_for(nv, 256, &grid));
-  k_wave_rhs<<<grid, 256, 0, m->ctx->stream>>>(m->brow_ptr[1].p, m->adj_nbr.p, m->adj_l.p, m->ldiag.p, m->isbnd[0].p,
-                                               u->d.p, udot->d.p, du->d.p, dudot->d.p, nv);
-  DDF_LAUNCH_CHECK(m->ctx);
-  return 0;
+  RowArgs a{};
+  a.u = u->d.p;
+  a.udot = udot->d.p;
+  a.out0 = du->d.p;
+  a.out1 = dudot->d.p;
+  a.row0 = 0;
+  a.row1 = nv;
+  return launch_rows<1>(m, m->ctx->stream, a);
   DDF_TRY_END
 }
 
@@ -192,31 +329,17 @@ extern "C" int ddf_wave_dt(ddf_mesh* m, double* dt) {
 // Fused leapfrog step (north_star; not in the reference, which uses Tsit5):
 //   v' = v + dt * ((1-b) .* (L u));   u' = u + dt * ((1-b) .* v')
 // One pass: u is read (own value + gathered neighbours), u' goes to the ping-pong
-// buffer so neighbours still see the old u.
-__global__ void __launch_bounds__(256)
-k_leapfrog(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, const double* __restrict__ lval,
-           const double* __restrict__ ldiag, const uint8_t* __restrict__ isb, const double* __restrict__ u,
-           double* __restrict__ v, double* __restrict__ unew, double dt, int64_t row0, int64_t row1) {
-  const int64_t i = row0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= row1) return;
-  const double ui = u[i];
-  const double m = isb[i] ? 0.0 : 1.0;
-  const double lu = row_laplace(i, rowptr, nbr, lval, ldiag, u, ui);
-  const double vn = __dadd_rn(v[i], __dmul_rn(dt, __dmul_rn(m, lu)));
-  v[i] = vn;
-  unew[i] = __dadd_rn(ui, __dmul_rn(dt, __dmul_rn(m, vn)));
-}
-
-// rows [row0, row1) of one leapfrog step on `stream`
+// buffer so neighbours still see the old u.  Rows [row0, row1) on `stream`.
 int ddf_leapfrog_launch(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
                         int64_t row0, int64_t row1) {
-  if (row1 <= row0) return 0;
-  int grid;
-  DDF_CHECK(grid_for(row1 - row0, 256, &grid));
-  k_leapfrog<<<grid, 256, 0, stream>>>(m->brow_ptr[1].p, m->adj_nbr.p, m->adj_l.p, m->ldiag.p, m->isbnd[0].p, u, v,
-                                       unew, dt, row0, row1);
-  DDF_LAUNCH_CHECK(m->ctx);
-  return 0;
+  RowArgs a{};
+  a.u = u;
+  a.out0 = v;
+  a.out1 = unew;
+  a.dt = dt;
+  a.row0 = row0;
+  a.row1 = row1;
+  return launch_rows<2>(m, stream, a);
 }
 
 extern "C" int ddf_wave_leapfrog(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt, int nsteps) {
@@ -239,6 +362,7 @@ extern "C" int ddf_wave_step_bytes(ddf_mesh* m, int64_t* algorithmic, int64_t* f
   DDF_CHECK(ddf_mesh_require_assembled(m));
   const int64_t E = m->n[1], V = m->n[0];
   *algorithmic = E * 16 + V * 41;                  // E*(2*4+8) + V*(8*5+1)
-  *format_bytes = 2 * E * 12 + V * (4 + 8 + 8 * 4 + 1);   // what this format streams per step
+  const int64_t nnz = m->has_wave ? m->adj_nnz : 2 * E + V;
+  *format_bytes = nnz * 12 + V * (4 + 8 * 4 + 1);  // what this format streams per step
   return 0;
 }

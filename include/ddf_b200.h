@@ -65,6 +65,9 @@ int ddf_event_record(ddf_ctx* ctx, int slot);
 int ddf_event_elapsed(ddf_ctx* ctx, int slot_a, int slot_b, double* ms);
 /* number of kernels the library has launched on this ctx since creation */
 int ddf_ctx_launch_count(ddf_ctx* ctx, int64_t* out);
+/* kernel-variant selector for profiling / A-B timing ("fixed", "wave"); every variant
+ * returns bit-identical results; 0 selects the default */
+int ddf_set_tuning(const char* key, int value);
 /* overwrite a >L2-sized scratch buffer (bench hygiene between timed launches) */
 int ddf_flush_l2(ddf_ctx* ctx);
 
