@@ -1,0 +1,179 @@
+# DDFB200.jl -- Julia glue over libddf_b200 (include/ddf_b200.h).
+#
+# UNEXECUTED: there is no Julia in the build image, so this file has never been run.
+# It shows the binding a DDF.jl maintainer would add (the precedent is
+# examples/wave-gpu.jl:22-34,121-126: swap the array type inside Fun/Op and overload
+# mul!).  The same C symbols are exercised by the Python ctypes binding
+# (ddf.jl_b200/_lib.py) in the GPU tests.
+module DDFB200
+
+using DDF
+using LinearAlgebra
+using SparseArrays
+
+const lib = "libddf_b200"
+
+struct DDFB200Error <: Exception
+    msg::String
+end
+last_error() = unsafe_string(ccall((:ddf_last_error, lib), Cstring, ()))
+check(status::Cint) = status == 0 ? nothing : throw(DDFB200Error(last_error()))
+
+# ---------------------------------------------------------------- handles
+mutable struct Ctx
+    h::Ptr{Cvoid}
+    function Ctx(device::Integer=0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:ddf_ctx_create, lib), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r))
+        c = new(r[])
+        finalizer(x -> ccall((:ddf_ctx_destroy, lib), Cint, (Ptr{Cvoid},), x.h), c)
+        return c
+    end
+end
+
+mutable struct DeviceManifold{D}
+    h::Ptr{Cvoid}
+    ctx::Ctx
+    host::Manifold{D}          # the reference's own object: metadata, sizes
+end
+
+"""
+Upload `simplices[D]`, `coords`, `weights` of a reference Manifold and assemble the
+faces/boundaries on the device -- replaces the loop at src/Manifolds.jl:361-368.
+"""
+function DeviceManifold(ctx::Ctx, mfd::Manifold{D,C,S}) where {D,C,S}
+    sD = get_simplices(mfd, D).op                      # SparseMatrixCSC{One,Int}
+    coords = get_coords(mfd).vec                       # Vector{SVector{C,Float64}} == C x V column-major
+    weights = get_weights(mfd).vec
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve sD coords weights begin
+        check(ccall((:ddf_mesh_create, lib), Cint,
+                    (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64},
+                     Ref{Ptr{Cvoid}}),
+                    ctx.h, D, C, size(sD, 1), size(sD, 2), sD.colptr, sD.rowval,
+                    reinterpret(Float64, coords), weights, r))
+    end
+    check(ccall((:ddf_mesh_assemble, lib), Cint, (Ptr{Cvoid},), r[]))
+    m = DeviceManifold{D}(r[], ctx, mfd)
+    finalizer(x -> ccall((:ddf_mesh_destroy, lib), Cint, (Ptr{Cvoid},), x.h), m)
+    return m
+end
+
+"Bit-exact export so that Manifold._boundaries[R] can still be filled (src/Manifolds.jl:443-450)."
+function get_boundaries(m::DeviceManifold, R::Int)
+    n = Ref{Int64}(0); nf = Ref{Int64}(0)
+    check(ccall((:ddf_mesh_nsimplices, lib), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}), m.h, R, n))
+    check(ccall((:ddf_mesh_nsimplices, lib), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}), m.h, R - 1, nf))
+    colptr = Vector{Int64}(undef, n[] + 1); rowval = Vector{Int64}(undef, (R + 1) * n[])
+    nzval = Vector{Int8}(undef, (R + 1) * n[])
+    check(ccall((:ddf_mesh_get_boundary_csc, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Int8}),
+                m.h, R, colptr, rowval, nzval))
+    return SparseOp{R - 1,R}(SparseMatrixCSC{Int8,Int}(nf[], n[], colptr, rowval, nzval))
+end
+
+# ---------------------------------------------------------------- cochains
+mutable struct DeviceVector <: AbstractVector{Float64}   # goes inside Fun.values (src/Funs.jl:18)
+    h::Ptr{Cvoid}
+    n::Int
+end
+function DeviceVector(ctx::Ctx, x::Vector{Float64})
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddf_vec_create, lib), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx.h, length(x), r))
+    v = DeviceVector(r[], length(x))
+    GC.@preserve x check(ccall((:ddf_vec_upload, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), v.h, x))
+    finalizer(y -> ccall((:ddf_vec_destroy, lib), Cint, (Ptr{Cvoid},), y.h), v)
+    return v
+end
+Base.size(v::DeviceVector) = (v.n,)
+function Base.Array(v::DeviceVector)
+    x = Vector{Float64}(undef, v.n)
+    check(ccall((:ddf_vec_download, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), v.h, x))
+    return x
+end
+function LinearAlgebra.norm(v::DeviceVector, p::Real=2)
+    out = Ref{Float64}(0)
+    kind = p == Inf ? 0 : Int(p)
+    check(ccall((:ddf_vec_norm, lib), Cint, (Ptr{Cvoid}, Cint, Ref{Float64}), v.h, kind, out))
+    return out[]
+end
+
+# ---------------------------------------------------------------- operators
+mutable struct DeviceOp <: AbstractMatrix{Float64}       # goes inside Op.values (src/Ops.jl:20)
+    h::Ptr{Cvoid}
+    m::DeviceManifold
+end
+function _op(sym::Symbol, m::DeviceManifold, P::PrimalDual, R::Int)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((sym, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Ptr{Cvoid}}), m.h, P == Pr ? 1 : 0, R, r))
+    op = DeviceOp(r[], m)
+    finalizer(x -> ccall((:ddf_op_destroy, lib), Cint, (Ptr{Cvoid},), x.h), op)
+    return op
+end
+function Base.size(A::DeviceOp)
+    a = Ref{Int64}(0); b = Ref{Int64}(0)
+    check(ccall((:ddf_op_shape, lib), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), A.h, a, b))
+    return (Int(a[]), Int(b[]))
+end
+
+# same call surface as src/ManifoldOps.jl:17-146, dispatching on the device manifold
+DDF.deriv(::Val{P}, ::Val{R}, m::DeviceManifold{D}) where {P,R,D} =
+    Op{D,P,R + (P == Pr ? 1 : -1),P,R}(m.host, _op(:ddf_op_deriv, m, P, R))
+DDF.boundary(::Val{P}, ::Val{R}, m::DeviceManifold{D}) where {P,R,D} =
+    Op{D,P,R - (P == Pr ? 1 : -1),P,R}(m.host, _op(:ddf_op_boundary, m, P, R))
+DDF.hodge(::Val{P}, ::Val{R}, m::DeviceManifold{D}) where {P,R,D} =
+    Op{D,!P,R,P,R}(m.host, _op(:ddf_op_hodge, m, P, R))
+DDF.invhodge(::Val{P}, ::Val{R}, m::DeviceManifold{D}) where {P,R,D} =
+    Op{D,!P,R,P,R}(m.host, _op(:ddf_op_invhodge, m, P, R))
+DDF.coderiv(::Val{P}, ::Val{R}, m::DeviceManifold{D}) where {P,R,D} =
+    Op{D,P,R - (P == Pr ? 1 : -1),P,R}(m.host, _op(:ddf_op_coderiv, m, P, R))
+DDF.laplace(::Val{P}, ::Val{R}, m::DeviceManifold{D}) where {P,R,D} =
+    Op{D,P,R,P,R}(m.host, _op(:ddf_op_laplace, m, P, R))
+DDF.isboundary(::Val{Pr}, ::Val{R}, m::DeviceManifold{D}) where {R,D} =
+    Op{D,Pr,R,Pr,R}(m.host, _op(:ddf_op_isboundary, m, Pr, R))
+
+# Op.values algebra used by src/Ops.jl:178-276 (dnz is the identity on DeviceOp: Ops.jl:40)
+function Base.:*(A::DeviceOp, B::DeviceOp)                       # Ops.jl:228-232
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddf_op_compose, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), A.h, B.h, r))
+    return DeviceOp(r[], A.m)
+end
+function Base.adjoint(A::DeviceOp)                               # Ops.jl:258-260
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddf_op_adjoint, lib), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), A.h, r))
+    return DeviceOp(r[], A.m)
+end
+function Base.:*(a::Number, A::DeviceOp)                         # Ops.jl:198-200
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddf_op_scale, lib), Cint, (Cdouble, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), Float64(a), A.h, r))
+    return DeviceOp(r[], A.m)
+end
+function Base.:+(A::DeviceOp, B::DeviceOp)                       # Ops.jl:186-190
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddf_op_add, lib), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), A.h, 1.0, B.h, r))
+    return DeviceOp(r[], A.m)
+end
+Base.:-(A::DeviceOp, B::DeviceOp) = A + (-1.0) * B
+
+# Op*Fun (src/Ops.jl:273-276) ends in `A.values * f.values.vec`:
+function Base.:*(A::DeviceOp, x::DeviceVector)
+    n, _ = size(A)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddf_vec_create, lib), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), A.m.ctx.h, n, r))
+    y = DeviceVector(r[], n)
+    check(ccall((:ddf_op_apply, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), A.h, x.h, y.h))
+    return y
+end
+# the ODE right-hand side of examples/wave.jl:100  f!(dU,U,p,t) = mul!(dU, F, U)
+function LinearAlgebra.mul!(y::DeviceVector, A::DeviceOp, x::DeviceVector)
+    check(ccall((:ddf_op_apply, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), A.h, x.h, y.h))
+    return y
+end
+
+# fused step (north_star): v += dt (1-b).(L u); u += dt (1-b).v
+function leapfrog!(m::DeviceManifold, u::DeviceVector, v::DeviceVector, dt::Float64, nsteps::Int)
+    check(ccall((:ddf_wave_leapfrog, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint),
+                m.h, u.h, v.h, dt, nsteps))
+    return u, v
+end
+
+end # module
