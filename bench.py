@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -241,7 +241,7 @@ def run_b200(args):
     if N == 1:
         mfd = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx, assemble=False)
     else:
-        mfd, slab = ddf.dist.slab_hypercube(3, (n, n, n * N), ctx)
+        mfd, slab = ddf.dist.slab_hypercube(3, (n, n, n * N), ctx, assemble=False)
     ctx.sync()
     ctx.tic()
     ddf._lib.call("ddf_mesh_assemble", mfd._h)
@@ -268,12 +268,12 @@ def run_b200(args):
             h[k].apply(x[k], z[k])
 
     K, W = args.steps, args.warmup
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # sampled from the warm-up to the end of the timed wave steps
     for _ in range(W):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     l0 = ctx.launch_count()
     ctx.tic()
     for s in range(K):

@@ -9,6 +9,25 @@
 #pragma once
 #include "common.cuh"
 
+#define DDF_SELL_PAD 0xFFFFFFFFu
+#define DDF_SELL_WIN 256
+// SELL-32-256 storage (built by sell.cuh)
+struct SellBufs {
+  DevBuf<uint32_t> ptr;     // entry offset per slice of 32 sorted rows (nwindows*8 + 1)
+  DevBuf<uint8_t> perm8;    // sorted position -> row offset inside its 256-row window
+  DevBuf<uint32_t> col;     // explicit indices (released when compressed)
+  DevBuf<double> val;
+  // compressed index stream: per slice a bit mask of uniform-offset columns and a word offset
+  bool compressed = false;
+  DevBuf<uint32_t> umask, iptr, cidx;
+  int64_t padded = 0;       // stored entries incl. padding
+  int64_t index_words = 0;  // 32-bit words of index data actually stored
+  void release() {
+    ptr.release(); perm8.release(); col.release(); val.release(); umask.release(); iptr.release(); cidx.release();
+    padded = 0; index_words = 0; compressed = false;
+  }
+};
+
 struct ddf_mesh {
   ddf_ctx* ctx = nullptr;
   int D = 0, C = 0;
@@ -43,6 +62,13 @@ struct ddf_mesh {
   DevBuf<int32_t> adj_nbr;               // nnz column j, ascending within a row
   DevBuf<double> adj_l;                  // nnz L[i,j] = fl(ih0[i] * star1[e]); L[i,i] = sequential sum of -L[i,j]
   int64_t adj_nnz = 0;
+  // the same rows in SELL-32-256 (sell.cuh), used by the row kernels when the padding is small
+  bool wave_sell = false;
+  SellBufs lsell;
+  // SELL copies of the row-CSR of d_R (boundary / dual derivative apply); state 0 = not
+  // built, 1 = in use, 2 = rejected (padding too large -> CSR kernel)
+  int bsell_state[DDF_MAXD + 1] = {0};
+  SellBufs bsell[DDF_MAXD + 1];
   DevBuf<double> utmp;                   // V   ping-pong buffer of the fused step
 
   // slab halo of the distributed wave step (comm.cu): vertex planes along the

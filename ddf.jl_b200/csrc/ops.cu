@@ -22,7 +22,9 @@
 #include <memory>
 
 #include "mesh.cuh"
+#include "sell.cuh"
 
+extern int g_tune_fixed;
 int ddf_laplace0_apply(ddf_mesh* m, const double* x, double* y);   // wave.cu
 
 enum OpKind { OPK_ZERO = 0, OPK_FIXED, OPK_CSRSIGN, OPK_DIAG, OPK_CSRF64, OPK_LAPLACE0, OPK_CHAIN, OPK_SUM };
@@ -161,6 +163,44 @@ k_apply_csrsign(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict_
   if (POST) a = __dmul_rn(post[i], a);
   if (alpha != 1.0) a = __dmul_rn(alpha, a);
   y[i] = a;
+}
+
+// The same operator from the SELL-32 copy of the row-CSR (sell.cuh): coalesced index loads.
+template <bool PRE, bool POST>
+__global__ void __launch_bounds__(256)
+k_apply_sellsign(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict__ perm8,
+                 const uint32_t* __restrict__ scol, int64_t nrows, const double* __restrict__ x,
+                 const double* __restrict__ pre, const double* __restrict__ post, double alpha,
+                 double* __restrict__ y) {
+  const int64_t r = (int64_t)blockIdx.x * DDF_SELL_WIN + threadIdx.x;        // sorted position
+  const int64_t i = (int64_t)blockIdx.x * DDF_SELL_WIN + perm8[r];           // the row it holds
+  const uint64_t pol_stream = make_policy_evict_first();
+  const uint64_t pol_keep = make_policy_evict_last();
+  const int64_t s = r >> 5;
+  const uint32_t base = sell_ptr[s] + (uint32_t)(r & 31);
+  const uint32_t w = (sell_ptr[s + 1] - sell_ptr[s]) >> 5;
+  double a = 0.0;
+  for (uint32_t q0 = 0; q0 < w; q0 += 8) {
+    uint32_t cw[8];
+    double xv[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      cw[q] = (q0 + q < w) ? (uint32_t)ld_stream_int(reinterpret_cast<const int*>(scol) + (size_t)base + (size_t)(q0 + q) * 32)
+                           : DDF_SELL_PAD;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const uint32_t c = cw[q] != DDF_SELL_PAD ? (cw[q] & 0x7fffffffu) : 0u;
+      xv[q] = ld_keep_f64(x + c, pol_keep);
+      if (PRE) xv[q] = __dmul_rn(ld_keep_f64(pre + c, pol_keep), xv[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (cw[q] != DDF_SELL_PAD) a = (cw[q] >> 31) ? __dsub_rn(a, xv[q]) : __dadd_rn(a, xv[q]);
+  }
+  if (i >= nrows) return;
+  if (POST) a = __dmul_rn(post[i], a);
+  if (alpha != 1.0) a = __dmul_rn(alpha, a);
+  st_hint_f64(y + i, a, pol_stream);
 }
 
 __global__ void k_apply_diag(const double* __restrict__ d, double sign_or_scale, const double* __restrict__ x,
@@ -927,7 +967,31 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
     const int W = f->R + 1;
     return launch_fixed(f->ctx, m->bnd_table(f->R), W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
   }
-  return launch_csrsign(f->ctx, m->brow_ptr[f->R].p, m->bcol[f->R].p, f->nrows, x, pre_d, post_d, a, y);
+  // boundary / dual derivative: SELL-32 copy of the row-CSR when its padding is small, else CSR
+  const int R = f->R;
+  if (m->bsell_state[R] == 0 && f->nrows > 0) {
+    const int64_t nnz = (int64_t)(R + 1) * m->n[R];
+    if (nnz < 3 * f->nrows) {
+      m->bsell_state[R] = 2;           // rows of 1-2 entries (faces of the top simplices): CSR is already coalesced
+    } else {
+      // length-only sort: rows of equal length stay in row order (consecutive y stores, measured 20 % faster
+      // than the stencil-signature sort on the Kuhn mesh)
+      DDF_CHECK(sell_build(f->ctx, m->brow_ptr[R].p, m->bcol[R].p, nullptr, f->nrows, m->bsell[R], false, false));
+      if (m->bsell[R].padded <= nnz + nnz / 8) m->bsell_state[R] = 1;
+      else { m->bsell_state[R] = 2; m->bsell[R].release(); }
+    }
+  }
+  if (m->bsell_state[R] == 1 && g_tune_fixed != 9) {
+    const int grid = (int)ceil_div64(f->nrows, DDF_SELL_WIN);
+    const SellBufs& sb = m->bsell[R];
+    if (pre_d && post_d) k_apply_sellsign<true, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y);
+    else if (pre_d) k_apply_sellsign<true, false><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y);
+    else if (post_d) k_apply_sellsign<false, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y);
+    else k_apply_sellsign<false, false><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y);
+    DDF_LAUNCH_CHECK(f->ctx);
+    return 0;
+  }
+  return launch_csrsign(f->ctx, m->brow_ptr[R].p, m->bcol[R].p, f->nrows, x, pre_d, post_d, a, y);
 }
 
 static bool fusable_diag(const OpRef& f) {

@@ -23,6 +23,7 @@
 #include <cub/cub.cuh>
 
 #include "mesh.cuh"
+#include "sell.cuh"
 
 int ddf_mesh_require_star(ddf_mesh* m, int R);   // ops.cu
 int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n, double* out);   // core.cu
@@ -113,6 +114,13 @@ int ddf_mesh_require_wave(ddf_mesh* m) {
                                                         m->star[1].p, nv, nullptr, m->adj_ptr.p, m->adj_nbr.p,
                                                         m->adj_l.p);
   DDF_LAUNCH_CHECK(ctx);
+  // SELL-32-256 copy for the row kernels; keep it when the padding costs < 12.5 % extra entries.
+  // Measured at C4 (profiles/r01_tuning.md): explicit indices stream at 95 % of the copy peak; the compressed
+  // index stream (tuning bit 4) saves 17 % of the bytes but adds a dependent load and is latency-bound -> off.
+  DDF_CHECK(sell_build(ctx, m->adj_ptr.p, reinterpret_cast<const uint32_t*>(m->adj_nbr.p), m->adj_l.p, nv, m->lsell,
+                       (g_tune_wave & 4) != 0, (g_tune_wave & 8) != 0));
+  m->wave_sell = m->lsell.padded <= m->adj_nnz + m->adj_nnz / 8;
+  if (!m->wave_sell) m->lsell.release();
   m->has_wave = true;
   return 0;
 }
@@ -176,7 +184,54 @@ __global__ void __launch_bounds__(256) k_rows_thread(RowArgs a) {
   row_epilogue<MODE>(a, i, acc, pol_stream);
 }
 
-// default: warp-cooperative row streaming
+// SELL-32: one thread per row, coalesced index/value loads, batches of 8 gathers in flight
+// COMPRESSED: indices come from the per-slice stream (uniform-offset columns hold one word)
+template <int MODE, bool COMPRESSED>
+__global__ void __launch_bounds__(256)
+k_rows_sell(RowArgs a, const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict__ perm8,
+            const uint32_t* __restrict__ snbr, const double* __restrict__ sl, const uint32_t* __restrict__ umask,
+            const uint32_t* __restrict__ iptr, int64_t first_window) {
+  const int64_t win = first_window + blockIdx.x;                            // one block = one sorted window
+  const int64_t r = win * DDF_SELL_WIN + threadIdx.x;                        // sorted position
+  const int64_t i = win * DDF_SELL_WIN + perm8[r];                           // the row it holds
+  const uint64_t pol_stream = make_policy_evict_first();
+  const uint64_t pol_keep = make_policy_evict_last();
+  const int64_t s = r >> 5;
+  const uint32_t lane = (uint32_t)(r & 31);
+  const uint32_t base = sell_ptr[s] + lane;
+  const uint32_t w = (sell_ptr[s + 1] - sell_ptr[s]) >> 5;
+  const uint32_t um = COMPRESSED ? umask[s] : 0u;
+  const uint32_t ib = COMPRESSED ? iptr[s] : 0u;
+  double acc = 0.0;
+  for (uint32_t q0 = 0; q0 < w; q0 += 8) {
+    uint32_t j[8];
+    double l[8], uu[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const uint32_t c = q0 + q;
+      const bool ok = c < w;                     // warp-uniform
+      const size_t pos = (size_t)base + (size_t)c * 32;
+      if (COMPRESSED) {
+        const bool uni = c < 32 && ((um >> c) & 1u);                      // warp-uniform
+        const uint32_t word = ok ? (uint32_t)ld_stream_int(reinterpret_cast<const int*>(snbr) + ib +
+                                                           sell_col_offset(um, c) + (uni ? 0u : lane))
+                                 : DDF_SELL_PAD;
+        j[q] = (ok && uni) ? (uint32_t)i + word : word;
+      } else {
+        j[q] = ok ? (uint32_t)ld_stream_int(reinterpret_cast<const int*>(snbr) + pos) : DDF_SELL_PAD;
+      }
+      l[q] = ok ? ld_stream_f64(sl + pos) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) uu[q] = ld_keep_f64(a.u + (j[q] != DDF_SELL_PAD ? j[q] : 0u), pol_keep);
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (j[q] != DDF_SELL_PAD) acc = __dadd_rn(acc, __dmul_rn(l[q], uu[q]));
+  }
+  if (i >= a.row0 && i < a.row1) row_epilogue<MODE>(a, i, acc, pol_stream);
+}
+
+// variant 2/3: warp-cooperative row streaming through shared memory (kept for A/B timing)
 #define DDF_ROW_CAP 512       // products staged per warp and chunk (4 KB)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_rows_warp(RowArgs a) {
@@ -234,7 +289,17 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
   a.nbr = m->adj_nbr.p;
   a.lval = m->adj_l.p;
   a.isb = m->isbnd[0].p;
-  if (g_tune_wave != 2 && g_tune_wave != 3) {   // default: one thread per row (measured faster than the staged variant)
+  if (m->wave_sell && (g_tune_wave & 3) == 0) {        // default: SELL-32 rows
+    const int64_t w0 = a.row0 / DDF_SELL_WIN, w1 = (a.row1 + DDF_SELL_WIN - 1) / DDF_SELL_WIN;
+    if (w1 - w0 > 0x7fffffffLL) DDF_FAIL("grid too large");
+    const SellBufs& sb = m->lsell;
+    if (sb.compressed)
+      k_rows_sell<MODE, true><<<(int)(w1 - w0), DDF_SELL_WIN, 0, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.cidx.p, sb.val.p,
+                                                                            sb.umask.p, sb.iptr.p, w0);
+    else
+      k_rows_sell<MODE, false><<<(int)(w1 - w0), DDF_SELL_WIN, 0, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.col.p, sb.val.p,
+                                                                             nullptr, nullptr, w0);
+  } else if ((g_tune_wave & 3) < 2) {   // CSR, one thread per row
     int grid;
     DDF_CHECK(grid_for(n, 256, &grid));
     k_rows_thread<MODE><<<grid, 256, 0, stream>>>(a);
@@ -243,7 +308,7 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
     DDF_CHECK(grid_for(n, 256, &grid));       // 8 warps x 32 rows per block
     // the staging buffer must not eat the L1 that serves the u-gathers: cap the shared-memory carveout
     static int carve_set[3] = {-1, -1, -1};
-    const int carve = g_tune_wave == 2 ? 50 : (g_tune_wave == 3 ? -1 : 25);
+    const int carve = (g_tune_wave & 3) == 2 ? 50 : -1;
     if (carve_set[MODE] != carve) {
       DDF_CUDA(cudaFuncSetAttribute(k_rows_warp<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
       carve_set[MODE] = carve;
@@ -362,7 +427,9 @@ extern "C" int ddf_wave_step_bytes(ddf_mesh* m, int64_t* algorithmic, int64_t* f
   DDF_CHECK(ddf_mesh_require_assembled(m));
   const int64_t E = m->n[1], V = m->n[0];
   *algorithmic = E * 16 + V * 41;                  // E*(2*4+8) + V*(8*5+1)
-  const int64_t nnz = m->has_wave ? m->adj_nnz : 2 * E + V;
-  *format_bytes = nnz * 12 + V * (4 + 8 * 4 + 1);  // what this format streams per step
+  // what this format streams per step: 12 B per stored entry + u, v (r/w), u', mask per vertex + row offsets
+  if (m->has_wave && m->wave_sell)
+    *format_bytes = m->lsell.padded * 8 + m->lsell.index_words * 4 + V * (8 * 4 + 1 + 1) + (V / 32 + 1) * 12;
+  else *format_bytes = (m->has_wave ? m->adj_nnz : 2 * E + V) * 12 + V * (4 + 8 * 4 + 1);
   return 0;
 }

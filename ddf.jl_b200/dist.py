@@ -87,7 +87,8 @@ def init_comm(ctx, group=None):
     ctx.comm_init(world, rank, obj[0])
 
 
-def slab_hypercube(D: int, nelts: Sequence[int], ctx, rank: Optional[int] = None, nranks: Optional[int] = None):
+def slab_hypercube(D: int, nelts: Sequence[int], ctx, rank: Optional[int] = None, nranks: Optional[int] = None,
+                   assemble: bool = True):
     """This rank's slab of large_hypercube_manifold(Val(D); nelts) as a device mesh
     with global coordinates and weights (hdiv = nelts[0]; the reference requires all
     nelts equal, ManifoldConstructors.jl:262 -- slabs relax that along the last axis
@@ -98,6 +99,6 @@ def slab_hypercube(D: int, nelts: Sequence[int], ctx, rank: Optional[int] = None
     plane = int(np.prod([n + 1 for n in nelts[:-1]])) if D > 1 else 1
     slab = partition_slabs(int(nelts[-1]), nranks, plane)[rank]
     local = list(nelts[:-1]) + [slab.nz_cells]
-    mfd = large_hypercube_manifold(D, local, ctx=ctx, hdiv=int(nelts[0]), z0=slab.z_cell_lo)
+    mfd = large_hypercube_manifold(D, local, ctx=ctx, hdiv=int(nelts[0]), z0=slab.z_cell_lo, assemble=assemble)
     mfd.set_halo(plane, slab.ghost_lo, slab.ghost_hi)
     return mfd, slab

@@ -56,17 +56,46 @@ def main():
         print(f"fixed variant {var}: {row}", flush=True)
     ddf._lib.call("ddf_set_tuning", b"fixed", 0)
 
+    # boundary / dual derivative (row-CSR vs SELL-32): y = d_k^T-type applies
+    dd = [ddf.deriv(ddf.Dl, k, m) for k in (1, 2, 3)]
+    xd = [ddf.rand_fun(m, ddf.Dl, k, seed=k + 7) for k in (1, 2, 3)]
+    yd = [ddf.Fun(m, ddf.Dl, k - 1) for k in (1, 2, 3)]
+    refd = None
+    for var, name in ((0, "sell"), (9, "csr")):
+        ddf._lib.call("ddf_set_tuning", b"fixed", var)
+        row = {}
+        for n_, k in enumerate((1, 2, 3)):
+            ms = timeit(lambda n_=n_: dd[n_].apply(xd[n_], yd[n_]))
+            b = (k + 1) * cnt[k] * 4 + cnt[k - 1] * 12 + cnt[k] * 8
+            row[f"dual_d{k}"] = (round(ms, 4), round(b / ms * 1e-6 / peak, 4))
+        vals = [yy.values[::997].copy() for yy in yd]
+        if refd is None:
+            refd = vals
+        else:
+            for a, b_ in zip(refd, vals):
+                assert np.array_equal(a, b_), "sell != csr"
+        out[f"dual_{name}"] = row
+        print(f"dual deriv {name}: {row}", flush=True)
+    ddf._lib.call("ddf_set_tuning", b"fixed", 0)
+
     u0 = ddf.sample(m, "wave")
     dt = ddf.wave_dt(m)
     alg, fmt = ddf.wave_step_bytes(m)
     refu = None
     for var in [int(v) for v in args.wave.split(",")]:
         ddf._lib.call("ddf_set_tuning", b"wave", var)
-        u, v = u0.copy(), ddf.Fun(m, ddf.Pr, 0)
-        ddf.wave_leapfrog(m, u, v, dt, 3)
+        if var & 12 or var == 0:     # build-time flags: fresh mesh so that the L rows are rebuilt
+            m2 = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
+            m2._geometry()
+        else:
+            m2 = m
+        u, v = ddf.sample(m2, "wave"), ddf.Fun(m2, ddf.Pr, 0)
+        alg, fmt = ddf.wave_step_bytes(m2)
+        ddf.wave_leapfrog(m2, u, v, dt, 3)
+        alg, fmt = ddf.wave_step_bytes(m2)
         ctx.sync()
         ctx.tic()
-        ddf.wave_leapfrog(m, u, v, dt, args.reps)
+        ddf.wave_leapfrog(m2, u, v, dt, args.reps)
         ms = ctx.toc() / args.reps
         uv = u.values[::97].copy()
         if refu is None:
@@ -74,7 +103,9 @@ def main():
         else:
             assert np.array_equal(refu, uv), f"wave variant {var} differs"
         out[f"wave{var}"] = (round(ms, 4), round(alg / ms * 1e-6 / peak, 4), round(fmt / ms * 1e-6 / peak, 4))
-        print(f"wave variant {var}: ms={ms:.4f} frac_alg={alg / ms * 1e-6 / peak:.4f} frac_fmt={fmt / ms * 1e-6 / peak:.4f}", flush=True)
+        if m2 is not m:
+            m2.close()
+        print(f"wave variant {var}: ms={ms:.4f} fmtGB={fmt/1e9:.3f} frac_alg={alg / ms * 1e-6 / peak:.4f} frac_fmt={fmt / ms * 1e-6 / peak:.4f}", flush=True)
     print(json.dumps(out))
 
 
