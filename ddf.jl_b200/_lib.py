@@ -64,6 +64,8 @@ SIGNATURES = {
     "ddf_vec_length": [_P, _i64p],
     "ddf_vec_upload": [_P, _f64p],
     "ddf_vec_download": [_P, _f64p],
+    "ddf_vec_upload_async": [_P, _f64p],
+    "ddf_vec_download_async": [_P, _f64p],
     "ddf_vec_fill": [_P, _f64],
     "ddf_vec_copy": [_P, _P],
     "ddf_vec_sample": [_P, _int, _P],

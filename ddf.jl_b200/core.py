@@ -260,6 +260,18 @@ class Fun:
         call("ddf_vec_upload", self._h, _f64p(v))
         return self
 
+    def upload_async(self, pinned: np.ndarray):
+        """Asynchronous upload from a page-locked float64 array that the caller keeps alive until ctx.sync()."""
+        assert pinned.dtype == np.float64 and pinned.flags.c_contiguous and pinned.shape == (len(self),)
+        call("ddf_vec_upload_async", self._h, _f64p(pinned))
+        return self
+
+    def download_async(self, pinned: np.ndarray):
+        """Asynchronous download into a page-locked float64 array; valid after ctx.sync()."""
+        assert pinned.dtype == np.float64 and pinned.flags.c_contiguous and pinned.shape == (len(self),)
+        call("ddf_vec_download_async", self._h, _f64p(pinned))
+        return pinned
+
     @property
     def values(self) -> np.ndarray:
         out = np.empty(len(self))

@@ -153,6 +153,7 @@ static int halo_exchange_on(ddf_mesh* m, double* u, cudaStream_t stream) {
 extern "C" int ddf_halo_exchange(ddf_mesh* m, ddf_vec* u) {
   DDF_TRY_BEGIN
   if (u->n != m->n[0]) DDF_FAIL("halo_exchange: vector must be a vertex cochain");
+  DDF_CHECK(ddf_vec_settle(u));
   return halo_exchange_on(m, u->d.p, m->ctx->stream);
   DDF_TRY_END
 }
@@ -165,6 +166,8 @@ extern "C" int ddf_wave_leapfrog_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* v, doubl
   const int64_t nv = m->n[0];
   if (u->n != nv || v->n != nv) DDF_FAIL("wave_leapfrog_dist: vectors must have length n0");
   if (!m->halo_plane) DDF_FAIL("wave_leapfrog_dist: slab not described (ddf_mesh_set_halo)");
+  DDF_CHECK(ddf_vec_settle(u));
+  DDF_CHECK(ddf_vec_settle(v));
   if ((int64_t)m->utmp.n != nv) {
     DDF_CHECK(m->utmp.alloc(ctx, nv));
     // ghost planes that are never written must still hold finite data

@@ -59,6 +59,7 @@ struct ddf_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;     // compute stream
   cudaStream_t comm_stream = nullptr;  // halo / NCCL stream
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // asynchronous host copies (one per PCIe direction)
   cudaEvent_t ev_tic = nullptr, ev_toc = nullptr, ev_a = nullptr, ev_b = nullptr;
   std::vector<cudaEvent_t> events;   // numbered timing events (ddf_event_record)
   int64_t bytes_in_use = 0;
@@ -109,7 +110,12 @@ struct ddf_vec {
   ddf_ctx* ctx = nullptr;
   DevBuf<double> d;
   int64_t n = 0;
+  // pending asynchronous copies (ddf_vec_upload_async / ddf_vec_download_async)
+  cudaEvent_t ev_up = nullptr, ev_down = nullptr;
+  bool up_pending = false, down_pending = false;
 };
+// make the compute stream wait for v's pending copies (call before any kernel touches v)
+int ddf_vec_settle(ddf_vec* v);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

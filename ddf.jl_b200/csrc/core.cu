@@ -59,6 +59,8 @@ extern "C" int ddf_ctx_create(int device, ddf_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   DDF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   DDF_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  DDF_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+  DDF_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
   DDF_CUDA(cudaEventCreate(&c->ev_tic));
   DDF_CUDA(cudaEventCreate(&c->ev_toc));
   DDF_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
@@ -84,6 +86,8 @@ extern "C" int ddf_ctx_destroy(ddf_ctx* c) {
   cudaEventDestroy(c->ev_b);
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->comm_stream);
+  cudaStreamDestroy(c->h2d_stream);
+  cudaStreamDestroy(c->d2h_stream);
   delete c;
   return 0;
 }
@@ -92,6 +96,8 @@ extern "C" int ddf_sync(ddf_ctx* c) {
   DDF_CUDA(cudaSetDevice(c->device));
   DDF_CUDA(cudaStreamSynchronize(c->stream));
   DDF_CUDA(cudaStreamSynchronize(c->comm_stream));
+  DDF_CUDA(cudaStreamSynchronize(c->h2d_stream));
+  DDF_CUDA(cudaStreamSynchronize(c->d2h_stream));
   return 0;
 }
 
@@ -163,6 +169,10 @@ extern "C" int ddf_vec_create(ddf_ctx* ctx, int64_t n, ddf_vec** out) {
 extern "C" int ddf_vec_destroy(ddf_vec* v) {
   if (!v) return 0;
   cudaStreamSynchronize(v->ctx->stream);
+  if (v->up_pending) cudaEventSynchronize(v->ev_up);
+  if (v->down_pending) cudaEventSynchronize(v->ev_down);
+  if (v->ev_up) cudaEventDestroy(v->ev_up);
+  if (v->ev_down) cudaEventDestroy(v->ev_down);
   delete v;
   return 0;
 }
@@ -170,14 +180,53 @@ extern "C" int ddf_vec_length(ddf_vec* v, int64_t* out) { *out = v->n; return 0;
 
 extern "C" int ddf_vec_upload(ddf_vec* v, const double* host) {
   if (v->n == 0) return 0;
+  DDF_CHECK(ddf_vec_settle(v));
   DDF_CUDA(cudaMemcpyAsync(v->d.p, host, v->n * sizeof(double), cudaMemcpyHostToDevice, v->ctx->stream));
   DDF_CUDA(cudaStreamSynchronize(v->ctx->stream));   // host pointer is borrowed for the call only
   return 0;
 }
 extern "C" int ddf_vec_download(ddf_vec* v, double* host) {
   if (v->n == 0) return 0;
+  DDF_CHECK(ddf_vec_settle(v));
   DDF_CUDA(cudaMemcpyAsync(host, v->d.p, v->n * sizeof(double), cudaMemcpyDeviceToHost, v->ctx->stream));
   DDF_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  return 0;
+}
+
+// ---- asynchronous transfers on dedicated copy streams (full-duplex PCIe, overlapped with compute).
+// Ordering is tracked per vector: kernels that touch v first wait for its pending copies.
+int ddf_vec_settle(ddf_vec* v) {
+  ddf_ctx* c = v->ctx;
+  if (v->up_pending) { DDF_CUDA(cudaStreamWaitEvent(c->stream, v->ev_up, 0)); v->up_pending = false; }
+  if (v->down_pending) { DDF_CUDA(cudaStreamWaitEvent(c->stream, v->ev_down, 0)); v->down_pending = false; }
+  return 0;
+}
+extern "C" int ddf_vec_upload_async(ddf_vec* v, const double* host) {
+  if (v->n == 0) return 0;
+  ddf_ctx* c = v->ctx;
+  if (!v->ev_up) DDF_CUDA(cudaEventCreateWithFlags(&v->ev_up, cudaEventDisableTiming));
+  if (!v->ev_down) DDF_CUDA(cudaEventCreateWithFlags(&v->ev_down, cudaEventDisableTiming));
+  // kernels already queued on the compute stream may still read v
+  DDF_CUDA(cudaEventRecord(c->ev_a, c->stream));
+  DDF_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->ev_a, 0));
+  if (v->down_pending) DDF_CUDA(cudaStreamWaitEvent(c->h2d_stream, v->ev_down, 0));
+  DDF_CUDA(cudaMemcpyAsync(v->d.p, host, v->n * sizeof(double), cudaMemcpyHostToDevice, c->h2d_stream));
+  DDF_CUDA(cudaEventRecord(v->ev_up, c->h2d_stream));
+  v->up_pending = true;
+  return 0;
+}
+extern "C" int ddf_vec_download_async(ddf_vec* v, double* host) {
+  if (v->n == 0) return 0;
+  ddf_ctx* c = v->ctx;
+  if (!v->ev_up) DDF_CUDA(cudaEventCreateWithFlags(&v->ev_up, cudaEventDisableTiming));
+  if (!v->ev_down) DDF_CUDA(cudaEventCreateWithFlags(&v->ev_down, cudaEventDisableTiming));
+  // the producing kernel is on the compute stream
+  DDF_CUDA(cudaEventRecord(c->ev_b, c->stream));
+  DDF_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->ev_b, 0));
+  if (v->up_pending) DDF_CUDA(cudaStreamWaitEvent(c->d2h_stream, v->ev_up, 0));
+  DDF_CUDA(cudaMemcpyAsync(host, v->d.p, v->n * sizeof(double), cudaMemcpyDeviceToHost, c->d2h_stream));
+  DDF_CUDA(cudaEventRecord(v->ev_down, c->d2h_stream));
+  v->down_pending = true;
   return 0;
 }
 
@@ -187,6 +236,7 @@ __global__ void k_fill(double* __restrict__ p, int64_t n, double a) {
 }
 extern "C" int ddf_vec_fill(ddf_vec* v, double a) {
   if (v->n == 0) return 0;
+  DDF_CHECK(ddf_vec_settle(v));
   int grid;
   DDF_CHECK(grid_for(v->n, 256, &grid));
   k_fill<<<grid, 256, 0, v->ctx->stream>>>(v->d.p, v->n, a);
@@ -196,6 +246,8 @@ extern "C" int ddf_vec_fill(ddf_vec* v, double a) {
 extern "C" int ddf_vec_copy(ddf_vec* dst, ddf_vec* src) {
   if (dst->n != src->n) DDF_FAIL("vec_copy: length mismatch %lld vs %lld", (long long)dst->n, (long long)src->n);
   if (dst->n == 0) return 0;
+  DDF_CHECK(ddf_vec_settle(dst));
+  DDF_CHECK(ddf_vec_settle(src));
   DDF_CUDA(cudaMemcpyAsync(dst->d.p, src->d.p, dst->n * sizeof(double), cudaMemcpyDeviceToDevice, dst->ctx->stream));
   return 0;
 }
@@ -224,6 +276,9 @@ __global__ void k_axpby(double a, const double* __restrict__ x, double b, const 
 extern "C" int ddf_vec_axpby(double a, ddf_vec* x, double b, ddf_vec* y, ddf_vec* z) {
   if (x->n != z->n || (y && y->n != z->n)) DDF_FAIL("vec_axpby: length mismatch");
   if (z->n == 0) return 0;
+  DDF_CHECK(ddf_vec_settle(x));
+  if (y) DDF_CHECK(ddf_vec_settle(y));
+  DDF_CHECK(ddf_vec_settle(z));
   int grid;
   DDF_CHECK(grid_for(ceil_div64(z->n, 2), 256, &grid));
   k_axpby<<<grid, 256, 0, z->ctx->stream>>>(a, x->d.p, b, y ? y->d.p : nullptr, z->d.p, z->n);
@@ -238,6 +293,9 @@ __global__ void k_mul(const double* __restrict__ x, const double* __restrict__ y
 extern "C" int ddf_vec_mul(ddf_vec* x, ddf_vec* y, ddf_vec* z) {
   if (x->n != z->n || y->n != z->n) DDF_FAIL("vec_mul: length mismatch");
   if (z->n == 0) return 0;
+  DDF_CHECK(ddf_vec_settle(x));
+  DDF_CHECK(ddf_vec_settle(y));
+  DDF_CHECK(ddf_vec_settle(z));
   int grid;
   DDF_CHECK(grid_for(z->n, 256, &grid));
   k_mul<<<grid, 256, 0, z->ctx->stream>>>(x->d.p, y->d.p, z->d.p, z->n);
@@ -252,6 +310,8 @@ __global__ void k_div(const double* __restrict__ x, double a, double* __restrict
 extern "C" int ddf_vec_div(ddf_vec* x, double a, ddf_vec* z) {
   if (x->n != z->n) DDF_FAIL("vec_div: length mismatch");
   if (z->n == 0) return 0;
+  DDF_CHECK(ddf_vec_settle(x));
+  DDF_CHECK(ddf_vec_settle(z));
   int grid;
   DDF_CHECK(grid_for(z->n, 256, &grid));
   k_div<<<grid, 256, 0, z->ctx->stream>>>(x->d.p, a, z->d.p, z->n);
@@ -275,6 +335,7 @@ __global__ void k_rand(double* __restrict__ p, int64_t n, uint64_t seed) {
 }
 extern "C" int ddf_vec_rand(ddf_vec* v, uint64_t seed) {
   if (v->n == 0) return 0;
+  DDF_CHECK(ddf_vec_settle(v));
   int grid;
   DDF_CHECK(grid_for(v->n, 256, &grid));
   k_rand<<<grid, 256, 0, v->ctx->stream>>>(v->d.p, v->n, seed);
@@ -351,6 +412,7 @@ int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n
 
 extern "C" int ddf_vec_norm(ddf_vec* v, int kind, double* out) {
   double r = 0;
+  DDF_CHECK(ddf_vec_settle(v));
   if (kind == DDF_NORM_INF) { DDF_CHECK(ddf_reduce(v->ctx, 3, v->d.p, nullptr, v->n, &r)); }
   else if (kind == DDF_NORM_1) { DDF_CHECK(ddf_reduce(v->ctx, 1, v->d.p, nullptr, v->n, &r)); }
   else if (kind == DDF_NORM_2) { DDF_CHECK(ddf_reduce(v->ctx, 2, v->d.p, nullptr, v->n, &r)); r = sqrt(r); }
@@ -360,8 +422,11 @@ extern "C" int ddf_vec_norm(ddf_vec* v, int kind, double* out) {
 }
 extern "C" int ddf_vec_dot(ddf_vec* x, ddf_vec* y, double* out) {
   if (x->n != y->n) DDF_FAIL("vec_dot: length mismatch");
+  DDF_CHECK(ddf_vec_settle(x));
+  DDF_CHECK(ddf_vec_settle(y));
   return ddf_reduce(x->ctx, 4, x->d.p, y->d.p, x->n, out);
 }
 extern "C" int ddf_vec_sum(ddf_vec* x, double* out) {
+  DDF_CHECK(ddf_vec_settle(x));
   return ddf_reduce(x->ctx, 0, x->d.p, nullptr, x->n, out);
 }

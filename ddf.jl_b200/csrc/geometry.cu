@@ -408,6 +408,7 @@ extern "C" int ddf_vec_sample(ddf_mesh* m, int kind, ddf_vec* out) {
   if (kind < 0 || kind > 2) DDF_FAIL("vec_sample: unknown field kind %d", kind);
   if (kind == 1 && m->C < 2) DDF_FAIL("vec_sample: field 1 needs C >= 2");
   if (!m->n[0]) return 0;
+  DDF_CHECK(ddf_vec_settle(out));
   int grid;
   DDF_CHECK(grid_for(m->n[0], 256, &grid));
   switch (m->C) {

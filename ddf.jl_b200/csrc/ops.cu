@@ -1087,6 +1087,8 @@ extern "C" int ddf_op_apply(ddf_op* A, ddf_vec* x, ddf_vec* y) {
   if (x->n != n->ncols) DDF_FAIL("apply: x has length %lld, operator has %lld columns", (long long)x->n, (long long)n->ncols);
   if (y->n != n->nrows) DDF_FAIL("apply: y has length %lld, operator has %lld rows", (long long)y->n, (long long)n->nrows);
   if (x == y) DDF_FAIL("apply: x and y must not alias");
+  DDF_CHECK(ddf_vec_settle(x));
+  DDF_CHECK(ddf_vec_settle(y));
   return apply_node(n, x->d.p, y->d.p);
   DDF_TRY_END
 }

@@ -370,6 +370,10 @@ extern "C" int ddf_wave_rhs(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, ddf_vec* du,
   const int64_t nv = m->n[0];
   if (u->n != nv || udot->n != nv || du->n != nv || dudot->n != nv) DDF_FAIL("wave_rhs: vectors must have length n0=%lld", (long long)nv);
   if (du == u || dudot == u) DDF_FAIL("wave_rhs: outputs must not alias u");
+  DDF_CHECK(ddf_vec_settle(u));
+  DDF_CHECK(ddf_vec_settle(udot));
+  DDF_CHECK(ddf_vec_settle(du));
+  DDF_CHECK(ddf_vec_settle(dudot));
   RowArgs a{};
   a.u = u->d.p;
   a.udot = udot->d.p;
@@ -414,6 +418,8 @@ extern "C" int ddf_wave_leapfrog(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt,
   if (u->n != nv || v->n != nv) DDF_FAIL("wave_leapfrog: vectors must have length n0=%lld", (long long)nv);
   if (u == v) DDF_FAIL("wave_leapfrog: u and v must not alias");
   if (!nv || nsteps <= 0) return 0;
+  DDF_CHECK(ddf_vec_settle(u));
+  DDF_CHECK(ddf_vec_settle(v));
   if ((int64_t)m->utmp.n != nv) DDF_CHECK(m->utmp.alloc(m->ctx, nv));
   for (int s = 0; s < nsteps; s++) {
     DDF_CHECK(ddf_leapfrog_launch(m, m->ctx->stream, u->d.p, v->d.p, m->utmp.p, dt, 0, nv));

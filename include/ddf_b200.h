@@ -119,6 +119,11 @@ int ddf_vec_destroy(ddf_vec* v);
 int ddf_vec_length(ddf_vec* v, int64_t* out);
 int ddf_vec_upload(ddf_vec* v, const double* host);
 int ddf_vec_download(ddf_vec* v, double* host);
+/* Asynchronous variants on dedicated copy streams (one per PCIe direction, overlapped with
+ * compute and with each other).  `host` must be page-locked and must stay valid until
+ * ddf_sync(ctx); ordering against kernels that touch `v` is tracked by the library. */
+int ddf_vec_upload_async(ddf_vec* v, const double* host);
+int ddf_vec_download_async(ddf_vec* v, double* host);
 int ddf_vec_fill(ddf_vec* v, double a);
 int ddf_vec_copy(ddf_vec* dst, ddf_vec* src);
 /* sample(Fun{D,Pr,0}, f, mfd) for the fields of the examples, evaluated at the

@@ -377,6 +377,32 @@ def test_large_mesh_properties(ddf, ctx):
     assert np.array_equal(u2.values, 4.0 * u1.values)
 
 
+def test_async_transfers_pipeline(ddf, ctx):
+    """upload_async -> apply -> download_async on three streams gives the same bits as the blocking path,
+    also when the same vectors are reused in the next round before the host synchronises."""
+    import torch
+    om = o.large_hypercube_manifold(3, (8, 8, 8))
+    dm = ddf.large_hypercube_manifold(3, (8, 8, 8), ctx=ctx)
+    d0, d1 = ddf.deriv(ddf.Pr, 0, dm), ddf.deriv(ddf.Pr, 1, dm)
+    n0, n1, n2 = (om.nsimplices(k) for k in range(3))
+    hx = torch.empty(n0, dtype=torch.float64).pin_memory().numpy()
+    hy = torch.empty(n1, dtype=torch.float64).pin_memory().numpy()
+    hz = torch.empty(n2, dtype=torch.float64).pin_memory().numpy()
+    x, y, z = ddf.Fun(dm, ddf.Pr, 0), ddf.Fun(dm, ddf.Pr, 1), ddf.Fun(dm, ddf.Pr, 2)
+    rng = np.random.default_rng(11)
+    for rnd in range(4):
+        xin = rng.integers(-99, 99, n0).astype(np.float64) if rnd % 2 else rng.standard_normal(n0)
+        hx[:] = xin
+        x.upload_async(hx)
+        d0.apply(x, y)
+        y.download_async(hy)
+        d1.apply(y, z)
+        z.download_async(hz)
+        ctx.sync()
+        assert np.array_equal(hy, o.apply_deriv(o.Pr, 0, om, xin))
+        assert np.array_equal(hz, o.apply_deriv(o.Pr, 1, om, o.apply_deriv(o.Pr, 0, om, xin)))
+
+
 def test_empty_and_tiny(ddf, ctx):
     """Edge cases of the reference's zoo: a single simplex per D and ragged tails."""
     for D in (1, 2, 3):
