@@ -99,6 +99,7 @@ SIGNATURES = {
     "ddf_wave_dt": [_P, _f64p],
     "ddf_wave_leapfrog": [_P, _P, _P, _f64, _int],
     "ddf_wave_step_bytes": [_P, _i64p, _i64p],
+    "ddf_wave_format": [_P, _P],
     "ddf_comm_unique_id": [_P],
     "ddf_comm_init": [_P, _int, _int, _P],
     "ddf_comm_destroy": [_P],

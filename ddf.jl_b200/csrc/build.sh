@@ -11,7 +11,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 pids=()
 for f in core mesh geometry ops wave comm; do
   src="$HERE/$f.cu"; obj="$OBJ/$f.o"
-  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/common.cuh" -nt "$obj" ] || [ "$HERE/mesh.cuh" -nt "$obj" ] || [ "$HERE/../../include/ddf_b200.h" -nt "$obj" ]; then
+  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/common.cuh" -nt "$obj" ] || [ "$HERE/mesh.cuh" -nt "$obj" ] || [ "$HERE/sell.cuh" -nt "$obj" ] || [ "$HERE/stage.cuh" -nt "$obj" ] || [ "$HERE/../../include/ddf_b200.h" -nt "$obj" ]; then
     ( $NVCC $FLAGS -c "$src" -o "$obj" > "$OBJ/$f.log" 2>&1 || { cat "$OBJ/$f.log"; exit 1; } ) &
     pids+=($!)
   fi

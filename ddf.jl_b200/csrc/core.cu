@@ -20,6 +20,7 @@ extern "C" int ddf_version(void) { return 100; }
 int ddf_dev_alloc(ddf_ctx* ctx, void** p, size_t bytes) {
   *p = nullptr;
   if (bytes == 0) return 0;
+  bytes = (bytes + 15) & ~(size_t)15;      // 16-byte TMA granules may read the pad element of an odd-length vector
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -34,7 +35,7 @@ int ddf_dev_alloc(ddf_ctx* ctx, void** p, size_t bytes) {
 void ddf_dev_free(ddf_ctx* ctx, void* p, size_t bytes) {
   if (!p) return;
   cudaFree(p);
-  if (ctx) ctx->bytes_in_use -= (int64_t)bytes;
+  if (ctx) ctx->bytes_in_use -= (int64_t)((bytes + 15) & ~(size_t)15);
 }
 
 extern "C" int ddf_ctx_create(int device, ddf_ctx** out) {

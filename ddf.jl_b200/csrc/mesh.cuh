@@ -28,6 +28,25 @@ struct SellBufs {
   }
 };
 
+// staged rows (stage.cuh): jagged slices, 16-bit slots into a per-window staging buffer of u
+struct StageBufs {
+  DevBuf<uint32_t> ptr;     // entry offset per slice of 32 sorted rows (nwindows*8 + 1), no padding
+  DevBuf<uint8_t> perm8;    // sorted position -> row offset inside its 256-row window
+  DevBuf<uint8_t> len8;     // row length by sorted position
+  DevBuf<uint32_t> tab;     // per window: nruns, nslots, (start_col, slot_off) per run
+  DevBuf<uint16_t> slot;    // per entry: slot of its column in the staging buffer
+  DevBuf<double> val;
+  uint32_t max_slots = 0;   // largest staging buffer of any window (Float64 elements)
+  uint32_t max_entries = 0; // most stored entries of any window (incl. its <= 7 padding entries)
+  int64_t entries = 0;      // stored entries incl. the per-window padding
+  int64_t nnz = 0;
+  bool ok = false;
+  void release() {
+    ptr.release(); perm8.release(); len8.release(); tab.release(); slot.release(); val.release();
+    max_slots = 0; max_entries = 0; entries = 0; nnz = 0; ok = false;
+  }
+};
+
 struct ddf_mesh {
   ddf_ctx* ctx = nullptr;
   int D = 0, C = 0;
@@ -65,6 +84,8 @@ struct ddf_mesh {
   // the same rows in SELL-32-256 (sell.cuh), used by the row kernels when the padding is small
   bool wave_sell = false;
   SellBufs lsell;
+  // ... or as staged rows (stage.cuh) when every window's columns fit a staging buffer (preferred)
+  StageBufs lstage;
   // SELL copies of the row-CSR of d_R (boundary / dual derivative apply); state 0 = not
   // built, 1 = in use, 2 = rejected (padding too large -> CSR kernel)
   int bsell_state[DDF_MAXD + 1] = {0};

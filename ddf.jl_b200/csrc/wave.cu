@@ -20,10 +20,12 @@
 // coalesced 128/256-byte requests, every lane issues its u-gathers back to back
 // (14 independent gathers per lane on the 3D Kuhn mesh), the products go to shared
 // memory and each lane then adds up its own row in order.
+#include <algorithm>
 #include <cub/cub.cuh>
 
 #include "mesh.cuh"
 #include "sell.cuh"
+#include "stage.cuh"
 
 int ddf_mesh_require_star(ddf_mesh* m, int R);   // ops.cu
 int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n, double* out);   // core.cu
@@ -114,6 +116,15 @@ int ddf_mesh_require_wave(ddf_mesh* m) {
                                                         m->star[1].p, nv, nullptr, m->adj_ptr.p, m->adj_nbr.p,
                                                         m->adj_l.p);
   DDF_LAUNCH_CHECK(ctx);
+  // staged rows (stage.cuh): 10 B per entry, no padding, u gathered from a TMA-staged shared-memory buffer.
+  // Tuning bit 16 disables it (A/B against the explicit-index SELL kernel below).
+  if (!(g_tune_wave & 16)) {
+    DDF_CHECK(stage_build(ctx, m->adj_ptr.p, m->adj_nbr.p, m->adj_l.p, nv, m->adj_nnz, m->lstage));
+    if (m->lstage.ok) {
+      m->has_wave = true;
+      return 0;
+    }
+  }
   // SELL-32-256 copy for the row kernels; keep it when the padding costs < 12.5 % extra entries.
   // Measured at C4 (profiles/r01_tuning.md): explicit indices stream at 95 % of the copy peak; the compressed
   // index stream (tuning bit 4) saves 17 % of the bytes but adds a dependent load and is latency-bound -> off.
@@ -231,6 +242,269 @@ k_rows_sell(RowArgs a, const uint32_t* __restrict__ sell_ptr, const uint8_t* __r
   if (i >= a.row0 && i < a.row1) row_epilogue<MODE>(a, i, acc, pol_stream);
 }
 
+// staged rows (stage.cuh): one block = one 256-row window.  Warp 0 issues the window's TMA bulk
+// copies of u into shared memory; meanwhile every thread prefetches its first batch of
+// (slot, value) pairs and its epilogue operands; the gather itself reads shared memory.
+// A slice is walked in SEGMENTS of constant active-lane count (rows are sorted by decreasing
+// length, so the active lanes are always a prefix): inside a segment a row's entries are
+// nact apart -- no per-entry ballots.  Slices of equal-length rows (all but <= 2-3 per window)
+// are a single segment of stride 32.
+template <int BATCH>
+__device__ __forceinline__ double stage_row_sum(const uint16_t* __restrict__ slot, const double* __restrict__ sl,
+                                                const double* stage, uint64_t* mbar, uint32_t off, uint32_t lane,
+                                                uint32_t mylen, uint32_t maxlen) {
+  double acc = 0.0;
+  bool staged = false;
+  const uint16_t* ps = slot + (size_t)off + lane;
+  const double* pv = sl + (size_t)off + lane;
+  uint32_t q = 0;
+  while (q < maxlen) {                                                     // warp-uniform control flow throughout
+    const uint32_t nact = __popc(__ballot_sync(0xffffffffu, q < mylen));   // lanes [0, nact) still hold entries
+    const uint32_t qend = __shfl_sync(0xffffffffu, mylen, nact - 1);       // the shortest of them ends the segment
+    const bool act = lane < nact;
+    for (; q < qend; q += BATCH) {
+      uint32_t sidx[BATCH];
+      double l[BATCH];
+#pragma unroll
+      for (int k = 0; k < BATCH; k++) {
+        const bool ok = act && q + k < qend;
+        sidx[k] = ok ? (uint32_t)__ldg(ps + k * nact) : 0xFFFFFFFFu;
+        l[k] = ok ? ld_stream_f64(pv + k * nact) : 0.0;
+      }
+      if (!staged) { stage_wait(mbar, 0); staged = true; }
+#pragma unroll
+      for (int k = 0; k < BATCH; k++)
+        if (sidx[k] != 0xFFFFFFFFu) acc = __dadd_rn(acc, __dmul_rn(l[k], stage[sidx[k]]));
+      const uint32_t adv = min((uint32_t)BATCH, qend - q) * nact;
+      ps += adv;
+      pv += adv;
+    }
+    q = qend;
+  }
+  if (!staged) stage_wait(mbar, 0);       // never leave while bulk copies into this block's shared memory are in flight
+  return acc;
+}
+
+template <int MODE, int BATCH>
+__global__ void __launch_bounds__(DDF_SELL_WIN)
+k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* __restrict__ perm8,
+             const uint8_t* __restrict__ len8, const uint32_t* __restrict__ tab, const uint16_t* __restrict__ slot,
+             const double* __restrict__ sl, int64_t first_window) {
+  extern __shared__ __align__(16) double stage[];
+  __shared__ __align__(8) uint64_t mbar;
+  const int64_t win = first_window + blockIdx.x;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) stage_issue(tab + win * STAGE_TAB, a.u, stage, &mbar, make_policy_evict_last());
+  const int64_t r = win * DDF_SELL_WIN + threadIdx.x;                        // sorted position
+  const int64_t i = win * DDF_SELL_WIN + perm8[r];                           // the row it holds
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t mylen = len8[r];
+  const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);                // rows are sorted by decreasing length
+  const uint32_t off = slice_ptr[r >> 5];
+  const bool mine = i >= a.row0 && i < a.row1;
+  // epilogue operands, requested before the row sum so that their latency overlaps it
+  double e0 = 0.0, e1 = 0.0;
+  uint8_t eb = 0;
+  if (MODE != 0 && mine) eb = a.isb[i];
+  if (MODE == 1 && mine) e0 = a.udot[i];
+  if (MODE == 2 && mine) { e0 = a.out0[i]; e1 = a.u[i]; }
+  const double lu = stage_row_sum<BATCH>(slot, sl, stage, &mbar, off, lane, mylen, maxlen);
+  if (!mine) return;
+  if (MODE == 0) {
+    st_hint_f64(a.out0 + i, lu, make_policy_evict_first());
+  } else if (MODE == 1) {
+    const double m = eb ? 0.0 : 1.0;
+    a.out0[i] = __dmul_rn(m, e0);
+    a.out1[i] = __dmul_rn(m, lu);
+  } else {
+    const double m = eb ? 0.0 : 1.0;
+    const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, lu)));
+    a.out0[i] = vn;
+    a.out1[i] = __dadd_rn(e1, __dmul_rn(a.dt, __dmul_rn(m, vn)));
+  }
+}
+
+// ---------------------------------------------------------------- staged rows, persistent TMA pipeline
+// One block per SM walks windows blockIdx.x, blockIdx.x + gridDim.x, ...  A producer warp streams
+// EVERYTHING a window needs into a ring of shared-memory stages with cp.async.bulk (completion
+// on the stage's "full" mbarrier): the runs of u, the window's value and slot streams (contiguous:
+// stage_build pads a window's entry range to 16-byte boundaries), its slice of v / udot, u, the
+// boundary mask and the perm/len bytes.  Eight consumer warps compute a window out of shared
+// memory only and release the stage through its "empty" mbarrier.  No register ever waits on
+// HBM, so the bytes in flight per SM are (stages - 1) x ~50 KB regardless of occupancy.
+struct PipeGeom {
+  uint32_t o_val, o_slot, o_v, o_u, o_isb, o_perm, o_len, stage_bytes;   // byte offsets inside a stage (x16)
+  int nstages;
+  int64_t nrows;
+};
+#define PIPE_GROUP 256          // threads of one consumer group (= rows of a window)
+#define PIPE_MAX_STAGES 6
+#define PIPE_TD 8               // depth of the run-table ring
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* mbar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(mbar)), "l"(policy)
+      : "memory");
+}
+
+template <int MODE, int NG>
+__global__ void __launch_bounds__(NG * PIPE_GROUP + 32, 1)
+k_rows_pipe(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* __restrict__ perm8,
+            const uint8_t* __restrict__ len8, const uint32_t* __restrict__ tab, const uint16_t* __restrict__ slot,
+            const double* __restrict__ sl, int64_t w0, int64_t w1, PipeGeom g) {
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  __shared__ __align__(8) uint64_t full[PIPE_MAX_STAGES], empty[PIPE_MAX_STAGES], tfull[PIPE_TD];
+  __shared__ __align__(16) uint32_t tabS[PIPE_TD * STAGE_TAB];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) {
+    for (int d = 0; d < PIPE_TD; d++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tfull[d])) : "memory");
+    for (int s = 0; s < g.nstages; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&empty[s])), "r"(PIPE_GROUP / 32) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t stride = gridDim.x;
+  if (warp == NG * PIPE_GROUP / 32) {
+    // ------------------------------------------------------------ producer warp
+    // The windows' run tables (256 B each) are themselves bulk-copied into a small ring PIPE_TD
+    // iterations ahead, so the producer never waits on a global load.
+    const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
+    int64_t win = w0 + blockIdx.x;
+    if (lane == 0) {
+      for (int d = 0; d < PIPE_TD; d++) {
+        const int64_t w = win + d * stride;
+        if (w < w1) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tfull[d])), "r"(STAGE_TAB * 4) : "memory");
+          bulk_g2s(tabS + d * STAGE_TAB, tab + w * STAGE_TAB, STAGE_TAB * 4, &tfull[d], pol_stream);
+        }
+      }
+    }
+    for (int64_t it = 0; win < w1; it++, win += stride) {
+      const int td = (int)(it % PIPE_TD);
+      stage_wait(&tfull[td], (uint32_t)(it / PIPE_TD) & 1u);
+      const uint32_t* wt = tabS + td * STAGE_TAB;
+      const uint32_t nruns = wt[0], total = wt[1], e0 = wt[2], nent = wt[3];
+      const uint32_t start = lane < STAGE_RMAX ? wt[4 + 2 * lane] : 0u, off = lane < STAGE_RMAX ? wt[5 + 2 * lane] : 0u;
+      const uint32_t end = lane + 1 < nruns ? wt[5 + 2 * (lane + 1)] : total;
+      __syncwarp();
+      if (lane == 0 && win + PIPE_TD * stride < w1) {                 // refill this table slot
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tfull[td])), "r"(STAGE_TAB * 4) : "memory");
+        bulk_g2s(tabS + td * STAGE_TAB, tab + (win + PIPE_TD * stride) * STAGE_TAB, STAGE_TAB * 4, &tfull[td], pol_stream);
+      }
+      const int s = (int)(it % g.nstages);
+      const uint32_t j = (uint32_t)(it / g.nstages);
+      if (j > 0) stage_wait(&empty[s], (j - 1) & 1u);
+      unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
+      const int64_t r0 = win * DDF_SELL_WIN;
+      const uint32_t nr = (uint32_t)min((int64_t)DDF_SELL_WIN, g.nrows - r0);
+      const uint32_t vbytes = ((nr + 1u) & ~1u) * 8u, mbytes = (nr + 15u) & ~15u;
+      uint32_t tx = total * 8u + nent * 10u + 2u * DDF_SELL_WIN;
+      if (MODE == 1) tx += vbytes + mbytes;
+      if (MODE == 2) tx += 2u * vbytes + mbytes;
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(tx) : "memory");
+      __syncwarp();
+      if (lane < nruns) bulk_g2s(sb + (size_t)off * 8, a.u + start, (end - off) * 8u, &full[s], pol_keep);
+      if (lane == 31 && nent) {
+        bulk_g2s(sb + g.o_val, sl + e0, nent * 8u, &full[s], pol_stream);
+        bulk_g2s(sb + g.o_slot, slot + e0, nent * 2u, &full[s], pol_stream);
+      }
+      if (lane == 30) {
+        bulk_g2s(sb + g.o_perm, perm8 + r0, DDF_SELL_WIN, &full[s], pol_stream);
+        bulk_g2s(sb + g.o_len, len8 + r0, DDF_SELL_WIN, &full[s], pol_stream);
+      }
+      if (lane == 29 && MODE != 0) {
+        bulk_g2s(sb + g.o_isb, a.isb + r0, mbytes, &full[s], pol_stream);
+        bulk_g2s(sb + g.o_v, (MODE == 1 ? a.udot : a.out0) + r0, vbytes, &full[s], pol_stream);
+        if (MODE == 2) bulk_g2s(sb + g.o_u, a.u + r0, vbytes, &full[s], pol_keep);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ consumer groups: thread = sorted row position;
+    // group k takes this block's iterations k, k + NG, ...
+    const uint64_t pol_stream = make_policy_evict_first();
+    const uint32_t grp = tid / PIPE_GROUP;
+    const uint32_t gtid = tid % PIPE_GROUP, gwarp = gtid >> 5;
+    int64_t it = grp;
+    for (int64_t win = w0 + blockIdx.x + grp * stride; win < w1; it += NG, win += NG * stride) {
+      const int s = (int)(it % g.nstages);
+      const uint32_t j = (uint32_t)(it / g.nstages);
+      stage_wait(&full[s], j & 1u);
+      const unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
+      const double* stage = reinterpret_cast<const double*>(sb);
+      const double* valS = reinterpret_cast<const double*>(sb + g.o_val);
+      const uint16_t* slotS = reinterpret_cast<const uint16_t*>(sb + g.o_slot);
+      const uint8_t* lenS = sb + g.o_len;
+      const uint32_t mylen = lenS[gtid];
+      const uint32_t p = (sb + g.o_perm)[gtid];
+      // entry offset of this slice inside the window = lengths of the rows of the earlier slices
+      uint32_t part = 0;
+      for (uint32_t k = lane; k < 32u * gwarp; k += 32u) part += lenS[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
+      uint32_t e = part + lane, q = 0;
+      double acc = 0.0;
+      while (q < maxlen) {                                                     // segments of constant active-lane count
+        const uint32_t nact = __popc(__ballot_sync(0xffffffffu, q < mylen));
+        const uint32_t qend = __shfl_sync(0xffffffffu, mylen, nact - 1);
+        if (lane < nact) {
+#pragma unroll 4
+          for (uint32_t k = q; k < qend; k++, e += nact) acc = __dadd_rn(acc, __dmul_rn(valS[e], stage[slotS[e]]));
+        }
+        q = qend;
+      }
+      const int64_t i = win * DDF_SELL_WIN + p;
+      if (i >= a.row0 && i < a.row1) {
+        if (MODE == 0) {
+          st_hint_f64(a.out0 + i, acc, pol_stream);
+        } else {
+          const double m = (sb + g.o_isb)[p] ? 0.0 : 1.0;
+          const double e0 = reinterpret_cast<const double*>(sb + g.o_v)[p];
+          if (MODE == 1) {
+            a.out0[i] = __dmul_rn(m, e0);
+            a.out1[i] = __dmul_rn(m, acc);
+          } else {
+            const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, acc)));
+            a.out0[i] = vn;
+            a.out1[i] = __dadd_rn(reinterpret_cast<const double*>(sb + g.o_u)[p], __dmul_rn(a.dt, __dmul_rn(m, vn)));
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+    }
+  }
+}
+
+static int pipe_geometry(const ddf_mesh* m, PipeGeom* g) {
+  const StageBufs& sb = m->lstage;
+  auto up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
+  g->o_val = up(sb.max_slots * 8u, 16);
+  g->o_slot = g->o_val + sb.max_entries * 8u;
+  g->o_v = g->o_slot + up(sb.max_entries * 2u, 16);
+  g->o_u = g->o_v + DDF_SELL_WIN * 8;
+  g->o_isb = g->o_u + DDF_SELL_WIN * 8;
+  g->o_perm = g->o_isb + DDF_SELL_WIN;
+  g->o_len = g->o_perm + DDF_SELL_WIN;
+  g->stage_bytes = up(g->o_len + DDF_SELL_WIN, 128);
+  const uint32_t budget = 227u * 1024u - 4096u;
+  g->nstages = (int)(budget / g->stage_bytes);
+  if (g->nstages > PIPE_MAX_STAGES) g->nstages = PIPE_MAX_STAGES;
+  g->nrows = m->n[0];
+  return g->nstages >= 2;
+}
+
 // variant 2/3: warp-cooperative row streaming through shared memory (kept for A/B timing)
 #define DDF_ROW_CAP 512       // products staged per warp and chunk (4 KB)
 template <int MODE>
@@ -289,7 +563,54 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
   a.nbr = m->adj_nbr.p;
   a.lval = m->adj_l.p;
   a.isb = m->isbnd[0].p;
-  if (m->wave_sell && (g_tune_wave & 3) == 0) {        // default: SELL-32 rows
+  if (m->lstage.ok && (g_tune_wave & 3) == 0) {          // default: staged rows
+    const int64_t w0 = a.row0 / DDF_SELL_WIN, w1 = (a.row1 + DDF_SELL_WIN - 1) / DDF_SELL_WIN;
+    if (w1 - w0 > 0x7fffffffLL) DDF_FAIL("grid too large");
+    const StageBufs& sb = m->lstage;
+    PipeGeom g;
+    if (!(g_tune_wave & 128) && pipe_geometry(m, &g) && w1 - w0 >= 4) {       // persistent TMA pipeline
+      const size_t smem_p = (size_t)g.nstages * g.stage_bytes;
+      const int grid = (int)std::min<int64_t>(m->ctx->sm_count, w1 - w0);
+      const int ng = (g_tune_wave >> 8) & 3;                     // A/B knob: consumer groups per block
+      static bool said = false;
+      if (!said && getenv("DDF_DEBUG")) {
+        fprintf(stderr, "[ddf] k_rows_pipe: %d stages x %u B (slots %u, entries %u), grid %d\n", g.nstages, g.stage_bytes,
+                sb.max_slots, sb.max_entries, grid);
+        said = true;
+      }
+#define DDF_PIPE_LAUNCH(NGV)                                                                                        \
+  do {                                                                                                              \
+    static size_t attr_p = 0;                                                                                       \
+    if (attr_p < smem_p) {                                                                                          \
+      DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe<MODE, NGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
+      attr_p = smem_p;                                                                                              \
+    }                                                                                                               \
+    k_rows_pipe<MODE, NGV><<<grid, NGV * PIPE_GROUP + 32, smem_p, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p,     \
+                                                                           sb.tab.p, sb.slot.p, sb.val.p, w0, w1, g); \
+  } while (0)
+      if (ng == 1) DDF_PIPE_LAUNCH(1);
+      else if (ng == 3) DDF_PIPE_LAUNCH(3);
+      else DDF_PIPE_LAUNCH(2);
+#undef DDF_PIPE_LAUNCH
+      DDF_LAUNCH_CHECK(m->ctx);
+      return 0;
+    }
+    const size_t smem = (size_t)sb.max_slots * 8;
+    if (smem > 48 * 1024 - 64) DDF_FAIL("staged rows: %zu bytes of staging exceed the static limit", smem);
+    const int batch = (g_tune_wave >> 5) & 3;          // A/B knob: gathers in flight per thread
+    if (batch == 1)
+      k_rows_stage<MODE, 4><<<(int)(w1 - w0), DDF_SELL_WIN, smem, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p, sb.tab.p,
+                                                                           sb.slot.p, sb.val.p, w0);
+    else if (batch == 2)
+      k_rows_stage<MODE, 6><<<(int)(w1 - w0), DDF_SELL_WIN, smem, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p, sb.tab.p,
+                                                                           sb.slot.p, sb.val.p, w0);
+    else if (batch == 3)
+      k_rows_stage<MODE, 12><<<(int)(w1 - w0), DDF_SELL_WIN, smem, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p, sb.tab.p,
+                                                                            sb.slot.p, sb.val.p, w0);
+    else
+      k_rows_stage<MODE, 8><<<(int)(w1 - w0), DDF_SELL_WIN, smem, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p, sb.tab.p,
+                                                                           sb.slot.p, sb.val.p, w0);
+  } else if (m->wave_sell && (g_tune_wave & 3) == 0) {   // explicit-index SELL-32 rows
     const int64_t w0 = a.row0 / DDF_SELL_WIN, w1 = (a.row1 + DDF_SELL_WIN - 1) / DDF_SELL_WIN;
     if (w1 - w0 > 0x7fffffffLL) DDF_FAIL("grid too large");
     const SellBufs& sb = m->lsell;
@@ -429,12 +750,22 @@ extern "C" int ddf_wave_leapfrog(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt,
   DDF_TRY_END
 }
 
+extern "C" int ddf_wave_format(ddf_mesh* m, int* format) {
+  DDF_TRY_BEGIN
+  DDF_CHECK(ddf_mesh_require_wave(m));
+  *format = m->lstage.ok ? 2 : (m->wave_sell ? 1 : 0);
+  return 0;
+  DDF_TRY_END
+}
+
 extern "C" int ddf_wave_step_bytes(ddf_mesh* m, int64_t* algorithmic, int64_t* format_bytes) {
   DDF_CHECK(ddf_mesh_require_assembled(m));
   const int64_t E = m->n[1], V = m->n[0];
   *algorithmic = E * 16 + V * 41;                  // E*(2*4+8) + V*(8*5+1)
   // what this format streams per step: 12 B per stored entry + u, v (r/w), u', mask per vertex + row offsets
-  if (m->has_wave && m->wave_sell)
+  if (m->has_wave && m->lstage.ok)   // 10 B per entry, no padding; per vertex u (staged once), v r/w, u', mask, perm, len
+    *format_bytes = m->lstage.entries * 10 + V * (8 * 4 + 1 + 2) + (V / 32 + 1) * 4 + (V / 256 + 1) * 96;
+  else if (m->has_wave && m->wave_sell)
     *format_bytes = m->lsell.padded * 8 + m->lsell.index_words * 4 + V * (8 * 4 + 1 + 1) + (V / 32 + 1) * 12;
   else *format_bytes = (m->has_wave ? m->adj_nnz : 2 * E + V) * 12 + V * (4 + 8 * 4 + 1);
   return 0;

@@ -43,6 +43,15 @@ def wave_leapfrog(mfd: Manifold, u: Fun, v: Fun, dt: float, nsteps: int):
     return u, v
 
 
+def wave_format(mfd: Manifold) -> str:
+    """Storage of the assembled L rows the row kernels use on this mesh: "staged" (TMA-staged gather,
+    16-bit slots, jagged slices), "sell" (explicit-index SELL-32-256) or "csr"."""
+    mfd._geometry()
+    f = C.c_int()
+    call("ddf_wave_format", mfd._h, C.byref(f))
+    return ("csr", "sell", "staged")[f.value]
+
+
 def wave_step_bytes(mfd: Manifold):
     a, b = C.c_int64(), C.c_int64()
     call("ddf_wave_step_bytes", mfd._h, C.byref(a), C.byref(b))

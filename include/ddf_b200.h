@@ -189,6 +189,9 @@ int ddf_wave_leapfrog(ddf_mesh* mesh, ddf_vec* u, ddf_vec* v, double dt, int nst
 /* one leapfrog step timed alone is exposed through ddf_timer_*; the algorithmic
  * byte count of a step (E*16 + V*41) is returned here for reporting */
 int ddf_wave_step_bytes(ddf_mesh* mesh, int64_t* algorithmic, int64_t* format_bytes);
+/* storage the row kernels use for L on this mesh: 0 = row-CSR, 1 = explicit-index SELL-32-256,
+ * 2 = staged rows (TMA-staged gather of u, 16-bit slots, jagged slices; csrc/stage.cuh) */
+int ddf_wave_format(ddf_mesh* mesh, int* format);
 
 /* --------------------------------------------------------- multi-GPU (NCCL) */
 /* ncclGetUniqueId: 128 bytes, created on rank 0 and broadcast by the host side */

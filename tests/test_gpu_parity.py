@@ -332,6 +332,45 @@ def test_wave_rhs_and_leapfrog_bit_exact(ddf, pairs, kind):
     assert np.array_equal(u.values, ou) and np.array_equal(v.values, ov)
 
 
+def test_wave_row_formats_agree(ddf, ctx):
+    """The three storage formats of the L rows -- staged rows (TMA-staged gather, 16-bit slots, jagged
+    slices; default), explicit-index SELL-32-256 (tuning 16) and CSR thread-per-row (tuning 16|1) -- give
+    the same bits as the oracle, also on a mesh with shuffled vertex numbers (no column locality: the
+    staged build must refuse it and fall back)."""
+    n = 12
+    simp, coords, weights = o.large_hypercube_tables(3, (n, n, n))
+    rng = np.random.default_rng(21)
+    perm = rng.permutation(coords.shape[0])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    cases = {"ordered": (simp, coords, weights), "shuffled": (inv[simp], coords[perm], weights[perm])}
+    for name, (s_, c_, w_) in cases.items():
+        om = o.build_manifold("m", s_, c_, w_)
+        ref = None
+        for tune in (0, 16, 17):
+            ddf._lib.call("ddf_set_tuning", b"wave", tune)
+            try:
+                dm = ddf.Manifold.from_simplices("m", s_, c_, w_, ctx=ctx)
+                omg = with_device_geometry(om, dm)
+                u0 = rng.standard_normal(om.nsimplices(0))
+                v0 = rng.standard_normal(om.nsimplices(0))
+                u, v = ddf.Fun(dm, ddf.Pr, 0, u0), ddf.Fun(dm, ddf.Pr, 0, v0)
+                dt = ddf.wave_dt(dm)
+                ddf.wave_leapfrog(dm, u, v, dt, 3)
+                ou, ov = o.wave_leapfrog(omg, u0, v0, dt, 3)
+                assert np.array_equal(u.values, ou) and np.array_equal(v.values, ov), (name, tune)
+                y = (ddf.laplace(ddf.Pr, 0, dm) * ddf.Fun(dm, ddf.Pr, 0, u0)).values
+                assert np.array_equal(y, o.spmv_csc(o.laplace(o.Pr, 0, omg), u0)), (name, tune)
+                fmt = ddf.wave_format(dm)
+                if tune == 0:
+                    assert (fmt == "staged") == (name == "ordered"), (name, fmt)
+                elif tune == 17:
+                    assert fmt != "staged"
+                dm.close()
+            finally:
+                ddf._lib.call("ddf_set_tuning", b"wave", 0)
+
+
 def test_wave_sample_and_convergence(ddf, ctx):
     """Device-sampled initial data and second-order convergence of the leapfrog
     solution (the oracle restatement of wave.jl is second order)."""
