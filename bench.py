@@ -33,6 +33,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 import numpy as np  # noqa: E402
 
+print_json = None
 METRIC = "cochain DOF updates/sec (d_k + star_k apply, 3D Kuhn mesh)"
 UNIT = "DOF/s"
 
@@ -188,7 +189,7 @@ def run_reference(args):
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "omp_allcores_crosscheck": {"value": omp["value"], "cores": omp["cores"]},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print_json(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -394,12 +395,22 @@ def run_b200(args):
             "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
             "hbm_bytes_in_use": ctx.bytes_in_use(),
         }
-        print(json.dumps(line))
+        print_json(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
 def main():
+    # libraries (NCCL_DEBUG=VERSION, torchrun banners) may write to fd 1: keep the real stdout for the ONE JSON
+    # line and send everything else to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global print_json
+
+    def print_json(line):
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

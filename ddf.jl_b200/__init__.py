@@ -12,5 +12,6 @@ from .manifoldops import (boundary, boundary_of, coderiv, coderiv_of, delaunay_m
                           hodge, hodge_of, integral, invhodge, invhodge_of, isboundary,
                           large_hypercube_manifold, laplace, laplace_of, one, refined_manifold,
                           refined_simplex_manifold, regular_simplex, sample, simplex_manifold, zero)
-from .wave import wave, wave_dt, wave_format, wave_leapfrog, wave_rhs, wave_step_bytes  # noqa: F401
+from .wave import (lincomb, wave, wave_dt, wave_format, wave_leapfrog, wave_rhs, wave_step_bytes,  # noqa: F401
+                   wave_tsit5)  # noqa: F401
 from . import dist  # noqa: F401

@@ -98,6 +98,8 @@ SIGNATURES = {
     "ddf_wave_rhs": [_P, _P, _P, _P, _P],
     "ddf_wave_dt": [_P, _f64p],
     "ddf_wave_leapfrog": [_P, _P, _P, _f64, _int],
+    "ddf_wave_tsit5": [_P, _P, _P, _f64, _int],
+    "ddf_vec_lincomb": [_P, _P, _f64, _int, _f64p, _PP],
     "ddf_wave_step_bytes": [_P, _i64p, _i64p],
     "ddf_wave_format": [_P, _P],
     "ddf_comm_unique_id": [_P],

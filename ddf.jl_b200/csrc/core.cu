@@ -287,6 +287,79 @@ extern "C" int ddf_vec_axpby(double a, ddf_vec* x, double b, ddf_vec* y, ddf_vec
   return 0;
 }
 
+// out = base + dt * (c_0 k_0 + c_1 k_1 + ...): the stage update of an explicit Runge-Kutta
+// step (OrdinaryDiffEq's `@.. tmp = uprev + dt*(a31*k1 + a32*k2)`), every product and sum
+// separately rounded, left to right.  One pass: N+1 reads, one write per element.
+struct LincombArgs {
+  const double* k[8];
+  double c[8];
+};
+template <int N>
+__global__ void __launch_bounds__(256) k_lincomb(const double* base, double dt, LincombArgs a, double* out,
+                                                 int64_t n) {   // out may alias base (same index, same thread)
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    double2 s = *reinterpret_cast<const double2*>(a.k[0] + i);
+    s.x = __dmul_rn(a.c[0], s.x);
+    s.y = __dmul_rn(a.c[0], s.y);
+#pragma unroll
+    for (int j = 1; j < N; j++) {
+      const double2 kv = *reinterpret_cast<const double2*>(a.k[j] + i);
+      s.x = __dadd_rn(s.x, __dmul_rn(a.c[j], kv.x));
+      s.y = __dadd_rn(s.y, __dmul_rn(a.c[j], kv.y));
+    }
+    const double2 b = *reinterpret_cast<const double2*>(base + i);
+    double2 r;
+    r.x = __dadd_rn(b.x, __dmul_rn(dt, s.x));
+    r.y = __dadd_rn(b.y, __dmul_rn(dt, s.y));
+    *reinterpret_cast<double2*>(out + i) = r;
+  } else if (i < n) {
+    double s = __dmul_rn(a.c[0], a.k[0][i]);
+#pragma unroll
+    for (int j = 1; j < N; j++) s = __dadd_rn(s, __dmul_rn(a.c[j], a.k[j][i]));
+    out[i] = __dadd_rn(base[i], __dmul_rn(dt, s));
+  }
+}
+
+int ddf_lincomb_launch(ddf_ctx* ctx, const double* base, double dt, int nk, const double* coef, const double* const* ks,
+                       double* out, int64_t n) {
+  if (nk < 1 || nk > 8) DDF_FAIL("lincomb: 1..8 terms supported, got %d", nk);
+  if (n == 0) return 0;
+  LincombArgs a{};
+  for (int j = 0; j < nk; j++) { a.k[j] = ks[j]; a.c[j] = coef[j]; }
+  int grid;
+  DDF_CHECK(grid_for(ceil_div64(n, 2), 256, &grid));
+  switch (nk) {
+    case 1: k_lincomb<1><<<grid, 256, 0, ctx->stream>>>(base, dt, a, out, n); break;
+    case 2: k_lincomb<2><<<grid, 256, 0, ctx->stream>>>(base, dt, a, out, n); break;
+    case 3: k_lincomb<3><<<grid, 256, 0, ctx->stream>>>(base, dt, a, out, n); break;
+    case 4: k_lincomb<4><<<grid, 256, 0, ctx->stream>>>(base, dt, a, out, n); break;
+    case 5: k_lincomb<5><<<grid, 256, 0, ctx->stream>>>(base, dt, a, out, n); break;
+    case 6: k_lincomb<6><<<grid, 256, 0, ctx->stream>>>(base, dt, a, out, n); break;
+    case 7: k_lincomb<7><<<grid, 256, 0, ctx->stream>>>(base, dt, a, out, n); break;
+    default: k_lincomb<8><<<grid, 256, 0, ctx->stream>>>(base, dt, a, out, n); break;
+  }
+  DDF_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int ddf_vec_lincomb(ddf_vec* out, ddf_vec* base, double dt, int nk, const double* coef, ddf_vec** ks) {
+  DDF_TRY_BEGIN
+  if (nk < 1 || nk > 8) DDF_FAIL("vec_lincomb: 1..8 terms supported, got %d", nk);
+  if (base->n != out->n) DDF_FAIL("vec_lincomb: length mismatch");
+  const double* kp[8];
+  DDF_CHECK(ddf_vec_settle(out));
+  DDF_CHECK(ddf_vec_settle(base));
+  for (int j = 0; j < nk; j++) {
+    if (ks[j]->n != out->n) DDF_FAIL("vec_lincomb: length mismatch in term %d", j);
+    if (ks[j] == out) DDF_FAIL("vec_lincomb: out must not alias a term");
+    DDF_CHECK(ddf_vec_settle(ks[j]));
+    kp[j] = ks[j]->d.p;
+  }
+  return ddf_lincomb_launch(out->ctx, base->d.p, dt, nk, coef, kp, out->d.p, out->n);
+  DDF_TRY_END
+}
+
 __global__ void k_mul(const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ z, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) z[i] = x[i] * y[i];

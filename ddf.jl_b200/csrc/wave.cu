@@ -750,6 +750,74 @@ extern "C" int ddf_wave_leapfrog(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt,
   DDF_TRY_END
 }
 
+// ---------------------------------------------------------------- N1: fixed-step Tsit5 on the device
+// examples/wave.jl:134 integrates dU = F U with `Tsit5(); adaptive=false, dt`.  This is
+// OrdinaryDiffEq's in-place perform_step! on device vectors: six stage updates (one fused
+// k_lincomb pass each, core.cu) and six right-hand sides (k_rows_* MODE 1) per step, the
+// seventh derivative re-used as k1 of the next step (FSAL).  Tableau: Tsitouras 5(4),
+// pinned by the order conditions in tests/test_oracle_pins.py.
+int ddf_lincomb_launch(ddf_ctx* ctx, const double* base, double dt, int nk, const double* coef, const double* const* ks,
+                       double* out, int64_t n);   // core.cu
+
+static const double TSIT5_A[6][6] = {
+    {0.161, 0, 0, 0, 0, 0},
+    {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+    {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+    {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
+    {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+
+static int wave_rhs_launch(ddf_mesh* m, const double* u, const double* udot, double* du, double* dudot) {
+  RowArgs a{};
+  a.u = u;
+  a.udot = udot;
+  a.out0 = du;
+  a.out1 = dudot;
+  a.row0 = 0;
+  a.row1 = m->n[0];
+  return launch_rows<1>(m, m->ctx->stream, a);
+}
+
+extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt, int nsteps) {
+  DDF_TRY_BEGIN
+  DDF_CHECK(ddf_mesh_require_wave(m));
+  ddf_ctx* ctx = m->ctx;
+  const int64_t nv = m->n[0];
+  if (u->n != nv || udot->n != nv) DDF_FAIL("wave_tsit5: vectors must have length n0=%lld", (long long)nv);
+  if (u == udot) DDF_FAIL("wave_tsit5: u and udot must not alias");
+  if (!nv || nsteps <= 0) return 0;
+  DDF_CHECK(ddf_vec_settle(u));
+  DDF_CHECK(ddf_vec_settle(udot));
+  // work space: k1..k7 and tmp, each for (u, udot)
+  DevBuf<double> k[7][2], tmp[2];
+  for (int s = 0; s < 7; s++)
+    for (int c = 0; c < 2; c++) DDF_CHECK(k[s][c].alloc(ctx, nv));
+  for (int c = 0; c < 2; c++) DDF_CHECK(tmp[c].alloc(ctx, nv));
+  double* kp[7][2];
+  for (int s = 0; s < 7; s++)
+    for (int c = 0; c < 2; c++) kp[s][c] = k[s][c].p;
+  double* U[2] = {u->d.p, udot->d.p};
+  DDF_CHECK(wave_rhs_launch(m, U[0], U[1], kp[0][0], kp[0][1]));
+  for (int step = 0; step < nsteps; step++) {
+    for (int s = 0; s < 6; s++) {
+      // stages 1..5 go to tmp; the last one IS the new state, written over U after its inputs are consumed
+      double* dst[2] = {tmp[0].p, tmp[1].p};
+      for (int c = 0; c < 2; c++) {
+        const double* ks[6];
+        for (int j = 0; j <= s; j++) ks[j] = kp[j][c];
+        DDF_CHECK(ddf_lincomb_launch(ctx, U[c], dt, s + 1, TSIT5_A[s], ks, s == 5 ? U[c] : dst[c], nv));
+      }
+      const double* su = s == 5 ? U[0] : dst[0];
+      const double* sv = s == 5 ? U[1] : dst[1];
+      DDF_CHECK(wave_rhs_launch(m, su, sv, kp[s + 1][0], kp[s + 1][1]));
+    }
+    for (int c = 0; c < 2; c++) std::swap(kp[0][c], kp[6][c]);     // FSAL
+  }
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));    // the work space is freed on return
+  return 0;
+  DDF_TRY_END
+}
+
 extern "C" int ddf_wave_format(ddf_mesh* m, int* format) {
   DDF_TRY_BEGIN
   DDF_CHECK(ddf_mesh_require_wave(m));

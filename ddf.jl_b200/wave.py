@@ -43,6 +43,22 @@ def wave_leapfrog(mfd: Manifold, u: Fun, v: Fun, dt: float, nsteps: int):
     return u, v
 
 
+def wave_tsit5(mfd: Manifold, u: Fun, udot: Fun, dt: float, nsteps: int):
+    """In-place fixed-step Tsit5 on dU = F U -- the integrator of examples/wave.jl:134."""
+    mfd._geometry()
+    call("ddf_wave_tsit5", mfd._h, u._h, udot._h, float(dt), int(nsteps))
+    return u, udot
+
+
+def lincomb(base: Fun, dt: float, coefs, ks, out: Fun = None) -> Fun:
+    """out = base + dt*(c1 k1 + c2 k2 + ...) in one pass (the Runge-Kutta stage broadcast)."""
+    out = out if out is not None else base._like()
+    coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+    arr = (C.c_void_p * len(ks))(*[k._h for k in ks])
+    call("ddf_vec_lincomb", out._h, base._h, float(dt), len(ks), coefs.ctypes.data_as(C.POINTER(C.c_double)), arr)
+    return out
+
+
 def wave_format(mfd: Manifold) -> str:
     """Storage of the assembled L rows the row kernels use on this mesh: "staged" (TMA-staged gather,
     16-bit slots, jagged slices), "sell" (explicit-index SELL-32-256) or "csr"."""
@@ -58,7 +74,7 @@ def wave_step_bytes(mfd: Manifold):
     return a.value, b.value
 
 
-def wave(D: int, levels: int, ctx=None, t1: float = 0.875):
+def wave(D: int, levels: int, ctx=None, t1: float = 0.875, integrator: str = "leapfrog"):
     """`Wave.wave(Val(D), levels)` with the leapfrog integrator: mesh n = 2^levels
     (wave.jl:32-34), u0 = prod sinpi(x_d), udot0 = 0 (wave.jl:42-58), integrate to
     t1 (the last `saveat` time of wave.jl:116 is 0.875) and return the error norm
@@ -70,6 +86,12 @@ def wave(D: int, levels: int, ctx=None, t1: float = 0.875):
     dt = wave_dt(mfd)
     nsteps = int(round(t1 / dt))
     omega = math.sqrt(D)
+    if integrator == "tsit5":            # what examples/wave.jl:134 runs
+        wave_tsit5(mfd, u, v, dt, nsteps)
+        t = nsteps * dt
+        exact = math.cos(math.pi * omega * t) * np.prod(np.sin(np.pi * mfd.get_coords()), axis=1)
+        e = u.values - exact
+        return float(np.sqrt(np.sum(e * e) / len(e))), mfd
     # leapfrog staggering: the step is v^{n+1/2} = v^{n-1/2} + dt L u^n; u^{n+1} = u^n + dt v^{n+1/2},
     # so start from v^{-1/2} = v0 - dt/2 (1-b) L u0 (second order overall)
     _, dv0 = wave_rhs(mfd, u, v)

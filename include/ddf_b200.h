@@ -124,6 +124,11 @@ int ddf_vec_download(ddf_vec* v, double* host);
  * ddf_sync(ctx); ordering against kernels that touch `v` is tracked by the library. */
 int ddf_vec_upload_async(ddf_vec* v, const double* host);
 int ddf_vec_download_async(ddf_vec* v, double* host);
+/* out = base + dt*(coef[0] ks[0] + ... + coef[nk-1] ks[nk-1]), 1 <= nk <= 8, products and sums separately
+ * rounded left to right: the stage update of an explicit Runge-Kutta step, i.e. the broadcast
+ * `@.. tmp = uprev + dt*(a31*k1 + a32*k2)` OrdinaryDiffEq issues on the state vector (examples/wave.jl:134).
+ * `out` may alias `base`, not a term. */
+int ddf_vec_lincomb(ddf_vec* out, ddf_vec* base, double dt, int nk, const double* coef, ddf_vec** ks);
 int ddf_vec_fill(ddf_vec* v, double a);
 int ddf_vec_copy(ddf_vec* dst, ddf_vec* src);
 /* sample(Fun{D,Pr,0}, f, mfd) for the fields of the examples, evaluated at the
@@ -186,6 +191,9 @@ int ddf_wave_dt(ddf_mesh* mesh, double* dt);
  *   v += dt (1-b) .* (L u);  u += dt (1-b) .* v     repeated nsteps times,
  * one kernel per step, L applied matrix-free from the vertex adjacency. */
 int ddf_wave_leapfrog(ddf_mesh* mesh, ddf_vec* u, ddf_vec* v, double dt, int nsteps);
+/* `nsteps` fixed steps of Tsit5 on dU = F U, U = [u; udot] -- what examples/wave.jl:134 runs
+ * (`solve(prob, Tsit5(); adaptive=false, dt=dt)`); in place. */
+int ddf_wave_tsit5(ddf_mesh* mesh, ddf_vec* u, ddf_vec* udot, double dt, int nsteps);
 /* one leapfrog step timed alone is exposed through ddf_timer_*; the algorithmic
  * byte count of a step (E*16 + V*41) is returned here for reporting */
 int ddf_wave_step_bytes(ddf_mesh* mesh, int64_t* algorithmic, int64_t* format_bytes);

@@ -771,6 +771,58 @@ def wave_leapfrog(mfd: Manifold, u: np.ndarray, v: np.ndarray, dt: float,
 
 
 # --------------------------------------------------------------------------- #
+# N1: the integrator the reference actually runs -- fixed-step Tsit5
+# (examples/wave.jl:134: solve(prob, Tsit5(); adaptive=false, dt=dt)).
+# OrdinaryDiffEq 5.49.1 (Manifest.toml:711-715) is not vendored in the reference; this
+# restates its published algorithm: the Tsitouras 5(4) tableau (Ch. Tsitouras, Comput.
+# Math. Appl. 62 (2011) 770-775, Float64 coefficients as in OrdinaryDiffEq's
+# tsit_tableaus.jl) and the in-place perform_step!:
+#     tmp = uprev + dt*(a_s1 k1 + ... + a_s,s-1 k_{s-1});  k_s = f(tmp)
+#     u   = uprev + dt*(a71 k1 + ... + a76 k6);  k7 = f(u) is k1 of the next step (FSAL)
+# The reference evaluates these under @muladd (FMA contraction is hardware dependent), so
+# element-wise parity with Julia is a 1e-12-class statement; here every product and sum is
+# separately rounded, left to right, and the device kernel does exactly the same.
+# tests/test_oracle_pins.py pins the tableau through the order conditions up to order 5.
+# --------------------------------------------------------------------------- #
+TSIT5_C = (0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0)
+TSIT5_A = (
+    (0.161,),
+    (-0.008480655492356989, 0.335480655492357),
+    (2.8971530571054935, -6.359448489975075, 4.3622954328695815),
+    (5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525),
+    (5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383),
+    (0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774),
+)
+
+
+def lincomb(base: np.ndarray, dt: float, coefs, ks) -> np.ndarray:
+    """base + dt*(c1 k1 + c2 k2 + ...), every product and sum separately rounded, left to right."""
+    s = coefs[0] * ks[0]
+    for c, k in zip(coefs[1:], ks[1:]):
+        s = s + c * k
+    return base + dt * s
+
+
+def tsit5_steps(f, U, dt: float, nsteps: int):
+    """`nsteps` fixed steps of Tsit5 on dU/dt = f(U) (autonomous), U a tuple of arrays."""
+    k = [None] * 7
+    k[0] = f(U)
+    for _ in range(nsteps):
+        for s in range(6):
+            tmp = tuple(lincomb(U[c], dt, TSIT5_A[s], [k[j][c] for j in range(s + 1)]) for c in range(len(U)))
+            k[s + 1] = f(tmp)
+            if s == 5:
+                U = tmp
+        k[0] = k[6]
+    return U
+
+
+def wave_tsit5(mfd: Manifold, u: np.ndarray, udot: np.ndarray, dt: float, nsteps: int):
+    """examples/wave.jl:98-100,134: dU = F U integrated with fixed-step Tsit5."""
+    return tsit5_steps(lambda U: wave_rhs(mfd, U[0], U[1]), (u.copy(), udot.copy()), dt, nsteps)
+
+
+# --------------------------------------------------------------------------- #
 # invariant (src/Manifolds.jl:154-189)
 # --------------------------------------------------------------------------- #
 def invariant(mfd: Manifold) -> bool:

@@ -371,6 +371,40 @@ def test_wave_row_formats_agree(ddf, ctx):
                 ddf._lib.call("ddf_set_tuning", b"wave", 0)
 
 
+@pytest.mark.parametrize("kind", ["kuhn2n4", "kuhn2n16", "kuhn3n4"])
+def test_wave_tsit5_bit_exact(ddf, pairs, kind):
+    """N1: the reference's integrator (fixed-step Tsit5, wave.jl:134) on the device == the oracle's restatement
+    of OrdinaryDiffEq's perform_step! (same rounding sequence: no contraction), including FSAL across steps."""
+    om, dm = pairs(kind)
+    om = with_device_geometry(om, dm)
+    u0 = o.wave_u0(om.coords)
+    rng = np.random.default_rng(12)
+    v0 = rng.standard_normal(len(u0))
+    dt = ddf.wave_dt(dm)
+    u, v = ddf.Fun(dm, ddf.Pr, 0, u0), ddf.Fun(dm, ddf.Pr, 0, v0)
+    ddf.wave_tsit5(dm, u, v, dt, 3)
+    ou, ov = o.wave_tsit5(om, u0, v0, dt, 3)
+    assert np.array_equal(u.values, ou) and np.array_equal(v.values, ov)
+    # the stage broadcast on its own, in place and out of place
+    ks = [ddf.Fun(dm, ddf.Pr, 0, rng.standard_normal(len(u0))) for _ in range(4)]
+    cs = [0.25, -1.5, 3.0, 0.125]
+    ref = o.lincomb(u0, dt, cs, [k.values for k in ks])
+    base = ddf.Fun(dm, ddf.Pr, 0, u0)
+    assert np.array_equal(ddf.lincomb(base, dt, cs, ks).values, ref)
+    assert np.array_equal(ddf.lincomb(base, dt, cs, ks, out=base).values, ref)
+
+
+def test_wave_tsit5_converges_to_exact_solution(ddf, ctx):
+    """Wave.wave(Val(2), levels) with the reference's integrator: the error against
+    cos(sqrt(2) pi t) prod sin(pi x) (wave.jl:150-163) falls at the same rate as with the leapfrog step
+    (the spatial error of the DEC Laplacian dominates; the accuracy table of wave.jl:172-186 is stale)."""
+    errs = []
+    for lv in (3, 4, 5):
+        e, _ = ddf.wave(2, lv, ctx=ctx, t1=0.5, integrator="tsit5")
+        errs.append(e)
+    assert errs[1] < errs[0] / 2.5 and errs[2] < errs[1] / 2.5, errs
+
+
 def test_wave_sample_and_convergence(ddf, ctx):
     """Device-sampled initial data and second-order convergence of the leapfrog
     solution (the oracle restatement of wave.jl is second order)."""
@@ -414,6 +448,87 @@ def test_large_mesh_properties(ddf, ctx):
     ddf.wave_leapfrog(m, u1, v1, dt, 5)
     ddf.wave_leapfrog(m, u2, v2, dt, 5)
     assert np.array_equal(u2.values, 4.0 * u1.values)
+
+
+# ------------------------------------------------- BASELINE configs at their full sizes
+def test_config2_poisson_mesh_full_size(ddf, ctx):
+    """BASELINE config 2: 2D simplex refined 10x (525,825 / 1,574,400 / 1,048,576) -- Delaunay through
+    scipy like the reference, assembly and L on the device.  Full-size checks: counts, dd = 0, sum of volumes,
+    and L*rho / d0*rho against the oracle on the SAME mesh (bit-exact given the device geometry)."""
+    dm = ddf.refined_simplex_manifold(2, 10, ctx=ctx)
+    assert [dm.nsimplices(R) for R in range(3)] == [525825, 1574400, 1048576]
+    rng = np.random.default_rng(31)
+    x = ddf.Fun(dm, ddf.Pr, 0, rng.integers(-99, 99, dm.nsimplices(0)).astype(float))
+    d0, d1 = ddf.deriv(ddf.Pr, 0, dm), ddf.deriv(ddf.Pr, 1, dm)
+    assert (d1 * (d0 * x)).norm(np.inf) == 0
+    area = np.sqrt(3) / 4                                    # regular simplex of edge length 1
+    assert abs(dm.get_volumes(2).sum() - area) < 1e-12 and abs(dm.get_dualvolumes(0).sum() - area) < 1e-12
+    # the oracle on the same tables (the triangle table is read back from the device: Qhull's order)
+    om = o.build_manifold("c2", dm.get_simplices(2), dm.get_coords(), dm.get_weights())
+    for R in (1, 2):
+        cp, rv, nz = dm.get_boundaries_csc(R)
+        ocp, orv, onz = o.to_julia_csc(om.boundaries[R])
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz)
+    om = with_device_geometry(om, dm)
+    rho = o.poisson_rho(om.coords)
+    frho = ddf.Fun(dm, ddf.Pr, 0, rho)
+    assert np.array_equal((d0 * frho).values, o.apply_deriv(o.Pr, 0, om, rho))
+    y = (ddf.laplace(ddf.Pr, 0, dm) * frho).values
+    assert np.array_equal(y, o.spmv_csc(o.laplace(o.Pr, 0, om), rho))
+
+
+def test_config3_wave_2d_full_size(ddf, ctx):
+    """BASELINE config 3: 2D Kuhn n=2048 (4,198,401 / 12,587,008 / 8,388,608), fused leapfrog.  Full-size
+    checks: closed-form counts, the staged-rows format is in use, the step is linear (exact for a power of
+    two), and the solution follows cos(sqrt(2) pi t) prod sin(pi x) (wave.jl:42-58,150-163)."""
+    n = 2048
+    m = ddf.large_hypercube_manifold(2, (n, n), ctx=ctx)
+    assert [m.nsimplices(R) for R in range(3)] == [(n + 1) ** 2, 3 * n * n + 2 * n, 2 * n * n]
+    assert ddf.wave_format(m) == "staged"
+    u0 = ddf.sample(m, "wave")
+    u1, v1 = u0.copy(), ddf.Fun(m, ddf.Pr, 0)
+    u2, v2 = u0 * 8.0, ddf.Fun(m, ddf.Pr, 0)
+    dt = ddf.wave_dt(m)
+    assert dt == 1.0 / (2 * n)
+    nsteps = 64
+    ddf.wave_leapfrog(m, u1, v1, dt, nsteps)
+    ddf.wave_leapfrog(m, u2, v2, dt, nsteps)
+    a = u1.values
+    assert np.array_equal(u2.values, 8.0 * a)
+    exact = np.cos(np.sqrt(2.0) * np.pi * nsteps * dt) * u0.values
+    assert np.max(np.abs(a - exact)) < 2e-4          # first-order in dt for this staggering, O(h^2) in space
+    assert np.array_equal(a[m.get_isboundary(0).astype(bool)], u0.values[m.get_isboundary(0).astype(bool)])
+
+
+def test_config4_3d_full_size(ddf, ctx):
+    """BASELINE config 4: 3D Kuhn n=256 (16,974,593 / 118,031,104 / 201,719,808 / 100,663,296): assembly on the
+    device, then exact identities on integer-valued cochains (d d = 0 is exact in Float64), d0 of a coordinate
+    function, volume sums, row-format choice and linearity of the fused step."""
+    n = 256
+    m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
+    assert [m.nsimplices(R) for R in range(4)] == [(n + 1) ** 3, 7 * n ** 3 + 9 * n ** 2 + 3 * n,
+                                                   12 * n ** 3 + 6 * n ** 2, 6 * n ** 3]
+    d0, d1, d2 = (ddf.deriv(ddf.Pr, k, m) for k in range(3))
+    rng = np.random.default_rng(41)
+    x = ddf.Fun(m, ddf.Pr, 0, rng.integers(-999, 999, m.nsimplices(0)).astype(np.float64))
+    assert (d1 * (d0 * x)).norm(np.inf) == 0
+    y = ddf.Fun(m, ddf.Pr, 1, rng.integers(-999, 999, m.nsimplices(1)).astype(np.float64))
+    assert (d2 * (d1 * y)).norm(np.inf) == 0
+    # d0 of the coordinate function x: every edge difference is 0 or +-h exactly (h = 2^-8)
+    cx = ddf.Fun(m, ddf.Pr, 0, np.ascontiguousarray(m.get_coords()[:, 0]))
+    e = (d0 * cx).values
+    assert set(np.unique(e).tolist()) <= {0.0, 1.0 / n, -1.0 / n}
+    assert abs(m.get_volumes(3).sum() - 1) < 1e-10
+    assert ddf.wave_format(m) == "staged"
+    u0 = ddf.sample(m, "wave")
+    u1, v1 = u0.copy(), ddf.Fun(m, ddf.Pr, 0)
+    u2, v2 = u0 * 4.0, ddf.Fun(m, ddf.Pr, 0)
+    dt = ddf.wave_dt(m)
+    ddf.wave_leapfrog(m, u1, v1, dt, 4)
+    ddf.wave_leapfrog(m, u2, v2, dt, 4)
+    assert (u2 - u1 * 4.0).norm(np.inf) == 0
+    exact = u0 * float(np.cos(np.sqrt(3.0) * np.pi * 4 * dt))
+    assert (u1 - exact).norm(np.inf) < 1e-3
 
 
 def test_async_transfers_pipeline(ddf, ctx):

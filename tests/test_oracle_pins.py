@@ -365,3 +365,38 @@ def test_wave_operator_and_second_order():
     U = np.concatenate([o.wave_u0(m.coords), np.arange(V, dtype=float)])
     du, dv = o.wave_rhs(m, U[:V], U[V:])
     assert np.array_equal(o.spmv_csc(F, U), np.concatenate([du, dv]))
+
+
+# ------------------------------------------------------------------ N1: Tsit5 tableau
+def test_tsit5_tableau_order_conditions():
+    """OrdinaryDiffEq is not vendored in the reference; the tableau restated in the oracle is pinned by the
+    Runge-Kutta order conditions up to order 5 (17 conditions) and the row-sum conditions."""
+    A = np.zeros((7, 7))
+    for s_, row in enumerate(o.TSIT5_A):
+        A[s_ + 1, :len(row)] = row
+    c = np.array((0.0,) + o.TSIT5_C)
+    b = A[6].copy()                         # FSAL: the weights are the last row
+    A6, c6, b6 = A[:6, :6], c[:6], b[:6]
+    assert np.allclose(A.sum(axis=1), c, atol=2e-15)
+    e = np.ones(6)
+    Ac = A6 @ c6
+    conds = [
+        (b6 @ e, 1), (b6 @ c6, 1 / 2), (b6 @ c6 ** 2, 1 / 3), (b6 @ Ac, 1 / 6),
+        (b6 @ c6 ** 3, 1 / 4), (b6 @ (c6 * Ac), 1 / 8), (b6 @ (A6 @ c6 ** 2), 1 / 12), (b6 @ (A6 @ Ac), 1 / 24),
+        (b6 @ c6 ** 4, 1 / 5), (b6 @ (c6 ** 2 * Ac), 1 / 10), (b6 @ (c6 * (A6 @ c6 ** 2)), 1 / 15),
+        (b6 @ (c6 * (A6 @ Ac)), 1 / 30), (b6 @ (Ac * Ac), 1 / 20), (b6 @ (A6 @ c6 ** 3), 1 / 20),
+        (b6 @ (A6 @ (c6 * Ac)), 1 / 40), (b6 @ (A6 @ (A6 @ c6 ** 2)), 1 / 60), (b6 @ (A6 @ (A6 @ Ac)), 1 / 120),
+    ]
+    for got, want in conds:
+        assert abs(got - want) < 5e-15, (got, want)
+
+
+def test_tsit5_fifth_order_on_oscillator():
+    """u'' = -u integrated to t = 1: the error falls by ~2^5 per halving of dt."""
+    def f(U):
+        return (U[1], -U[0])
+    errs = []
+    for n in (8, 16, 32):
+        u, v = o.tsit5_steps(f, (np.array([1.0]), np.array([0.0])), 1.0 / n, n)
+        errs.append(abs(u[0] - np.cos(1.0)) + abs(v[0] + np.sin(1.0)))
+    assert 24 < errs[0] / errs[1] < 40 and 24 < errs[1] / errs[2] < 40, errs
