@@ -201,6 +201,14 @@ int ddf_wave_step_bytes(ddf_mesh* mesh, int64_t* algorithmic, int64_t* format_by
  * 2 = staged rows (TMA-staged gather of u, 16-bit slots, jagged slices; csrc/stage.cuh) */
 int ddf_wave_format(ddf_mesh* mesh, int* format);
 
+/* ------------------------------------------------------------ Krylov solve (N2) */
+/* BiCGStab(l) on device vectors around any operator: the solver examples/poisson.jl:203-227 runs for D >= 3
+ * (IterativeSolvers.bicgstabl_iterator!(x, A', b'; Pl = Identity): l = 2, reltol = sqrt(eps), abstol = 0,
+ * max_mv_products = size(A,2)).  x holds the initial guess on entry and the solution on return; the loop stops
+ * when |r| <= max(reltol*|r0|, abstol) or another sweep would exceed max_mv_products.  Outputs may be NULL. */
+int ddf_solve_bicgstabl(ddf_op* A, ddf_vec* b, ddf_vec* x, int l, double reltol, double abstol, int max_mv_products,
+                        int* mv_products, double* residual, int* converged);
+
 /* --------------------------------------------------------- multi-GPU (NCCL) */
 /* ncclGetUniqueId: 128 bytes, created on rank 0 and broadcast by the host side */
 int ddf_comm_unique_id(void* id128);

@@ -823,6 +823,57 @@ def wave_tsit5(mfd: Manifold, u: np.ndarray, udot: np.ndarray, dt: float, nsteps
 
 
 # --------------------------------------------------------------------------- #
+# N2: the Poisson system of examples/poisson.jl:124-227, block form as in the reference
+# --------------------------------------------------------------------------- #
+def poisson_u_exact(coords: np.ndarray) -> np.ndarray:
+    """examples/poisson.jl:93-122 (D = 1, 2, 3): free-space potential of poisson_rho."""
+    from scipy.special import erf, expi
+    D = coords.shape[1]
+    sigma = 0.2
+    r = np.sqrt(np.sum((coords - 0.1) ** 2, axis=1))
+    rp = r / (np.sqrt(2.0) * sigma)
+    if D == 1:
+        return sigma / np.sqrt(2 * np.pi) * (np.exp(-rp ** 2) - 1) + r / 2 * erf(rp)
+    if D == 2:
+        small = r ** 8 <= np.finfo(np.float64).eps
+        rs = np.where(small, 1.0, rp)
+        big = -1 / (4 * np.pi) * (-np.euler_gamma + expi(-rs ** 2) + np.log(1 / rs ** 2))
+        ser = 1 / (4 * np.pi) * rp ** 2 - 1 / (16 * np.pi) * rp ** 4 + 1 / (72 * np.pi) * rp ** 6
+        return np.where(small, ser, big)
+    if D == 3:
+        rs = np.where(r == 0, 1.0, r)
+        return np.where(r == 0, -1 / (4 * np.pi) * 2 / (np.sqrt(2 * np.pi) * sigma), -1 / (4 * np.pi * rs) * erf(rp))
+    raise ValueError("D <= 3")
+
+
+def poisson_system(mfd: Manifold, rho: np.ndarray, u0: np.ndarray):
+    """A', b' of examples/poisson.jl:172-201:
+        A = [0 delta; -d 1],  b = [rho; 0],  B = [B0 0; 0 0],  c = [u0; 0],
+        A' = (E - B) A + B,   b' = (E - B) b + B c."""
+    n0, n1 = mfd.nsimplices(0), mfd.nsimplices(1)
+    d = deriv(Pr, 0, mfd).astype(np.float64)
+    delta = coderiv(Pr, 1, mfd)
+    B0 = sp.diags(calc_isboundary(mfd, 0).astype(np.float64))
+    A = sp.bmat([[None, delta], [-d, sp.identity(n1)]], format="csc")
+    B = sp.bmat([[B0, None], [None, sp.csc_matrix((n1, n1))]], format="csc")
+    E = sp.identity(n0 + n1, format="csc")
+    b = np.concatenate([rho, np.zeros(n1)])
+    c = np.concatenate([u0, np.zeros(n1)])
+    Ap = ((E - B) @ A + B).tocsc()
+    bp = (E - B) @ b + B @ c
+    return Ap, bp
+
+
+def poisson_solve(mfd: Manifold, rho: np.ndarray, u0: np.ndarray):
+    """x = A' \\ b' (poisson.jl:205-206; UMFPACK there, SuperLU here) split into (u, f)."""
+    import scipy.sparse.linalg as spla
+    Ap, bp = poisson_system(mfd, rho, u0)
+    x = spla.spsolve(Ap, bp)
+    n0 = mfd.nsimplices(0)
+    return x[:n0], x[n0:]
+
+
+# --------------------------------------------------------------------------- #
 # invariant (src/Manifolds.jl:154-189)
 # --------------------------------------------------------------------------- #
 def invariant(mfd: Manifold) -> bool:
