@@ -315,6 +315,8 @@ def run_b200(args):
     dt = ddf.wave_dt(mfd)
     if N > 1:
         dt = ctx.allreduce(dt, "min")
+    if args.wave_tune:
+        ddf._lib.call("ddf_set_tuning", b"wave", int(args.wave_tune))
     ddf.wave_leapfrog(mfd, u, v, dt, W)
     barrier()
     ctx.tic()
@@ -328,7 +330,8 @@ def run_b200(args):
     unorm = u.norm(np.inf)
     wave = {"ms_per_step": wave_ms, "vertex_updates_per_s": sum_over_ranks(float(own[0])) / (wave_ms * 1e-3),
             "algorithmic_bytes": alg, "format_bytes": fmt, "GBps": alg / wave_ms * 1e-6,
-            "frac": alg / wave_ms * 1e-6 / peak, "dt": dt, "u_inf_after": unorm}
+            "frac": alg / wave_ms * 1e-6 / peak, "dt": dt, "u_inf_after": unorm, "row_format": ddf.wave_format(mfd),
+            "halo": ddf.dist.halo_mode(mfd) if N > 1 else "none"}
     clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
@@ -421,6 +424,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--wave-tune", type=int, default=0, help="ddf_set_tuning('wave', x) for A/B runs (1024: NCCL halo)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

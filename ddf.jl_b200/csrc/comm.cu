@@ -10,10 +10,16 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "mesh.cuh"
 
 int ddf_leapfrog_launch(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
                         int64_t row0, int64_t row1);   // wave.cu
+int ddf_leapfrog_launch_p2p(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
+                            int64_t row0, int64_t row1, double* peer_lo, double* peer_hi, int64_t plane);   // wave.cu
+extern int g_tune_wave;
 
 struct NcclApi {
   void* handle = nullptr;
@@ -158,6 +164,193 @@ extern "C" int ddf_halo_exchange(ddf_mesh* m, ddf_vec* u) {
   DDF_TRY_END
 }
 
+// =====================================================================================
+// Fused halo over NVLink peer memory.
+//
+// The NCCL path (ddf_wave_leapfrog_dist below) needs three row-kernel launches and one send/recv kernel per step.
+// Here the compute of a step is ONE launch: the row kernel stores the new u of its two
+// interface planes straight into a landing area in the neighbours' memory (a per-mesh arena
+// mapped once through CUDA IPC), so the transfer rides along with the compute, row by row.
+// Neighbours stay within one step of each other through a counter in the same arena:
+//   * after step k a 1-thread kernel release-stores k into both neighbours' flag words;
+//   * before step k a small kernel waits until both of MY flag words hold >= k-1 -- the
+//     neighbour has then finished step k-1, its stores into my landing area (parity (k-1)&1)
+//     have arrived -- and copies them into the ghost planes of u.  The neighbour overwrites
+//     that parity again in its step k+1, which it cannot start before I signal step k.
+// The handshake (IPC handle of the arena, plane size, step counter) travels over the NCCL
+// communicator on the first distributed step of a mesh.  If IPC is unavailable on any rank,
+// every rank falls back to the NCCL path (agreed through an all-reduce).
+// Arena layout: 4 x u64 {flag from lower, flag from upper, error, magic} | pad to 256 B |
+//               landing[from lower][parity 0,1][P] | landing[from upper][parity 0,1][P]
+// =====================================================================================
+struct HaloRecord {                    // 128 bytes, exchanged with both neighbours
+  cudaIpcMemHandle_t arena;
+  unsigned long long step;
+  long long plane;
+  unsigned long long magic;
+  int ok;
+  char pad[128 - 64 - 3 * 8 - 4];
+};
+static_assert(sizeof(HaloRecord) == 128, "HaloRecord is 128 bytes");
+
+struct HaloP2P {
+  DevBuf<unsigned char> arena;
+  unsigned char* lo_base = nullptr;    // mapped arena of rank-1 / rank+1
+  unsigned char* hi_base = nullptr;
+  unsigned long long* flags() { return reinterpret_cast<unsigned long long*>(arena.p); }
+  static double* landing(unsigned char* base, int from_upper, int parity, int64_t P) {
+    return reinterpret_cast<double*>(base + 256) + ((int64_t)from_upper * 2 + parity) * P;
+  }
+};
+
+// every block waits for the neighbours' step flags, then copies its share of the landed planes into u
+__global__ void __launch_bounds__(256)
+k_halo_wait_copy(unsigned long long* flags, unsigned long long need_lo, unsigned long long need_hi,
+                 const double* __restrict__ land_lo, double* __restrict__ ghost_lo, const double* __restrict__ land_hi,
+                 double* __restrict__ ghost_hi, int64_t P) {
+  __shared__ int bad;
+  if (threadIdx.x == 0) {
+    bad = 0;
+    if (*(volatile unsigned long long*)(flags + 2)) bad = 1;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (!bad) {
+      unsigned long long a, b;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(flags) : "memory");
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(b) : "l"(flags + 1) : "memory");
+      if (a >= need_lo && b >= need_hi) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) { flags[2] = 1ull; bad = 1; }     // 20 s: the neighbour is gone
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  if (bad) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
+    if (land_lo) ghost_lo[i] = __ldcv(land_lo + i);     // written by a peer: do not trust a cached line
+    if (land_hi) ghost_hi[i] = __ldcv(land_hi + i);
+  }
+}
+
+__global__ void k_halo_signal(unsigned long long* to_lower, unsigned long long* to_upper, unsigned long long step) {
+  __threadfence_system();
+  if (to_lower) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(to_lower), "l"(step) : "memory");
+  if (to_upper) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(to_upper), "l"(step) : "memory");
+}
+
+void ddf_halo_release(ddf_mesh* m) {
+  HaloP2P* hp = (HaloP2P*)m->halo_p2p;
+  if (!hp) return;
+  if (hp->lo_base) cudaIpcCloseMemHandle(hp->lo_base);
+  if (hp->hi_base) cudaIpcCloseMemHandle(hp->hi_base);
+  delete hp;
+  m->halo_p2p = nullptr;
+}
+
+// first distributed step of a mesh: allocate the arena, exchange its handle with both neighbours, map theirs
+static int halo_handshake(ddf_mesh* m, int* usable) {
+  ddf_ctx* ctx = m->ctx;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  const int64_t P = m->halo_plane;
+  HaloP2P* hp = new HaloP2P();
+  m->halo_p2p = hp;
+  // a dedicated allocation of whole 2 MiB pages: cudaMalloc never shares those with other buffers, so the
+  // IPC handle maps exactly this arena at offset 0
+  const size_t need = 256 + 4 * (size_t)P * sizeof(double);
+  const size_t bytes = (need + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+  DDF_CHECK(hp->arena.alloc(ctx, bytes));
+  DDF_CUDA(cudaMemsetAsync(hp->arena.p, 0, 256, ctx->stream));
+  const unsigned long long magic = 0xDDF0B200ull * 1315423911ull + (unsigned long long)ctx->rank;
+  DDF_CUDA(cudaMemcpyAsync(hp->flags() + 3, &magic, 8, cudaMemcpyHostToDevice, ctx->stream));
+  HaloRecord* host = reinterpret_cast<HaloRecord*>(ctx->red_host);      // 3 records in the pinned scratch
+  HaloRecord* dev = reinterpret_cast<HaloRecord*>(ctx->red_dev);
+  memset(&host[0], 0, 3 * sizeof(HaloRecord));
+  int ok = 1;
+  if (cudaIpcGetMemHandle(&host[0].arena, hp->arena.p) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  host[0].step = m->halo_step;
+  host[0].plane = P;
+  host[0].magic = magic;
+  host[0].ok = ok;
+  DDF_CUDA(cudaMemcpyAsync(&dev[0], &host[0], sizeof(HaloRecord), cudaMemcpyHostToDevice, ctx->stream));
+  DDF_NCCL(g_nccl.GroupStart());
+  if (m->halo_lo > 0) {
+    DDF_NCCL(g_nccl.Send(&dev[0], sizeof(HaloRecord), ncclChar, ctx->rank - 1, comm, ctx->stream));
+    DDF_NCCL(g_nccl.Recv(&dev[1], sizeof(HaloRecord), ncclChar, ctx->rank - 1, comm, ctx->stream));
+  }
+  if (m->halo_hi > 0) {
+    DDF_NCCL(g_nccl.Send(&dev[0], sizeof(HaloRecord), ncclChar, ctx->rank + 1, comm, ctx->stream));
+    DDF_NCCL(g_nccl.Recv(&dev[2], sizeof(HaloRecord), ncclChar, ctx->rank + 1, comm, ctx->stream));
+  }
+  DDF_NCCL(g_nccl.GroupEnd());
+  DDF_CUDA(cudaMemcpyAsync(&host[1], &dev[1], 2 * sizeof(HaloRecord), cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  const HaloRecord lo = host[1], hi = host[2];
+  auto map = [&](const HaloRecord& r, unsigned char** base) {
+    if (!r.ok || r.plane != P || r.step != m->halo_step) { ok = 0; return; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, r.arena, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; return; }
+    *base = (unsigned char*)p;
+    unsigned long long seen = 0;                       // the mapping must show the exporter's magic word
+    if (cudaMemcpy(&seen, (unsigned long long*)p + 3, 8, cudaMemcpyDeviceToHost) != cudaSuccess || seen != r.magic) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  };
+  if (m->halo_lo > 0) map(lo, &hp->lo_base);
+  if (m->halo_hi > 0 && ok) map(hi, &hp->hi_base);
+  double agreed = ok ? 1.0 : 0.0;
+  DDF_CHECK(ddf_comm_allreduce(ctx, &agreed, 2));       // min over ranks
+  *usable = agreed > 0.5;
+  return 0;
+}
+
+static int leapfrog_dist_p2p(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt, int nsteps) {
+  ddf_ctx* ctx = m->ctx;
+  HaloP2P* hp = (HaloP2P*)m->halo_p2p;
+  const int64_t nv = m->n[0], P = m->halo_plane;
+  const int64_t own_lo = m->halo_lo * P, own_hi = nv - m->halo_hi * P;
+  unsigned long long* flags = hp->flags();
+  const bool has_lo = m->halo_lo > 0, has_hi = m->halo_hi > 0;
+  const int cgrid = (int)std::min<int64_t>(32, ceil_div64(P, 256));
+  unsigned long long err = 0;
+  DDF_CUDA(cudaMemcpyAsync(&err, flags + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (err) DDF_FAIL("halo: timed out waiting for a neighbour's step flag in an earlier call");
+  for (int s = 0; s < nsteps; s++) {
+    const unsigned long long k = ++m->halo_step;
+    const int par_in = (int)((k - 1) & 1), par_out = (int)(k & 1);
+    // the ghost planes are valid on entry (caller's contract); later steps take what the neighbours landed
+    const bool copy = s > 0;
+    double* uo = u->d.p;
+    k_halo_wait_copy<<<cgrid, 256, 0, ctx->stream>>>(
+        flags, has_lo ? k - 1 : 0ull, has_hi ? k - 1 : 0ull,
+        copy && has_lo ? HaloP2P::landing(hp->arena.p, 0, par_in, P) : nullptr, uo + own_lo - P,
+        copy && has_hi ? HaloP2P::landing(hp->arena.p, 1, par_in, P) : nullptr, uo + own_hi, P);
+    DDF_LAUNCH_CHECK(ctx);
+    // I am the UPPER neighbour of rank-1 and the LOWER neighbour of rank+1
+    DDF_CHECK(ddf_leapfrog_launch_p2p(m, ctx->stream, uo, v->d.p, m->utmp.p, dt, own_lo, own_hi,
+                                      has_lo ? HaloP2P::landing(hp->lo_base, 1, par_out, P) : nullptr,
+                                      has_hi ? HaloP2P::landing(hp->hi_base, 0, par_out, P) : nullptr, P));
+    k_halo_signal<<<1, 1, 0, ctx->stream>>>(has_lo ? reinterpret_cast<unsigned long long*>(hp->lo_base) + 1 : nullptr,
+                                            has_hi ? reinterpret_cast<unsigned long long*>(hp->hi_base) + 0 : nullptr, k);
+    DDF_LAUNCH_CHECK(ctx);
+    u->d.swap(m->utmp);
+  }
+  // leave with valid ghost planes: what the neighbours landed in their last step
+  const unsigned long long k = m->halo_step;
+  k_halo_wait_copy<<<cgrid, 256, 0, ctx->stream>>>(
+      flags, has_lo ? k : 0ull, has_hi ? k : 0ull, has_lo ? HaloP2P::landing(hp->arena.p, 0, (int)(k & 1), P) : nullptr,
+      u->d.p + own_lo - P, has_hi ? HaloP2P::landing(hp->arena.p, 1, (int)(k & 1), P) : nullptr, u->d.p + own_hi, P);
+  DDF_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int ddf_halo_mode(ddf_mesh* m, int* mode) {
+  *mode = m->halo_last;
+  return 0;
+}
+
 extern "C" int ddf_wave_leapfrog_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt, int nsteps) {
   DDF_TRY_BEGIN
   ddf_ctx* ctx = m->ctx;
@@ -175,6 +368,20 @@ extern "C" int ddf_wave_leapfrog_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* v, doubl
   }
   const int64_t P = m->halo_plane;
   const int64_t own_lo = m->halo_lo * P, own_hi = nv - m->halo_hi * P;
+  if (nsteps <= 0) return 0;
+  // fused peer-memory halo (default when every rank can map its neighbours; tuning bit 1024 forces NCCL)
+  if (ctx->nranks > 1 && !(g_tune_wave & 1024)) {
+    if (m->halo_p2p_state == 0) {
+      int usable = 0;
+      DDF_CHECK(halo_handshake(m, &usable));
+      m->halo_p2p_state = usable ? 1 : 2;
+    }
+    if (m->halo_p2p_state == 1) {
+      m->halo_last = 1;
+      return leapfrog_dist_p2p(m, u, v, dt, nsteps);
+    }
+  }
+  m->halo_last = 2;
   for (int s = 0; s < nsteps; s++) {
     const double* uo = u->d.p;
     double* un = m->utmp.p;

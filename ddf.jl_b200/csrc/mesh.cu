@@ -104,6 +104,7 @@ extern "C" int ddf_mesh_create(ddf_ctx* ctx, int D, int C, int64_t nvertices, in
 extern "C" int ddf_mesh_destroy(ddf_mesh* m) {
   if (!m) return 0;
   cudaStreamSynchronize(m->ctx->stream);
+  ddf_halo_release(m);
   delete m;
   return 0;
 }

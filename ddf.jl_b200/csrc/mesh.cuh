@@ -95,6 +95,12 @@ struct ddf_mesh {
   // slab halo of the distributed wave step (comm.cu): vertex planes along the
   // slowest axis; the first halo_lo / last halo_hi planes are ghosts owned by rank-1 / rank+1
   int64_t halo_plane = 0, halo_lo = 0, halo_hi = 0;
+  // fused peer-memory halo (comm.cu): arena + peer mappings, the step counter the flags carry;
+  // state 0 = untried, 1 = in use, 2 = unavailable (NCCL send/recv is used instead)
+  void* halo_p2p = nullptr;
+  unsigned long long halo_step = 0;
+  int halo_p2p_state = 0;
+  int halo_last = 0;                     // what the last distributed step used: 1 = peer memory, 2 = NCCL
 
   // hypercube generator parameters (slab meshes of the distributed wave step)
   bool is_hypercube = false;
@@ -111,3 +117,5 @@ int ddf_mesh_require_geometry(ddf_mesh* m);
 int ddf_mesh_require_isboundary(ddf_mesh* m);
 // implemented in wave.cu
 int ddf_mesh_require_wave(ddf_mesh* m);
+// implemented in comm.cu
+void ddf_halo_release(ddf_mesh* m);

@@ -149,7 +149,18 @@ struct RowArgs {
   double* out1;         //            MODE 1: dudot ; MODE 2: unew
   double dt;
   int64_t row0, row1;
+  // fused halo (comm.cu, MODE 2): the new u of the interface planes is ALSO stored straight into the
+  // neighbours' ghost planes through NVLink peer mappings -- rows [row0, send_lo_end) to peer_lo[i - row0],
+  // rows [send_hi_beg, row1) to peer_hi[i - send_hi_beg]
+  double* peer_lo;
+  double* peer_hi;
+  int64_t send_lo_end, send_hi_beg;
 };
+
+__device__ __forceinline__ void peer_store(const RowArgs& a, int64_t i, double w) {
+  if (a.peer_lo && i < a.send_lo_end) a.peer_lo[i - a.row0] = w;
+  if (a.peer_hi && i >= a.send_hi_beg) a.peer_hi[i - a.send_hi_beg] = w;
+}
 
 template <int MODE>
 __device__ __forceinline__ void row_epilogue(const RowArgs& a, int64_t i, double lu, uint64_t pol_stream) {
@@ -163,7 +174,9 @@ __device__ __forceinline__ void row_epilogue(const RowArgs& a, int64_t i, double
     const double m = a.isb[i] ? 0.0 : 1.0;
     const double vn = __dadd_rn(a.out0[i], __dmul_rn(a.dt, __dmul_rn(m, lu)));
     a.out0[i] = vn;
-    a.out1[i] = __dadd_rn(a.u[i], __dmul_rn(a.dt, __dmul_rn(m, vn)));
+    const double w = __dadd_rn(a.u[i], __dmul_rn(a.dt, __dmul_rn(m, vn)));
+    a.out1[i] = w;
+    peer_store(a, i, w);
   }
 }
 
@@ -324,7 +337,9 @@ k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* _
     const double m = eb ? 0.0 : 1.0;
     const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, lu)));
     a.out0[i] = vn;
-    a.out1[i] = __dadd_rn(e1, __dmul_rn(a.dt, __dmul_rn(m, vn)));
+    const double w = __dadd_rn(e1, __dmul_rn(a.dt, __dmul_rn(m, vn)));
+    a.out1[i] = w;
+    peer_store(a, i, w);
   }
 }
 
@@ -477,7 +492,9 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* __
           } else {
             const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, acc)));
             a.out0[i] = vn;
-            a.out1[i] = __dadd_rn(reinterpret_cast<const double*>(sb + g.o_u)[p], __dmul_rn(a.dt, __dmul_rn(m, vn)));
+            const double w = __dadd_rn(reinterpret_cast<const double*>(sb + g.o_u)[p], __dmul_rn(a.dt, __dmul_rn(m, vn)));
+            a.out1[i] = w;
+            peer_store(a, i, w);
           }
         }
       }
@@ -720,6 +737,22 @@ extern "C" int ddf_wave_dt(ddf_mesh* m, double* dt) {
 //   v' = v + dt * ((1-b) .* (L u));   u' = u + dt * ((1-b) .* v')
 // One pass: u is read (own value + gathered neighbours), u' goes to the ping-pong
 // buffer so neighbours still see the old u.  Rows [row0, row1) on `stream`.
+int ddf_leapfrog_launch_p2p(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
+                            int64_t row0, int64_t row1, double* peer_lo, double* peer_hi, int64_t plane) {
+  RowArgs a{};
+  a.u = u;
+  a.out0 = v;
+  a.out1 = unew;
+  a.dt = dt;
+  a.row0 = row0;
+  a.row1 = row1;
+  a.peer_lo = peer_lo;
+  a.peer_hi = peer_hi;
+  a.send_lo_end = row0 + plane;
+  a.send_hi_beg = row1 - plane;
+  return launch_rows<2>(m, stream, a);
+}
+
 int ddf_leapfrog_launch(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
                         int64_t row0, int64_t row1) {
   RowArgs a{};

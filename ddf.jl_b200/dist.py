@@ -102,3 +102,13 @@ def slab_hypercube(D: int, nelts: Sequence[int], ctx, rank: Optional[int] = None
     mfd = large_hypercube_manifold(D, local, ctx=ctx, hdiv=int(nelts[0]), z0=slab.z_cell_lo, assemble=assemble)
     mfd.set_halo(plane, slab.ghost_lo, slab.ghost_hi)
     return mfd, slab
+
+
+def halo_mode(mfd) -> str:
+    """How the last distributed wave step on `mfd` moved its ghost planes: "p2p" (fused peer-memory stores from
+    the row kernel + step flags), "nccl" (ncclSend/ncclRecv fallback) or "none" (not run yet)."""
+    import ctypes as C
+    from ._lib import call
+    mode = C.c_int()
+    call("ddf_halo_mode", mfd._h, C.byref(mode))
+    return ("none", "p2p", "nccl")[mode.value]

@@ -222,6 +222,11 @@ int ddf_mesh_set_halo(ddf_mesh* mesh, int64_t plane, int64_t ghost_lo, int64_t g
 /* fused leapfrog on the owned rows + one-plane halo exchange of u per step with
  * ncclSend/ncclRecv to rank-1 / rank+1, overlapped with the interior rows. */
 int ddf_wave_leapfrog_dist(ddf_mesh* mesh, ddf_vec* u, ddf_vec* v, double dt, int nsteps);
+/* how the last ddf_wave_leapfrog_dist moved its ghost planes: 0 = not run yet, 1 = fused peer-memory stores
+ * (the row kernel writes the interface planes straight into the neighbours' ghost planes over NVLink; neighbours
+ * are kept within one step by release/acquire step flags in peer memory), 2 = ncclSend/ncclRecv (fallback when
+ * CUDA IPC mappings are unavailable on any rank, or forced by ddf_set_tuning("wave", 1024)) */
+int ddf_halo_mode(ddf_mesh* mesh, int* mode);
 /* halo exchange of a vertex cochain alone (fills the ghost planes next to the owned rows) */
 int ddf_halo_exchange(ddf_mesh* mesh, ddf_vec* u);
 /* sum / max all-reduce of a host scalar across ranks (norms, CFL minimum) */

@@ -117,3 +117,95 @@ def test_slab_wave_equals_undivided(world, D, nxy, nz):
     for rank, zlo, zhi, u, v in sorted(res):
         assert np.array_equal(u, ou[zlo * plane:zhi * plane]), f"rank {rank} u"
         assert np.array_equal(v, ov[zlo * plane:zhi * plane]), f"rank {rank} v"
+
+
+def test_peer_memory_halo_protocol_model():
+    """Model of the fused peer-memory halo of csrc/comm.cu (leapfrog_dist_p2p): every rank writes its interface
+    planes into the NEIGHBOURS' landing areas (parity k&1), release-stores the step number k into their flag
+    words, and before step k waits for flags >= k-1 and copies landing[(k-1)&1] into its ghost planes.  Three
+    ranks run as threads with random delays (any interleaving the flags allow); the owned rows must still equal
+    the undivided oracle bit for bit -- i.e. the protocol has neither a RAW nor a WAR hazard."""
+    import random
+    import threading
+    import time
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import ddf_oracle as o
+    from importlib import import_module
+    dd = import_module("ddf.jl_b200.dist")
+    D, nxy, nz, world, nsteps = 3, 2, 12, 3, 9
+    calls = (1, 2, 6)                                   # several calls: the ghost copy is skipped on a call's first step
+    plane = (nxy + 1) ** (D - 1)
+    slabs = dd.partition_slabs(nz, world, plane)
+    flags = [[0, 0] for _ in range(world)]              # [from lower, from upper]
+    landing = [np.zeros((2, 2, plane)) for _ in range(world)]   # [from lower / from upper][parity][P]
+    results = [None] * world
+    errors = []
+
+    def rank_main(rank):
+        try:
+            rnd = random.Random(100 + rank)
+            slab = slabs[rank]
+            simp, coords, weights = o.large_hypercube_tables(D, (nxy,) * (D - 1) + (slab.nz_cells,), h_div=nxy)
+            coords = coords.copy()
+            coords[:, -1] += slab.z_cell_lo / nxy
+            m = o.build_manifold("slab", simp, coords, weights)
+            b, L = o.wave_operators(m)
+            mask = 1.0 - b.astype(np.float64)
+            lo, hi = slab.own_rows
+            has_lo, has_hi = slab.ghost_lo > 0, slab.ghost_hi > 0
+            u = o.wave_u0(m.coords)
+            v = np.zeros_like(u)
+            dt = 1.0 / (2 * nxy)
+            Lr = L.tocsr()
+            Lr.sort_indices()
+            k = 0
+
+            def wait_copy(uvec, need, copy, par):
+                t0 = time.time()
+                while (has_lo and flags[rank][0] < need) or (has_hi and flags[rank][1] < need):
+                    if time.time() - t0 > 60:
+                        raise RuntimeError("flag timeout")
+                    time.sleep(0)
+                if copy:
+                    if has_lo:
+                        uvec[lo - plane:lo] = landing[rank][0][par]
+                    if has_hi:
+                        uvec[hi:hi + plane] = landing[rank][1][par]
+
+            for nst in calls:
+                for s in range(nst):
+                    k += 1
+                    time.sleep(rnd.random() * 0.003)
+                    wait_copy(u, k - 1, s > 0, (k - 1) & 1)
+                    lu = o._segment_sum_sequential(Lr.data * u[Lr.indices], Lr.indptr)
+                    vn, un = v.copy(), u.copy()
+                    vn[lo:hi] = v[lo:hi] + dt * (mask[lo:hi] * lu[lo:hi])
+                    un[lo:hi] = u[lo:hi] + dt * (mask[lo:hi] * vn[lo:hi])
+                    time.sleep(rnd.random() * 0.003)
+                    if has_lo:                           # I am the UPPER neighbour of rank-1
+                        landing[rank - 1][1][k & 1][:] = un[lo:lo + plane]
+                    if has_hi:                           # ... and the LOWER neighbour of rank+1
+                        landing[rank + 1][0][k & 1][:] = un[hi - plane:hi]
+                    if has_lo:
+                        flags[rank - 1][1] = k
+                    if has_hi:
+                        flags[rank + 1][0] = k
+                    u, v = un, vn
+                wait_copy(u, k, True, k & 1)             # leave the call with valid ghost planes
+            results[rank] = (slab.z_own_lo, slab.z_own_hi, u[lo:hi].copy(), v[lo:hi].copy())
+        except Exception as e:                            # pragma: no cover
+            errors.append((rank, repr(e)))
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    m = o.large_hypercube_manifold(D, (nxy,) * (D - 1) + (nz,), h_div=nxy)
+    ou, ov = o.wave_leapfrog(m, o.wave_u0(m.coords), np.zeros(m.nsimplices(0)), 1.0 / (2 * nxy), nsteps)
+    for zlo, zhi, u, v in results:
+        assert np.array_equal(u, ou[zlo * plane:zhi * plane])
+        assert np.array_equal(v, ov[zlo * plane:zhi * plane])

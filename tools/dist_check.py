@@ -26,12 +26,21 @@ def main():
     ctx = ddf.Context(local)
     ddf.dist.init_comm(ctx)
     ok = True
-    for D, nelts, nsteps in ((3, (8, 8, 8 * world), 9), (2, (16, 16 * world), 12), (3, (16, 16, 4 * world + 4), 5)):
+    cases = ((3, (8, 8, 8 * world), 9), (2, (16, 16 * world), 12), (3, (16, 16, 4 * world + 4), 5),
+             (3, (48, 48, 16 * world), 7))
+    for tune, (D, nelts, nsteps) in [(t, c) for t in (0, 1024) for c in cases]:
+        ddf._lib.call("ddf_set_tuning", b"wave", tune)       # 0: fused peer-memory halo, 1024: NCCL send/recv
         mfd, slab = ddf.dist.slab_hypercube(D, nelts, ctx)
         u = ddf.sample(mfd, "wave")
         v = ddf.Fun(mfd, ddf.Pr, 0)
         dt = ctx.allreduce(ddf.wave_dt(mfd), "min")
-        ddf.wave_leapfrog(mfd, u, v, dt, nsteps)
+        # several calls with odd and even step counts: the ping-pong buffers swap roles between calls
+        done = 0
+        for part in (1, 2, nsteps - 3):
+            ddf.wave_leapfrog(mfd, u, v, dt, part)
+            done += part
+        assert done == nsteps
+        mode = ddf.dist.halo_mode(mfd)
         lo, hi = slab.own_rows
         mine = (slab.z_own_lo, u.values[lo:hi].copy(), v.values[lo:hi].copy(), u.norm(np.inf))
         parts = [None] * world
@@ -49,7 +58,7 @@ def main():
             for zlo, pu, pv, _ in sorted(parts, key=lambda t: t[0]):
                 a = zlo * plane
                 same = same and np.array_equal(pu, ru[a:a + len(pu)]) and np.array_equal(pv, rv[a:a + len(pv)])
-            print(f"dist_check D={D} nelts={nelts} world={world} steps={nsteps}: "
+            print(f"dist_check halo={mode} D={D} nelts={nelts} world={world} steps={nsteps}: "
                   f"{'BIT-EXACT' if same else 'MISMATCH'}  |u|inf={np.max(np.abs(ru)):.6f}", flush=True)
             ok = ok and same
             full.close()
