@@ -53,6 +53,13 @@ struct OpNode {
   std::vector<double> coefs;
   // scratch vectors reused across applies
   std::vector<std::unique_ptr<DevBuf<double>>> temps;
+  // The expression as the caller wrote it (association kept): `factors` above is flattened for the lazy
+  // apply, but the ASSEMBLED matrix of the reference is rounded and chopped after every binary product /
+  // sum (Ops.jl:25,228-232), so ddf_op_to_csc evaluates this tree instead.
+  std::vector<OpRef> tree_ops;       // CHAIN: operands left to right ; SUM: terms
+  std::vector<double> tree_coefs;    // SUM: coefficient of every term
+  double tree_scale = 1.0;           // CHAIN: scalar applied to the assembled product (a * A, Ops.jl:240-243)
+  OpRef adj_of;                      // this node is adjoint(adj_of)
 };
 
 struct ddf_op {
@@ -547,6 +554,8 @@ static OpRef chain_of(std::vector<OpRef> f, double scalar) {
   n->nrows = f.front()->nrows;
   n->ncols = f.back()->ncols;
   n->scale = scalar;
+  n->tree_ops = f;
+  n->tree_scale = scalar;
   // flatten nested chains
   for (auto& g : f) {
     if (g->kind == OPK_CHAIN) {
@@ -620,6 +629,8 @@ extern "C" int ddf_op_laplace(ddf_mesh* m, int P, int R, ddf_op** out) {
     sum->coefs.push_back(1.0);
   }
   if (sum->factors.empty()) { sum->kind = OPK_ZERO; }
+  sum->tree_ops = sum->factors;          // op = zero; op += d*delta; op += delta*d  (ManifoldOps.jl:131-143)
+  sum->tree_coefs = sum->coefs;
   *out = wrap(sum);
   return 0;
   DDF_TRY_END
@@ -850,6 +861,8 @@ extern "C" int ddf_op_add(ddf_op* A, double b, ddf_op* B, ddf_op** out) {
   };
   push(a, 1.0);
   push(bb, b);
+  s->tree_ops = {a, bb};
+  s->tree_coefs = {1.0, b};
   if (s->factors.empty()) s->kind = OPK_ZERO;
   *out = wrap(s);
   return 0;
@@ -911,6 +924,8 @@ static int adjoint_node(OpRef n, OpRef* out) {
         f.push_back(a);
       }
       *out = chain_of(f, n->scale);
+      (*out)->tree_ops.clear();
+      (*out)->adj_of = n;
       return 0;
     }
     case OPK_SUM: {
@@ -922,6 +937,7 @@ static int adjoint_node(OpRef n, OpRef* out) {
         s->factors.push_back(a);
         s->coefs.push_back(n->coefs[i]);
       }
+      s->adj_of = n;
       *out = s;
       return 0;
     }
@@ -1100,6 +1116,7 @@ struct Coo {
   DevBuf<int32_t> row, col;
   DevBuf<double> val;
   int64_t nnz = 0;
+  bool is_diag = false;     // a Diagonal in the reference: products of Diagonals stay Diagonal and are never chopped
 };
 
 // d_R^T (FIXED, n_R x n_{R-1}): CSC columns are faces -> parents = the row-CSR of d_R
@@ -1277,6 +1294,217 @@ static int transpose_csrf64(OpRef src, OpRef* out) {
   return 0;
 }
 
+// ----------------------------------------------------------------------------- N3: assembled Op algebra
+// SparseArrays' A*B (spmatmul): for every column j of B, for k in B[:,j] ascending, for i in A[:,k]
+// ascending: the first touch of C[i,j] assigns fl(A[i,k]*B[k,j]), later touches add -- i.e. a left fold
+// over k ascending.  Here: expand every product in exactly that order, stable radix sort by (j, i)
+// (ties keep the expansion order), left fold of every run.  Bit-identical values, CSC-ordered output.
+__global__ void k_count_products(const int32_t* __restrict__ brow, int64_t bnnz, const uint32_t* __restrict__ acolptr,
+                                 uint32_t* __restrict__ cnt) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < bnnz) { const int32_t k = brow[p]; cnt[p] = acolptr[k + 1] - acolptr[k]; }
+  if (p == bnnz) cnt[p] = 0;
+}
+__global__ void k_expand_products(const int32_t* __restrict__ brow, const int32_t* __restrict__ bcol,
+                                  const double* __restrict__ bval, int64_t bnnz, const uint32_t* __restrict__ acolptr,
+                                  const int32_t* __restrict__ arow, const double* __restrict__ aval,
+                                  const uint32_t* __restrict__ off, unsigned long long* __restrict__ key,
+                                  double* __restrict__ val) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= bnnz) return;
+  const int32_t k = brow[p];
+  const unsigned long long j = (unsigned long long)(uint32_t)bcol[p] << 32;
+  const double b = bval[p];
+  uint32_t o = off[p];
+  for (uint32_t q = acolptr[k]; q < acolptr[k + 1]; q++, o++) {
+    key[o] = j | (uint32_t)arow[q];
+    val[o] = __dmul_rn(aval[q], b);
+  }
+}
+__global__ void k_key_heads(const unsigned long long* __restrict__ key, int64_t n, uint8_t* __restrict__ head) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) head[p] = (p == 0 || key[p] != key[p - 1]) ? 1 : 0;
+}
+// one thread per run head: sequential left fold of the run, output at the run's rank
+__global__ void k_fold_runs(const unsigned long long* __restrict__ key, const double* __restrict__ val,
+                            const uint8_t* __restrict__ head, const uint32_t* __restrict__ rank, int64_t n,
+                            int32_t* __restrict__ row, int32_t* __restrict__ col, double* __restrict__ out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n || !head[p]) return;
+  double acc = val[p];
+  for (int64_t q = p + 1; q < n && !head[q]; q++) acc = __dadd_rn(acc, val[q]);
+  const uint32_t r = rank[p];
+  row[r] = (int32_t)(key[p] & 0xffffffffull);
+  col[r] = (int32_t)(key[p] >> 32);
+  out[r] = acc;
+}
+__global__ void k_scale_vals(double* __restrict__ v, int64_t n, double a) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) v[p] = __dmul_rn(a, v[p]);
+}
+__global__ void k_pack_keys(const int32_t* __restrict__ row, const int32_t* __restrict__ col, int64_t n,
+                            unsigned long long* __restrict__ key) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) key[p] = ((unsigned long long)(uint32_t)col[p] << 32) | (uint32_t)row[p];
+}
+
+static void coo_move(Coo& dst, Coo& src) {
+  dst.row.swap(src.row); dst.col.swap(src.col); dst.val.swap(src.val);
+  dst.nnz = src.nnz; dst.is_diag = src.is_diag;
+}
+static int coo_scale(ddf_ctx* ctx, Coo& c, double a) {
+  if (a == 1.0 || c.nnz == 0) return 0;
+  int grid;
+  DDF_CHECK(grid_for(c.nnz, 256, &grid));
+  k_scale_vals<<<grid, 256, 0, ctx->stream>>>(c.val.p, c.nnz, a);
+  DDF_LAUNCH_CHECK(ctx);
+  return 0;
+}
+static int bits_for(int64_t n) { int b = 1; while (((int64_t)1 << b) < n) b++; return b; }
+
+// (key, val) in expansion order -> sorted by key (stable), runs folded left to right -> Coo in CSC order
+static int coo_from_keyed(ddf_ctx* ctx, DevBuf<unsigned long long>& key, DevBuf<double>& val, int64_t n, int64_t ncols,
+                          Coo& out) {
+  if (n == 0) return coo_alloc(ctx, out, 0);
+  if (n > 0xFFFFFFF0LL) DDF_FAIL("assembled product: %lld partial products exceed the 32-bit staging index", (long long)n);
+  DevBuf<unsigned long long> key2;
+  DevBuf<uint32_t> i0, i1, rank;
+  DevBuf<uint8_t> temp, head;
+  DevBuf<double> sval;
+  DDF_CHECK(key2.alloc(ctx, n)); DDF_CHECK(i0.alloc(ctx, n)); DDF_CHECK(i1.alloc(ctx, n));
+  int grid;
+  DDF_CHECK(grid_for(n, 256, &grid));
+  k_iota_u32<<<grid, 256, 0, ctx->stream>>>(i0.p, n);
+  DDF_LAUNCH_CHECK(ctx);
+  cub::DoubleBuffer<unsigned long long> dk(key.p, key2.p);
+  cub::DoubleBuffer<uint32_t> di(i0.p, i1.p);
+  size_t tb = 0;
+  const int end_bit = 32 + bits_for(ncols);
+  DDF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, di, n, 0, end_bit, ctx->stream));
+  DDF_CHECK(temp.alloc(ctx, tb));
+  DDF_CUDA(cub::DeviceRadixSort::SortPairs(temp.p, tb, dk, di, n, 0, end_bit, ctx->stream));
+  ctx->launches += (end_bit + 7) / 8 + 1;
+  DDF_CHECK(sval.alloc(ctx, n));
+  k_gather_f64<<<grid, 256, 0, ctx->stream>>>(di.Current(), val.p, n, sval.p);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CHECK(head.alloc(ctx, n));
+  DDF_CHECK(rank.alloc(ctx, n + 1));
+  k_key_heads<<<grid, 256, 0, ctx->stream>>>(dk.Current(), n, head.p);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, head.p, rank.p, n, ctx->stream));
+  DDF_CHECK(temp.alloc(ctx, tb));
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, head.p, rank.p, n, ctx->stream));
+  ctx->launches++;
+  uint32_t last_rank = 0;
+  uint8_t last_head = 0;
+  DDF_CUDA(cudaMemcpyAsync(&last_rank, rank.p + n - 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaMemcpyAsync(&last_head, head.p + n - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int64_t nout = (int64_t)last_rank + (last_head ? 1 : 0);
+  DDF_CHECK(coo_alloc(ctx, out, nout));
+  k_fold_runs<<<grid, 256, 0, ctx->stream>>>(dk.Current(), sval.p, head.p, rank.p, n, out.row.p, out.col.p, out.val.p);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// column pointers of a CSC-ordered Coo
+static int coo_colptr(ddf_ctx* ctx, const Coo& c, int64_t ncols, DevBuf<uint32_t>& cp) {
+  DevBuf<uint32_t> keys;
+  DDF_CHECK(cp.alloc(ctx, ncols + 1));
+  int grid;
+  if (c.nnz) {
+    DDF_CHECK(keys.alloc(ctx, c.nnz));
+    DDF_CHECK(grid_for(c.nnz, 256, &grid));
+    k_i32_to_u32<<<grid, 256, 0, ctx->stream>>>(c.col.p, keys.p, c.nnz);
+    DDF_LAUNCH_CHECK(ctx);
+  }
+  DDF_CHECK(grid_for(ncols + 1, 256, &grid));
+  k_lower_bound<<<grid, 256, 0, ctx->stream>>>(keys.p, c.nnz, ncols, cp.p);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// C = A * B, both CSC-ordered; A is nrowsA x inner, B is inner x ncolsB
+static int coo_spgemm(ddf_ctx* ctx, const Coo& A, int64_t nrowsA, int64_t inner, const Coo& B, int64_t ncolsB, Coo& C) {
+  (void)nrowsA;
+  if (A.nnz == 0 || B.nnz == 0) return coo_alloc(ctx, C, 0);
+  DevBuf<uint32_t> acp, cnt, off;
+  DevBuf<uint8_t> temp;
+  DDF_CHECK(coo_colptr(ctx, A, inner, acp));
+  DDF_CHECK(cnt.alloc(ctx, B.nnz + 1));
+  DDF_CHECK(off.alloc(ctx, B.nnz + 1));
+  int grid;
+  DDF_CHECK(grid_for(B.nnz + 1, 256, &grid));
+  k_count_products<<<grid, 256, 0, ctx->stream>>>(B.row.p, B.nnz, acp.p, cnt.p);
+  DDF_LAUNCH_CHECK(ctx);
+  size_t tb = 0;
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, B.nnz + 1, ctx->stream));
+  DDF_CHECK(temp.alloc(ctx, tb));
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, cnt.p, off.p, B.nnz + 1, ctx->stream));
+  ctx->launches++;
+  uint32_t total = 0;
+  DDF_CUDA(cudaMemcpyAsync(&total, off.p + B.nnz, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (total == 0) return coo_alloc(ctx, C, 0);
+  DevBuf<unsigned long long> key;
+  DevBuf<double> val;
+  DDF_CHECK(key.alloc(ctx, total));
+  DDF_CHECK(val.alloc(ctx, total));
+  DDF_CHECK(grid_for(B.nnz, 256, &grid));
+  k_expand_products<<<grid, 256, 0, ctx->stream>>>(B.row.p, B.col.p, B.val.p, B.nnz, acp.p, A.row.p, A.val.p, off.p, key.p,
+                                                   val.p);
+  DDF_LAUNCH_CHECK(ctx);
+  return coo_from_keyed(ctx, key, val, total, ncolsB, C);
+}
+
+// C = A + B over the union pattern (A's value first in every sum)
+static int coo_add(ddf_ctx* ctx, const Coo& A, const Coo& B, int64_t nrows, int64_t ncols, Coo& C) {
+  (void)nrows;
+  const int64_t n = A.nnz + B.nnz;
+  if (n == 0) return coo_alloc(ctx, C, 0);
+  DevBuf<unsigned long long> key;
+  DevBuf<double> val;
+  DDF_CHECK(key.alloc(ctx, n));
+  DDF_CHECK(val.alloc(ctx, n));
+  int grid;
+  if (A.nnz) {
+    DDF_CHECK(grid_for(A.nnz, 256, &grid));
+    k_pack_keys<<<grid, 256, 0, ctx->stream>>>(A.row.p, A.col.p, A.nnz, key.p);
+    DDF_LAUNCH_CHECK(ctx);
+    DDF_CUDA(cudaMemcpyAsync(val.p, A.val.p, A.nnz * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  if (B.nnz) {
+    DDF_CHECK(grid_for(B.nnz, 256, &grid));
+    k_pack_keys<<<grid, 256, 0, ctx->stream>>>(B.row.p, B.col.p, B.nnz, key.p + A.nnz);
+    DDF_LAUNCH_CHECK(ctx);
+    DDF_CUDA(cudaMemcpyAsync(val.p + A.nnz, B.val.p, B.nnz * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return coo_from_keyed(ctx, key, val, n, ncols, C);
+}
+
+// in-place transpose of a CSC-ordered Coo (result CSC-ordered again); nrows = rows of the input
+static int coo_transpose(ddf_ctx* ctx, Coo& c, int64_t nrows) {
+  c.row.swap(c.col);                     // entries (j, i); still sorted by the OLD column = new row
+  if (c.nnz == 0) return 0;
+  DevBuf<unsigned long long> key;
+  DevBuf<double> val;
+  DDF_CHECK(key.alloc(ctx, c.nnz));
+  DDF_CHECK(val.alloc(ctx, c.nnz));
+  int grid;
+  DDF_CHECK(grid_for(c.nnz, 256, &grid));
+  k_pack_keys<<<grid, 256, 0, ctx->stream>>>(c.row.p, c.col.p, c.nnz, key.p);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CUDA(cudaMemcpyAsync(val.p, c.val.p, c.nnz * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  Coo out;
+  const bool d = c.is_diag;
+  DDF_CHECK(coo_from_keyed(ctx, key, val, c.nnz, nrows, out));
+  coo_move(c, out);
+  c.is_diag = d;
+  return 0;
+}
+
 int ddf_laplace0_to_coo(ddf_mesh* m, DevBuf<int32_t>& row, DevBuf<int32_t>& col, DevBuf<double>& val, int64_t* nnz);  // wave.cu
 
 // materialise node -> Coo in CSC order, chopped
@@ -1284,6 +1512,10 @@ static int materialise(OpNode* n, Coo& c) {
   ddf_ctx* ctx = n->ctx;
   ddf_mesh* m = n->mesh;
   int grid;
+  if (n->adj_of) {                      // adjoint(A).values = transpose of the assembled A
+    DDF_CHECK(materialise(n->adj_of.get(), c));
+    return coo_transpose(ctx, c, n->adj_of->nrows);
+  }
   // pattern [DIAG] sparse [DIAG] (also a bare sparse leaf / bare diagonal)
   const OpNode *dl = nullptr, *dr = nullptr, *core = nullptr;
   if (n->kind == OPK_FIXED || n->kind == OPK_CSRSIGN) core = n;
@@ -1325,6 +1557,7 @@ static int materialise(OpNode* n, Coo& c) {
       k_coo_diag<<<grid, 256, 0, ctx->stream>>>(n->diag, n->scale, n->nrows, c.row.p, c.col.p, c.val.p);
       DDF_LAUNCH_CHECK(ctx);
     }
+    c.is_diag = true;
     return 0;     // Diagonal is not an AbstractSparseMatrix: dnz leaves it alone (Ops.jl:40)
   }
   if (n->kind == OPK_ZERO) return coo_alloc(ctx, c, 0);
@@ -1344,8 +1577,40 @@ static int materialise(OpNode* n, Coo& c) {
     DDF_CHECK(ddf_laplace0_to_coo(m, c.row, c.col, c.val, &c.nnz));
     return coo_chop(ctx, c);
   }
-  ddf_set_error("to_csc: assembled export is implemented for deriv/boundary, hodge, coderiv (diag*sparse*diag), "
-                "laplace(Pr,0) and from_csc operators; general Op*Op SpGEMM is a next-row item (SURVEY 8f N3)");
+  if (n->kind == OPK_CHAIN && !n->tree_ops.empty()) {
+    // ((o1 * o2) * o3) ... : SparseArrays spmatmul + dnz/chop after every product (Ops.jl:228-232)
+    DDF_CHECK(materialise(n->tree_ops[0].get(), c));
+    int64_t nrows = n->tree_ops[0]->nrows;
+    for (size_t t = 1; t < n->tree_ops.size(); t++) {
+      Coo b, prod;
+      DDF_CHECK(materialise(n->tree_ops[t].get(), b));
+      DDF_CHECK(coo_spgemm(ctx, c, nrows, n->tree_ops[t]->nrows, b, n->tree_ops[t]->ncols, prod));
+      prod.is_diag = c.is_diag && b.is_diag;
+      if (!prod.is_diag) DDF_CHECK(coo_chop(ctx, prod));
+      coo_move(c, prod);
+    }
+    if (n->tree_scale != 1.0) {
+      DDF_CHECK(coo_scale(ctx, c, n->tree_scale));
+      if (!c.is_diag) DDF_CHECK(coo_chop(ctx, c));
+    }
+    return 0;
+  }
+  if (n->kind == OPK_SUM && !n->tree_ops.empty()) {
+    // A + b*B: map(+, A, B) over the union pattern, then dnz/chop (Ops.jl:186-196)
+    DDF_CHECK(materialise(n->tree_ops[0].get(), c));
+    DDF_CHECK(coo_scale(ctx, c, n->tree_coefs[0]));
+    for (size_t t = 1; t < n->tree_ops.size(); t++) {
+      Coo b, sum;
+      DDF_CHECK(materialise(n->tree_ops[t].get(), b));
+      DDF_CHECK(coo_scale(ctx, b, n->tree_coefs[t]));
+      DDF_CHECK(coo_add(ctx, c, b, n->nrows, n->ncols, sum));
+      sum.is_diag = c.is_diag && b.is_diag;
+      if (!sum.is_diag) DDF_CHECK(coo_chop(ctx, sum));
+      coo_move(c, sum);
+    }
+    return 0;
+  }
+  ddf_set_error("to_csc: this operator has no assembled form (kind %d)", (int)n->kind);
   return 1;
 }
 

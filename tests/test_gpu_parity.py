@@ -313,6 +313,55 @@ def test_export_deriv_and_hodge(ddf, pairs):
         assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
 
 
+# ------------------------------------------------------- N3: assembled Op algebra (SpGEMM)
+@pytest.mark.parametrize("kind", ["kuhn2n4", "kuhn3n4", "simplex3", "refined2l4"])
+def test_assembled_products_bit_exact(ddf, pairs, kind):
+    """Op*Op and Op+Op as ASSEMBLED matrices (Ops.jl:186-196,228-232: SparseArrays spmatmul, dnz/chop after every
+    operation): laplace(P,R) for every (P,R), delta*delta, adjoints and user-composed products, exported with
+    to_csc(), against the oracle's restatement of Julia's spmatmul order -- pattern and values bit for bit."""
+    om, dm = pairs(kind)
+    om = with_device_geometry(om, dm)
+    D = om.D
+
+    def same(A, B, what):
+        B = B.tocsc()
+        B.sort_indices()
+        assert A.shape == B.shape, what
+        assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices), what
+        assert np.array_equal(A.data, B.data), what
+
+    for P in (o.Pr, o.Dl):
+        for R in range(D + 1):
+            same(ddf.laplace(P, R, dm).to_csc(), o.laplace(P, R, om), ("laplace", P, R))
+    for R in range(1, D):                                  # delta_R delta_{R+1} (test-manifoldops.jl:116-131)
+        A = (ddf.coderiv(ddf.Pr, R, dm) * ddf.coderiv(ddf.Pr, R + 1, dm)).to_csc()
+        B = o.chop_sparse(o.julia_spgemm(o.coderiv(o.Pr, R, om), o.coderiv(o.Pr, R + 1, om)))
+        same(A, B, ("delta delta", R))
+    d0, d1 = ddf.deriv(ddf.Pr, 0, dm), (ddf.deriv(ddf.Pr, 1, dm) if D >= 2 else None)
+    od0 = o.deriv(o.Pr, 0, om).astype(np.float64)
+    if d1 is not None:
+        od1 = o.deriv(o.Pr, 1, om).astype(np.float64)
+        assert (d1 * d0).to_csc().nnz == 0                 # dd = 0 exactly, every partial sum chopped away
+        # (d1' * d1) * (2 * (d0 * d0')) + d0 * d0' : association, scalar, adjoint and sum
+        A = ((d1.T * d1) * (2.0 * (d0 * d0.T)) + d0 * d0.T).to_csc()
+        X = o.chop_sparse(o.julia_spgemm(od1.T.tocsc(), od1))
+        Y = o.chop_sparse(o.julia_spgemm(od0, od0.T.tocsc()))
+        Z = o.chop_sparse(o.julia_spgemm(X, o.chop_sparse(2.0 * Y)))
+        same(A, o.chop_sparse(Z + Y), "composite")
+    # star-weighted: (d0' * hodge1) * d0 versus d0' * (hodge1 * d0): different roundings, both reproduced
+    h1 = ddf.hodge(ddf.Pr, 1, dm)
+    oh1 = sp.diags(o.hodge_diag(o.Pr, 1, om)).tocsc()
+    dd1 = ddf.deriv(ddf.Dl, 1, dm)                         # the matrix d0' typed as a dual derivative (ManifoldOps.jl:46)
+    lhs = ((dd1 * h1) * d0).to_csc()
+    same(lhs, o.chop_sparse(o.julia_spgemm(o.chop_sparse(od0.T.tocsc() @ oh1), od0)), "left assoc")
+    rhs = (dd1 * (h1 * d0)).to_csc()
+    same(rhs, o.chop_sparse(o.julia_spgemm(od0.T.tocsc(), o.chop_sparse(oh1 @ od0))), "right assoc")
+    # the Dirichlet-projected Poisson operator of examples/poisson.jl:197 (u block)
+    b0 = sp.diags(o.calc_isboundary(om, 0).astype(np.float64)).tocsc()
+    e0 = sp.identity(om.nsimplices(0), format="csc")
+    same(ddf.poisson_operator(dm).to_csc(), o.chop_sparse(o.chop_sparse((e0 - b0) @ o.laplace(o.Pr, 0, om)) + b0), "A'")
+
+
 # ------------------------------------------------------------------ N2: Poisson solve
 @pytest.mark.parametrize("kind", ["refined2l4", "kuhn2n16", "kuhn3n4", "kuhn3n8"])
 def test_poisson_solve_matches_direct_solve(ddf, pairs, kind):
