@@ -379,6 +379,18 @@ def run_b200(args):
 
     if rank == 0:
         d1_bytes = dk_bytes(cnt[2], cnt[1], 1)
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch); scaled by the
+        # algorithmic bytes when this run's slab differs slightly from the captured n=256 cube
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("n") == n:
+                e = tj["k_apply_fixed<3>"]
+                traffic = e["traffic_bytes"] * d1_bytes / e["algorithmic_bytes"]
+                traffic_src = tj["source"]
+        except (OSError, KeyError, ValueError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -391,7 +403,8 @@ def run_b200(args):
                        "parallelism": "none" if N == 1 else f"z-slabs x{N}, no collective in d_k/star_k apply; "
                                                             "NCCL send/recv halo in the wave step"},
             "roofline": {"bound": "hbm", "kernel": "k_apply_fixed<3> (y = d1 x)", "achieved": d1_bytes / d1_ms * 1e-6,
-                         "peak": peak, "unit": "GB/s", "frac": d1_bytes / d1_ms * 1e-6 / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": d1_bytes / d1_ms * 1e-6 / peak, "traffic": traffic,
+                         "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(d1_bytes),
                          "ms_per_launch": d1_ms, "frac_of_nominal_8TBs": d1_bytes / d1_ms * 1e-6 / 8000.0},
             "breakdown": breakdown, "wave": wave, "assembly_ms": asm_ms, "setup_s": setup_s,

@@ -169,6 +169,46 @@ function LinearAlgebra.mul!(y::DeviceVector, A::DeviceOp, x::DeviceVector)
     return y
 end
 
+# `.values` of an assembled operator (src/Ops.jl:25: Op(...) runs dnz/chop): the device evaluates the
+# expression with SparseArrays' spmatmul order and the chop after every product / sum
+function SparseArrays.sparse(A::DeviceOp)
+    nnz = Ref{Int64}(0)
+    check(ccall((:ddf_op_to_csc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                A.h, nnz, C_NULL, C_NULL, C_NULL))
+    nr, nc = size(A)
+    colptr = Vector{Int64}(undef, nc + 1); rowval = Vector{Int64}(undef, nnz[]); nzval = Vector{Float64}(undef, nnz[])
+    check(ccall((:ddf_op_to_csc, lib), Cint, (Ptr{Cvoid}, Ref{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                A.h, nnz, colptr, rowval, nzval))
+    return SparseMatrixCSC{Float64,Int}(nr, nc, colptr, rowval, nzval)
+end
+
+# OrdinaryDiffEq's stage broadcasts on the state vector (`@.. tmp = uprev + dt*(a31*k1 + a32*k2)`,
+# examples/wave.jl:134) in one pass
+function lincomb!(out::DeviceVector, base::DeviceVector, dt::Float64, coefs::Vector{Float64}, ks::Vector{DeviceVector})
+    hs = Ptr{Cvoid}[k.h for k in ks]
+    GC.@preserve coefs hs check(ccall((:ddf_vec_lincomb, lib), Cint,
+                                      (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Float64}, Ptr{Ptr{Cvoid}}),
+                                      out.h, base.h, dt, length(ks), coefs, hs))
+    return out
+end
+
+# the whole fixed-step Tsit5 loop of examples/wave.jl:134 on the device (U = [u; udot])
+function tsit5!(m::DeviceManifold, u::DeviceVector, udot::DeviceVector, dt::Float64, nsteps::Int)
+    check(ccall((:ddf_wave_tsit5, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint),
+                m.h, u.h, udot.h, dt, nsteps))
+    return u, udot
+end
+
+# examples/poisson.jl:203-227: bicgstabl_iterator!(x, A', b'; Pl = Identity()) with IterativeSolvers' defaults
+function bicgstabl!(x::DeviceVector, A::DeviceOp, b::DeviceVector; l::Int=2, reltol::Float64=sqrt(eps(Float64)),
+                    abstol::Float64=0.0, max_mv_products::Int=size(A, 2))
+    mv = Ref{Cint}(0); res = Ref{Float64}(0); conv = Ref{Cint}(0)
+    check(ccall((:ddf_solve_bicgstabl, lib), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cdouble, Cdouble, Cint, Ref{Cint}, Ref{Float64}, Ref{Cint}),
+                A.h, b.h, x.h, l, reltol, abstol, max_mv_products, mv, res, conv))
+    return x, (mv_products=Int(mv[]), residual=res[], converged=conv[] != 0)
+end
+
 # fused step (north_star): v += dt (1-b).(L u); u += dt (1-b).v
 function leapfrog!(m::DeviceManifold, u::DeviceVector, v::DeviceVector, dt::Float64, nsteps::Int)
     check(ccall((:ddf_wave_leapfrog, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint),
