@@ -47,6 +47,18 @@ struct StageBufs {
   }
 };
 
+// staged fixed-width rows of d_k (fstage.cuh): run tables + 16-bit slots per 1024-row window
+struct FStageBufs {
+  DevBuf<uint32_t> tab;
+  DevBuf<uint16_t> slot;
+  uint32_t max_slots = 0;
+  int W = 0;
+  int win = 0;              // rows per window
+  int64_t nwin = 0;
+  int state = 0;            // 0 = not built, 1 = in use, 2 = rejected (explicit-index kernel)
+  void release() { tab.release(); slot.release(); max_slots = 0; W = 0; win = 0; nwin = 0; state = 0; }
+};
+
 struct ddf_mesh {
   ddf_ctx* ctx = nullptr;
   int D = 0, C = 0;
@@ -90,6 +102,8 @@ struct ddf_mesh {
   // built, 1 = in use, 2 = rejected (padding too large -> CSR kernel)
   int bsell_state[DDF_MAXD + 1] = {0};
   SellBufs bsell[DDF_MAXD + 1];
+  // staged copies of the fixed-width tables of d_{R-1} = d_R^T (primal derivative apply)
+  FStageBufs fstage[DDF_MAXD + 1];
   DevBuf<double> utmp;                   // V   ping-pong buffer of the fused step
 
   // slab halo of the distributed wave step (comm.cu): vertex planes along the

@@ -23,6 +23,7 @@
 
 #include "mesh.cuh"
 #include "sell.cuh"
+#include "fstage.cuh"
 
 extern int g_tune_fixed;
 int ddf_laplace0_apply(ddf_mesh* m, const double* x, double* y);   // wave.cu
@@ -381,7 +382,7 @@ static int launch_fixed(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, 
   if (nrows == 0) return 0;
   int grid;
   DDF_CHECK(grid_for(ceil_div64(nrows, 4), 256, &grid));
-  if (g_tune_fixed > 0 && !pre && !post && alpha == 1.0 && W >= 2 && W <= 4) {
+  if (g_tune_fixed > 0 && g_tune_fixed < 9 && !pre && !post && alpha == 1.0 && W >= 2 && W <= 4) {
     if (W == 2) launch_fixed_x<2>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
     else if (W == 3) launch_fixed_x<3>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
     else launch_fixed_x<4>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
@@ -981,6 +982,25 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
   if (post) a *= post->scale;
   if (f->kind == OPK_FIXED) {
     const int W = f->R + 1;
+    // plain y = d_k x: staged rows through the persistent TMA pipeline (fstage.cuh) when the table stages
+    // Staged rows through a TMA pipeline (fstage.cuh) are OPT-IN: tuning value 100 + 10*NG + RPT.  Measured at C4
+    // (profiles/r01_tuning.md) they lose to the explicit-index kernel -- the pipeline is bound by the rate at
+    // which one SM accepts cp.async.bulk requests (~100 ns each, ~10 per window), not by bytes.
+    if (!pre_d && !post_d && a == 1.0 && W <= 4 && g_tune_fixed >= 100) {
+      const int var = g_tune_fixed - 100;
+      const int ng = var / 10, rpt = var % 10;
+      FStageBufs& fs = m->fstage[f->R];
+      if (fs.state == 1 && fs.win != 256 * rpt) fs.release();
+      if (fs.state == 0) DDF_CHECK(fstage_build(f->ctx, m->bnd_table(f->R), W, f->nrows, 256 * rpt, fs));
+      if (fs.state == 1) {
+        int rc = W == 2 ? launch_fixed_pipe<2>(f->ctx, fs, ng, f->nrows, (f->R & 1), x, y)
+                 : W == 3 ? launch_fixed_pipe<3>(f->ctx, fs, ng, f->nrows, (f->R & 1), x, y)
+                          : launch_fixed_pipe<4>(f->ctx, fs, ng, f->nrows, (f->R & 1), x, y);
+        if (rc == 0) return 0;
+        if (rc > 0) return rc;
+        fs.state = 2;                    // does not fit the shared-memory ring
+      }
+    }
     return launch_fixed(f->ctx, m->bnd_table(f->R), W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
   }
   // boundary / dual derivative: SELL-32 copy of the row-CSR when its padding is small, else CSR

@@ -261,6 +261,17 @@ __device__ __forceinline__ void stage_issue(const uint32_t* __restrict__ wtab, c
   }
 }
 
+#define PIPE_TD 8               // depth of the run-table ring of the persistent pipelines
+
+// one TMA bulk copy global -> shared, completion counted on `mbar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* mbar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(mbar)), "l"(policy)
+      : "memory");
+}
+
 __device__ __forceinline__ void stage_wait(uint64_t* mbar, uint32_t parity) {
   asm volatile(
       "{\n"

@@ -358,15 +358,6 @@ struct PipeGeom {
 };
 #define PIPE_GROUP 256          // threads of one consumer group (= rows of a window)
 #define PIPE_MAX_STAGES 6
-#define PIPE_TD 8               // depth of the run-table ring
-
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* mbar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(mbar)), "l"(policy)
-      : "memory");
-}
 
 template <int MODE, int NG>
 __global__ void __launch_bounds__(NG * PIPE_GROUP + 32, 1)

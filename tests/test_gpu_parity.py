@@ -137,6 +137,41 @@ def test_deriv_apply_bit_exact(ddf, pairs, kind):
         assert np.array_equal(yb, o.spmv_adjoint_csc(om.boundaries[k + 1], x))
 
 
+def test_deriv_apply_staged_pipeline(ddf, ctx):
+    """y = d_k x through the opt-in staged fixed-width TMA pipeline (csrc/fstage.cuh, tuning 100+10*NG+RPT; tables of
+    >= 4096 rows) against the oracle and against the default explicit-index kernel -- bit for bit, including a
+    ragged last window."""
+    n = 20
+    om = o.large_hypercube_manifold(3, (n, n, n))
+    dm = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
+    rng = np.random.default_rng(23)
+    for k in range(3):
+        x = rng.standard_normal(om.nsimplices(k))
+        fx = ddf.Fun(dm, ddf.Pr, k, x)
+        y = (ddf.deriv(ddf.Pr, k, dm) * fx).values
+        assert np.array_equal(y, o.apply_deriv(o.Pr, k, om, x)), k
+        for var in (114, 122, 111):
+            ddf._lib.call("ddf_set_tuning", b"fixed", var)
+            try:
+                y2 = (ddf.deriv(ddf.Pr, k, dm) * fx).values
+            finally:
+                ddf._lib.call("ddf_set_tuning", b"fixed", 0)
+            assert np.array_equal(y, y2), (k, var)
+    # a mesh without column locality: the staged build must refuse it and the explicit-index kernel takes over
+    ddf._lib.call("ddf_set_tuning", b"fixed", 114)
+    simp, coords, weights = o.large_hypercube_tables(3, (12, 12, 12))
+    perm = rng.permutation(coords.shape[0])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    om2 = o.build_manifold("shuffled", inv[simp], coords[perm], weights[perm])
+    dm2 = ddf.Manifold.from_simplices("shuffled", inv[simp], coords[perm], weights[perm], ctx=ctx)
+    for k in range(3):
+        x = rng.standard_normal(om2.nsimplices(k))
+        y = (ddf.deriv(ddf.Pr, k, dm2) * ddf.Fun(dm2, ddf.Pr, k, x)).values
+        assert np.array_equal(y, o.apply_deriv(o.Pr, k, om2, x)), k
+    ddf._lib.call("ddf_set_tuning", b"fixed", 0)
+
+
 def test_deriv_apply_ragged_sizes(ddf, ctx):
     """rows % 4 != 0 exercises the scalar tail of the 4-rows-per-thread kernel."""
     for n in (2, 6, 10):
