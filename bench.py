@@ -242,7 +242,8 @@ def run_b200(args):
     if N == 1:
         mfd = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx, assemble=False)
     else:
-        mfd, slab = ddf.dist.slab_hypercube(3, (n, n, n * N), ctx, assemble=False)
+        # weak scaling: one n^3 cube per GPU stacked along z; --strong: ONE n^3 cube cut into N slabs
+        mfd, slab = ddf.dist.slab_hypercube(3, (n, n, n if args.strong else n * N), ctx, assemble=False)
     ctx.sync()
     ctx.tic()
     ddf._lib.call("ddf_mesh_assemble", mfd._h)
@@ -393,10 +394,13 @@ def run_b200(args):
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": K, "warmup": W,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.strong and N > 1 else "weak",
+            "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"BASELINE config 4: 3D Kuhn large_hypercube n={n}"
-                                   + (f" per GPU, z-slabs of {n * N} layers over {N} GPUs (config 5 weak scaling)" if N > 1 else "")
+                                   + ((f", ONE cube cut into {N} z-slabs (config 5 strong scaling)" if args.strong else
+                                       f" per GPU, z-slabs of {n * N} layers over {N} GPUs (config 5 weak scaling)")
+                                      if N > 1 else "")
                                    + ": y=d_k x (k=0,1,2) and star_k x (k=0..3), Float64",
                        "nsimplices_local": cnt, "dof_per_step": int(dof_total),
                        "l2_hygiene": "inputs larger than L2 (index tables 0.9-2.4 GB, vectors 0.14-1.6 GB vs 126 MB L2)",
@@ -432,11 +436,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="cells per axis (per GPU along z)")
+    ap.add_argument("--n", "--cells", dest="n", type=int, default=256,
+                    help="cells per axis (per GPU along z); use --cells under torchrun (its parser rejects --n)")
     ap.add_argument("--n-ref", type=int, default=64, help="cells per axis of the CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="N > 1: cut ONE n^3 cube into N slabs (default: weak scaling)")
     ap.add_argument("--wave-tune", type=int, default=0, help="ddf_set_tuning('wave', x) for A/B runs (1024: NCCL halo)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -7,7 +7,8 @@
 // form a few contiguous runs (9 on the 3D Kuhn mesh: the x-rows (dy,dz) around the window).
 // This format stores, per 256-row window,
 //   * a run table  {nruns, nslots, first entry, entries, (start_col_k, slot_off_k)...}  -- runs start on even
-//     columns and have even length, so each is one 16-byte-aligned TMA bulk copy
+//     columns, have even length and absorb gaps of <= STAGE_GAP untouched columns, so each is one
+//     16-byte-aligned TMA bulk copy
 //     (cp.async.bulk global -> shared, completion on an mbarrier) of u into a staging buffer;
 //   * per stored entry a 16-bit slot into that buffer + the 8-byte value: 10 B instead of 12 B;
 //   * rows sorted by decreasing length inside the window (perm8, len8 in sorted order) and
@@ -18,7 +19,7 @@
 // The order of the entries inside a row is unchanged: sums are bit-identical to the CSR form.
 //
 // Windows whose columns do not fit (more than STAGE_RMAX runs, more than STAGE_MAX_SLOTS
-// slots, column span >= 2^18, a row longer than 255) make the whole build report
+// slots, more than STAGE_KEYS entries, a row longer than 255) make the whole build report
 // "unstageable"; the caller then keeps the explicit-index SELL kernel.
 #pragma once
 #include <cub/cub.cuh>
@@ -27,8 +28,8 @@
 
 #define STAGE_RMAX 30                    // runs per window
 #define STAGE_TAB (4 + 2 * STAGE_RMAX)    // table words per window (256 B: one 16-byte-aligned bulk copy)
-#define STAGE_BITS (1 << 18)             // bitmap span in columns
-#define STAGE_WORDS (STAGE_BITS / 32)
+#define STAGE_KEYS 8192                  // most entries of a 256-row window the builder sorts
+#define STAGE_GAP 7u                     // untouched columns a run may absorb
 #define STAGE_MAX_SLOTS 6080             // 47.5 KB of staged Float64 per block (static shared-memory limit)
 
 // ---- pass A: sort the rows of a window by decreasing length (stable), slice entry totals
@@ -68,103 +69,83 @@ k_stage_sort(const uint32_t* __restrict__ rowptr, int64_t nrows, uint8_t* __rest
   }
 }
 
-// ---- pass B: per window: bitmap of touched columns -> runs, slots; entries into jagged slices
-// dynamic shared memory: STAGE_WORDS bitmap words + STAGE_WORDS 16-bit slot prefixes
+// ---- pass B: per window: sort the touched columns -> runs, slots; entries into jagged slices
+// dynamic shared memory: STAGE_KEYS sorted column indices
 static __global__ void __launch_bounds__(DDF_SELL_WIN)
 k_stage_fill(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
              int64_t nrows, const uint8_t* __restrict__ perm8, const uint8_t* __restrict__ len8,
              const uint32_t* __restrict__ slice_ptr, uint32_t* __restrict__ tab, uint16_t* __restrict__ slot,
              double* __restrict__ sval, uint32_t* __restrict__ status /* [0] = max slots or ~0 */) {
-  extern __shared__ uint32_t sm_dyn[];
-  uint32_t* bm = sm_dyn;                                               // STAGE_WORDS
-  uint16_t* pre = reinterpret_cast<uint16_t*>(sm_dyn + STAGE_WORDS);   // STAGE_WORDS slot prefixes
-  __shared__ uint32_t s_min, s_max, s_bad;
-  __shared__ uint32_t s_runs[DDF_SELL_WIN], s_slots[DDF_SELL_WIN];     // per-thread counts -> exclusive prefixes
+  extern __shared__ uint32_t keys[];                                   // STAGE_KEYS
+  __shared__ uint32_t rstart[STAGE_RMAX + 1], roff[STAGE_RMAX + 1];
+  __shared__ uint32_t s_nruns, s_bad;
   const int t = threadIdx.x;
   const int64_t wbase = (int64_t)blockIdx.x * DDF_SELL_WIN;
-  const int64_t row = wbase + t;
-  const uint32_t lo = row < nrows ? rowptr[row] : 0u, hi = row < nrows ? rowptr[row + 1] : 0u;
-  if (t == 0) { s_min = 0xFFFFFFFFu; s_max = 0u; s_bad = 0u; }
-  for (int w = t; w < STAGE_WORDS; w += DDF_SELL_WIN) bm[w] = 0u;
-  __syncthreads();
-  if (hi > lo) {                         // columns ascend inside a row
-    atomicMin(&s_min, (uint32_t)col[lo]);
-    atomicMax(&s_max, (uint32_t)col[hi - 1]);
-  }
-  __syncthreads();
+  const int64_t wend = min(wbase + DDF_SELL_WIN, nrows);
+  const uint32_t e_lo = rowptr[wbase], e_hi = rowptr[wend];
+  const uint32_t nent = e_hi - e_lo;
   uint32_t* wtab = tab + (int64_t)blockIdx.x * STAGE_TAB;
-  if (s_min == 0xFFFFFFFFu) {            // a window of empty rows
-    if (t == 0) { wtab[0] = 0u; wtab[1] = 0u; wtab[2] = slice_ptr[(int64_t)blockIdx.x * (DDF_SELL_WIN / 32)]; wtab[3] = 0u; }
+  const uint32_t first_entry = slice_ptr[(int64_t)blockIdx.x * (DDF_SELL_WIN / 32)];
+  const uint32_t stored = slice_ptr[(int64_t)(blockIdx.x + 1) * (DDF_SELL_WIN / 32)] - first_entry;
+  if (nent > (uint32_t)STAGE_KEYS) {
+    if (t == 0) { wtab[0] = 0u; wtab[1] = 0u; wtab[2] = first_entry; wtab[3] = stored; atomicMax(status, 0xFFFFFFFFu); }
     return;
   }
-  const uint32_t cbase = s_min & ~63u;
-  if (s_max - cbase >= (uint32_t)STAGE_BITS) {
-    if (t == 0) { wtab[0] = 0u; wtab[1] = 0u; atomicMax(status, 0xFFFFFFFFu); }
-    return;
-  }
-  for (uint32_t p = lo; p < hi; p++) {
-    const uint32_t c = (uint32_t)col[p] - cbase;
-    atomicOr(&bm[c >> 5], 1u << (c & 31u));
-  }
+  for (uint32_t e = t; e < (uint32_t)STAGE_KEYS; e += DDF_SELL_WIN) keys[e] = e < nent ? (uint32_t)col[e_lo + e] : 0xFFFFFFFFu;
   __syncthreads();
-  // pairs: even start, even length (16-byte TMA granularity).  Each thread owns 32 consecutive words.
-  uint32_t nslots = 0, nruns = 0;
-  constexpr int WPT = STAGE_WORDS / DDF_SELL_WIN;
-  for (int k = 0; k < WPT; k++) {
-    const int w = t * WPT + k;
-    uint32_t b = bm[w];
-    b |= ((b | (b >> 1)) & 0x55555555u) * 3u;
-    bm[w] = b;
-    nslots += __popc(b);
-  }
-  __syncthreads();
-  for (int k = 0; k < WPT; k++) {
-    const int w = t * WPT + k;
-    const uint32_t b = bm[w];
-    const uint32_t prev = w > 0 ? bm[w - 1] >> 31 : 0u;
-    nruns += __popc(b & ~((b << 1) | prev));
-  }
-  // block exclusive scan of (runs, slots)
-  s_runs[t] = nruns;
-  s_slots[t] = nslots;
-  __syncthreads();
-  if (t == 0) {
-    uint32_t ar = 0, as = 0;
-    for (int k = 0; k < DDF_SELL_WIN; k++) {
-      const uint32_t r = s_runs[k], s = s_slots[k];
-      s_runs[k] = ar;
-      s_slots[k] = as;
-      ar += r;
-      as += s;
+  for (int k = 2; k <= STAGE_KEYS; k <<= 1) {                           // bitonic sort
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < STAGE_KEYS; i += DDF_SELL_WIN) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t a = keys[i], b = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
     }
-    wtab[0] = ar;
-    wtab[1] = as;
-    wtab[2] = slice_ptr[(int64_t)blockIdx.x * (DDF_SELL_WIN / 32)];                  // the window's entry range
-    wtab[3] = slice_ptr[(int64_t)(blockIdx.x + 1) * (DDF_SELL_WIN / 32)] - wtab[2];
-    if (ar > (uint32_t)STAGE_RMAX || as > (uint32_t)STAGE_MAX_SLOTS) { s_bad = 1u; atomicMax(status, 0xFFFFFFFFu); }
-    else atomicMax(status, as);
+  }
+  if (t == 0) {
+    // maximal runs of touched columns; runs start on even columns and have even length (16-byte TMA
+    // granularity) and absorb gaps of up to STAGE_GAP untouched columns
+    uint32_t nruns = 0, total = 0, cur_start = 0, cur_end = 0;
+    bool open = false;
+    for (uint32_t e = 0; e < nent; e++) {
+      const uint32_t c = keys[e];
+      if (open && c <= cur_end + STAGE_GAP) {
+        const uint32_t ne = (c + 2u) & ~1u;
+        if (ne > cur_end) cur_end = ne;
+      } else {
+        if (open) {
+          if (nruns < STAGE_RMAX) { rstart[nruns] = cur_start; roff[nruns] = total; }
+          total += cur_end - cur_start;
+          nruns++;
+        }
+        cur_start = c & ~1u;
+        cur_end = (c + 2u) & ~1u;
+        open = true;
+      }
+    }
+    if (open) {
+      if (nruns < STAGE_RMAX) { rstart[nruns] = cur_start; roff[nruns] = total; }
+      total += cur_end - cur_start;
+      nruns++;
+    }
+    const bool bad = nruns > (uint32_t)STAGE_RMAX || total > (uint32_t)STAGE_MAX_SLOTS;
+    s_nruns = nruns;
+    s_bad = bad ? 1u : 0u;
+    wtab[0] = bad ? 0u : nruns;
+    wtab[1] = bad ? 0u : total;
+    wtab[2] = first_entry;                                              // the window's entry range
+    wtab[3] = stored;
+    if (!bad)
+      for (uint32_t k = 0; k < nruns; k++) { wtab[4 + 2 * k] = rstart[k]; wtab[5 + 2 * k] = roff[k]; }
+    atomicMax(status, bad ? 0xFFFFFFFFu : total);
   }
   __syncthreads();
   if (s_bad) return;
-  {
-    uint32_t r = s_runs[t], s = s_slots[t];
-    for (int k = 0; k < WPT; k++) {
-      const int w = t * WPT + k;
-      const uint32_t b = bm[w];
-      const uint32_t prev = w > 0 ? bm[w - 1] >> 31 : 0u;
-      pre[w] = (uint16_t)s;
-      uint32_t starts = b & ~((b << 1) | prev);
-      while (starts) {
-        const int bit = __ffs(starts) - 1;
-        starts &= starts - 1;
-        wtab[4 + 2 * r] = cbase + 32u * (uint32_t)w + (uint32_t)bit;
-        wtab[5 + 2 * r] = s + __popc(b & ((1u << bit) - 1u));
-        r++;
-      }
-      s += __popc(b);
-    }
-  }
-  __syncthreads();
+  const uint32_t nruns = s_nruns;
   // entries -> jagged slices (same addressing as the row kernels)
   const int64_t r = wbase + t;                       // sorted position
   const int64_t i = wbase + perm8[r];
@@ -177,8 +158,13 @@ k_stage_fill(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     const bool act = q < mylen;
     const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, act));
     if (act) {
-      const uint32_t c = (uint32_t)col[rlo + q] - cbase;
-      slot[(size_t)off + lane] = (uint16_t)(pre[c >> 5] + __popc(bm[c >> 5] & ((1u << (c & 31u)) - 1u)));
+      const uint32_t c = (uint32_t)col[rlo + q];
+      uint32_t lo = 0, hi = nruns;                   // last run with start <= c
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (rstart[mid] <= c) lo = mid; else hi = mid;
+      }
+      slot[(size_t)off + lane] = (uint16_t)(roff[lo] + (c - rstart[lo]));
       sval[(size_t)off + lane] = val[rlo + q];
     }
     off += cnt;
@@ -220,12 +206,7 @@ static int stage_build(ddf_ctx* ctx, const uint32_t* rowptr, const int32_t* col,
   // padding entries are never read by a row, but they travel in the bulk copies: keep them defined
   DDF_CUDA(cudaMemsetAsync(out.slot.p, 0, ((size_t)total + 8) * 2, ctx->stream));
   DDF_CUDA(cudaMemsetAsync(out.val.p, 0, ((size_t)total + 8) * 8, ctx->stream));
-  const size_t smem = STAGE_WORDS * 4 + STAGE_WORDS * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DDF_CUDA(cudaFuncSetAttribute(k_stage_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  const size_t smem = STAGE_KEYS * 4;
   k_stage_fill<<<(int)nwin, DDF_SELL_WIN, smem, ctx->stream>>>(rowptr, col, val, nrows, out.perm8.p, out.len8.p, out.ptr.p,
                                                               out.tab.p, out.slot.p, out.val.p, status.p);
   DDF_LAUNCH_CHECK(ctx);

@@ -457,7 +457,7 @@ def test_wave_row_formats_agree(ddf, ctx):
     slices; default), explicit-index SELL-32-256 (tuning 16) and CSR thread-per-row (tuning 16|1) -- give
     the same bits as the oracle, also on a mesh with shuffled vertex numbers (no column locality: the
     staged build must refuse it and fall back)."""
-    n = 12
+    n = 20        # 9261 vertices: a window of the shuffled mesh touches more columns than a staging buffer holds
     simp, coords, weights = o.large_hypercube_tables(3, (n, n, n))
     rng = np.random.default_rng(21)
     perm = rng.permutation(coords.shape[0])
@@ -523,6 +523,26 @@ def test_wave_tsit5_converges_to_exact_solution(ddf, ctx):
         e, _ = ddf.wave(2, lv, ctx=ctx, t1=0.5, integrator="tsit5")
         errs.append(e)
     assert errs[1] < errs[0] / 2.5 and errs[2] < errs[1] / 2.5, errs
+
+
+def test_wave_staged_wide_planes(ddf, ctx):
+    """A slab with 513 x 513 vertex planes (the cross-section of BASELINE config 5's n=512 cube): a window's
+    columns span 2 planes = 526k vertex ids.  The staged build must accept it (no span limit) and agree bit for bit
+    with the explicit-index SELL kernel."""
+    res = {}
+    for tune in (0, 16):
+        ddf._lib.call("ddf_set_tuning", b"wave", tune)
+        try:
+            m = ddf.large_hypercube_manifold(3, (512, 512, 4), ctx=ctx, hdiv=512)
+            u, v = ddf.sample(m, "wave"), ddf.Fun(m, ddf.Pr, 0)
+            ddf.wave_leapfrog(m, u, v, ddf.wave_dt(m), 3)
+            res[tune] = (ddf.wave_format(m), u.values, v.values)
+            m.close()
+        finally:
+            ddf._lib.call("ddf_set_tuning", b"wave", 0)
+    assert res[0][0] == "staged" and res[16][0] == "sell"
+    assert np.array_equal(res[0][1], res[16][1]) and np.array_equal(res[0][2], res[16][2])
+    assert np.abs(res[0][1]).max() > 0.01
 
 
 def test_wave_sample_and_convergence(ddf, ctx):
