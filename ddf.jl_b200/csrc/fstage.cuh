@@ -271,3 +271,94 @@ static int launch_fixed_pipe(ddf_ctx* ctx, const FStageBufs& fs, int ng, int64_t
   if (ng == 2 && rpt == 2) return launch_fixed_pipe_v<W, 2, 2>(ctx, fs, nrows, first_negative, x, y);
   return launch_fixed_pipe_v<W, 2, 4>(ctx, fs, nrows, first_negative, x, y);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Tiled variant (no TMA): one block per window of 256*RPT rows.  All 256 threads copy the window's
+// runs of x into shared memory with coalesced 16-byte loads (every run starts on an even column), their
+// slot words are already in flight, then each thread gathers its RPT rows from shared memory.
+// Unlike the pipeline above the loads are issued by 256 threads, not by one producer warp, so the
+// per-request cost of cp.async.bulk does not apply; latency is hidden by 4-5 resident blocks per SM.
+__device__ __forceinline__ double2 ld_keep_f64x2(const double2* p, uint64_t pol) {
+  double2 r;
+  asm("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+  return r;
+}
+
+template <int W, int RPT>
+__global__ void __launch_bounds__(256)
+k_fixed_tiled(const uint32_t* __restrict__ tab, const uint16_t* __restrict__ slot, const double* __restrict__ x,
+              double* __restrict__ y, int first_negative, int64_t nrows) {
+  extern __shared__ __align__(16) double tile[];
+  __shared__ uint32_t wt[STAGE_TAB];
+  constexpr int WIN = 256 * RPT;
+  const uint32_t tid = threadIdx.x;
+  const int64_t win = blockIdx.x;
+  const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
+  if (tid < STAGE_TAB) wt[tid] = (uint32_t)ld_stream_int(reinterpret_cast<const int*>(tab) + win * STAGE_TAB + tid);
+  // this thread's slot words (rows tid, tid+256, ...), requested before the tile is filled
+  uint32_t sl[RPT][W];
+  const uint16_t* ws = slot + win * (int64_t)(WIN * W);
+#pragma unroll
+  for (int q = 0; q < RPT; q++) {
+    const uint32_t r = tid + 256u * q;
+    if (W == 4) {
+      const int2 v = ld_stream_int2(reinterpret_cast<const int2*>(ws + 4 * r));
+      sl[q][0] = (uint32_t)v.x & 0xffffu; sl[q][1] = (uint32_t)v.x >> 16;
+      sl[q][2] = (uint32_t)v.y & 0xffffu; sl[q][W - 1] = (uint32_t)v.y >> 16;
+    } else if (W == 2) {
+      const uint32_t v = (uint32_t)ld_stream_int(reinterpret_cast<const int*>(ws + 2 * r));
+      sl[q][0] = v & 0xffffu; sl[q][1] = v >> 16;
+    } else {
+#pragma unroll
+      for (int p = 0; p < W; p++) sl[q][p] = __ldg(ws + W * r + p);
+    }
+  }
+  __syncthreads();
+  const uint32_t nruns = wt[0], total = wt[1];
+  for (uint32_t k = 0; k < nruns; k++) {
+    const uint32_t start = wt[4 + 2 * k], off = wt[5 + 2 * k];
+    const uint32_t len = (k + 1 < nruns ? wt[5 + 2 * (k + 1)] : total) - off;
+    for (uint32_t i = 2 * tid; i < len; i += 512)      // asynchronous 16-byte copies: no register waits on the load
+      asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(tile + off + i)),
+                   "l"(x + start + i), "l"(pol_keep)
+                   : "memory");
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  const int64_t r0 = win * WIN;
+#pragma unroll
+  for (int q = 0; q < RPT; q++) {
+    const uint32_t r = tid + 256u * q;
+    double a = 0.0;                                   // tmp = zero(eltype(C))
+#pragma unroll
+    for (int p = 0; p < W; p++) {
+      const double v = tile[sl[q][p]];
+      const bool neg = ((p & 1) != 0) != (first_negative != 0);
+      a = neg ? __dsub_rn(a, v) : __dadd_rn(a, v);
+    }
+    if (r0 + r < nrows) st_hint_f64(y + r0 + r, a, pol_stream);
+  }
+}
+
+template <int W, int RPT>
+static int launch_fixed_tiled_v(ddf_ctx* ctx, const FStageBufs& fs, int64_t nrows, int first_negative, const double* x,
+                                double* y) {
+  const size_t smem = ((size_t)fs.max_slots * 8 + 15) & ~(size_t)15;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && attr < smem) {
+    DDF_CUDA(cudaFuncSetAttribute(k_fixed_tiled<W, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  if (fs.nwin > 0x7fffffffLL) DDF_FAIL("grid too large");
+  k_fixed_tiled<W, RPT><<<(int)fs.nwin, 256, smem, ctx->stream>>>(fs.tab.p, fs.slot.p, x, y, first_negative, nrows);
+  DDF_LAUNCH_CHECK(ctx);
+  return 0;
+}
+template <int W>
+static int launch_fixed_tiled(ddf_ctx* ctx, const FStageBufs& fs, int64_t nrows, int first_negative, const double* x,
+                              double* y) {
+  const int rpt = fs.win / 256;
+  if (rpt == 1) return launch_fixed_tiled_v<W, 1>(ctx, fs, nrows, first_negative, x, y);
+  if (rpt == 2) return launch_fixed_tiled_v<W, 2>(ctx, fs, nrows, first_negative, x, y);
+  return launch_fixed_tiled_v<W, 4>(ctx, fs, nrows, first_negative, x, y);
+}

@@ -987,11 +987,17 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
     // (profiles/r01_tuning.md) they lose to the explicit-index kernel -- the pipeline is bound by the rate at
     // which one SM accepts cp.async.bulk requests (~100 ns each, ~10 per window), not by bytes.
     if (!pre_d && !post_d && a == 1.0 && W <= 4 && g_tune_fixed >= 100) {
-      const int var = g_tune_fixed - 100;
+      const bool tiled = g_tune_fixed >= 200;            // 200 + RPT: tiled variant (no TMA)
+      const int var = tiled ? 10 + (g_tune_fixed - 200) : g_tune_fixed - 100;
       const int ng = var / 10, rpt = var % 10;
       FStageBufs& fs = m->fstage[f->R];
       if (fs.state == 1 && fs.win != 256 * rpt) fs.release();
       if (fs.state == 0) DDF_CHECK(fstage_build(f->ctx, m->bnd_table(f->R), W, f->nrows, 256 * rpt, fs));
+      if (fs.state == 1 && tiled) {
+        return W == 2 ? launch_fixed_tiled<2>(f->ctx, fs, f->nrows, (f->R & 1), x, y)
+               : W == 3 ? launch_fixed_tiled<3>(f->ctx, fs, f->nrows, (f->R & 1), x, y)
+                        : launch_fixed_tiled<4>(f->ctx, fs, f->nrows, (f->R & 1), x, y);
+      }
       if (fs.state == 1) {
         int rc = W == 2 ? launch_fixed_pipe<2>(f->ctx, fs, ng, f->nrows, (f->R & 1), x, y)
                  : W == 3 ? launch_fixed_pipe<3>(f->ctx, fs, ng, f->nrows, (f->R & 1), x, y)

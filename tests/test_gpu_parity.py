@@ -152,7 +152,7 @@ def test_deriv_apply_staged_pipeline(ddf, ctx):
         fx = ddf.Fun(dm, ddf.Pr, k, x)
         y = (ddf.deriv(ddf.Pr, k, dm) * fx).values
         assert np.array_equal(y, o.apply_deriv(o.Pr, k, om, x)), k
-        for var in (114, 122, 111):
+        for var in (114, 122, 111, 204, 202, 201):
             ddf._lib.call("ddf_set_tuning", b"fixed", var)
             try:
                 y2 = (ddf.deriv(ddf.Pr, k, dm) * fx).values
