@@ -387,7 +387,7 @@ def run_b200(args):
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
                 tj = json.load(f)
             if tj.get("n") == n:
-                e = tj["k_apply_fixed<3>"]
+                e = tj["k_apply_fixed_rows<3,4>"]
                 traffic = e["traffic_bytes"] * d1_bytes / e["algorithmic_bytes"]
                 traffic_src = tj["source"]
         except (OSError, KeyError, ValueError):
@@ -406,7 +406,7 @@ def run_b200(args):
                        "l2_hygiene": "inputs larger than L2 (index tables 0.9-2.4 GB, vectors 0.14-1.6 GB vs 126 MB L2)",
                        "parallelism": "none" if N == 1 else f"z-slabs x{N}, no collective in d_k/star_k apply; "
                                                             "NCCL send/recv halo in the wave step"},
-            "roofline": {"bound": "hbm", "kernel": "k_apply_fixed<3> (y = d1 x)", "achieved": d1_bytes / d1_ms * 1e-6,
+            "roofline": {"bound": "hbm", "kernel": "k_apply_fixed_rows<3,4> (y = d1 x)", "achieved": d1_bytes / d1_ms * 1e-6,
                          "peak": peak, "unit": "GB/s", "frac": d1_bytes / d1_ms * 1e-6 / peak, "traffic": traffic,
                          "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(d1_bytes),

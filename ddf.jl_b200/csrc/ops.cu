@@ -104,8 +104,10 @@ k_apply_fixed(const int32_t* __restrict__ tab, int64_t nrows, int first_negative
       idx[4 * q + 0] = v.x; idx[4 * q + 1] = v.y; idx[4 * q + 2] = v.z; idx[4 * q + 3] = v.w;
     }
     double xv[4 * W];
+    // evict_last on the gathered x pays for W <= 3 (d1: 84 -> 97 % of the copy peak); with 16 gathers per thread
+    // (W = 4) the plain read-only load is 2-3 % faster and moves the same DRAM bytes (profiles/r01_tuning.md)
 #pragma unroll
-    for (int q = 0; q < 4 * W; q++) xv[q] = ld_keep_f64(x + idx[q], pol_keep);
+    for (int q = 0; q < 4 * W; q++) xv[q] = W >= 4 ? __ldg(x + idx[q]) : ld_keep_f64(x + idx[q], pol_keep);
     if (PRE) {
 #pragma unroll
       for (int q = 0; q < 4 * W; q++) xv[q] = __dmul_rn(ld_keep_f64(pre + idx[q], pol_keep), xv[q]);
@@ -211,13 +213,36 @@ k_apply_sellsign(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restric
   st_hint_f64(y + i, a, pol_stream);
 }
 
-__global__ void k_apply_diag(const double* __restrict__ d, double sign_or_scale, const double* __restrict__ x,
-                             double* __restrict__ y, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// y = scale * (d .* x): pure streaming (24 B per element).  Four elements per thread as two 128-bit accesses per
+// array, read-once loads (L1 no-allocate), evict-first stores; the tail and unaligned views take the scalar path.
+__global__ void __launch_bounds__(256)
+k_apply_diag(const double* __restrict__ d, double sign_or_scale, const double* __restrict__ x, double* __restrict__ y,
+             int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
-  double v = d ? __dmul_rn(d[i], x[i]) : x[i];
-  if (sign_or_scale != 1.0) v = __dmul_rn(sign_or_scale, v);
-  y[i] = v;
+  if (i + 3 < n) {
+    const double2 x0 = ld_stream_f64x2(reinterpret_cast<const double2*>(x + i));
+    const double2 x1 = ld_stream_f64x2(reinterpret_cast<const double2*>(x + i + 2));
+    double v[4] = {x0.x, x0.y, x1.x, x1.y};
+    if (d) {
+      const double2 d0 = ld_stream_f64x2(reinterpret_cast<const double2*>(d + i));
+      const double2 d1 = ld_stream_f64x2(reinterpret_cast<const double2*>(d + i + 2));
+      v[0] = __dmul_rn(d0.x, v[0]); v[1] = __dmul_rn(d0.y, v[1]);
+      v[2] = __dmul_rn(d1.x, v[2]); v[3] = __dmul_rn(d1.y, v[3]);
+    }
+    if (sign_or_scale != 1.0) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) v[q] = __dmul_rn(sign_or_scale, v[q]);
+    }
+    st_stream_f64x2(reinterpret_cast<double2*>(y + i), v[0], v[1]);
+    st_stream_f64x2(reinterpret_cast<double2*>(y + i + 2), v[2], v[3]);
+  } else {
+    for (int64_t k = i; k < n; k++) {
+      double w = d ? __dmul_rn(d[k], x[k]) : x[k];
+      if (sign_or_scale != 1.0) w = __dmul_rn(sign_or_scale, w);
+      y[k] = w;
+    }
+  }
 }
 
 __global__ void k_apply_csrf64(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -250,13 +275,17 @@ extern "C" int ddf_set_tuning(const char* key, int value) {
 //   4: 1 + persistent blocks with the next tile's indices prefetched
 int g_tune_fixed = 0;
 
-template <int W>
+template <int W, int XM = 0>
 __device__ __forceinline__ void fixed_rows4(const int* idx, const double* __restrict__ x, uint64_t pol_keep,
                                             uint64_t pol_stream, int first_negative, double* __restrict__ y,
                                             int64_t r0) {
   double xv[4 * W];
 #pragma unroll
-  for (int q = 0; q < 4 * W; q++) xv[q] = ld_keep_f64(x + idx[q], pol_keep);
+  for (int q = 0; q < 4 * W; q++) {
+    if (XM == 0) xv[q] = ld_keep_f64(x + idx[q], pol_keep);
+    else if (XM == 1) xv[q] = __ldg(x + idx[q]);                                   // no eviction hint
+    else asm("ld.global.nc.L2::256B.f64 %0, [%1];" : "=d"(xv[q]) : "l"(x + idx[q]));   // fetch whole lines into L2
+  }
   double acc[4];
 #pragma unroll
   for (int r = 0; r < 4; r++) {
@@ -293,7 +322,7 @@ k_apply_fixed_x(const int32_t* __restrict__ tab, int64_t nrows, int first_negati
                 double* __restrict__ y) {
   const uint64_t pol_keep = make_policy_evict_last();
   const uint64_t pol_stream = make_policy_evict_first();
-  if (VAR == 1 || VAR == 2) {
+  if (VAR == 1 || VAR == 2 || VAR == 5 || VAR == 6) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r0 = t * 4;
     if (r0 >= nrows) return;
@@ -305,7 +334,7 @@ k_apply_fixed_x(const int32_t* __restrict__ tab, int64_t nrows, int first_negati
         int4 v = VAR == 1 ? ld_stream_int4_hint(tp + q, pol_stream) : ld_l1_int4_hint(tp + q, pol_stream);
         idx[4 * q + 0] = v.x; idx[4 * q + 1] = v.y; idx[4 * q + 2] = v.z; idx[4 * q + 3] = v.w;
       }
-      fixed_rows4<W>(idx, x, pol_keep, pol_stream, first_negative, y, r0);
+      fixed_rows4<W, VAR == 5 ? 1 : (VAR == 6 ? 2 : 0)>(idx, x, pol_keep, pol_stream, first_negative, y, r0);
     } else {
       fixed_tail<W>(tab, x, first_negative, y, r0, nrows);
     }
@@ -360,6 +389,54 @@ k_apply_fixed_x(const int32_t* __restrict__ tab, int64_t nrows, int first_negati
   }
 }
 
+// VAR 7: lane = consecutive rows.  A warp owns 32*RPW consecutive rows; in every gather instruction the 32 lanes
+// read the x entries of 32 CONSECUTIVE rows (lexicographically adjacent simplices share faces, so the lanes hit
+// few distinct sectors -> fewer L1 wavefronts per instruction than the rows-4t..4t+3-per-thread mapping).
+template <int W, int RPW>
+__global__ void __launch_bounds__(256)
+k_apply_fixed_rows(const int32_t* __restrict__ tab, int64_t nrows, int first_negative, const double* __restrict__ x,
+                   double* __restrict__ y) {
+  const uint64_t pol_keep = make_policy_evict_last();
+  const uint64_t pol_stream = make_policy_evict_first();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r0 = warp * (32 * RPW) + lane;
+  if (warp * (32 * RPW) >= nrows) return;
+  int idx[RPW][W];
+#pragma unroll
+  for (int k = 0; k < RPW; k++) {
+    const int64_t r = r0 + 32 * k;
+    if (W == 2) {                     // one 8-byte load per row, 256 B per warp
+      int2 v = make_int2(0, 0);
+      if (r < nrows) v = ld_stream_int2(reinterpret_cast<const int2*>(tab) + r);
+      idx[k][0] = v.x; idx[k][W - 1] = v.y;
+    } else if (W == 4) {              // one 16-byte load per row, 512 B per warp
+      int4 v = make_int4(0, 0, 0, 0);
+      if (r < nrows) v = ld_stream_int4_hint(reinterpret_cast<const int4*>(tab) + r, pol_stream);
+      idx[k][0] = v.x; idx[k][1] = v.y; idx[k][W - 2] = v.z; idx[k][W - 1] = v.w;
+    } else {                          // 12-byte rows: three L1-allocating loads that share their lines
+#pragma unroll
+      for (int p = 0; p < W; p++) idx[k][p] = r < nrows ? ld_keep_s32(tab + r * W + p, pol_stream) : 0;
+    }
+  }
+  double xv[RPW][W];
+#pragma unroll
+  for (int k = 0; k < RPW; k++)
+#pragma unroll
+    for (int p = 0; p < W; p++) xv[k][p] = ld_keep_f64(x + idx[k][p], pol_keep);
+#pragma unroll
+  for (int k = 0; k < RPW; k++) {
+    const int64_t r = r0 + 32 * k;
+    double a = 0.0;
+#pragma unroll
+    for (int p = 0; p < W; p++) {
+      const bool neg = ((p & 1) != 0) != (first_negative != 0);
+      a = neg ? __dsub_rn(a, xv[k][p]) : __dadd_rn(a, xv[k][p]);
+    }
+    if (r < nrows) st_hint_f64(y + r, a, pol_stream);
+  }
+}
+
 template <int W>
 static void launch_fixed_x(ddf_ctx* ctx, int var, const int32_t* tab, int64_t nrows, int first_negative,
                            const double* x, double* y) {
@@ -368,6 +445,13 @@ static void launch_fixed_x(ddf_ctx* ctx, int var, const int32_t* tab, int64_t nr
     case 1: k_apply_fixed_x<W, 1><<<grid4, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
     case 2: k_apply_fixed_x<W, 2><<<grid4, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
     case 3: k_apply_fixed_x<W, 3><<<(int)ceil_div64(nrows, 1024), 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
+    case 7: k_apply_fixed_rows<W, 4><<<grid4, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
+    case 8: k_apply_fixed_rows<W, 8><<<(int)ceil_div64(ceil_div64(nrows, 8), 256), 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
+    case 10: k_apply_fixed_rows<W, 2><<<(int)ceil_div64(ceil_div64(nrows, 2), 256), 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
+    case 11: k_apply_fixed_rows<W, 6><<<(int)ceil_div64(ceil_div64(nrows, 6), 256), 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
+    case 12: k_apply_fixed_rows<W, 3><<<(int)ceil_div64(ceil_div64(nrows, 3), 256), 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
+    case 5: k_apply_fixed_x<W, 5><<<grid4, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
+    case 6: k_apply_fixed_x<W, 6><<<grid4, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y); break;
     default: {
       int g = ctx->sm_count * 8;
       if (g > grid4) g = grid4;
@@ -382,10 +466,18 @@ static int launch_fixed(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, 
   if (nrows == 0) return 0;
   int grid;
   DDF_CHECK(grid_for(ceil_div64(nrows, 4), 256, &grid));
-  if (g_tune_fixed > 0 && g_tune_fixed < 9 && !pre && !post && alpha == 1.0 && W >= 2 && W <= 4) {
+  if (g_tune_fixed > 0 && g_tune_fixed < 16 && g_tune_fixed != 9 && !pre && !post && alpha == 1.0 && W >= 2 && W <= 4) {
     if (W == 2) launch_fixed_x<2>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
     else if (W == 3) launch_fixed_x<3>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
     else launch_fixed_x<4>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
+    DDF_LAUNCH_CHECK(ctx);
+    return 0;
+  }
+  // default for the plain d_1 / d_2 apply: lane = consecutive rows (k_apply_fixed_rows).  Measured at C4
+  // (profiles/r01_tuning.md): d1 0.786 -> 0.733 ms, d2 0.769 -> 0.564 ms; d0 (W = 2) is faster with 4 rows per thread.
+  if (g_tune_fixed == 0 && !pre && !post && alpha == 1.0 && (W == 3 || W == 4)) {
+    if (W == 3) k_apply_fixed_rows<3, 4><<<grid, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y);
+    else k_apply_fixed_rows<4, 3><<<(int)ceil_div64(ceil_div64(nrows, 3), 256), 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y);
     DDF_LAUNCH_CHECK(ctx);
     return 0;
   }
@@ -425,7 +517,7 @@ static int launch_csrsign(ddf_ctx* ctx, const uint32_t* rowptr, const uint32_t* 
 static int launch_diag(ddf_ctx* ctx, const double* d, double s, const double* x, double* y, int64_t n) {
   if (n == 0) return 0;
   int grid;
-  DDF_CHECK(grid_for(n, 256, &grid));
+  DDF_CHECK(grid_for(ceil_div64(n, 4), 256, &grid));
   k_apply_diag<<<grid, 256, 0, ctx->stream>>>(d, s, x, y, n);
   DDF_LAUNCH_CHECK(ctx);
   return 0;
