@@ -392,10 +392,11 @@ k_apply_fixed_x(const int32_t* __restrict__ tab, int64_t nrows, int first_negati
 // VAR 7: lane = consecutive rows.  A warp owns 32*RPW consecutive rows; in every gather instruction the 32 lanes
 // read the x entries of 32 CONSECUTIVE rows (lexicographically adjacent simplices share faces, so the lanes hit
 // few distinct sectors -> fewer L1 wavefronts per instruction than the rows-4t..4t+3-per-thread mapping).
-template <int W, int RPW>
+template <int W, int RPW, bool PRE = false, bool POST = false>
 __global__ void __launch_bounds__(256)
 k_apply_fixed_rows(const int32_t* __restrict__ tab, int64_t nrows, int first_negative, const double* __restrict__ x,
-                   double* __restrict__ y) {
+                   double* __restrict__ y, const double* __restrict__ pre = nullptr,
+                   const double* __restrict__ post = nullptr, double alpha = 1.0) {
   const uint64_t pol_keep = make_policy_evict_last();
   const uint64_t pol_stream = make_policy_evict_first();
   const int lane = threadIdx.x & 31;
@@ -424,6 +425,12 @@ k_apply_fixed_rows(const int32_t* __restrict__ tab, int64_t nrows, int first_neg
   for (int k = 0; k < RPW; k++)
 #pragma unroll
     for (int p = 0; p < W; p++) xv[k][p] = ld_keep_f64(x + idx[k][p], pol_keep);
+  if (PRE) {                          // fused diagonal on the input side: fl(pre[c] * x[c]) like the unfused sequence
+#pragma unroll
+    for (int k = 0; k < RPW; k++)
+#pragma unroll
+      for (int p = 0; p < W; p++) xv[k][p] = __dmul_rn(ld_keep_f64(pre + idx[k][p], pol_keep), xv[k][p]);
+  }
 #pragma unroll
   for (int k = 0; k < RPW; k++) {
     const int64_t r = r0 + 32 * k;
@@ -433,7 +440,11 @@ k_apply_fixed_rows(const int32_t* __restrict__ tab, int64_t nrows, int first_neg
       const bool neg = ((p & 1) != 0) != (first_negative != 0);
       a = neg ? __dsub_rn(a, xv[k][p]) : __dadd_rn(a, xv[k][p]);
     }
-    if (r < nrows) st_hint_f64(y + r, a, pol_stream);
+    if (r < nrows) {
+      if (POST) a = __dmul_rn(ld_stream_f64(post + r), a);
+      if (alpha != 1.0) a = __dmul_rn(alpha, a);
+      st_hint_f64(y + r, a, pol_stream);
+    }
   }
 }
 
@@ -475,9 +486,18 @@ static int launch_fixed(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, 
   }
   // default for the plain d_1 / d_2 apply: lane = consecutive rows (k_apply_fixed_rows).  Measured at C4
   // (profiles/r01_tuning.md): d1 0.786 -> 0.733 ms, d2 0.769 -> 0.564 ms; d0 (W = 2) is faster with 4 rows per thread.
-  if (g_tune_fixed == 0 && !pre && !post && alpha == 1.0 && (W == 3 || W == 4)) {
-    if (W == 3) k_apply_fixed_rows<3, 4><<<grid, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y);
-    else k_apply_fixed_rows<4, 3><<<(int)ceil_div64(ceil_div64(nrows, 3), 256), 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y);
+  if (g_tune_fixed == 0 && (W == 3 || W == 4)) {
+    const int g3 = (int)ceil_div64(ceil_div64(nrows, 3), 256);
+#define DDF_ROWS_CASE(PRE_, POST_)                                                                                   \
+  do {                                                                                                               \
+    if (W == 3) k_apply_fixed_rows<3, 4, PRE_, POST_><<<grid, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y, pre, post, alpha); \
+    else k_apply_fixed_rows<4, 3, PRE_, POST_><<<g3, 256, 0, ctx->stream>>>(tab, nrows, first_negative, x, y, pre, post, alpha);          \
+  } while (0)
+    if (pre && post) DDF_ROWS_CASE(true, true);
+    else if (pre) DDF_ROWS_CASE(true, false);
+    else if (post) DDF_ROWS_CASE(false, true);
+    else DDF_ROWS_CASE(false, false);
+#undef DDF_ROWS_CASE
     DDF_LAUNCH_CHECK(ctx);
     return 0;
   }
