@@ -177,17 +177,21 @@ def run_reference(args):
     # warmup W passes + K timed steps, each step a bounded sample (n=64)
     import c_oracle
     c_oracle.load()
-    res = cpu_reference_pass(args.n_ref, seconds_target=min(60.0, 2.0 * max(args.steps, 1)))
-    omp = cpu_reference_pass(args.n_ref, seconds_target=5.0, threads_omp=True)
+    single = cpu_reference_pass(args.n_ref, seconds_target=min(60.0, 2.0 * max(args.steps, 1)))
+    omp = cpu_reference_pass(args.n_ref, seconds_target=min(30.0, 1.0 * max(args.steps, 1)), threads_omp=True)
+    # Julia's sparse mul! is single-threaded, so the 1-thread loop is the faithful restatement; the line reports
+    # whichever of {1 thread, row-parallel OpenMP on all host cores} is FASTER on this box, and keeps both
+    res = omp if omp["value"] > single["value"] else single
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D Kuhn large_hypercube n={args.n_ref} bounded sample of config 4 "
-                                   "(d0,d1,d2 + star0..3 apply)", "reference_runnable": False,
+            "config": {"workload": f"BASELINE config 4 (3D Kuhn large_hypercube: d0,d1,d2 + star0..3 apply, Float64), "
+                                   f"bounded sample n={args.n_ref}", "reference_runnable": False,
                        "note": "DDF.jl is Julia; no julia binary in the image -> C restatement of its SparseArrays "
-                               "mul! loops on the reference's storage, 1 thread like Julia's sparse mul!"},
+                               "mul! loops on the reference's storage (Int64 CSC, Int8 values)"},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "omp_allcores_crosscheck": {"value": omp["value"], "cores": omp["cores"]},
+            "single_thread": {"value": single["value"], "cores": 1},
+            "omp_allcores": {"value": omp["value"], "cores": omp["cores"]},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print_json(line)
 

@@ -139,7 +139,9 @@ k_fixed_pipe(const uint32_t* __restrict__ tab, const uint16_t* __restrict__ slot
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   __shared__ __align__(8) uint64_t full[8], empty[8], tfull[PIPE_TD];
   __shared__ __align__(16) uint32_t tabS[PIPE_TD * STAGE_TAB];
+  __shared__ uint32_t issued[8];       // see k_rows_pipe: guards the parity wait of consumer groups that share the ring
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid < 8) issued[tid] = 0u;
   if (tid == 0) {
     for (int d = 0; d < PIPE_TD; d++)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tfull[d])) : "memory");
@@ -183,8 +185,10 @@ k_fixed_pipe(const uint32_t* __restrict__ tab, const uint16_t* __restrict__ slot
       const uint32_t j = (uint32_t)(it / g.nstages);
       if (j > 0) stage_wait(&empty[s], (j - 1) & 1u);
       unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
-      if (lane == 0)
+      if (lane == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(total * 8u + SLOT_BYTES) : "memory");
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&issued[s])), "r"((uint32_t)it + 1u) : "memory");
+      }
       __syncwarp();
       if (lane < nruns) bulk_g2s(sb + (size_t)off * 8, x + start, (end - off) * 8u, &full[s], pol_keep);
       if (lane == 31) bulk_g2s(sb + g.o_slot, slot + win * (WIN * W), SLOT_BYTES, &full[s], pol_stream);
@@ -197,6 +201,11 @@ k_fixed_pipe(const uint32_t* __restrict__ tab, const uint16_t* __restrict__ slot
     for (int64_t win = blockIdx.x + grp * stride; win < nwin; it += NG, win += NG * stride) {
       const int s = (int)(it % g.nstages);
       const uint32_t j = (uint32_t)(it / g.nstages);
+      for (;;) {                          // the producer has armed stage s for THIS iteration
+        uint32_t seen;
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&issued[s])) : "memory");
+        if (seen >= (uint32_t)it + 1u) break;
+      }
       stage_wait(&full[s], j & 1u);
       const unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
       const double* stage = reinterpret_cast<const double*>(sb);

@@ -34,15 +34,18 @@ struct StageBufs {
   DevBuf<uint8_t> perm8;    // sorted position -> row offset inside its 256-row window
   DevBuf<uint8_t> len8;     // row length by sorted position
   DevBuf<uint32_t> tab;     // per window: nruns, nslots, (start_col, slot_off) per run
-  DevBuf<uint16_t> slot;    // per entry: slot of its column in the staging buffer
-  DevBuf<double> val;
+  // per window ONE contiguous record: [values f64 x nent][slots u16 x nent], nent = the window's stored entries
+  // (a multiple of 8), at byte offset 10 * (first entry): one TMA bulk copy per window
+  DevBuf<unsigned char> packed;
+  // per window 800 B: {u32 nent, pad to 16} | perm8[256] | len8[256] | boundary mask by row offset [256] | pad
+  DevBuf<unsigned char> meta;
   uint32_t max_slots = 0;   // largest staging buffer of any window (Float64 elements)
   uint32_t max_entries = 0; // most stored entries of any window (incl. its <= 7 padding entries)
   int64_t entries = 0;      // stored entries incl. the per-window padding
   int64_t nnz = 0;
   bool ok = false;
   void release() {
-    ptr.release(); perm8.release(); len8.release(); tab.release(); slot.release(); val.release();
+    ptr.release(); perm8.release(); len8.release(); tab.release(); packed.release(); meta.release();
     max_slots = 0; max_entries = 0; entries = 0; nnz = 0; ok = false;
   }
 };

@@ -10,7 +10,8 @@
 //     columns, have even length and absorb gaps of <= STAGE_GAP untouched columns, so each is one
 //     16-byte-aligned TMA bulk copy
 //     (cp.async.bulk global -> shared, completion on an mbarrier) of u into a staging buffer;
-//   * per stored entry a 16-bit slot into that buffer + the 8-byte value: 10 B instead of 12 B;
+//   * per stored entry a 16-bit slot into that buffer + the 8-byte value: 10 B instead of 12 B, packed per
+//     window as one record [values][slots] (one bulk copy), plus an 800-byte meta record (perm, len, mask);
 //   * rows sorted by decreasing length inside the window (perm8, len8 in sorted order) and
 //     every slice of 32 sorted rows stored as jagged diagonals: "column" q holds the entries
 //     of the cnt_q = #{rows with len > q} leading lanes, packed -- no padding at all.
@@ -30,6 +31,7 @@
 #define STAGE_TAB (4 + 2 * STAGE_RMAX)    // table words per window (256 B: one 16-byte-aligned bulk copy)
 #define STAGE_KEYS 8192                  // most entries of a 256-row window the builder sorts
 #define STAGE_GAP 7u                     // untouched columns a run may absorb
+#define STAGE_META 800                   // bytes of the per-window meta record
 #define STAGE_MAX_SLOTS 6080             // 47.5 KB of staged Float64 per block (static shared-memory limit)
 
 // ---- pass A: sort the rows of a window by decreasing length (stable), slice entry totals
@@ -74,8 +76,9 @@ k_stage_sort(const uint32_t* __restrict__ rowptr, int64_t nrows, uint8_t* __rest
 static __global__ void __launch_bounds__(DDF_SELL_WIN)
 k_stage_fill(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
              int64_t nrows, const uint8_t* __restrict__ perm8, const uint8_t* __restrict__ len8,
-             const uint32_t* __restrict__ slice_ptr, uint32_t* __restrict__ tab, uint16_t* __restrict__ slot,
-             double* __restrict__ sval, uint32_t* __restrict__ status /* [0] = max slots or ~0 */) {
+             const uint32_t* __restrict__ slice_ptr, const uint8_t* __restrict__ isb, uint32_t* __restrict__ tab,
+             unsigned char* __restrict__ packed, unsigned char* __restrict__ meta,
+             uint32_t* __restrict__ status /* [0] = max slots or ~0 */) {
   extern __shared__ uint32_t keys[];                                   // STAGE_KEYS
   __shared__ uint32_t rstart[STAGE_RMAX + 1], roff[STAGE_RMAX + 1];
   __shared__ uint32_t s_nruns, s_bad;
@@ -146,14 +149,24 @@ k_stage_fill(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ co
   __syncthreads();
   if (s_bad) return;
   const uint32_t nruns = s_nruns;
+  // the window's record: values, then slots
+  double* sval = reinterpret_cast<double*>(packed + (size_t)first_entry * 10);
+  uint16_t* slot = reinterpret_cast<uint16_t*>(packed + (size_t)first_entry * 10 + (size_t)stored * 8);
   // entries -> jagged slices (same addressing as the row kernels)
   const int64_t r = wbase + t;                       // sorted position
   const int64_t i = wbase + perm8[r];
   const uint32_t mylen = len8[r];
   const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
   const uint32_t lane = (uint32_t)t & 31u;
-  uint32_t off = slice_ptr[r >> 5];
+  uint32_t off = slice_ptr[r >> 5] - first_entry;    // entry offset inside the window's record
   const uint32_t rlo = i < nrows ? rowptr[i] : 0u;
+  {
+    unsigned char* wm = meta + (size_t)blockIdx.x * STAGE_META;
+    if (t == 0) *reinterpret_cast<uint32_t*>(wm) = stored;
+    wm[16 + t] = perm8[r];
+    wm[16 + DDF_SELL_WIN + t] = (unsigned char)mylen;
+    wm[16 + 2 * DDF_SELL_WIN + t] = (isb && wbase + t < nrows) ? isb[wbase + t] : 0;
+  }
   for (uint32_t q = 0; q < maxlen; q++) {
     const bool act = q < mylen;
     const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, act));
@@ -172,7 +185,7 @@ k_stage_fill(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ co
 }
 
 static int stage_build(ddf_ctx* ctx, const uint32_t* rowptr, const int32_t* col, const double* val, int64_t nrows,
-                       int64_t nnz, StageBufs& out) {
+                       int64_t nnz, const uint8_t* isb, StageBufs& out) {
   out.release();
   const int64_t nwin = (nrows + DDF_SELL_WIN - 1) / DDF_SELL_WIN;
   const int64_t nslices = nwin * (DDF_SELL_WIN / 32);
@@ -201,14 +214,14 @@ static int stage_build(ddf_ctx* ctx, const uint32_t* rowptr, const int32_t* col,
   out.max_entries = stv[1];
   out.entries = total;
   DDF_CHECK(out.tab.alloc(ctx, nwin * STAGE_TAB));
-  DDF_CHECK(out.slot.alloc(ctx, (size_t)total + 8));
-  DDF_CHECK(out.val.alloc(ctx, (size_t)total + 8));
+  DDF_CHECK(out.packed.alloc(ctx, (size_t)total * 10 + 64));
+  DDF_CHECK(out.meta.alloc(ctx, (size_t)nwin * STAGE_META));
   // padding entries are never read by a row, but they travel in the bulk copies: keep them defined
-  DDF_CUDA(cudaMemsetAsync(out.slot.p, 0, ((size_t)total + 8) * 2, ctx->stream));
-  DDF_CUDA(cudaMemsetAsync(out.val.p, 0, ((size_t)total + 8) * 8, ctx->stream));
+  DDF_CUDA(cudaMemsetAsync(out.packed.p, 0, (size_t)total * 10 + 64, ctx->stream));
+  DDF_CUDA(cudaMemsetAsync(out.meta.p, 0, (size_t)nwin * STAGE_META, ctx->stream));
   const size_t smem = STAGE_KEYS * 4;
   k_stage_fill<<<(int)nwin, DDF_SELL_WIN, smem, ctx->stream>>>(rowptr, col, val, nrows, out.perm8.p, out.len8.p, out.ptr.p,
-                                                              out.tab.p, out.slot.p, out.val.p, status.p);
+                                                              isb, out.tab.p, out.packed.p, out.meta.p, status.p);
   DDF_LAUNCH_CHECK(ctx);
   DDF_CUDA(cudaMemcpyAsync(&st, status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   DDF_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -119,7 +119,7 @@ int ddf_mesh_require_wave(ddf_mesh* m) {
   // staged rows (stage.cuh): 10 B per entry, no padding, u gathered from a TMA-staged shared-memory buffer.
   // Tuning bit 16 disables it (A/B against the explicit-index SELL kernel below).
   if (!(g_tune_wave & 16)) {
-    DDF_CHECK(stage_build(ctx, m->adj_ptr.p, m->adj_nbr.p, m->adj_l.p, nv, m->adj_nnz, m->lstage));
+    DDF_CHECK(stage_build(ctx, m->adj_ptr.p, m->adj_nbr.p, m->adj_l.p, nv, m->adj_nnz, m->isbnd[0].p, m->lstage));
     if (m->lstage.ok) {
       m->has_wave = true;
       return 0;
@@ -301,8 +301,8 @@ __device__ __forceinline__ double stage_row_sum(const uint16_t* __restrict__ slo
 template <int MODE, int BATCH>
 __global__ void __launch_bounds__(DDF_SELL_WIN)
 k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* __restrict__ perm8,
-             const uint8_t* __restrict__ len8, const uint32_t* __restrict__ tab, const uint16_t* __restrict__ slot,
-             const double* __restrict__ sl, int64_t first_window) {
+             const uint8_t* __restrict__ len8, const uint32_t* __restrict__ tab, const unsigned char* __restrict__ packed,
+             int64_t first_window) {
   extern __shared__ __align__(16) double stage[];
   __shared__ __align__(8) uint64_t mbar;
   const int64_t win = first_window + blockIdx.x;
@@ -317,7 +317,11 @@ k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* _
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t mylen = len8[r];
   const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);                // rows are sorted by decreasing length
-  const uint32_t off = slice_ptr[r >> 5];
+  // the window's record: values at byte 10*e0, slots behind them; entry offsets are relative to e0
+  const uint32_t ent0 = __ldg(tab + win * STAGE_TAB + 2), stored = __ldg(tab + win * STAGE_TAB + 3);
+  const double* sl = reinterpret_cast<const double*>(packed + (size_t)ent0 * 10);
+  const uint16_t* slot = reinterpret_cast<const uint16_t*>(packed + (size_t)ent0 * 10 + (size_t)stored * 8);
+  const uint32_t off = slice_ptr[r >> 5] - ent0;
   const bool mine = i >= a.row0 && i < a.row1;
   // epilogue operands, requested before the row sum so that their latency overlaps it
   double e0 = 0.0, e1 = 0.0;
@@ -352,7 +356,7 @@ k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* _
 // memory only and release the stage through its "empty" mbarrier.  No register ever waits on
 // HBM, so the bytes in flight per SM are (stages - 1) x ~50 KB regardless of occupancy.
 struct PipeGeom {
-  uint32_t o_val, o_slot, o_v, o_u, o_isb, o_perm, o_len, stage_bytes;   // byte offsets inside a stage (x16)
+  uint32_t o_ent, o_v, o_u, o_meta, stage_bytes;   // byte offsets inside a stage (x16): entries record, v, u, meta
   int nstages;
   int64_t nrows;
 };
@@ -361,13 +365,17 @@ struct PipeGeom {
 
 template <int MODE, int NG>
 __global__ void __launch_bounds__(NG * PIPE_GROUP + 32, 1)
-k_rows_pipe(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* __restrict__ perm8,
-            const uint8_t* __restrict__ len8, const uint32_t* __restrict__ tab, const uint16_t* __restrict__ slot,
-            const double* __restrict__ sl, int64_t w0, int64_t w1, PipeGeom g) {
+k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __restrict__ packed,
+            const unsigned char* __restrict__ meta, int64_t w0, int64_t w1, PipeGeom g) {
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   __shared__ __align__(8) uint64_t full[PIPE_MAX_STAGES], empty[PIPE_MAX_STAGES], tfull[PIPE_TD];
   __shared__ __align__(16) uint32_t tabS[PIPE_TD * STAGE_TAB];
+  // issued[s] = 1 + the last iteration the producer has armed stage s for.  A consumer group must see its own
+  // iteration here BEFORE it waits on full[s] by parity: with NG groups sharing the ring, the previous use of the
+  // stage belongs to another group, and a parity wait entered a whole phase early would pass at once.
+  __shared__ uint32_t issued[PIPE_MAX_STAGES];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid < PIPE_MAX_STAGES) issued[tid] = 0u;
   if (tid == 0) {
     for (int d = 0; d < PIPE_TD; d++)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tfull[d])) : "memory");
@@ -413,24 +421,20 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* __
       unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
       const int64_t r0 = win * DDF_SELL_WIN;
       const uint32_t nr = (uint32_t)min((int64_t)DDF_SELL_WIN, g.nrows - r0);
-      const uint32_t vbytes = ((nr + 1u) & ~1u) * 8u, mbytes = (nr + 15u) & ~15u;
-      uint32_t tx = total * 8u + nent * 10u + 2u * DDF_SELL_WIN;
-      if (MODE == 1) tx += vbytes + mbytes;
-      if (MODE == 2) tx += 2u * vbytes + mbytes;
-      if (lane == 0)
+      const uint32_t vbytes = ((nr + 1u) & ~1u) * 8u;
+      // requests per window: the runs of u, ONE entries record, ONE meta record, v (or udot) and u
+      uint32_t tx = total * 8u + nent * 10u + STAGE_META;
+      if (MODE == 1) tx += vbytes;
+      if (MODE == 2) tx += 2u * vbytes;
+      if (lane == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(tx) : "memory");
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&issued[s])), "r"((uint32_t)it + 1u) : "memory");
+      }
       __syncwarp();
       if (lane < nruns) bulk_g2s(sb + (size_t)off * 8, a.u + start, (end - off) * 8u, &full[s], pol_keep);
-      if (lane == 31 && nent) {
-        bulk_g2s(sb + g.o_val, sl + e0, nent * 8u, &full[s], pol_stream);
-        bulk_g2s(sb + g.o_slot, slot + e0, nent * 2u, &full[s], pol_stream);
-      }
-      if (lane == 30) {
-        bulk_g2s(sb + g.o_perm, perm8 + r0, DDF_SELL_WIN, &full[s], pol_stream);
-        bulk_g2s(sb + g.o_len, len8 + r0, DDF_SELL_WIN, &full[s], pol_stream);
-      }
+      if (lane == 31 && nent) bulk_g2s(sb + g.o_ent, packed + (size_t)e0 * 10, nent * 10u, &full[s], pol_stream);
+      if (lane == 30) bulk_g2s(sb + g.o_meta, meta + win * STAGE_META, STAGE_META, &full[s], pol_stream);
       if (lane == 29 && MODE != 0) {
-        bulk_g2s(sb + g.o_isb, a.isb + r0, mbytes, &full[s], pol_stream);
         bulk_g2s(sb + g.o_v, (MODE == 1 ? a.udot : a.out0) + r0, vbytes, &full[s], pol_stream);
         if (MODE == 2) bulk_g2s(sb + g.o_u, a.u + r0, vbytes, &full[s], pol_keep);
       }
@@ -445,14 +449,21 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* __
     for (int64_t win = w0 + blockIdx.x + grp * stride; win < w1; it += NG, win += NG * stride) {
       const int s = (int)(it % g.nstages);
       const uint32_t j = (uint32_t)(it / g.nstages);
+      for (;;) {                          // the producer has armed stage s for THIS iteration
+        uint32_t seen;
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&issued[s])) : "memory");
+        if (seen >= (uint32_t)it + 1u) break;
+      }
       stage_wait(&full[s], j & 1u);
       const unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
       const double* stage = reinterpret_cast<const double*>(sb);
-      const double* valS = reinterpret_cast<const double*>(sb + g.o_val);
-      const uint16_t* slotS = reinterpret_cast<const uint16_t*>(sb + g.o_slot);
-      const uint8_t* lenS = sb + g.o_len;
+      const unsigned char* metaS = sb + g.o_meta;
+      const uint32_t nentS = *reinterpret_cast<const uint32_t*>(metaS);
+      const double* valS = reinterpret_cast<const double*>(sb + g.o_ent);
+      const uint16_t* slotS = reinterpret_cast<const uint16_t*>(sb + g.o_ent + (size_t)nentS * 8);
+      const uint8_t* lenS = metaS + 16 + DDF_SELL_WIN;
       const uint32_t mylen = lenS[gtid];
-      const uint32_t p = (sb + g.o_perm)[gtid];
+      const uint32_t p = (metaS + 16)[gtid];
       // entry offset of this slice inside the window = lengths of the rows of the earlier slices
       uint32_t part = 0;
       for (uint32_t k = lane; k < 32u * gwarp; k += 32u) part += lenS[k];
@@ -475,7 +486,7 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* __
         if (MODE == 0) {
           st_hint_f64(a.out0 + i, acc, pol_stream);
         } else {
-          const double m = (sb + g.o_isb)[p] ? 0.0 : 1.0;
+          const double m = (metaS + 16 + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
           const double e0 = reinterpret_cast<const double*>(sb + g.o_v)[p];
           if (MODE == 1) {
             a.out0[i] = __dmul_rn(m, e0);
@@ -498,14 +509,11 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* __
 static int pipe_geometry(const ddf_mesh* m, PipeGeom* g) {
   const StageBufs& sb = m->lstage;
   auto up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
-  g->o_val = up(sb.max_slots * 8u, 16);
-  g->o_slot = g->o_val + sb.max_entries * 8u;
-  g->o_v = g->o_slot + up(sb.max_entries * 2u, 16);
+  g->o_ent = up(sb.max_slots * 8u, 16);
+  g->o_v = g->o_ent + up(sb.max_entries * 10u, 16);
   g->o_u = g->o_v + DDF_SELL_WIN * 8;
-  g->o_isb = g->o_u + DDF_SELL_WIN * 8;
-  g->o_perm = g->o_isb + DDF_SELL_WIN;
-  g->o_len = g->o_perm + DDF_SELL_WIN;
-  g->stage_bytes = up(g->o_len + DDF_SELL_WIN, 128);
+  g->o_meta = g->o_u + DDF_SELL_WIN * 8;
+  g->stage_bytes = up(g->o_meta + STAGE_META, 128);
   const uint32_t budget = 227u * 1024u - 4096u;
   g->nstages = (int)(budget / g->stage_bytes);
   if (g->nstages > PIPE_MAX_STAGES) g->nstages = PIPE_MAX_STAGES;
@@ -593,8 +601,8 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
       DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe<MODE, NGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
       attr_p = smem_p;                                                                                              \
     }                                                                                                               \
-    k_rows_pipe<MODE, NGV><<<grid, NGV * PIPE_GROUP + 32, smem_p, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p,     \
-                                                                           sb.tab.p, sb.slot.p, sb.val.p, w0, w1, g); \
+    k_rows_pipe<MODE, NGV><<<grid, NGV * PIPE_GROUP + 32, smem_p, stream>>>(a, sb.tab.p, sb.packed.p, sb.meta.p,    \
+                                                                           w0, w1, g);                               \
   } while (0)
       if (ng == 1) DDF_PIPE_LAUNCH(1);
       else if (ng == 3) DDF_PIPE_LAUNCH(3);
@@ -608,16 +616,16 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
     const int batch = (g_tune_wave >> 5) & 3;          // A/B knob: gathers in flight per thread
     if (batch == 1)
       k_rows_stage<MODE, 4><<<(int)(w1 - w0), DDF_SELL_WIN, smem, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p, sb.tab.p,
-                                                                           sb.slot.p, sb.val.p, w0);
+                                                                           sb.packed.p, w0);
     else if (batch == 2)
       k_rows_stage<MODE, 6><<<(int)(w1 - w0), DDF_SELL_WIN, smem, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p, sb.tab.p,
-                                                                           sb.slot.p, sb.val.p, w0);
+                                                                           sb.packed.p, w0);
     else if (batch == 3)
       k_rows_stage<MODE, 12><<<(int)(w1 - w0), DDF_SELL_WIN, smem, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p, sb.tab.p,
-                                                                            sb.slot.p, sb.val.p, w0);
+                                                                            sb.packed.p, w0);
     else
       k_rows_stage<MODE, 8><<<(int)(w1 - w0), DDF_SELL_WIN, smem, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p, sb.tab.p,
-                                                                           sb.slot.p, sb.val.p, w0);
+                                                                           sb.packed.p, w0);
   } else if (m->wave_sell && (g_tune_wave & 3) == 0) {   // explicit-index SELL-32 rows
     const int64_t w0 = a.row0 / DDF_SELL_WIN, w1 = (a.row1 + DDF_SELL_WIN - 1) / DDF_SELL_WIN;
     if (w1 - w0 > 0x7fffffffLL) DDF_FAIL("grid too large");
@@ -855,8 +863,8 @@ extern "C" int ddf_wave_step_bytes(ddf_mesh* m, int64_t* algorithmic, int64_t* f
   const int64_t E = m->n[1], V = m->n[0];
   *algorithmic = E * 16 + V * 41;                  // E*(2*4+8) + V*(8*5+1)
   // what this format streams per step: 12 B per stored entry + u, v (r/w), u', mask per vertex + row offsets
-  if (m->has_wave && m->lstage.ok)   // 10 B per entry, no padding; per vertex u (staged once), v r/w, u', mask, perm, len
-    *format_bytes = m->lstage.entries * 10 + V * (8 * 4 + 1 + 2) + (V / 32 + 1) * 4 + (V / 256 + 1) * 96;
+  if (m->has_wave && m->lstage.ok)   // 10 B per entry, no padding; per vertex u (staged once), v r/w, u'; per window meta + run table
+    *format_bytes = m->lstage.entries * 10 + V * (8 * 4) + (V / 256 + 1) * (STAGE_META + STAGE_TAB * 4);
   else if (m->has_wave && m->wave_sell)
     *format_bytes = m->lsell.padded * 8 + m->lsell.index_words * 4 + V * (8 * 4 + 1 + 1) + (V / 32 + 1) * 12;
   else *format_bytes = (m->has_wave ? m->adj_nnz : 2 * E + V) * 12 + V * (4 + 8 * 4 + 1);

@@ -545,6 +545,31 @@ def test_wave_staged_wide_planes(ddf, ctx):
     assert np.abs(res[0][1]).max() > 0.01
 
 
+def test_wave_pipeline_repeatable(ddf, ctx):
+    """The persistent TMA pipeline shares its stage ring between consumer groups; a consumer that entered a
+    parity wait one phase early once read a stage before its data had landed (rare, size dependent).  Guarded by
+    the producer's `issued` counter now: repeated runs at a size with ~8400 windows must be bit-identical to each
+    other and to the explicit-index SELL kernel."""
+    n = 128
+    ref = None
+    for tune, reps in ((16, 1), (0, 6), (768, 3)):
+        ddf._lib.call("ddf_set_tuning", b"wave", tune)
+        try:
+            m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
+            u0 = ddf.sample(m, "wave")
+            dt = ddf.wave_dt(m)
+            for _ in range(reps):
+                u, v = u0.copy(), ddf.Fun(m, ddf.Pr, 0)
+                ddf.wave_leapfrog(m, u, v, dt, 8)
+                out = (u.values, v.values)
+                if ref is None:
+                    ref = out
+                assert np.array_equal(out[0], ref[0]) and np.array_equal(out[1], ref[1]), tune
+            m.close()
+        finally:
+            ddf._lib.call("ddf_set_tuning", b"wave", 0)
+
+
 def test_wave_sample_and_convergence(ddf, ctx):
     """Device-sampled initial data and second-order convergence of the leapfrog
     solution (the oracle restatement of wave.jl is second order)."""
