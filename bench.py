@@ -415,7 +415,12 @@ def run_b200(args):
                          "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(d1_bytes),
                          "ms_per_launch": d1_ms, "frac_of_nominal_8TBs": d1_bytes / d1_ms * 1e-6 / 8000.0},
-            "breakdown": breakdown, "wave": wave, "assembly_ms": asm_ms, "setup_s": setup_s,
+            "breakdown": breakdown, "wave": wave, "assembly_ms": asm_ms,
+            # assembly of d_3, d_2, d_1 on the device from the tet table (bit-exact; no roofline target):
+            # face tuples generated, sorted and ranked per second
+            "assembly": {"ms": asm_ms, "tuples": int(sum((R + 1) * cnt[R] for R in (1, 2, 3))),
+                         "tuples_per_s": sum((R + 1) * cnt[R] for R in (1, 2, 3)) / (asm_ms * 1e-3)},
+            "setup_s": setup_s,
             "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
             "hbm_bytes_in_use": ctx.bytes_in_use(),
         }

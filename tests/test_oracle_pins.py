@@ -8,6 +8,8 @@ CPU only (no GPU needed): runs in the `-m "not gpu"` tier.
 import itertools
 import math
 
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -400,3 +402,21 @@ def test_tsit5_fifth_order_on_oscillator():
         u, v = o.tsit5_steps(f, (np.array([1.0]), np.array([0.0])), 1.0 / n, n)
         errs.append(abs(u[0] - np.cos(1.0)) + abs(v[0] + np.sin(1.0)))
     assert 24 < errs[0] / errs[1] < 40 and 24 < errs[1] / errs[2] < 40, errs
+
+
+# ------------------------------------------------------------------ hand-derived known answer
+def test_two_triangle_known_answer():
+    """tests/golden/two_triangles.json (derived by hand from the reference's rules, see make_two_triangles.py;
+    the same numbers are compiled into tests/c/abi_client.c): the oracle reproduces edges, signs and d0 x."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "two_triangles.json")))
+    m = o.build_manifold("square", np.array(g["triangles"]) - 1, np.array(g["coords"], dtype=float))
+    assert [m.nsimplices(R) for R in range(3)] == [4, 5, 2]
+    assert (m.simplices[1] + 1).tolist() == g["edges"]
+    for R, key in ((1, "boundary1"), (2, "boundary2")):
+        cp, rv, nz = o.to_julia_csc(m.boundaries[R])
+        for j, col in enumerate(g[key]):
+            assert rv[cp[j] - 1:cp[j + 1] - 1].tolist() == col["rows"]
+            assert nz[cp[j] - 1:cp[j + 1] - 1].tolist() == col["signs"]
+    assert o.apply_deriv(o.Pr, 0, m, np.array(g["x"])).tolist() == g["d0x"]
+    assert np.allclose(o.calc_volumes(m, 2), g["area_per_triangle"], atol=1e-15)
