@@ -105,6 +105,8 @@ struct ddf_mesh {
   // built, 1 = in use, 2 = rejected (padding too large -> CSR kernel)
   int bsell_state[DDF_MAXD + 1] = {0};
   SellBufs bsell[DDF_MAXD + 1];
+  // rows of <= 2 entries (faces of the top simplices): (entry0, entry1 | 0xFFFFFFFF) pairs, one 8-byte load per row
+  DevBuf<uint32_t> bpair[DDF_MAXD + 1];
   // staged copies of the fixed-width tables of d_{R-1} = d_R^T (primal derivative apply)
   FStageBufs fstage[DDF_MAXD + 1];
   DevBuf<double> utmp;                   // V   ping-pong buffer of the fused step
