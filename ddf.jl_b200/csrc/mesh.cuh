@@ -15,7 +15,9 @@
 struct SellBufs {
   DevBuf<uint32_t> ptr;     // entry offset per slice of 32 sorted rows (nwindows*8 + 1)
   DevBuf<uint8_t> perm8;    // sorted position -> row offset inside its 256-row window
-  DevBuf<uint32_t> col;     // explicit indices (released when compressed)
+  DevBuf<uint32_t> col;     // explicit indices (released when compressed or stored as 16-bit offsets)
+  DevBuf<uint16_t> col16;   // column - row as int16 (0x8000 = padding) when every offset fits: 10 B per entry
+  bool idx16 = false;
   DevBuf<double> val;
   // compressed index stream: per slice a bit mask of uniform-offset columns and a word offset
   bool compressed = false;
@@ -23,8 +25,9 @@ struct SellBufs {
   int64_t padded = 0;       // stored entries incl. padding
   int64_t index_words = 0;  // 32-bit words of index data actually stored
   void release() {
-    ptr.release(); perm8.release(); col.release(); val.release(); umask.release(); iptr.release(); cidx.release();
-    padded = 0; index_words = 0; compressed = false;
+    ptr.release(); perm8.release(); col.release(); col16.release(); val.release(); umask.release(); iptr.release();
+    cidx.release();
+    padded = 0; index_words = 0; compressed = false; idx16 = false;
   }
 };
 

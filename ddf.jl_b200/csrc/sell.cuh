@@ -129,6 +129,27 @@ k_sell_pack(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict__ p
   }
 }
 
+// explicit 32-bit columns -> 16-bit offsets column - row (0x8000 = padding); *bad is set when an offset does not fit
+static __global__ void __launch_bounds__(DDF_SELL_WIN)
+k_sell_to16(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict__ perm8, const uint32_t* __restrict__ scol,
+            uint16_t* __restrict__ col16, uint32_t* __restrict__ bad) {
+  const int64_t r = (int64_t)blockIdx.x * DDF_SELL_WIN + threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * DDF_SELL_WIN + perm8[r];
+  const int64_t s = r >> 5;
+  const uint32_t base = sell_ptr[s] + (uint32_t)(r & 31), w = (sell_ptr[s + 1] - sell_ptr[s]) >> 5;
+  for (uint32_t q = 0; q < w; q++) {
+    const size_t pos = (size_t)base + (size_t)q * 32;
+    const uint32_t j = scol[pos];
+    uint16_t d = 0x8000u;
+    if (j != DDF_SELL_PAD) {
+      const int64_t off = (int64_t)j - i;
+      if (off < -32767 || off > 32767) *bad = 1u;
+      d = (uint16_t)(int16_t)off;
+    }
+    col16[pos] = d;
+  }
+}
+
 // position of column q in the compressed index stream of a slice
 __device__ __forceinline__ uint32_t sell_col_offset(uint32_t um, uint32_t q) {
   const uint32_t before = q >= 32 ? um : (um & ((1u << q) - 1u));
@@ -137,7 +158,7 @@ __device__ __forceinline__ uint32_t sell_col_offset(uint32_t um, uint32_t q) {
 
 // Build SELL-32-256 from a row-CSR (col may carry a sign in bit 31; val may be null).
 static int sell_build(ddf_ctx* ctx, const uint32_t* rowptr, const uint32_t* col, const double* val, int64_t nrows,
-                      SellBufs& out, bool compress, bool sort_sig = true) {
+                      SellBufs& out, bool compress, bool sort_sig = true, bool try16 = false) {
   const int64_t nwin = (nrows + DDF_SELL_WIN - 1) / DDF_SELL_WIN;
   const int64_t nslices = nwin * (DDF_SELL_WIN / 32);
   DevBuf<uint32_t> w32, sig;
@@ -171,6 +192,19 @@ static int sell_build(ddf_ctx* ctx, const uint32_t* rowptr, const uint32_t* col,
   if (val) k_sell_fill<true><<<(int)nwin, DDF_SELL_WIN, 0, ctx->stream>>>(rowptr, col, val, out.ptr.p, out.perm8.p, nrows, out.col.p, out.val.p);
   else k_sell_fill<false><<<(int)nwin, DDF_SELL_WIN, 0, ctx->stream>>>(rowptr, col, nullptr, out.ptr.p, out.perm8.p, nrows, out.col.p, nullptr);
   DDF_LAUNCH_CHECK(ctx);
+  if (try16 && !compress) {          // 16-bit offsets when the matrix is banded enough (|col - row| <= 32767)
+    DevBuf<uint32_t> bad;
+    DDF_CHECK(bad.alloc(ctx, 1));
+    DDF_CUDA(cudaMemsetAsync(bad.p, 0, 4, ctx->stream));
+    DDF_CHECK(out.col16.alloc(ctx, tot));
+    k_sell_to16<<<(int)nwin, DDF_SELL_WIN, 0, ctx->stream>>>(out.ptr.p, out.perm8.p, out.col.p, out.col16.p, bad.p);
+    DDF_LAUNCH_CHECK(ctx);
+    uint32_t hb = 0;
+    DDF_CUDA(cudaMemcpyAsync(&hb, bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hb) out.col16.release();
+    else { out.col.release(); out.idx16 = true; out.index_words = (tot + 1) / 2; }
+  }
   if (!compress) return 0;
   // ---- index compression
   DevBuf<uint32_t> isize;

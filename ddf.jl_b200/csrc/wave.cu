@@ -116,20 +116,23 @@ int ddf_mesh_require_wave(ddf_mesh* m) {
                                                         m->star[1].p, nv, nullptr, m->adj_ptr.p, m->adj_nbr.p,
                                                         m->adj_l.p);
   DDF_LAUNCH_CHECK(ctx);
-  // staged rows (stage.cuh): 10 B per entry, no padding, u gathered from a TMA-staged shared-memory buffer.
-  // Tuning bit 16 disables it (A/B against the explicit-index SELL kernel below).
-  if (!(g_tune_wave & 16)) {
+  // Two storage candidates for the row kernels:
+  //  * staged rows (stage.cuh): 10 B per entry, no padding, everything streamed by the persistent TMA pipeline.  Its
+  //    cost is ~1 us per 256-row WINDOW (bulk-request rate), so it pays when a window carries enough bytes: rows of
+  //    >= 10 entries on average (3D meshes).  Tuning bit 16 disables it.
+  //  * SELL-32-256 with explicit indices -- as 16-bit offsets column - row (10 B per entry) when the matrix is
+  //    banded enough, else 32-bit (12 B per entry).  Short rows (2D meshes: 7 entries) are faster here
+  //    (profiles/r01_tuning.md).  Tuning bit 2048 forces 32-bit indices.
+  const bool long_rows = m->adj_nnz >= 10 * nv;
+  if (!(g_tune_wave & 16) && (long_rows || (g_tune_wave & 4096))) {
     DDF_CHECK(stage_build(ctx, m->adj_ptr.p, m->adj_nbr.p, m->adj_l.p, nv, m->adj_nnz, m->isbnd[0].p, m->lstage));
     if (m->lstage.ok) {
       m->has_wave = true;
       return 0;
     }
   }
-  // SELL-32-256 copy for the row kernels; keep it when the padding costs < 12.5 % extra entries.
-  // Measured at C4 (profiles/r01_tuning.md): explicit indices stream at 95 % of the copy peak; the compressed
-  // index stream (tuning bit 4) saves 17 % of the bytes but adds a dependent load and is latency-bound -> off.
   DDF_CHECK(sell_build(ctx, m->adj_ptr.p, reinterpret_cast<const uint32_t*>(m->adj_nbr.p), m->adj_l.p, nv, m->lsell,
-                       (g_tune_wave & 4) != 0, (g_tune_wave & 8) != 0));
+                       (g_tune_wave & 4) != 0, (g_tune_wave & 8) != 0, !(g_tune_wave & 2048)));
   m->wave_sell = m->lsell.padded <= m->adj_nnz + m->adj_nnz / 8;
   if (!m->wave_sell) m->lsell.release();
   m->has_wave = true;
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(256) k_rows_thread(RowArgs a) {
 
 // SELL-32: one thread per row, coalesced index/value loads, batches of 8 gathers in flight
 // COMPRESSED: indices come from the per-slice stream (uniform-offset columns hold one word)
-template <int MODE, bool COMPRESSED>
+template <int MODE, bool COMPRESSED, bool IDX16 = false>
 __global__ void __launch_bounds__(256)
 k_rows_sell(RowArgs a, const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict__ perm8,
             const uint32_t* __restrict__ snbr, const double* __restrict__ sl, const uint32_t* __restrict__ umask,
@@ -241,6 +244,9 @@ k_rows_sell(RowArgs a, const uint32_t* __restrict__ sell_ptr, const uint8_t* __r
                                                            sell_col_offset(um, c) + (uni ? 0u : lane))
                                  : DDF_SELL_PAD;
         j[q] = (ok && uni) ? (uint32_t)i + word : word;
+      } else if (IDX16) {                        // 16-bit offsets column - row, 0x8000 = padding
+        const uint16_t d = ok ? __ldg(reinterpret_cast<const uint16_t*>(snbr) + pos) : (uint16_t)0x8000u;
+        j[q] = d != 0x8000u ? (uint32_t)((int64_t)i + (int16_t)d) : DDF_SELL_PAD;
       } else {
         j[q] = ok ? (uint32_t)ld_stream_int(reinterpret_cast<const int*>(snbr) + pos) : DDF_SELL_PAD;
       }
@@ -633,6 +639,9 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
     if (sb.compressed)
       k_rows_sell<MODE, true><<<(int)(w1 - w0), DDF_SELL_WIN, 0, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.cidx.p, sb.val.p,
                                                                             sb.umask.p, sb.iptr.p, w0);
+    else if (sb.idx16)
+      k_rows_sell<MODE, false, true><<<(int)(w1 - w0), DDF_SELL_WIN, 0, stream>>>(
+          a, sb.ptr.p, sb.perm8.p, reinterpret_cast<const uint32_t*>(sb.col16.p), sb.val.p, nullptr, nullptr, w0);
     else
       k_rows_sell<MODE, false><<<(int)(w1 - w0), DDF_SELL_WIN, 0, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.col.p, sb.val.p,
                                                                              nullptr, nullptr, w0);
@@ -866,7 +875,7 @@ extern "C" int ddf_wave_step_bytes(ddf_mesh* m, int64_t* algorithmic, int64_t* f
   if (m->has_wave && m->lstage.ok)   // 10 B per entry, no padding; per vertex u (staged once), v r/w, u'; per window meta + run table
     *format_bytes = m->lstage.entries * 10 + V * (8 * 4) + (V / 256 + 1) * (STAGE_META + STAGE_TAB * 4);
   else if (m->has_wave && m->wave_sell)
-    *format_bytes = m->lsell.padded * 8 + m->lsell.index_words * 4 + V * (8 * 4 + 1 + 1) + (V / 32 + 1) * 12;
+    *format_bytes = m->lsell.padded * 8 + m->lsell.index_words * 4 + V * (8 * 4 + 1 + 1) + (V / 32 + 1) * 12;   // index_words: 16-bit offsets count as half words
   else *format_bytes = (m->has_wave ? m->adj_nnz : 2 * E + V) * 12 + V * (4 + 8 * 4 + 1);
   return 0;
 }

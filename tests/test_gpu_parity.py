@@ -570,6 +570,31 @@ def test_wave_pipeline_repeatable(ddf, ctx):
             ddf._lib.call("ddf_set_tuning", b"wave", 0)
 
 
+def test_wave_row_formats_2d(ddf, ctx):
+    """2D mesh (7 entries per row): SELL with 16-bit column offsets (default), 32-bit indices (tuning 2048), staged
+    rows forced (4096) and CSR (17) all reproduce the oracle bit for bit."""
+    n = 40
+    om = o.large_hypercube_manifold(2, (n, n))
+    rng = np.random.default_rng(22)
+    u0 = rng.standard_normal(om.nsimplices(0))
+    v0 = rng.standard_normal(om.nsimplices(0))
+    want = {0: "sell", 2048: "sell", 4096: "staged", 17: "sell"}     # 17: SELL storage, CSR thread-per-row kernel
+    for tune, fmt in want.items():
+        ddf._lib.call("ddf_set_tuning", b"wave", tune)
+        try:
+            dm = ddf.large_hypercube_manifold(2, (n, n), ctx=ctx)
+            omg = with_device_geometry(om, dm)
+            u, v = ddf.Fun(dm, ddf.Pr, 0, u0), ddf.Fun(dm, ddf.Pr, 0, v0)
+            dt = ddf.wave_dt(dm)
+            ddf.wave_leapfrog(dm, u, v, dt, 5)
+            ou, ov = o.wave_leapfrog(omg, u0, v0, dt, 5)
+            assert np.array_equal(u.values, ou) and np.array_equal(v.values, ov), tune
+            assert ddf.wave_format(dm) == fmt, (tune, ddf.wave_format(dm))
+            dm.close()
+        finally:
+            ddf._lib.call("ddf_set_tuning", b"wave", 0)
+
+
 def test_wave_sample_and_convergence(ddf, ctx):
     """Device-sampled initial data and second-order convergence of the leapfrog
     solution (the oracle restatement of wave.jl is second order)."""
@@ -644,12 +669,12 @@ def test_config2_poisson_mesh_full_size(ddf, ctx):
 
 def test_config3_wave_2d_full_size(ddf, ctx):
     """BASELINE config 3: 2D Kuhn n=2048 (4,198,401 / 12,587,008 / 8,388,608), fused leapfrog.  Full-size
-    checks: closed-form counts, the staged-rows format is in use, the step is linear (exact for a power of
+    checks: closed-form counts, the row format chosen for short rows, the step is linear (exact for a power of
     two), and the solution follows cos(sqrt(2) pi t) prod sin(pi x) (wave.jl:42-58,150-163)."""
     n = 2048
     m = ddf.large_hypercube_manifold(2, (n, n), ctx=ctx)
     assert [m.nsimplices(R) for R in range(3)] == [(n + 1) ** 2, 3 * n * n + 2 * n, 2 * n * n]
-    assert ddf.wave_format(m) == "staged"
+    assert ddf.wave_format(m) == "sell"          # 7 entries per row: explicit 16-bit offsets beat the TMA pipeline
     u0 = ddf.sample(m, "wave")
     u1, v1 = u0.copy(), ddf.Fun(m, ddf.Pr, 0)
     u2, v2 = u0 * 8.0, ddf.Fun(m, ddf.Pr, 0)
