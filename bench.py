@@ -337,6 +337,23 @@ def run_b200(args):
             "algorithmic_bytes": alg, "format_bytes": fmt, "GBps": alg / wave_ms * 1e-6,
             "frac": alg / wave_ms * 1e-6 / peak, "dt": dt, "u_inf_after": unorm, "row_format": ddf.wave_format(mfd),
             "halo": ddf.dist.halo_mode(mfd) if N > 1 else "none"}
+    # BASELINE config 3: 2D scalar wave on the n=2048 Kuhn mesh (8.39e6 triangles), fused leapfrog step, 1 GPU
+    wave2d = None
+    if N == 1 and not args.no_wave2d:
+        m2 = ddf.large_hypercube_manifold(2, (2048, 2048), ctx=ctx)
+        u2, v2 = ddf.sample(m2, "wave"), ddf.Fun(m2, ddf.Pr, 0)
+        dt2 = ddf.wave_dt(m2)
+        ddf.wave_leapfrog(m2, u2, v2, dt2, 20)
+        ctx.sync()
+        ctx.tic()
+        ddf.wave_leapfrog(m2, u2, v2, dt2, 200)
+        ms2 = ctx.toc() / 200
+        alg2, fmt2 = ddf.wave_step_bytes(m2)
+        wave2d = {"workload": "BASELINE config 3: 2D Kuhn n=2048, fused leapfrog step", "ms_per_step": ms2,
+                  "vertex_updates_per_s": m2.nsimplices(0) / (ms2 * 1e-3), "algorithmic_bytes": alg2,
+                  "format_bytes": fmt2, "GBps": alg2 / ms2 * 1e-6, "frac": alg2 / ms2 * 1e-6 / peak,
+                  "row_format": ddf.wave_format(m2), "steps": 200}
+        m2.close()
     clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
@@ -415,7 +432,7 @@ def run_b200(args):
                          "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(d1_bytes),
                          "ms_per_launch": d1_ms, "frac_of_nominal_8TBs": d1_bytes / d1_ms * 1e-6 / 8000.0},
-            "breakdown": breakdown, "wave": wave, "assembly_ms": asm_ms,
+            "breakdown": breakdown, "wave": wave, "wave2d": wave2d, "assembly_ms": asm_ms,
             # assembly of d_3, d_2, d_1 on the device from the tet table (bit-exact; no roofline target):
             # face tuples generated, sorted and ranked per second
             "assembly": {"ms": asm_ms, "tuples": int(sum((R + 1) * cnt[R] for R in (1, 2, 3))),
@@ -451,6 +468,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-wave2d", action="store_true")
     ap.add_argument("--strong", action="store_true", help="N > 1: cut ONE n^3 cube into N slabs (default: weak scaling)")
     ap.add_argument("--wave-tune", type=int, default=0, help="ddf_set_tuning('wave', x) for A/B runs (1024: NCCL halo)")
     args = ap.parse_args()

@@ -43,13 +43,15 @@ struct StageBufs {
   // per window 800 B: {u32 nent, pad to 16} | perm8[256] | len8[256] | boundary mask by row offset [256] | pad
   DevBuf<unsigned char> meta;
   uint32_t max_slots = 0;   // largest staging buffer of any window (Float64 elements)
-  uint32_t max_entries = 0; // most stored entries of any window (incl. its <= 7 padding entries)
+  uint32_t max_entries = 0; // most stored entries of any group of K windows (incl. their <= 7 padding entries each)
+  int K = 1;                // consecutive windows that share one run table / one pipeline stage
+  int64_t ngroups = 0;
   int64_t entries = 0;      // stored entries incl. the per-window padding
   int64_t nnz = 0;
   bool ok = false;
   void release() {
     ptr.release(); perm8.release(); len8.release(); tab.release(); packed.release(); meta.release();
-    max_slots = 0; max_entries = 0; entries = 0; nnz = 0; ok = false;
+    max_slots = 0; max_entries = 0; K = 1; ngroups = 0; entries = 0; nnz = 0; ok = false;
   }
 };
 

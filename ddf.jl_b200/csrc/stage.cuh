@@ -71,25 +71,28 @@ k_stage_sort(const uint32_t* __restrict__ rowptr, int64_t nrows, uint8_t* __rest
   }
 }
 
-// ---- pass B: per window: sort the touched columns -> runs, slots; entries into jagged slices
+// ---- pass B: per GROUP of K consecutive windows (K = 1 for long rows; K > 1 lets short rows -- 2D meshes --
+// amortise the per-group bulk requests of the persistent pipeline): sort the touched columns -> runs and
+// slots shared by the group; each window's entries into its own jagged record.
 // dynamic shared memory: STAGE_KEYS sorted column indices
 static __global__ void __launch_bounds__(DDF_SELL_WIN)
 k_stage_fill(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
-             int64_t nrows, const uint8_t* __restrict__ perm8, const uint8_t* __restrict__ len8,
+             int64_t nrows, int K, const uint8_t* __restrict__ perm8, const uint8_t* __restrict__ len8,
              const uint32_t* __restrict__ slice_ptr, const uint8_t* __restrict__ isb, uint32_t* __restrict__ tab,
              unsigned char* __restrict__ packed, unsigned char* __restrict__ meta,
-             uint32_t* __restrict__ status /* [0] = max slots or ~0 */) {
+             uint32_t* __restrict__ status /* [0] = max slots or ~0, [2] = max entries of a group */) {
   extern __shared__ uint32_t keys[];                                   // STAGE_KEYS
   __shared__ uint32_t rstart[STAGE_RMAX + 1], roff[STAGE_RMAX + 1];
   __shared__ uint32_t s_nruns, s_bad;
   const int t = threadIdx.x;
-  const int64_t wbase = (int64_t)blockIdx.x * DDF_SELL_WIN;
-  const int64_t wend = min(wbase + DDF_SELL_WIN, nrows);
-  const uint32_t e_lo = rowptr[wbase], e_hi = rowptr[wend];
+  const int64_t gbase = min((int64_t)blockIdx.x * K * DDF_SELL_WIN, nrows);
+  const int64_t gend = min(gbase + (int64_t)K * DDF_SELL_WIN, nrows);
+  const uint32_t e_lo = rowptr[gbase], e_hi = rowptr[gend];
   const uint32_t nent = e_hi - e_lo;
   uint32_t* wtab = tab + (int64_t)blockIdx.x * STAGE_TAB;
-  const uint32_t first_entry = slice_ptr[(int64_t)blockIdx.x * (DDF_SELL_WIN / 32)];
-  const uint32_t stored = slice_ptr[(int64_t)(blockIdx.x + 1) * (DDF_SELL_WIN / 32)] - first_entry;
+  const int64_t s0 = (int64_t)blockIdx.x * K * (DDF_SELL_WIN / 32);
+  const uint32_t first_entry = slice_ptr[s0];
+  const uint32_t stored = slice_ptr[s0 + (int64_t)K * (DDF_SELL_WIN / 32)] - first_entry;
   if (nent > (uint32_t)STAGE_KEYS) {
     if (t == 0) { wtab[0] = 0u; wtab[1] = 0u; wtab[2] = first_entry; wtab[3] = stored; atomicMax(status, 0xFFFFFFFFu); }
     return;
@@ -140,64 +143,74 @@ k_stage_fill(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     s_bad = bad ? 1u : 0u;
     wtab[0] = bad ? 0u : nruns;
     wtab[1] = bad ? 0u : total;
-    wtab[2] = first_entry;                                              // the window's entry range
+    wtab[2] = first_entry;                                              // the group's entry range
     wtab[3] = stored;
     if (!bad)
       for (uint32_t k = 0; k < nruns; k++) { wtab[4 + 2 * k] = rstart[k]; wtab[5 + 2 * k] = roff[k]; }
     atomicMax(status, bad ? 0xFFFFFFFFu : total);
+    atomicMax(status + 2, stored);
   }
   __syncthreads();
   if (s_bad) return;
   const uint32_t nruns = s_nruns;
-  // the window's record: values, then slots
-  double* sval = reinterpret_cast<double*>(packed + (size_t)first_entry * 10);
-  uint16_t* slot = reinterpret_cast<uint16_t*>(packed + (size_t)first_entry * 10 + (size_t)stored * 8);
-  // entries -> jagged slices (same addressing as the row kernels)
-  const int64_t r = wbase + t;                       // sorted position
-  const int64_t i = wbase + perm8[r];
-  const uint32_t mylen = len8[r];
-  const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
   const uint32_t lane = (uint32_t)t & 31u;
-  uint32_t off = slice_ptr[r >> 5] - first_entry;    // entry offset inside the window's record
-  const uint32_t rlo = i < nrows ? rowptr[i] : 0u;
-  {
-    unsigned char* wm = meta + (size_t)blockIdx.x * STAGE_META;
-    if (t == 0) *reinterpret_cast<uint32_t*>(wm) = stored;
-    wm[16 + t] = perm8[r];
-    wm[16 + DDF_SELL_WIN + t] = (unsigned char)mylen;
-    wm[16 + 2 * DDF_SELL_WIN + t] = (isb && wbase + t < nrows) ? isb[wbase + t] : 0;
-  }
-  for (uint32_t q = 0; q < maxlen; q++) {
-    const bool act = q < mylen;
-    const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, act));
-    if (act) {
-      const uint32_t c = (uint32_t)col[rlo + q];
-      uint32_t lo = 0, hi = nruns;                   // last run with start <= c
-      while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (rstart[mid] <= c) lo = mid; else hi = mid;
-      }
-      slot[(size_t)off + lane] = (uint16_t)(roff[lo] + (c - rstart[lo]));
-      sval[(size_t)off + lane] = val[rlo + q];
+  for (int kk = 0; kk < K; kk++) {
+    const int64_t win = (int64_t)blockIdx.x * K + kk;
+    const int64_t wbase = win * DDF_SELL_WIN;
+    const uint32_t wfirst = slice_ptr[win * (DDF_SELL_WIN / 32)];
+    const uint32_t wstored = slice_ptr[(win + 1) * (DDF_SELL_WIN / 32)] - wfirst;
+    // the window's record: values, then slots
+    double* sval = reinterpret_cast<double*>(packed + (size_t)wfirst * 10);
+    uint16_t* slot = reinterpret_cast<uint16_t*>(packed + (size_t)wfirst * 10 + (size_t)wstored * 8);
+    // entries -> jagged slices (same addressing as the row kernels)
+    const int64_t r = wbase + t;                       // sorted position
+    const int64_t i = wbase + perm8[r];
+    const uint32_t mylen = len8[r];
+    const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
+    uint32_t off = slice_ptr[r >> 5] - wfirst;         // entry offset inside the window's record
+    const uint32_t rlo = i < nrows ? rowptr[i] : 0u;
+    {
+      unsigned char* wm = meta + (size_t)win * STAGE_META;
+      if (t == 0) *reinterpret_cast<uint32_t*>(wm) = wstored;
+      wm[16 + t] = perm8[r];
+      wm[16 + DDF_SELL_WIN + t] = (unsigned char)mylen;
+      wm[16 + 2 * DDF_SELL_WIN + t] = (isb && wbase + t < nrows) ? isb[wbase + t] : 0;
     }
-    off += cnt;
+    for (uint32_t q = 0; q < maxlen; q++) {
+      const bool act = q < mylen;
+      const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, act));
+      if (act) {
+        const uint32_t c = (uint32_t)col[rlo + q];
+        uint32_t lo = 0, hi = nruns;                   // last run with start <= c
+        while (hi - lo > 1) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (rstart[mid] <= c) lo = mid; else hi = mid;
+        }
+        slot[(size_t)off + lane] = (uint16_t)(roff[lo] + (c - rstart[lo]));
+        sval[(size_t)off + lane] = val[rlo + q];
+      }
+      off += cnt;
+    }
   }
 }
 
 static int stage_build(ddf_ctx* ctx, const uint32_t* rowptr, const int32_t* col, const double* val, int64_t nrows,
-                       int64_t nnz, const uint8_t* isb, StageBufs& out) {
+                       int64_t nnz, const uint8_t* isb, int K, StageBufs& out) {
   out.release();
-  const int64_t nwin = (nrows + DDF_SELL_WIN - 1) / DDF_SELL_WIN;
+  if (K < 1 || K > 4) DDF_FAIL("stage_build: 1 <= K <= 4");
+  const int64_t nwin_real = (nrows + DDF_SELL_WIN - 1) / DDF_SELL_WIN;
+  const int64_t ngroups = (nwin_real + K - 1) / K;
+  const int64_t nwin = ngroups * K;                     // windows incl. the empty ones that complete the last group
   const int64_t nslices = nwin * (DDF_SELL_WIN / 32);
   if (nwin == 0 || nnz == 0) return 0;
   DevBuf<uint32_t> tot, status;
   DevBuf<uint8_t> temp;
   DDF_CHECK(tot.alloc(ctx, nslices + 1));
-  DDF_CHECK(status.alloc(ctx, 2));
+  DDF_CHECK(status.alloc(ctx, 4));
   DDF_CHECK(out.ptr.alloc(ctx, nslices + 1));
   DDF_CHECK(out.perm8.alloc(ctx, nwin * DDF_SELL_WIN));
   DDF_CHECK(out.len8.alloc(ctx, nwin * DDF_SELL_WIN));
-  DDF_CUDA(cudaMemsetAsync(status.p, 0, 8, ctx->stream));
+  DDF_CUDA(cudaMemsetAsync(status.p, 0, 16, ctx->stream));
   DDF_CUDA(cudaMemsetAsync(tot.p + nslices, 0, 4, ctx->stream));
   k_stage_sort<<<(int)nwin, DDF_SELL_WIN, 0, ctx->stream>>>(rowptr, nrows, out.perm8.p, out.len8.p, tot.p, status.p);
   DDF_LAUNCH_CHECK(ctx);
@@ -206,27 +219,30 @@ static int stage_build(ddf_ctx* ctx, const uint32_t* rowptr, const int32_t* col,
   DDF_CHECK(temp.alloc(ctx, tb));
   DDF_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, tot.p, out.ptr.p, nslices + 1, ctx->stream));
   ctx->launches++;
-  uint32_t st = 0, stv[2] = {0, 0}, total = 0;
-  DDF_CUDA(cudaMemcpyAsync(stv, status.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  uint32_t stv[4] = {0, 0, 0, 0}, total = 0;
+  DDF_CUDA(cudaMemcpyAsync(stv, status.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
   DDF_CUDA(cudaMemcpyAsync(&total, out.ptr.p + nslices, 4, cudaMemcpyDeviceToHost, ctx->stream));
   DDF_CUDA(cudaStreamSynchronize(ctx->stream));
   if (stv[0] == 0xFFFFFFFFu) { out.release(); return 0; }     // a row longer than 255 entries
-  out.max_entries = stv[1];
   out.entries = total;
-  DDF_CHECK(out.tab.alloc(ctx, nwin * STAGE_TAB));
+  DDF_CHECK(out.tab.alloc(ctx, ngroups * STAGE_TAB));
   DDF_CHECK(out.packed.alloc(ctx, (size_t)total * 10 + 64));
   DDF_CHECK(out.meta.alloc(ctx, (size_t)nwin * STAGE_META));
   // padding entries are never read by a row, but they travel in the bulk copies: keep them defined
   DDF_CUDA(cudaMemsetAsync(out.packed.p, 0, (size_t)total * 10 + 64, ctx->stream));
   DDF_CUDA(cudaMemsetAsync(out.meta.p, 0, (size_t)nwin * STAGE_META, ctx->stream));
   const size_t smem = STAGE_KEYS * 4;
-  k_stage_fill<<<(int)nwin, DDF_SELL_WIN, smem, ctx->stream>>>(rowptr, col, val, nrows, out.perm8.p, out.len8.p, out.ptr.p,
-                                                              isb, out.tab.p, out.packed.p, out.meta.p, status.p);
+  k_stage_fill<<<(int)ngroups, DDF_SELL_WIN, smem, ctx->stream>>>(rowptr, col, val, nrows, K, out.perm8.p, out.len8.p,
+                                                                 out.ptr.p, isb, out.tab.p, out.packed.p, out.meta.p,
+                                                                 status.p);
   DDF_LAUNCH_CHECK(ctx);
-  DDF_CUDA(cudaMemcpyAsync(&st, status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaMemcpyAsync(stv, status.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
   DDF_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (st == 0xFFFFFFFFu) { out.release(); return 0; }     // some window does not fit the staging limits
-  out.max_slots = st;
+  if (stv[0] == 0xFFFFFFFFu) { out.release(); return 0; }     // some group does not fit the staging limits
+  out.max_slots = stv[0];
+  out.max_entries = stv[2];                                   // of a group of K windows
+  out.K = K;
+  out.ngroups = ngroups;
   out.nnz = nnz;
   out.ok = true;
   return 0;

@@ -31,6 +31,34 @@ int ddf_mesh_require_star(ddf_mesh* m, int R);   // ops.cu
 int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n, double* out);   // core.cu
 
 int g_tune_wave = 0;
+// windows per pipeline group the builder tries first for short rows (2D meshes); 0 = SELL with 16-bit offsets
+#define DDF_STAGE_K_SHORT 2
+
+#define PIPE_GROUP 256          // threads of one consumer group (= rows of a window)
+#define PIPE_MAX_STAGES 6
+// geometry of one stage of the persistent pipeline (k_rows_pipe below)
+struct PipeGeom {
+  uint32_t o_ent, o_v, o_u, o_meta, stage_bytes;   // byte offsets inside a stage (x16): entries records, v, u, meta
+  int nstages;
+  int K;                                           // windows per group (= per stage)
+  int64_t nrows;
+};
+
+static int pipe_geometry(const ddf_mesh* m, PipeGeom* g) {
+  const StageBufs& sb = m->lstage;
+  auto up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
+  g->K = sb.K;
+  g->o_ent = up(sb.max_slots * 8u, 16);
+  g->o_v = g->o_ent + up(sb.max_entries * 10u, 16);
+  g->o_u = g->o_v + (uint32_t)sb.K * DDF_SELL_WIN * 8;
+  g->o_meta = g->o_u + (uint32_t)sb.K * DDF_SELL_WIN * 8;
+  g->stage_bytes = up(g->o_meta + (uint32_t)sb.K * STAGE_META, 128);
+  const uint32_t budget = 227u * 1024u - 4096u;
+  g->nstages = (int)(budget / g->stage_bytes);
+  if (g->nstages > PIPE_MAX_STAGES) g->nstages = PIPE_MAX_STAGES;
+  g->nrows = m->n[0];
+  return g->nstages >= 2;
+}
 
 // pass 1 (count) / pass 2 (fill) of the assembly of L rows
 template <bool FILL>
@@ -124,11 +152,19 @@ int ddf_mesh_require_wave(ddf_mesh* m) {
   //    banded enough, else 32-bit (12 B per entry).  Short rows (2D meshes: 7 entries) are faster here
   //    (profiles/r01_tuning.md).  Tuning bit 2048 forces 32-bit indices.
   const bool long_rows = m->adj_nnz >= 10 * nv;
-  if (!(g_tune_wave & 16) && (long_rows || (g_tune_wave & 4096))) {
-    DDF_CHECK(stage_build(ctx, m->adj_ptr.p, m->adj_nbr.p, m->adj_l.p, nv, m->adj_nnz, m->isbnd[0].p, m->lstage));
-    if (m->lstage.ok) {
-      m->has_wave = true;
-      return 0;
+  // tuning bits 13-14: windows per pipeline group for SHORT rows (0 = use SELL); bit 4096 = legacy "force staged, K = 1"
+  const int k_short = (g_tune_wave & 4096) ? 1 : ((g_tune_wave >> 13) & 3) ? ((g_tune_wave >> 13) & 3) + 1 : DDF_STAGE_K_SHORT;
+  if (!(g_tune_wave & 16) && (long_rows || k_short > 0)) {
+    for (int K = long_rows ? 1 : k_short; K >= 1; K--) {
+      DDF_CHECK(stage_build(ctx, m->adj_ptr.p, m->adj_nbr.p, m->adj_l.p, nv, m->adj_nnz, m->isbnd[0].p, K, m->lstage));
+      if (m->lstage.ok && K > 1) {                 // a group must leave room for >= 3 stages
+        PipeGeom g;
+        if (!pipe_geometry(m, &g) || g.nstages < 3) m->lstage.release();
+      }
+      if (m->lstage.ok) {
+        m->has_wave = true;
+        return 0;
+      }
     }
   }
   DDF_CHECK(sell_build(ctx, m->adj_ptr.p, reinterpret_cast<const uint32_t*>(m->adj_nbr.p), m->adj_l.p, nv, m->lsell,
@@ -361,13 +397,6 @@ k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* _
 // boundary mask and the perm/len bytes.  Eight consumer warps compute a window out of shared
 // memory only and release the stage through its "empty" mbarrier.  No register ever waits on
 // HBM, so the bytes in flight per SM are (stages - 1) x ~50 KB regardless of occupancy.
-struct PipeGeom {
-  uint32_t o_ent, o_v, o_u, o_meta, stage_bytes;   // byte offsets inside a stage (x16): entries record, v, u, meta
-  int nstages;
-  int64_t nrows;
-};
-#define PIPE_GROUP 256          // threads of one consumer group (= rows of a window)
-#define PIPE_MAX_STAGES 6
 
 template <int MODE, int NG>
 __global__ void __launch_bounds__(NG * PIPE_GROUP + 32, 1)
@@ -425,11 +454,13 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
       const uint32_t j = (uint32_t)(it / g.nstages);
       if (j > 0) stage_wait(&empty[s], (j - 1) & 1u);
       unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
-      const int64_t r0 = win * DDF_SELL_WIN;
-      const uint32_t nr = (uint32_t)min((int64_t)DDF_SELL_WIN, g.nrows - r0);
+      // `win` counts GROUPS of K consecutive 256-row windows here (K = 1 on 3D meshes)
+      const int64_t r0 = win * g.K * DDF_SELL_WIN;
+      const uint32_t nr = (uint32_t)min((int64_t)g.K * DDF_SELL_WIN, g.nrows - r0);
       const uint32_t vbytes = ((nr + 1u) & ~1u) * 8u;
-      // requests per window: the runs of u, ONE entries record, ONE meta record, v (or udot) and u
-      uint32_t tx = total * 8u + nent * 10u + STAGE_META;
+      const uint32_t mbytes = (uint32_t)g.K * STAGE_META;
+      // requests per group: the runs of u, ONE range of entries records, ONE range of meta records, v (or udot), u
+      uint32_t tx = total * 8u + nent * 10u + mbytes;
       if (MODE == 1) tx += vbytes;
       if (MODE == 2) tx += 2u * vbytes;
       if (lane == 0) {
@@ -439,7 +470,7 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
       __syncwarp();
       if (lane < nruns) bulk_g2s(sb + (size_t)off * 8, a.u + start, (end - off) * 8u, &full[s], pol_keep);
       if (lane == 31 && nent) bulk_g2s(sb + g.o_ent, packed + (size_t)e0 * 10, nent * 10u, &full[s], pol_stream);
-      if (lane == 30) bulk_g2s(sb + g.o_meta, meta + win * STAGE_META, STAGE_META, &full[s], pol_stream);
+      if (lane == 30) bulk_g2s(sb + g.o_meta, meta + win * g.K * STAGE_META, mbytes, &full[s], pol_stream);
       if (lane == 29 && MODE != 0) {
         bulk_g2s(sb + g.o_v, (MODE == 1 ? a.udot : a.out0) + r0, vbytes, &full[s], pol_stream);
         if (MODE == 2) bulk_g2s(sb + g.o_u, a.u + r0, vbytes, &full[s], pol_keep);
@@ -463,46 +494,51 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
       stage_wait(&full[s], j & 1u);
       const unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
       const double* stage = reinterpret_cast<const double*>(sb);
-      const unsigned char* metaS = sb + g.o_meta;
-      const uint32_t nentS = *reinterpret_cast<const uint32_t*>(metaS);
-      const double* valS = reinterpret_cast<const double*>(sb + g.o_ent);
-      const uint16_t* slotS = reinterpret_cast<const uint16_t*>(sb + g.o_ent + (size_t)nentS * 8);
-      const uint8_t* lenS = metaS + 16 + DDF_SELL_WIN;
-      const uint32_t mylen = lenS[gtid];
-      const uint32_t p = (metaS + 16)[gtid];
-      // entry offset of this slice inside the window = lengths of the rows of the earlier slices
-      uint32_t part = 0;
-      for (uint32_t k = lane; k < 32u * gwarp; k += 32u) part += lenS[k];
+      uint32_t rec = 0;                                        // byte offset of window kk's record in the stage
+      for (int kk = 0; kk < g.K; kk++) {
+        const unsigned char* metaS = sb + g.o_meta + kk * STAGE_META;
+        const uint32_t nentS = *reinterpret_cast<const uint32_t*>(metaS);
+        const double* valS = reinterpret_cast<const double*>(sb + g.o_ent + rec);
+        const uint16_t* slotS = reinterpret_cast<const uint16_t*>(sb + g.o_ent + rec + (size_t)nentS * 8);
+        rec += nentS * 10u;
+        const uint8_t* lenS = metaS + 16 + DDF_SELL_WIN;
+        const uint32_t mylen = lenS[gtid];
+        const uint32_t p = (metaS + 16)[gtid];
+        // entry offset of this slice inside the window = lengths of the rows of the earlier slices
+        uint32_t part = 0;
+        for (uint32_t k = lane; k < 32u * gwarp; k += 32u) part += lenS[k];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
-      uint32_t e = part + lane, q = 0;
-      double acc = 0.0;
-      while (q < maxlen) {                                                     // segments of constant active-lane count
-        const uint32_t nact = __popc(__ballot_sync(0xffffffffu, q < mylen));
-        const uint32_t qend = __shfl_sync(0xffffffffu, mylen, nact - 1);
-        if (lane < nact) {
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
+        uint32_t e = part + lane, q = 0;
+        double acc = 0.0;
+        while (q < maxlen) {                                                   // segments of constant active-lane count
+          const uint32_t nact = __popc(__ballot_sync(0xffffffffu, q < mylen));
+          const uint32_t qend = __shfl_sync(0xffffffffu, mylen, nact - 1);
+          if (lane < nact) {
 #pragma unroll 4
-          for (uint32_t k = q; k < qend; k++, e += nact) acc = __dadd_rn(acc, __dmul_rn(valS[e], stage[slotS[e]]));
+            for (uint32_t k = q; k < qend; k++, e += nact) acc = __dadd_rn(acc, __dmul_rn(valS[e], stage[slotS[e]]));
+          }
+          q = qend;
         }
-        q = qend;
-      }
-      const int64_t i = win * DDF_SELL_WIN + p;
-      if (i >= a.row0 && i < a.row1) {
-        if (MODE == 0) {
-          st_hint_f64(a.out0 + i, acc, pol_stream);
-        } else {
-          const double m = (metaS + 16 + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
-          const double e0 = reinterpret_cast<const double*>(sb + g.o_v)[p];
-          if (MODE == 1) {
-            a.out0[i] = __dmul_rn(m, e0);
-            a.out1[i] = __dmul_rn(m, acc);
+        const uint32_t pl = (uint32_t)kk * DDF_SELL_WIN + p;                  // row offset inside the group
+        const int64_t i = win * g.K * DDF_SELL_WIN + pl;
+        if (i >= a.row0 && i < a.row1) {
+          if (MODE == 0) {
+            st_hint_f64(a.out0 + i, acc, pol_stream);
           } else {
-            const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, acc)));
-            a.out0[i] = vn;
-            const double w = __dadd_rn(reinterpret_cast<const double*>(sb + g.o_u)[p], __dmul_rn(a.dt, __dmul_rn(m, vn)));
-            a.out1[i] = w;
-            peer_store(a, i, w);
+            const double m = (metaS + 16 + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
+            const double e0 = reinterpret_cast<const double*>(sb + g.o_v)[pl];
+            if (MODE == 1) {
+              a.out0[i] = __dmul_rn(m, e0);
+              a.out1[i] = __dmul_rn(m, acc);
+            } else {
+              const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, acc)));
+              a.out0[i] = vn;
+              const double w = __dadd_rn(reinterpret_cast<const double*>(sb + g.o_u)[pl], __dmul_rn(a.dt, __dmul_rn(m, vn)));
+              a.out1[i] = w;
+              peer_store(a, i, w);
+            }
           }
         }
       }
@@ -512,20 +548,6 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
   }
 }
 
-static int pipe_geometry(const ddf_mesh* m, PipeGeom* g) {
-  const StageBufs& sb = m->lstage;
-  auto up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
-  g->o_ent = up(sb.max_slots * 8u, 16);
-  g->o_v = g->o_ent + up(sb.max_entries * 10u, 16);
-  g->o_u = g->o_v + DDF_SELL_WIN * 8;
-  g->o_meta = g->o_u + DDF_SELL_WIN * 8;
-  g->stage_bytes = up(g->o_meta + STAGE_META, 128);
-  const uint32_t budget = 227u * 1024u - 4096u;
-  g->nstages = (int)(budget / g->stage_bytes);
-  if (g->nstages > PIPE_MAX_STAGES) g->nstages = PIPE_MAX_STAGES;
-  g->nrows = m->n[0];
-  return g->nstages >= 2;
-}
 
 // variant 2/3: warp-cooperative row streaming through shared memory (kept for A/B timing)
 #define DDF_ROW_CAP 512       // products staged per warp and chunk (4 KB)
@@ -590,14 +612,19 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
     if (w1 - w0 > 0x7fffffffLL) DDF_FAIL("grid too large");
     const StageBufs& sb = m->lstage;
     PipeGeom g;
-    if (!(g_tune_wave & 128) && pipe_geometry(m, &g) && w1 - w0 >= 4) {       // persistent TMA pipeline
+    // groups of K windows: the pipeline is the only kernel that understands K > 1
+    const int64_t gw = (int64_t)sb.K * DDF_SELL_WIN;
+    const int64_t g0 = a.row0 / gw, g1 = (a.row1 + gw - 1) / gw;
+    const bool fits = pipe_geometry(m, &g);
+    if (sb.K > 1 && !fits) DDF_FAIL("staged rows: a group of %d windows does not fit the shared-memory ring", sb.K);
+    if (sb.K > 1 || (!(g_tune_wave & 128) && fits && w1 - w0 >= 4)) {          // persistent TMA pipeline
       const size_t smem_p = (size_t)g.nstages * g.stage_bytes;
-      const int grid = (int)std::min<int64_t>(m->ctx->sm_count, w1 - w0);
+      const int grid = (int)std::min<int64_t>(m->ctx->sm_count, g1 - g0);
       const int ng = (g_tune_wave >> 8) & 3;                     // A/B knob: consumer groups per block
       static bool said = false;
       if (!said && getenv("DDF_DEBUG")) {
-        fprintf(stderr, "[ddf] k_rows_pipe: %d stages x %u B (slots %u, entries %u), grid %d\n", g.nstages, g.stage_bytes,
-                sb.max_slots, sb.max_entries, grid);
+        fprintf(stderr, "[ddf] k_rows_pipe: %d stages x %u B (K %d, slots %u, entries %u), grid %d\n", g.nstages,
+                g.stage_bytes, sb.K, sb.max_slots, sb.max_entries, grid);
         said = true;
       }
 #define DDF_PIPE_LAUNCH(NGV)                                                                                        \
@@ -608,7 +635,7 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
       attr_p = smem_p;                                                                                              \
     }                                                                                                               \
     k_rows_pipe<MODE, NGV><<<grid, NGV * PIPE_GROUP + 32, smem_p, stream>>>(a, sb.tab.p, sb.packed.p, sb.meta.p,    \
-                                                                           w0, w1, g);                               \
+                                                                           g0, g1, g);                               \
   } while (0)
       if (ng == 1) DDF_PIPE_LAUNCH(1);
       else if (ng == 3) DDF_PIPE_LAUNCH(3);

@@ -571,14 +571,15 @@ def test_wave_pipeline_repeatable(ddf, ctx):
 
 
 def test_wave_row_formats_2d(ddf, ctx):
-    """2D mesh (7 entries per row): SELL with 16-bit column offsets (default), 32-bit indices (tuning 2048), staged
-    rows forced (4096) and CSR (17) all reproduce the oracle bit for bit."""
-    n = 40
+    """2D mesh (7 entries per row): staged rows in groups of 2 windows per pipeline stage (default), staged with one
+    window per stage (tuning 4096), SELL with 16-bit column offsets (16), with 32-bit indices (16|2048) and the CSR
+    kernel (17) all reproduce the oracle bit for bit."""
+    n = 48
     om = o.large_hypercube_manifold(2, (n, n))
     rng = np.random.default_rng(22)
     u0 = rng.standard_normal(om.nsimplices(0))
     v0 = rng.standard_normal(om.nsimplices(0))
-    want = {0: "sell", 2048: "sell", 4096: "staged", 17: "sell"}     # 17: SELL storage, CSR thread-per-row kernel
+    want = {0: "staged", 4096: "staged", 16: "sell", 16 | 2048: "sell", 17: "sell"}   # 17: SELL storage, CSR kernel
     for tune, fmt in want.items():
         ddf._lib.call("ddf_set_tuning", b"wave", tune)
         try:
@@ -674,7 +675,7 @@ def test_config3_wave_2d_full_size(ddf, ctx):
     n = 2048
     m = ddf.large_hypercube_manifold(2, (n, n), ctx=ctx)
     assert [m.nsimplices(R) for R in range(3)] == [(n + 1) ** 2, 3 * n * n + 2 * n, 2 * n * n]
-    assert ddf.wave_format(m) == "sell"          # 7 entries per row: explicit 16-bit offsets beat the TMA pipeline
+    assert ddf.wave_format(m) == "staged"        # short rows: two windows per pipeline stage
     u0 = ddf.sample(m, "wave")
     u1, v1 = u0.copy(), ddf.Fun(m, ddf.Pr, 0)
     u2, v2 = u0 * 8.0, ddf.Fun(m, ddf.Pr, 0)
