@@ -801,3 +801,46 @@ def test_write_vtu_roundtrip(ddf, ctx, tmp_path):
     assert set(arrays["types"].text.split()) == {"10"}
     assert np.array_equal(np.array(arrays["u"].text.split(), dtype=float), u.values)
     assert np.array_equal(np.array(arrays["vol"].text.split(), dtype=float), vol.values)
+
+
+@pytest.mark.parametrize("D,npts,seed", [(2, 400, 0), (2, 3000, 1), (3, 300, 2), (3, 2500, 3)])
+def test_random_delaunay_meshes(ddf, ctx, D, npts, seed):
+    """Irregular input: the Delaunay triangulation of random points (vertex degrees 3..40, no numbering locality,
+    ragged row lengths, boundary faces everywhere).  Assembly, every d_k / boundary apply, the Hodge stars, the
+    assembled Laplacian, its apply and the fused wave step must still match the oracle bit for bit (the oracle is
+    given the device geometry: slivers make circumcentres ill-conditioned, which is compared on the regular zoo)."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(100 + seed)
+    pts = rng.random((npts, D))
+    simp = np.asarray(Delaunay(pts).simplices, dtype=np.int64)
+    used = np.unique(simp)
+    assert len(used) == npts                       # Qhull keeps every point of a random cloud
+    om = o.build_manifold("delaunay", simp, pts)
+    dm = ddf.Manifold.from_simplices("delaunay", simp, pts, ctx=ctx)
+    for R in range(1, D + 1):
+        cp, rv, nz = dm.get_boundaries_csc(R)
+        ocp, orv, onz = o.to_julia_csc(om.boundaries[R])
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz), R
+    om = with_device_geometry(om, dm)
+    for k in range(D):
+        x = rng.standard_normal(om.nsimplices(k))
+        y = (ddf.deriv(ddf.Pr, k, dm) * ddf.Fun(dm, ddf.Pr, k, x)).values
+        assert np.array_equal(y, o.apply_deriv(o.Pr, k, om, x)), ("d", k)
+        z = rng.standard_normal(om.nsimplices(k + 1))
+        w = (ddf.deriv(ddf.Dl, k + 1, dm) * ddf.Fun(dm, ddf.Dl, k + 1, z)).values      # the matrix d_{k+1} by rows
+        assert np.array_equal(w, o.apply_deriv(o.Dl, k + 1, om, z)), ("dual d", k + 1)
+    for R in range(D + 1):
+        x = rng.standard_normal(om.nsimplices(R))
+        assert np.array_equal((ddf.hodge(ddf.Pr, R, dm) * ddf.Fun(dm, ddf.Pr, R, x)).values,
+                              o.hodge_diag(o.Pr, R, om) * x), ("hodge", R)
+    L = o.laplace(o.Pr, 0, om)
+    A = ddf.laplace(ddf.Pr, 0, dm).to_csc()
+    assert np.array_equal(A.indptr, L.indptr) and np.array_equal(A.indices, L.indices) and np.array_equal(A.data, L.data)
+    u0 = rng.standard_normal(npts)
+    assert np.array_equal((ddf.laplace(ddf.Pr, 0, dm) * ddf.Fun(dm, ddf.Pr, 0, u0)).values, o.spmv_csc(L, u0))
+    v0 = rng.standard_normal(npts)
+    dt = 1e-3
+    u, v = ddf.Fun(dm, ddf.Pr, 0, u0), ddf.Fun(dm, ddf.Pr, 0, v0)
+    ddf.wave_leapfrog(dm, u, v, dt, 4)
+    ou, ov = o.wave_leapfrog(om, u0, v0, dt, 4)
+    assert np.array_equal(u.values, ou) and np.array_equal(v.values, ov)
