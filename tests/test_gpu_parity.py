@@ -844,3 +844,38 @@ def test_random_delaunay_meshes(ddf, ctx, D, npts, seed):
     ddf.wave_leapfrog(dm, u, v, dt, 4)
     ou, ov = o.wave_leapfrog(om, u0, v0, dt, 4)
     assert np.array_equal(u.values, ou) and np.array_equal(v.values, ov)
+
+
+@pytest.mark.parametrize("kind", ["simplex4", "simplex5", "kuhn4n2", "kuhn5n2"])
+def test_topology_in_higher_dimensions(ddf, ctx, kind):
+    """The reference's topology tests run up to D = 5 (test/test-manifolds.jl).  Assembly (128-bit face keys for the
+    wider tuples), every boundary matrix, d_k applies through the W = 5, 6 fixed-width kernels and d d = 0 on the
+    4- and 5-dimensional simplex and Kuhn cube; geometry is 2D/3D only (DDF_MAXC)."""
+    D = int(kind[-3]) if kind.startswith("kuhn") else int(kind[-1])
+    if kind.startswith("simplex"):
+        simp = np.arange(D + 1, dtype=np.int64)[None, :]
+        coords = o.regular_simplex(D)
+    else:
+        simp, coords, _ = o.large_hypercube_tables(D, (2,) * D)
+    V = coords.shape[0]
+    om = o.manifold_from_simplices(kind, simp, V, C=D)          # dummy coordinates: topology only
+    dm = ddf.Manifold.from_simplices(kind, simp, np.ascontiguousarray(om.coords), ctx=ctx)
+    assert [dm.nsimplices(R) for R in range(D + 1)] == [om.nsimplices(R) for R in range(D + 1)]
+    for R in range(1, D + 1):
+        cp, rv, nz = dm.get_boundaries_csc(R)
+        ocp, orv, onz = o.to_julia_csc(om.boundaries[R])
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz), R
+        assert np.array_equal(dm.get_simplices(R), om.simplices[R]), R
+    rng = np.random.default_rng(7)
+    prev = None
+    for k in range(D):
+        x = rng.integers(-9, 9, om.nsimplices(k)).astype(np.float64)
+        d = ddf.deriv(ddf.Pr, k, dm)
+        y = d * ddf.Fun(dm, ddf.Pr, k, x)
+        assert np.array_equal(y.values, o.apply_deriv(o.Pr, k, om, x)), k
+        if prev is not None:
+            assert (d * prev).norm(np.inf) == 0                       # d_k d_{k-1} x = 0 exactly
+        prev = y
+        z = rng.integers(-9, 9, om.nsimplices(k + 1)).astype(np.float64)
+        w = (ddf.boundary(ddf.Pr, k + 1, dm) * ddf.Fun(dm, ddf.Pr, k + 1, z)).values
+        assert np.array_equal(w, om.boundaries[k + 1].astype(np.float64) @ z), ("boundary", k + 1)
