@@ -179,9 +179,10 @@ def run_reference(args):
     c_oracle.load()
     single = cpu_reference_pass(args.n_ref, seconds_target=min(60.0, 2.0 * max(args.steps, 1)))
     omp = cpu_reference_pass(args.n_ref, seconds_target=min(30.0, 1.0 * max(args.steps, 1)), threads_omp=True)
-    # Julia's sparse mul! is single-threaded, so the 1-thread loop is the faithful restatement; the line reports
-    # whichever of {1 thread, row-parallel OpenMP on all host cores} is FASTER on this box, and keeps both
-    res = omp if omp["value"] > single["value"] else single
+    # Julia's SparseArrays mul! is single-threaded whatever JULIA_NUM_THREADS says: one thread IS all the
+    # host threads the reference's own implementation can use, so the line's value is the 1-thread loop.  A
+    # row-parallel OpenMP variant on every host core is timed beside it as a cross-check (not what DDF.jl does).
+    res = single
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -190,8 +191,8 @@ def run_reference(args):
                        "note": "DDF.jl is Julia; no julia binary in the image -> C restatement of its SparseArrays "
                                "mul! loops on the reference's storage (Int64 CSC, Int8 values)"},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "single_thread": {"value": single["value"], "cores": 1},
-            "omp_allcores": {"value": omp["value"], "cores": omp["cores"]},
+            "omp_allcores_crosscheck": {"value": omp["value"], "cores": omp["cores"],
+                                        "note": "row-parallel OpenMP restatement; the reference itself cannot thread this path"},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print_json(line)
 
