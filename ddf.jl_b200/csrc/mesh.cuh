@@ -40,7 +40,7 @@ struct StageBufs {
   // per window ONE contiguous record: [values f64 x nent][slots u16 x nent], nent = the window's stored entries
   // (a multiple of 8), at byte offset 10 * (first entry): one TMA bulk copy per window
   DevBuf<unsigned char> packed;
-  // per window 800 B: {u32 nent, pad to 16} | perm8[256] | len8[256] | boundary mask by row offset [256] | pad
+  // per window 816 B: {u32 nent, pad to 16, u32 slice offset x 8} | perm8[256] | len8[256] | boundary mask by row offset [256]
   DevBuf<unsigned char> meta;
   uint32_t max_slots = 0;   // largest staging buffer of any window (Float64 elements)
   uint32_t max_entries = 0; // most stored entries of any group of K windows (incl. their <= 7 padding entries each)

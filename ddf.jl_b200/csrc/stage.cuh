@@ -31,7 +31,8 @@
 #define STAGE_TAB (4 + 2 * STAGE_RMAX)    // table words per window (256 B: one 16-byte-aligned bulk copy)
 #define STAGE_KEYS 8192                  // most entries of a 256-row window the builder sorts
 #define STAGE_GAP 7u                     // untouched columns a run may absorb
-#define STAGE_META 800                   // bytes of the per-window meta record
+#define STAGE_META 816                   // bytes of the per-window meta record
+#define STAGE_META_HDR 48                // {u32 nent, 3 pad, u32 slice offset x 8} then perm8, len8, mask
 #define STAGE_MAX_SLOTS 6080             // 47.5 KB of staged Float64 per block (static shared-memory limit)
 
 // ---- pass A: sort the rows of a window by decreasing length (stable), slice entry totals
@@ -172,9 +173,11 @@ k_stage_fill(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     {
       unsigned char* wm = meta + (size_t)win * STAGE_META;
       if (t == 0) *reinterpret_cast<uint32_t*>(wm) = wstored;
-      wm[16 + t] = perm8[r];
-      wm[16 + DDF_SELL_WIN + t] = (unsigned char)mylen;
-      wm[16 + 2 * DDF_SELL_WIN + t] = (isb && wbase + t < nrows) ? isb[wbase + t] : 0;
+      // entry offset of every slice inside the window's record (header words 4..11)
+      if (t < DDF_SELL_WIN / 32) reinterpret_cast<uint32_t*>(wm)[4 + t] = slice_ptr[win * (DDF_SELL_WIN / 32) + t] - wfirst;
+      wm[STAGE_META_HDR + t] = perm8[r];
+      wm[STAGE_META_HDR + DDF_SELL_WIN + t] = (unsigned char)mylen;
+      wm[STAGE_META_HDR + 2 * DDF_SELL_WIN + t] = (isb && wbase + t < nrows) ? isb[wbase + t] : 0;
     }
     for (uint32_t q = 0; q < maxlen; q++) {
       const bool act = q < mylen;

@@ -398,6 +398,21 @@ k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* _
 // memory only and release the stage through its "empty" mbarrier.  No register ever waits on
 // HBM, so the bytes in flight per SM are (stages - 1) x ~50 KB regardless of occupancy.
 
+#ifdef DDF_PIPE_TRACE
+// block 0 records %globaltimer at: producer armed stage (0), consumer saw data (1), consumer released stage (2)
+__device__ unsigned long long g_pipe_trace[5 * 1024];
+#define PIPE_TRACE(kind, it)                                                        \
+  do {                                                                              \
+    if (blockIdx.x == 0 && (it) < 1024 && (threadIdx.x & 31) == 0) {                \
+      unsigned long long t_;                                                        \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                        \
+      if ((kind) != 0 && (threadIdx.x & 255) != 0) {} else g_pipe_trace[(kind) * 1024 + (it)] = t_; \
+    }                                                                               \
+  } while (0)
+#else
+#define PIPE_TRACE(kind, it)
+#endif
+
 template <int MODE, int NG>
 __global__ void __launch_bounds__(NG * PIPE_GROUP + 32, 1)
 k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __restrict__ packed,
@@ -467,6 +482,7 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(tx) : "memory");
         asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&issued[s])), "r"((uint32_t)it + 1u) : "memory");
       }
+      PIPE_TRACE(0, it);
       __syncwarp();
       if (lane < nruns) bulk_g2s(sb + (size_t)off * 8, a.u + start, (end - off) * 8u, &full[s], pol_keep);
       if (lane == 31 && nent) bulk_g2s(sb + g.o_ent, packed + (size_t)e0 * 10, nent * 10u, &full[s], pol_stream);
@@ -492,6 +508,7 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
         if (seen >= (uint32_t)it + 1u) break;
       }
       stage_wait(&full[s], j & 1u);
+      PIPE_TRACE(1, it);
       const unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
       const double* stage = reinterpret_cast<const double*>(sb);
       uint32_t rec = 0;                                        // byte offset of window kk's record in the stage
@@ -501,17 +518,15 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
         const double* valS = reinterpret_cast<const double*>(sb + g.o_ent + rec);
         const uint16_t* slotS = reinterpret_cast<const uint16_t*>(sb + g.o_ent + rec + (size_t)nentS * 8);
         rec += nentS * 10u;
-        const uint8_t* lenS = metaS + 16 + DDF_SELL_WIN;
+        const uint8_t* lenS = metaS + STAGE_META_HDR + DDF_SELL_WIN;
         const uint32_t mylen = lenS[gtid];
-        const uint32_t p = (metaS + 16)[gtid];
-        // entry offset of this slice inside the window = lengths of the rows of the earlier slices
-        uint32_t part = 0;
-        for (uint32_t k = lane; k < 32u * gwarp; k += 32u) part += lenS[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        const uint32_t p = (metaS + STAGE_META_HDR)[gtid];
+        // entry offset of this slice inside the window's record: precomputed in the meta header
+        const uint32_t part = reinterpret_cast<const uint32_t*>(metaS)[4 + gwarp];
         const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
         uint32_t e = part + lane, q = 0;
         double acc = 0.0;
+        PIPE_TRACE(3, it);
         while (q < maxlen) {                                                   // segments of constant active-lane count
           const uint32_t nact = __popc(__ballot_sync(0xffffffffu, q < mylen));
           const uint32_t qend = __shfl_sync(0xffffffffu, mylen, nact - 1);
@@ -521,13 +536,14 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
           }
           q = qend;
         }
+        PIPE_TRACE(4, it);
         const uint32_t pl = (uint32_t)kk * DDF_SELL_WIN + p;                  // row offset inside the group
         const int64_t i = win * g.K * DDF_SELL_WIN + pl;
         if (i >= a.row0 && i < a.row1) {
           if (MODE == 0) {
             st_hint_f64(a.out0 + i, acc, pol_stream);
           } else {
-            const double m = (metaS + 16 + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
+            const double m = (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
             const double e0 = reinterpret_cast<const double*>(sb + g.o_v)[pl];
             if (MODE == 1) {
               a.out0[i] = __dmul_rn(m, e0);
@@ -543,10 +559,17 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
         }
       }
       __syncwarp();
+      PIPE_TRACE(2, it);
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
     }
   }
 }
+
+#ifdef DDF_PIPE_TRACE
+extern "C" __attribute__((visibility("default"))) int ddf_debug_pipe_trace(unsigned long long* out /* 3*1024 */) {
+  return cudaMemcpyFromSymbol(out, g_pipe_trace, sizeof(unsigned long long) * 5 * 1024) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 
 // variant 2/3: warp-cooperative row streaming through shared memory (kept for A/B timing)
