@@ -355,6 +355,40 @@ def run_b200(args):
                   "format_bytes": fmt2, "GBps": alg2 / ms2 * 1e-6, "frac": alg2 / ms2 * 1e-6 / peak,
                   "row_format": ddf.wave_format(m2), "steps": 200}
         m2.close()
+    # the reference's own integrator on the same mesh: fixed-step Tsit5 (wave.jl:134), 6 right-hand sides per step
+    tsit5 = None
+    if N == 1 and not args.no_extras:
+        ut, vt = ddf.sample(mfd, "wave"), ddf.Fun(mfd, ddf.Pr, 0)
+        ddf.wave_tsit5(mfd, ut, vt, dt, 1)
+        ctx.sync()
+        ctx.tic()
+        ddf.wave_tsit5(mfd, ut, vt, dt, 5)
+        t5 = ctx.toc() / 5
+        tsit5 = {"ms_per_step": t5, "rhs_per_step": 6, "vertex_updates_per_s": cnt[0] / (t5 * 1e-3)}
+        del ut, vt
+    # BASELINE config 2: the Laplacian of examples/poisson.jl on the 2D simplex refined 10x (1,048,576 triangles;
+    # Delaunay through scipy like the reference): y = L rho
+    poisson2d = None
+    if N == 1 and not args.no_extras:
+        t0 = time.time()
+        mp_ = ddf.refined_simplex_manifold(2, 10, ctx=ctx)
+        t_mesh = time.time() - t0
+        rho = ddf.sample(mp_, "poisson_rho")
+        Lp = ddf.laplace(ddf.Pr, 0, mp_)
+        yp = ddf.Fun(mp_, ddf.Pr, 0)
+        Lp.apply(rho, yp)
+        ctx.sync()
+        ctx.tic()
+        for _ in range(200):
+            Lp.apply(rho, yp)
+        msp = ctx.toc() / 200
+        np2 = [mp_.nsimplices(k) for k in range(3)]
+        poisson2d = {"workload": "BASELINE config 2: 2D simplex refined 10x, y = laplace(Pr,0) * rho", "nsimplices": np2,
+                     "ms_per_apply": msp, "vertex_updates_per_s": np2[0] / (msp * 1e-3),
+                     "row_format": ddf.wave_format(mp_), "mesh_build_s": t_mesh,
+                     "note": "38 MB working set: L2-resident, launch-latency bound"}
+        del rho, yp, Lp
+        mp_.close()
     clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
@@ -433,7 +467,8 @@ def run_b200(args):
                          "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(d1_bytes),
                          "ms_per_launch": d1_ms, "frac_of_nominal_8TBs": d1_bytes / d1_ms * 1e-6 / 8000.0},
-            "breakdown": breakdown, "wave": wave, "wave2d": wave2d, "assembly_ms": asm_ms,
+            "breakdown": breakdown, "wave": wave, "wave2d": wave2d, "wave_tsit5": tsit5, "poisson2d": poisson2d,
+            "assembly_ms": asm_ms,
             # assembly of d_3, d_2, d_1 on the device from the tet table (bit-exact; no roofline target):
             # face tuples generated, sorted and ranked per second
             "assembly": {"ms": asm_ms, "tuples": int(sum((R + 1) * cnt[R] for R in (1, 2, 3))),
@@ -470,6 +505,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-wave2d", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the Tsit5 and config-2 Poisson entries")
     ap.add_argument("--strong", action="store_true", help="N > 1: cut ONE n^3 cube into N slabs (default: weak scaling)")
     ap.add_argument("--wave-tune", type=int, default=0, help="ddf_set_tuning('wave', x) for A/B runs (1024: NCCL halo)")
     args = ap.parse_args()
