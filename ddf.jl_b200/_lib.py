@@ -110,6 +110,7 @@ SIGNATURES = {
     "ddf_mesh_set_halo": [_P, _i64, _i64, _i64],
     "ddf_wave_leapfrog_dist": [_P, _P, _P, _f64, _int],
     "ddf_halo_exchange": [_P, _P],
+    "ddf_halo_exchange_k": [_P, _P, _int],
     "ddf_comm_allreduce": [_P, _f64p, _int],
 }
 NON_STATUS = {"ddf_last_error": (C.c_char_p, []), "ddf_version": (_int, [])}

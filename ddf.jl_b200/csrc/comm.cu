@@ -10,6 +10,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <vector>
 
@@ -239,7 +241,9 @@ __global__ void k_halo_signal(unsigned long long* to_lower, unsigned long long* 
   if (to_upper) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(to_upper), "l"(step) : "memory");
 }
 
+void ddf_halo_lists_release(ddf_mesh* m);
 void ddf_halo_release(ddf_mesh* m) {
+  ddf_halo_lists_release(m);
   HaloP2P* hp = (HaloP2P*)m->halo_p2p;
   if (!hp) return;
   if (hp->lo_base) cudaIpcCloseMemHandle(hp->lo_base);
@@ -344,6 +348,193 @@ static int leapfrog_dist_p2p(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt, int
       u->d.p + own_lo - P, has_hi ? HaloP2P::landing(hp->arena.p, 1, (int)(k & 1), P) : nullptr, u->d.p + own_hi, P);
   DDF_LAUNCH_CHECK(ctx);
   return 0;
+}
+
+// =====================================================================================
+// Ghost exchange of a cochain of ANY rank ("rows owned locally need x on ghost
+// k-simplices owned by r+-1").  A k-simplex is owned by the rank that owns its smallest vertex.
+// The slabs of two neighbours overlap in whole cell layers and local vertex ids differ by a
+// constant, so -- local simplex ids being lexicographic ranks of vertex tuples
+// (Manifolds.jl:735-757) -- the simplices of the overlap appear in the SAME relative order on
+// both ranks.  Four index lists per rank R therefore suffice (built once per mesh and R by a
+// flag + stream-compaction pass over the vertex table):
+//   recv_lo  ghosts below:  min vertex in the lower ghost planes
+//   recv_hi  ghosts above:  min vertex in the upper ghost planes
+//   send_lo  what rank-1 holds of mine as ITS upper ghosts: min vertex owned, every vertex inside
+//            rank-1's top planes (its ghost_hi, exchanged once)
+//   send_hi  what rank+1 holds as ITS lower ghosts: min vertex in my last (its ghost_lo) owned planes
+// and the i-th entry of my send list is the i-th entry of the neighbour's recv list.
+// Exchange = gather -> ncclSend/ncclRecv in one group -> scatter.
+// =====================================================================================
+struct HaloLists {
+  struct PerRank {
+    bool built = false;
+    DevBuf<uint32_t> idx[4];           // 0 send_lo, 1 send_hi, 2 recv_lo, 3 recv_hi
+    int64_t cnt[4] = {0, 0, 0, 0};
+    DevBuf<double> buf[4];
+  };
+  PerRank r[DDF_MAXD + 1];
+  int64_t peer_lo_ghost_hi = 0, peer_hi_ghost_lo = 0;
+  bool peers_known = false;
+};
+
+void ddf_halo_lists_release(ddf_mesh* m) {
+  delete (HaloLists*)m->halo_lists;
+  m->halo_lists = nullptr;
+}
+
+// flags[c][i] = 1 when simplex i belongs to list c
+__global__ void k_halo_flags(const int32_t* __restrict__ simp, int N, int64_t n, int64_t P, int64_t nplanes,
+                             int64_t ghost_lo, int64_t ghost_hi, int64_t peer_lo_ghost_hi, int64_t peer_hi_ghost_lo,
+                             uint8_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t vmin = simp ? simp[i * N] : i, vmax = simp ? simp[i * N + N - 1] : i;
+  const int64_t pmin = vmin / P, pmax = vmax / P;
+  const int64_t own_hi = nplanes - ghost_hi;         // first upper ghost plane
+  flags[0 * n + i] = (ghost_lo > 0 && pmin >= ghost_lo && pmax <= ghost_lo + peer_lo_ghost_hi - 1) ? 1 : 0;
+  flags[1 * n + i] = (ghost_hi > 0 && pmin >= own_hi - peer_hi_ghost_lo && pmin < own_hi) ? 1 : 0;
+  flags[2 * n + i] = (ghost_lo > 0 && pmin < ghost_lo) ? 1 : 0;
+  flags[3 * n + i] = (ghost_hi > 0 && pmin >= own_hi) ? 1 : 0;
+}
+__global__ void k_pack_f64(const uint32_t* __restrict__ idx, const double* __restrict__ src, int64_t n, double* __restrict__ dst) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[p] = src[idx[p]];
+}
+__global__ void k_unpack_f64(const uint32_t* __restrict__ idx, const double* __restrict__ src, int64_t n, double* __restrict__ dst) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[idx[p]] = src[p];
+}
+
+static int halo_lists_build(ddf_mesh* m, int R) {
+  ddf_ctx* ctx = m->ctx;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  if (!m->halo_lists) m->halo_lists = new HaloLists();
+  HaloLists* hl = (HaloLists*)m->halo_lists;
+  const int64_t P = m->halo_plane, nplanes = m->n[0] / P;
+  // how many of my planes each neighbour keeps as ghosts (once per mesh)
+  if (!hl->peers_known) {
+    long long* host = reinterpret_cast<long long*>(ctx->red_host);
+    long long* dev = reinterpret_cast<long long*>(ctx->red_dev);
+    host[0] = m->halo_lo;
+    host[1] = m->halo_hi;
+    host[2] = host[3] = host[4] = host[5] = 0;
+    DDF_CUDA(cudaMemcpyAsync(dev, host, 48, cudaMemcpyHostToDevice, ctx->stream));
+    DDF_NCCL(g_nccl.GroupStart());
+    if (m->halo_lo > 0) {
+      DDF_NCCL(g_nccl.Send(dev, 2, ncclInt64, ctx->rank - 1, comm, ctx->stream));
+      DDF_NCCL(g_nccl.Recv(dev + 2, 2, ncclInt64, ctx->rank - 1, comm, ctx->stream));
+    }
+    if (m->halo_hi > 0) {
+      DDF_NCCL(g_nccl.Send(dev, 2, ncclInt64, ctx->rank + 1, comm, ctx->stream));
+      DDF_NCCL(g_nccl.Recv(dev + 4, 2, ncclInt64, ctx->rank + 1, comm, ctx->stream));
+    }
+    DDF_NCCL(g_nccl.GroupEnd());
+    DDF_CUDA(cudaMemcpyAsync(host, dev, 48, cudaMemcpyDeviceToHost, ctx->stream));
+    DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+    hl->peer_lo_ghost_hi = host[3];          // rank-1's ghost_hi
+    hl->peer_hi_ghost_lo = host[4];          // rank+1's ghost_lo
+    hl->peers_known = true;
+  }
+  HaloLists::PerRank& pr = hl->r[R];
+  const int64_t n = m->n[R];
+  DevBuf<uint8_t> flags, temp;
+  DevBuf<int64_t> nsel;
+  DDF_CHECK(flags.alloc(ctx, 4 * (size_t)n));
+  DDF_CHECK(nsel.alloc(ctx, 1));
+  if (n) {
+    int grid;
+    DDF_CHECK(grid_for(n, 256, &grid));
+    k_halo_flags<<<grid, 256, 0, ctx->stream>>>(R >= 1 ? m->simp[R].p : nullptr, R + 1, n, P, nplanes, m->halo_lo, m->halo_hi,
+                                                hl->peer_lo_ghost_hi, hl->peer_hi_ghost_lo, flags.p);
+    DDF_LAUNCH_CHECK(ctx);
+  }
+  for (int c = 0; c < 4; c++) {
+    DevBuf<uint32_t> all;
+    DDF_CHECK(all.alloc(ctx, n));
+    int64_t h = 0;
+    if (n) {
+      cub::CountingInputIterator<uint32_t> it(0);
+      size_t tb = 0;
+      DDF_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, it, flags.p + (size_t)c * n, all.p, nsel.p, n, ctx->stream));
+      DDF_CHECK(temp.alloc(ctx, tb));
+      DDF_CUDA(cub::DeviceSelect::Flagged(temp.p, tb, it, flags.p + (size_t)c * n, all.p, nsel.p, n, ctx->stream));
+      ctx->launches++;
+      DDF_CUDA(cudaMemcpyAsync(&h, nsel.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    pr.cnt[c] = h;
+    DDF_CHECK(pr.idx[c].alloc(ctx, h));
+    DDF_CHECK(pr.buf[c].alloc(ctx, h));
+    if (h) DDF_CUDA(cudaMemcpyAsync(pr.idx[c].p, all.p, h * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  // the neighbour's recv list must be as long as my send list
+  {
+    long long* host = reinterpret_cast<long long*>(ctx->red_host);
+    long long* dev = reinterpret_cast<long long*>(ctx->red_dev);
+    host[0] = pr.cnt[0]; host[1] = pr.cnt[1]; host[2] = host[3] = -1;
+    DDF_CUDA(cudaMemcpyAsync(dev, host, 32, cudaMemcpyHostToDevice, ctx->stream));
+    DDF_NCCL(g_nccl.GroupStart());
+    if (m->halo_lo > 0) {
+      DDF_NCCL(g_nccl.Send(dev, 1, ncclInt64, ctx->rank - 1, comm, ctx->stream));        // my send_lo count
+      DDF_NCCL(g_nccl.Recv(dev + 2, 1, ncclInt64, ctx->rank - 1, comm, ctx->stream));    // its send_hi count
+    }
+    if (m->halo_hi > 0) {
+      DDF_NCCL(g_nccl.Send(dev + 1, 1, ncclInt64, ctx->rank + 1, comm, ctx->stream));    // my send_hi count
+      DDF_NCCL(g_nccl.Recv(dev + 3, 1, ncclInt64, ctx->rank + 1, comm, ctx->stream));    // its send_lo count
+    }
+    DDF_NCCL(g_nccl.GroupEnd());
+    DDF_CUDA(cudaMemcpyAsync(host, dev, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (m->halo_lo > 0 && host[2] != pr.cnt[2])
+      DDF_FAIL("halo_exchange_k(R=%d): rank %d sends %lld simplices, %lld ghosts expected below", R, ctx->rank - 1, host[2], (long long)pr.cnt[2]);
+    if (m->halo_hi > 0 && host[3] != pr.cnt[3])
+      DDF_FAIL("halo_exchange_k(R=%d): rank %d sends %lld simplices, %lld ghosts expected above", R, ctx->rank + 1, host[3], (long long)pr.cnt[3]);
+  }
+  pr.built = true;
+  return 0;
+}
+
+extern "C" int ddf_halo_exchange_k(ddf_mesh* m, ddf_vec* x, int R) {
+  DDF_TRY_BEGIN
+  ddf_ctx* ctx = m->ctx;
+  if (R < 0 || R > m->D) DDF_FAIL("halo_exchange_k: 0 <= R <= D");
+  if (x->n != m->n[R]) DDF_FAIL("halo_exchange_k: vector has length %lld, the mesh has %lld %d-simplices", (long long)x->n, (long long)m->n[R], R);
+  if (ctx->nranks == 1) return 0;
+  if (!ctx->nccl_comm) DDF_FAIL("halo: communicator not initialised (ddf_comm_init)");
+  if (!m->halo_plane) DDF_FAIL("halo: slab not described (ddf_mesh_set_halo)");
+  DDF_CHECK(ddf_mesh_require_assembled(m));
+  DDF_CHECK(ddf_vec_settle(x));
+  if (!m->halo_lists || !((HaloLists*)m->halo_lists)->r[R].built) DDF_CHECK(halo_lists_build(m, R));
+  HaloLists::PerRank& pr = ((HaloLists*)m->halo_lists)->r[R];
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  int grid;
+  for (int c = 0; c < 2; c++)
+    if (pr.cnt[c]) {
+      DDF_CHECK(grid_for(pr.cnt[c], 256, &grid));
+      k_pack_f64<<<grid, 256, 0, ctx->stream>>>(pr.idx[c].p, x->d.p, pr.cnt[c], pr.buf[c].p);
+      DDF_LAUNCH_CHECK(ctx);
+    }
+  DDF_NCCL(g_nccl.GroupStart());
+  if (m->halo_lo > 0) {
+    DDF_NCCL(g_nccl.Send(pr.buf[0].p, pr.cnt[0], ncclDouble, ctx->rank - 1, comm, ctx->stream));
+    DDF_NCCL(g_nccl.Recv(pr.buf[2].p, pr.cnt[2], ncclDouble, ctx->rank - 1, comm, ctx->stream));
+  }
+  if (m->halo_hi > 0) {
+    DDF_NCCL(g_nccl.Send(pr.buf[1].p, pr.cnt[1], ncclDouble, ctx->rank + 1, comm, ctx->stream));
+    DDF_NCCL(g_nccl.Recv(pr.buf[3].p, pr.cnt[3], ncclDouble, ctx->rank + 1, comm, ctx->stream));
+  }
+  DDF_NCCL(g_nccl.GroupEnd());
+  ctx->launches += (m->halo_lo > 0) + (m->halo_hi > 0);
+  for (int c = 2; c < 4; c++)
+    if (pr.cnt[c]) {
+      DDF_CHECK(grid_for(pr.cnt[c], 256, &grid));
+      k_unpack_f64<<<grid, 256, 0, ctx->stream>>>(pr.idx[c].p, pr.buf[c].p, pr.cnt[c], x->d.p);
+      DDF_LAUNCH_CHECK(ctx);
+    }
+  return 0;
+  DDF_TRY_END
 }
 
 extern "C" int ddf_halo_mode(ddf_mesh* m, int* mode) {

@@ -122,6 +122,7 @@ struct ddf_mesh {
   // fused peer-memory halo (comm.cu): arena + peer mappings, the step counter the flags carry;
   // state 0 = untried, 1 = in use, 2 = unavailable (NCCL send/recv is used instead)
   void* halo_p2p = nullptr;
+  void* halo_lists = nullptr;            // per-rank-R pack / unpack index lists of ddf_halo_exchange_k (comm.cu)
   unsigned long long halo_step = 0;
   int halo_p2p_state = 0;
   int halo_last = 0;                     // what the last distributed step used: 1 = peer memory, 2 = NCCL

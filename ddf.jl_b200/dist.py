@@ -112,3 +112,17 @@ def halo_mode(mfd) -> str:
     mode = C.c_int()
     call("ddf_halo_mode", mfd._h, C.byref(mode))
     return ("none", "p2p", "nccl")[mode.value]
+
+
+def halo_exchange(mfd, f):
+    """Fill the ghost entries of the cochain `f` (any rank R) with the owners' values; in place."""
+    from ._lib import call
+    call("ddf_halo_exchange_k", mfd._h, f._h, int(f.R))
+    return f
+
+
+def owned_mask(mfd, slab: "Slab", R: int) -> np.ndarray:
+    """True for the local R-simplices this rank owns (smallest vertex in an owned plane)."""
+    lo, hi = slab.own_rows
+    first = np.arange(mfd.nsimplices(0)) if R == 0 else mfd.get_simplices(R)[:, 0]
+    return (first >= lo) & (first < hi)

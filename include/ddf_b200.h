@@ -229,6 +229,11 @@ int ddf_wave_leapfrog_dist(ddf_mesh* mesh, ddf_vec* u, ddf_vec* v, double dt, in
 int ddf_halo_mode(ddf_mesh* mesh, int* mode);
 /* halo exchange of a vertex cochain alone (fills the ghost planes next to the owned rows) */
 int ddf_halo_exchange(ddf_mesh* mesh, ddf_vec* u);
+/* ghost exchange of a cochain of ANY rank R on a slab mesh: every local R-simplex whose smallest vertex lies in a
+ * ghost plane receives the value held by the rank that owns it (ownership = owner of the smallest vertex).  The
+ * pack / unpack lists are built on the first call per (mesh, R); neighbours find matching entries by position
+ * because local simplex ids are lexicographic ranks and neighbouring slabs differ by a constant vertex shift. */
+int ddf_halo_exchange_k(ddf_mesh* mesh, ddf_vec* x, int R);
 /* sum / max all-reduce of a host scalar across ranks (norms, CFL minimum) */
 int ddf_comm_allreduce(ddf_ctx* ctx, double* value, int op /* 0 sum, 1 max, 2 min */);
 
