@@ -209,3 +209,53 @@ def test_peer_memory_halo_protocol_model():
     for zlo, zhi, u, v in results:
         assert np.array_equal(u, ou[zlo * plane:zhi * plane])
         assert np.array_equal(v, ov[zlo * plane:zhi * plane])
+
+
+def test_rank_k_ghost_lists_match_by_position():
+    """Host model of ddf_halo_exchange_k (csrc/comm.cu): with ownership = owner of the smallest vertex and the
+    four list predicates of k_halo_flags, the i-th simplex of a rank's send list is the i-th simplex of the
+    neighbour's receive list (same GLOBAL vertex tuple) -- because local ids are lexicographic ranks and slabs
+    differ by a constant vertex shift.  Checked for every rank R on 3 slabs of a 3D and a 2D Kuhn mesh."""
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import ddf_oracle as o
+    from importlib import import_module
+    dd = import_module("ddf.jl_b200.dist")
+    for D, nxy, nz, world in ((3, 2, 14, 3), (2, 4, 12, 3)):
+        plane = (nxy + 1) ** (D - 1)
+        slabs = dd.partition_slabs(nz, world, plane)
+        meshes = []
+        for s in slabs:
+            simp, coords, weights = o.large_hypercube_tables(D, (nxy,) * (D - 1) + (s.nz_cells,), h_div=nxy)
+            meshes.append(o.build_manifold("slab", simp, coords, weights))
+
+        def lists(rank, R):
+            s, m = slabs[rank], meshes[rank]
+            tab = np.arange(m.nsimplices(0))[:, None] if R == 0 else m.simplices[R]
+            pmin, pmax = tab[:, 0] // plane, tab[:, -1] // plane
+            nplanes = s.n_local_planes
+            own_hi = nplanes - s.ghost_hi
+            peer_lo_ghost_hi = slabs[rank - 1].ghost_hi if rank > 0 else 0
+            peer_hi_ghost_lo = slabs[rank + 1].ghost_lo if rank < world - 1 else 0
+            send_lo = np.nonzero((s.ghost_lo > 0) & (pmin >= s.ghost_lo) & (pmax <= s.ghost_lo + peer_lo_ghost_hi - 1))[0]
+            send_hi = np.nonzero((s.ghost_hi > 0) & (pmin >= own_hi - peer_hi_ghost_lo) & (pmin < own_hi))[0]
+            recv_lo = np.nonzero((s.ghost_lo > 0) & (pmin < s.ghost_lo))[0]
+            recv_hi = np.nonzero((s.ghost_hi > 0) & (pmin >= own_hi))[0]
+            glob = tab + s.z_cell_lo * plane                       # global vertex ids
+            return {k: glob[v] for k, v in (("send_lo", send_lo), ("send_hi", send_hi), ("recv_lo", recv_lo),
+                                            ("recv_hi", recv_hi))}, tab.shape[0]
+        for R in range(D + 1):
+            L = [lists(r, R) for r in range(world)]
+            for r in range(world - 1):
+                a, b = L[r][0], L[r + 1][0]
+                assert len(a["send_hi"]) > 0 and len(b["send_lo"]) > 0
+                assert np.array_equal(a["send_hi"], b["recv_lo"]), (D, R, r)
+                assert np.array_equal(b["send_lo"], a["recv_hi"]), (D, R, r)
+            # every ghost simplex is in exactly one receive list, no owned simplex is
+            for r in range(world):
+                s, m = slabs[r], meshes[r]
+                tab = np.arange(m.nsimplices(0))[:, None] if R == 0 else m.simplices[R]
+                lo, hi = s.own_rows
+                nghost = int(np.sum((tab[:, 0] < lo) | (tab[:, 0] >= hi)))
+                assert len(L[r][0]["recv_lo"]) + len(L[r][0]["recv_hi"]) == nghost
