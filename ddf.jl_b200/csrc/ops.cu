@@ -231,7 +231,7 @@ k_apply_pairsign(const uint32_t* __restrict__ pair, int64_t nrows, const double*
 }
 
 // The same operator from the SELL-32 copy of the row-CSR (sell.cuh): coalesced index loads.
-template <bool PRE, bool POST>
+template <bool PRE, bool POST, int BATCH = 8>
 __global__ void __launch_bounds__(256)
 k_apply_sellsign(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict__ perm8,
                  const uint32_t* __restrict__ scol, int64_t nrows, const double* __restrict__ x,
@@ -245,21 +245,21 @@ k_apply_sellsign(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restric
   const uint32_t base = sell_ptr[s] + (uint32_t)(r & 31);
   const uint32_t w = (sell_ptr[s + 1] - sell_ptr[s]) >> 5;
   double a = 0.0;
-  for (uint32_t q0 = 0; q0 < w; q0 += 8) {
-    uint32_t cw[8];
-    double xv[8];
+  for (uint32_t q0 = 0; q0 < w; q0 += BATCH) {
+    uint32_t cw[BATCH];
+    double xv[BATCH];
 #pragma unroll
-    for (int q = 0; q < 8; q++)
+    for (int q = 0; q < BATCH; q++)
       cw[q] = (q0 + q < w) ? (uint32_t)ld_stream_int(reinterpret_cast<const int*>(scol) + (size_t)base + (size_t)(q0 + q) * 32)
                            : DDF_SELL_PAD;
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
+    for (int q = 0; q < BATCH; q++) {
       const uint32_t c = cw[q] != DDF_SELL_PAD ? (cw[q] & 0x7fffffffu) : 0u;
       xv[q] = ld_keep_f64(x + c, pol_keep);
       if (PRE) xv[q] = __dmul_rn(ld_keep_f64(pre + c, pol_keep), xv[q]);
     }
 #pragma unroll
-    for (int q = 0; q < 8; q++)
+    for (int q = 0; q < BATCH; q++)
       if (cw[q] != DDF_SELL_PAD) a = (cw[q] >> 31) ? __dsub_rn(a, xv[q]) : __dadd_rn(a, xv[q]);
   }
   if (i >= nrows) return;
@@ -1215,10 +1215,18 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
   if (m->bsell_state[R] == 1 && g_tune_fixed != 9) {
     const int grid = (int)ceil_div64(f->nrows, DDF_SELL_WIN);
     const SellBufs& sb = m->bsell[R];
-    if (pre_d && post_d) k_apply_sellsign<true, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y);
-    else if (pre_d) k_apply_sellsign<true, false><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y);
-    else if (post_d) k_apply_sellsign<false, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y);
-    else k_apply_sellsign<false, false><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y);
+    // short rows (edges -> faces: ~5 entries): 4 gathers per round keep the kernel at 32 registers / full occupancy
+    const bool short_rows = (int64_t)(R + 1) * m->n[R] < 8 * f->nrows && g_tune_fixed != 17;
+#define DDF_SELLSIGN(PRE_, POST_)                                                                                   \
+  do {                                                                                                              \
+    if (short_rows) k_apply_sellsign<PRE_, POST_, 4><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y); \
+    else k_apply_sellsign<PRE_, POST_, 8><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y);            \
+  } while (0)
+    if (pre_d && post_d) DDF_SELLSIGN(true, true);
+    else if (pre_d) DDF_SELLSIGN(true, false);
+    else if (post_d) DDF_SELLSIGN(false, true);
+    else DDF_SELLSIGN(false, false);
+#undef DDF_SELLSIGN
     DDF_LAUNCH_CHECK(f->ctx);
     return 0;
   }
