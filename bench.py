@@ -183,6 +183,27 @@ def run_reference(args):
     # host threads the reference's own implementation can use, so the line's value is the 1-thread loop.  A
     # row-parallel OpenMP variant on every host core is timed beside it as a cross-check (not what DDF.jl does).
     res = single
+    # second cross-check: scipy.sparse CSR y = A x on the same matrices (Int8 -> Float64 values)
+    scipy_x = None
+    try:
+        import scipy.sparse as sp
+        import ddf_oracle as o
+        om = o.large_hypercube_manifold(3, (args.n_ref,) * 3)
+        mats = [o.deriv(o.Pr, k, om).astype(np.float64).tocsr() for k in range(3)]
+        xs = [np.random.default_rng(k).random(m_.shape[1]) for k, m_ in enumerate(mats)]
+        stars = [np.random.default_rng(9 + k).random(om.nsimplices(k)) for k in range(4)]
+        xd = [np.random.default_rng(5 + k).random(om.nsimplices(k)) for k in range(4)]
+        t0 = time.time()
+        reps = 0
+        while time.time() - t0 < 3.0:
+            for m_, x_ in zip(mats, xs):
+                m_ @ x_
+            for d_, x_ in zip(stars, xd):
+                d_ * x_
+            reps += 1
+        scipy_x = {"value": single["dof_per_step"] * reps / (time.time() - t0), "cores": 1, "what": "scipy.sparse CSR @ x"}
+    except Exception as e:      # the cross-check must never break the arm
+        scipy_x = {"error": repr(e)}
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -191,6 +212,7 @@ def run_reference(args):
                        "note": "DDF.jl is Julia; no julia binary in the image -> C restatement of its SparseArrays "
                                "mul! loops on the reference's storage (Int64 CSC, Int8 values)"},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "scipy_csr_crosscheck": scipy_x,
             "omp_allcores_crosscheck": {"value": omp["value"], "cores": omp["cores"],
                                         "note": "row-parallel OpenMP restatement; the reference itself cannot thread this path"},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
