@@ -14,6 +14,7 @@
 //                        row-CSR (brow_ptr/bcol, parent | sign bit) in one pass
 //                        (:759-765; the two `sparse()` calls become direct writes
 //                        because the sort is stable and rows/columns come out ordered)
+#include <chrono>
 #include <cub/cub.cuh>
 
 #include "mesh.cuh"
@@ -410,8 +411,260 @@ static int assemble_level(ddf_mesh* m, int vbits) {
   return 0;
 }
 
+// -------------------------------------------------------------- assembly, bucket ranking (default)
+// The lexicographic rank of a face (a < b < c ...) is decided first by its smallest vertex a.  So instead of
+// radix-sorting 75-bit tuples globally (20 CUB passes over 16-byte keys at C4), faces are
+//   1. counted per smallest vertex (one atomicAdd per simplex and bucket),
+//   2. scattered into their vertex's bucket as (rest-of-tuple packed in 64 bits, tuple id),
+//   3. sorted INSIDE each bucket by (rest, tuple id) -- a warp per bucket, bitonic network in shared memory; buckets
+//      hold the few dozen faces above one vertex -- and their distinct faces counted,
+//   4. ranked: face id = (distinct faces of all smaller vertices) + rank inside the bucket; the same pass writes
+//      faces, the column table and the row-CSR exactly like k_scatter_faces.
+// Ties (the same face from several parents) are ordered by tuple id = parent id, which is what the stable radix
+// sort of the reference path produces, so every table is bit-identical (tests/test_gpu_parity.py compares both
+// paths with the oracle).  Used when the rest of the tuple fits 64 bits; otherwise the radix path below.
+int g_tune_asm = 0;      // ddf_set_tuning("asm", 1): force the radix-sort path
+
+#define BK_MAX 128       // largest bucket sorted in shared memory; larger ones are sorted serially in place
+
+template <int N>
+__global__ void k_bucket_count(const int32_t* __restrict__ simp, int64_t nsimp, uint32_t* __restrict__ cnt) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nsimp) return;
+  atomicAdd(&cnt[simp[j * N]], (uint32_t)(N - 1));     // the N-1 faces that keep the smallest vertex
+  atomicAdd(&cnt[simp[j * N + 1]], 1u);                // the face that omits it
+}
+
+template <int N>
+__global__ void k_bucket_scatter(const int32_t* __restrict__ simp, int64_t nsimp, int vbits, uint32_t* __restrict__ cursor,
+                                 unsigned long long* __restrict__ rest, uint32_t* __restrict__ tup) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nsimp) return;
+  int32_t v[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) v[k] = simp[j * N + k];
+  const uint32_t base = atomicAdd(&cursor[v[0]], (uint32_t)(N - 1));
+#pragma unroll
+  for (int k = 1; k < N; k++) {                        // leave out vertex k; the bucket is v[0]
+    unsigned long long key = 0;
+#pragma unroll
+    for (int q = 1; q < N; q++)
+      if (q != k) key = (key << vbits) | (unsigned long long)(uint32_t)v[q];
+    rest[base + (k - 1)] = key;
+    tup[base + (k - 1)] = (uint32_t)(j * N + k);
+  }
+  {                                                    // leave out vertex 0; the bucket is v[1]
+    unsigned long long key = 0;
+#pragma unroll
+    for (int q = 2; q < N; q++) key = (key << vbits) | (unsigned long long)(uint32_t)v[q];
+    const uint32_t p = atomicAdd(&cursor[v[1]], 1u);
+    rest[p] = key;
+    tup[p] = (uint32_t)(j * N);
+  }
+}
+
+__device__ __forceinline__ bool bk_less(unsigned long long ra, uint32_t ta, unsigned long long rb, uint32_t tb) {
+  return ra < rb || (ra == rb && ta < tb);
+}
+
+// warp per bucket: sort by (rest, tuple id), count the distinct faces
+__global__ void __launch_bounds__(256)
+k_bucket_sort(const uint32_t* __restrict__ start, int64_t nbuckets, unsigned long long* __restrict__ rest,
+              uint32_t* __restrict__ tup, uint32_t* __restrict__ ucnt) {
+  __shared__ unsigned long long sr[8][BK_MAX];
+  __shared__ uint32_t st[8][BK_MAX];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * 8 + w;
+  if (b >= nbuckets) return;
+  const uint32_t lo = start[b], sz = start[b + 1] - lo;
+  if (sz == 0) { if (lane == 0) ucnt[b] = 0u; return; }
+  if (sz > BK_MAX) {                                  // rare: serial insertion sort in place
+    if (lane == 0) {
+      for (uint32_t i = 1; i < sz; i++) {
+        const unsigned long long r = rest[lo + i];
+        const uint32_t t = tup[lo + i];
+        uint32_t k = i;
+        while (k > 0 && bk_less(r, t, rest[lo + k - 1], tup[lo + k - 1])) {
+          rest[lo + k] = rest[lo + k - 1];
+          tup[lo + k] = tup[lo + k - 1];
+          k--;
+        }
+        rest[lo + k] = r;
+        tup[lo + k] = t;
+      }
+      uint32_t u = 1;
+      for (uint32_t i = 1; i < sz; i++) u += rest[lo + i] != rest[lo + i - 1];
+      ucnt[b] = u;
+    }
+    return;
+  }
+  // rank by counting: every lane compares its element(s) with all sz elements of the bucket (broadcast reads of
+  // shared memory, no barriers) -- cheaper than a bitonic network for the few dozen faces above one vertex
+  for (uint32_t i = lane; i < sz; i += 32) {
+    sr[w][i] = rest[lo + i];
+    st[w][i] = tup[lo + i];
+  }
+  __syncwarp();
+  uint32_t u = 0;
+  for (uint32_t i0 = 0; i0 < sz; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    bool head = false;
+    if (i < sz) {
+      const unsigned long long myr = sr[w][i];
+      const uint32_t myt = st[w][i];
+      uint32_t rank = 0, eq_lower = 0;
+      for (uint32_t j = 0; j < sz; j++) {
+        const unsigned long long rj = sr[w][j];
+        const uint32_t tj = st[w][j];
+        const bool same = rj == myr;
+        rank += (rj < myr) || (same && tj < myt);
+        eq_lower += same && tj < myt;
+      }
+      rest[lo + rank] = myr;
+      tup[lo + rank] = myt;
+      head = eq_lower == 0;                     // first (smallest parent) of its face
+    }
+    u += __popc(__ballot_sync(0xffffffffu, head));
+  }
+  if (lane == 0) ucnt[b] = u;
+}
+
+// warp per bucket: face ids and every output table (the bucket variant of k_scatter_faces)
+template <int N>
+__global__ void __launch_bounds__(256)
+k_bucket_rank(const uint32_t* __restrict__ start, const uint32_t* __restrict__ fbase, int64_t nbuckets,
+              const unsigned long long* __restrict__ rest, const uint32_t* __restrict__ tup, int vbits,
+              int32_t* __restrict__ faces, int32_t* __restrict__ bnd, uint32_t* __restrict__ brow_ptr,
+              uint32_t* __restrict__ bcol, uint32_t ntuples, uint32_t nfaces) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * 8 + w;
+  if (b == 0 && lane == 0) brow_ptr[nfaces] = ntuples;
+  if (b >= nbuckets) return;
+  const uint32_t lo = start[b], sz = start[b + 1] - lo;
+  uint32_t running = 0;
+  const uint32_t fb = fbase[b];
+  for (uint32_t i0 = 0; i0 < sz; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    const bool valid = i < sz;
+    unsigned long long r = 0;
+    uint32_t t = 0;
+    bool head = false;
+    if (valid) {
+      r = rest[lo + i];
+      t = tup[lo + i];
+      head = i == 0 || r != rest[lo + i - 1];
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, head);
+    if (valid) {
+      const uint32_t f = fb + running + __popc(mask & (0xffffffffu >> (31 - lane))) - 1u;
+      const uint32_t gpos = lo + i;
+      const uint32_t j = t / N, k = t - j * N;
+      if (bnd) bnd[(size_t)j * N + (N - 1 - k)] = (int32_t)f;
+      bcol[gpos] = j | ((k & 1u) ? 0x80000000u : 0u);
+      if (head) {
+        brow_ptr[f] = gpos;
+        if (faces) {
+          const unsigned long long vm = (1ull << vbits) - 1ull;
+          faces[(size_t)f * (N - 1)] = (int32_t)b;
+#pragma unroll
+          for (int q = N - 2; q >= 1; q--) {
+            faces[(size_t)f * (N - 1) + q] = (int32_t)(uint32_t)(r & vm);
+            r >>= vbits;
+          }
+        }
+      }
+    }
+    running += __popc(mask);
+  }
+}
+
+// one grow-only device workspace for all levels of an assembly: cudaMalloc / cudaFree of several GB cost
+// milliseconds per GB, more than the kernels they would serve
+struct AsmWork {
+  DevBuf<unsigned char> buf;
+  int ensure(ddf_ctx* ctx, size_t bytes) {
+    if (buf.n >= bytes) return 0;
+    buf.release();
+    return buf.alloc(ctx, bytes);
+  }
+};
+static AsmWork* g_asm_work = nullptr;     // set by ddf_mesh_assemble for the duration of the call
+
+template <int N>
+static int assemble_level_bucket(ddf_mesh* m, int vbits) {
+  constexpr int R = N - 1;
+  ddf_ctx* ctx = m->ctx;
+  const int64_t nsimp = m->n[R], nv = m->n[0];
+  const int64_t ntuples = nsimp * N;
+  if (ntuples >= 0xffffffffLL) DDF_FAIL("assemble: (R+1)*n_R = %lld >= 2^32 tuples; partition the mesh", (long long)ntuples);
+  // workspace layout: rest[ntuples] u64 | tup[ntuples] u32 | cnt, start, cursor, ucnt, fbase [nv+1] u32 each | scan temp
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t tb = 0;
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t*)nullptr, (uint32_t*)nullptr, nv + 1, ctx->stream));
+  const size_t o_rest = 0, o_tup = up((size_t)ntuples * 8), o_cnt = o_tup + up((size_t)ntuples * 4);
+  const size_t vsz = up((size_t)(nv + 1) * 4);
+  const size_t o_start = o_cnt + vsz, o_cursor = o_start + vsz, o_ucnt = o_cursor + vsz, o_fbase = o_ucnt + vsz;
+  const size_t o_temp = o_fbase + vsz, total = o_temp + up(tb);
+  AsmWork local;
+  AsmWork* wk = g_asm_work ? g_asm_work : &local;
+  const bool dbg = getenv("DDF_DEBUG") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_a = now();
+  DDF_CHECK(wk->ensure(ctx, total));
+  const double t_b = now();
+  unsigned char* base = wk->buf.p;
+  unsigned long long* rest = reinterpret_cast<unsigned long long*>(base + o_rest);
+  uint32_t* tup = reinterpret_cast<uint32_t*>(base + o_tup);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(base + o_cnt);
+  uint32_t* start = reinterpret_cast<uint32_t*>(base + o_start);
+  uint32_t* cursor = reinterpret_cast<uint32_t*>(base + o_cursor);
+  uint32_t* ucnt = reinterpret_cast<uint32_t*>(base + o_ucnt);
+  uint32_t* fbase = reinterpret_cast<uint32_t*>(base + o_fbase);
+  void* temp = base + o_temp;
+  DDF_CUDA(cudaMemsetAsync(cnt, 0, (nv + 1) * 4, ctx->stream));
+  int gs, gb;
+  DDF_CHECK(grid_for(nsimp, 256, &gs));
+  DDF_CHECK(grid_for(ceil_div64(nv, 8) * 256, 256, &gb));
+  k_bucket_count<N><<<gs, 256, 0, ctx->stream>>>(m->simp[R].p, nsimp, cnt);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, cnt, start, nv + 1, ctx->stream));
+  ctx->launches++;
+  DDF_CUDA(cudaMemcpyAsync(cursor, start, (nv + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  k_bucket_scatter<N><<<gs, 256, 0, ctx->stream>>>(m->simp[R].p, nsimp, vbits, cursor, rest, tup);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CUDA(cudaMemsetAsync(ucnt + nv, 0, 4, ctx->stream));
+  k_bucket_sort<<<gb, 256, 0, ctx->stream>>>(start, nv, rest, tup, ucnt);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, ucnt, fbase, nv + 1, ctx->stream));
+  ctx->launches++;
+  uint32_t nfaces = 0;
+  DDF_CUDA(cudaMemcpyAsync(&nfaces, fbase + nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (R == 1 && (int64_t)nfaces != m->n[0])
+    DDF_FAIL("assemble: %lld of %lld vertices are not used by any edge; the reference numbers 0-simplices by rank "
+             "among used vertices (Manifolds.jl:745-757), which is inconsistent with coords -- remove unused vertices",
+             (long long)(m->n[0] - nfaces), (long long)m->n[0]);
+  m->n[R - 1] = nfaces;
+  const double t_c = now();
+  if (R - 1 >= 1) DDF_CHECK(m->simp[R - 1].alloc(ctx, (size_t)nfaces * R));
+  if (R >= 2) DDF_CHECK(m->bnd[R].alloc(ctx, (size_t)ntuples));
+  DDF_CHECK(m->brow_ptr[R].alloc(ctx, (size_t)nfaces + 1));
+  DDF_CHECK(m->bcol[R].alloc(ctx, (size_t)ntuples));
+  const double t_d = now();
+  if (dbg)
+    fprintf(stderr, "[ddf] assemble R=%d: workspace %.1f ms (%.2f GB), count..sort %.1f ms, output alloc %.1f ms\n", R,
+            t_b - t_a, total * 1e-9, t_c - t_b, t_d - t_c);
+  k_bucket_rank<N><<<gb, 256, 0, ctx->stream>>>(start, fbase, nv, rest, tup, vbits,
+                                               R - 1 >= 1 ? m->simp[R - 1].p : nullptr, R >= 2 ? m->bnd[R].p : nullptr,
+                                               m->brow_ptr[R].p, m->bcol[R].p, (uint32_t)ntuples, nfaces);
+  DDF_LAUNCH_CHECK(ctx);
+  if (!g_asm_work) DDF_CUDA(cudaStreamSynchronize(ctx->stream));     // the local workspace is freed on return
+  return 0;
+}
+
 template <int N>
 static int assemble_level_dispatch(ddf_mesh* m, int vbits) {
+  if (!g_tune_asm && (N - 2) * vbits <= 64) return assemble_level_bucket<N>(m, vbits);
   const int bits = (N - 1) * vbits;
   if (bits <= 32) return assemble_level<uint32_t, N>(m, vbits);
   if (bits <= 64) return assemble_level<uint64_t, N>(m, vbits);
@@ -426,6 +679,12 @@ extern "C" int ddf_mesh_assemble(ddf_mesh* m) {
   DDF_CUDA(cudaSetDevice(m->ctx->device));
   int vbits = 1;
   while (((int64_t)1 << vbits) < m->n[0]) vbits++;
+  AsmWork work;                          // shared by all levels, released (after a sync) when this call returns
+  struct WorkScope {
+    AsmWork* w; cudaStream_t st;
+    ~WorkScope() { cudaStreamSynchronize(st); g_asm_work = nullptr; }
+  } scope{&work, m->ctx->stream};
+  g_asm_work = &work;
   for (int R = m->D; R >= 1; R--) {
     if (m->n[R] == 0) {                 // empty manifold: every level is empty
       m->n[R - 1] = (R - 1 == 0) ? m->n[0] : 0;

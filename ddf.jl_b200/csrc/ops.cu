@@ -313,10 +313,12 @@ __global__ void k_apply_csrf64(const uint32_t* __restrict__ rowptr, const int32_
 }
 
 extern int g_tune_wave;   // wave.cu
+extern int g_tune_asm;    // mesh.cu
 extern int g_tune_fixed;
 extern "C" int ddf_set_tuning(const char* key, int value) {
   if (!strcmp(key, "fixed")) g_tune_fixed = value;
   else if (!strcmp(key, "wave")) g_tune_wave = value;
+  else if (!strcmp(key, "asm")) g_tune_asm = value;
   else DDF_FAIL("set_tuning: unknown key %s", key);
   return 0;
 }

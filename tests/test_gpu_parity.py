@@ -879,3 +879,37 @@ def test_topology_in_higher_dimensions(ddf, ctx, kind):
         z = rng.integers(-9, 9, om.nsimplices(k + 1)).astype(np.float64)
         w = (ddf.boundary(ddf.Pr, k + 1, dm) * ddf.Fun(dm, ddf.Pr, k + 1, z)).values
         assert np.array_equal(w, om.boundaries[k + 1].astype(np.float64) @ z), ("boundary", k + 1)
+
+
+def test_assembly_bucket_ranking_equals_radix_sort(ddf, ctx):
+    """K1 has two paths: the bucket ranking (count / scatter by smallest vertex, warp-sorted buckets; default) and
+    the global radix sort of the full tuples (tuning asm=1; also the fallback for wide tuples).  Every table they
+    produce -- simplices, boundary CSC with signs, and through it the row-CSR -- must be identical, on a Kuhn
+    mesh, an irregular Delaunay mesh (large, ragged buckets) and in 2D."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(77)
+    pts3 = rng.random((4000, 3))
+    cases = [("kuhn3", None, (40, 40, 40)), ("kuhn2", None, (300, 300)),
+             ("delaunay3", (np.asarray(Delaunay(pts3).simplices, dtype=np.int64), pts3), None)]
+    for name, tables, nelts in cases:
+        res = []
+        for asm in (0, 1):
+            ddf._lib.call("ddf_set_tuning", b"asm", asm)
+            try:
+                if tables is None:
+                    m = ddf.large_hypercube_manifold(len(nelts), nelts, ctx=ctx)
+                else:
+                    m = ddf.Manifold.from_simplices(name, tables[0], tables[1], ctx=ctx)
+                D = m.D
+                out = [m.get_simplices(R) for R in range(1, D + 1)] + [a for R in range(1, D + 1)
+                                                                       for a in m.get_boundaries_csc(R)]
+                rngx = np.random.default_rng(5)
+                x = rngx.standard_normal(m.nsimplices(D))
+                out.append((ddf.boundary(ddf.Pr, D, m) * ddf.Fun(m, ddf.Pr, D, x)).values)   # exercises the row-CSR
+                res.append(out)
+                m.close()
+            finally:
+                ddf._lib.call("ddf_set_tuning", b"asm", 0)
+        assert len(res[0]) == len(res[1])
+        for a, b in zip(res[0], res[1]):
+            assert np.array_equal(a, b), name
