@@ -578,6 +578,83 @@ k_bucket_rank(const uint32_t* __restrict__ start, const uint32_t* __restrict__ f
   }
 }
 
+// ---------------------------------------------------------------- exclusive prefix sum (uint32), hand-written
+// Three passes: per-tile sums, a single-block scan of the tile sums, per-tile scan + offset.  Tiles of 4096.
+#define SCAN_TILE 4096
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ sums) {
+  __shared__ uint32_t ws[8];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  uint32_t acc = 0;
+  for (int k = threadIdx.x; k < SCAN_TILE; k += 256) acc += base + k < n ? in[base + k] : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; w++) t += ws[w];
+    sums[blockIdx.x] = t;
+  }
+}
+// one block: exclusive scan of `m` tile sums in place (m is a few thousand)
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* __restrict__ sums, int64_t m) {
+  __shared__ uint32_t part[1024];
+  const int64_t per = (m + 1023) / 1024;
+  const int64_t lo = threadIdx.x * per, hi = min(lo + per, m);
+  uint32_t acc = 0;
+  for (int64_t k = lo; k < hi; k++) acc += sums[k];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int k = 0; k < 1024; k++) { const uint32_t v = part[k]; part[k] = run; run += v; }
+  }
+  __syncthreads();
+  uint32_t run = part[threadIdx.x];
+  for (int64_t k = lo; k < hi; k++) { const uint32_t v = sums[k]; sums[k] = run; run += v; }
+}
+__global__ void __launch_bounds__(256) k_scan_tiles(const uint32_t* __restrict__ in, int64_t n, const uint32_t* __restrict__ sums,
+                                                   uint32_t* __restrict__ out) {
+  __shared__ uint32_t ws[8];
+  __shared__ uint32_t carry;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = sums[blockIdx.x];
+  __syncthreads();
+  for (int c = 0; c < SCAN_TILE; c += 256) {            // 16 chunks of 256, scanned in order
+    const int64_t i = base + c + threadIdx.x;
+    const uint32_t v = i < n ? in[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) ws[w] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int k = 0; k < w; k++) woff += ws[k];
+    const uint32_t c0 = carry;
+    if (i < n) out[i] = c0 + woff + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry = c0 + woff + incl;
+    __syncthreads();
+  }
+}
+// out[i] = in[0] + ... + in[i-1]; `sums` holds ceil(n / SCAN_TILE) words of scratch
+static int scan_exclusive_u32(ddf_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, uint32_t* sums) {
+  if (n <= 0) return 0;
+  const int64_t tiles = ceil_div64(n, SCAN_TILE);
+  if (tiles > 0x7fffffffLL) DDF_FAIL("scan: too many tiles");
+  k_scan_tile_sums<<<(int)tiles, 256, 0, ctx->stream>>>(in, n, sums);
+  DDF_LAUNCH_CHECK(ctx);
+  k_scan_sums<<<1, 1024, 0, ctx->stream>>>(sums, tiles);
+  DDF_LAUNCH_CHECK(ctx);
+  k_scan_tiles<<<(int)tiles, 256, 0, ctx->stream>>>(in, n, sums, out);
+  DDF_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 // one grow-only device workspace for all levels of an assembly: cudaMalloc / cudaFree of several GB cost
 // milliseconds per GB, more than the kernels they would serve
 struct AsmWork {
@@ -599,8 +676,7 @@ static int assemble_level_bucket(ddf_mesh* m, int vbits) {
   if (ntuples >= 0xffffffffLL) DDF_FAIL("assemble: (R+1)*n_R = %lld >= 2^32 tuples; partition the mesh", (long long)ntuples);
   // workspace layout: rest[ntuples] u64 | tup[ntuples] u32 | cnt, start, cursor, ucnt, fbase [nv+1] u32 each | scan temp
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  size_t tb = 0;
-  DDF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t*)nullptr, (uint32_t*)nullptr, nv + 1, ctx->stream));
+  const size_t tb = (size_t)ceil_div64(nv + 1, SCAN_TILE) * 4;       // scratch of the hand-written scan
   const size_t o_rest = 0, o_tup = up((size_t)ntuples * 8), o_cnt = o_tup + up((size_t)ntuples * 4);
   const size_t vsz = up((size_t)(nv + 1) * 4);
   const size_t o_start = o_cnt + vsz, o_cursor = o_start + vsz, o_ucnt = o_cursor + vsz, o_fbase = o_ucnt + vsz;
@@ -620,23 +696,21 @@ static int assemble_level_bucket(ddf_mesh* m, int vbits) {
   uint32_t* cursor = reinterpret_cast<uint32_t*>(base + o_cursor);
   uint32_t* ucnt = reinterpret_cast<uint32_t*>(base + o_ucnt);
   uint32_t* fbase = reinterpret_cast<uint32_t*>(base + o_fbase);
-  void* temp = base + o_temp;
+  uint32_t* temp = reinterpret_cast<uint32_t*>(base + o_temp);
   DDF_CUDA(cudaMemsetAsync(cnt, 0, (nv + 1) * 4, ctx->stream));
   int gs, gb;
   DDF_CHECK(grid_for(nsimp, 256, &gs));
   DDF_CHECK(grid_for(ceil_div64(nv, 8) * 256, 256, &gb));
   k_bucket_count<N><<<gs, 256, 0, ctx->stream>>>(m->simp[R].p, nsimp, cnt);
   DDF_LAUNCH_CHECK(ctx);
-  DDF_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, cnt, start, nv + 1, ctx->stream));
-  ctx->launches++;
+  DDF_CHECK(scan_exclusive_u32(ctx, cnt, start, nv + 1, temp));
   DDF_CUDA(cudaMemcpyAsync(cursor, start, (nv + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   k_bucket_scatter<N><<<gs, 256, 0, ctx->stream>>>(m->simp[R].p, nsimp, vbits, cursor, rest, tup);
   DDF_LAUNCH_CHECK(ctx);
   DDF_CUDA(cudaMemsetAsync(ucnt + nv, 0, 4, ctx->stream));
   k_bucket_sort<<<gb, 256, 0, ctx->stream>>>(start, nv, rest, tup, ucnt);
   DDF_LAUNCH_CHECK(ctx);
-  DDF_CUDA(cub::DeviceScan::ExclusiveSum(temp, tb, ucnt, fbase, nv + 1, ctx->stream));
-  ctx->launches++;
+  DDF_CHECK(scan_exclusive_u32(ctx, ucnt, fbase, nv + 1, temp));
   uint32_t nfaces = 0;
   DDF_CUDA(cudaMemcpyAsync(&nfaces, fbase + nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   DDF_CUDA(cudaStreamSynchronize(ctx->stream));
