@@ -913,3 +913,32 @@ def test_assembly_bucket_ranking_equals_radix_sort(ddf, ctx):
         assert len(res[0]) == len(res[1])
         for a, b in zip(res[0], res[1]):
             assert np.array_equal(a, b), name
+
+
+def test_assembly_huge_bucket(ddf, ctx):
+    """A fan of 300 triangles around vertex 0: 600 edge tuples share the smallest vertex, far more than a warp ranks
+    in shared memory (BK_MAX = 128) -- the serial in-place path of k_bucket_sort; plus the same fan in 3D (cone of
+    tets over a triangulated disc)."""
+    M = 300
+    ang = 2 * np.pi * np.arange(M) / M
+    pts = np.concatenate([[[0.0, 0.0]], np.stack([np.cos(ang), np.sin(ang)], axis=1)])
+    tris = np.array([[0, 1 + i, 1 + (i + 1) % M] for i in range(M)], dtype=np.int64)
+    pts3 = np.concatenate([np.concatenate([pts, np.zeros((M + 1, 1))], axis=1), [[0.0, 0.0, 1.0]]])
+    tets = np.array([[0, 1 + i, 1 + (i + 1) % M, M + 1] for i in range(M)], dtype=np.int64)
+    for simp, coords in ((tris, pts), (tets, pts3)):
+        om = o.build_manifold("fan", simp, coords)
+        dm = ddf.Manifold.from_simplices("fan", simp, coords, ctx=ctx)
+        D = om.D
+        for R in range(1, D + 1):
+            cp, rv, nz = dm.get_boundaries_csc(R)
+            ocp, orv, onz = o.to_julia_csc(om.boundaries[R])
+            assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz), R
+            assert np.array_equal(dm.get_simplices(R), om.simplices[R]), R
+        rng = np.random.default_rng(3)
+        for k in range(D):
+            x = rng.standard_normal(om.nsimplices(k))
+            assert np.array_equal((ddf.deriv(ddf.Pr, k, dm) * ddf.Fun(dm, ddf.Pr, k, x)).values,
+                                  o.apply_deriv(o.Pr, k, om, x))
+            z = rng.standard_normal(om.nsimplices(k + 1))
+            assert np.array_equal((ddf.boundary(ddf.Pr, k + 1, dm) * ddf.Fun(dm, ddf.Pr, k + 1, z)).values,
+                                  om.boundaries[k + 1].astype(np.float64) @ z)
