@@ -388,6 +388,20 @@ def run_b200(args):
                   "format_bytes": fmt2, "GBps": alg2 / ms2 * 1e-6, "frac": alg2 / ms2 * 1e-6 / peak,
                   "row_format": ddf.wave_format(m2), "steps": 200}
         m2.close()
+    # north_star kernel (3), Poisson flavour: one fused weighted-Jacobi sweep on the same mesh
+    # algorithmic bytes (SURVEY 8d counting): E*(2*4+8) + V*(u r/w 16 + rho 8 + 1/diag 8 + mask 1)
+    poisson_step = None
+    if N == 1 and not args.no_extras:
+        up_, rho_ = ddf.sample(mfd, "wave"), ddf.sample(mfd, "poisson_rho")
+        ddf.poisson_jacobi(mfd, up_, rho_, 2.0 / 3.0, 5)
+        ctx.sync()
+        ctx.tic()
+        ddf.poisson_jacobi(mfd, up_, rho_, 2.0 / 3.0, K)
+        pj = ctx.toc() / K
+        algp = cnt[1] * 16 + cnt[0] * 33
+        poisson_step = {"ms_per_sweep": pj, "algorithmic_bytes": int(algp), "GBps": algp / pj * 1e-6,
+                        "frac": algp / pj * 1e-6 / peak, "vertex_updates_per_s": cnt[0] / (pj * 1e-3)}
+        del up_, rho_
     # the reference's own integrator on the same mesh: fixed-step Tsit5 (wave.jl:134), 6 right-hand sides per step
     tsit5 = None
     if N == 1 and not args.no_extras:
@@ -500,7 +514,7 @@ def run_b200(args):
                          "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(d1_bytes),
                          "ms_per_launch": d1_ms, "frac_of_nominal_8TBs": d1_bytes / d1_ms * 1e-6 / 8000.0},
-            "breakdown": breakdown, "wave": wave, "wave2d": wave2d, "wave_tsit5": tsit5, "poisson2d": poisson2d,
+            "breakdown": breakdown, "wave": wave, "wave2d": wave2d, "poisson_step": poisson_step, "wave_tsit5": tsit5, "poisson2d": poisson2d,
             "assembly_ms": asm_ms,
             # assembly of d_3, d_2, d_1 on the device from the tet table (bit-exact; no roofline target):
             # face tuples generated, sorted and ranked per second

@@ -14,6 +14,6 @@ from .manifoldops import (boundary, boundary_of, coderiv, coderiv_of, delaunay_m
                           refined_simplex_manifold, regular_simplex, sample, simplex_manifold, zero)
 from .wave import (lincomb, wave, wave_dt, wave_format, wave_leapfrog, wave_rhs, wave_step_bytes,  # noqa: F401
                    wave_tsit5)  # noqa: F401
-from .poisson import bicgstabl, poisson, poisson_operator, poisson_solve  # noqa: F401
+from .poisson import bicgstabl, poisson, poisson_jacobi, poisson_operator, poisson_solve  # noqa: F401
 from .vtkout import write_vtu  # noqa: F401
 from . import dist  # noqa: F401

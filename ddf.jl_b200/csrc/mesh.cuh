@@ -115,6 +115,7 @@ struct ddf_mesh {
   // staged copies of the fixed-width tables of d_{R-1} = d_R^T (primal derivative apply)
   FStageBufs fstage[DDF_MAXD + 1];
   DevBuf<double> utmp;                   // V   ping-pong buffer of the fused step
+  DevBuf<double> ldinv;                  // V   1 ./ diag(L) for the fused Poisson relaxation step
 
   // slab halo of the distributed wave step (comm.cu): vertex planes along the
   // slowest axis; the first halo_lo / last halo_hi planes are ghosts owned by rank-1 / rank+1

@@ -194,7 +194,17 @@ struct RowArgs {
   double* peer_lo;
   double* peer_hi;
   int64_t send_lo_end, send_hi_beg;
+  // MODE 3 (fused Poisson relaxation): u' = u + theta * ((1-b) .* ((rho - L u) .* dinv)),  dinv = 1 ./ diag(L)
+  const double* rho;
+  const double* dinv;
+  double theta;
 };
+
+// the epilogue of MODE 3, shared by every row kernel: one rounding per operation, in this order
+__device__ __forceinline__ double jacobi_update(double u_i, double lu, double rho_i, double dinv_i, double m, double theta) {
+  const double c = __dmul_rn(__dsub_rn(rho_i, lu), dinv_i);
+  return __dadd_rn(u_i, __dmul_rn(theta, __dmul_rn(m, c)));
+}
 
 __device__ __forceinline__ void peer_store(const RowArgs& a, int64_t i, double w) {
   if (a.peer_lo && i < a.send_lo_end) a.peer_lo[i - a.row0] = w;
@@ -209,6 +219,9 @@ __device__ __forceinline__ void row_epilogue(const RowArgs& a, int64_t i, double
     const double m = a.isb[i] ? 0.0 : 1.0;
     a.out0[i] = __dmul_rn(m, a.udot[i]);
     a.out1[i] = __dmul_rn(m, lu);
+  } else if (MODE == 3) {
+    const double m = a.isb[i] ? 0.0 : 1.0;
+    a.out1[i] = jacobi_update(a.u[i], lu, a.rho[i], a.dinv[i], m, a.theta);
   } else {
     const double m = a.isb[i] ? 0.0 : 1.0;
     const double vn = __dadd_rn(a.out0[i], __dmul_rn(a.dt, __dmul_rn(m, lu)));
@@ -371,6 +384,8 @@ k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* _
   if (MODE != 0 && mine) eb = a.isb[i];
   if (MODE == 1 && mine) e0 = a.udot[i];
   if (MODE == 2 && mine) { e0 = a.out0[i]; e1 = a.u[i]; }
+  double e2 = 0.0;
+  if (MODE == 3 && mine) { e0 = a.rho[i]; e1 = a.u[i]; e2 = a.dinv[i]; }
   const double lu = stage_row_sum<BATCH>(slot, sl, stage, &mbar, off, lane, mylen, maxlen);
   if (!mine) return;
   if (MODE == 0) {
@@ -379,6 +394,8 @@ k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* _
     const double m = eb ? 0.0 : 1.0;
     a.out0[i] = __dmul_rn(m, e0);
     a.out1[i] = __dmul_rn(m, lu);
+  } else if (MODE == 3) {
+    a.out1[i] = jacobi_update(e1, lu, e0, e2, eb ? 0.0 : 1.0, a.theta);
   } else {
     const double m = eb ? 0.0 : 1.0;
     const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, lu)));
@@ -477,7 +494,7 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
       // requests per group: the runs of u, ONE range of entries records, ONE range of meta records, v (or udot), u
       uint32_t tx = total * 8u + nent * 10u + mbytes;
       if (MODE == 1) tx += vbytes;
-      if (MODE == 2) tx += 2u * vbytes;
+      if (MODE == 2 || MODE == 3) tx += 2u * vbytes;
       if (lane == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(tx) : "memory");
         asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&issued[s])), "r"((uint32_t)it + 1u) : "memory");
@@ -488,8 +505,8 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
       if (lane == 31 && nent) bulk_g2s(sb + g.o_ent, packed + (size_t)e0 * 10, nent * 10u, &full[s], pol_stream);
       if (lane == 30) bulk_g2s(sb + g.o_meta, meta + win * g.K * STAGE_META, mbytes, &full[s], pol_stream);
       if (lane == 29 && MODE != 0) {
-        bulk_g2s(sb + g.o_v, (MODE == 1 ? a.udot : a.out0) + r0, vbytes, &full[s], pol_stream);
-        if (MODE == 2) bulk_g2s(sb + g.o_u, a.u + r0, vbytes, &full[s], pol_keep);
+        bulk_g2s(sb + g.o_v, (MODE == 1 ? a.udot : (MODE == 3 ? a.rho : a.out0)) + r0, vbytes, &full[s], pol_stream);
+        if (MODE == 2 || MODE == 3) bulk_g2s(sb + g.o_u, a.u + r0, vbytes, &full[s], pol_keep);
       }
     }
   } else {
@@ -521,6 +538,11 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
         const uint8_t* lenS = metaS + STAGE_META_HDR + DDF_SELL_WIN;
         const uint32_t mylen = lenS[gtid];
         const uint32_t p = (metaS + STAGE_META_HDR)[gtid];
+        double dinv_i = 0.0;                                 // MODE 3: requested now, needed after the row sum
+        if (MODE == 3) {
+          const int64_t ip = win * g.K * DDF_SELL_WIN + (int64_t)kk * DDF_SELL_WIN + p;
+          if (ip >= a.row0 && ip < a.row1) dinv_i = __ldg(a.dinv + ip);
+        }
         // entry offset of this slice inside the window's record: precomputed in the meta header
         const uint32_t part = reinterpret_cast<const uint32_t*>(metaS)[4 + gwarp];
         const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
@@ -548,6 +570,8 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
             if (MODE == 1) {
               a.out0[i] = __dmul_rn(m, e0);
               a.out1[i] = __dmul_rn(m, acc);
+            } else if (MODE == 3) {
+              a.out1[i] = jacobi_update(reinterpret_cast<const double*>(sb + g.o_u)[pl], acc, e0, dinv_i, m, a.theta);
             } else {
               const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, acc)));
               a.out0[i] = vn;
@@ -905,6 +929,55 @@ extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt,
     for (int c = 0; c < 2; c++) std::swap(kp[0][c], kp[6][c]);     // FSAL
   }
   DDF_CUDA(cudaStreamSynchronize(ctx->stream));    // the work space is freed on return
+  return 0;
+  DDF_TRY_END
+}
+
+// 1 ./ diag(L) from the assembled rows (0 where the diagonal entry was chopped away)
+__global__ void k_laplace0_dinv(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
+                                const double* __restrict__ lval, int64_t nv, double* __restrict__ dinv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  double d = 0.0;
+  for (uint32_t p = rowptr[i]; p < rowptr[i + 1]; p++)
+    if (nbr[p] == (int32_t)i) d = lval[p];
+  dinv[i] = d != 0.0 ? __ddiv_rn(1.0, d) : 0.0;
+}
+
+// Fused Poisson relaxation step (north_star kernel (3), "wave/Poisson step"): weighted Jacobi on
+//   L u = rho in the interior, u fixed on the boundary   (examples/poisson.jl:75-81, 172-201 with f eliminated)
+//   u' = u + theta * ((1-b) .* ((rho - L u) ./ diag(L)))
+// one pass per sweep through the same row kernels as the wave step (u ping-pong, rho and u staged by TMA).
+extern "C" int ddf_poisson_jacobi(ddf_mesh* m, ddf_vec* u, ddf_vec* rho, double theta, int nsweeps) {
+  DDF_TRY_BEGIN
+  DDF_CHECK(ddf_mesh_require_wave(m));
+  ddf_ctx* ctx = m->ctx;
+  const int64_t nv = m->n[0];
+  if (u->n != nv || rho->n != nv) DDF_FAIL("poisson_jacobi: vectors must have length n0=%lld", (long long)nv);
+  if (u == rho) DDF_FAIL("poisson_jacobi: u and rho must not alias");
+  if (!nv || nsweeps <= 0) return 0;
+  DDF_CHECK(ddf_vec_settle(u));
+  DDF_CHECK(ddf_vec_settle(rho));
+  if ((int64_t)m->ldinv.n != nv) {
+    DDF_CHECK(m->ldinv.alloc(ctx, nv));
+    int grid;
+    DDF_CHECK(grid_for(nv, 256, &grid));
+    k_laplace0_dinv<<<grid, 256, 0, ctx->stream>>>(m->adj_ptr.p, m->adj_nbr.p, m->adj_l.p, nv, m->ldinv.p);
+    DDF_LAUNCH_CHECK(ctx);
+  }
+  if ((int64_t)m->utmp.n != nv) DDF_CHECK(m->utmp.alloc(ctx, nv));
+  for (int s = 0; s < nsweeps; s++) {
+    RowArgs a{};
+    a.u = u->d.p;
+    a.out1 = m->utmp.p;
+    a.rho = rho->d.p;
+    a.dinv = m->ldinv.p;
+    a.theta = theta;
+    a.row0 = 0;
+    a.row1 = nv;
+    DDF_CHECK(launch_rows<3>(m, ctx->stream, a));
+    u->d.swap(m->utmp);
+  }
   return 0;
   DDF_TRY_END
 }

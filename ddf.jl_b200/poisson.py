@@ -38,6 +38,14 @@ def bicgstabl(A: Op, b: Fun, x: Fun = None, l: int = 2, reltol: float = math.sqr
     return x, {"mv_products": mv.value, "residual": res.value, "converged": bool(conv.value)}
 
 
+def poisson_jacobi(mfd: Manifold, u: Fun, rho: Fun, theta: float = 2.0 / 3.0, nsweeps: int = 1) -> Fun:
+    """In-place fused relaxation sweeps on L u = rho with the boundary values of u held fixed:
+    u <- u + theta * ((1-b) .* ((rho - L u) ./ diag(L)))."""
+    mfd._geometry()
+    call("ddf_poisson_jacobi", mfd._h, u._h, rho._h, float(theta), int(nsweeps))
+    return u
+
+
 def rho_exact(coords: np.ndarray) -> np.ndarray:
     """poisson.jl:85-92: Gaussian of width sigma = 0.2 centred at x0 = 0.1*1."""
     D = coords.shape[1]

@@ -194,6 +194,10 @@ int ddf_wave_leapfrog(ddf_mesh* mesh, ddf_vec* u, ddf_vec* v, double dt, int nst
 /* `nsteps` fixed steps of Tsit5 on dU = F U, U = [u; udot] -- what examples/wave.jl:134 runs
  * (`solve(prob, Tsit5(); adaptive=false, dt=dt)`); in place. */
 int ddf_wave_tsit5(ddf_mesh* mesh, ddf_vec* u, ddf_vec* udot, double dt, int nsteps);
+/* Fused Poisson relaxation sweep (weighted Jacobi on L u = rho with the boundary values of u held fixed --
+ * the Dirichlet problem of examples/poisson.jl:75-81): u <- u + theta * ((1-b) .* ((rho - L u) ./ diag(L))),
+ * `nsweeps` times, one pass over the rows per sweep (same kernels as the wave step). */
+int ddf_poisson_jacobi(ddf_mesh* mesh, ddf_vec* u, ddf_vec* rho, double theta, int nsweeps);
 /* one leapfrog step timed alone is exposed through ddf_timer_*; the algorithmic
  * byte count of a step (E*16 + V*41) is returned here for reporting */
 int ddf_wave_step_bytes(ddf_mesh* mesh, int64_t* algorithmic, int64_t* format_bytes);

@@ -209,6 +209,13 @@ function bicgstabl!(x::DeviceVector, A::DeviceOp, b::DeviceVector; l::Int=2, rel
     return x, (mv_products=Int(mv[]), residual=res[], converged=conv[] != 0)
 end
 
+# fused Poisson relaxation sweep (north_star): u += theta (1-b).((rho - L u) ./ diag(L))
+function jacobi!(m::DeviceManifold, u::DeviceVector, rho::DeviceVector, theta::Float64, nsweeps::Int)
+    check(ccall((:ddf_poisson_jacobi, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint),
+                m.h, u.h, rho.h, theta, nsweeps))
+    return u
+end
+
 # fused step (north_star): v += dt (1-b).(L u); u += dt (1-b).v
 function leapfrog!(m::DeviceManifold, u::DeviceVector, v::DeviceVector, dt::Float64, nsteps::Int)
     check(ccall((:ddf_wave_leapfrog, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint),

@@ -864,6 +864,20 @@ def poisson_system(mfd: Manifold, rho: np.ndarray, u0: np.ndarray):
     return Ap, bp
 
 
+def poisson_jacobi(mfd: Manifold, u: np.ndarray, rho: np.ndarray, theta: float, nsweeps: int) -> np.ndarray:
+    """north_star's fused Poisson step (NOT in the reference, which solves with UMFPACK / BiCGStab(l)): weighted Jacobi
+    on L u = rho with the boundary values held fixed (the Dirichlet problem of poisson.jl:75-81),
+        u <- u + theta * ((1-b) .* ((rho - L u) ./ diag(L))),   every operation separately rounded."""
+    b, L = wave_operators(mfd)
+    m = 1.0 - b.astype(np.float64)
+    d = L.diagonal()
+    dinv = np.where(d != 0.0, 1.0 / np.where(d != 0.0, d, 1.0), 0.0)
+    u = u.copy()
+    for _ in range(nsweeps):
+        u = u + theta * (m * ((rho - spmv_csc(L, u)) * dinv))
+    return u
+
+
 def poisson_solve(mfd: Manifold, rho: np.ndarray, u0: np.ndarray):
     """x = A' \\ b' (poisson.jl:205-206; UMFPACK there, SuperLU here) split into (u, f)."""
     import scipy.sparse.linalg as spla
