@@ -297,27 +297,36 @@ struct LincombArgs {
 template <int N>
 __global__ void __launch_bounds__(256) k_lincomb(const double* base, double dt, LincombArgs a, double* out,
                                                  int64_t n) {   // out may alias base (same index, same thread)
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (i + 1 < n) {
-    double2 s = *reinterpret_cast<const double2*>(a.k[0] + i);
-    s.x = __dmul_rn(a.c[0], s.x);
-    s.y = __dmul_rn(a.c[0], s.y);
+  // four elements per thread as two 128-bit accesses per array, read-once loads, like k_apply_diag
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  if (i + 3 < n) {
+    double s[4];
+    {
+      const double2 k0 = ld_stream_f64x2(reinterpret_cast<const double2*>(a.k[0] + i));
+      const double2 k1 = ld_stream_f64x2(reinterpret_cast<const double2*>(a.k[0] + i + 2));
+      s[0] = __dmul_rn(a.c[0], k0.x); s[1] = __dmul_rn(a.c[0], k0.y);
+      s[2] = __dmul_rn(a.c[0], k1.x); s[3] = __dmul_rn(a.c[0], k1.y);
+    }
 #pragma unroll
     for (int j = 1; j < N; j++) {
-      const double2 kv = *reinterpret_cast<const double2*>(a.k[j] + i);
-      s.x = __dadd_rn(s.x, __dmul_rn(a.c[j], kv.x));
-      s.y = __dadd_rn(s.y, __dmul_rn(a.c[j], kv.y));
+      const double2 k0 = ld_stream_f64x2(reinterpret_cast<const double2*>(a.k[j] + i));
+      const double2 k1 = ld_stream_f64x2(reinterpret_cast<const double2*>(a.k[j] + i + 2));
+      s[0] = __dadd_rn(s[0], __dmul_rn(a.c[j], k0.x)); s[1] = __dadd_rn(s[1], __dmul_rn(a.c[j], k0.y));
+      s[2] = __dadd_rn(s[2], __dmul_rn(a.c[j], k1.x)); s[3] = __dadd_rn(s[3], __dmul_rn(a.c[j], k1.y));
     }
-    const double2 b = *reinterpret_cast<const double2*>(base + i);
-    double2 r;
-    r.x = __dadd_rn(b.x, __dmul_rn(dt, s.x));
-    r.y = __dadd_rn(b.y, __dmul_rn(dt, s.y));
-    *reinterpret_cast<double2*>(out + i) = r;
-  } else if (i < n) {
-    double s = __dmul_rn(a.c[0], a.k[0][i]);
+    // base is read with a plain load: it may be `out` itself
+    const double2 b0 = *reinterpret_cast<const double2*>(base + i);
+    const double2 b1 = *reinterpret_cast<const double2*>(base + i + 2);
+    st_stream_f64x2(reinterpret_cast<double2*>(out + i), __dadd_rn(b0.x, __dmul_rn(dt, s[0])), __dadd_rn(b0.y, __dmul_rn(dt, s[1])));
+    st_stream_f64x2(reinterpret_cast<double2*>(out + i + 2), __dadd_rn(b1.x, __dmul_rn(dt, s[2])), __dadd_rn(b1.y, __dmul_rn(dt, s[3])));
+  } else {
+    for (int64_t q = i; q < n; q++) {
+      double s = __dmul_rn(a.c[0], a.k[0][q]);
 #pragma unroll
-    for (int j = 1; j < N; j++) s = __dadd_rn(s, __dmul_rn(a.c[j], a.k[j][i]));
-    out[i] = __dadd_rn(base[i], __dmul_rn(dt, s));
+      for (int j = 1; j < N; j++) s = __dadd_rn(s, __dmul_rn(a.c[j], a.k[j][q]));
+      out[q] = __dadd_rn(base[q], __dmul_rn(dt, s));
+    }
   }
 }
 
@@ -328,7 +337,7 @@ int ddf_lincomb_launch(ddf_ctx* ctx, const double* base, double dt, int nk, cons
   LincombArgs a{};
   for (int j = 0; j < nk; j++) { a.k[j] = ks[j]; a.c[j] = coef[j]; }
   int grid;
-  DDF_CHECK(grid_for(ceil_div64(n, 2), 256, &grid));
+  DDF_CHECK(grid_for(ceil_div64(n, 4), 256, &grid));
   switch (nk) {
     case 1: k_lincomb<1><<<grid, 256, 0, ctx->stream>>>(base, dt, a, out, n); break;
     case 2: k_lincomb<2><<<grid, 256, 0, ctx->stream>>>(base, dt, a, out, n); break;

@@ -116,6 +116,7 @@ struct ddf_mesh {
   FStageBufs fstage[DDF_MAXD + 1];
   DevBuf<double> utmp;                   // V   ping-pong buffer of the fused step
   DevBuf<double> ldinv;                  // V   1 ./ diag(L) for the fused Poisson relaxation step
+  DevBuf<double> tsit_work;              // 16 V  stage derivatives and scratch of ddf_wave_tsit5 (allocated on first use)
 
   // slab halo of the distributed wave step (comm.cu): vertex planes along the
   // slowest axis; the first halo_lo / last halo_hi planes are ghosts owned by rank-1 / rank+1

@@ -903,14 +903,13 @@ extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt,
   if (!nv || nsteps <= 0) return 0;
   DDF_CHECK(ddf_vec_settle(u));
   DDF_CHECK(ddf_vec_settle(udot));
-  // work space: k1..k7 and tmp, each for (u, udot)
-  DevBuf<double> k[7][2], tmp[2];
-  for (int s = 0; s < 7; s++)
-    for (int c = 0; c < 2; c++) DDF_CHECK(k[s][c].alloc(ctx, nv));
-  for (int c = 0; c < 2; c++) DDF_CHECK(tmp[c].alloc(ctx, nv));
+  // work space: k1..k7 and tmp, each for (u, udot): 16 vertex vectors, kept with the mesh between calls
+  const size_t nvp = ((size_t)nv + 1) & ~(size_t)1;       // even stride: every sub-vector stays 16-byte aligned (TMA, 128-bit loads)
+  if (m->tsit_work.n != 16 * nvp) DDF_CHECK(m->tsit_work.alloc(ctx, 16 * nvp));
   double* kp[7][2];
   for (int s = 0; s < 7; s++)
-    for (int c = 0; c < 2; c++) kp[s][c] = k[s][c].p;
+    for (int c = 0; c < 2; c++) kp[s][c] = m->tsit_work.p + (size_t)(2 * s + c) * nvp;
+  struct { double* p; } tmp[2] = {{m->tsit_work.p + 14 * nvp}, {m->tsit_work.p + 15 * nvp}};
   double* U[2] = {u->d.p, udot->d.p};
   DDF_CHECK(wave_rhs_launch(m, U[0], U[1], kp[0][0], kp[0][1]));
   for (int step = 0; step < nsteps; step++) {
