@@ -158,6 +158,9 @@ static int halo_exchange_on(ddf_mesh* m, double* u, cudaStream_t stream) {
   return 0;
 }
 
+// raw-pointer variant for the integrators of wave.cu (vertex cochain on the compute stream)
+int ddf_halo_exchange_raw(ddf_mesh* m, double* u) { return halo_exchange_on(m, u, m->ctx->stream); }
+
 extern "C" int ddf_halo_exchange(ddf_mesh* m, ddf_vec* u) {
   DDF_TRY_BEGIN
   if (u->n != m->n[0]) DDF_FAIL("halo_exchange: vector must be a vertex cochain");

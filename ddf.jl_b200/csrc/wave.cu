@@ -874,6 +874,8 @@ extern "C" int ddf_wave_leapfrog(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt,
 int ddf_lincomb_launch(ddf_ctx* ctx, const double* base, double dt, int nk, const double* coef, const double* const* ks,
                        double* out, int64_t n);   // core.cu
 
+int ddf_halo_exchange_raw(ddf_mesh* m, double* u);     // comm.cu
+
 static const double TSIT5_A[6][6] = {
     {0.161, 0, 0, 0, 0, 0},
     {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
@@ -911,6 +913,10 @@ extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt,
     for (int c = 0; c < 2; c++) kp[s][c] = m->tsit_work.p + (size_t)(2 * s + c) * nvp;
   struct { double* p; } tmp[2] = {{m->tsit_work.p + 14 * nvp}, {m->tsit_work.p + 15 * nvp}};
   double* U[2] = {u->d.p, udot->d.p};
+  // slab meshes (one rank per GPU): the ghost planes of the state every right-hand side reads are refreshed from
+  // their owners first; ghost rows of the derivatives are scratch and never reach an owned row
+  const bool dist = ctx->nranks > 1 && m->halo_plane > 0;
+  if (dist) DDF_CHECK(ddf_halo_exchange_raw(m, U[0]));
   DDF_CHECK(wave_rhs_launch(m, U[0], U[1], kp[0][0], kp[0][1]));
   for (int step = 0; step < nsteps; step++) {
     for (int s = 0; s < 6; s++) {
@@ -921,8 +927,9 @@ extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt,
         for (int j = 0; j <= s; j++) ks[j] = kp[j][c];
         DDF_CHECK(ddf_lincomb_launch(ctx, U[c], dt, s + 1, TSIT5_A[s], ks, s == 5 ? U[c] : dst[c], nv));
       }
-      const double* su = s == 5 ? U[0] : dst[0];
+      double* su = s == 5 ? U[0] : dst[0];
       const double* sv = s == 5 ? U[1] : dst[1];
+      if (dist) DDF_CHECK(ddf_halo_exchange_raw(m, su));
       DDF_CHECK(wave_rhs_launch(m, su, sv, kp[s + 1][0], kp[s + 1][1]));
     }
     for (int c = 0; c < 2; c++) std::swap(kp[0][c], kp[6][c]);     // FSAL

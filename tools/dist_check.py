@@ -63,6 +63,30 @@ def main():
             ok = ok and same
             full.close()
         mfd.close()
+    # the reference's integrator on slabs: fixed-step Tsit5 with a ghost-plane exchange before every right-hand side
+    for D, nelts, nsteps in ((3, (8, 8, 8 * world), 3), (2, (16, 16 * world), 4)):
+        mfd, slab = ddf.dist.slab_hypercube(D, nelts, ctx)
+        u, v = ddf.sample(mfd, "wave"), ddf.Fun(mfd, ddf.Pr, 0)
+        dt = ctx.allreduce(ddf.wave_dt(mfd), "min")
+        ddf.wave_tsit5(mfd, u, v, dt, nsteps)
+        lo, hi = slab.own_rows
+        parts = [None] * world
+        dist.all_gather_object(parts, (slab.z_own_lo, u.values[lo:hi].copy(), v.values[lo:hi].copy()))
+        if rank == 0:
+            full = ddf.large_hypercube_manifold(D, nelts, ctx=ctx, hdiv=nelts[0])
+            fu, fv = ddf.sample(full, "wave"), ddf.Fun(full, ddf.Pr, 0)
+            ctx.nranks_save = None
+            ddf._lib.call("ddf_wave_tsit5", full._h, fu._h, fv._h, float(dt), int(nsteps))
+            ru, rv = fu.values, fv.values
+            same = True
+            for zlo, pu, pv in sorted(parts, key=lambda t: t[0]):
+                a = zlo * slab.plane
+                same = same and np.array_equal(pu, ru[a:a + len(pu)]) and np.array_equal(pv, rv[a:a + len(pv)])
+            print(f"dist_check tsit5 D={D} nelts={nelts} world={world} steps={nsteps}: {'BIT-EXACT' if same else 'MISMATCH'}",
+                  flush=True)
+            ok = ok and same
+            full.close()
+        mfd.close()
     # ghost exchange of cochains of every rank: a globally consistent R-cochain (a function of the simplex's
     # global vertex coordinates), ghost entries wiped, exchanged, must come back bit for bit
     ddf._lib.call("ddf_set_tuning", b"wave", 0)
