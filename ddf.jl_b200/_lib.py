@@ -100,6 +100,7 @@ SIGNATURES = {
     "ddf_wave_leapfrog": [_P, _P, _P, _f64, _int],
     "ddf_wave_tsit5": [_P, _P, _P, _f64, _int],
     "ddf_poisson_jacobi": [_P, _P, _P, _f64, _int],
+    "ddf_poisson_jacobi_dist": [_P, _P, _P, _f64, _int],
     "ddf_halo_mode": [_P, _intp],
     "ddf_solve_bicgstabl": [_P, _P, _P, _int, _f64, _f64, _int, _intp, _f64p, _intp],
     "ddf_vec_lincomb": [_P, _P, _f64, _int, _f64p, _PP],

@@ -21,6 +21,9 @@ int ddf_leapfrog_launch(ddf_mesh* m, cudaStream_t stream, const double* u, doubl
                         int64_t row0, int64_t row1);   // wave.cu
 int ddf_leapfrog_launch_p2p(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
                             int64_t row0, int64_t row1, double* peer_lo, double* peer_hi, int64_t plane);   // wave.cu
+int ddf_step_launch(ddf_mesh* m, cudaStream_t stream, int kind, const double* u, double* aux, double* unew, double coef,
+                    int64_t row0, int64_t row1, double* peer_lo, double* peer_hi, int64_t plane);           // wave.cu
+int ddf_mesh_require_dinv(ddf_mesh* m);                                                                      // wave.cu
 extern int g_tune_wave;
 
 struct NcclApi {
@@ -312,7 +315,8 @@ static int halo_handshake(ddf_mesh* m, int* usable) {
   return 0;
 }
 
-static int leapfrog_dist_p2p(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt, int nsteps) {
+// kind 0: leapfrog (aux = v, coef = dt); kind 1: Poisson relaxation sweep (aux = rho, coef = theta)
+static int steps_dist_p2p(ddf_mesh* m, int kind, ddf_vec* u, ddf_vec* v, double dt, int nsteps) {
   ddf_ctx* ctx = m->ctx;
   HaloP2P* hp = (HaloP2P*)m->halo_p2p;
   const int64_t nv = m->n[0], P = m->halo_plane;
@@ -336,9 +340,9 @@ static int leapfrog_dist_p2p(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt, int
         copy && has_hi ? HaloP2P::landing(hp->arena.p, 1, par_in, P) : nullptr, uo + own_hi, P);
     DDF_LAUNCH_CHECK(ctx);
     // I am the UPPER neighbour of rank-1 and the LOWER neighbour of rank+1
-    DDF_CHECK(ddf_leapfrog_launch_p2p(m, ctx->stream, uo, v->d.p, m->utmp.p, dt, own_lo, own_hi,
-                                      has_lo ? HaloP2P::landing(hp->lo_base, 1, par_out, P) : nullptr,
-                                      has_hi ? HaloP2P::landing(hp->hi_base, 0, par_out, P) : nullptr, P));
+    DDF_CHECK(ddf_step_launch(m, ctx->stream, kind, uo, v->d.p, m->utmp.p, dt, own_lo, own_hi,
+                              has_lo ? HaloP2P::landing(hp->lo_base, 1, par_out, P) : nullptr,
+                              has_hi ? HaloP2P::landing(hp->hi_base, 0, par_out, P) : nullptr, P));
     k_halo_signal<<<1, 1, 0, ctx->stream>>>(has_lo ? reinterpret_cast<unsigned long long*>(hp->lo_base) + 1 : nullptr,
                                             has_hi ? reinterpret_cast<unsigned long long*>(hp->hi_base) + 0 : nullptr, k);
     DDF_LAUNCH_CHECK(ctx);
@@ -545,14 +549,14 @@ extern "C" int ddf_halo_mode(ddf_mesh* m, int* mode) {
   return 0;
 }
 
-extern "C" int ddf_wave_leapfrog_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt, int nsteps) {
-  DDF_TRY_BEGIN
+static int steps_dist(ddf_mesh* m, int kind, ddf_vec* u, ddf_vec* v, double dt, int nsteps) {
   ddf_ctx* ctx = m->ctx;
-  if (ctx->nranks == 1 && !m->halo_plane) return ddf_wave_leapfrog(m, u, v, dt, nsteps);
   DDF_CHECK(ddf_mesh_require_wave(m));
+  if (kind == 1) DDF_CHECK(ddf_mesh_require_dinv(m));
   const int64_t nv = m->n[0];
-  if (u->n != nv || v->n != nv) DDF_FAIL("wave_leapfrog_dist: vectors must have length n0");
-  if (!m->halo_plane) DDF_FAIL("wave_leapfrog_dist: slab not described (ddf_mesh_set_halo)");
+  if (u->n != nv || v->n != nv) DDF_FAIL("distributed step: vectors must have length n0");
+  if (u == v) DDF_FAIL("distributed step: the two vectors must not alias");
+  if (!m->halo_plane) DDF_FAIL("distributed step: slab not described (ddf_mesh_set_halo)");
   DDF_CHECK(ddf_vec_settle(u));
   DDF_CHECK(ddf_vec_settle(v));
   if ((int64_t)m->utmp.n != nv) {
@@ -572,7 +576,7 @@ extern "C" int ddf_wave_leapfrog_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* v, doubl
     }
     if (m->halo_p2p_state == 1) {
       m->halo_last = 1;
-      return leapfrog_dist_p2p(m, u, v, dt, nsteps);
+      return steps_dist_p2p(m, kind, u, v, dt, nsteps);
     }
   }
   m->halo_last = 2;
@@ -581,10 +585,16 @@ extern "C" int ddf_wave_leapfrog_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* v, doubl
     double* un = m->utmp.p;
     // interface planes first, so that their transfer overlaps the interior rows
     int64_t lo_end = own_lo, hi_beg = own_hi;
-    if (m->halo_lo > 0) { lo_end = own_lo + P < own_hi ? own_lo + P : own_hi; DDF_CHECK(ddf_leapfrog_launch(m, ctx->stream, uo, v->d.p, un, dt, own_lo, lo_end)); }
-    if (m->halo_hi > 0) { hi_beg = own_hi - P > lo_end ? own_hi - P : lo_end; DDF_CHECK(ddf_leapfrog_launch(m, ctx->stream, uo, v->d.p, un, dt, hi_beg, own_hi)); }
+    if (m->halo_lo > 0) {
+      lo_end = own_lo + P < own_hi ? own_lo + P : own_hi;
+      DDF_CHECK(ddf_step_launch(m, ctx->stream, kind, uo, v->d.p, un, dt, own_lo, lo_end, nullptr, nullptr, P));
+    }
+    if (m->halo_hi > 0) {
+      hi_beg = own_hi - P > lo_end ? own_hi - P : lo_end;
+      DDF_CHECK(ddf_step_launch(m, ctx->stream, kind, uo, v->d.p, un, dt, hi_beg, own_hi, nullptr, nullptr, P));
+    }
     DDF_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
-    DDF_CHECK(ddf_leapfrog_launch(m, ctx->stream, uo, v->d.p, un, dt, lo_end, hi_beg));
+    DDF_CHECK(ddf_step_launch(m, ctx->stream, kind, uo, v->d.p, un, dt, lo_end, hi_beg, nullptr, nullptr, P));
     DDF_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));
     DDF_CHECK(halo_exchange_on(m, un, ctx->comm_stream));
     DDF_CUDA(cudaEventRecord(ctx->ev_b, ctx->comm_stream));
@@ -592,5 +602,20 @@ extern "C" int ddf_wave_leapfrog_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* v, doubl
     u->d.swap(m->utmp);
   }
   return 0;
+}
+
+extern "C" int ddf_wave_leapfrog_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt, int nsteps) {
+  DDF_TRY_BEGIN
+  if (m->ctx->nranks == 1 && !m->halo_plane) return ddf_wave_leapfrog(m, u, v, dt, nsteps);
+  return steps_dist(m, 0, u, v, dt, nsteps);
+  DDF_TRY_END
+}
+
+// the fused Poisson relaxation sweep on slab meshes: same halo protocols as the wave step (peer-memory stores of the
+// interface planes + step flags, or NCCL send/recv), u ping-pong, rho read-only
+extern "C" int ddf_poisson_jacobi_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* rho, double theta, int nsweeps) {
+  DDF_TRY_BEGIN
+  if (m->ctx->nranks == 1 && !m->halo_plane) return ddf_poisson_jacobi(m, u, rho, theta, nsweeps);
+  return steps_dist(m, 1, u, rho, theta, nsweeps);
   DDF_TRY_END
 }

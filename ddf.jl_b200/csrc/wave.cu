@@ -221,7 +221,9 @@ __device__ __forceinline__ void row_epilogue(const RowArgs& a, int64_t i, double
     a.out1[i] = __dmul_rn(m, lu);
   } else if (MODE == 3) {
     const double m = a.isb[i] ? 0.0 : 1.0;
-    a.out1[i] = jacobi_update(a.u[i], lu, a.rho[i], a.dinv[i], m, a.theta);
+    const double w = jacobi_update(a.u[i], lu, a.rho[i], a.dinv[i], m, a.theta);
+    a.out1[i] = w;
+    peer_store(a, i, w);
   } else {
     const double m = a.isb[i] ? 0.0 : 1.0;
     const double vn = __dadd_rn(a.out0[i], __dmul_rn(a.dt, __dmul_rn(m, lu)));
@@ -395,7 +397,9 @@ k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* _
     a.out0[i] = __dmul_rn(m, e0);
     a.out1[i] = __dmul_rn(m, lu);
   } else if (MODE == 3) {
-    a.out1[i] = jacobi_update(e1, lu, e0, e2, eb ? 0.0 : 1.0, a.theta);
+    const double w = jacobi_update(e1, lu, e0, e2, eb ? 0.0 : 1.0, a.theta);
+    a.out1[i] = w;
+    peer_store(a, i, w);
   } else {
     const double m = eb ? 0.0 : 1.0;
     const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, lu)));
@@ -571,7 +575,9 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
               a.out0[i] = __dmul_rn(m, e0);
               a.out1[i] = __dmul_rn(m, acc);
             } else if (MODE == 3) {
-              a.out1[i] = jacobi_update(reinterpret_cast<const double*>(sb + g.o_u)[pl], acc, e0, dinv_i, m, a.theta);
+              const double w = jacobi_update(reinterpret_cast<const double*>(sb + g.o_u)[pl], acc, e0, dinv_i, m, a.theta);
+              a.out1[i] = w;
+              peer_store(a, i, w);
             } else {
               const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, acc)));
               a.out0[i] = vn;
@@ -835,6 +841,31 @@ int ddf_leapfrog_launch_p2p(ddf_mesh* m, cudaStream_t stream, const double* u, d
   return launch_rows<2>(m, stream, a);
 }
 
+// One fused step on rows [row0, row1) for the distributed drivers of comm.cu.
+// kind 0: leapfrog (aux = v, in/out; coef = dt)    kind 1: Poisson relaxation sweep (aux = rho; coef = theta)
+int ddf_step_launch(ddf_mesh* m, cudaStream_t stream, int kind, const double* u, double* aux, double* unew, double coef,
+                    int64_t row0, int64_t row1, double* peer_lo, double* peer_hi, int64_t plane) {
+  RowArgs a{};
+  a.u = u;
+  a.out1 = unew;
+  a.row0 = row0;
+  a.row1 = row1;
+  a.peer_lo = peer_lo;
+  a.peer_hi = peer_hi;
+  a.send_lo_end = row0 + plane;
+  a.send_hi_beg = row1 - plane;
+  if (kind == 0) {
+    a.out0 = aux;
+    a.dt = coef;
+    return launch_rows<2>(m, stream, a);
+  }
+  if ((int64_t)m->ldinv.n != m->n[0]) DDF_FAIL("step_launch: 1/diag(L) not built");
+  a.rho = aux;
+  a.dinv = m->ldinv.p;
+  a.theta = coef;
+  return launch_rows<3>(m, stream, a);
+}
+
 int ddf_leapfrog_launch(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
                         int64_t row0, int64_t row1) {
   RowArgs a{};
@@ -950,6 +981,19 @@ __global__ void k_laplace0_dinv(const uint32_t* __restrict__ rowptr, const int32
   dinv[i] = d != 0.0 ? __ddiv_rn(1.0, d) : 0.0;
 }
 
+int ddf_mesh_require_dinv(ddf_mesh* m) {
+  DDF_CHECK(ddf_mesh_require_wave(m));
+  const int64_t nv = m->n[0];
+  if ((int64_t)m->ldinv.n == nv) return 0;
+  DDF_CHECK(m->ldinv.alloc(m->ctx, nv));
+  if (!nv) return 0;
+  int grid;
+  DDF_CHECK(grid_for(nv, 256, &grid));
+  k_laplace0_dinv<<<grid, 256, 0, m->ctx->stream>>>(m->adj_ptr.p, m->adj_nbr.p, m->adj_l.p, nv, m->ldinv.p);
+  DDF_LAUNCH_CHECK(m->ctx);
+  return 0;
+}
+
 // Fused Poisson relaxation step (north_star kernel (3), "wave/Poisson step"): weighted Jacobi on
 //   L u = rho in the interior, u fixed on the boundary   (examples/poisson.jl:75-81, 172-201 with f eliminated)
 //   u' = u + theta * ((1-b) .* ((rho - L u) ./ diag(L)))
@@ -964,13 +1008,7 @@ extern "C" int ddf_poisson_jacobi(ddf_mesh* m, ddf_vec* u, ddf_vec* rho, double 
   if (!nv || nsweeps <= 0) return 0;
   DDF_CHECK(ddf_vec_settle(u));
   DDF_CHECK(ddf_vec_settle(rho));
-  if ((int64_t)m->ldinv.n != nv) {
-    DDF_CHECK(m->ldinv.alloc(ctx, nv));
-    int grid;
-    DDF_CHECK(grid_for(nv, 256, &grid));
-    k_laplace0_dinv<<<grid, 256, 0, ctx->stream>>>(m->adj_ptr.p, m->adj_nbr.p, m->adj_l.p, nv, m->ldinv.p);
-    DDF_LAUNCH_CHECK(ctx);
-  }
+  DDF_CHECK(ddf_mesh_require_dinv(m));
   if ((int64_t)m->utmp.n != nv) DDF_CHECK(m->utmp.alloc(ctx, nv));
   for (int s = 0; s < nsweeps; s++) {
     RowArgs a{};

@@ -42,7 +42,8 @@ def poisson_jacobi(mfd: Manifold, u: Fun, rho: Fun, theta: float = 2.0 / 3.0, ns
     """In-place fused relaxation sweeps on L u = rho with the boundary values of u held fixed:
     u <- u + theta * ((1-b) .* ((rho - L u) ./ diag(L)))."""
     mfd._geometry()
-    call("ddf_poisson_jacobi", mfd._h, u._h, rho._h, float(theta), int(nsweeps))
+    fn = "ddf_poisson_jacobi_dist" if mfd.ctx.nranks > 1 else "ddf_poisson_jacobi"
+    call(fn, mfd._h, u._h, rho._h, float(theta), int(nsweeps))
     return u
 
 

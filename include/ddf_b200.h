@@ -226,6 +226,8 @@ int ddf_mesh_set_halo(ddf_mesh* mesh, int64_t plane, int64_t ghost_lo, int64_t g
 /* fused leapfrog on the owned rows + one-plane halo exchange of u per step with
  * ncclSend/ncclRecv to rank-1 / rank+1, overlapped with the interior rows. */
 int ddf_wave_leapfrog_dist(ddf_mesh* mesh, ddf_vec* u, ddf_vec* v, double dt, int nsteps);
+/* ddf_poisson_jacobi on a slab mesh: the same halo protocols as the distributed wave step */
+int ddf_poisson_jacobi_dist(ddf_mesh* mesh, ddf_vec* u, ddf_vec* rho, double theta, int nsweeps);
 /* how the last ddf_wave_leapfrog_dist moved its ghost planes: 0 = not run yet, 1 = fused peer-memory stores
  * (the row kernel writes the interface planes straight into the neighbours' ghost planes over NVLink; neighbours
  * are kept within one step by release/acquire step flags in peer memory), 2 = ncclSend/ncclRecv (fallback when

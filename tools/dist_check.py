@@ -63,6 +63,32 @@ def main():
             ok = ok and same
             full.close()
         mfd.close()
+    # fused Poisson relaxation sweeps on slabs, both halo protocols
+    for tune, (D, nelts, nsw) in [(t, c) for t in (0, 1024) for c in ((3, (8, 8, 8 * world), 7), (3, (32, 32, 8 * world), 4))]:
+        ddf._lib.call("ddf_set_tuning", b"wave", tune)
+        mfd, slab = ddf.dist.slab_hypercube(D, nelts, ctx)
+        u, rho = ddf.sample(mfd, "wave"), ddf.sample(mfd, "poisson_rho")
+        for part in (1, 2, nsw - 3):
+            ddf.poisson_jacobi(mfd, u, rho, 2.0 / 3.0, part)
+        mode = ddf.dist.halo_mode(mfd)
+        lo, hi = slab.own_rows
+        parts = [None] * world
+        dist.all_gather_object(parts, (slab.z_own_lo, u.values[lo:hi].copy()))
+        if rank == 0:
+            full = ddf.large_hypercube_manifold(D, nelts, ctx=ctx, hdiv=nelts[0])
+            fu, frho = ddf.sample(full, "wave"), ddf.sample(full, "poisson_rho")
+            ddf._lib.call("ddf_poisson_jacobi", full._h, fu._h, frho._h, 2.0 / 3.0, int(nsw))
+            ru = fu.values
+            same = True
+            for zlo, pu in sorted(parts, key=lambda t: t[0]):
+                a = zlo * slab.plane
+                same = same and np.array_equal(pu, ru[a:a + len(pu)])
+            print(f"dist_check jacobi halo={mode} D={D} nelts={nelts} world={world} sweeps={nsw}: "
+                  f"{'BIT-EXACT' if same else 'MISMATCH'}", flush=True)
+            ok = ok and same
+            full.close()
+        mfd.close()
+    ddf._lib.call("ddf_set_tuning", b"wave", 0)
     # the reference's integrator on slabs: fixed-step Tsit5 with a ghost-plane exchange before every right-hand side
     for D, nelts, nsteps in ((3, (8, 8, 8 * world), 3), (2, (16, 16 * world), 4)):
         mfd, slab = ddf.dist.slab_hypercube(D, nelts, ctx)
