@@ -17,10 +17,6 @@
 
 #include "mesh.cuh"
 
-int ddf_leapfrog_launch(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
-                        int64_t row0, int64_t row1);   // wave.cu
-int ddf_leapfrog_launch_p2p(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
-                            int64_t row0, int64_t row1, double* peer_lo, double* peer_hi, int64_t plane);   // wave.cu
 int ddf_step_launch(ddf_mesh* m, cudaStream_t stream, int kind, const double* u, double* aux, double* unew, double coef,
                     int64_t row0, int64_t row1, double* peer_lo, double* peer_hi, int64_t plane);           // wave.cu
 int ddf_mesh_require_dinv(ddf_mesh* m);                                                                      // wave.cu

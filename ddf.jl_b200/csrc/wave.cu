@@ -825,22 +825,6 @@ extern "C" int ddf_wave_dt(ddf_mesh* m, double* dt) {
 //   v' = v + dt * ((1-b) .* (L u));   u' = u + dt * ((1-b) .* v')
 // One pass: u is read (own value + gathered neighbours), u' goes to the ping-pong
 // buffer so neighbours still see the old u.  Rows [row0, row1) on `stream`.
-int ddf_leapfrog_launch_p2p(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
-                            int64_t row0, int64_t row1, double* peer_lo, double* peer_hi, int64_t plane) {
-  RowArgs a{};
-  a.u = u;
-  a.out0 = v;
-  a.out1 = unew;
-  a.dt = dt;
-  a.row0 = row0;
-  a.row1 = row1;
-  a.peer_lo = peer_lo;
-  a.peer_hi = peer_hi;
-  a.send_lo_end = row0 + plane;
-  a.send_hi_beg = row1 - plane;
-  return launch_rows<2>(m, stream, a);
-}
-
 // One fused step on rows [row0, row1) for the distributed drivers of comm.cu.
 // kind 0: leapfrog (aux = v, in/out; coef = dt)    kind 1: Poisson relaxation sweep (aux = rho; coef = theta)
 int ddf_step_launch(ddf_mesh* m, cudaStream_t stream, int kind, const double* u, double* aux, double* unew, double coef,
