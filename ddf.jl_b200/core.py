@@ -448,6 +448,11 @@ class Op:
         call("ddf_op_apply", self._h, x._h, out._h)
         return out
 
+    def assemble(self) -> "Op":
+        """This operator held the way the reference holds every Op: as its assembled sparse matrix (Ops.jl:25), with
+        the constructor's dnz/chop after every product and sum.  `A.assemble() * f` is one row kernel."""
+        return self._new("ddf_op_assemble", self._h)
+
     def to_csc(self):
         """Assembled `.values` with dnz/chop applied (Ops.jl:25,36-58) as a scipy CSC."""
         import scipy.sparse as sp

@@ -493,6 +493,84 @@ int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n
   return 0;
 }
 
+// All inner products <v_r, v_c>, r <= c, of up to 8 vectors in one pass and one host synchronisation (the
+// Gram matrix of BiCGStab(l)'s minimal-residual step, solve.cu).  Each block owns a contiguous range and
+// writes its npairs partial sums; the host adds the blocks in index order, so the result is deterministic.
+struct GramPtrs {
+  const double* p[8];
+};
+template <int NV>
+__global__ void k_gram(GramPtrs vs, int64_t n, double* __restrict__ partial) {
+  constexpr int NP = NV * (NV + 1) / 2;
+  __shared__ double sm[8][NP];
+  double acc[NP];
+#pragma unroll
+  for (int k = 0; k < NP; k++) acc[k] = 0.0;
+  int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  int64_t lo = (int64_t)blockIdx.x * per;
+  int64_t hi = lo + per < n ? lo + per : n;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    double x[NV];
+#pragma unroll
+    for (int r = 0; r < NV; r++) x[r] = vs.p[r][i];
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < NV; r++)
+#pragma unroll
+      for (int c = r; c < NV; c++) acc[k++] += x[r] * x[c];
+  }
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NP; k++) {
+    double a = acc[k];
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+    if (lane == 0) sm[w][k] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < NP) {
+    double a = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); q++) a += sm[q][threadIdx.x];
+    partial[(int64_t)blockIdx.x * NP + threadIdx.x] = a;
+  }
+}
+
+// out[r * nv + c] = <v_r, v_c> (symmetric, both triangles filled)
+int ddf_vec_gram(ddf_ctx* c, int nv, ddf_vec* const* vs, double* out) {
+  if (nv < 1 || nv > 8) DDF_FAIL("vec_gram: 1 <= nv <= 8, got %d", nv);
+  GramPtrs g{};
+  const int64_t n = vs[0]->n;
+  for (int r = 0; r < nv; r++) {
+    if (vs[r]->n != n) DDF_FAIL("vec_gram: length mismatch");
+    DDF_CHECK(ddf_vec_settle(vs[r]));
+    g.p[r] = vs[r]->d.p;
+  }
+  const int np = nv * (nv + 1) / 2;
+  int grid = (int)(ceil_div64(n, 2048) < 4096 / np ? ceil_div64(n, 2048) : 4096 / np);
+  if (grid < 1) grid = 1;
+  switch (nv) {
+    case 1: k_gram<1><<<grid, 256, 0, c->stream>>>(g, n, c->red_dev); break;
+    case 2: k_gram<2><<<grid, 256, 0, c->stream>>>(g, n, c->red_dev); break;
+    case 3: k_gram<3><<<grid, 256, 0, c->stream>>>(g, n, c->red_dev); break;
+    case 4: k_gram<4><<<grid, 256, 0, c->stream>>>(g, n, c->red_dev); break;
+    case 5: k_gram<5><<<grid, 256, 0, c->stream>>>(g, n, c->red_dev); break;
+    case 6: k_gram<6><<<grid, 256, 0, c->stream>>>(g, n, c->red_dev); break;
+    case 7: k_gram<7><<<grid, 256, 0, c->stream>>>(g, n, c->red_dev); break;
+    default: k_gram<8><<<grid, 256, 0, c->stream>>>(g, n, c->red_dev); break;
+  }
+  DDF_LAUNCH_CHECK(c);
+  DDF_CUDA(cudaMemcpyAsync(c->red_host, c->red_dev, (size_t)grid * np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  DDF_CUDA(cudaStreamSynchronize(c->stream));
+  int k = 0;
+  for (int r = 0; r < nv; r++)
+    for (int cc = r; cc < nv; cc++, k++) {
+      double a = 0.0;
+      for (int b = 0; b < grid; b++) a += c->red_host[(size_t)b * np + k];
+      out[r * nv + cc] = a;
+      out[cc * nv + r] = a;
+    }
+  return 0;
+}
+
 extern "C" int ddf_vec_norm(ddf_vec* v, int kind, double* out) {
   double r = 0;
   DDF_CHECK(ddf_vec_settle(v));

@@ -49,6 +49,8 @@ struct OpNode {
   DevBuf<int32_t> col;
   DevBuf<double> val;
   int64_t nnz = 0;
+  SellBufs sell;                  // CSRF64: SELL-32-256 copy of the rows, built at the first apply of a large operator
+  int sell_state = 0;             // 0 not tried, 1 built, 2 not worth it / failed
   // CHAIN (factors left to right) / SUM (coef, term)
   std::vector<OpRef> factors;
   std::vector<double> coefs;
@@ -310,6 +312,37 @@ __global__ void k_apply_csrf64(const uint32_t* __restrict__ rowptr, const int32_
   for (uint32_t p = lo; p < hi; p++) a = __dadd_rn(a, __dmul_rn(__ldg(val + p), __ldg(x + __ldg(col + p))));
   if (alpha != 1.0) a = __dmul_rn(alpha, a);
   y[i] = a;
+}
+
+// The same rows from SELL-32-256 storage (sell.cuh): one thread per row, a warp's index/value loads coalesced,
+// 8 gathers in flight.  Entries of a row keep their ascending-column order, so the result is bit-identical to
+// k_apply_csrf64.
+__global__ void __launch_bounds__(DDF_SELL_WIN)
+k_apply_sellf64(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict__ perm8, const uint32_t* __restrict__ scol,
+                const double* __restrict__ sval, int64_t nrows, const double* __restrict__ x, double* __restrict__ y) {
+  const int64_t r = (int64_t)blockIdx.x * DDF_SELL_WIN + threadIdx.x;        // sorted position
+  const int64_t i = (int64_t)blockIdx.x * DDF_SELL_WIN + perm8[r];           // the row it holds
+  const int64_t s = r >> 5;
+  const uint32_t base = sell_ptr[s] + (uint32_t)(r & 31);
+  const uint32_t w = (sell_ptr[s + 1] - sell_ptr[s]) >> 5;
+  double acc = 0.0;
+  for (uint32_t q0 = 0; q0 < w; q0 += 8) {
+    uint32_t j[8];
+    double l[8], xv[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const bool ok = q0 + q < w;                // warp-uniform
+      const size_t pos = (size_t)base + (size_t)(q0 + q) * 32;
+      j[q] = ok ? (uint32_t)ld_stream_int(reinterpret_cast<const int*>(scol) + pos) : DDF_SELL_PAD;
+      l[q] = ok ? ld_stream_f64(sval + pos) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) xv[q] = __ldg(x + (j[q] != DDF_SELL_PAD ? j[q] : 0u));
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (j[q] != DDF_SELL_PAD) acc = __dadd_rn(acc, __dmul_rn(l[q], xv[q]));
+  }
+  if (i < nrows) y[i] = acc;
 }
 
 extern int g_tune_wave;   // wave.cu
@@ -1295,6 +1328,23 @@ static int apply_node(OpNode* n, const double* x, double* y) {
     case OPK_DIAG: return launch_diag(ctx, n->diag, n->scale, x, y, n->nrows);
     case OPK_CSRF64: {
       if (!n->nrows) return 0;
+      if (n->sell_state == 0) {                  // large operators: SELL copy of the rows, once
+        n->sell_state = 2;
+        if (n->nrows >= 4 * DDF_SELL_WIN && n->nnz >= 2 * n->nrows && !(g_tune_fixed == 9) &&
+            sell_build(ctx, n->rowptr.p, reinterpret_cast<const uint32_t*>(n->col.p), n->val.p, n->nrows, n->sell,
+                       false, true, false) == 0 &&
+            n->sell.padded <= 2 * n->nnz)
+          n->sell_state = 1;
+        else
+          n->sell.release();
+      }
+      if (n->sell_state == 1) {
+        const int64_t nwin = ceil_div64(n->nrows, DDF_SELL_WIN);
+        k_apply_sellf64<<<(int)nwin, DDF_SELL_WIN, 0, ctx->stream>>>(n->sell.ptr.p, n->sell.perm8.p, n->sell.col.p,
+                                                                     n->sell.val.p, n->nrows, x, y);
+        DDF_LAUNCH_CHECK(ctx);
+        return 0;
+      }
       int grid;
       DDF_CHECK(grid_for(n->nrows, 256, &grid));
       k_apply_csrf64<<<grid, 256, 0, ctx->stream>>>(n->rowptr.p, n->col.p, n->val.p, n->nrows, x, 1.0, y);
@@ -1837,6 +1887,42 @@ static int materialise(OpNode* n, Coo& c) {
   }
   ddf_set_error("to_csc: this operator has no assembled form (kind %d)", (int)n->kind);
   return 1;
+}
+
+// The reference stores EVERY Op as its assembled sparse matrix (Ops.jl:25) and `A * f` is SparseArrays' mul! on it
+// (Ops.jl:262-266): this is that representation on the device -- the tree is materialised with the reference's
+// roundings and chops, then held as rows (ascending columns) so that an apply is one kernel.
+extern "C" int ddf_op_assemble(ddf_op* A, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  OpNode* n = A->node.get();
+  ddf_ctx* ctx = n->ctx;
+  Coo c;
+  DDF_CHECK(materialise(n, c));
+  DDF_CHECK(coo_transpose(ctx, c, n->nrows));   // sorted by (row, column): c.col = row, c.row = column
+  OpRef o = std::make_shared<OpNode>();
+  o->kind = OPK_CSRF64; o->ctx = ctx; o->mesh = n->mesh;
+  o->nrows = n->nrows; o->ncols = n->ncols; o->nnz = c.nnz;
+  DDF_CHECK(o->rowptr.alloc(ctx, o->nrows + 1));
+  DDF_CHECK(o->col.alloc(ctx, c.nnz));
+  DDF_CHECK(o->val.alloc(ctx, c.nnz));
+  int grid;
+  DevBuf<uint32_t> keys;
+  if (c.nnz) {
+    DDF_CHECK(keys.alloc(ctx, c.nnz));
+    DDF_CHECK(grid_for(c.nnz, 256, &grid));
+    k_i32_to_u32<<<grid, 256, 0, ctx->stream>>>(c.col.p, keys.p, c.nnz);
+    DDF_LAUNCH_CHECK(ctx);
+    DDF_CUDA(cudaMemcpyAsync(o->col.p, c.row.p, c.nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    DDF_CUDA(cudaMemcpyAsync(o->val.p, c.val.p, c.nnz * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  DDF_CHECK(grid_for(o->nrows + 1, 256, &grid));
+  k_lower_bound<<<grid, 256, 0, ctx->stream>>>(keys.p, c.nnz, o->nrows, o->rowptr.p);
+  DDF_LAUNCH_CHECK(ctx);
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = wrap(o);
+  return 0;
+  DDF_TRY_END
 }
 
 extern "C" int ddf_op_to_csc(ddf_op* A, int64_t* nnz, int64_t* colptr, int64_t* rowval, double* nzval) {

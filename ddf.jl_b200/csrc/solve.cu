@@ -16,6 +16,8 @@
 
 #include "common.cuh"
 
+int ddf_vec_gram(ddf_ctx* c, int nv, ddf_vec* const* vs, double* out);   // core.cu
+
 namespace {
 struct VecSet {
   std::vector<ddf_vec*> v;
@@ -103,22 +105,19 @@ extern "C" int ddf_solve_bicgstabl(ddf_op* A, ddf_vec* b, ddf_vec* x, int l, dou
       DDF_CHECK(ddf_vec_axpby(1.0, x, alpha, us[0], x));
     }
     // ---- minimal-residual part: gamma = argmin | rs[0] - sum_k gamma_k rs[k] |,  k = 1..l
-    double G[49], g[7];
+    double G[49], g[7], W[64];
+    DDF_CHECK(ddf_vec_gram(ctx, l + 1, rs.data(), W));      // one pass, one synchronisation for all (l+1)(l+2)/2 products
     for (int r = 1; r <= l; r++) {
-      for (int c = r; c <= l; c++) {
-        double d = 0;
-        DDF_CHECK(ddf_vec_dot(rs[r], rs[c], &d));
-        G[(r - 1) * l + (c - 1)] = d;
-        G[(c - 1) * l + (r - 1)] = d;
-      }
-      DDF_CHECK(ddf_vec_dot(rs[r], rs[0], &g[r - 1]));
+      for (int c = 1; c <= l; c++) G[(r - 1) * l + (c - 1)] = W[r * (l + 1) + c];
+      g[r - 1] = W[r * (l + 1)];
     }
     if (small_solve(l, G, g)) DDF_FAIL("bicgstabl: singular minimal-residual system after %d products", mv);
-    for (int k = 1; k <= l; k++) {
-      DDF_CHECK(ddf_vec_axpby(1.0, us[0], -g[k - 1], us[k], us[0]));
-      DDF_CHECK(ddf_vec_axpby(1.0, x, g[k - 1], rs[k - 1], x));
-    }
-    for (int k = 1; k <= l; k++) DDF_CHECK(ddf_vec_axpby(1.0, rs[0], -g[k - 1], rs[k], rs[0]));
+    // us[0] -= sum g_k us[k];  x += sum g_k rs[k-1];  rs[0] -= sum g_k rs[k]: one pass each (x before rs[0] changes)
+    double mg[7];
+    for (int k = 0; k < l; k++) mg[k] = -g[k];
+    DDF_CHECK(ddf_vec_lincomb(us[0], us[0], 1.0, l, mg, us.data() + 1));
+    DDF_CHECK(ddf_vec_lincomb(x, x, 1.0, l, g, rs.data()));
+    DDF_CHECK(ddf_vec_lincomb(rs[0], rs[0], 1.0, l, mg, rs.data() + 1));
     omega = g[l - 1];
     DDF_CHECK(ddf_vec_norm(rs[0], DDF_NORM_2, &nrm));
     ok = nrm <= tol;

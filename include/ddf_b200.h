@@ -178,6 +178,11 @@ int ddf_op_scale(double a, ddf_op* A, ddf_op** out);
 int ddf_op_adjoint(ddf_op* A, ddf_op** out);
 /* Op*Fun (Ops.jl:273-276): y = A x */
 int ddf_op_apply(ddf_op* A, ddf_vec* x, ddf_vec* y);
+/* The operator in the reference's own representation: every Op holds its assembled sparse matrix (Ops.jl:25),
+ * rounded and chopped after each product / sum (Ops.jl:36-58,186-232), and `A * f` is a sparse mat-vec on it
+ * (Ops.jl:273-276).  Returns a new operator whose apply is one row kernel over those values; the iterates of a
+ * Krylov solve on it then see the matrix the reference's solver sees (examples/poisson.jl:203-227). */
+int ddf_op_assemble(ddf_op* A, ddf_op** out);
 /* Assembled export in the reference's storage, with the Op constructor's
  * dnz/chop applied (Ops.jl:36-58).  Call with NULL arrays to query nnz. */
 int ddf_op_to_csc(ddf_op* A, int64_t* nnz, int64_t* colptr, int64_t* rowval, double* nzval);

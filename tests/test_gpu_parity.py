@@ -399,6 +399,33 @@ def test_assembled_products_bit_exact(ddf, pairs, kind):
     same(ddf.poisson_operator(dm).to_csc(), o.chop_sparse(o.chop_sparse((e0 - b0) @ o.laplace(o.Pr, 0, om)) + b0), "A'")
 
 
+@pytest.mark.parametrize("D,n", [(2, 6), (2, 48), (3, 4), (3, 14)])
+def test_assembled_apply_bit_exact(ddf, ctx, D, n):
+    """Op.assemble(): the operator held as the reference holds it (its assembled, chopped sparse matrix, Ops.jl:25)
+    and applied the way SparseArrays applies it (Ops.jl:273-276): same pattern and values as to_csc() of the
+    expression, and A*x bit for bit the oracle's Julia-order sparse mat-vec of that matrix -- on meshes small enough
+    for the plain row kernel and large enough for the SELL one."""
+    dm = ddf.large_hypercube_manifold(D, (n,) * D, ctx=ctx)
+    rng = np.random.default_rng(3 * D + n)
+    ops = {"poisson": ddf.poisson_operator(dm), "laplace1": ddf.laplace(ddf.Pr, 1, dm),
+           "delta1": ddf.coderiv(ddf.Pr, 1, dm), "d0": ddf.deriv(ddf.Pr, 0, dm), "star1": ddf.hodge(ddf.Pr, 1, dm),
+           "dd": ddf.deriv(ddf.Pr, 1, dm) * ddf.deriv(ddf.Pr, 0, dm)}
+    for name, A in ops.items():
+        M = A.to_csc()
+        B = A.assemble()
+        assert B.shape == A.shape and (B.P1, B.R1, B.P2, B.R2) == (A.P1, A.R1, A.P2, A.R2)
+        N = B.to_csc()
+        assert np.array_equal(M.indptr, N.indptr) and np.array_equal(M.indices, N.indices), name
+        assert np.array_equal(M.data, N.data), name
+        x = rng.standard_normal(A.shape[1])
+        y = (B * ddf.Fun(dm, A.P2, A.R2, x)).values
+        assert np.array_equal(y, o.spmv_csc(M, x)), name
+        # and it composes like any other operator
+        z = ((2.0 * B) * ddf.Fun(dm, A.P2, A.R2, x)).values
+        assert np.allclose(z, 2.0 * y, rtol=1e-15, atol=0)
+    dm.close()
+
+
 # ------------------------------------------------------------------ N2: Poisson solve
 @pytest.mark.parametrize("kind", ["refined2l4", "kuhn2n16", "kuhn3n4", "kuhn3n8"])
 def test_poisson_solve_matches_direct_solve(ddf, pairs, kind):
@@ -415,6 +442,10 @@ def test_poisson_solve_matches_direct_solve(ddf, pairs, kind):
     assert relerr(f.values, of) <= 1e-8
     b = o.calc_isboundary(om, 0)
     assert np.max(np.abs(u.values[b] - u0[b])) <= 1e-12 * np.abs(u0).max()      # Dirichlet rows
+    # the same solve on the assembled A' (what the reference's solver is handed)
+    ua, fa, infa = ddf.poisson_solve(dm, ddf.Fun(dm, ddf.Pr, 0, rho), ddf.Fun(dm, ddf.Pr, 0, u0), assembled=True,
+                                     reltol=1e-14, max_mv_products=20000)
+    assert infa["converged"] and relerr(ua.values, ou) <= 1e-9 and relerr(fa.values, of) <= 1e-8
     # the reference's own stopping rule (IterativeSolvers defaults) converges too
     _, _, out = ddf.poisson(om.D, 0, mfd=dm)
     assert out["converged"] and out["residual2"] < 1e-5 * max(1.0, np.abs(rho).max())
