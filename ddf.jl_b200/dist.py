@@ -126,3 +126,36 @@ def owned_mask(mfd, slab: "Slab", R: int) -> np.ndarray:
     lo, hi = slab.own_rows
     first = np.arange(mfd.nsimplices(0)) if R == 0 else mfd.get_simplices(R)[:, 0]
     return (first >= lo) & (first < hi)
+
+
+def owned_offsets(mfd, slab: "Slab", R: int, counts: Optional[Sequence[int]] = None):
+    """(offset, total): this rank's owned R-simplices are the global ids [offset, offset + count) of the undivided
+    mesh (a simplex belongs to the rank owning its smallest vertex; face ids are lexicographic ranks and
+    slabs own contiguous vertex ranges, so every rank's share is one contiguous id range in rank order).  `counts`
+    (owned count per rank) may be passed by a caller that already gathered them; otherwise they are summed over the
+    ranks with the context's all-reduce."""
+    mine = int(owned_mask(mfd, slab, R).sum())
+    if counts is None:
+        counts = [int(round(mfd.ctx.allreduce(float(mine if r == slab.rank else 0), "sum"))) if slab.nranks > 1 else mine
+                  for r in range(slab.nranks)]
+    return int(sum(counts[:slab.rank])), int(sum(counts))
+
+
+def global_ids(mfd, slab: "Slab", R: int, counts: Optional[Sequence[int]] = None) -> np.ndarray:
+    """Global id (0-based, the numbering `Manifold` gives the undivided mesh, Manifolds.jl:735-757) of every local
+    R-simplex.  Owned simplices: offset + rank among the owned ones (the local order is the global order, because the
+    local -> global vertex map is monotone); ghosts: their owners' ids, fetched with the rank-R ghost exchange."""
+    from .core import Fun, Pr
+    own = owned_mask(mfd, slab, R)
+    offset, total = owned_offsets(mfd, slab, R, counts)
+    if total >= 2 ** 53:
+        raise ValueError("global ids beyond 2^53 do not survive the Float64 ghost exchange")
+    gid = np.where(own, offset + np.cumsum(own) - 1, -1).astype(np.float64)
+    if slab.nranks > 1:
+        f = Fun(mfd, Pr, R, gid)
+        halo_exchange(mfd, f)
+        gid = f.values
+    out = gid.astype(np.int64)
+    if (out < 0).any():
+        raise RuntimeError(f"{int((out < 0).sum())} local {R}-simplices have no owner among the neighbouring slabs")
+    return out

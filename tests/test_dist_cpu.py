@@ -259,3 +259,35 @@ def test_rank_k_ghost_lists_match_by_position():
                 lo, hi = s.own_rows
                 nghost = int(np.sum((tab[:, 0] < lo) | (tab[:, 0] >= hi)))
                 assert len(L[r][0]["recv_lo"]) + len(L[r][0]["recv_hi"]) == nghost
+
+
+def test_global_numbering_of_owned_simplices():
+    """Host model of ddf.dist.global_ids / owned_offsets: with ownership = owner of the smallest vertex,
+    every rank's owned R-simplices are ONE contiguous range of the undivided mesh's ids (Manifolds.jl:735-757:
+    lexicographic ranks), in rank order, and inside the range the local order is the global order.  So
+    global id = exclusive scan of the owned counts + rank among the owned -- checked by comparing vertex tuples with
+    the undivided oracle mesh, for every R, on 3 slabs of a 3D and a 2D Kuhn mesh; the owned sets partition the mesh."""
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import ddf_oracle as o
+    from importlib import import_module
+    dd = import_module("ddf.jl_b200.dist")
+    for D, nxy, nz, world in ((3, 2, 14, 3), (2, 4, 12, 3), (3, 4, 8, 2)):
+        plane = (nxy + 1) ** (D - 1)
+        full = o.large_hypercube_manifold(D, (nxy,) * (D - 1) + (nz,), h_div=nxy)
+        slabs = dd.partition_slabs(nz, world, plane)
+        for R in range(D + 1):
+            ftab = np.arange(full.nsimplices(0))[:, None] if R == 0 else full.simplices[R]
+            offset = 0
+            for s in slabs:
+                simp, coords, weights = o.large_hypercube_tables(D, (nxy,) * (D - 1) + (s.nz_cells,), h_div=nxy)
+                m = o.build_manifold("slab", simp, coords, weights)
+                tab = np.arange(m.nsimplices(0))[:, None] if R == 0 else m.simplices[R]
+                lo, hi = s.own_rows
+                own = (tab[:, 0] >= lo) & (tab[:, 0] < hi)
+                glob = tab[own] + s.z_cell_lo * plane
+                cnt = int(own.sum())
+                assert np.array_equal(glob, ftab[offset:offset + cnt]), (D, R, s.rank)
+                offset += cnt
+            assert offset == ftab.shape[0], (D, R)

@@ -141,6 +141,56 @@ def main():
                   f"{'BIT-EXACT' if all(res) else 'MISMATCH'}", flush=True)
             ok = ok and all(res)
         mfd.close()
+    # global numbering + sharded d_k / star_k apply: every rank numbers its owned simplices into the
+    # undivided mesh's id space, applies its local d_R / star_R to the matching entries of ONE global cochain, and the
+    # owned rows of all ranks together must be the undivided mesh's tables and results bit for bit
+    for D, nelts in ((3, (8, 8, 8 * world)), (2, (16, 16 * world)), (3, (20, 20, 6 * world + 2))):
+        mfd, slab = ddf.dist.slab_hypercube(D, nelts, ctx)
+        voff = slab.z_cell_lo * slab.plane                       # local -> global vertex id
+        gids = [ddf.dist.global_ids(mfd, slab, R) for R in range(D + 1)]
+        totals = [ddf.dist.owned_offsets(mfd, slab, R)[1] for R in range(D + 1)]
+        payload = {"tables": [], "d": [], "star": []}
+        for R in range(D + 1):
+            own = ddf.dist.owned_mask(mfd, slab, R)
+            tab = (np.arange(mfd.nsimplices(0))[:, None] if R == 0 else mfd.get_simplices(R)) + voff
+            payload["tables"].append((gids[R][own], tab[own]))
+            xg = np.random.default_rng(40 + R).standard_normal(totals[R])      # the same global cochain on every rank
+            x = ddf.Fun(mfd, ddf.Pr, R, xg[gids[R]])
+            ys = (ddf.hodge(ddf.Pr, R, mfd) * x).values
+            payload["star"].append((gids[R][own], ys[own]))
+            if R < D:
+                own1 = ddf.dist.owned_mask(mfd, slab, R + 1)
+                yd = (ddf.deriv(ddf.Pr, R, mfd) * x).values
+                payload["d"].append((gids[R + 1][own1], yd[own1]))
+        parts = [None] * world
+        dist.all_gather_object(parts, payload)
+        if rank == 0:
+            full = ddf.large_hypercube_manifold(D, nelts, ctx=ctx, hdiv=nelts[0])
+            same = all(totals[R] == full.nsimplices(R) for R in range(D + 1))
+            for R in range(D + 1):
+                ftab = np.arange(full.nsimplices(0))[:, None] if R == 0 else full.get_simplices(R)
+                xg = np.random.default_rng(40 + R).standard_normal(full.nsimplices(R))
+                fx = ddf.Fun(full, ddf.Pr, R, xg)
+                fs = (ddf.hodge(ddf.Pr, R, full) * fx).values
+                fd = (ddf.deriv(ddf.Pr, R, full) * fx).values if R < D else None
+                seen = np.zeros(full.nsimplices(R), dtype=np.int64)
+                seen1 = np.zeros(full.nsimplices(R + 1), dtype=np.int64) if R < D else None
+                for p in parts:
+                    g, t = p["tables"][R]
+                    same = same and np.array_equal(ftab[g], t)
+                    np.add.at(seen, g, 1)
+                    g, y = p["star"][R]
+                    same = same and np.array_equal(fs[g], y)
+                    if R < D:
+                        g, y = p["d"][R]
+                        same = same and np.array_equal(fd[g], y)
+                        np.add.at(seen1, g, 1)
+                same = same and bool((seen == 1).all()) and (seen1 is None or bool((seen1 == 1).all()))   # a partition
+            print(f"dist_check global numbering + sharded d_k/star_k D={D} nelts={nelts} world={world}: "
+                  f"{'BIT-EXACT' if same else 'MISMATCH'}", flush=True)
+            ok = ok and same
+            full.close()
+        mfd.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
