@@ -342,7 +342,12 @@ def run_b200(args):
     for k in range(3):
         ms = time_op(lambda k=k: d[k].apply(x[k], y[k]), K)
         b = dk_bytes(cnt[k + 1], cnt[k], k)
-        breakdown[f"d{k}"] = {"ms": ms, "GBps": b / ms * 1e-6, "frac": b / ms * 1e-6 / peak, "bytes": b}
+        fmt = ddf.deriv_format(mfd, k)
+        # bytes the stored format moves: prefix-packed rows keep k+1 index words per row + one base per 32 rows
+        fb = b - (4 * cnt[k + 1] - cnt[k + 1] // 8) if fmt == "packed" else b
+        breakdown[f"d{k}"] = {"ms": ms, "GBps": b / ms * 1e-6, "frac": b / ms * 1e-6 / peak, "bytes": b,
+                              "row_format": fmt, "format_bytes": int(fb), "format_GBps": fb / ms * 1e-6,
+                              "format_frac": fb / ms * 1e-6 / peak}
     for k in range(4):
         ms = time_op(lambda k=k: h[k].apply(x[k], z[k]), K)
         b = 24 * cnt[k]
@@ -483,6 +488,9 @@ def run_b200(args):
 
     if rank == 0:
         d1_bytes = dk_bytes(cnt[2], cnt[1], 1)
+        d1_packed = breakdown["d1"]["row_format"] == "packed"
+        d1_kernel = "k_apply_packed_rows<3,4>" if d1_packed else "k_apply_fixed_rows<3,4>"
+        d1_format_bytes = breakdown["d1"]["format_bytes"]
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch); scaled by the
         # algorithmic bytes when this run's slab differs slightly from the captured n=256 cube
         traffic, traffic_src = None, None
@@ -490,7 +498,7 @@ def run_b200(args):
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
                 tj = json.load(f)
             if tj.get("n") == n:
-                e = tj["k_apply_fixed_rows<3,4>"]
+                e = tj[d1_kernel]
                 traffic = e["traffic_bytes"] * d1_bytes / e["algorithmic_bytes"]
                 traffic_src = tj["source"]
         except (OSError, KeyError, ValueError):
@@ -509,11 +517,17 @@ def run_b200(args):
                        "l2_hygiene": "inputs larger than L2 (index tables 0.9-2.4 GB, vectors 0.14-1.6 GB vs 126 MB L2)",
                        "parallelism": "none" if N == 1 else f"z-slabs x{N}, no collective in d_k/star_k apply; "
                                                             "NCCL send/recv halo in the wave step"},
-            "roofline": {"bound": "hbm", "kernel": "k_apply_fixed_rows<3,4> (y = d1 x)", "achieved": d1_bytes / d1_ms * 1e-6,
+            "roofline": {"bound": "hbm", "kernel": d1_kernel + " (y = d1 x" + (", prefix-packed rows)" if d1_packed else ")"),
+                         "achieved": d1_bytes / d1_ms * 1e-6,
                          "peak": peak, "unit": "GB/s", "frac": d1_bytes / d1_ms * 1e-6 / peak, "traffic": traffic,
                          "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(d1_bytes),
-                         "ms_per_launch": d1_ms, "frac_of_nominal_8TBs": d1_bytes / d1_ms * 1e-6 / 8000.0},
+                         "ms_per_launch": d1_ms, "frac_of_nominal_8TBs": d1_bytes / d1_ms * 1e-6 / 8000.0,
+                         # `achieved` counts SURVEY 8(d)'s algorithmic bytes (explicit int32 indices); the packed rows
+                         # store one index word less per row, so the bytes actually moved are these:
+                         "format_bytes_per_launch": int(d1_format_bytes),
+                         "format_achieved": d1_format_bytes / d1_ms * 1e-6,
+                         "format_frac": d1_format_bytes / d1_ms * 1e-6 / peak},
             "breakdown": breakdown, "wave": wave, "wave2d": wave2d, "poisson_step": poisson_step, "wave_tsit5": tsit5, "poisson2d": poisson2d,
             "assembly_ms": asm_ms,
             # assembly of d_3, d_2, d_1 on the device from the tet table (bit-exact; no roofline target):

@@ -95,6 +95,7 @@ SIGNATURES = {
     "ddf_op_adjoint": [_P, _PP],
     "ddf_op_apply": [_P, _P, _P],
     "ddf_op_assemble": [_P, _PP],
+    "ddf_mesh_deriv_format": [_P, C.c_int, C.POINTER(C.c_int)],
     "ddf_op_to_csc": [_P, _i64p, _i64p, _i64p, _f64p],
     "ddf_wave_rhs": [_P, _P, _P, _P, _P],
     "ddf_wave_dt": [_P, _f64p],

@@ -67,6 +67,14 @@ struct FStageBufs {
   void release() { tab.release(); slot.release(); max_slots = 0; W = 0; win = 0; nwin = 0; state = 0; }
 };
 
+// prefix-packed fixed-width rows of d_k (ops.cu, k_pack_fixed): W-1 words per row + one base per 32 rows
+struct PackedBufs {
+  DevBuf<uint32_t> words;   // row r: word 0 = (idx0 - base[r/32]) << 24 | (idx1 - idx0), words 1.. = idx2.. explicit
+  DevBuf<uint32_t> base;    // idx0 of the first row of every group of 32 rows
+  int state = 0;            // 0 = not built, 1 = in use, 2 = does not pack (explicit table)
+  void release() { words.release(); base.release(); state = 0; }
+};
+
 struct ddf_mesh {
   ddf_ctx* ctx = nullptr;
   int D = 0, C = 0;
@@ -114,6 +122,7 @@ struct ddf_mesh {
   DevBuf<uint32_t> bpair[DDF_MAXD + 1];
   // staged copies of the fixed-width tables of d_{R-1} = d_R^T (primal derivative apply)
   FStageBufs fstage[DDF_MAXD + 1];
+  PackedBufs bpack[DDF_MAXD + 1];
   DevBuf<double> utmp;                   // V   ping-pong buffer of the fused step
   DevBuf<double> ldinv;                  // V   1 ./ diag(L) for the fused Poisson relaxation step
   DevBuf<double> tsit_work;              // 16 V  stage derivatives and scratch of ddf_wave_tsit5 (allocated on first use)

@@ -26,6 +26,7 @@
 #include "fstage.cuh"
 
 extern int g_tune_fixed;
+static int g_tune_packbits = 24;
 int ddf_laplace0_apply(ddf_mesh* m, const double* x, double* y);   // wave.cu
 
 enum OpKind { OPK_ZERO = 0, OPK_FIXED, OPK_CSRSIGN, OPK_DIAG, OPK_CSRF64, OPK_LAPLACE0, OPK_CHAIN, OPK_SUM };
@@ -352,6 +353,7 @@ extern "C" int ddf_set_tuning(const char* key, int value) {
   if (!strcmp(key, "fixed")) g_tune_fixed = value;
   else if (!strcmp(key, "wave")) g_tune_wave = value;
   else if (!strcmp(key, "asm")) g_tune_asm = value;
+  else if (!strcmp(key, "packbits")) g_tune_packbits = value >= 1 && value <= 24 ? value : 24;
   else DDF_FAIL("set_tuning: unknown key %s", key);
   return 0;
 }
@@ -538,6 +540,202 @@ k_apply_fixed_rows(const int32_t* __restrict__ tab, int64_t nrows, int first_neg
   }
 }
 
+// ---------------------------------------------------------------- prefix-packed rows of d_k
+// Row tau = (v_0 .. v_k+1) of d_k holds the ids of its faces in ascending order, and the FIRST of them -- the face
+// that omits the last vertex -- is tau's prefix (v_0 .. v_k).  Ids are lexicographic ranks (Manifolds.jl:735-757), so
+// down the rows that first column is non-decreasing, and the second one (the face (v_0 .. v_k-1, v_k+1), which
+// shares the prefix's first k vertices) lies a short way after it.  The packed table stores, per row, W-1 words
+// instead of W: word 0 = (idx0 - base) << 24 | (idx1 - idx0) with one `base` per group of 32 rows, the remaining
+// indices as they are: 4 / 8 / 12 instead of 8 / 12 / 16 bytes of index data per row of d0 / d1 / d2.  The gathers,
+// their order and the arithmetic are those of k_apply_fixed_rows, so results are bit-identical.  A mesh whose rows
+// do not pack (a delta beyond 8 bits or an offset beyond 24) keeps the explicit table.
+template <int W>
+__global__ void __launch_bounds__(256)
+k_pack_fixed(const int32_t* __restrict__ tab, int64_t nrows, uint32_t max_offset, uint32_t* __restrict__ words,
+             uint32_t* __restrict__ base, uint32_t* __restrict__ bad) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const uint32_t b = (uint32_t)tab[(r & ~(int64_t)31) * W];
+  const uint32_t i0 = (uint32_t)tab[r * W], i1 = (uint32_t)tab[r * W + 1];
+  if ((r & 31) == 0) base[r >> 5] = b;
+  const uint32_t d = i0 - b, o = i1 - i0;
+  if (i0 < b || d > 255u || i1 <= i0 || o > max_offset) { atomicOr(bad, 1u); return; }
+  words[r * (W - 1)] = (d << 24) | o;
+#pragma unroll
+  for (int p = 2; p < W; p++) words[r * (W - 1) + p - 1] = (uint32_t)tab[r * W + p];
+}
+
+// lane = consecutive rows, RPW groups of 32 rows per warp (the mapping of k_apply_fixed_rows)
+template <int W, int RPW, bool PRE, bool POST>
+__global__ void __launch_bounds__(256)
+k_apply_packed_rows(const uint32_t* __restrict__ words, const uint32_t* __restrict__ base, int64_t nrows,
+                    int first_negative, const double* __restrict__ x, double* __restrict__ y,
+                    const double* __restrict__ pre, const double* __restrict__ post, double alpha) {
+  const uint64_t pol_keep = make_policy_evict_last();
+  const uint64_t pol_stream = make_policy_evict_first();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r0 = warp * (32 * RPW) + lane;
+  if (warp * (32 * RPW) >= nrows) return;
+  int idx[RPW][W];
+#pragma unroll
+  for (int k = 0; k < RPW; k++) {
+    const int64_t r = r0 + 32 * k;
+    const bool ok = r < nrows;
+    const uint32_t b = ok ? __ldg(base + warp * RPW + k) : 0u;
+    uint32_t w0 = 0;
+    if constexpr (W == 2) {
+      if (ok) w0 = (uint32_t)ld_stream_int(reinterpret_cast<const int*>(words) + r);
+    } else if constexpr (W == 3) {    // one 8-byte load per row, 256 B per warp
+      int2 v = make_int2(0, 0);
+      if (ok) v = ld_stream_int2(reinterpret_cast<const int2*>(words) + r);
+      w0 = (uint32_t)v.x; idx[k][W - 1] = v.y;
+    } else {                          // 12-byte rows: three L1-allocating loads that share their lines
+      int v[W - 1];
+#pragma unroll
+      for (int p = 0; p < W - 1; p++) v[p] = ok ? ld_keep_s32(reinterpret_cast<const int*>(words) + r * (W - 1) + p, pol_stream) : 0;
+      w0 = (uint32_t)v[0];
+#pragma unroll
+      for (int p = 2; p < W; p++) idx[k][p] = v[p - 1];
+    }
+    idx[k][0] = (int)(b + (w0 >> 24));
+    idx[k][1] = idx[k][0] + (int)(w0 & 0xffffffu);
+  }
+  double xv[RPW][W];
+#pragma unroll
+  for (int k = 0; k < RPW; k++)
+#pragma unroll
+    for (int p = 0; p < W; p++) xv[k][p] = ld_keep_f64(x + idx[k][p], pol_keep);
+  if (PRE) {
+#pragma unroll
+    for (int k = 0; k < RPW; k++)
+#pragma unroll
+      for (int p = 0; p < W; p++) xv[k][p] = __dmul_rn(ld_keep_f64(pre + idx[k][p], pol_keep), xv[k][p]);
+  }
+#pragma unroll
+  for (int k = 0; k < RPW; k++) {
+    const int64_t r = r0 + 32 * k;
+    double a = 0.0;
+#pragma unroll
+    for (int p = 0; p < W; p++) {
+      const bool neg = ((p & 1) != 0) != (first_negative != 0);
+      a = neg ? __dsub_rn(a, xv[k][p]) : __dadd_rn(a, xv[k][p]);
+    }
+    if (r < nrows) {
+      if (POST) a = __dmul_rn(ld_stream_f64(post + r), a);
+      if (alpha != 1.0) a = __dmul_rn(alpha, a);
+      st_hint_f64(y + r, a, pol_stream);
+    }
+  }
+}
+
+// d0 (W = 2): four consecutive rows per thread = ONE 16-byte load of their four words, 16-byte stores
+template <bool PRE, bool POST>
+__global__ void __launch_bounds__(256)
+k_apply_packed_quad(const uint32_t* __restrict__ words, const uint32_t* __restrict__ base, int64_t nrows,
+                    int first_negative, const double* __restrict__ x, double* __restrict__ y,
+                    const double* __restrict__ pre, const double* __restrict__ post, double alpha) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r0 = t * 4;
+  if (r0 >= nrows) return;
+  const uint64_t pol_keep = make_policy_evict_last();
+  const uint64_t pol_stream = make_policy_evict_first();
+  const uint32_t b = __ldg(base + (r0 >> 5));
+  uint32_t w[4] = {0, 0, 0, 0};
+  if (r0 + 3 < nrows) {
+    const int4 v = ld_stream_int4_hint(reinterpret_cast<const int4*>(words) + t, pol_stream);
+    w[0] = (uint32_t)v.x; w[1] = (uint32_t)v.y; w[2] = (uint32_t)v.z; w[3] = (uint32_t)v.w;
+  } else {
+    for (int q = 0; q < 4 && r0 + q < nrows; q++) w[q] = words[r0 + q];
+  }
+  int idx[8];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    idx[2 * q] = (int)(b + (w[q] >> 24));
+    idx[2 * q + 1] = idx[2 * q] + (int)(w[q] & 0xffffffu);
+  }
+  double xv[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) xv[q] = ld_keep_f64(x + idx[q], pol_keep);
+  if (PRE) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) xv[q] = __dmul_rn(ld_keep_f64(pre + idx[q], pol_keep), xv[q]);
+  }
+  double acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    double a = 0.0;
+    a = first_negative ? __dsub_rn(a, xv[2 * q]) : __dadd_rn(a, xv[2 * q]);
+    a = first_negative ? __dadd_rn(a, xv[2 * q + 1]) : __dsub_rn(a, xv[2 * q + 1]);
+    acc[q] = a;
+  }
+  if (r0 + 3 < nrows) {
+    if (POST) {
+      const double2 p0 = ld_stream_f64x2_hint(reinterpret_cast<const double2*>(post + r0), pol_stream);
+      const double2 p1 = ld_stream_f64x2_hint(reinterpret_cast<const double2*>(post + r0 + 2), pol_stream);
+      acc[0] = __dmul_rn(p0.x, acc[0]); acc[1] = __dmul_rn(p0.y, acc[1]);
+      acc[2] = __dmul_rn(p1.x, acc[2]); acc[3] = __dmul_rn(p1.y, acc[3]);
+    }
+    if (alpha != 1.0) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[q] = __dmul_rn(alpha, acc[q]);
+    }
+    st_hint_f64x2(reinterpret_cast<double2*>(y + r0), acc[0], acc[1], pol_stream);
+    st_hint_f64x2(reinterpret_cast<double2*>(y + r0 + 2), acc[2], acc[3], pol_stream);
+  } else {
+    for (int q = 0; q < 4 && r0 + q < nrows; q++) {
+      double a = acc[q];
+      if (POST) a = __dmul_rn(post[r0 + q], a);
+      if (alpha != 1.0) a = __dmul_rn(alpha, a);
+      y[r0 + q] = a;
+    }
+  }
+}
+
+static int packed_build(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, PackedBufs& pb) {
+  pb.release();
+  pb.state = 2;
+  if (W < 2 || W > 4 || nrows == 0) return 0;
+  DevBuf<uint32_t> bad;
+  DDF_CHECK(bad.alloc(ctx, 1));
+  DDF_CUDA(cudaMemsetAsync(bad.p, 0, 4, ctx->stream));
+  DDF_CHECK(pb.words.alloc(ctx, (size_t)nrows * (W - 1)));
+  DDF_CHECK(pb.base.alloc(ctx, (size_t)ceil_div64(nrows, 32)));
+  int grid;
+  DDF_CHECK(grid_for(nrows, 256, &grid));
+  const uint32_t max_off = (1u << g_tune_packbits) - 1u;      // 24 bits; the tuning knob only narrows it (tests)
+  if (W == 2) k_pack_fixed<2><<<grid, 256, 0, ctx->stream>>>(tab, nrows, max_off, pb.words.p, pb.base.p, bad.p);
+  else if (W == 3) k_pack_fixed<3><<<grid, 256, 0, ctx->stream>>>(tab, nrows, max_off, pb.words.p, pb.base.p, bad.p);
+  else k_pack_fixed<4><<<grid, 256, 0, ctx->stream>>>(tab, nrows, max_off, pb.words.p, pb.base.p, bad.p);
+  DDF_LAUNCH_CHECK(ctx);
+  uint32_t hb = 0;
+  DDF_CUDA(cudaMemcpyAsync(&hb, bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (hb) { pb.words.release(); pb.base.release(); return 0; }
+  pb.state = 1;
+  return 0;
+}
+
+static int launch_packed(ddf_ctx* ctx, const PackedBufs& pb, int W, int64_t nrows, int first_negative, const double* x,
+                         const double* pre, const double* post, double alpha, double* y) {
+  const int g4 = (int)ceil_div64(ceil_div64(nrows, 4), 256), g3 = (int)ceil_div64(ceil_div64(nrows, 3), 256);
+  const bool quad = W == 2 && g_tune_fixed != 19;
+#define DDF_PACKED_CASE(PRE_, POST_)                                                                                 \
+  do {                                                                                                               \
+    if (quad) k_apply_packed_quad<PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha); \
+    else if (W == 2) k_apply_packed_rows<2, 4, PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha); \
+    else if (W == 3) k_apply_packed_rows<3, 4, PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha); \
+    else k_apply_packed_rows<4, 3, PRE_, POST_><<<g3, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha);             \
+  } while (0)
+  if (pre && post) DDF_PACKED_CASE(true, true);
+  else if (pre) DDF_PACKED_CASE(true, false);
+  else if (post) DDF_PACKED_CASE(false, true);
+  else DDF_PACKED_CASE(false, false);
+#undef DDF_PACKED_CASE
+  DDF_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 template <int W>
 static void launch_fixed_x(ddf_ctx* ctx, int var, const int32_t* tab, int64_t nrows, int first_negative,
                            const double* x, double* y) {
@@ -576,7 +774,7 @@ static int launch_fixed(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, 
   }
   // default for the plain d_1 / d_2 apply: lane = consecutive rows (k_apply_fixed_rows).  Measured at C4
   // (profiles/r01_tuning.md): d1 0.786 -> 0.733 ms, d2 0.769 -> 0.564 ms; d0 (W = 2) is faster with 4 rows per thread.
-  if (g_tune_fixed == 0 && (W == 3 || W == 4)) {
+  if ((g_tune_fixed == 0 || g_tune_fixed == 18) && (W == 3 || W == 4)) {
     const int g3 = (int)ceil_div64(ceil_div64(nrows, 3), 256);
 #define DDF_ROWS_CASE(PRE_, POST_)                                                                                   \
   do {                                                                                                               \
@@ -1208,6 +1406,12 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
         if (rc > 0) return rc;
         fs.state = 2;                    // does not fit the shared-memory ring
       }
+    }
+    // default: prefix-packed rows (4 bytes less index data per row); tuning 18 keeps the explicit table
+    if ((g_tune_fixed == 0 || g_tune_fixed == 19) && W >= 2 && W <= 4 && f->nrows > 0) {
+      PackedBufs& pb = m->bpack[f->R];
+      if (pb.state == 0) DDF_CHECK(packed_build(f->ctx, m->bnd_table(f->R), W, f->nrows, pb));
+      if (pb.state == 1) return launch_packed(f->ctx, pb, W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
     }
     return launch_fixed(f->ctx, m->bnd_table(f->R), W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
   }
@@ -1921,6 +2125,18 @@ extern "C" int ddf_op_assemble(ddf_op* A, ddf_op** out) {
   DDF_LAUNCH_CHECK(ctx);
   DDF_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = wrap(o);
+  return 0;
+  DDF_TRY_END
+}
+
+extern "C" int ddf_mesh_deriv_format(ddf_mesh* m, int k, int* format) {
+  DDF_TRY_BEGIN
+  DDF_CHECK(ddf_mesh_require_assembled(m));
+  if (k < 0 || k >= m->D) DDF_FAIL("deriv_format: need 0 <= k < D");
+  const int R = k + 1, W = R + 1;
+  PackedBufs& pb = m->bpack[R];
+  if (pb.state == 0 && W <= 4 && m->n[R] > 0) DDF_CHECK(packed_build(m->ctx, m->bnd_table(R), W, m->n[R], pb));
+  *format = pb.state == 1 ? 1 : 0;
   return 0;
   DDF_TRY_END
 }

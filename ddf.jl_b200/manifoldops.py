@@ -213,3 +213,14 @@ def large_hypercube_manifold(D: int, nelts: Optional[Sequence[int]] = None, ctx:
     if assemble:
         call("ddf_mesh_assemble", h)
     return m
+
+
+def deriv_format(mfd, k: int) -> str:
+    """Storage of the rows of deriv(Pr,k) the apply kernels use on this mesh: "packed" (the first face of a row is
+    its prefix -- W-1 words per row + one base per 32 rows) or "explicit" (the top level, whose rows keep the
+    caller's order; meshes that do not pack).  Same bits either way."""
+    import ctypes as C
+    from ._lib import call
+    f = C.c_int()
+    call("ddf_mesh_deriv_format", mfd._h, int(k), C.byref(f))
+    return ("explicit", "packed")[f.value]

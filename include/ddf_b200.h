@@ -65,8 +65,9 @@ int ddf_event_record(ddf_ctx* ctx, int slot);
 int ddf_event_elapsed(ddf_ctx* ctx, int slot_a, int slot_b, double* ms);
 /* number of kernels the library has launched on this ctx since creation */
 int ddf_ctx_launch_count(ddf_ctx* ctx, int64_t* out);
-/* kernel-variant selector for profiling / A-B timing ("fixed", "wave"); every variant
- * returns bit-identical results; 0 selects the default */
+/* kernel-variant selector for profiling / A-B timing ("fixed", "wave", "asm"; "packbits" narrows the offset field of
+ * the prefix-packed d_k rows so that tests can reach the explicit-table fallback); every variant returns
+ * bit-identical results; 0 selects the default */
 int ddf_set_tuning(const char* key, int value);
 /* overwrite a >L2-sized scratch buffer (bench hygiene between timed launches) */
 int ddf_flush_l2(ddf_ctx* ctx);
@@ -178,6 +179,11 @@ int ddf_op_scale(double a, ddf_op* A, ddf_op** out);
 int ddf_op_adjoint(ddf_op* A, ddf_op** out);
 /* Op*Fun (Ops.jl:273-276): y = A x */
 int ddf_op_apply(ddf_op* A, ddf_vec* x, ddf_vec* y);
+/* Storage of the rows of d_k = deriv(Pr,k) the apply kernels use on this mesh: 1 = prefix-packed (the first face of
+ * every row is its prefix, whose ids run non-decreasing down the rows: W-1 words per row + a base per 32 rows),
+ * 0 = explicit index table (the top level, whose rows come in the caller's order, and meshes that do not pack).
+ * Both give identical bits (same gathers, same order). */
+int ddf_mesh_deriv_format(ddf_mesh* m, int k, int* format);
 /* The operator in the reference's own representation: every Op holds its assembled sparse matrix (Ops.jl:25),
  * rounded and chopped after each product / sum (Ops.jl:36-58,186-232), and `A * f` is a sparse mat-vec on it
  * (Ops.jl:273-276).  Returns a new operator whose apply is one row kernel over those values; the iterates of a

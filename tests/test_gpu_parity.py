@@ -174,6 +174,67 @@ def test_deriv_apply_staged_pipeline(ddf, ctx):
     ddf._lib.call("ddf_set_tuning", b"fixed", 0)
 
 
+def test_prefix_packed_rows_match_explicit_table(ddf, ctx):
+    """The default storage of d_k below the top level: the first face of every row is its prefix and prefix ids run
+    non-decreasing down the rows (lexicographic numbering, Manifolds.jl:735-757), so a row keeps W-1 words.  Bit for
+    bit the explicit-table kernel and the oracle, plain and with fused Hodge stars on either side; on ordered,
+    shuffled, random-Delaunay and ragged meshes; the top level (rows in the caller's order) and meshes whose offsets
+    do not fit (forced here with the 'packbits' knob) keep the explicit table."""
+    rng = np.random.default_rng(77)
+    meshes = {}
+    for name, (D, n) in {"kuhn3": (3, 10), "kuhn2": (2, 37 * 2), "kuhn3odd": (3, 6)}.items():
+        meshes[name] = o.large_hypercube_tables(D, (n,) * D)
+    simp, coords, weights = o.large_hypercube_tables(3, (8, 8, 8))
+    perm = rng.permutation(coords.shape[0])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    meshes["shuffled"] = (inv[simp], coords[perm], weights[perm])
+    pts = rng.random((400, 2))
+    meshes["delaunay"] = (ddf.delaunay_mesh(pts), pts, np.zeros(len(pts)))
+    for name, (s_, c_, w_) in meshes.items():
+        om = o.build_manifold(name, s_, c_, w_)
+        D = om.D
+        for bits in (24, 3):
+            ddf._lib.call("ddf_set_tuning", b"packbits", bits)
+            try:
+                dm = ddf.Manifold.from_simplices(name, s_, c_, w_, ctx=ctx)
+                omg = with_device_geometry(om, dm)
+                for k in range(D):
+                    fmt = ddf.deriv_format(dm, k)
+                    if k == D - 1 or bits == 3:
+                        # top level: rows in input order (only a mesh given in lexicographic order would pack)
+                        assert fmt == "explicit" or (k == D - 1 and bits == 24), (name, k, fmt)
+                    else:
+                        assert fmt == "packed", (name, k, bits)
+                    x = rng.standard_normal(om.nsimplices(k))
+                    fx = ddf.Fun(dm, ddf.Pr, k, x)
+                    d = ddf.deriv(ddf.Pr, k, dm)
+                    y = (d * fx).values
+                    assert np.array_equal(y, o.apply_deriv(o.Pr, k, om, x)), (name, k, bits)
+                    # fused stars: (star_{k+1} d_k) x and (d_k star_k^-1-typed diagonal) x against the unfused sequence
+                    h1 = ddf.hodge(ddf.Pr, k + 1, dm)
+                    y1 = ((h1 * d) * fx).values
+                    assert np.array_equal(y1, (h1 * (d * fx)).values), (name, k, bits)
+                    g = ddf.op_from_diag(dm, ddf.Pr, k, ddf.Pr, k, rng.standard_normal(om.nsimplices(k)))
+                    y2 = ((d * g) * fx).values
+                    assert np.array_equal(y2, (d * (g * fx)).values), (name, k, bits)
+                    ddf._lib.call("ddf_set_tuning", b"fixed", 18)          # explicit table, same mapping
+                    try:
+                        assert np.array_equal((d * fx).values, y), (name, k, bits)
+                        assert np.array_equal(((h1 * d) * fx).values, y1), (name, k, bits)
+                    finally:
+                        ddf._lib.call("ddf_set_tuning", b"fixed", 0)
+                    ddf._lib.call("ddf_set_tuning", b"fixed", 19)          # packed d0 with lane = consecutive rows
+                    try:
+                        assert np.array_equal((d * fx).values, y), (name, k, bits)
+                    finally:
+                        ddf._lib.call("ddf_set_tuning", b"fixed", 0)
+                del omg
+                dm.close()
+            finally:
+                ddf._lib.call("ddf_set_tuning", b"packbits", 24)
+
+
 def test_deriv_apply_ragged_sizes(ddf, ctx):
     """rows % 4 != 0 exercises the scalar tail of the 4-rows-per-thread kernel."""
     for n in (2, 6, 10):
