@@ -120,6 +120,8 @@ struct ddf_mesh {
   SellBufs bsell[DDF_MAXD + 1];
   // rows of <= 2 entries (faces of the top simplices): (entry0, entry1 | 0xFFFFFFFF) pairs, one 8-byte load per row
   DevBuf<uint32_t> bpair[DDF_MAXD + 1];
+  uint32_t bup_cap[DDF_MAXD + 1] = {0};  // longest upper run of a 256-row window (doubles, rounded): shared memory of the staged kernel
+  DevBuf<uint32_t> bup[DDF_MAXD + 1];    // upper-run offsets of the rows of the boundary matrix (ops.cu, upper_build): bsell then holds the lower entries only
   // staged copies of the fixed-width tables of d_{R-1} = d_R^T (primal derivative apply)
   FStageBufs fstage[DDF_MAXD + 1];
   PackedBufs bpack[DDF_MAXD + 1];

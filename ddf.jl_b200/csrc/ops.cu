@@ -234,16 +234,43 @@ k_apply_pairsign(const uint32_t* __restrict__ pair, int64_t nrows, const double*
 }
 
 // The same operator from the SELL-32 copy of the row-CSR (sell.cuh): coalesced index loads.
-template <bool PRE, bool POST, int BATCH = 8>
+// UP: the SELL copy holds only the LOWER entries of a row; its upper entries -- the cofaces (sigma, c) that extend
+// the row's simplex sigma at the end -- are the contiguous ids [up[i], up[i+1]) and all carry the sign (-1)^R
+// (upper_build below).  They come last in ascending-column order, so the sum keeps the reference's order.
+// STAGE: the upper runs of the 256 rows of a window are ONE contiguous piece of x (and of pre): thread 0 fetches it
+// with a single TMA bulk copy per array while all threads gather their lower entries; the upper sums then read
+// shared memory.  `cap` = doubles of shared memory per array (the longest window run of the mesh, rounded).
+template <bool PRE, bool POST, int BATCH = 8, bool UP = false, bool STAGE = false>
 __global__ void __launch_bounds__(256)
 k_apply_sellsign(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict__ perm8,
                  const uint32_t* __restrict__ scol, int64_t nrows, const double* __restrict__ x,
                  const double* __restrict__ pre, const double* __restrict__ post, double alpha,
-                 double* __restrict__ y) {
+                 double* __restrict__ y, const uint32_t* __restrict__ up = nullptr, int up_negative = 0,
+                 uint32_t cap = 0) {
   const int64_t r = (int64_t)blockIdx.x * DDF_SELL_WIN + threadIdx.x;        // sorted position
   const int64_t i = (int64_t)blockIdx.x * DDF_SELL_WIN + perm8[r];           // the row it holds
   const uint64_t pol_stream = make_policy_evict_first();
   const uint64_t pol_keep = make_policy_evict_last();
+  extern __shared__ __align__(16) double sx[];
+  __shared__ uint64_t mbar;
+  uint32_t a0 = 0, staged = 0;
+  if (STAGE) {
+    const int64_t w0 = (int64_t)blockIdx.x * DDF_SELL_WIN;
+    const int64_t w1 = w0 + DDF_SELL_WIN < nrows ? w0 + DDF_SELL_WIN : nrows;
+    const uint32_t ua = up[w0], ub = up[w1];
+    a0 = ua & ~1u;                                        // 16-byte aligned start, even count
+    staged = (ub - a0 + 1u) & ~1u;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (staged) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(staged * (PRE ? 16u : 8u)) : "memory");
+        bulk_g2s(sx, x + a0, staged * 8u, &mbar, pol_keep);
+        if (PRE) bulk_g2s(sx + cap, pre + a0, staged * 8u, &mbar, pol_keep);
+      }
+    }
+    __syncthreads();                                      // the barrier is initialised before anyone waits on it
+  }
   const int64_t s = r >> 5;
   const uint32_t base = sell_ptr[s] + (uint32_t)(r & 31);
   const uint32_t w = (sell_ptr[s + 1] - sell_ptr[s]) >> 5;
@@ -265,7 +292,30 @@ k_apply_sellsign(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restric
     for (int q = 0; q < BATCH; q++)
       if (cw[q] != DDF_SELL_PAD) a = (cw[q] >> 31) ? __dsub_rn(a, xv[q]) : __dadd_rn(a, xv[q]);
   }
+  if (STAGE && staged) stage_wait(&mbar, 0);
   if (i >= nrows) return;
+  if (UP && STAGE) {
+    const uint32_t u0 = up[i] - a0, u1 = up[i + 1] - a0;
+    for (uint32_t q = u0; q < u1; q++) {
+      double v = sx[q];
+      if (PRE) v = __dmul_rn(sx[cap + q], v);
+      a = up_negative ? __dsub_rn(a, v) : __dadd_rn(a, v);
+    }
+  } else if (UP) {
+    const uint32_t u0 = up[i], u1 = up[i + 1];
+    for (uint32_t q0 = u0; q0 < u1; q0 += BATCH) {
+      double xv[BATCH];
+#pragma unroll
+      for (int q = 0; q < BATCH; q++) {
+        const uint32_t c = q0 + q < u1 ? q0 + q : u0;
+        xv[q] = ld_keep_f64(x + c, pol_keep);
+        if (PRE) xv[q] = __dmul_rn(ld_keep_f64(pre + c, pol_keep), xv[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < BATCH; q++)
+        if (q0 + q < u1) a = up_negative ? __dsub_rn(a, xv[q]) : __dadd_rn(a, xv[q]);
+    }
+  }
   if (POST) a = __dmul_rn(post[i], a);
   if (alpha != 1.0) a = __dmul_rn(alpha, a);
   st_hint_f64(y + i, a, pol_stream);
@@ -1373,6 +1423,104 @@ static bool is_sparse_leaf(const OpRef& f) { return f->kind == OPK_FIXED || f->k
 // sparse leaf with optional fused diagonals.  A diagonal payload with scale != 1
 // cannot be fused bit-identically unless the scale is +-1 (sign flips commute with
 // rounding), which is all the DEC operators ever produce.
+// ---------------------------------------------------------------- upper runs of the boundary rows
+// Row sigma of the boundary matrix d_R (R < D) lists the R-simplices that contain sigma, ascending.  Those that
+// extend sigma at the END, (sigma, c) with c above every vertex of sigma, share the prefix sigma: in the lexicographic
+// numbering (Manifolds.jl:735-757) they are consecutive ids, they are the LAST entries of the row, and the runs of
+// consecutive rows tile the R-simplices in order -- every R-simplex is the upper coface of exactly one row, its prefix.
+// So a row keeps its lower entries explicitly and its upper ones as [up[i], up[i+1]): a third (rows = edges) to a half
+// (rows = vertices) of the index data goes away, and those gathers no longer wait for an index load.
+__global__ void k_upper_count(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, const int32_t* __restrict__ tab,
+                              int W, int64_t nrows, int up_negative, uint32_t* __restrict__ nlow, uint32_t* __restrict__ nup,
+                              uint32_t* __restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const uint32_t lo = rowptr[i], hi = rowptr[i + 1];
+  uint32_t n = 0;
+  bool ok = true;
+  for (uint32_t p = hi; p > lo; p--) {                     // trailing entries whose prefix is this row
+    const uint32_t e = col[p - 1], c = e & 0x7fffffffu;
+    if ((uint32_t)tab[(int64_t)c * W] != (uint32_t)i) break;
+    if ((int)(e >> 31) != up_negative) ok = false;
+    if (n > 0 && (col[p] & 0x7fffffffu) != c + 1u) ok = false;     // consecutive ids
+    n++;
+  }
+  for (uint32_t p = lo; p + n < hi; p++)                   // and no other entry has it
+    if ((uint32_t)tab[(int64_t)(col[p] & 0x7fffffffu) * W] == (uint32_t)i) ok = false;
+  if (!ok) atomicOr(bad, 1u);
+  nlow[i] = hi - lo - n;
+  nup[i] = n;
+}
+__global__ void k_upper_fill(const uint32_t* __restrict__ rowptr, const uint32_t* __restrict__ col, int64_t nrows,
+                             const uint32_t* __restrict__ lowptr, const uint32_t* __restrict__ up,
+                             uint32_t* __restrict__ lowcol, uint32_t* __restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const uint32_t lo = rowptr[i], hi = rowptr[i + 1], l0 = lowptr[i], nl = lowptr[i + 1] - l0;
+  for (uint32_t q = 0; q < nl; q++) lowcol[l0 + q] = col[lo + q];
+  if (lo + nl < hi && (col[lo + nl] & 0x7fffffffu) != up[i]) atomicOr(bad, 1u);      // the runs tile the columns in row order
+  if (hi - lo - nl != up[i + 1] - up[i]) atomicOr(bad, 1u);
+}
+
+// bsell[R] <- SELL copy of the lower entries, bup[R] <- run offsets; returns with state 4 on success, 0 otherwise
+static int upper_build(ddf_mesh* m, int R, int64_t nrows) {
+  ddf_ctx* ctx = m->ctx;
+  const int W = R + 1;
+  const int64_t nnz = (int64_t)W * m->n[R];
+  DevBuf<uint32_t> nlow, nup, lowptr, lowcol, bad;
+  DevBuf<uint8_t> temp;
+  DDF_CHECK(nlow.alloc(ctx, nrows + 1));
+  DDF_CHECK(nup.alloc(ctx, nrows + 1));
+  DDF_CHECK(lowptr.alloc(ctx, nrows + 1));
+  DDF_CHECK(m->bup[R].alloc(ctx, nrows + 1));
+  DDF_CHECK(bad.alloc(ctx, 1));
+  DDF_CUDA(cudaMemsetAsync(bad.p, 0, 4, ctx->stream));
+  DDF_CUDA(cudaMemsetAsync(nlow.p + nrows, 0, 4, ctx->stream));
+  DDF_CUDA(cudaMemsetAsync(nup.p + nrows, 0, 4, ctx->stream));
+  int grid;
+  DDF_CHECK(grid_for(nrows, 256, &grid));
+  k_upper_count<<<grid, 256, 0, ctx->stream>>>(m->brow_ptr[R].p, m->bcol[R].p, m->bnd_table(R), W, nrows, R & 1, nlow.p, nup.p, bad.p);
+  DDF_LAUNCH_CHECK(ctx);
+  size_t tb = 0;
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, nlow.p, lowptr.p, nrows + 1, ctx->stream));
+  DDF_CHECK(temp.alloc(ctx, tb));
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, nlow.p, lowptr.p, nrows + 1, ctx->stream));
+  DDF_CUDA(cub::DeviceScan::ExclusiveSum(temp.p, tb, nup.p, m->bup[R].p, nrows + 1, ctx->stream));
+  ctx->launches += 2;
+  uint32_t tot[2] = {0, 0};
+  DDF_CUDA(cudaMemcpyAsync(&tot[0], lowptr.p + nrows, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaMemcpyAsync(&tot[1], m->bup[R].p + nrows, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  bool ok = (int64_t)tot[0] + tot[1] == nnz && (int64_t)tot[1] == m->n[R];
+  if (ok) {
+    DDF_CHECK(lowcol.alloc(ctx, tot[0] ? tot[0] : 1));
+    k_upper_fill<<<grid, 256, 0, ctx->stream>>>(m->brow_ptr[R].p, m->bcol[R].p, nrows, lowptr.p, m->bup[R].p, lowcol.p, bad.p);
+    DDF_LAUNCH_CHECK(ctx);
+    uint32_t hb = 0;
+    DDF_CUDA(cudaMemcpyAsync(&hb, bad.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+    ok = hb == 0;
+  }
+  if (ok) {
+    DDF_CHECK(sell_build(ctx, lowptr.p, lowcol.p, nullptr, nrows, m->bsell[R], false, false));
+    ok = m->bsell[R].padded <= (int64_t)tot[0] + tot[0] / 4 + 32 * DDF_SELL_WIN;
+  }
+  if (!ok) { m->bsell[R].release(); m->bup[R].release(); return 0; }
+  // longest upper run of a 256-row window (+2 for the aligned start / even count): shared memory of the staged kernel
+  {
+    const int64_t nwin = ceil_div64(nrows, DDF_SELL_WIN);
+    std::vector<uint32_t> h(nwin + 1);
+    DDF_CUDA(cudaMemcpy2DAsync(h.data(), 4, m->bup[R].p, (size_t)DDF_SELL_WIN * 4, 4, nwin, cudaMemcpyDeviceToHost, ctx->stream));
+    DDF_CUDA(cudaMemcpyAsync(&h[nwin], m->bup[R].p + nrows, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint32_t mx = 0;
+    for (int64_t w = 0; w < nwin; w++) mx = std::max(mx, h[w + 1] - h[w]);
+    m->bup_cap[R] = (mx + 3u) & ~1u;
+  }
+  m->bsell_state[R] = 4;
+  return 0;
+}
+
 static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpNode* post, double alpha, double* y) {
   ddf_mesh* m = f->mesh;
   const double* pre_d = pre ? pre->diag : nullptr;
@@ -1436,9 +1584,15 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
     } else {
       // length-only sort: rows of equal length stay in row order (consecutive y stores, measured 20 % faster
       // than the stencil-signature sort on the Kuhn mesh)
-      DDF_CHECK(sell_build(f->ctx, m->brow_ptr[R].p, m->bcol[R].p, nullptr, f->nrows, m->bsell[R], false, false));
-      if (m->bsell[R].padded <= nnz + nnz / 8) m->bsell_state[R] = 1;
-      else { m->bsell_state[R] = 2; m->bsell[R].release(); }
+      // lower entries + upper runs: pays for long rows (vertex rows of a 3D mesh, 14 entries: 0.484 -> 0.436 ms at C4);
+      // rows of ~5 entries lose to the plain SELL copy (1.21 -> 1.39-1.51 ms), tuning 22 forces it for them anyway
+      if (R < m->D && g_tune_fixed != 20 && (nnz >= 8 * f->nrows || g_tune_fixed == 22 || g_tune_fixed == 21))
+        DDF_CHECK(upper_build(m, R, f->nrows));
+      if (m->bsell_state[R] == 0) {
+        DDF_CHECK(sell_build(f->ctx, m->brow_ptr[R].p, m->bcol[R].p, nullptr, f->nrows, m->bsell[R], false, false));
+        if (m->bsell[R].padded <= nnz + nnz / 8) m->bsell_state[R] = 1;
+        else { m->bsell_state[R] = 2; m->bsell[R].release(); }
+      }
     }
   }
   if (m->bsell_state[R] == 3 && g_tune_fixed != 9) {
@@ -1448,6 +1602,32 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
     else if (pre_d) k_apply_pairsign<true, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y);
     else if (post_d) k_apply_pairsign<false, true, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y);
     else k_apply_pairsign<false, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y);
+    DDF_LAUNCH_CHECK(f->ctx);
+    return 0;
+  }
+  if (m->bsell_state[R] == 4 && g_tune_fixed != 9) {
+    const int grid = (int)ceil_div64(f->nrows, DDF_SELL_WIN);
+    const SellBufs& sb = m->bsell[R];
+    const uint32_t* up = m->bup[R].p;
+    const bool short_rows = (int64_t)(R + 1) * m->n[R] < 8 * f->nrows;
+    // staged upper runs: one TMA bulk copy per window and array, when the longest window run fits ~24 KB of shared
+    // memory (8 blocks per SM stay resident) and x / pre are 16-byte aligned; tuning 21 keeps the global-memory loop
+    const uint32_t cap = m->bup_cap[R];
+    const size_t smem = (size_t)cap * 8 * (pre_d ? 2 : 1);
+    const bool stage = g_tune_fixed != 21 && smem <= 24 * 1024 + (pre_d ? 12 * 1024 : 0) && ((uintptr_t)x & 15) == 0 &&
+                       (!pre_d || ((uintptr_t)pre_d & 15) == 0);
+#define DDF_SELLUP(PRE_, POST_)                                                                                     \
+  do {                                                                                                              \
+    if (stage && short_rows) k_apply_sellsign<PRE_, POST_, 4, true, true><<<grid, DDF_SELL_WIN, smem, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, cap); \
+    else if (stage) k_apply_sellsign<PRE_, POST_, 8, true, true><<<grid, DDF_SELL_WIN, smem, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, cap);            \
+    else if (short_rows) k_apply_sellsign<PRE_, POST_, 4, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1); \
+    else k_apply_sellsign<PRE_, POST_, 8, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1);            \
+  } while (0)
+    if (pre_d && post_d) DDF_SELLUP(true, true);
+    else if (pre_d) DDF_SELLUP(true, false);
+    else if (post_d) DDF_SELLUP(false, true);
+    else DDF_SELLUP(false, false);
+#undef DDF_SELLUP
     DDF_LAUNCH_CHECK(f->ctx);
     return 0;
   }

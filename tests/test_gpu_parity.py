@@ -235,6 +235,49 @@ def test_prefix_packed_rows_match_explicit_table(ddf, ctx):
                 ddf._lib.call("ddf_set_tuning", b"packbits", 24)
 
 
+def test_boundary_upper_runs_match_plain_rows(ddf, ctx):
+    """Rows of the boundary matrix d_R (R < D): the cofaces that extend the row's simplex at the end are consecutive
+    ids, come last, and tile the R-simplices in row order (lexicographic numbering), so they are stored as run offsets
+    and -- one contiguous piece of x per 256-row window -- fetched by a single TMA bulk copy.  Bit for bit the plain
+    SELL copy, the row-CSR and the oracle, with and without fused stars, on ordered, shuffled and Delaunay meshes."""
+    rng = np.random.default_rng(91)
+    meshes = {"kuhn3": o.large_hypercube_tables(3, (10, 10, 10)), "kuhn3odd": o.large_hypercube_tables(3, (6, 6, 6)),
+              "kuhn2": o.large_hypercube_tables(2, (40, 40))}
+    simp, coords, weights = o.large_hypercube_tables(3, (8, 8, 8))
+    perm = rng.permutation(coords.shape[0])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    meshes["shuffled"] = (inv[simp], coords[perm], weights[perm])
+    pts = rng.random((300, 3))
+    meshes["delaunay3"] = (ddf.delaunay_mesh(pts), pts, np.zeros(len(pts)))
+    for name, (s_, c_, w_) in meshes.items():
+        om = o.build_manifold(name, s_, c_, w_)
+        D = om.D
+        ref = {}
+        for tune in (20, 22, 21, 0, 9):       # plain SELL; upper runs staged (forced for short rows) / global loop; default; CSR
+            ddf._lib.call("ddf_set_tuning", b"fixed", tune)
+            try:
+                dm = ddf.Manifold.from_simplices(name, s_, c_, w_, ctx=ctx)
+                rng2 = np.random.default_rng(5)
+                for R in range(1, D + 1):
+                    x = rng2.standard_normal(om.nsimplices(R))
+                    fx = ddf.Fun(dm, ddf.Dl, R, x)
+                    A = ddf.deriv(ddf.Dl, R, dm)                 # the matrix d_R as stored (ManifoldOps.jl:46)
+                    y = (A * fx).values
+                    g1 = ddf.op_from_diag(dm, ddf.Dl, R - 1, ddf.Dl, R - 1, rng2.standard_normal(om.nsimplices(R - 1)))
+                    g2 = ddf.op_from_diag(dm, ddf.Dl, R, ddf.Dl, R, rng2.standard_normal(om.nsimplices(R)))
+                    y2 = (((g1 * A) * g2) * fx).values           # fused diagonals on both sides
+                    if tune == 20:
+                        assert np.array_equal(y, o.apply_deriv(o.Dl, R, om, x)), (name, R)
+                        assert np.array_equal(y2, (g1 * (A * (g2 * fx))).values), (name, R)
+                        ref[R] = (y, y2)
+                    else:
+                        assert np.array_equal(y, ref[R][0]) and np.array_equal(y2, ref[R][1]), (name, R, tune)
+                dm.close()
+            finally:
+                ddf._lib.call("ddf_set_tuning", b"fixed", 0)
+
+
 def test_deriv_apply_ragged_sizes(ddf, ctx):
     """rows % 4 != 0 exercises the scalar tail of the 4-rows-per-thread kernel."""
     for n in (2, 6, 10):
