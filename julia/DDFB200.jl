@@ -182,6 +182,23 @@ function SparseArrays.sparse(A::DeviceOp)
     return SparseMatrixCSC{Float64,Int}(nr, nc, colptr, rowval, nzval)
 end
 
+# The operator held the way the reference holds every Op -- its assembled, chopped sparse matrix (src/Ops.jl:25) -- but
+# on the device: one row kernel per `A * f`, and the matrix a Krylov solver is handed in examples/poisson.jl:203
+function assemble(A::DeviceOp)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddf_op_assemble, lib), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), A.h, r))
+    op = DeviceOp(r[], A.m)
+    finalizer(x -> ccall((:ddf_op_destroy, lib), Cint, (Ptr{Cvoid},), x.h), op)
+    return op
+end
+
+# storage of the rows of deriv(Pr,k): :packed (prefix-packed rows) or :explicit (index table)
+function deriv_format(m::DeviceManifold, k::Int)
+    f = Ref{Cint}(0)
+    check(ccall((:ddf_mesh_deriv_format, lib), Cint, (Ptr{Cvoid}, Cint, Ref{Cint}), m.h, k, f))
+    return f[] == 1 ? :packed : :explicit
+end
+
 # OrdinaryDiffEq's stage broadcasts on the state vector (`@.. tmp = uprev + dt*(a31*k1 + a32*k2)`,
 # examples/wave.jl:134) in one pass
 function lincomb!(out::DeviceVector, base::DeviceVector, dt::Float64, coefs::Vector{Float64}, ks::Vector{DeviceVector})
