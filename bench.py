@@ -343,8 +343,9 @@ def run_b200(args):
         ms = time_op(lambda k=k: d[k].apply(x[k], y[k]), K)
         b = dk_bytes(cnt[k + 1], cnt[k], k)
         fmt = ddf.deriv_format(mfd, k)
-        # bytes the stored format moves: prefix-packed rows keep k+1 index words per row + one base per 32 rows
-        fb = b - (4 * cnt[k + 1] - cnt[k + 1] // 8) if fmt == "packed" else b
+        # bytes the stored format moves: bit-packed rows keep ONE 4- / 8-byte word per row, prefix-packed rows k+1
+        # index words, both + one base per 32 rows
+        fb = b - int((4 * (k + 2) - ddf.deriv_index_bytes(fmt, k)) * cnt[k + 1])
         breakdown[f"d{k}"] = {"ms": ms, "GBps": b / ms * 1e-6, "frac": b / ms * 1e-6 / peak, "bytes": b,
                               "row_format": fmt, "format_bytes": int(fb), "format_GBps": fb / ms * 1e-6,
                               "format_frac": fb / ms * 1e-6 / peak}
@@ -488,8 +489,11 @@ def run_b200(args):
 
     if rank == 0:
         d1_bytes = dk_bytes(cnt[2], cnt[1], 1)
-        d1_packed = breakdown["d1"]["row_format"] == "packed"
-        d1_kernel = "k_apply_packed_rows<3,4>" if d1_packed else "k_apply_fixed_rows<3,4>"
+        d1_fmt = breakdown["d1"]["row_format"]
+        d1_kernel = {"bits32": "k_apply_bits_rows<3,4,4>", "bits64": "k_apply_bits_rows<3,8,4>",
+                     "packed": "k_apply_packed_rows<3,4>", "explicit": "k_apply_fixed_rows<3,4>"}[d1_fmt]
+        d1_note = {"bits32": ", bit-packed 4-byte rows)", "bits64": ", bit-packed 8-byte rows)",
+                   "packed": ", prefix-packed rows)", "explicit": ")"}[d1_fmt]
         d1_format_bytes = breakdown["d1"]["format_bytes"]
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch); scaled by the
         # algorithmic bytes when this run's slab differs slightly from the captured n=256 cube
@@ -517,14 +521,14 @@ def run_b200(args):
                        "l2_hygiene": "inputs larger than L2 (index tables 0.9-2.4 GB, vectors 0.14-1.6 GB vs 126 MB L2)",
                        "parallelism": "none" if N == 1 else f"z-slabs x{N}, no collective in d_k/star_k apply; "
                                                             "NCCL send/recv halo in the wave step"},
-            "roofline": {"bound": "hbm", "kernel": d1_kernel + " (y = d1 x" + (", prefix-packed rows)" if d1_packed else ")"),
+            "roofline": {"bound": "hbm", "kernel": d1_kernel + " (y = d1 x" + d1_note,
                          "achieved": d1_bytes / d1_ms * 1e-6,
                          "peak": peak, "unit": "GB/s", "frac": d1_bytes / d1_ms * 1e-6 / peak, "traffic": traffic,
                          "traffic_unit": "bytes per launch (ncu dram read+write)", "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(d1_bytes),
                          "ms_per_launch": d1_ms, "frac_of_nominal_8TBs": d1_bytes / d1_ms * 1e-6 / 8000.0,
                          # `achieved` counts SURVEY 8(d)'s algorithmic bytes (explicit int32 indices); the packed rows
-                         # store one index word less per row, so the bytes actually moved are these:
+                         # store fewer index bytes per row, so the bytes actually moved are these:
                          "format_bytes_per_launch": int(d1_format_bytes),
                          "format_achieved": d1_format_bytes / d1_ms * 1e-6,
                          "format_frac": d1_format_bytes / d1_ms * 1e-6 / peak},

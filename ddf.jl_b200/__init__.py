@@ -8,7 +8,7 @@ the dotted name onto this directory).  All compute runs in libddf_b200.so
 from ._lib import DDFError, LIB_PATH, load  # noqa: F401
 from .core import (Context, Dl, Fun, Manifold, Op, Pr, default_context, op_from_csc, op_from_diag,  # noqa: F401
                    rand_fun, set_default_context, unit_fun, zero_fun)
-from .manifoldops import (boundary, boundary_of, coderiv, coderiv_of, delaunay_mesh, deriv, deriv_format, deriv_of,  # noqa: F401
+from .manifoldops import (boundary, boundary_of, coderiv, coderiv_of, delaunay_mesh, deriv, deriv_format, deriv_index_bytes, deriv_of,  # noqa: F401
                           hodge, hodge_of, integral, invhodge, invhodge_of, isboundary,
                           large_hypercube_manifold, laplace, laplace_of, one, refined_manifold,
                           refined_simplex_manifold, regular_simplex, sample, simplex_manifold, zero)

@@ -75,6 +75,18 @@ struct PackedBufs {
   void release() { words.release(); base.release(); state = 0; }
 };
 
+// bit-packed fixed-width rows of d_k (ops.cu, k_bits_*): ONE 4- or 8-byte word per row + one base per 32 rows.
+// Field widths are chosen per table from the largest differences it holds (index 0 against the smallest index 0 of
+// its 32-row group, every later index against its predecessor in the row: face ids ascend inside a row).
+struct BitRows {
+  DevBuf<uint32_t> words;   // nrows * wbytes / 4 words
+  DevBuf<uint32_t> base;    // smallest idx0 of every group of 32 rows
+  int wbytes = 0;           // 4 or 8
+  int b[4] = {0, 0, 0, 0};  // bits of idx0 - base, idx1 - idx0, idx2 - idx1, idx3 - idx2
+  int state = 0;            // 0 = not built, 1 = in use, 2 = does not fit (prefix-packed rows / explicit table)
+  void release() { words.release(); base.release(); wbytes = 0; state = 0; }
+};
+
 struct ddf_mesh {
   ddf_ctx* ctx = nullptr;
   int D = 0, C = 0;
@@ -125,6 +137,7 @@ struct ddf_mesh {
   // staged copies of the fixed-width tables of d_{R-1} = d_R^T (primal derivative apply)
   FStageBufs fstage[DDF_MAXD + 1];
   PackedBufs bpack[DDF_MAXD + 1];
+  BitRows bbits[DDF_MAXD + 1];
   DevBuf<double> utmp;                   // V   ping-pong buffer of the fused step
   DevBuf<double> ldinv;                  // V   1 ./ diag(L) for the fused Poisson relaxation step
   DevBuf<double> tsit_work;              // 16 V  stage derivatives and scratch of ddf_wave_tsit5 (allocated on first use)

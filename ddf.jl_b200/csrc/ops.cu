@@ -786,6 +786,221 @@ static int launch_packed(ddf_ctx* ctx, const PackedBufs& pb, int W, int64_t nrow
   return 0;
 }
 
+// ---------------------------------------------------------------- bit-packed rows of d_k
+// The face ids of a row ascend, the later ones lie a bounded way after the earlier ones (faces of one simplex share
+// vertices, ids are lexicographic ranks, Manifolds.jl:735-757), and rows that are stored next to each other start
+// near each other.  So a row is stored as ONE word of differences -- idx0 against the smallest idx0 of its 32-row
+// group, idx_p against idx_{p-1} -- with field widths chosen per table from the largest differences it holds
+// (k_bits_scan): 4 bytes per row when they sum to <= 32 bits, 8 bytes when <= 64, instead of 4 (W-1) / 4 W.
+// 3D Kuhn n=256: d1 rows (6+4+19 bits) take 4 bytes instead of 8, d2 rows at the top level (23+2+5+20 bits, rows in
+// the generator's order) 8 instead of 16.  Same gathers in the same order as k_apply_fixed_rows => identical bits.
+struct BitFmt {
+  int s1, s2, s3;                 // shifts of the fields idx1 - idx0, idx2 - idx1, idx3 - idx2
+  uint32_t m0, m1, m2, m3;        // field masks
+};
+
+template <int W>
+__global__ void __launch_bounds__(256)
+k_bits_scan(const int32_t* __restrict__ tab, int64_t nrows, uint32_t* __restrict__ base, uint32_t* __restrict__ maxd,
+            uint32_t* __restrict__ bad) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // a warp = one aligned group of 32 rows
+  const bool ok = r < nrows;
+  uint32_t idx[W];
+#pragma unroll
+  for (int p = 0; p < W; p++) idx[p] = ok ? (uint32_t)tab[r * W + p] : 0xffffffffu;
+  const uint32_t b = __reduce_min_sync(0xffffffffu, idx[0]);
+  if (ok && (threadIdx.x & 31) == 0) base[r >> 5] = b;
+  uint32_t d[W];
+  d[0] = ok ? idx[0] - b : 0u;
+  bool unsorted = false;
+#pragma unroll
+  for (int p = 1; p < W; p++) {
+    d[p] = ok ? idx[p] - idx[p - 1] : 0u;
+    unsorted |= ok && idx[p] <= idx[p - 1];
+  }
+  if (unsorted) atomicOr(bad, 1u);
+#pragma unroll
+  for (int p = 0; p < W; p++) {
+    const uint32_t mx = __reduce_max_sync(0xffffffffu, d[p]);
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(maxd + p, mx);
+  }
+}
+
+template <int W, int WB>
+__global__ void __launch_bounds__(256)
+k_bits_pack(const int32_t* __restrict__ tab, int64_t nrows, const uint32_t* __restrict__ base, BitFmt f,
+            uint32_t* __restrict__ words) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  uint32_t idx[W];
+#pragma unroll
+  for (int p = 0; p < W; p++) idx[p] = (uint32_t)tab[r * W + p];
+  uint64_t w = (uint64_t)(idx[0] - base[r >> 5]);
+  w |= (uint64_t)(idx[1] - idx[0]) << f.s1;
+  if constexpr (W > 2) w |= (uint64_t)(idx[2] - idx[1]) << f.s2;
+  if constexpr (W > 3) w |= (uint64_t)(idx[3] - idx[2]) << f.s3;
+  if (WB == 4) words[r] = (uint32_t)w;
+  else reinterpret_cast<uint2*>(words)[r] = make_uint2((uint32_t)w, (uint32_t)(w >> 32));
+}
+
+// lane = consecutive rows, RPW groups of 32 rows per warp (the mapping of k_apply_fixed_rows)
+template <int W, int WB, int RPW, bool PRE, bool POST>
+__global__ void __launch_bounds__(256)
+k_apply_bits_rows(const uint32_t* __restrict__ words, const uint32_t* __restrict__ base, BitFmt f, int64_t nrows,
+                  int first_negative, const double* __restrict__ x, double* __restrict__ y,
+                  const double* __restrict__ pre, const double* __restrict__ post, double alpha) {
+  const uint64_t pol_keep = make_policy_evict_last();
+  const uint64_t pol_stream = make_policy_evict_first();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r0 = warp * (32 * RPW) + lane;
+  if (warp * (32 * RPW) >= nrows) return;
+  uint32_t idx[RPW][W];
+#pragma unroll
+  for (int k = 0; k < RPW; k++) {
+    const int64_t r = r0 + 32 * k;
+    const bool ok = r < nrows;
+    const uint32_t b = ok ? __ldg(base + warp * RPW + k) : 0u;
+    if constexpr (WB == 4) {          // one 4-byte word per row, 128 B per warp
+      const uint32_t w = ok ? (uint32_t)ld_stream_int(reinterpret_cast<const int*>(words) + r) : 0u;
+      idx[k][0] = b + (w & f.m0);
+      idx[k][1] = idx[k][0] + ((w >> f.s1) & f.m1);
+      if constexpr (W > 2) idx[k][2] = idx[k][1] + ((w >> f.s2) & f.m2);
+      if constexpr (W > 3) idx[k][3] = idx[k][2] + ((w >> f.s3) & f.m3);
+    } else {                          // one 8-byte word per row, 256 B per warp
+      int2 v = make_int2(0, 0);
+      if (ok) v = ld_stream_int2(reinterpret_cast<const int2*>(words) + r);
+      const uint64_t w = (uint64_t)(uint32_t)v.x | ((uint64_t)(uint32_t)v.y << 32);
+      idx[k][0] = b + ((uint32_t)w & f.m0);
+      idx[k][1] = idx[k][0] + ((uint32_t)(w >> f.s1) & f.m1);
+      if constexpr (W > 2) idx[k][2] = idx[k][1] + ((uint32_t)(w >> f.s2) & f.m2);
+      if constexpr (W > 3) idx[k][3] = idx[k][2] + ((uint32_t)(w >> f.s3) & f.m3);
+    }
+  }
+  double xv[RPW][W];
+#pragma unroll
+  for (int k = 0; k < RPW; k++)
+#pragma unroll
+    for (int p = 0; p < W; p++) xv[k][p] = ld_keep_f64(x + idx[k][p], pol_keep);
+  if (PRE) {
+#pragma unroll
+    for (int k = 0; k < RPW; k++)
+#pragma unroll
+      for (int p = 0; p < W; p++) xv[k][p] = __dmul_rn(ld_keep_f64(pre + idx[k][p], pol_keep), xv[k][p]);
+  }
+#pragma unroll
+  for (int k = 0; k < RPW; k++) {
+    const int64_t r = r0 + 32 * k;
+    double a = 0.0;
+#pragma unroll
+    for (int p = 0; p < W; p++) {
+      const bool neg = ((p & 1) != 0) != (first_negative != 0);
+      a = neg ? __dsub_rn(a, xv[k][p]) : __dadd_rn(a, xv[k][p]);
+    }
+    if (r < nrows) {
+      if (POST) a = __dmul_rn(ld_stream_f64(post + r), a);
+      if (alpha != 1.0) a = __dmul_rn(alpha, a);
+      st_hint_f64(y + r, a, pol_stream);
+    }
+  }
+}
+
+static BitFmt bits_fmt(const BitRows& br) {
+  BitFmt f;
+  f.s1 = br.b[0]; f.s2 = br.b[0] + br.b[1]; f.s3 = br.b[0] + br.b[1] + br.b[2];
+  auto mask = [](int bits) { return bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u); };
+  f.m0 = mask(br.b[0]); f.m1 = mask(br.b[1]); f.m2 = mask(br.b[2]); f.m3 = mask(br.b[3]);
+  return f;
+}
+
+static int bits_build(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, BitRows& br) {
+  br.release();
+  br.state = 2;
+  if (W < 3 || W > 4 || nrows == 0) return 0;
+  DevBuf<uint32_t> stat;                       // maxd[0..3], bad
+  DDF_CHECK(stat.alloc(ctx, 5));
+  DDF_CUDA(cudaMemsetAsync(stat.p, 0, 5 * 4, ctx->stream));
+  DDF_CHECK(br.base.alloc(ctx, (size_t)ceil_div64(nrows, 32)));
+  int grid;
+  DDF_CHECK(grid_for(nrows, 256, &grid));
+  if (W == 3) k_bits_scan<3><<<grid, 256, 0, ctx->stream>>>(tab, nrows, br.base.p, stat.p, stat.p + 4);
+  else k_bits_scan<4><<<grid, 256, 0, ctx->stream>>>(tab, nrows, br.base.p, stat.p, stat.p + 4);
+  DDF_LAUNCH_CHECK(ctx);
+  uint32_t h[5] = {0, 0, 0, 0, 0};
+  DDF_CUDA(cudaMemcpyAsync(h, stat.p, 5 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  int total = 0;
+  for (int p = 0; p < 4; p++) {
+    int bits = 1;
+    while (bits < 32 && (h[p] >> bits) != 0) bits++;
+    br.b[p] = p < W ? bits : 0;
+    total += br.b[p];
+  }
+  if (h[4] || total > 64) { br.base.release(); return 0; }
+  br.wbytes = total <= 32 ? 4 : 8;
+  DDF_CHECK(br.words.alloc(ctx, (size_t)nrows * (br.wbytes / 4)));
+  const BitFmt f = bits_fmt(br);
+  if (W == 3 && br.wbytes == 4) k_bits_pack<3, 4><<<grid, 256, 0, ctx->stream>>>(tab, nrows, br.base.p, f, br.words.p);
+  else if (W == 3) k_bits_pack<3, 8><<<grid, 256, 0, ctx->stream>>>(tab, nrows, br.base.p, f, br.words.p);
+  else if (br.wbytes == 4) k_bits_pack<4, 4><<<grid, 256, 0, ctx->stream>>>(tab, nrows, br.base.p, f, br.words.p);
+  else k_bits_pack<4, 8><<<grid, 256, 0, ctx->stream>>>(tab, nrows, br.base.p, f, br.words.p);
+  DDF_LAUNCH_CHECK(ctx);
+  br.state = 1;
+  return 0;
+}
+
+template <int W, int WB>
+static void launch_bits_w(ddf_ctx* ctx, const BitRows& br, const BitFmt& f, int64_t nrows, int first_negative,
+                          const double* x, const double* pre, const double* post, double alpha, double* y) {
+  constexpr int RPW = W == 3 ? 4 : 3;
+  const int g = (int)ceil_div64(ceil_div64(nrows, RPW), 256);
+  const uint32_t *w = br.words.p, *b = br.base.p;
+  if (!pre && !post && (g_tune_fixed == 21 || g_tune_fixed == 22)) {      // A/B: other rows-per-lane counts
+    constexpr int RA = W == 3 ? 8 : 4, RB = 2;
+    if (g_tune_fixed == 21)
+      k_apply_bits_rows<W, WB, RA, false, false><<<(int)ceil_div64(ceil_div64(nrows, RA), 256), 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
+    else
+      k_apply_bits_rows<W, WB, RB, false, false><<<(int)ceil_div64(ceil_div64(nrows, RB), 256), 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
+    return;
+  }
+  if (pre && post) k_apply_bits_rows<W, WB, RPW, true, true><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
+  else if (pre) k_apply_bits_rows<W, WB, RPW, true, false><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
+  else if (post) k_apply_bits_rows<W, WB, RPW, false, true><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
+  else k_apply_bits_rows<W, WB, RPW, false, false><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
+}
+
+static int launch_bits(ddf_ctx* ctx, const BitRows& br, int W, int64_t nrows, int first_negative, const double* x,
+                       const double* pre, const double* post, double alpha, double* y) {
+  const BitFmt f = bits_fmt(br);
+  if (W == 3 && br.wbytes == 4) launch_bits_w<3, 4>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y);
+  else if (W == 3) launch_bits_w<3, 8>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y);
+  else if (br.wbytes == 4) launch_bits_w<4, 4>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y);
+  else launch_bits_w<4, 8>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y);
+  DDF_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+// Which storage the rows of d_{R-1} (the table of level R) use on this mesh, built on first use:
+// 0 = explicit table, 1 = prefix-packed, 2 = bit-packed 4-byte rows, 3 = bit-packed 8-byte rows.
+// Tuning: fixed 18 = explicit only, 20 = no bit-packed rows; a narrowed "packbits" (tests) also switches them off.
+static int dk_rows_format(ddf_mesh* m, int R, int* fmt) {
+  const int W = R + 1;
+  *fmt = 0;
+  if (W < 2 || W > 4 || m->n[R] == 0) return 0;
+  if (!(g_tune_fixed == 0 || (g_tune_fixed >= 19 && g_tune_fixed <= 22))) return 0;
+  const bool allow_bits = W >= 3 && g_tune_fixed != 20 && g_tune_packbits == 24;
+  BitRows& br = m->bbits[R];
+  PackedBufs& pb = m->bpack[R];
+  if (allow_bits) {
+    if (br.state == 0) DDF_CHECK(bits_build(m->ctx, m->bnd_table(R), W, m->n[R], br));
+    if (br.state == 1 && (br.wbytes == 4 || W == 4)) { *fmt = br.wbytes == 4 ? 2 : 3; return 0; }
+  }
+  if (pb.state == 0) DDF_CHECK(packed_build(m->ctx, m->bnd_table(R), W, m->n[R], pb));
+  if (pb.state == 1) { *fmt = 1; return 0; }
+  if (allow_bits && br.state == 1) *fmt = 3;      // W = 3 rows that do not prefix-pack (top level): 8 instead of 12 bytes
+  return 0;
+}
+
 template <int W>
 static void launch_fixed_x(ddf_ctx* ctx, int var, const int32_t* tab, int64_t nrows, int first_negative,
                            const double* x, double* y) {
@@ -1556,10 +1771,11 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
       }
     }
     // default: prefix-packed rows (4 bytes less index data per row); tuning 18 keeps the explicit table
-    if ((g_tune_fixed == 0 || g_tune_fixed == 19) && W >= 2 && W <= 4 && f->nrows > 0) {
-      PackedBufs& pb = m->bpack[f->R];
-      if (pb.state == 0) DDF_CHECK(packed_build(f->ctx, m->bnd_table(f->R), W, f->nrows, pb));
-      if (pb.state == 1) return launch_packed(f->ctx, pb, W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
+    {
+      int fmt = 0;
+      DDF_CHECK(dk_rows_format(m, f->R, &fmt));
+      if (fmt >= 2) return launch_bits(f->ctx, m->bbits[f->R], W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
+      if (fmt == 1) return launch_packed(f->ctx, m->bpack[f->R], W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
     }
     return launch_fixed(f->ctx, m->bnd_table(f->R), W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
   }
@@ -2314,9 +2530,8 @@ extern "C" int ddf_mesh_deriv_format(ddf_mesh* m, int k, int* format) {
   DDF_CHECK(ddf_mesh_require_assembled(m));
   if (k < 0 || k >= m->D) DDF_FAIL("deriv_format: need 0 <= k < D");
   const int R = k + 1, W = R + 1;
-  PackedBufs& pb = m->bpack[R];
-  if (pb.state == 0 && W <= 4 && m->n[R] > 0) DDF_CHECK(packed_build(m->ctx, m->bnd_table(R), W, m->n[R], pb));
-  *format = pb.state == 1 ? 1 : 0;
+  (void)W;
+  DDF_CHECK(dk_rows_format(m, R, format));
   return 0;
   DDF_TRY_END
 }

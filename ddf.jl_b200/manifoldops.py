@@ -216,11 +216,17 @@ def large_hypercube_manifold(D: int, nelts: Optional[Sequence[int]] = None, ctx:
 
 
 def deriv_format(mfd, k: int) -> str:
-    """Storage of the rows of deriv(Pr,k) the apply kernels use on this mesh: "packed" (the first face of a row is
-    its prefix -- W-1 words per row + one base per 32 rows) or "explicit" (the top level, whose rows keep the
-    caller's order; meshes that do not pack).  Same bits either way."""
+    """Storage of the rows of deriv(Pr,k) the apply kernels use on this mesh: "bits32" / "bits64" (one 4- / 8-byte
+    word of index differences per row, field widths chosen per table, + one base per 32 rows), "packed" (the first
+    face of a row is its prefix -- W-1 words per row + one base per 32 rows) or "explicit" (tables whose differences
+    do not fit, e.g. top simplices given in a scattered order).  Same bits either way."""
     import ctypes as C
     from ._lib import call
     f = C.c_int()
     call("ddf_mesh_deriv_format", mfd._h, int(k), C.byref(f))
-    return ("explicit", "packed")[f.value]
+    return ("explicit", "packed", "bits32", "bits64")[f.value]
+
+
+def deriv_index_bytes(fmt: str, k: int) -> float:
+    """Index bytes per row of deriv(Pr,k) in storage `fmt` (see deriv_format)."""
+    return {"explicit": 4.0 * (k + 2), "packed": 4.0 * (k + 1) + 0.125, "bits32": 4.125, "bits64": 8.125}[fmt]

@@ -179,10 +179,13 @@ int ddf_op_scale(double a, ddf_op* A, ddf_op** out);
 int ddf_op_adjoint(ddf_op* A, ddf_op** out);
 /* Op*Fun (Ops.jl:273-276): y = A x */
 int ddf_op_apply(ddf_op* A, ddf_vec* x, ddf_vec* y);
-/* Storage of the rows of d_k = deriv(Pr,k) the apply kernels use on this mesh: 1 = prefix-packed (the first face of
- * every row is its prefix, whose ids run non-decreasing down the rows: W-1 words per row + a base per 32 rows),
- * 0 = explicit index table (the top level, whose rows come in the caller's order, and meshes that do not pack).
- * Both give identical bits (same gathers, same order). */
+/* Storage of the rows of d_k = deriv(Pr,k) the apply kernels use on this mesh (chosen on first use):
+ * 2 / 3 = bit-packed rows: ONE 4- / 8-byte word of index differences per row (index 0 against the smallest index 0
+ * of its 32-row group, every later index against its predecessor; field widths chosen per table from the largest
+ * differences it holds) + a base per 32 rows; 1 = prefix-packed (the first face of every row is its prefix, whose
+ * ids run non-decreasing down the rows: W-1 words per row + a base per 32 rows); 0 = explicit index table (tables
+ * whose differences do not fit, e.g. top simplices given in a scattered order).  All give identical bits (same
+ * gathers, same order). */
 int ddf_mesh_deriv_format(ddf_mesh* m, int k, int* format);
 /* The operator in the reference's own representation: every Op holds its assembled sparse matrix (Ops.jl:25),
  * rounded and chopped after each product / sum (Ops.jl:36-58,186-232), and `A * f` is a sparse mat-vec on it

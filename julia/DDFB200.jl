@@ -192,11 +192,12 @@ function assemble(A::DeviceOp)
     return op
 end
 
-# storage of the rows of deriv(Pr,k): :packed (prefix-packed rows) or :explicit (index table)
+# storage of the rows of deriv(Pr,k): :bits32 / :bits64 (one word of index differences per row), :packed
+# (prefix-packed rows) or :explicit (index table)
 function deriv_format(m::DeviceManifold, k::Int)
     f = Ref{Cint}(0)
     check(ccall((:ddf_mesh_deriv_format, lib), Cint, (Ptr{Cvoid}, Cint, Ref{Cint}), m.h, k, f))
-    return f[] == 1 ? :packed : :explicit
+    return (:explicit, :packed, :bits32, :bits64)[f[] + 1]
 end
 
 # OrdinaryDiffEq's stage broadcasts on the state vector (`@.. tmp = uprev + dt*(a31*k1 + a32*k2)`,

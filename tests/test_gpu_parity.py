@@ -201,11 +201,18 @@ def test_prefix_packed_rows_match_explicit_table(ddf, ctx):
                 omg = with_device_geometry(om, dm)
                 for k in range(D):
                     fmt = ddf.deriv_format(dm, k)
+                    ddf._lib.call("ddf_set_tuning", b"fixed", 20)          # no bit-packed rows: the prefix-packed storage
+                    try:
+                        fmt20 = ddf.deriv_format(dm, k)
+                    finally:
+                        ddf._lib.call("ddf_set_tuning", b"fixed", 0)
                     if k == D - 1 or bits == 3:
-                        # top level: rows in input order (only a mesh given in lexicographic order would pack)
-                        assert fmt == "explicit" or (k == D - 1 and bits == 24), (name, k, fmt)
+                        # top level: rows in input order (only a mesh given in lexicographic order would prefix-pack)
+                        assert fmt20 == "explicit" or (k == D - 1 and bits == 24), (name, k, fmt20)
+                        assert fmt == "explicit" or bits == 24, (name, k, fmt)
                     else:
-                        assert fmt == "packed", (name, k, bits)
+                        assert fmt20 == "packed", (name, k, bits)
+                        assert fmt == ("packed" if k == 0 else "bits32"), (name, k, fmt)
                     x = rng.standard_normal(om.nsimplices(k))
                     fx = ddf.Fun(dm, ddf.Pr, k, x)
                     d = ddf.deriv(ddf.Pr, k, dm)
@@ -224,15 +231,72 @@ def test_prefix_packed_rows_match_explicit_table(ddf, ctx):
                         assert np.array_equal(((h1 * d) * fx).values, y1), (name, k, bits)
                     finally:
                         ddf._lib.call("ddf_set_tuning", b"fixed", 0)
-                    ddf._lib.call("ddf_set_tuning", b"fixed", 19)          # packed d0 with lane = consecutive rows
-                    try:
-                        assert np.array_equal((d * fx).values, y), (name, k, bits)
-                    finally:
-                        ddf._lib.call("ddf_set_tuning", b"fixed", 0)
+                    # 19: packed d0 with lane = consecutive rows; 20: prefix-packed instead of bit-packed rows;
+                    # 21, 22: other rows-per-lane counts of the bit-packed kernel
+                    for var in (19, 20, 21, 22):
+                        ddf._lib.call("ddf_set_tuning", b"fixed", var)
+                        try:
+                            assert np.array_equal((d * fx).values, y), (name, k, bits, var)
+                            if var == 20:
+                                assert np.array_equal(((h1 * d) * fx).values, y1), (name, k, bits)
+                                assert np.array_equal(((d * g) * fx).values, y2), (name, k, bits)
+                        finally:
+                            ddf._lib.call("ddf_set_tuning", b"fixed", 0)
                 del omg
                 dm.close()
             finally:
                 ddf._lib.call("ddf_set_tuning", b"packbits", 24)
+
+
+def test_bit_packed_rows_match_explicit_table(ddf, ctx):
+    """Default storage of d_1, d_2: ONE word of index differences per row (index 0 against the smallest index 0 of its
+    32-row group, later indices against their predecessors), 4 or 8 bytes as the table's largest differences need.
+    Every (row width, word size) combination, bit for bit the explicit-table kernel and the oracle, plain and with
+    fused Hodge stars on either side: Kuhn cubes (d1: 4-byte words; d2 at the top level: 4-byte words on a small cube,
+    8-byte words on a larger one), a vertex-shuffled cube (8-byte words for d2), a large random Delaunay triangulation
+    in Qhull's triangle order (d1 at the top level: 8-byte words), a ragged row count (not a multiple of 32 * RPW)."""
+    rng = np.random.default_rng(78)
+    meshes = {}
+    meshes["kuhn3n6"] = o.large_hypercube_tables(3, (6, 6, 6)) + ({1: "bits32", 2: "bits32"},)
+    meshes["kuhn3n24"] = o.large_hypercube_tables(3, (24, 24, 24)) + ({1: "bits32", 2: "bits64"},)
+    simp, coords, weights = o.large_hypercube_tables(3, (8, 8, 8))
+    perm = rng.permutation(coords.shape[0])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    meshes["shuffled"] = (inv[simp], coords[perm], weights[perm], {1: "bits32", 2: "bits64"})
+    pts = rng.random((30000, 2))
+    meshes["delaunay2"] = (ddf.delaunay_mesh(pts), pts, np.zeros(len(pts)), {1: "bits64"})
+    seen = set()
+    for name, (s_, c_, w_, expect) in meshes.items():
+        om = o.build_manifold(name, s_, c_, w_)
+        dm = ddf.Manifold.from_simplices(name, s_, c_, w_, ctx=ctx)
+        for k in range(1, om.D):
+            fmt = ddf.deriv_format(dm, k)
+            assert fmt == expect[k], (name, k, fmt)
+            seen.add((k + 2, fmt))
+            x = rng.standard_normal(om.nsimplices(k))
+            fx = ddf.Fun(dm, ddf.Pr, k, x)
+            d = ddf.deriv(ddf.Pr, k, dm)
+            y = (d * fx).values
+            assert np.array_equal(y, o.apply_deriv(o.Pr, k, om, x)), (name, k)
+            h1 = ddf.hodge(ddf.Pr, k + 1, dm)
+            g = ddf.op_from_diag(dm, ddf.Pr, k, ddf.Pr, k, rng.standard_normal(om.nsimplices(k)))
+            y1 = ((h1 * d) * fx).values
+            y2 = ((d * g) * fx).values
+            y3 = ((h1 * d * g) * fx).values
+            assert np.array_equal(y1, (h1 * (d * fx)).values), (name, k)
+            assert np.array_equal(y2, (d * (g * fx)).values), (name, k)
+            assert np.array_equal(y3, (h1 * (d * (g * fx))).values), (name, k)
+            for var in (18, 20, 21, 22):                     # explicit table; no bit-packed rows; other rows per lane
+                ddf._lib.call("ddf_set_tuning", b"fixed", var)
+                try:
+                    assert np.array_equal((d * fx).values, y), (name, k, var)
+                    assert np.array_equal(((h1 * d) * fx).values, y1), (name, k, var)
+                    assert np.array_equal(((d * g) * fx).values, y2), (name, k, var)
+                finally:
+                    ddf._lib.call("ddf_set_tuning", b"fixed", 0)
+        dm.close()
+    assert seen == {(3, "bits32"), (3, "bits64"), (4, "bits32"), (4, "bits64")}, seen
 
 
 def test_boundary_upper_runs_match_plain_rows(ddf, ctx):
