@@ -216,6 +216,11 @@ __device__ __forceinline__ void st_hint_f64x2(double2* p, double a, double b, ui
 __device__ __forceinline__ void st_hint_f64(double* p, double a, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(a), "l"(pol) : "memory");
 }
+// L2 prefetch of a contiguous piece of global memory (address and size multiples of 16 bytes): a block asks for the
+// index words a LATER block will read, so that block's first load hits L2 instead of waiting on HBM.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
 // streaming (write-once) stores: evict-first so the outputs do not push the
 // gathered x out of L2.
 __device__ __forceinline__ void st_stream_f64x2(double2* p, double a, double b) {

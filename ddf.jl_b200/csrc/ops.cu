@@ -27,6 +27,10 @@
 
 extern int g_tune_fixed;
 static int g_tune_packbits = 24;
+// blocks ahead a block prefetches index words into L2 (0 = off).  Measured at C4 (profiles/r01_tuning.md): any
+// distance from 148 to 2368 blocks gives the same gain; 4 x 148 keeps the request well ahead of the block scheduler.
+static int g_tune_prefetch = 592;
+static int g_tune_diagpf = 0;        // the same for the x and diagonal streams of k_apply_diag
 int ddf_laplace0_apply(ddf_mesh* m, const double* x, double* y);   // wave.cu
 
 enum OpKind { OPK_ZERO = 0, OPK_FIXED, OPK_CSRSIGN, OPK_DIAG, OPK_CSRF64, OPK_LAPLACE0, OPK_CHAIN, OPK_SUM };
@@ -194,9 +198,14 @@ __global__ void k_build_pairs(const uint32_t* __restrict__ rowptr, const uint32_
 template <bool PRE, bool POST, int RPW>
 __global__ void __launch_bounds__(256)
 k_apply_pairsign(const uint32_t* __restrict__ pair, int64_t nrows, const double* __restrict__ x,
-                 const double* __restrict__ pre, const double* __restrict__ post, double alpha, double* __restrict__ y) {
+                 const double* __restrict__ pre, const double* __restrict__ post, double alpha, double* __restrict__ y,
+                 int pf_blocks = 0) {
   const uint64_t pol_keep = make_policy_evict_last();
   const uint64_t pol_stream = make_policy_evict_first();
+  if (pf_blocks && threadIdx.x == 0) {       // pairs of the block that runs pf_blocks later: 256 * RPW rows, contiguous
+    const int64_t rp = ((int64_t)blockIdx.x + pf_blocks) * (256 * RPW);
+    if (rp + 256 * RPW <= nrows) bulk_prefetch_l2(pair + 2 * rp, 256 * RPW * 8);
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t r0 = warp * (32 * RPW) + lane;
@@ -240,13 +249,19 @@ k_apply_pairsign(const uint32_t* __restrict__ pair, int64_t nrows, const double*
 // STAGE: the upper runs of the 256 rows of a window are ONE contiguous piece of x (and of pre): thread 0 fetches it
 // with a single TMA bulk copy per array while all threads gather their lower entries; the upper sums then read
 // shared memory.  `cap` = doubles of shared memory per array (the longest window run of the mesh, rounded).
-template <bool PRE, bool POST, int BATCH = 8, bool UP = false, bool STAGE = false>
+template <bool PRE, bool POST, int BATCH = 8, bool UP = false, bool STAGE = false, int CB = BATCH>
 __global__ void __launch_bounds__(256)
 k_apply_sellsign(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict__ perm8,
                  const uint32_t* __restrict__ scol, int64_t nrows, const double* __restrict__ x,
                  const double* __restrict__ pre, const double* __restrict__ post, double alpha,
                  double* __restrict__ y, const uint32_t* __restrict__ up = nullptr, int up_negative = 0,
-                 uint32_t cap = 0) {
+                 uint32_t cap = 0, int pf_blocks = 0) {
+  if (pf_blocks && threadIdx.x == 0 && blockIdx.x + pf_blocks < gridDim.x) {
+    // index words of the window that runs pf_blocks later (slice offsets are multiples of 32 entries = 128 bytes)
+    const int64_t sp = ((int64_t)blockIdx.x + pf_blocks) * (DDF_SELL_WIN / 32);
+    const uint32_t pa = sell_ptr[sp], pb = sell_ptr[sp + DDF_SELL_WIN / 32];
+    if (pb > pa) bulk_prefetch_l2(scol + pa, (pb - pa) * 4u);
+  }
   const int64_t r = (int64_t)blockIdx.x * DDF_SELL_WIN + threadIdx.x;        // sorted position
   const int64_t i = (int64_t)blockIdx.x * DDF_SELL_WIN + perm8[r];           // the row it holds
   const uint64_t pol_stream = make_policy_evict_first();
@@ -275,22 +290,28 @@ k_apply_sellsign(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restric
   const uint32_t base = sell_ptr[s] + (uint32_t)(r & 31);
   const uint32_t w = (sell_ptr[s + 1] - sell_ptr[s]) >> 5;
   double a = 0.0;
-  for (uint32_t q0 = 0; q0 < w; q0 += BATCH) {
-    uint32_t cw[BATCH];
-    double xv[BATCH];
+  // CB index words are fetched at once, their gathers issued in groups of BATCH (CB > BATCH: the index loads of a
+  // row of up to CB entries are ONE round trip although only BATCH gathered values are held at a time)
+  for (uint32_t q0 = 0; q0 < w; q0 += CB) {
+    uint32_t cw[CB];
 #pragma unroll
-    for (int q = 0; q < BATCH; q++)
+    for (int q = 0; q < CB; q++)
       cw[q] = (q0 + q < w) ? (uint32_t)ld_stream_int(reinterpret_cast<const int*>(scol) + (size_t)base + (size_t)(q0 + q) * 32)
                            : DDF_SELL_PAD;
 #pragma unroll
-    for (int q = 0; q < BATCH; q++) {
-      const uint32_t c = cw[q] != DDF_SELL_PAD ? (cw[q] & 0x7fffffffu) : 0u;
-      xv[q] = ld_keep_f64(x + c, pol_keep);
-      if (PRE) xv[q] = __dmul_rn(ld_keep_f64(pre + c, pol_keep), xv[q]);
-    }
+    for (int g = 0; g < CB; g += BATCH) {
+      if (g > 0 && q0 + g >= w) break;
+      double xv[BATCH];
 #pragma unroll
-    for (int q = 0; q < BATCH; q++)
-      if (cw[q] != DDF_SELL_PAD) a = (cw[q] >> 31) ? __dsub_rn(a, xv[q]) : __dadd_rn(a, xv[q]);
+      for (int q = 0; q < BATCH; q++) {
+        const uint32_t c = cw[g + q] != DDF_SELL_PAD ? (cw[g + q] & 0x7fffffffu) : 0u;
+        xv[q] = ld_keep_f64(x + c, pol_keep);
+        if (PRE) xv[q] = __dmul_rn(ld_keep_f64(pre + c, pol_keep), xv[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < BATCH; q++)
+        if (cw[g + q] != DDF_SELL_PAD) a = (cw[g + q] >> 31) ? __dsub_rn(a, xv[q]) : __dadd_rn(a, xv[q]);
+    }
   }
   if (STAGE && staged) stage_wait(&mbar, 0);
   if (i >= nrows) return;
@@ -325,7 +346,12 @@ k_apply_sellsign(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restric
 // array, read-once loads (L1 no-allocate), evict-first stores; the tail and unaligned views take the scalar path.
 __global__ void __launch_bounds__(256)
 k_apply_diag(const double* __restrict__ d, double sign_or_scale, const double* __restrict__ x, double* __restrict__ y,
-             int64_t n) {
+             int64_t n, int pf_blocks) {
+  if (pf_blocks && (threadIdx.x == 0 || threadIdx.x == 32)) {   // x and d of the block that runs pf_blocks later
+    const int64_t ip = ((int64_t)blockIdx.x + pf_blocks) * 1024;
+    const double* src = threadIdx.x == 0 ? x : d;
+    if (src && ip + 1024 <= n && ((uintptr_t)src & 15) == 0) bulk_prefetch_l2(src + ip, 8192);
+  }
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   if (i + 3 < n) {
@@ -397,13 +423,17 @@ k_apply_sellf64(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict
 }
 
 extern int g_tune_wave;   // wave.cu
+extern int g_tune_wavepf; // wave.cu
 extern int g_tune_asm;    // mesh.cu
 extern int g_tune_fixed;
 extern "C" int ddf_set_tuning(const char* key, int value) {
   if (!strcmp(key, "fixed")) g_tune_fixed = value;
   else if (!strcmp(key, "wave")) g_tune_wave = value;
+  else if (!strcmp(key, "diagpf")) g_tune_diagpf = value >= 0 ? value : 0;
+  else if (!strcmp(key, "wavepf")) g_tune_wavepf = value >= 0 && value < 8 ? value : 0;
   else if (!strcmp(key, "asm")) g_tune_asm = value;
   else if (!strcmp(key, "packbits")) g_tune_packbits = value >= 1 && value <= 24 ? value : 24;
+  else if (!strcmp(key, "prefetch")) g_tune_prefetch = value >= 0 ? value : 0;
   else DDF_FAIL("set_tuning: unknown key %s", key);
   return 0;
 }
@@ -684,9 +714,13 @@ template <bool PRE, bool POST>
 __global__ void __launch_bounds__(256)
 k_apply_packed_quad(const uint32_t* __restrict__ words, const uint32_t* __restrict__ base, int64_t nrows,
                     int first_negative, const double* __restrict__ x, double* __restrict__ y,
-                    const double* __restrict__ pre, const double* __restrict__ post, double alpha) {
+                    const double* __restrict__ pre, const double* __restrict__ post, double alpha, int pf_blocks) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t r0 = t * 4;
+  if (pf_blocks && threadIdx.x == 0) {       // words of the block that runs pf_blocks later: 1024 rows, contiguous
+    const int64_t rp = ((int64_t)blockIdx.x + pf_blocks) * 1024;
+    if (rp + 1024 <= nrows) bulk_prefetch_l2(words + rp, 4096);
+  }
   if (r0 >= nrows) return;
   const uint64_t pol_keep = make_policy_evict_last();
   const uint64_t pol_stream = make_policy_evict_first();
@@ -772,7 +806,7 @@ static int launch_packed(ddf_ctx* ctx, const PackedBufs& pb, int W, int64_t nrow
   const bool quad = W == 2 && g_tune_fixed != 19;
 #define DDF_PACKED_CASE(PRE_, POST_)                                                                                 \
   do {                                                                                                               \
-    if (quad) k_apply_packed_quad<PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha); \
+    if (quad) k_apply_packed_quad<PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch); \
     else if (W == 2) k_apply_packed_rows<2, 4, PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha); \
     else if (W == 3) k_apply_packed_rows<3, 4, PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha); \
     else k_apply_packed_rows<4, 3, PRE_, POST_><<<g3, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha);             \
@@ -848,9 +882,13 @@ template <int W, int WB, int RPW, bool PRE, bool POST>
 __global__ void __launch_bounds__(256)
 k_apply_bits_rows(const uint32_t* __restrict__ words, const uint32_t* __restrict__ base, BitFmt f, int64_t nrows,
                   int first_negative, const double* __restrict__ x, double* __restrict__ y,
-                  const double* __restrict__ pre, const double* __restrict__ post, double alpha) {
+                  const double* __restrict__ pre, const double* __restrict__ post, double alpha, int pf_blocks) {
   const uint64_t pol_keep = make_policy_evict_last();
   const uint64_t pol_stream = make_policy_evict_first();
+  if (pf_blocks && threadIdx.x == 0) {       // words of the block that runs pf_blocks later: 256 * RPW rows, contiguous
+    const int64_t rp = ((int64_t)blockIdx.x + pf_blocks) * (256 * RPW);
+    if (rp + 256 * RPW <= nrows) bulk_prefetch_l2(reinterpret_cast<const char*>(words) + rp * WB, 256 * RPW * WB);
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t r0 = warp * (32 * RPW) + lane;
@@ -958,15 +996,15 @@ static void launch_bits_w(ddf_ctx* ctx, const BitRows& br, const BitFmt& f, int6
   if (!pre && !post && (g_tune_fixed == 21 || g_tune_fixed == 22)) {      // A/B: other rows-per-lane counts
     constexpr int RA = W == 3 ? 8 : 4, RB = 2;
     if (g_tune_fixed == 21)
-      k_apply_bits_rows<W, WB, RA, false, false><<<(int)ceil_div64(ceil_div64(nrows, RA), 256), 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
+      k_apply_bits_rows<W, WB, RA, false, false><<<(int)ceil_div64(ceil_div64(nrows, RA), 256), 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
     else
-      k_apply_bits_rows<W, WB, RB, false, false><<<(int)ceil_div64(ceil_div64(nrows, RB), 256), 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
+      k_apply_bits_rows<W, WB, RB, false, false><<<(int)ceil_div64(ceil_div64(nrows, RB), 256), 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
     return;
   }
-  if (pre && post) k_apply_bits_rows<W, WB, RPW, true, true><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
-  else if (pre) k_apply_bits_rows<W, WB, RPW, true, false><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
-  else if (post) k_apply_bits_rows<W, WB, RPW, false, true><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
-  else k_apply_bits_rows<W, WB, RPW, false, false><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha);
+  if (pre && post) k_apply_bits_rows<W, WB, RPW, true, true><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
+  else if (pre) k_apply_bits_rows<W, WB, RPW, true, false><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
+  else if (post) k_apply_bits_rows<W, WB, RPW, false, true><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
+  else k_apply_bits_rows<W, WB, RPW, false, false><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
 }
 
 static int launch_bits(ddf_ctx* ctx, const BitRows& br, int W, int64_t nrows, int first_negative, const double* x,
@@ -1091,7 +1129,7 @@ static int launch_diag(ddf_ctx* ctx, const double* d, double s, const double* x,
   if (n == 0) return 0;
   int grid;
   DDF_CHECK(grid_for(ceil_div64(n, 4), 256, &grid));
-  k_apply_diag<<<grid, 256, 0, ctx->stream>>>(d, s, x, y, n);
+  k_apply_diag<<<grid, 256, 0, ctx->stream>>>(d, s, x, y, n, g_tune_diagpf);
   DDF_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1814,10 +1852,10 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
   if (m->bsell_state[R] == 3 && g_tune_fixed != 9) {
     const int grid = (int)ceil_div64(ceil_div64(f->nrows, 4), 256);
     const uint32_t* pp = m->bpair[R].p;
-    if (pre_d && post_d) k_apply_pairsign<true, true, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y);
-    else if (pre_d) k_apply_pairsign<true, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y);
-    else if (post_d) k_apply_pairsign<false, true, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y);
-    else k_apply_pairsign<false, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y);
+    if (pre_d && post_d) k_apply_pairsign<true, true, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);
+    else if (pre_d) k_apply_pairsign<true, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);
+    else if (post_d) k_apply_pairsign<false, true, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);
+    else k_apply_pairsign<false, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);
     DDF_LAUNCH_CHECK(f->ctx);
     return 0;
   }
@@ -1834,10 +1872,10 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
                        (!pre_d || ((uintptr_t)pre_d & 15) == 0);
 #define DDF_SELLUP(PRE_, POST_)                                                                                     \
   do {                                                                                                              \
-    if (stage && short_rows) k_apply_sellsign<PRE_, POST_, 4, true, true><<<grid, DDF_SELL_WIN, smem, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, cap); \
-    else if (stage) k_apply_sellsign<PRE_, POST_, 8, true, true><<<grid, DDF_SELL_WIN, smem, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, cap);            \
-    else if (short_rows) k_apply_sellsign<PRE_, POST_, 4, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1); \
-    else k_apply_sellsign<PRE_, POST_, 8, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1);            \
+    if (stage && short_rows) k_apply_sellsign<PRE_, POST_, 4, true, true><<<grid, DDF_SELL_WIN, smem, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, cap, g_tune_prefetch); \
+    else if (stage) k_apply_sellsign<PRE_, POST_, 8, true, true><<<grid, DDF_SELL_WIN, smem, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, cap, g_tune_prefetch);            \
+    else if (short_rows) k_apply_sellsign<PRE_, POST_, 4, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, 0, g_tune_prefetch); \
+    else k_apply_sellsign<PRE_, POST_, 8, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, 0, g_tune_prefetch);            \
   } while (0)
     if (pre_d && post_d) DDF_SELLUP(true, true);
     else if (pre_d) DDF_SELLUP(true, false);
@@ -1850,12 +1888,14 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
   if (m->bsell_state[R] == 1 && g_tune_fixed != 9) {
     const int grid = (int)ceil_div64(f->nrows, DDF_SELL_WIN);
     const SellBufs& sb = m->bsell[R];
-    // short rows (edges -> faces: ~5 entries): 4 gathers per round keep the kernel at 32 registers / full occupancy
+    // short rows (edges -> faces: ~5 entries): 4 gathers per round keep the kernel at 32 registers / full occupancy;
+    // the index words of up to 8 entries are fetched in ONE round trip (1.230 -> 1.136 ms at C4; tuning 28: 4 at a time)
     const bool short_rows = (int64_t)(R + 1) * m->n[R] < 8 * f->nrows && g_tune_fixed != 17;
 #define DDF_SELLSIGN(PRE_, POST_)                                                                                   \
   do {                                                                                                              \
-    if (short_rows) k_apply_sellsign<PRE_, POST_, 4><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y); \
-    else k_apply_sellsign<PRE_, POST_, 8><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y);            \
+    if (short_rows && g_tune_fixed == 28) k_apply_sellsign<PRE_, POST_, 4><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, nullptr, 0, 0, g_tune_prefetch); \
+    else if (short_rows) k_apply_sellsign<PRE_, POST_, 4, false, false, 8><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, nullptr, 0, 0, g_tune_prefetch); \
+    else k_apply_sellsign<PRE_, POST_, 8><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, nullptr, 0, 0, g_tune_prefetch);            \
   } while (0)
     if (pre_d && post_d) DDF_SELLSIGN(true, true);
     else if (pre_d) DDF_SELLSIGN(true, false);

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--fixed", default="0,1,2,3,4")
     ap.add_argument("--wave", default="0,1")
+    ap.add_argument("--prefetch", default="", help="L2 prefetch distances (blocks) to time the d_k applies with")
     args = ap.parse_args()
     ctx = ddf.Context(0)
     n = args.n
@@ -55,6 +56,17 @@ def main():
         out[f"fixed{var}"] = row
         print(f"fixed variant {var}: {row}", flush=True)
     ddf._lib.call("ddf_set_tuning", b"fixed", 0)
+    for pf in [int(v) for v in args.prefetch.split(",") if v]:
+        ddf._lib.call("ddf_set_tuning", b"prefetch", pf)
+        row = {}
+        for k in range(3):
+            ms = timeit(lambda k=k: d[k].apply(x[k], y[k]))
+            b = cnt[k + 1] * (4 * (k + 2) + 8) + 8 * cnt[k]
+            row[f"d{k}"] = (round(ms, 4), round(b / ms * 1e-6 / peak, 4))
+        for a, b_ in zip(ref, [yy.values[:: max(1, len(yy) // 100000)].copy() for yy in y]):
+            assert np.array_equal(a, b_), f"prefetch {pf} differs"
+        print(f"prefetch {pf}: {row}", flush=True)
+    ddf._lib.call("ddf_set_tuning", b"prefetch", 0)
 
     # boundary / dual derivative (row-CSR vs SELL-32): y = d_k^T-type applies
     dd = [ddf.deriv(ddf.Dl, k, m) for k in (1, 2, 3)]
