@@ -30,7 +30,6 @@ static int g_tune_packbits = 24;
 // blocks ahead a block prefetches index words into L2 (0 = off).  Measured at C4 (profiles/r01_tuning.md): any
 // distance from 148 to 2368 blocks gives the same gain; 4 x 148 keeps the request well ahead of the block scheduler.
 static int g_tune_prefetch = 592;
-static int g_tune_diagpf = 0;        // the same for the x and diagonal streams of k_apply_diag
 int ddf_laplace0_apply(ddf_mesh* m, const double* x, double* y);   // wave.cu
 
 enum OpKind { OPK_ZERO = 0, OPK_FIXED, OPK_CSRSIGN, OPK_DIAG, OPK_CSRF64, OPK_LAPLACE0, OPK_CHAIN, OPK_SUM };
@@ -346,12 +345,7 @@ k_apply_sellsign(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restric
 // array, read-once loads (L1 no-allocate), evict-first stores; the tail and unaligned views take the scalar path.
 __global__ void __launch_bounds__(256)
 k_apply_diag(const double* __restrict__ d, double sign_or_scale, const double* __restrict__ x, double* __restrict__ y,
-             int64_t n, int pf_blocks) {
-  if (pf_blocks && (threadIdx.x == 0 || threadIdx.x == 32)) {   // x and d of the block that runs pf_blocks later
-    const int64_t ip = ((int64_t)blockIdx.x + pf_blocks) * 1024;
-    const double* src = threadIdx.x == 0 ? x : d;
-    if (src && ip + 1024 <= n && ((uintptr_t)src & 15) == 0) bulk_prefetch_l2(src + ip, 8192);
-  }
+             int64_t n) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   if (i + 3 < n) {
@@ -423,14 +417,11 @@ k_apply_sellf64(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict
 }
 
 extern int g_tune_wave;   // wave.cu
-extern int g_tune_wavepf; // wave.cu
 extern int g_tune_asm;    // mesh.cu
 extern int g_tune_fixed;
 extern "C" int ddf_set_tuning(const char* key, int value) {
   if (!strcmp(key, "fixed")) g_tune_fixed = value;
   else if (!strcmp(key, "wave")) g_tune_wave = value;
-  else if (!strcmp(key, "diagpf")) g_tune_diagpf = value >= 0 ? value : 0;
-  else if (!strcmp(key, "wavepf")) g_tune_wavepf = value >= 0 && value < 8 ? value : 0;
   else if (!strcmp(key, "asm")) g_tune_asm = value;
   else if (!strcmp(key, "packbits")) g_tune_packbits = value >= 1 && value <= 24 ? value : 24;
   else if (!strcmp(key, "prefetch")) g_tune_prefetch = value >= 0 ? value : 0;
@@ -1129,7 +1120,7 @@ static int launch_diag(ddf_ctx* ctx, const double* d, double s, const double* x,
   if (n == 0) return 0;
   int grid;
   DDF_CHECK(grid_for(ceil_div64(n, 4), 256, &grid));
-  k_apply_diag<<<grid, 256, 0, ctx->stream>>>(d, s, x, y, n, g_tune_diagpf);
+  k_apply_diag<<<grid, 256, 0, ctx->stream>>>(d, s, x, y, n);
   DDF_LAUNCH_CHECK(ctx);
   return 0;
 }

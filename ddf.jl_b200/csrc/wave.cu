@@ -31,7 +31,6 @@ int ddf_mesh_require_star(ddf_mesh* m, int R);   // ops.cu
 int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n, double* out);   // core.cu
 
 int g_tune_wave = 0;
-int g_tune_wavepf = 0;          // iterations ahead the pipeline's producer prefetches a window's streams into L2 (0 = off, < PIPE_TD)
 // windows per pipeline group the builder tries first for short rows (2D meshes); 0 = SELL with 16-bit offsets
 #define DDF_STAGE_K_SHORT 2
 
@@ -42,7 +41,6 @@ struct PipeGeom {
   uint32_t o_ent, o_v, o_u, o_meta, stage_bytes;   // byte offsets inside a stage (x16): entries records, v, u, meta
   int nstages;
   int K;                                           // windows per group (= per stage)
-  int pf;                                          // producer's L2 prefetch distance in iterations (0 = off)
   int64_t nrows;
 };
 
@@ -59,7 +57,6 @@ static int pipe_geometry(const ddf_mesh* m, PipeGeom* g) {
   g->nstages = (int)(budget / g->stage_bytes);
   if (g->nstages > PIPE_MAX_STAGES) g->nstages = PIPE_MAX_STAGES;
   g->nrows = m->n[0];
-  g->pf = g_tune_wavepf;
   return g->nstages >= 2;
 }
 
@@ -488,27 +485,6 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tfull[td])), "r"(STAGE_TAB * 4) : "memory");
         bulk_g2s(tabS + td * STAGE_TAB, tab + (win + PIPE_TD * stride) * STAGE_TAB, STAGE_TAB * 4, &tfull[td], pol_stream);
-      }
-      if (g.pf > 0 && win + g.pf * stride < w1) {
-        // L2 prefetch of everything the window g.pf iterations ahead will stream (its run table is already in the
-        // ring): the stage's bulk copies then fill from L2 instead of HBM
-        const int64_t itp = it + g.pf, winp = win + g.pf * stride;
-        const int tp = (int)(itp % PIPE_TD);
-        stage_wait(&tfull[tp], (uint32_t)(itp / PIPE_TD) & 1u);
-        const uint32_t* wp = tabS + tp * STAGE_TAB;
-        const uint32_t nruns_p = wp[0], total_p = wp[1], e0_p = wp[2], nent_p = wp[3];
-        const uint32_t start_p = lane < STAGE_RMAX ? wp[4 + 2 * lane] : 0u, off_p = lane < STAGE_RMAX ? wp[5 + 2 * lane] : 0u;
-        const uint32_t end_p = lane + 1 < nruns_p ? wp[5 + 2 * (lane + 1)] : total_p;
-        const int64_t r0p = winp * g.K * DDF_SELL_WIN;
-        const uint32_t nrp = (uint32_t)min((int64_t)g.K * DDF_SELL_WIN, g.nrows - r0p);
-        const uint32_t vbp = ((nrp + 1u) & ~1u) * 8u;
-        if (lane < nruns_p && end_p > off_p) bulk_prefetch_l2(a.u + start_p, (end_p - off_p) * 8u);
-        if (lane == 31 && nent_p) bulk_prefetch_l2(packed + (size_t)e0_p * 10, nent_p * 10u);
-        if (lane == 30) bulk_prefetch_l2(meta + winp * g.K * STAGE_META, (uint32_t)g.K * STAGE_META);
-        if (lane == 29 && MODE != 0) {
-          bulk_prefetch_l2((MODE == 1 ? a.udot : (MODE == 3 ? a.rho : a.out0)) + r0p, vbp);
-          if (MODE == 2 || MODE == 3) bulk_prefetch_l2(a.u + r0p, vbp);
-        }
       }
       const int s = (int)(it % g.nstages);
       const uint32_t j = (uint32_t)(it / g.nstages);
