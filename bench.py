@@ -309,7 +309,7 @@ def run_b200(args):
 
     K, W = args.steps, args.warmup
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("DDF_BENCH_NO_SAMPLER"):     # (diagnostic switch: is the polling itself visible?)
         sampler.start()          # sampled from the warm-up to the end of the timed wave steps
     for _ in range(W):
         step()

@@ -935,6 +935,17 @@ def test_config4_3d_full_size(ddf, ctx):
     assert (d1 * (d0 * x)).norm(np.inf) == 0
     y = ddf.Fun(m, ddf.Pr, 1, rng.integers(-999, 999, m.nsimplices(1)).astype(np.float64))
     assert (d2 * (d1 * y)).norm(np.inf) == 0
+    # storage of the rows at this size: d0 prefix-packed, d1 one 4-byte word, d2 (top level) one 8-byte word per row;
+    # bit for bit the explicit-table kernels
+    assert [ddf.deriv_format(m, k) for k in range(3)] == ["packed", "bits32", "bits64"]
+    z = ddf.rand_fun(m, ddf.Pr, 2, seed=5)
+    got = [(d1 * y).values[::3].copy(), (d2 * z).values[::3].copy()]
+    ddf._lib.call("ddf_set_tuning", b"fixed", 18)
+    try:
+        assert np.array_equal((d1 * y).values[::3], got[0]) and np.array_equal((d2 * z).values[::3], got[1])
+    finally:
+        ddf._lib.call("ddf_set_tuning", b"fixed", 0)
+    del z, got
     # d0 of the coordinate function x: every edge difference is 0 or +-h exactly (h = 2^-8)
     cx = ddf.Fun(m, ddf.Pr, 0, np.ascontiguousarray(m.get_coords()[:, 0]))
     e = (d0 * cx).values

@@ -18,17 +18,32 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--fixed", default="0,1,2,3,4")
     ap.add_argument("--wave", default="0,1")
+    ap.add_argument("--torch", action="store_true", help="initialise torch's CUDA state first, like bench.py")
+    ap.add_argument("--rebuild", action="store_true", help="build the mesh twice (the first one is closed), like bench.py")
+    ap.add_argument("--extra", action="store_true", help="allocate bench.py's other work vectors too")
     ap.add_argument("--prefetch", default="", help="L2 prefetch distances (blocks) to time the d_k applies with")
     args = ap.parse_args()
+    if args.torch:
+        import torch
+        torch.cuda.set_device(0)
+        keep = torch.zeros(1 << 20, device="cuda")      # noqa: F841
     ctx = ddf.Context(0)
     n = args.n
     m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
+    if args.rebuild:
+        m.close()
+        m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
     m._geometry()
     cnt = [m.nsimplices(k) for k in range(4)]
+    extra = [ddf.hodge(ddf.Pr, k, m) for k in range(4)] if args.extra else None
     peak = 6539.9
     d = [ddf.deriv(ddf.Pr, k, m) for k in range(3)]
     x = [ddf.rand_fun(m, ddf.Pr, k, seed=k + 1) for k in range(3)]
+    if args.extra:
+        x.append(ddf.rand_fun(m, ddf.Pr, 3, seed=4))
     y = [ddf.Fun(m, ddf.Pr, k + 1) for k in range(3)]
+    if args.extra:
+        extra += [ddf.Fun(m, ddf.Dl, k) for k in range(4)]
     ref = None
     out = {}
 
