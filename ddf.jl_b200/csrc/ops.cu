@@ -436,6 +436,12 @@ extern "C" int ddf_set_tuning(const char* key, int value) {
 //   2: 1 + index loads allocate in L1
 //   3: 1 + warp-coalesced index loads transposed through shared memory
 //   4: 1 + persistent blocks with the next tile's indices prefetched
+// Storage / launch variants of the default paths (the value means one thing for y = d_k x and another for the
+// boundary / dual-derivative apply; an operator only looks at its own):
+//   y = d_k x:        18 explicit tables; 19 prefix-packed d0 with lane = consecutive rows; 20 prefix-packed instead
+//                     of bit-packed rows; 21 / 22 bit-packed rows with more / fewer rows per lane
+//   boundary apply:   9 row-CSR; 17 8 gathers per round on short rows; 20 plain SELL copy (no upper runs); 21 upper
+//                     runs read from global memory; 22 upper runs for short rows too; 28 index words 4 at a time
 int g_tune_fixed = 0;
 
 template <int W, int XM = 0>

@@ -66,8 +66,9 @@ int ddf_event_elapsed(ddf_ctx* ctx, int slot_a, int slot_b, double* ms);
 /* number of kernels the library has launched on this ctx since creation */
 int ddf_ctx_launch_count(ddf_ctx* ctx, int64_t* out);
 /* kernel-variant selector for profiling / A-B timing ("fixed", "wave", "asm"; "packbits" narrows the offset field of
- * the prefix-packed d_k rows so that tests can reach the explicit-table fallback); every variant returns
- * bit-identical results; 0 selects the default */
+ * the prefix-packed d_k rows -- and switches the bit-packed rows off -- so that tests can reach the explicit-table
+ * fallback; "prefetch" = how many blocks ahead a block asks L2 for the index words of a later block, default 592,
+ * 0 = off); every variant returns bit-identical results; for "fixed", "wave" and "asm" 0 selects the default */
 int ddf_set_tuning(const char* key, int value);
 /* overwrite a >L2-sized scratch buffer (bench hygiene between timed launches) */
 int ddf_flush_l2(ddf_ctx* ctx);

@@ -40,3 +40,25 @@ for _ in range(25):
         h[k].apply(x[k], z[k])
 print("after steps:", t(lambda: d2.apply(x2, y2)), t(lambda: d[2].apply(x[2], y[2])), flush=True)
 print("d0,d1:", t(lambda: d[0].apply(x[0], y[0])), t(lambda: d[1].apply(x[1], y[1])), flush=True)
+
+
+def hot():
+    for _ in range(10):
+        for k in range(3):
+            d[k].apply(x[k], y[k])
+        for k in range(4):
+            h[k].apply(x[k], z[k])
+
+
+# sustained-load A/B of the rows-per-lane variants (21: d1 RPW 8 / d2 RPW 4, 22: RPW 2) and of the prefetch distance
+for var in (0, 21, 22, 0):
+    ddf._lib.call("ddf_set_tuning", b"fixed", var)
+    hot()
+    print(f"sustained fixed={var}: d1 {t(lambda: d[1].apply(x[1], y[1]))} d2 {t(lambda: d[2].apply(x[2], y[2]))}", flush=True)
+ddf._lib.call("ddf_set_tuning", b"fixed", 0)
+for pf in (0, 148, 592, 2368):
+    ddf._lib.call("ddf_set_tuning", b"prefetch", pf)
+    hot()
+    print(f"sustained prefetch={pf}: d0 {t(lambda: d[0].apply(x[0], y[0]))} d1 {t(lambda: d[1].apply(x[1], y[1]))} "
+          f"d2 {t(lambda: d[2].apply(x[2], y[2]))}", flush=True)
+ddf._lib.call("ddf_set_tuning", b"prefetch", 592)
