@@ -8,10 +8,17 @@
 module DDFB200
 
 using DDF
+using Libdl
 using LinearAlgebra
 using SparseArrays
 
 const lib = "libddf_b200"
+# ccall needs a constant (symbol, library) pair; entry points chosen at run time go through dlsym
+const libhandle = Ref{Ptr{Cvoid}}(C_NULL)
+function fptr(sym::Symbol)
+    libhandle[] == C_NULL && (libhandle[] = Libdl.dlopen(lib))
+    return Libdl.dlsym(libhandle[], sym)
+end
 
 struct DDFB200Error <: Exception
     msg::String
@@ -79,11 +86,11 @@ end
 function DeviceVector(ctx::Ctx, x::Vector{Float64})
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ddf_vec_create, lib), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx.h, length(x), r))
-    v = DeviceVector(r[], length(x))
+    v = own(DeviceVector(r[], length(x)))
     GC.@preserve x check(ccall((:ddf_vec_upload, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), v.h, x))
-    finalizer(y -> ccall((:ddf_vec_destroy, lib), Cint, (Ptr{Cvoid},), y.h), v)
     return v
 end
+own(v::DeviceVector) = finalizer(y -> ccall((:ddf_vec_destroy, lib), Cint, (Ptr{Cvoid},), y.h), v)
 Base.size(v::DeviceVector) = (v.n,)
 function Base.Array(v::DeviceVector)
     x = Vector{Float64}(undef, v.n)
@@ -104,11 +111,11 @@ mutable struct DeviceOp <: AbstractMatrix{Float64}       # goes inside Op.values
 end
 function _op(sym::Symbol, m::DeviceManifold, P::PrimalDual, R::Int)
     r = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((sym, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Ptr{Cvoid}}), m.h, P == Pr ? 1 : 0, R, r))
-    op = DeviceOp(r[], m)
-    finalizer(x -> ccall((:ddf_op_destroy, lib), Cint, (Ptr{Cvoid},), x.h), op)
-    return op
+    check(ccall(fptr(sym), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Ptr{Cvoid}}), m.h, P == Pr ? 1 : 0, R, r))
+    return own(DeviceOp(r[], m))
 end
+# every handle the library hands out is released by a finalizer
+own(op::DeviceOp) = finalizer(x -> ccall((:ddf_op_destroy, lib), Cint, (Ptr{Cvoid},), x.h), op)
 function Base.size(A::DeviceOp)
     a = Ref{Int64}(0); b = Ref{Int64}(0)
     check(ccall((:ddf_op_shape, lib), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), A.h, a, b))
@@ -135,22 +142,22 @@ DDF.isboundary(::Val{Pr}, ::Val{R}, m::DeviceManifold{D}) where {R,D} =
 function Base.:*(A::DeviceOp, B::DeviceOp)                       # Ops.jl:228-232
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ddf_op_compose, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), A.h, B.h, r))
-    return DeviceOp(r[], A.m)
+    return own(DeviceOp(r[], A.m))
 end
 function Base.adjoint(A::DeviceOp)                               # Ops.jl:258-260
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ddf_op_adjoint, lib), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), A.h, r))
-    return DeviceOp(r[], A.m)
+    return own(DeviceOp(r[], A.m))
 end
 function Base.:*(a::Number, A::DeviceOp)                         # Ops.jl:198-200
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ddf_op_scale, lib), Cint, (Cdouble, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), Float64(a), A.h, r))
-    return DeviceOp(r[], A.m)
+    return own(DeviceOp(r[], A.m))
 end
 function Base.:+(A::DeviceOp, B::DeviceOp)                       # Ops.jl:186-190
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ddf_op_add, lib), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), A.h, 1.0, B.h, r))
-    return DeviceOp(r[], A.m)
+    return own(DeviceOp(r[], A.m))
 end
 Base.:-(A::DeviceOp, B::DeviceOp) = A + (-1.0) * B
 
@@ -159,7 +166,7 @@ function Base.:*(A::DeviceOp, x::DeviceVector)
     n, _ = size(A)
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ddf_vec_create, lib), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), A.m.ctx.h, n, r))
-    y = DeviceVector(r[], n)
+    y = own(DeviceVector(r[], n))
     check(ccall((:ddf_op_apply, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), A.h, x.h, y.h))
     return y
 end
@@ -187,9 +194,7 @@ end
 function assemble(A::DeviceOp)
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:ddf_op_assemble, lib), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), A.h, r))
-    op = DeviceOp(r[], A.m)
-    finalizer(x -> ccall((:ddf_op_destroy, lib), Cint, (Ptr{Cvoid},), x.h), op)
-    return op
+    return own(DeviceOp(r[], A.m))
 end
 
 # storage of the rows of deriv(Pr,k): :bits32 / :bits64 (one word of index differences per row), :packed
