@@ -408,6 +408,19 @@ def run_b200(args):
         poisson_step = {"ms_per_sweep": pj, "algorithmic_bytes": int(algp), "GBps": algp / pj * 1e-6,
                         "frac": algp / pj * 1e-6 / peak, "vertex_updates_per_s": cnt[0] / (pj * 1e-3)}
         del up_, rho_
+    # deriv(Val(Dl), Val(k)) = the boundary matrices as plain CSC (ManifoldOps.jl:40-47): y = d_k^dual x, rows = (k-1)-simplices.
+    # Bytes counted like SURVEY 8(d) counts d_k: int32 index per entry, row offset + y per row, x once.
+    dual = None
+    if N == 1 and not args.no_extras:
+        dual = {}
+        for k in (1, 2, 3):
+            A = ddf.deriv(ddf.Dl, k, mfd)
+            xd, yd = ddf.rand_fun(mfd, ddf.Dl, k, seed=k + 7), ddf.Fun(mfd, ddf.Dl, k - 1)
+            ms = time_op(lambda: A.apply(xd, yd), K)
+            b = (k + 1) * cnt[k] * 4 + cnt[k - 1] * 12 + cnt[k] * 8
+            dual[f"dual_d{k}"] = {"ms": ms, "rows": cnt[k - 1], "bytes": int(b), "GBps": b / ms * 1e-6,
+                                  "frac": b / ms * 1e-6 / peak}
+            del A, xd, yd
     # the reference's own integrator on the same mesh: fixed-step Tsit5 (wave.jl:134), 6 right-hand sides per step
     tsit5 = None
     if N == 1 and not args.no_extras:
@@ -532,7 +545,7 @@ def run_b200(args):
                          "format_bytes_per_launch": int(d1_format_bytes),
                          "format_achieved": d1_format_bytes / d1_ms * 1e-6,
                          "format_frac": d1_format_bytes / d1_ms * 1e-6 / peak},
-            "breakdown": breakdown, "wave": wave, "wave2d": wave2d, "poisson_step": poisson_step, "wave_tsit5": tsit5, "poisson2d": poisson2d,
+            "breakdown": breakdown, "wave": wave, "wave2d": wave2d, "poisson_step": poisson_step, "dual_deriv": dual, "wave_tsit5": tsit5, "poisson2d": poisson2d,
             "assembly_ms": asm_ms,
             # assembly of d_3, d_2, d_1 on the device from the tet table (bit-exact; no roofline target):
             # face tuples generated, sorted and ranked per second
