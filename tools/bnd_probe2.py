@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Boundary / dual-derivative apply on the rows of ~5 entries (rows = edges of a 3D mesh): A/B of the launch variants
-that are chosen per apply (ddf_set_tuning("fixed", v)) on ONE mesh.  Usage: python tools/bnd_probe2.py [n] [v,v,...] [prefetch,prefetch,...]"""
+that are chosen per apply (ddf_set_tuning("fixed", v)) on ONE mesh.  Usage: python tools/bnd_probe2.py [n] [v,v,...] [prefetch,prefetch,...] [reps]"""
 import os
 import sys
 
@@ -11,7 +11,7 @@ import ddf.jl_b200 as ddf  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 28, 0]
 prefetch = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
-reps = 20
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 ctx = ddf.Context(0)
 m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
 cnt = [m.nsimplices(k) for k in range(4)]

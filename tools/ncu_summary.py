@@ -40,6 +40,10 @@ def main():
                     g = to_gb(r[i], units[i])
                     traffic += g
                     cells.append(f"{g:.3f}")
+                elif short == "us":
+                    scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[i].lower().replace("second", "s").replace("usecond", "us"), 1.0)
+                    scale = {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}.get(units[i].lower(), scale)
+                    cells.append(f"{float(r[i].replace(',', '')) * scale:.1f}")
                 else:
                     try:
                         cells.append(f"{float(r[i].replace(',', '')):.1f}")
