@@ -195,10 +195,10 @@ __global__ void k_build_pairs(const uint32_t* __restrict__ rowptr, const uint32_
 }
 
 template <bool PRE, bool POST, int RPW>
-__global__ void __launch_bounds__(256)
-k_apply_pairsign(const uint32_t* __restrict__ pair, int64_t nrows, const double* __restrict__ x,
-                 const double* __restrict__ pre, const double* __restrict__ post, double alpha, double* __restrict__ y,
-                 int pf_blocks = 0) {
+__device__ __forceinline__ void
+pairsign_body(const uint32_t* __restrict__ pair, int64_t nrows, const double* __restrict__ x,
+              const double* __restrict__ pre, const double* __restrict__ post, double alpha, double* __restrict__ y,
+              int pf_blocks) {
   const uint64_t pol_keep = make_policy_evict_last();
   const uint64_t pol_stream = make_policy_evict_first();
   if (pf_blocks && threadIdx.x == 0) {       // pairs of the block that runs pf_blocks later: 256 * RPW rows, contiguous
@@ -239,6 +239,23 @@ k_apply_pairsign(const uint32_t* __restrict__ pair, int64_t nrows, const double*
     if (alpha != 1.0) a = __dmul_rn(alpha, a);
     st_hint_f64(y + r, a, pol_stream);
   }
+}
+
+template <bool PRE, bool POST, int RPW>
+__global__ void __launch_bounds__(256)
+k_apply_pairsign(const uint32_t* __restrict__ pair, int64_t nrows, const double* __restrict__ x,
+                 const double* __restrict__ pre, const double* __restrict__ post, double alpha, double* __restrict__ y,
+                 int pf_blocks = 0) {
+  pairsign_body<PRE, POST, RPW>(pair, nrows, x, pre, post, alpha, y, pf_blocks);
+}
+// The unfused apply capped at 32 registers (8 resident blocks per SM instead of 6): 0.652 -> 0.599 ms at C4, no spills.
+// (`__launch_bounds__(256, 1)` is NOT the same as `__launch_bounds__(256)`: with it ptxas spends more registers and
+// the kernel slows to 0.77 ms -- hence two wrappers instead of a template parameter.)
+template <int RPW>
+__global__ void __launch_bounds__(256, 8)
+k_apply_pairsign32(const uint32_t* __restrict__ pair, int64_t nrows, const double* __restrict__ x, double* __restrict__ y,
+                   int pf_blocks) {
+  pairsign_body<false, false, RPW>(pair, nrows, x, nullptr, nullptr, 1.0, y, pf_blocks);
 }
 
 // The same operator from the SELL-32 copy of the row-CSR (sell.cuh): coalesced index loads.
@@ -441,7 +458,7 @@ extern "C" int ddf_set_tuning(const char* key, int value) {
 //   y = d_k x:        18 explicit tables; 19 prefix-packed d0 with lane = consecutive rows; 20 prefix-packed instead
 //                     of bit-packed rows; 21 / 22 bit-packed rows with more / fewer rows per lane
 //   boundary apply:   9 row-CSR; 17 8 gathers per round on short rows; 20 plain SELL copy (no upper runs); 21 upper
-//                     runs read from global memory; 22 upper runs for short rows too; 28 index words 4 at a time
+//                     runs read from global memory; 22 upper runs for short rows too; 28 index words 4 at a time; 32 pair table with the 40-register build
 int g_tune_fixed = 0;
 
 template <int W, int XM = 0>
@@ -1854,7 +1871,8 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
     if (pre_d && post_d) k_apply_pairsign<true, true, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);
     else if (pre_d) k_apply_pairsign<true, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);
     else if (post_d) k_apply_pairsign<false, true, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);
-    else k_apply_pairsign<false, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);
+    else if (a == 1.0 && g_tune_fixed != 32) k_apply_pairsign32<4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, y, g_tune_prefetch);
+    else k_apply_pairsign<false, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);   // tuning 32: the 40-register build
     DDF_LAUNCH_CHECK(f->ctx);
     return 0;
   }
