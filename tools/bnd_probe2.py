@@ -39,4 +39,4 @@ for tune, pf in [(t, p) for t in variants for p in prefetch]:
             ref[k] = v
     print(f"fixed={tune} prefetch={pf}: {row}", flush=True)
 ddf._lib.call("ddf_set_tuning", b"fixed", 0)
-ddf._lib.call("ddf_set_tuning", b"prefetch", 0)
+ddf._lib.call("ddf_set_tuning", b"prefetch", 592)      # the library default

@@ -81,7 +81,7 @@ def main():
         for a, b_ in zip(ref, [yy.values[:: max(1, len(yy) // 100000)].copy() for yy in y]):
             assert np.array_equal(a, b_), f"prefetch {pf} differs"
         print(f"prefetch {pf}: {row}", flush=True)
-    ddf._lib.call("ddf_set_tuning", b"prefetch", 0)
+    ddf._lib.call("ddf_set_tuning", b"prefetch", 592)      # the library default
 
     # boundary / dual derivative (row-CSR vs SELL-32): y = d_k^T-type applies
     dd = [ddf.deriv(ddf.Dl, k, m) for k in (1, 2, 3)]
