@@ -10,7 +10,7 @@ import ddf.jl_b200 as ddf  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 28, 0]
-prefetch = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
+prefetch = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [592]
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 ctx = ddf.Context(0)
 m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
