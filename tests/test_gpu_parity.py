@@ -368,6 +368,24 @@ def test_geometry_parity(pairs, kind):
     assert np.all(dm.get_volumes(0) == 1) and np.all(dm.get_dualvolumes(om.D) == 1)
 
 
+def test_weighted_circumcentre_reference_notebook(ddf, ctx):
+    """tests/golden/hypercube_weights.json = the OUTPUT cells of the reference's src/hypercube-weights.nb: with the
+    notebook's weights (which enter its equation with a factor D, see tests/golden/make_hypercube_weights.py) the
+    weighted circumcentre of the Kuhn path simplex is its barycentre.  The device kernel on the same input, D = 2, 3."""
+    import json
+    from fractions import Fraction as F
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hypercube_weights.json")))
+    for D in (2, 3):
+        xs = np.array([[1.0 if d >= D - i else 0.0 for d in range(D)] for i in range(D + 1)])
+        k = g["solved"][str(D)]
+        w = D * np.array([0.0] + [float(F(*v)) for v in k["w"]] + [0.0])
+        dm = ddf.Manifold.from_simplices("path simplex", np.arange(D + 1, dtype=np.int64)[None, :], xs, w, ctx=ctx)
+        cc = dm.get_dualcoords(D)
+        want = np.array([float(F(*v)) for v in k["centre"]])
+        assert np.max(np.abs(cc.reshape(-1) - want)) <= RTOL, (D, cc, want)
+        dm.close()
+
+
 @pytest.mark.parametrize("kind", GEO_ZOO)
 def test_isboundary_bit_exact(pairs, kind):
     om, dm = pairs(kind)

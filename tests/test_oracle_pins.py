@@ -420,3 +420,70 @@ def test_two_triangle_known_answer():
             assert nz[cp[j] - 1:cp[j + 1] - 1].tolist() == col["signs"]
     assert o.apply_deriv(o.Pr, 0, m, np.array(g["x"])).tolist() == g["d0x"]
     assert np.allclose(o.calc_volumes(m, 2), g["area_per_triangle"], atol=1e-15)
+
+
+def test_regular_simplex_closed_forms():
+    """tests/golden/regular_simplex.json: volumes, circumcentric dual volumes, Hodge stars and laplace(Pr,0) of ONE
+    regular unit simplex in closed form (derived by hand in make_regular_simplex.py from the reference's definitions,
+    not from this oracle) -- an element-wise known answer for star_k and L beyond the reference's identities."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regular_simplex.json")))
+    for D in (2, 3):
+        m = o.simplex_manifold(D)
+        k = g[str(D)]
+        for R in range(D + 1):
+            assert np.allclose(o.calc_volumes(m, R), k["vol"][R], rtol=1e-14, atol=0), (D, R)
+            assert np.allclose(o.calc_dualvolumes(m, R), k["dualvol"][R], rtol=1e-13, atol=0), (D, R)
+            assert np.allclose(o.hodge_diag(o.Pr, R, m), k["hodge"][R], rtol=1e-13, atol=0), (D, R)
+        L = o.laplace(o.Pr, 0, m).toarray()
+        off = ~np.eye(D + 1, dtype=bool)
+        assert np.allclose(L[off], k["laplace_offdiag"], rtol=1e-13) and np.allclose(np.diag(L), k["laplace_diag"], rtol=1e-13)
+
+
+def test_weighted_circumcentre_reference_notebook():
+    """src/hypercube-weights.nb (the reference's own Mathematica derivation of the level weights, outputs stored in the
+    file; transcribed by tests/golden/make_hypercube_weights.py): weighted circumcentre and squared radius of the Kuhn
+    path simplex in D = 1..5 -- with the solved weights the centre is the barycentre (Out[14], [21], [28], [35]), and for
+    ARBITRARY weights it is the linear function of Out[12], [19], [26], [33].  Pins circumcentre() (Algorithms.jl:56-96)
+    against values the reference holds.  The notebook's `Total[(x - c)^2 - w]` subtracts w from every component, i.e.
+    its weights enter with a factor D (see the make script); the Julia code has no such factor, and the last block pins
+    what the CODE yields for the generator's table (ManifoldConstructors.jl:253-271), worked out by hand."""
+    import json
+    from fractions import Fraction as F
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hypercube_weights.json")))
+
+    def path_simplex(D):
+        return np.array([[1.0 if d >= D - i else 0.0 for d in range(D)] for i in range(D + 1)])
+
+    def power_radius2(xs, ws, c):
+        r2 = ((xs - c) ** 2).sum(axis=1) - ws
+        assert np.allclose(r2, r2[0], rtol=0, atol=1e-14)        # the same power distance from every vertex
+        return r2[0]
+    xs = path_simplex(1)
+    c = o.circumcentre(xs[None], np.zeros((1, 2)))[0]
+    assert np.allclose(c, 0.5) and abs(power_radius2(xs, np.zeros(2), c) - 0.25) < 1e-15
+    rng = np.random.default_rng(3)
+    for D in (2, 3, 4, 5):
+        xs = path_simplex(D)
+        k = g["solved"][str(D)]
+        wnb = np.array([0.0] + [float(F(*w)) for w in k["w"]] + [0.0])       # the notebook's weights ...
+        c = o.circumcentre(xs[None], (D * wnb)[None])[0]                     # ... enter its equation with a factor D
+        want = np.array([float(F(*v)) for v in k["centre"]])
+        assert np.allclose(c, want, rtol=0, atol=1e-15 * D), (D, c, want)
+        assert np.allclose(want, xs.mean(axis=0))                 # = the barycentre (Out[10], [17], [24], [31])
+        assert abs(power_radius2(xs, D * wnb, c) - float(F(*k["cr2"]))) < 1e-14, D
+        if D in (2, 3):                                           # the generator's table holds the same numbers
+            assert np.array_equal(wnb, np.array({2: [0.0, -1.0 / 6, 0.0], 3: [0.0, -1.0 / 6, -1.0 / 6, 0.0]}[D]))
+        # arbitrary weights: the general solution
+        M = np.array(g["general"][str(D)]["M"], dtype=float)
+        for _ in range(5):
+            w = rng.uniform(-0.3, 0.3, D - 1)
+            wnb = np.concatenate([[0.0], w, [0.0]])
+            c = o.circumcentre(xs[None], (D * wnb)[None])[0]
+            assert np.allclose(c, 0.5 * (1 + D * (M @ w)), rtol=0, atol=1e-14), (D, w)
+            cr2 = D / 4 * (1 + 2 * D * ((w ** 2).sum() - (w[:-1] * w[1:]).sum()))
+            assert abs(power_radius2(xs, D * wnb, c) - cr2) < 1e-13, (D, w)
+    # What the Julia CODE yields for the generator's D = 2 table (b_i = x_i.x_i - w_i, no factor D): subtracting the
+    # equations pairwise gives 1 - 2 c_2 = w_2 and 1 - 2 c_1 = -w_2, i.e. (5/12, 7/12) -- 1/12 off the barycentre
+    c = o.circumcentre(path_simplex(2)[None], np.array([[0.0, -1.0 / 6, 0.0]]))[0]
+    assert np.allclose(c, [5.0 / 12, 7.0 / 12], rtol=0, atol=1e-15)
