@@ -21,8 +21,11 @@ that touches this path (``tests/test_oracle_pins.py``): simplex counts, exact
 dd=0 / boundary-boundary=0, closed-form simplex volumes, volume sums,
 dual-volume sums, the hodge sign rule, |star' star - (+-1)| <= 10 eps,
 |delta delta| bound, weighted-circumcentre equidistance, the hand-written
-complexes of ``test/test-topologies.jl``.  Element-wise float values beyond
-those identities are UNPINNED (parity = "GPU == this restatement").
+complexes of ``test/test-topologies.jl``; and against the one set of computed
+values the reference stores, the weighted-circumcentre outputs of
+``src/hypercube-weights.nb`` (``tests/golden/hypercube_weights.json``).
+Element-wise float values beyond those are UNPINNED (parity = "GPU == this
+restatement"), apart from hand-derived closed forms on the regular simplex.
 
 Conventions: everything is 0-based internally; ``to_julia_csc`` converts to the
 reference's storage (1-based Int64 ``colptr``/``rowval``).
