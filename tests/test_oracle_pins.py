@@ -487,3 +487,28 @@ def test_weighted_circumcentre_reference_notebook():
     # equations pairwise gives 1 - 2 c_2 = w_2 and 1 - 2 c_1 = -w_2, i.e. (5/12, 7/12) -- 1/12 off the barycentre
     c = o.circumcentre(path_simplex(2)[None], np.array([[0.0, -1.0 / 6, 0.0]]))[0]
     assert np.allclose(c, [5.0 / 12, 7.0 / 12], rtol=0, atol=1e-15)
+
+
+def test_poisson_exact_solution_reference_notebook():
+    """examples/poisson.nb (the reference's Mathematica derivation, outputs stored in the file) holds the free-space
+    potentials of the Gaussian charge that examples/poisson.jl:93-122 hard-codes: Out[5] (D=1), Out[13] (D=2),
+    Out[20] (D=3) and their small-r series Out[6], Out[14].  The restated u_exact equals those closed forms."""
+    from scipy.special import erf, expi
+    sigma, x0 = 0.2, 0.1
+    rng = np.random.default_rng(9)
+    for D in (1, 2, 3):
+        x = rng.uniform(-0.5, 1.5, (200, D))
+        r = np.linalg.norm(x - x0, axis=1)
+        if D == 1:      # Out[5]: (-1 + e^(-r^2/2s^2)) s / sqrt(2 pi) + r/2 Erf[r / (sqrt 2 s)]
+            want = (-1 + np.exp(-r ** 2 / (2 * sigma ** 2))) * sigma / np.sqrt(2 * np.pi) + 0.5 * r * erf(r / (np.sqrt(2) * sigma))
+        elif D == 2:    # Out[13]: -(-EulerGamma + Ei(-r^2/2s^2) + Log 2 - 2 Log r + 2 Log s) / (4 pi)
+            want = -(-np.euler_gamma + expi(-r ** 2 / (2 * sigma ** 2)) + np.log(2) - 2 * np.log(r) + 2 * np.log(sigma)) / (4 * np.pi)
+        else:           # Out[20]: -Erf[r / (sqrt 2 s)] / (4 pi r)
+            want = -erf(r / (np.sqrt(2) * sigma)) / (4 * np.pi * r)
+        got = o.poisson_u_exact(x)
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-15), D
+    # the small-r branch of D = 2 (poisson.jl:103-105) against the series Out[14]: r^2/(8 pi s^2) - r^4/(64 pi s^4) + O(r^6)
+    x = np.full((1, 2), x0) + np.array([[3e-3, 0.0]])
+    r = 3e-3
+    ser = r ** 2 / (8 * np.pi * sigma ** 2) - r ** 4 / (64 * np.pi * sigma ** 4)
+    assert abs(o.poisson_u_exact(x)[0] - ser) < 1e-9 * abs(ser) + (r / sigma) ** 6
