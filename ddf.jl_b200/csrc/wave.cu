@@ -850,6 +850,10 @@ int ddf_step_launch(ddf_mesh* m, cudaStream_t stream, int kind, const double* u,
   return launch_rows<3>(m, stream, a);
 }
 
+#ifdef DDF_WAVEFRONT2
+#include "wavefront2.cuh"      // experimental two-step wavefront (never run on a device yet; not built by default)
+#endif
+
 int ddf_leapfrog_launch(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
                         int64_t row0, int64_t row1) {
   RowArgs a{};
@@ -872,7 +876,16 @@ extern "C" int ddf_wave_leapfrog(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt,
   DDF_CHECK(ddf_vec_settle(u));
   DDF_CHECK(ddf_vec_settle(v));
   if ((int64_t)m->utmp.n != nv) DDF_CHECK(m->utmp.alloc(m->ctx, nv));
-  for (int s = 0; s < nsteps; s++) {
+  int s = 0;
+#ifdef DDF_WAVEFRONT2
+  if (g_tune_wave & 65536) {       // experimental: two steps per launch (the state ends up in u again: no swap)
+    for (bool ran = true; ran && s + 1 < nsteps;) {
+      DDF_CHECK(launch_pipe2(m, m->ctx->stream, u->d.p, v->d.p, m->utmp.p, dt, &ran));
+      if (ran) s += 2;
+    }
+  }
+#endif
+  for (; s < nsteps; s++) {
     DDF_CHECK(ddf_leapfrog_launch(m, m->ctx->stream, u->d.p, v->d.p, m->utmp.p, dt, 0, nv));
     u->d.swap(m->utmp);          // O(1) ping-pong: the vector handle now owns the new state
   }

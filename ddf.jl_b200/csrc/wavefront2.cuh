@@ -1,0 +1,288 @@
+// wavefront2.cuh -- EXPERIMENTAL, NOT BUILT BY DEFAULT (compile wave.cu with -DDDF_WAVEFRONT2; build.sh does not).
+//
+// STATUS: written at the end of round 1 when no GPU minutes were left.  It compiles for sm_100a and its schedule is
+// model-checked on host threads (tests/test_wavefront_model.py), but it has NEVER RUN on a device.  Nothing in the
+// shipped library, the tests or the bench uses it.  DESIGN.md section 7 holds the plan it implements.
+//
+// Two fused leapfrog steps per launch with a wavefront through L2.  The persistent blocks of k_rows_pipe walk the
+// windows in order; here iteration `it` of a block runs the step-n task of window it*B + b and then the step-(n+1)
+// task of the window `lag` iterations back, so the entries of a window are read from HBM once (evict_last) and from
+// L2 the second time (evict_first).  u ping-pong: step n reads U0 = a.u and writes U1 = a.out1, step n+1 reads U1 and
+// writes U0; v = a.out0 is updated in place by both.  A step-(n+1) task of window w may be staged once every
+// step-n window <= w + reach has finished: blocks count their finished step-n tasks per iteration in `done[it]`
+// (threadfence + one atomic per task), the producer warp polls the counters it needs before it arms the stage.
+// With lag >= ceil(reach / B) + 1 a block only ever waits for iterations it has armed itself (no deadlock while all
+// blocks are co-resident: one block per SM, grid <= SM count).
+#pragma once
+
+struct Wave2Task {
+  int kind;        // 0 = step n, 1 = step n+1
+  int64_t it;      // the task's own iteration (window = w0 + b + it * stride)
+  int64_t win;
+};
+
+// The order in which ONE block runs its tasks; producer and consumers enumerate it identically.
+struct Wave2Enum {
+  int64_t it = 0;
+  int phase = 0;
+  int64_t nit, lag, w0, w1, stride, b;
+  __device__ Wave2Enum(int64_t nit_, int64_t lag_, int64_t w0_, int64_t w1_, int64_t stride_, int64_t b_)
+      : nit(nit_), lag(lag_), w0(w0_), w1(w1_), stride(stride_), b(b_) {}
+  __device__ bool next(Wave2Task& t) {
+    for (;;) {
+      if (it >= nit + lag) return false;
+      if (phase == 0) {
+        phase = 1;
+        const int64_t win = w0 + b + it * stride;
+        if (it < nit && win < w1) { t.kind = 0; t.it = it; t.win = win; return true; }
+      } else {
+        phase = 0;
+        const int64_t itb = it - lag;
+        it++;
+        if (itb >= 0) {
+          const int64_t win = w0 + b + itb * stride;
+          if (win < w1) { t.kind = 1; t.it = itb; t.win = win; return true; }
+        }
+      }
+    }
+  }
+};
+
+template <int NG>
+__global__ void __launch_bounds__(NG * PIPE_GROUP + 32, 1)
+k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __restrict__ packed,
+             const unsigned char* __restrict__ meta, int64_t w0, int64_t w1, PipeGeom g, int lag, int reachw,
+             uint32_t* __restrict__ done) {
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  __shared__ __align__(8) uint64_t full[PIPE_MAX_STAGES], empty[PIPE_MAX_STAGES], tfull[PIPE_TD];
+  __shared__ __align__(16) uint32_t tabS[PIPE_TD * STAGE_TAB];
+  __shared__ uint32_t issued[PIPE_MAX_STAGES];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid < PIPE_MAX_STAGES) issued[tid] = 0u;
+  if (tid == 0) {
+    for (int d = 0; d < PIPE_TD; d++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tfull[d])) : "memory");
+    for (int s = 0; s < g.nstages; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&empty[s])), "r"(PIPE_GROUP / 32) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t stride = gridDim.x;
+  const int64_t nit = (w1 - w0 + stride - 1) / stride;
+  double* const U0 = const_cast<double*>(a.u);       // step n input, step n+1 output
+  double* const U1 = a.out1;                         // step n output, step n+1 input
+  double* const V = a.out0;
+  if (warp == NG * PIPE_GROUP / 32) {
+    // ------------------------------------------------------------ producer warp
+    const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
+    Wave2Enum ahead(nit, lag, w0, w1, stride, blockIdx.x), cur(nit, lag, w0, w1, stride, blockIdx.x);
+    Wave2Task t;
+    if (lane == 0) {
+      for (int d = 0; d < PIPE_TD; d++) {
+        Wave2Task ta;
+        if (ahead.next(ta)) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tfull[d])), "r"(STAGE_TAB * 4) : "memory");
+          bulk_g2s(tabS + d * STAGE_TAB, tab + ta.win * STAGE_TAB, STAGE_TAB * 4, &tfull[d], pol_keep);
+        }
+      }
+    }
+    for (int64_t pit = 0; cur.next(t); pit++) {
+      const int td = (int)(pit % PIPE_TD);
+      stage_wait(&tfull[td], (uint32_t)(pit / PIPE_TD) & 1u);
+      const uint32_t* wt = tabS + td * STAGE_TAB;
+      const uint32_t nruns = wt[0], total = wt[1], e0 = wt[2], nent = wt[3];
+      const uint32_t start = lane < STAGE_RMAX ? wt[4 + 2 * lane] : 0u, off = lane < STAGE_RMAX ? wt[5 + 2 * lane] : 0u;
+      const uint32_t end = lane + 1 < nruns ? wt[5 + 2 * (lane + 1)] : total;
+      __syncwarp();
+      if (lane == 0) {                                                      // refill this table slot
+        Wave2Task ta;
+        if (ahead.next(ta)) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tfull[td])), "r"(STAGE_TAB * 4) : "memory");
+          bulk_g2s(tabS + td * STAGE_TAB, tab + ta.win * STAGE_TAB, STAGE_TAB * 4, &tfull[td], pol_keep);
+        }
+      }
+      if (t.kind == 1) {
+        // every step-n window <= win + reachw must be finished.  A block's consumer groups take the tasks alternately,
+        // so its step-n tasks may finish out of order -- but never by more than the ring holds (a task is armed only
+        // after the task nstages before it released its stage): the iteration that holds window win + reachw and the
+        // nstages - 1 before it are checked, everything older is implied.
+        int64_t need = ((t.win - w0) + reachw) / stride;
+        if (need > nit - 1) need = nit - 1;
+        if (lane == 0) {
+          for (int64_t q = need; q >= 0 && q > need - g.nstages; q--) {
+            const int64_t left = (w1 - w0) - q * stride;
+            const uint32_t active = (uint32_t)(left < stride ? left : stride);
+            uint32_t seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + q) : "memory");
+            } while (seen < active);
+          }
+        }
+        __syncwarp();
+        asm volatile("fence.proxy.async.global;" ::: "memory");             // generic-proxy stores of U1 / V -> our bulk reads
+      }
+      const int s = (int)(pit % g.nstages);
+      const uint32_t j = (uint32_t)(pit / g.nstages);
+      if (j > 0) stage_wait(&empty[s], (j - 1) & 1u);
+      unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
+      const int64_t r0 = t.win * g.K * DDF_SELL_WIN;
+      const uint32_t nr = (uint32_t)min((int64_t)g.K * DDF_SELL_WIN, g.nrows - r0);
+      const uint32_t vbytes = ((nr + 1u) & ~1u) * 8u;
+      const uint32_t mbytes = (uint32_t)g.K * STAGE_META;
+      const uint32_t tx = total * 8u + nent * 10u + mbytes + 2u * vbytes;
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(tx) : "memory");
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&issued[s])), "r"((uint32_t)pit + 1u) : "memory");
+      }
+      __syncwarp();
+      const double* uin = t.kind ? U1 : U0;
+      // first touch of a window's entries keeps them in L2 for the second step, the second touch lets them go
+      const uint64_t pol_ent = t.kind ? pol_stream : pol_keep;
+      if (lane < nruns) bulk_g2s(sb + (size_t)off * 8, uin + start, (end - off) * 8u, &full[s], pol_keep);
+      if (lane == 31 && nent) bulk_g2s(sb + g.o_ent, packed + (size_t)e0 * 10, nent * 10u, &full[s], pol_ent);
+      if (lane == 30) bulk_g2s(sb + g.o_meta, meta + t.win * g.K * STAGE_META, mbytes, &full[s], pol_ent);
+      if (lane == 29) {
+        bulk_g2s(sb + g.o_v, V + r0, vbytes, &full[s], pol_stream);
+        bulk_g2s(sb + g.o_u, uin + r0, vbytes, &full[s], pol_keep);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ consumer groups: group k takes tasks k, k + NG, ...
+    const uint32_t grp = tid / PIPE_GROUP;
+    const uint32_t gtid = tid % PIPE_GROUP, gwarp = gtid >> 5;
+    Wave2Enum cur(nit, lag, w0, w1, stride, blockIdx.x);
+    Wave2Task t;
+    for (int64_t pit = 0; cur.next(t); pit++) {
+      if ((uint32_t)(pit % NG) != grp) continue;
+      const int s = (int)(pit % g.nstages);
+      const uint32_t j = (uint32_t)(pit / g.nstages);
+      for (;;) {                          // the producer has armed stage s for THIS task
+        uint32_t seen;
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&issued[s])) : "memory");
+        if (seen >= (uint32_t)pit + 1u) break;
+      }
+      stage_wait(&full[s], j & 1u);
+      const unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
+      const double* stage = reinterpret_cast<const double*>(sb);
+      double* const uout = t.kind ? U0 : U1;
+      uint32_t rec = 0;
+      for (int kk = 0; kk < g.K; kk++) {
+        const unsigned char* metaS = sb + g.o_meta + kk * STAGE_META;
+        const uint32_t nentS = *reinterpret_cast<const uint32_t*>(metaS);
+        const double* valS = reinterpret_cast<const double*>(sb + g.o_ent + rec);
+        const uint16_t* slotS = reinterpret_cast<const uint16_t*>(sb + g.o_ent + rec + (size_t)nentS * 8);
+        rec += nentS * 10u;
+        const uint8_t* lenS = metaS + STAGE_META_HDR + DDF_SELL_WIN;
+        const uint32_t mylen = lenS[gtid];
+        const uint32_t p = (metaS + STAGE_META_HDR)[gtid];
+        const uint32_t part = reinterpret_cast<const uint32_t*>(metaS)[4 + gwarp];
+        const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
+        uint32_t e = part + lane, q = 0;
+        double acc = 0.0;
+        while (q < maxlen) {
+          const uint32_t nact = __popc(__ballot_sync(0xffffffffu, q < mylen));
+          const uint32_t qend = __shfl_sync(0xffffffffu, mylen, nact - 1);
+          if (lane < nact) {
+#pragma unroll 4
+            for (uint32_t k = q; k < qend; k++, e += nact) acc = __dadd_rn(acc, __dmul_rn(valS[e], stage[slotS[e]]));
+          }
+          q = qend;
+        }
+        const uint32_t pl = (uint32_t)kk * DDF_SELL_WIN + p;
+        const int64_t i = t.win * g.K * DDF_SELL_WIN + pl;
+        if (i >= a.row0 && i < a.row1) {
+          const double m = (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
+          const double ev = reinterpret_cast<const double*>(sb + g.o_v)[pl];
+          const double vn = __dadd_rn(ev, __dmul_rn(a.dt, __dmul_rn(m, acc)));
+          V[i] = vn;
+          uout[i] = __dadd_rn(reinterpret_cast<const double*>(sb + g.o_u)[pl], __dmul_rn(a.dt, __dmul_rn(m, vn)));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+      if (t.kind == 0) {
+        // publish: every thread's stores of this task are visible device-wide before the count moves
+        __threadfence();
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)grp), "r"(PIPE_GROUP) : "memory");
+        if (gtid == 0) atomicAdd(done + t.it, 1u);
+      }
+    }
+  }
+}
+
+// largest |column - row| of the assembled L rows (how far a row reaches), for the wavefront's dependency distance
+__global__ void k_row_reach(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr, int64_t nv,
+                            unsigned long long* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long r = 0;
+  if (i < nv)
+    for (uint32_t p = rowptr[i]; p < rowptr[i + 1]; p++) {
+      const long long d = (long long)nbr[p] - (long long)i;
+      const unsigned long long ad = (unsigned long long)(d < 0 ? -d : d);
+      r = ad > r ? ad : r;
+    }
+  r = __reduce_max_sync(0xffffffffu, (unsigned)r);      // local dimensions stay below 2^31
+  if ((threadIdx.x & 31) == 0 && r > *reinterpret_cast<volatile unsigned long long*>(out)) atomicMax(out, r);
+}
+
+// Two leapfrog steps in one launch: on return u (U0) holds the state after both steps, utmp the one in between.
+static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, double* utmp, double dt, bool* ran) {
+  *ran = false;
+  const StageBufs& sb = m->lstage;
+  if (!sb.ok || m->ctx->nranks > 1) return 0;
+  PipeGeom g;
+  if (!pipe_geometry(m, &g)) return 0;
+  const int64_t nv = m->n[0];
+  const int64_t gw = (int64_t)sb.K * DDF_SELL_WIN;
+  const int64_t g0 = 0, g1 = (nv + gw - 1) / gw;
+  const int grid = (int)std::min<int64_t>(m->ctx->sm_count, g1 - g0);
+  if (g1 - g0 < 4 * (int64_t)grid) return 0;                   // too few windows for a wavefront
+  static ddf_mesh* reach_mesh = nullptr;
+  static int64_t reach_rows = 0;
+  if (reach_mesh != m) {
+    DevBuf<unsigned long long> r;
+    DDF_CHECK(r.alloc(m->ctx, 1));
+    DDF_CUDA(cudaMemsetAsync(r.p, 0, 8, stream));
+    int gr;
+    DDF_CHECK(grid_for(nv, 256, &gr));
+    k_row_reach<<<gr, 256, 0, stream>>>(m->adj_ptr.p, m->adj_nbr.p, nv, r.p);
+    DDF_LAUNCH_CHECK(m->ctx);
+    unsigned long long h = 0;
+    DDF_CUDA(cudaMemcpyAsync(&h, r.p, 8, cudaMemcpyDeviceToHost, stream));
+    DDF_CUDA(cudaStreamSynchronize(stream));
+    reach_rows = (int64_t)h;
+    reach_mesh = m;
+  }
+  const int reachw = (int)(reach_rows / gw) + 2;
+  const int lag = (reachw + grid - 1) / grid + 1;
+  const int64_t nit = (g1 - g0 + grid - 1) / grid;
+  static uint32_t* done_p = nullptr;                            // one counter per iteration, zeroed per launch
+  static int64_t done_n = 0;                                    // (experimental: a process-lifetime scratch buffer)
+  if (done_n < nit) {
+    if (done_p) cudaFree(done_p);
+    DDF_CUDA(cudaMalloc((void**)&done_p, (size_t)nit * 4));
+    done_n = nit;
+  }
+  DDF_CUDA(cudaMemsetAsync(done_p, 0, (size_t)nit * 4, stream));
+  RowArgs a{};
+  a.u = u;
+  a.out0 = v;
+  a.out1 = utmp;
+  a.dt = dt;
+  a.row0 = 0;
+  a.row1 = nv;
+  const size_t smem_p = (size_t)g.nstages * g.stage_bytes;
+  static size_t attr_p = 0;
+  if (attr_p < smem_p) {
+    DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    attr_p = smem_p;
+  }
+  k_rows_pipe2<2><<<grid, 2 * PIPE_GROUP + 32, smem_p, stream>>>(a, sb.tab.p, sb.packed.p, sb.meta.p, g0, g1, g, lag,
+                                                                 reachw, done_p);
+  DDF_LAUNCH_CHECK(m->ctx);
+  *ran = true;
+  return 0;
+}
