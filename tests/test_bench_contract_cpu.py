@@ -35,3 +35,15 @@ def test_product_arm_needs_a_gpu():
     r = run("--steps", "1", "--warmup", "0", "--cells", "4", "--no-e2e", "--no-cpu", "--no-extras", "--no-wave2d")
     assert r.returncode != 0                       # fails loudly: libddf_b200 has no CPU path
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """The driver launches both arms the same way (torchrun for N > 1): rank 0 alone runs and prints the reference
+    line, the other ranks exit 0 without work."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--n-ref", "12"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1 and json.loads(lines[0])["impl"] == "reference"
