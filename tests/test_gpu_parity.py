@@ -818,6 +818,29 @@ def test_wave_pipeline_repeatable(ddf, ctx):
             ddf._lib.call("ddf_set_tuning", b"wave", 0)
 
 
+@pytest.mark.skipif(not os.environ.get("DDF_WAVEFRONT2"), reason="experimental two-step wavefront: build wave.cu with "
+                    "-DDDF_WAVEFRONT2 and set DDF_WAVEFRONT2=1 (csrc/wavefront2.cuh; not part of the default library)")
+def test_wavefront2_equals_single_steps(ddf, ctx):
+    """Two leapfrog steps per launch (wavefront through L2) against the one-step-per-launch default: same bits after an
+    even and an odd number of steps, repeatably.  Only meaningful with a library built with -DDDF_WAVEFRONT2 (otherwise
+    the tuning bit is ignored and the test would compare the default with itself)."""
+    n = 64                                           # 65^3 vertices = 1073 windows: enough for a wavefront on 148 SMs
+    m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
+    dt = ddf.wave_dt(m)
+    for steps in (6, 7):
+        ref_u, ref_v = ddf.sample(m, "wave"), ddf.Fun(m, ddf.Pr, 0)
+        ddf.wave_leapfrog(m, ref_u, ref_v, dt, steps)
+        for _ in range(3):
+            u, v = ddf.sample(m, "wave"), ddf.Fun(m, ddf.Pr, 0)
+            ddf._lib.call("ddf_set_tuning", b"wave", 65536)
+            try:
+                ddf.wave_leapfrog(m, u, v, dt, steps)
+            finally:
+                ddf._lib.call("ddf_set_tuning", b"wave", 0)
+            assert np.array_equal(u.values, ref_u.values) and np.array_equal(v.values, ref_v.values), steps
+    m.close()
+
+
 def test_wave_row_formats_2d(ddf, ctx):
     """2D mesh (7 entries per row): staged rows in groups of 2 windows per pipeline stage (default), staged with one
     window per stage (tuning 4096), SELL with 16-bit column offsets (16), with 32-bit indices (16|2048) and the CSR
