@@ -7,7 +7,9 @@ OUT="$HERE/../libddf_b200.so"
 OBJ="$HERE/_obj"
 mkdir -p "$OBJ"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -Xptxas -v"
+# DDF_EXTRA_FLAGS: extra nvcc flags for experiments, e.g. DDF_EXTRA_FLAGS=-DDDF_WAVEFRONT2 (delete _obj/wave.o first:
+# objects are only rebuilt when a source is newer).  Unset for the shipped library.
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -Xptxas -v ${DDF_EXTRA_FLAGS:-}"
 pids=()
 for f in core mesh geometry ops wave comm solve; do
   src="$HERE/$f.cu"; obj="$OBJ/$f.o"
