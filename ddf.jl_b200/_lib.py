@@ -37,6 +37,7 @@ SIGNATURES = {
     "ddf_ctx_destroy": [_P],
     "ddf_sync": [_P],
     "ddf_ctx_bytes_in_use": [_P, _i64p],
+    "ddf_ctx_trim": [_P],
     "ddf_timer_tic": [_P],
     "ddf_timer_toc": [_P, _f64p],
     "ddf_ctx_launch_count": [_P, _i64p],
@@ -44,6 +45,7 @@ SIGNATURES = {
     "ddf_event_elapsed": [_P, _int, _int, _f64p],
     "ddf_flush_l2": [_P],
     "ddf_set_tuning": [C.c_char_p, _int],
+    "ddf_ctx_set_tuning": [_P, C.c_char_p, _int],
     "ddf_mesh_create": [_P, _int, _int, _i64, _i64, _i64p, _i64p, _f64p, _f64p, _PP],
     "ddf_mesh_create_hypercube": [_P, _int, _i64p, _i64, _i64, _PP],
     "ddf_mesh_destroy": [_P],
@@ -76,6 +78,7 @@ SIGNATURES = {
     "ddf_vec_norm": [_P, _int, _f64p],
     "ddf_vec_dot": [_P, _P, _f64p],
     "ddf_vec_sum": [_P, _f64p],
+    "ddf_vec_wdot": [_P, _int, _int, _P, _P, _f64p],
     "ddf_op_boundary": [_P, _int, _int, _PP],
     "ddf_op_deriv": [_P, _int, _int, _PP],
     "ddf_op_hodge": [_P, _int, _int, _PP],
@@ -92,6 +95,7 @@ SIGNATURES = {
     "ddf_op_compose": [_P, _P, _PP],
     "ddf_op_add": [_P, _f64, _P, _PP],
     "ddf_op_scale": [_f64, _P, _PP],
+    "ddf_op_div": [_P, _f64, _PP],
     "ddf_op_adjoint": [_P, _PP],
     "ddf_op_apply": [_P, _P, _P],
     "ddf_op_assemble": [_P, _PP],

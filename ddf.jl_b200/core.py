@@ -51,6 +51,10 @@ class Context:
         call("ddf_ctx_bytes_in_use", self._h, C.byref(out))
         return out.value
 
+    def trim(self):
+        """Synchronise and hand the library's cached device memory back to the driver."""
+        call("ddf_ctx_trim", self._h)
+
     def launch_count(self) -> int:
         out = C.c_int64()
         call("ddf_ctx_launch_count", self._h, C.byref(out))
@@ -127,6 +131,10 @@ class Manifold:
         # options of the outer constructor (Manifolds.jl:321-323)
         self.dualkind = "CircumcentricDuals"
         self.use_weighted_duals = True
+        # Ops hold raw pointers into this mesh's device tables (diagonals, boundary tables): count the live ones so
+        # that close() cannot leave them dangling; Fun / Op also keep `self` alive through their .manifold reference
+        self._live_ops = 0
+        self._closing = False
 
     @classmethod
     def from_simplices(cls, name: str, simplices: np.ndarray, coords: np.ndarray,
@@ -229,9 +237,20 @@ class Manifold:
         call("ddf_mesh_set_halo", self._h, int(plane), int(ghost_lo), int(ghost_hi))
 
     def close(self):
-        if self._h:
+        """Release the device tables.  Operators built on this manifold borrow its tables, so while any of them is
+        alive the release is deferred to the moment the last one is dropped (Op.__del__)."""
+        self._closing = True
+        if self._h and self._live_ops <= 0:
             _lib.load().ddf_mesh_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self._h and _lib._lib is not None and self.ctx._h:
+                _lib._lib.ddf_mesh_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 class Fun:
@@ -328,9 +347,19 @@ class Fun:
         call("ddf_vec_norm", self._h, kind, C.byref(out))
         return out.value
 
-    def dot(self, g) -> float:
+    def vdot(self, g) -> float:
+        """Plain Euclidean dot of the value vectors, `dot(f.values, g.values)` (no weights)."""
         out = C.c_double()
         call("ddf_vec_dot", self._h, g._h, C.byref(out))
+        return out.value
+
+    def dot(self, g) -> float:
+        """dot(f, g) of the reference (ManifoldOps.jl:154-164): weighted by 1 ./ vol_D for Fun{D,Pr,D} and by
+        1 ./ dualvol_0 for Fun{D,Dl,0}; the reference defines no other method, so other (P, R) raise."""
+        self._check(g)
+        self.manifold._geometry()
+        out = C.c_double()
+        call("ddf_vec_wdot", self.manifold._h, _P(self.P), self.R, self._h, g._h, C.byref(out))
         return out.value
 
     def sum(self) -> float:
@@ -380,6 +409,7 @@ class Op:
         self.manifold = manifold
         self.P1, self.R1, self.P2, self.R2 = bool(P1), int(R1), bool(P2), int(R2)
         self._h = handle
+        manifold._live_ops += 1
 
     @property
     def shape(self):
@@ -415,7 +445,8 @@ class Op:
         return self._new("ddf_op_scale", float(a), self._h)
 
     def __truediv__(self, a):
-        return self._new("ddf_op_scale", 1.0 / float(a), self._h)
+        # A / a divides the assembled values (Ops.jl:210-212): not the same bits as (1/a) * A unless 1/a is exact
+        return self._new("ddf_op_div", self._h, float(a))
 
     def __neg__(self):
         return self._new("ddf_op_scale", -1.0, self._h)
@@ -470,6 +501,10 @@ class Op:
             if self._h and _lib._lib is not None:
                 _lib._lib.ddf_op_destroy(self._h)
                 self._h = None
+                m = self.manifold
+                m._live_ops -= 1
+                if m._closing and m._live_ops <= 0:
+                    m.close()
         except Exception:
             pass
 

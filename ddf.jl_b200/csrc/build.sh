@@ -7,13 +7,13 @@ OUT="$HERE/../libddf_b200.so"
 OBJ="$HERE/_obj"
 mkdir -p "$OBJ"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-# DDF_EXTRA_FLAGS: extra nvcc flags for experiments, e.g. DDF_EXTRA_FLAGS=-DDDF_WAVEFRONT2 (delete _obj/wave.o first:
+# DDF_EXTRA_FLAGS: extra nvcc flags for experiments, e.g. DDF_EXTRA_FLAGS=-DDDF_PIPE_TRACE (delete _obj/wave.o first:
 # objects are only rebuilt when a source is newer).  Unset for the shipped library.
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -Xptxas -v ${DDF_EXTRA_FLAGS:-}"
 pids=()
 for f in core mesh geometry ops wave comm solve; do
   src="$HERE/$f.cu"; obj="$OBJ/$f.o"
-  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/common.cuh" -nt "$obj" ] || [ "$HERE/mesh.cuh" -nt "$obj" ] || [ "$HERE/sell.cuh" -nt "$obj" ] || [ "$HERE/stage.cuh" -nt "$obj" ] || [ "$HERE/../../include/ddf_b200.h" -nt "$obj" ]; then
+  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/common.cuh" -nt "$obj" ] || [ "$HERE/mesh.cuh" -nt "$obj" ] || [ "$HERE/sell.cuh" -nt "$obj" ] || [ "$HERE/stage.cuh" -nt "$obj" ] || [ "$HERE/wavefront2.cuh" -nt "$obj" ] || [ "$HERE/../../include/ddf_b200.h" -nt "$obj" ]; then
     ( $NVCC $FLAGS -c "$src" -o "$obj" > "$OBJ/$f.log" 2>&1 || { cat "$OBJ/$f.log"; exit 1; } ) &
     pids+=($!)
   fi

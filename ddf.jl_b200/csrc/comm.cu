@@ -20,7 +20,6 @@
 int ddf_step_launch(ddf_mesh* m, cudaStream_t stream, int kind, const double* u, double* aux, double* unew, double coef,
                     int64_t row0, int64_t row1, double* peer_lo, double* peer_hi, int64_t plane);           // wave.cu
 int ddf_mesh_require_dinv(ddf_mesh* m);                                                                      // wave.cu
-extern int g_tune_wave;
 
 struct NcclApi {
   void* handle = nullptr;
@@ -255,7 +254,8 @@ void ddf_halo_release(ddf_mesh* m) {
 }
 
 // first distributed step of a mesh: allocate the arena, exchange its handle with both neighbours, map theirs
-static int halo_handshake(ddf_mesh* m, int* usable) {
+static int halo_handshake_local(ddf_mesh* m, int* ok_out) {
+  *ok_out = 0;
   ddf_ctx* ctx = m->ctx;
   ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
   const int64_t P = m->halo_plane;
@@ -265,6 +265,7 @@ static int halo_handshake(ddf_mesh* m, int* usable) {
   // IPC handle maps exactly this arena at offset 0
   const size_t need = 256 + 4 * (size_t)P * sizeof(double);
   const size_t bytes = (need + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+  hp->arena.plain = true;                 // cudaMalloc: pool memory cannot be exported with cudaIpcGetMemHandle
   DDF_CHECK(hp->arena.alloc(ctx, bytes));
   DDF_CUDA(cudaMemsetAsync(hp->arena.p, 0, 256, ctx->stream));
   const unsigned long long magic = 0xDDF0B200ull * 1315423911ull + (unsigned long long)ctx->rank;
@@ -305,11 +306,23 @@ static int halo_handshake(ddf_mesh* m, int* usable) {
   };
   if (m->halo_lo > 0) map(lo, &hp->lo_base);
   if (m->halo_hi > 0 && ok) map(hi, &hp->hi_base);
+  *ok_out = ok;
+  return 0;
+}
+
+// Every rank reaches the agreeing all-reduce, also the one whose local part failed on the host (a CUDA / NCCL error,
+// an allocation that did not fit): its neighbours would otherwise wait in that all-reduce for ever.  A local failure
+// counts as "peer memory unusable" and the step falls back to ncclSend/ncclRecv on all ranks.
+static int halo_handshake(ddf_mesh* m, int* usable) {
+  int ok = 0;
+  const int rc = halo_handshake_local(m, &ok);
+  if (rc != 0) { ok = 0; cudaGetLastError(); }
   double agreed = ok ? 1.0 : 0.0;
-  DDF_CHECK(ddf_comm_allreduce(ctx, &agreed, 2));       // min over ranks
+  DDF_CHECK(ddf_comm_allreduce(m->ctx, &agreed, 2));    // min over ranks
   *usable = agreed > 0.5;
   return 0;
 }
+
 
 // kind 0: leapfrog (aux = v, coef = dt); kind 1: Poisson relaxation sweep (aux = rho, coef = theta)
 static int steps_dist_p2p(ddf_mesh* m, int kind, ddf_vec* u, ddf_vec* v, double dt, int nsteps) {
@@ -350,6 +363,10 @@ static int steps_dist_p2p(ddf_mesh* m, int kind, ddf_vec* u, ddf_vec* v, double 
       flags, has_lo ? k : 0ull, has_hi ? k : 0ull, has_lo ? HaloP2P::landing(hp->arena.p, 0, (int)(k & 1), P) : nullptr,
       u->d.p + own_lo - P, has_hi ? HaloP2P::landing(hp->arena.p, 1, (int)(k & 1), P) : nullptr, u->d.p + own_hi, P);
   DDF_LAUNCH_CHECK(ctx);
+  // a wait that timed out inside THIS call left stale ghost planes behind: report it now, not in the next call
+  DDF_CUDA(cudaMemcpyAsync(&err, flags + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (err) DDF_FAIL("halo: timed out (20 s) waiting for a neighbour's step flag; the ghost planes are stale");
   return 0;
 }
 
@@ -564,7 +581,7 @@ static int steps_dist(ddf_mesh* m, int kind, ddf_vec* u, ddf_vec* v, double dt, 
   const int64_t own_lo = m->halo_lo * P, own_hi = nv - m->halo_hi * P;
   if (nsteps <= 0) return 0;
   // fused peer-memory halo (default when every rank can map its neighbours; tuning bit 1024 forces NCCL)
-  if (ctx->nranks > 1 && !(g_tune_wave & 1024)) {
+  if (ctx->nranks > 1 && !(ctx->tune.wave & 1024)) {
     if (m->halo_p2p_state == 0) {
       int usable = 0;
       DDF_CHECK(halo_handshake(m, &usable));

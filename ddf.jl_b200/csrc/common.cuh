@@ -54,8 +54,20 @@ void ddf_set_error(const char* fmt, ...);
     return 1;                                              \
   }
 
+// kernel-variant selectors (ddf_set_tuning / ddf_ctx_set_tuning): per context, so that distinct contexts can be
+// driven from distinct threads; every variant returns bit-identical results
+struct DdfTune {
+  int fixed = 0;       // storage / launch variant of the d_k and boundary applies (ops.cu)
+  int wave = 0;        // row-kernel variant of the fused steps (wave.cu), bit 1024: NCCL halo (comm.cu)
+  int asm_path = 0;    // 1: radix-sort assembly instead of bucket ranking (mesh.cu)
+  int packbits = 24;   // offset bits of the prefix-packed rows (tests narrow it to reach the explicit tables)
+  int prefetch = 592;  // blocks ahead a block asks L2 for the index words of a later block (0 = off)
+};
+
 struct ddf_ctx {
   int device = -1;
+  DdfTune tune;
+  void* asm_work = nullptr;          // workspace of the ddf_mesh_assemble in flight on this ctx (mesh.cu)
   int sm_count = 0;
   cudaStream_t stream = nullptr;     // compute stream
   cudaStream_t comm_stream = nullptr;  // halo / NCCL stream
@@ -75,8 +87,8 @@ struct ddf_ctx {
   int nranks = 1, rank = 0;
 };
 
-int ddf_dev_alloc(ddf_ctx* ctx, void** p, size_t bytes);
-void ddf_dev_free(ddf_ctx* ctx, void* p, size_t bytes);
+int ddf_dev_alloc(ddf_ctx* ctx, void** p, size_t bytes, bool plain = false);
+void ddf_dev_free(ddf_ctx* ctx, void* p, size_t bytes, bool plain = false);
 
 // RAII-ish device buffer tied to a ctx (not thread safe; one ctx per thread)
 template <typename T>
@@ -84,6 +96,7 @@ struct DevBuf {
   ddf_ctx* ctx = nullptr;
   T* p = nullptr;
   size_t n = 0;
+  bool plain = false;        // cudaMalloc instead of the stream-ordered pool (memory exported through CUDA IPC)
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -93,15 +106,15 @@ struct DevBuf {
     ctx = c;
     n = count;
     if (count == 0) { p = nullptr; return 0; }
-    return ddf_dev_alloc(c, (void**)&p, count * sizeof(T));
+    return ddf_dev_alloc(c, (void**)&p, count * sizeof(T), plain);
   }
   void release() {
-    if (p) ddf_dev_free(ctx, p, n * sizeof(T));
+    if (p) ddf_dev_free(ctx, p, n * sizeof(T), plain);
     p = nullptr;
     n = 0;
   }
   void swap(DevBuf& o) {
-    std::swap(ctx, o.ctx); std::swap(p, o.p); std::swap(n, o.n);
+    std::swap(ctx, o.ctx); std::swap(p, o.p); std::swap(n, o.n); std::swap(plain, o.plain);
   }
   size_t bytes() const { return n * sizeof(T); }
 };

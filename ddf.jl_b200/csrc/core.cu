@@ -5,7 +5,34 @@
 #include "common.cuh"
 #include "mesh.cuh"
 
+#include <algorithm>
+#include <mutex>
+
 static thread_local char g_err[1024] = "";
+
+// Tuning selectors live in the context (DdfTune).  ddf_set_tuning -- the process-wide convenience the probes and
+// tests use -- writes the defaults new contexts start from and every live context, under a lock; a thread that
+// drives its own context and wants its own variant calls ddf_ctx_set_tuning.
+static std::mutex g_ctx_mu;
+static std::vector<ddf_ctx*> g_ctxs;
+static DdfTune g_tune_default;
+
+static int tune_set(DdfTune& t, const char* key, int value) {
+  if (!strcmp(key, "fixed")) t.fixed = value;
+  else if (!strcmp(key, "wave")) t.wave = value;
+  else if (!strcmp(key, "asm")) t.asm_path = value;
+  else if (!strcmp(key, "packbits")) t.packbits = value >= 1 && value <= 24 ? value : 24;
+  else if (!strcmp(key, "prefetch")) t.prefetch = value >= 0 ? value : 0;
+  else DDF_FAIL("set_tuning: unknown key %s", key);
+  return 0;
+}
+extern "C" int ddf_set_tuning(const char* key, int value) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  DDF_CHECK(tune_set(g_tune_default, key, value));
+  for (ddf_ctx* c : g_ctxs) tune_set(c->tune, key, value);
+  return 0;
+}
+extern "C" int ddf_ctx_set_tuning(ddf_ctx* ctx, const char* key, int value) { return tune_set(ctx->tune, key, value); }
 
 void ddf_set_error(const char* fmt, ...) {
   va_list ap;
@@ -17,14 +44,27 @@ void ddf_set_error(const char* fmt, ...) {
 extern "C" const char* ddf_last_error(void) { return g_err; }
 extern "C" int ddf_version(void) { return 100; }
 
-int ddf_dev_alloc(ddf_ctx* ctx, void** p, size_t bytes) {
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync / cudaFreeAsync on the compute stream)
+// with an unlimited release threshold: a freed table goes back to the pool, not to the driver, so building and
+// dropping multi-GB tables (assembly workspace, operator storages, cochains) costs no cudaMalloc / cudaFree round
+// trip -- and cudaFree's implicit device synchronisation is gone.  Buffers are used on the library's other streams
+// only behind event dependencies on the compute stream, and every destroy path synchronises before it frees.
+// `plain` = cudaMalloc (memory that is exported through CUDA IPC must not come from a pool).
+int ddf_dev_alloc(ddf_ctx* ctx, void** p, size_t bytes, bool plain) {
   *p = nullptr;
   if (bytes == 0) return 0;
   bytes = (bytes + 15) & ~(size_t)15;      // 16-byte TMA granules may read the pad element of an odd-length vector
-  cudaError_t e = cudaMalloc(p, bytes);
+  cudaError_t e = plain ? cudaMalloc(p, bytes) : cudaMallocAsync(p, bytes, ctx->stream);
+  if (e != cudaSuccess && !plain) {        // out of memory with cached blocks in the pool: give them back and retry
+    cudaGetLastError();
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    e = cudaMallocAsync(p, bytes, ctx->stream);
+  }
   if (e != cudaSuccess) {
     cudaGetLastError();
-    ddf_set_error("cudaMalloc(%zu bytes) failed: %s (in use: %lld bytes)", bytes,
+    ddf_set_error("device allocation of %zu bytes failed: %s (in use: %lld bytes)", bytes,
                   cudaGetErrorString(e), (long long)ctx->bytes_in_use);
     return 1;
   }
@@ -32,10 +72,21 @@ int ddf_dev_alloc(ddf_ctx* ctx, void** p, size_t bytes) {
   return 0;
 }
 
-void ddf_dev_free(ddf_ctx* ctx, void* p, size_t bytes) {
+void ddf_dev_free(ddf_ctx* ctx, void* p, size_t bytes, bool plain) {
   if (!p) return;
-  cudaFree(p);
+  if (plain || !ctx) cudaFree(p);
+  else cudaFreeAsync(p, ctx->stream);
   if (ctx) ctx->bytes_in_use -= (int64_t)((bytes + 15) & ~(size_t)15);
+}
+
+// give the cached blocks of the pool back to the driver (e.g. before another allocator in the process needs them)
+extern "C" int ddf_ctx_trim(ddf_ctx* c) {
+  DDF_CUDA(cudaSetDevice(c->device));
+  DDF_CHECK(ddf_sync(c));
+  cudaMemPool_t pool;
+  DDF_CUDA(cudaDeviceGetDefaultMemPool(&pool, c->device));
+  DDF_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return 0;
 }
 
 extern "C" int ddf_ctx_create(int device, ddf_ctx** out) {
@@ -55,6 +106,12 @@ extern "C" int ddf_ctx_create(int device, ddf_ctx** out) {
     DDF_FAIL("device %d is sm_%d%d; libddf_b200 is built for sm_100a only (no fallback)", device,
              prop.major, prop.minor);
   DDF_CUDA(cudaSetDevice(device));
+  {
+    cudaMemPool_t pool;
+    DDF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;            // freed blocks stay cached in the pool
+    DDF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   ddf_ctx* c = new ddf_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
@@ -68,6 +125,11 @@ extern "C" int ddf_ctx_create(int device, ddf_ctx** out) {
   DDF_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
   DDF_CHECK(ddf_dev_alloc(c, (void**)&c->red_dev, 4096 * sizeof(double)));
   DDF_CUDA(cudaMallocHost((void**)&c->red_host, 4096 * sizeof(double)));
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    c->tune = g_tune_default;
+    g_ctxs.push_back(c);
+  }
   *out = c;
   return 0;
   DDF_TRY_END
@@ -75,11 +137,16 @@ extern "C" int ddf_ctx_create(int device, ddf_ctx** out) {
 
 extern "C" int ddf_ctx_destroy(ddf_ctx* c) {
   if (!c) return 0;
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    g_ctxs.erase(std::remove(g_ctxs.begin(), g_ctxs.end(), c), g_ctxs.end());
+  }
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   ddf_comm_destroy(c);
   if (c->flush_buf) ddf_dev_free(c, c->flush_buf, c->flush_bytes);
   ddf_dev_free(c, c->red_dev, 4096 * sizeof(double));
+  cudaStreamSynchronize(c->stream);          // the stream-ordered frees above
   cudaFreeHost(c->red_host);
   cudaEventDestroy(c->ev_tic);
   cudaEventDestroy(c->ev_toc);
@@ -429,10 +496,11 @@ extern "C" int ddf_vec_rand(ddf_vec* v, uint64_t seed) {
 // ------------------------------------------------------------------ reductions
 // Two-stage deterministic reduction: fixed grid, each block reduces a contiguous
 // chunk in a fixed order, the (<= 1024) partials are combined on the host in
-// index order.  mode: 0 sum(x), 1 sum|x|, 2 sum x^2, 3 max|x|, 4 sum x*y, 5 min(x)
+// index order.  mode: 0 sum(x), 1 sum|x|, 2 sum x^2, 3 max|x|, 4 sum x*y, 5 min(x),
+// 6 sum (x * (1/w)) * y  (the weighted inner product of ManifoldOps.jl:154-164: dot(f, Diagonal(1 ./ w), g))
 template <int MODE>
 __global__ void k_reduce(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
-                         double* __restrict__ partial) {
+                         double* __restrict__ partial, const double* __restrict__ wgt = nullptr) {
   __shared__ double sm[32];
   double acc = (MODE == 5) ? INFINITY : 0.0;
   int64_t per = (n + gridDim.x - 1) / gridDim.x;
@@ -445,6 +513,7 @@ __global__ void k_reduce(const double* __restrict__ x, const double* __restrict_
     else if (MODE == 2) acc += v * v;
     else if (MODE == 3) acc = fmax(acc, fabs(v));
     else if (MODE == 4) acc += v * y[i];
+    else if (MODE == 6) acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(v, __ddiv_rn(1.0, wgt[i])), y[i]));
     else acc = fmin(acc, v);
   }
   for (int off = 16; off > 0; off >>= 1) {
@@ -469,7 +538,7 @@ __global__ void k_reduce(const double* __restrict__ x, const double* __restrict_
   }
 }
 
-int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n, double* out) {
+static int reduce_impl(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n, double* out, const double* w) {
   if (n == 0) { *out = (mode == 5) ? INFINITY : 0.0; return 0; }
   int grid = (int)(ceil_div64(n, 4096) < 1024 ? ceil_div64(n, 4096) : 1024);
   switch (mode) {
@@ -478,6 +547,7 @@ int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n
     case 2: k_reduce<2><<<grid, 256, 0, c->stream>>>(x, y, n, c->red_dev); break;
     case 3: k_reduce<3><<<grid, 256, 0, c->stream>>>(x, y, n, c->red_dev); break;
     case 4: k_reduce<4><<<grid, 256, 0, c->stream>>>(x, y, n, c->red_dev); break;
+    case 6: k_reduce<6><<<grid, 256, 0, c->stream>>>(x, y, n, c->red_dev, w); break;
     default: k_reduce<5><<<grid, 256, 0, c->stream>>>(x, y, n, c->red_dev); break;
   }
   DDF_LAUNCH_CHECK(c);
@@ -491,6 +561,10 @@ int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n
   }
   *out = acc;
   return 0;
+}
+
+int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n, double* out) {
+  return reduce_impl(c, mode, x, y, n, out, nullptr);
 }
 
 // All inner products <v_r, v_c>, r <= c, of up to 8 vectors in one pass and one host synchronisation (the
@@ -586,6 +660,20 @@ extern "C" int ddf_vec_dot(ddf_vec* x, ddf_vec* y, double* out) {
   DDF_CHECK(ddf_vec_settle(x));
   DDF_CHECK(ddf_vec_settle(y));
   return ddf_reduce(x->ctx, 4, x->d.p, y->d.p, x->n, out);
+}
+// dot(f, g) of the reference (ManifoldOps.jl:154-164): defined for Fun{D,Pr,D} (weights 1 ./ vol_D) and
+// Fun{D,Dl,0} (weights 1 ./ dualvol_0) only; one pass, the 1/w division fused into the read of the weight.
+extern "C" int ddf_vec_wdot(ddf_mesh* m, int P, int R, ddf_vec* f, ddf_vec* g, double* out) {
+  DDF_TRY_BEGIN
+  const bool prD = (P == DDF_PR && R == m->D), dl0 = (P == DDF_DL && R == 0);
+  if (!prD && !dl0) DDF_FAIL("dot: defined for Fun{D,Pr,D} and Fun{D,Dl,0} only (ManifoldOps.jl:154-164), got P=%d R=%d", P, R);
+  DDF_CHECK(ddf_mesh_require_geometry(m));
+  if (f->n != m->n[R] || g->n != m->n[R]) DDF_FAIL("dot: cochain length %lld / %lld, mesh has %lld %d-simplices", (long long)f->n, (long long)g->n, (long long)m->n[R], R);
+  DDF_CHECK(ddf_vec_settle(f));
+  DDF_CHECK(ddf_vec_settle(g));
+  const double* w = prD ? m->vol[R].p : m->dualvol[0].p;
+  return reduce_impl(m->ctx, 6, f->d.p, g->d.p, f->n, out, w);
+  DDF_TRY_END
 }
 extern "C" int ddf_vec_sum(ddf_vec* x, double* out) {
   DDF_CHECK(ddf_vec_settle(x));

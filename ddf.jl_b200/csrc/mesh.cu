@@ -14,6 +14,7 @@
 //                        row-CSR (brow_ptr/bcol, parent | sign bit) in one pass
 //                        (:759-765; the two `sparse()` calls become direct writes
 //                        because the sort is stable and rows/columns come out ordered)
+#include <algorithm>
 #include <chrono>
 #include <cub/cub.cuh>
 
@@ -104,7 +105,7 @@ extern "C" int ddf_mesh_create(ddf_ctx* ctx, int D, int C, int64_t nvertices, in
 
 extern "C" int ddf_mesh_destroy(ddf_mesh* m) {
   if (!m) return 0;
-  cudaStreamSynchronize(m->ctx->stream);
+  ddf_sync(m->ctx);                 // every library stream: the tables go back to the pool in compute-stream order
   ddf_halo_release(m);
   delete m;
   return 0;
@@ -423,9 +424,8 @@ static int assemble_level(ddf_mesh* m, int vbits) {
 // Ties (the same face from several parents) are ordered by tuple id = parent id, which is what the stable radix
 // sort of the reference path produces, so every table is bit-identical (tests/test_gpu_parity.py compares both
 // paths with the oracle).  Used when the rest of the tuple fits 64 bits; otherwise the radix path below.
-int g_tune_asm = 0;      // ddf_set_tuning("asm", 1): force the radix-sort path
 
-#define BK_MAX 128       // largest bucket sorted in shared memory; larger ones are sorted serially in place
+#define BK_MAX 128       // largest bucket ranked by one warp in shared memory; larger ones go to k_bucket_sort_big
 
 template <int N>
 __global__ void k_bucket_count(const int32_t* __restrict__ simp, int64_t nsimp, uint32_t* __restrict__ cnt) {
@@ -470,7 +470,7 @@ __device__ __forceinline__ bool bk_less(unsigned long long ra, uint32_t ta, unsi
 // warp per bucket: sort by (rest, tuple id), count the distinct faces
 __global__ void __launch_bounds__(256)
 k_bucket_sort(const uint32_t* __restrict__ start, int64_t nbuckets, unsigned long long* __restrict__ rest,
-              uint32_t* __restrict__ tup, uint32_t* __restrict__ ucnt) {
+              uint32_t* __restrict__ tup, uint32_t* __restrict__ ucnt, uint32_t* __restrict__ big /* [0] = count, then ids */) {
   __shared__ unsigned long long sr[8][BK_MAX];
   __shared__ uint32_t st[8][BK_MAX];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -478,24 +478,8 @@ k_bucket_sort(const uint32_t* __restrict__ start, int64_t nbuckets, unsigned lon
   if (b >= nbuckets) return;
   const uint32_t lo = start[b], sz = start[b + 1] - lo;
   if (sz == 0) { if (lane == 0) ucnt[b] = 0u; return; }
-  if (sz > BK_MAX) {                                  // rare: serial insertion sort in place
-    if (lane == 0) {
-      for (uint32_t i = 1; i < sz; i++) {
-        const unsigned long long r = rest[lo + i];
-        const uint32_t t = tup[lo + i];
-        uint32_t k = i;
-        while (k > 0 && bk_less(r, t, rest[lo + k - 1], tup[lo + k - 1])) {
-          rest[lo + k] = rest[lo + k - 1];
-          tup[lo + k] = tup[lo + k - 1];
-          k--;
-        }
-        rest[lo + k] = r;
-        tup[lo + k] = t;
-      }
-      uint32_t u = 1;
-      for (uint32_t i = 1; i < sz; i++) u += rest[lo + i] != rest[lo + i - 1];
-      ucnt[b] = u;
-    }
+  if (sz > BK_MAX) {                                  // a high-valence vertex: whole blocks sort it (k_bucket_sort_big)
+    if (lane == 0) big[1 + atomicAdd(&big[0], 1u)] = (uint32_t)b;
     return;
   }
   // rank by counting: every lane compares its element(s) with all sz elements of the bucket (broadcast reads of
@@ -527,6 +511,53 @@ k_bucket_sort(const uint32_t* __restrict__ start, int64_t nbuckets, unsigned lon
     u += __popc(__ballot_sync(0xffffffffu, head));
   }
   if (lane == 0) ucnt[b] = u;
+}
+
+// Buckets above BK_MAX tuples (a vertex of very high valence): one block of 1024 threads per bucket sorts it in
+// place in global memory with a bitonic network written with ascending comparators only ("flip" then "disperse"
+// steps), so that any length works -- positions beyond the bucket act as +infinity and are never touched.  Sorted by
+// (rest, tuple id) like the warp path; then the distinct faces are counted.  O(n log^2 n / 1024) per bucket.
+__global__ void __launch_bounds__(1024)
+k_bucket_sort_big(const uint32_t* __restrict__ start, unsigned long long* __restrict__ rest, uint32_t* __restrict__ tup,
+                  uint32_t* __restrict__ ucnt, const uint32_t* __restrict__ big) {
+  __shared__ uint32_t wsum[32];
+  const uint32_t nbig = big[0];
+  for (uint32_t q = blockIdx.x; q < nbig; q += gridDim.x) {
+    const uint32_t b = big[1 + q];
+    const uint32_t lo = start[b], sz = start[b + 1] - lo;
+    unsigned long long* r = rest + lo;
+    uint32_t* t = tup + lo;
+    uint32_t P = 1;
+    while (P < sz) P <<= 1;
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        const bool flip = j == (k >> 1);
+        for (uint32_t h = threadIdx.x; h < (P >> 1); h += blockDim.x) {
+          // h-th comparator of this step: lower index i has bit j clear
+          const uint32_t i = ((h & ~(j - 1u)) << 1) | (h & (j - 1u));
+          const uint32_t p = flip ? (i ^ (k - 1u)) : (i | j);
+          if (p < sz) {
+            const unsigned long long ri = r[i], rp = r[p];
+            const uint32_t ti = t[i], tp = t[p];
+            if (bk_less(rp, tp, ri, ti)) { r[i] = rp; t[i] = tp; r[p] = ri; t[p] = ti; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    uint32_t u = 0;
+    for (uint32_t i = threadIdx.x; i < sz; i += blockDim.x) u += (i == 0 || r[i] != r[i - 1]) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) u += __shfl_xor_sync(0xffffffffu, u, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += wsum[w];
+      ucnt[b] = tot;
+    }
+    __syncthreads();
+  }
 }
 
 // warp per bucket: face ids and every output table (the bucket variant of k_scatter_faces)
@@ -665,7 +696,15 @@ struct AsmWork {
     return buf.alloc(ctx, bytes);
   }
 };
-static AsmWork* g_asm_work = nullptr;     // set by ddf_mesh_assemble for the duration of the call
+// the workspace of the ddf_mesh_assemble in flight is held by its ctx (ctx->asm_work), not by a process global
+
+// bytes of workspace one level of the bucket ranking needs (layout in assemble_level_bucket)
+static size_t bucket_ws_bytes(int64_t ntuples, int64_t nv) {
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t tb = (size_t)ceil_div64(nv + 1, 4096) * 4;
+  return up((size_t)ntuples * 8) + up((size_t)ntuples * 4) + 5 * up((size_t)(nv + 1) * 4) + up(tb) +
+         up(((size_t)ntuples / BK_MAX + 2) * 4);
+}
 
 template <int N>
 static int assemble_level_bucket(ddf_mesh* m, int vbits) {
@@ -680,9 +719,10 @@ static int assemble_level_bucket(ddf_mesh* m, int vbits) {
   const size_t o_rest = 0, o_tup = up((size_t)ntuples * 8), o_cnt = o_tup + up((size_t)ntuples * 4);
   const size_t vsz = up((size_t)(nv + 1) * 4);
   const size_t o_start = o_cnt + vsz, o_cursor = o_start + vsz, o_ucnt = o_cursor + vsz, o_fbase = o_ucnt + vsz;
-  const size_t o_temp = o_fbase + vsz, total = o_temp + up(tb);
+  const size_t o_temp = o_fbase + vsz, o_big = o_temp + up(tb);
+  const size_t total = o_big + up(((size_t)ntuples / BK_MAX + 2) * 4);      // ids of the buckets above BK_MAX tuples
   AsmWork local;
-  AsmWork* wk = g_asm_work ? g_asm_work : &local;
+  AsmWork* wk = ctx->asm_work ? static_cast<AsmWork*>(ctx->asm_work) : &local;
   const bool dbg = getenv("DDF_DEBUG") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_a = now();
@@ -697,6 +737,8 @@ static int assemble_level_bucket(ddf_mesh* m, int vbits) {
   uint32_t* ucnt = reinterpret_cast<uint32_t*>(base + o_ucnt);
   uint32_t* fbase = reinterpret_cast<uint32_t*>(base + o_fbase);
   uint32_t* temp = reinterpret_cast<uint32_t*>(base + o_temp);
+  uint32_t* big = reinterpret_cast<uint32_t*>(base + o_big);
+  DDF_CUDA(cudaMemsetAsync(big, 0, 4, ctx->stream));
   DDF_CUDA(cudaMemsetAsync(cnt, 0, (nv + 1) * 4, ctx->stream));
   int gs, gb;
   DDF_CHECK(grid_for(nsimp, 256, &gs));
@@ -708,7 +750,9 @@ static int assemble_level_bucket(ddf_mesh* m, int vbits) {
   k_bucket_scatter<N><<<gs, 256, 0, ctx->stream>>>(m->simp[R].p, nsimp, vbits, cursor, rest, tup);
   DDF_LAUNCH_CHECK(ctx);
   DDF_CUDA(cudaMemsetAsync(ucnt + nv, 0, 4, ctx->stream));
-  k_bucket_sort<<<gb, 256, 0, ctx->stream>>>(start, nv, rest, tup, ucnt);
+  k_bucket_sort<<<gb, 256, 0, ctx->stream>>>(start, nv, rest, tup, ucnt, big);
+  DDF_LAUNCH_CHECK(ctx);
+  k_bucket_sort_big<<<2 * ctx->sm_count, 1024, 0, ctx->stream>>>(start, rest, tup, ucnt, big);   // no-op without big buckets
   DDF_LAUNCH_CHECK(ctx);
   DDF_CHECK(scan_exclusive_u32(ctx, ucnt, fbase, nv + 1, temp));
   uint32_t nfaces = 0;
@@ -732,13 +776,13 @@ static int assemble_level_bucket(ddf_mesh* m, int vbits) {
                                                R - 1 >= 1 ? m->simp[R - 1].p : nullptr, R >= 2 ? m->bnd[R].p : nullptr,
                                                m->brow_ptr[R].p, m->bcol[R].p, (uint32_t)ntuples, nfaces);
   DDF_LAUNCH_CHECK(ctx);
-  if (!g_asm_work) DDF_CUDA(cudaStreamSynchronize(ctx->stream));     // the local workspace is freed on return
+  if (!ctx->asm_work) DDF_CUDA(cudaStreamSynchronize(ctx->stream));     // the local workspace is freed on return
   return 0;
 }
 
 template <int N>
 static int assemble_level_dispatch(ddf_mesh* m, int vbits) {
-  if (!g_tune_asm && (N - 2) * vbits <= 64) return assemble_level_bucket<N>(m, vbits);
+  if (!m->ctx->tune.asm_path && (N - 2) * vbits <= 64) return assemble_level_bucket<N>(m, vbits);
   const int bits = (N - 1) * vbits;
   if (bits <= 32) return assemble_level<uint32_t, N>(m, vbits);
   if (bits <= 64) return assemble_level<uint64_t, N>(m, vbits);
@@ -755,10 +799,24 @@ extern "C" int ddf_mesh_assemble(ddf_mesh* m) {
   while (((int64_t)1 << vbits) < m->n[0]) vbits++;
   AsmWork work;                          // shared by all levels, released (after a sync) when this call returns
   struct WorkScope {
-    AsmWork* w; cudaStream_t st;
-    ~WorkScope() { cudaStreamSynchronize(st); g_asm_work = nullptr; }
-  } scope{&work, m->ctx->stream};
-  g_asm_work = &work;
+    ddf_ctx* c;
+    ~WorkScope() { cudaStreamSynchronize(c->stream); c->asm_work = nullptr; }
+  } scope{m->ctx};
+  m->ctx->asm_work = &work;
+  {
+    // One allocation for all levels: the lower levels of a mesh usually hold MORE tuples than the top one (3D Kuhn:
+    // 4.0e8 / 6.1e8 / 2.4e8), and growing the workspace in the middle of the assembly costs a free + an allocation
+    // of several GB.  Face counts are predicted from "a face is shared by two simplices" (+3 %); a mesh that beats
+    // the prediction just takes the grow path.
+    size_t need = 0;
+    int64_t nR = m->n[m->D];
+    for (int R = m->D; R >= 1 && nR > 0; R--) {
+      const int64_t ntuples = nR * (R + 1);
+      need = std::max(need, bucket_ws_bytes(ntuples, m->n[0]));
+      nR = (int64_t)((double)ntuples / 2 * 1.03) + 1024;       // predicted n_{R-1}
+    }
+    if (!m->ctx->tune.asm_path && need) DDF_CHECK(work.ensure(m->ctx, need));
+  }
   for (int R = m->D; R >= 1; R--) {
     if (m->n[R] == 0) {                 // empty manifold: every level is empty
       m->n[R - 1] = (R - 1 == 0) ? m->n[0] : 0;

@@ -55,18 +55,6 @@ struct StageBufs {
   }
 };
 
-// staged fixed-width rows of d_k (fstage.cuh): run tables + 16-bit slots per 1024-row window
-struct FStageBufs {
-  DevBuf<uint32_t> tab;
-  DevBuf<uint16_t> slot;
-  uint32_t max_slots = 0;
-  int W = 0;
-  int win = 0;              // rows per window
-  int64_t nwin = 0;
-  int state = 0;            // 0 = not built, 1 = in use, 2 = rejected (explicit-index kernel)
-  void release() { tab.release(); slot.release(); max_slots = 0; W = 0; win = 0; nwin = 0; state = 0; }
-};
-
 // prefix-packed fixed-width rows of d_k (ops.cu, k_pack_fixed): W-1 words per row + one base per 32 rows
 struct PackedBufs {
   DevBuf<uint32_t> words;   // row r: word 0 = (idx0 - base[r/32]) << 24 | (idx1 - idx0), words 1.. = idx2.. explicit
@@ -134,10 +122,10 @@ struct ddf_mesh {
   DevBuf<uint32_t> bpair[DDF_MAXD + 1];
   uint32_t bup_cap[DDF_MAXD + 1] = {0};  // longest upper run of a 256-row window (doubles, rounded): shared memory of the staged kernel
   DevBuf<uint32_t> bup[DDF_MAXD + 1];    // upper-run offsets of the rows of the boundary matrix (ops.cu, upper_build): bsell then holds the lower entries only
-  // staged copies of the fixed-width tables of d_{R-1} = d_R^T (primal derivative apply)
-  FStageBufs fstage[DDF_MAXD + 1];
   PackedBufs bpack[DDF_MAXD + 1];
   BitRows bbits[DDF_MAXD + 1];
+  int64_t wave2_reach = -1;              // largest |column - row| of the L rows (dependency distance of the two-step wavefront)
+  DevBuf<uint32_t> wave2_done;           // per-iteration completion counters of the two-step wavefront (zeroed per launch)
   DevBuf<double> utmp;                   // V   ping-pong buffer of the fused step
   DevBuf<double> ldinv;                  // V   1 ./ diag(L) for the fused Poisson relaxation step
   DevBuf<double> tsit_work;              // 16 V  stage derivatives and scratch of ddf_wave_tsit5 (allocated on first use)

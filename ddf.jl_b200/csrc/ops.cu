@@ -23,13 +23,11 @@
 
 #include "mesh.cuh"
 #include "sell.cuh"
-#include "fstage.cuh"
+#include "stage.cuh"      // bulk_g2s / stage_wait / smem_u32 (TMA staging helpers)
 
-extern int g_tune_fixed;
-static int g_tune_packbits = 24;
-// blocks ahead a block prefetches index words into L2 (0 = off).  Measured at C4 (profiles/r01_tuning.md): any
-// distance from 148 to 2368 blocks gives the same gain; 4 x 148 keeps the request well ahead of the block scheduler.
-static int g_tune_prefetch = 592;
+// Tuning (DdfTune in the ctx).  prefetch: blocks ahead a block prefetches index words into L2 (0 = off); measured at
+// C4 (profiles/r01_tuning.md) any distance from 148 to 2368 blocks gives the same gain; 4 x 148 keeps the request
+// well ahead of the block scheduler.
 int ddf_laplace0_apply(ddf_mesh* m, const double* x, double* y);   // wave.cu
 
 enum OpKind { OPK_ZERO = 0, OPK_FIXED, OPK_CSRSIGN, OPK_DIAG, OPK_CSRF64, OPK_LAPLACE0, OPK_CHAIN, OPK_SUM };
@@ -433,19 +431,6 @@ k_apply_sellf64(const uint32_t* __restrict__ sell_ptr, const uint8_t* __restrict
   if (i < nrows) y[i] = acc;
 }
 
-extern int g_tune_wave;   // wave.cu
-extern int g_tune_asm;    // mesh.cu
-extern int g_tune_fixed;
-extern "C" int ddf_set_tuning(const char* key, int value) {
-  if (!strcmp(key, "fixed")) g_tune_fixed = value;
-  else if (!strcmp(key, "wave")) g_tune_wave = value;
-  else if (!strcmp(key, "asm")) g_tune_asm = value;
-  else if (!strcmp(key, "packbits")) g_tune_packbits = value >= 1 && value <= 24 ? value : 24;
-  else if (!strcmp(key, "prefetch")) g_tune_prefetch = value >= 0 ? value : 0;
-  else DDF_FAIL("set_tuning: unknown key %s", key);
-  return 0;
-}
-
 // ------------------------------------------------------------- tuning variants
 // Experimental variants of the plain (no fused diagonal) fixed-width kernel, selected
 // with ddf_set_tuning("fixed", v).  All produce bit-identical results.
@@ -459,7 +444,6 @@ extern "C" int ddf_set_tuning(const char* key, int value) {
 //                     of bit-packed rows; 21 / 22 bit-packed rows with more / fewer rows per lane
 //   boundary apply:   9 row-CSR; 17 8 gathers per round on short rows; 20 plain SELL copy (no upper runs); 21 upper
 //                     runs read from global memory; 22 upper runs for short rows too; 28 index words 4 at a time; 32 pair table with the 40-register build
-int g_tune_fixed = 0;
 
 template <int W, int XM = 0>
 __device__ __forceinline__ void fixed_rows4(const int* idx, const double* __restrict__ x, uint64_t pol_keep,
@@ -791,6 +775,7 @@ k_apply_packed_quad(const uint32_t* __restrict__ words, const uint32_t* __restri
 }
 
 static int packed_build(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, PackedBufs& pb) {
+  const DdfTune& tn = ctx->tune;
   pb.release();
   pb.state = 2;
   if (W < 2 || W > 4 || nrows == 0) return 0;
@@ -801,7 +786,7 @@ static int packed_build(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, 
   DDF_CHECK(pb.base.alloc(ctx, (size_t)ceil_div64(nrows, 32)));
   int grid;
   DDF_CHECK(grid_for(nrows, 256, &grid));
-  const uint32_t max_off = (1u << g_tune_packbits) - 1u;      // 24 bits; the tuning knob only narrows it (tests)
+  const uint32_t max_off = (1u << tn.packbits) - 1u;      // 24 bits; the tuning knob only narrows it (tests)
   if (W == 2) k_pack_fixed<2><<<grid, 256, 0, ctx->stream>>>(tab, nrows, max_off, pb.words.p, pb.base.p, bad.p);
   else if (W == 3) k_pack_fixed<3><<<grid, 256, 0, ctx->stream>>>(tab, nrows, max_off, pb.words.p, pb.base.p, bad.p);
   else k_pack_fixed<4><<<grid, 256, 0, ctx->stream>>>(tab, nrows, max_off, pb.words.p, pb.base.p, bad.p);
@@ -816,11 +801,12 @@ static int packed_build(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, 
 
 static int launch_packed(ddf_ctx* ctx, const PackedBufs& pb, int W, int64_t nrows, int first_negative, const double* x,
                          const double* pre, const double* post, double alpha, double* y) {
+  const DdfTune& tn = ctx->tune;
   const int g4 = (int)ceil_div64(ceil_div64(nrows, 4), 256), g3 = (int)ceil_div64(ceil_div64(nrows, 3), 256);
-  const bool quad = W == 2 && g_tune_fixed != 19;
+  const bool quad = W == 2 && tn.fixed != 19;
 #define DDF_PACKED_CASE(PRE_, POST_)                                                                                 \
   do {                                                                                                               \
-    if (quad) k_apply_packed_quad<PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch); \
+    if (quad) k_apply_packed_quad<PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha, tn.prefetch); \
     else if (W == 2) k_apply_packed_rows<2, 4, PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha); \
     else if (W == 3) k_apply_packed_rows<3, 4, PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha); \
     else k_apply_packed_rows<4, 3, PRE_, POST_><<<g3, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha);             \
@@ -1006,21 +992,22 @@ static int bits_build(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, Bi
 template <int W, int WB>
 static void launch_bits_w(ddf_ctx* ctx, const BitRows& br, const BitFmt& f, int64_t nrows, int first_negative,
                           const double* x, const double* pre, const double* post, double alpha, double* y) {
+  const DdfTune& tn = ctx->tune;
   constexpr int RPW = W == 3 ? 4 : 3;
   const int g = (int)ceil_div64(ceil_div64(nrows, RPW), 256);
   const uint32_t *w = br.words.p, *b = br.base.p;
-  if (!pre && !post && (g_tune_fixed == 21 || g_tune_fixed == 22)) {      // A/B: other rows-per-lane counts
+  if (!pre && !post && (tn.fixed == 21 || tn.fixed == 22)) {      // A/B: other rows-per-lane counts
     constexpr int RA = W == 3 ? 8 : 4, RB = 2;
-    if (g_tune_fixed == 21)
-      k_apply_bits_rows<W, WB, RA, false, false><<<(int)ceil_div64(ceil_div64(nrows, RA), 256), 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
+    if (tn.fixed == 21)
+      k_apply_bits_rows<W, WB, RA, false, false><<<(int)ceil_div64(ceil_div64(nrows, RA), 256), 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, tn.prefetch);
     else
-      k_apply_bits_rows<W, WB, RB, false, false><<<(int)ceil_div64(ceil_div64(nrows, RB), 256), 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
+      k_apply_bits_rows<W, WB, RB, false, false><<<(int)ceil_div64(ceil_div64(nrows, RB), 256), 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, tn.prefetch);
     return;
   }
-  if (pre && post) k_apply_bits_rows<W, WB, RPW, true, true><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
-  else if (pre) k_apply_bits_rows<W, WB, RPW, true, false><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
-  else if (post) k_apply_bits_rows<W, WB, RPW, false, true><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
-  else k_apply_bits_rows<W, WB, RPW, false, false><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, g_tune_prefetch);
+  if (pre && post) k_apply_bits_rows<W, WB, RPW, true, true><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, tn.prefetch);
+  else if (pre) k_apply_bits_rows<W, WB, RPW, true, false><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, tn.prefetch);
+  else if (post) k_apply_bits_rows<W, WB, RPW, false, true><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, tn.prefetch);
+  else k_apply_bits_rows<W, WB, RPW, false, false><<<g, 256, 0, ctx->stream>>>(w, b, f, nrows, first_negative, x, y, pre, post, alpha, tn.prefetch);
 }
 
 static int launch_bits(ddf_ctx* ctx, const BitRows& br, int W, int64_t nrows, int first_negative, const double* x,
@@ -1038,11 +1025,12 @@ static int launch_bits(ddf_ctx* ctx, const BitRows& br, int W, int64_t nrows, in
 // 0 = explicit table, 1 = prefix-packed, 2 = bit-packed 4-byte rows, 3 = bit-packed 8-byte rows.
 // Tuning: fixed 18 = explicit only, 20 = no bit-packed rows; a narrowed "packbits" (tests) also switches them off.
 static int dk_rows_format(ddf_mesh* m, int R, int* fmt) {
+  const DdfTune& tn = m->ctx->tune;
   const int W = R + 1;
   *fmt = 0;
   if (W < 2 || W > 4 || m->n[R] == 0) return 0;
-  if (!(g_tune_fixed == 0 || (g_tune_fixed >= 19 && g_tune_fixed <= 22))) return 0;
-  const bool allow_bits = W >= 3 && g_tune_fixed != 20 && g_tune_packbits == 24;
+  if (!(tn.fixed == 0 || (tn.fixed >= 19 && tn.fixed <= 22))) return 0;
+  const bool allow_bits = W >= 3 && tn.fixed != 20 && tn.packbits == 24;
   BitRows& br = m->bbits[R];
   PackedBufs& pb = m->bpack[R];
   if (allow_bits) {
@@ -1081,19 +1069,20 @@ static void launch_fixed_x(ddf_ctx* ctx, int var, const int32_t* tab, int64_t nr
 // ================================================================ kernel launchers
 static int launch_fixed(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, int first_negative, const double* x,
                         const double* pre, const double* post, double alpha, double* y) {
+  const DdfTune& tn = ctx->tune;
   if (nrows == 0) return 0;
   int grid;
   DDF_CHECK(grid_for(ceil_div64(nrows, 4), 256, &grid));
-  if (g_tune_fixed > 0 && g_tune_fixed < 16 && g_tune_fixed != 9 && !pre && !post && alpha == 1.0 && W >= 2 && W <= 4) {
-    if (W == 2) launch_fixed_x<2>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
-    else if (W == 3) launch_fixed_x<3>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
-    else launch_fixed_x<4>(ctx, g_tune_fixed, tab, nrows, first_negative, x, y);
+  if (tn.fixed > 0 && tn.fixed < 16 && tn.fixed != 9 && !pre && !post && alpha == 1.0 && W >= 2 && W <= 4) {
+    if (W == 2) launch_fixed_x<2>(ctx, tn.fixed, tab, nrows, first_negative, x, y);
+    else if (W == 3) launch_fixed_x<3>(ctx, tn.fixed, tab, nrows, first_negative, x, y);
+    else launch_fixed_x<4>(ctx, tn.fixed, tab, nrows, first_negative, x, y);
     DDF_LAUNCH_CHECK(ctx);
     return 0;
   }
   // default for the plain d_1 / d_2 apply: lane = consecutive rows (k_apply_fixed_rows).  Measured at C4
   // (profiles/r01_tuning.md): d1 0.786 -> 0.733 ms, d2 0.769 -> 0.564 ms; d0 (W = 2) is faster with 4 rows per thread.
-  if ((g_tune_fixed == 0 || g_tune_fixed == 18) && (W == 3 || W == 4)) {
+  if ((tn.fixed == 0 || tn.fixed == 18) && (W == 3 || W == 4)) {
     const int g3 = (int)ceil_div64(ceil_div64(nrows, 3), 256);
 #define DDF_ROWS_CASE(PRE_, POST_)                                                                                   \
   do {                                                                                                               \
@@ -1791,6 +1780,7 @@ static int upper_build(ddf_mesh* m, int R, int64_t nrows) {
 }
 
 static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpNode* post, double alpha, double* y) {
+  const DdfTune& tn = f->ctx->tune;
   ddf_mesh* m = f->mesh;
   const double* pre_d = pre ? pre->diag : nullptr;
   const double* post_d = post ? post->diag : nullptr;
@@ -1799,31 +1789,6 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
   if (post) a *= post->scale;
   if (f->kind == OPK_FIXED) {
     const int W = f->R + 1;
-    // plain y = d_k x: staged rows through the persistent TMA pipeline (fstage.cuh) when the table stages
-    // Staged rows through a TMA pipeline (fstage.cuh) are OPT-IN: tuning value 100 + 10*NG + RPT.  Measured at C4
-    // (profiles/r01_tuning.md) they lose to the explicit-index kernel -- the pipeline is bound by the rate at
-    // which one SM accepts cp.async.bulk requests (~100 ns each, ~10 per window), not by bytes.
-    if (!pre_d && !post_d && a == 1.0 && W <= 4 && g_tune_fixed >= 100) {
-      const bool tiled = g_tune_fixed >= 200;            // 200 + RPT: tiled variant (no TMA)
-      const int var = tiled ? 10 + (g_tune_fixed - 200) : g_tune_fixed - 100;
-      const int ng = var / 10, rpt = var % 10;
-      FStageBufs& fs = m->fstage[f->R];
-      if (fs.state == 1 && fs.win != 256 * rpt) fs.release();
-      if (fs.state == 0) DDF_CHECK(fstage_build(f->ctx, m->bnd_table(f->R), W, f->nrows, 256 * rpt, fs));
-      if (fs.state == 1 && tiled) {
-        return W == 2 ? launch_fixed_tiled<2>(f->ctx, fs, f->nrows, (f->R & 1), x, y)
-               : W == 3 ? launch_fixed_tiled<3>(f->ctx, fs, f->nrows, (f->R & 1), x, y)
-                        : launch_fixed_tiled<4>(f->ctx, fs, f->nrows, (f->R & 1), x, y);
-      }
-      if (fs.state == 1) {
-        int rc = W == 2 ? launch_fixed_pipe<2>(f->ctx, fs, ng, f->nrows, (f->R & 1), x, y)
-                 : W == 3 ? launch_fixed_pipe<3>(f->ctx, fs, ng, f->nrows, (f->R & 1), x, y)
-                          : launch_fixed_pipe<4>(f->ctx, fs, ng, f->nrows, (f->R & 1), x, y);
-        if (rc == 0) return 0;
-        if (rc > 0) return rc;
-        fs.state = 2;                    // does not fit the shared-memory ring
-      }
-    }
     // default: prefix-packed rows (4 bytes less index data per row); tuning 18 keeps the explicit table
     {
       int fmt = 0;
@@ -1856,7 +1821,7 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
       // than the stencil-signature sort on the Kuhn mesh)
       // lower entries + upper runs: pays for long rows (vertex rows of a 3D mesh, 14 entries: 0.484 -> 0.436 ms at C4);
       // rows of ~5 entries lose to the plain SELL copy (1.21 -> 1.39-1.51 ms), tuning 22 forces it for them anyway
-      if (R < m->D && g_tune_fixed != 20 && (nnz >= 8 * f->nrows || g_tune_fixed == 22 || g_tune_fixed == 21))
+      if (R < m->D && tn.fixed != 20 && (nnz >= 8 * f->nrows || tn.fixed == 22 || tn.fixed == 21))
         DDF_CHECK(upper_build(m, R, f->nrows));
       if (m->bsell_state[R] == 0) {
         DDF_CHECK(sell_build(f->ctx, m->brow_ptr[R].p, m->bcol[R].p, nullptr, f->nrows, m->bsell[R], false, false));
@@ -1865,18 +1830,18 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
       }
     }
   }
-  if (m->bsell_state[R] == 3 && g_tune_fixed != 9) {
+  if (m->bsell_state[R] == 3 && tn.fixed != 9) {
     const int grid = (int)ceil_div64(ceil_div64(f->nrows, 4), 256);
     const uint32_t* pp = m->bpair[R].p;
-    if (pre_d && post_d) k_apply_pairsign<true, true, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);
-    else if (pre_d) k_apply_pairsign<true, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);
-    else if (post_d) k_apply_pairsign<false, true, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);
-    else if (a == 1.0 && g_tune_fixed != 32) k_apply_pairsign32<4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, y, g_tune_prefetch);
-    else k_apply_pairsign<false, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, g_tune_prefetch);   // tuning 32: the 40-register build
+    if (pre_d && post_d) k_apply_pairsign<true, true, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, tn.prefetch);
+    else if (pre_d) k_apply_pairsign<true, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, tn.prefetch);
+    else if (post_d) k_apply_pairsign<false, true, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, tn.prefetch);
+    else if (a == 1.0 && tn.fixed != 32) k_apply_pairsign32<4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, y, tn.prefetch);
+    else k_apply_pairsign<false, false, 4><<<grid, 256, 0, f->ctx->stream>>>(pp, f->nrows, x, pre_d, post_d, a, y, tn.prefetch);   // tuning 32: the 40-register build
     DDF_LAUNCH_CHECK(f->ctx);
     return 0;
   }
-  if (m->bsell_state[R] == 4 && g_tune_fixed != 9) {
+  if (m->bsell_state[R] == 4 && tn.fixed != 9) {
     const int grid = (int)ceil_div64(f->nrows, DDF_SELL_WIN);
     const SellBufs& sb = m->bsell[R];
     const uint32_t* up = m->bup[R].p;
@@ -1885,14 +1850,14 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
     // memory (8 blocks per SM stay resident) and x / pre are 16-byte aligned; tuning 21 keeps the global-memory loop
     const uint32_t cap = m->bup_cap[R];
     const size_t smem = (size_t)cap * 8 * (pre_d ? 2 : 1);
-    const bool stage = g_tune_fixed != 21 && smem <= 24 * 1024 + (pre_d ? 12 * 1024 : 0) && ((uintptr_t)x & 15) == 0 &&
+    const bool stage = tn.fixed != 21 && smem <= 24 * 1024 + (pre_d ? 12 * 1024 : 0) && ((uintptr_t)x & 15) == 0 &&
                        (!pre_d || ((uintptr_t)pre_d & 15) == 0);
 #define DDF_SELLUP(PRE_, POST_)                                                                                     \
   do {                                                                                                              \
-    if (stage && short_rows) k_apply_sellsign<PRE_, POST_, 4, true, true><<<grid, DDF_SELL_WIN, smem, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, cap, g_tune_prefetch); \
-    else if (stage) k_apply_sellsign<PRE_, POST_, 8, true, true><<<grid, DDF_SELL_WIN, smem, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, cap, g_tune_prefetch);            \
-    else if (short_rows) k_apply_sellsign<PRE_, POST_, 4, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, 0, g_tune_prefetch); \
-    else k_apply_sellsign<PRE_, POST_, 8, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, 0, g_tune_prefetch);            \
+    if (stage && short_rows) k_apply_sellsign<PRE_, POST_, 4, true, true><<<grid, DDF_SELL_WIN, smem, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, cap, tn.prefetch); \
+    else if (stage) k_apply_sellsign<PRE_, POST_, 8, true, true><<<grid, DDF_SELL_WIN, smem, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, cap, tn.prefetch);            \
+    else if (short_rows) k_apply_sellsign<PRE_, POST_, 4, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, 0, tn.prefetch); \
+    else k_apply_sellsign<PRE_, POST_, 8, true><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, up, R & 1, 0, tn.prefetch);            \
   } while (0)
     if (pre_d && post_d) DDF_SELLUP(true, true);
     else if (pre_d) DDF_SELLUP(true, false);
@@ -1902,17 +1867,17 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
     DDF_LAUNCH_CHECK(f->ctx);
     return 0;
   }
-  if (m->bsell_state[R] == 1 && g_tune_fixed != 9) {
+  if (m->bsell_state[R] == 1 && tn.fixed != 9) {
     const int grid = (int)ceil_div64(f->nrows, DDF_SELL_WIN);
     const SellBufs& sb = m->bsell[R];
     // short rows (edges -> faces: ~5 entries): 4 gathers per round keep the kernel at 32 registers / full occupancy;
     // the index words of up to 8 entries are fetched in ONE round trip (1.230 -> 1.136 ms at C4; tuning 28: 4 at a time)
-    const bool short_rows = (int64_t)(R + 1) * m->n[R] < 8 * f->nrows && g_tune_fixed != 17;
+    const bool short_rows = (int64_t)(R + 1) * m->n[R] < 8 * f->nrows && tn.fixed != 17;
 #define DDF_SELLSIGN(PRE_, POST_)                                                                                   \
   do {                                                                                                              \
-    if (short_rows && g_tune_fixed == 28) k_apply_sellsign<PRE_, POST_, 4><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, nullptr, 0, 0, g_tune_prefetch); \
-    else if (short_rows) k_apply_sellsign<PRE_, POST_, 4, false, false, 8><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, nullptr, 0, 0, g_tune_prefetch); \
-    else k_apply_sellsign<PRE_, POST_, 8><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, nullptr, 0, 0, g_tune_prefetch);            \
+    if (short_rows && tn.fixed == 28) k_apply_sellsign<PRE_, POST_, 4><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, nullptr, 0, 0, tn.prefetch); \
+    else if (short_rows) k_apply_sellsign<PRE_, POST_, 4, false, false, 8><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, nullptr, 0, 0, tn.prefetch); \
+    else k_apply_sellsign<PRE_, POST_, 8><<<grid, DDF_SELL_WIN, 0, f->ctx->stream>>>(sb.ptr.p, sb.perm8.p, sb.col.p, f->nrows, x, pre_d, post_d, a, y, nullptr, 0, 0, tn.prefetch);            \
   } while (0)
     if (pre_d && post_d) DDF_SELLSIGN(true, true);
     else if (pre_d) DDF_SELLSIGN(true, false);
@@ -1975,6 +1940,7 @@ __global__ void k_axpy_inplace(double c, const double* __restrict__ t, double* _
 }
 
 static int apply_node(OpNode* n, const double* x, double* y) {
+  const DdfTune& tn = n->ctx->tune;
   ddf_ctx* ctx = n->ctx;
   switch (n->kind) {
     case OPK_ZERO:
@@ -1987,7 +1953,7 @@ static int apply_node(OpNode* n, const double* x, double* y) {
       if (!n->nrows) return 0;
       if (n->sell_state == 0) {                  // large operators: SELL copy of the rows, once
         n->sell_state = 2;
-        if (n->nrows >= 4 * DDF_SELL_WIN && n->nnz >= 2 * n->nrows && !(g_tune_fixed == 9) &&
+        if (n->nrows >= 4 * DDF_SELL_WIN && n->nnz >= 2 * n->nrows && !(tn.fixed == 9) &&
             sell_build(ctx, n->rowptr.p, reinterpret_cast<const uint32_t*>(n->col.p), n->val.p, n->nrows, n->sell,
                        false, true, false) == 0 &&
             n->sell.padded <= 2 * n->nnz)
@@ -2549,13 +2515,7 @@ static int materialise(OpNode* n, Coo& c) {
 // The reference stores EVERY Op as its assembled sparse matrix (Ops.jl:25) and `A * f` is SparseArrays' mul! on it
 // (Ops.jl:262-266): this is that representation on the device -- the tree is materialised with the reference's
 // roundings and chops, then held as rows (ascending columns) so that an apply is one kernel.
-extern "C" int ddf_op_assemble(ddf_op* A, ddf_op** out) {
-  DDF_TRY_BEGIN
-  *out = nullptr;
-  OpNode* n = A->node.get();
-  ddf_ctx* ctx = n->ctx;
-  Coo c;
-  DDF_CHECK(materialise(n, c));
+static int rows_from_coo(ddf_ctx* ctx, OpNode* n, Coo& c, ddf_op** out) {
   DDF_CHECK(coo_transpose(ctx, c, n->nrows));   // sorted by (row, column): c.col = row, c.row = column
   OpRef o = std::make_shared<OpNode>();
   o->kind = OPK_CSRF64; o->ctx = ctx; o->mesh = n->mesh;
@@ -2579,6 +2539,63 @@ extern "C" int ddf_op_assemble(ddf_op* A, ddf_op** out) {
   DDF_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = wrap(o);
   return 0;
+}
+
+extern "C" int ddf_op_assemble(ddf_op* A, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  OpNode* n = A->node.get();
+  Coo c;
+  DDF_CHECK(materialise(n, c));
+  return rows_from_coo(n->ctx, n, c, out);
+  DDF_TRY_END
+}
+
+__global__ void k_div_vals(double* __restrict__ v, int64_t n, double a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = __ddiv_rn(v[i], a);
+}
+__global__ void k_diag_div(const double* __restrict__ d, double s, double a, double* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __ddiv_rn(d ? __dmul_rn(s, d[i]) : s, a);
+}
+
+// A / a (Ops.jl:210-212): `Op(A.manifold, A.values / a)` -- every stored value DIVIDED by a (one rounding; (1/a) * A
+// rounds twice unless 1/a is exact), then the constructor's dnz/chop.  A power-of-two divisor stays lazy (exact either
+// way); anything else is held like the reference holds it, as the assembled matrix.
+extern "C" int ddf_op_div(ddf_op* A, double a, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  OpNode* n = A->node.get();
+  ddf_ctx* ctx = n->ctx;
+  int e = 0;
+  const double mant = frexp(a, &e);
+  if ((mant == 0.5 || mant == -0.5) && e > -1000 && e < 1000) return ddf_op_scale(1.0 / a, A, out);
+  if (n->kind == OPK_ZERO) { *out = wrap(A->node); return 0; }
+  int grid;
+  if (n->kind == OPK_DIAG) {           // Diagonal(d) / a = Diagonal(d ./ a)
+    OpRef o = std::make_shared<OpNode>();
+    o->kind = OPK_DIAG; o->ctx = ctx; o->mesh = n->mesh; o->nrows = n->nrows; o->ncols = n->ncols;
+    DDF_CHECK(o->diag_own.alloc(ctx, n->nrows));
+    if (n->nrows) {
+      DDF_CHECK(grid_for(n->nrows, 256, &grid));
+      k_diag_div<<<grid, 256, 0, ctx->stream>>>(n->diag, n->scale, a, o->diag_own.p, n->nrows);
+      DDF_LAUNCH_CHECK(ctx);
+    }
+    o->diag = o->diag_own.p;
+    o->factors.push_back(A->node);
+    *out = wrap(o);
+    return 0;
+  }
+  Coo c;
+  DDF_CHECK(materialise(n, c));
+  if (c.nnz) {
+    DDF_CHECK(grid_for(c.nnz, 256, &grid));
+    k_div_vals<<<grid, 256, 0, ctx->stream>>>(c.val.p, c.nnz, a);
+    DDF_LAUNCH_CHECK(ctx);
+  }
+  if (!c.is_diag) DDF_CHECK(coo_chop(ctx, c));
+  return rows_from_coo(ctx, n, c, out);
   DDF_TRY_END
 }
 

@@ -30,7 +30,6 @@
 int ddf_mesh_require_star(ddf_mesh* m, int R);   // ops.cu
 int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n, double* out);   // core.cu
 
-int g_tune_wave = 0;
 // windows per pipeline group the builder tries first for short rows (2D meshes); 0 = SELL with 16-bit offsets
 #define DDF_STAGE_K_SHORT 2
 
@@ -152,9 +151,10 @@ int ddf_mesh_require_wave(ddf_mesh* m) {
   //    banded enough, else 32-bit (12 B per entry).  Short rows (2D meshes: 7 entries) are faster here
   //    (profiles/r01_tuning.md).  Tuning bit 2048 forces 32-bit indices.
   const bool long_rows = m->adj_nnz >= 10 * nv;
+  const int tune_wave = ctx->tune.wave;
   // tuning bits 13-14: windows per pipeline group for SHORT rows (0 = use SELL); bit 4096 = legacy "force staged, K = 1"
-  const int k_short = (g_tune_wave & 4096) ? 1 : ((g_tune_wave >> 13) & 3) ? ((g_tune_wave >> 13) & 3) + 1 : DDF_STAGE_K_SHORT;
-  if (!(g_tune_wave & 16) && (long_rows || k_short > 0)) {
+  const int k_short = (tune_wave & 4096) ? 1 : ((tune_wave >> 13) & 3) ? ((tune_wave >> 13) & 3) + 1 : DDF_STAGE_K_SHORT;
+  if (!(tune_wave & 16) && (long_rows || k_short > 0)) {
     for (int K = long_rows ? 1 : k_short; K >= 1; K--) {
       DDF_CHECK(stage_build(ctx, m->adj_ptr.p, m->adj_nbr.p, m->adj_l.p, nv, m->adj_nnz, m->isbnd[0].p, K, m->lstage));
       if (m->lstage.ok && K > 1) {                 // a group must leave room for >= 3 stages
@@ -168,7 +168,7 @@ int ddf_mesh_require_wave(ddf_mesh* m) {
     }
   }
   DDF_CHECK(sell_build(ctx, m->adj_ptr.p, reinterpret_cast<const uint32_t*>(m->adj_nbr.p), m->adj_l.p, nv, m->lsell,
-                       (g_tune_wave & 4) != 0, (g_tune_wave & 8) != 0, !(g_tune_wave & 2048)));
+                       (tune_wave & 4) != 0, (tune_wave & 8) != 0, !(tune_wave & 2048)));
   m->wave_sell = m->lsell.padded <= m->adj_nnz + m->adj_nnz / 8;
   if (!m->wave_sell) m->lsell.release();
   m->has_wave = true;
@@ -602,56 +602,6 @@ extern "C" __attribute__((visibility("default"))) int ddf_debug_pipe_trace(unsig
 #endif
 
 
-// variant 2/3: warp-cooperative row streaming through shared memory (kept for A/B timing)
-#define DDF_ROW_CAP 512       // products staged per warp and chunk (4 KB)
-template <int MODE>
-__global__ void __launch_bounds__(256) k_rows_warp(RowArgs a) {
-  __shared__ double sm[8][DDF_ROW_CAP];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t r0 = a.row0 + ((int64_t)blockIdx.x * 8 + w) * 32;
-  if (r0 >= a.row1) return;
-  const uint64_t pol_keep = make_policy_evict_last();
-  const uint64_t pol_stream = make_policy_evict_first();
-  const int64_t i = r0 + lane;
-  const bool active = i < a.row1;
-  const int64_t ic = active ? i : a.row1 - 1;
-  const uint32_t lo = a.rowptr[ic];
-  const uint32_t hi = active ? a.rowptr[ic + 1] : lo;
-  const uint32_t wlo = __shfl_sync(0xffffffffu, lo, 0);
-  uint32_t whi = hi;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, off));
-  double acc = 0.0;
-  double* s = sm[w];
-  for (uint32_t base = wlo; base < whi; base += DDF_ROW_CAP) {
-    const uint32_t cend = min(base + (uint32_t)DDF_ROW_CAP, whi);
-    // coalesced loads of the warp's entries, gathers issued back to back
-    for (uint32_t k0 = base + lane; k0 < cend; k0 += 32 * 4) {
-      int j[4];
-      double l[4], uu[4];
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const uint32_t k = k0 + 32 * q;
-        const bool ok = k < cend;
-        j[q] = ok ? ld_stream_int(a.nbr + k) : (int)ic;
-        l[q] = ok ? ld_stream_f64(a.lval + k) : 0.0;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; q++) uu[q] = ld_keep_f64(a.u + j[q], pol_keep);
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const uint32_t k = k0 + 32 * q;
-        if (k < cend) s[k - base] = __dmul_rn(l[q], uu[q]);
-      }
-    }
-    __syncwarp();
-    const uint32_t sb = max(lo, base), se = min(hi, cend);
-    for (uint32_t q = sb; q < se; q++) acc = __dadd_rn(acc, s[q - base]);
-    __syncwarp();
-  }
-  if (active) row_epilogue<MODE>(a, i, acc, pol_stream);
-}
-
 template <int MODE>
 static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
   const int64_t n = a.row1 - a.row0;
@@ -660,7 +610,8 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
   a.nbr = m->adj_nbr.p;
   a.lval = m->adj_l.p;
   a.isb = m->isbnd[0].p;
-  if (m->lstage.ok && (g_tune_wave & 3) == 0) {          // default: staged rows
+  const int tune_wave = m->ctx->tune.wave;
+  if (m->lstage.ok && (tune_wave & 3) == 0) {          // default: staged rows
     const int64_t w0 = a.row0 / DDF_SELL_WIN, w1 = (a.row1 + DDF_SELL_WIN - 1) / DDF_SELL_WIN;
     if (w1 - w0 > 0x7fffffffLL) DDF_FAIL("grid too large");
     const StageBufs& sb = m->lstage;
@@ -670,23 +621,15 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
     const int64_t g0 = a.row0 / gw, g1 = (a.row1 + gw - 1) / gw;
     const bool fits = pipe_geometry(m, &g);
     if (sb.K > 1 && !fits) DDF_FAIL("staged rows: a group of %d windows does not fit the shared-memory ring", sb.K);
-    if (sb.K > 1 || (!(g_tune_wave & 128) && fits && w1 - w0 >= 4)) {          // persistent TMA pipeline
+    if (sb.K > 1 || (!(tune_wave & 128) && fits && w1 - w0 >= 4)) {          // persistent TMA pipeline
       const size_t smem_p = (size_t)g.nstages * g.stage_bytes;
       const int grid = (int)std::min<int64_t>(m->ctx->sm_count, g1 - g0);
-      const int ng = (g_tune_wave >> 8) & 3;                     // A/B knob: consumer groups per block
-      static bool said = false;
-      if (!said && getenv("DDF_DEBUG")) {
-        fprintf(stderr, "[ddf] k_rows_pipe: %d stages x %u B (K %d, slots %u, entries %u), grid %d\n", g.nstages,
-                g.stage_bytes, sb.K, sb.max_slots, sb.max_entries, grid);
-        said = true;
-      }
+      const int ng = (tune_wave >> 8) & 3;                     // A/B knob: consumer groups per block
+      // the dynamic shared-memory limit is a per-device function attribute: set it on every launch (a host-side
+      // table update, no device work) instead of caching it in a process-wide static
 #define DDF_PIPE_LAUNCH(NGV)                                                                                        \
   do {                                                                                                              \
-    static size_t attr_p = 0;                                                                                       \
-    if (attr_p < smem_p) {                                                                                          \
-      DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe<MODE, NGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
-      attr_p = smem_p;                                                                                              \
-    }                                                                                                               \
+    DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe<MODE, NGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
     k_rows_pipe<MODE, NGV><<<grid, NGV * PIPE_GROUP + 32, smem_p, stream>>>(a, sb.tab.p, sb.packed.p, sb.meta.p,    \
                                                                            g0, g1, g);                               \
   } while (0)
@@ -699,7 +642,7 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
     }
     const size_t smem = (size_t)sb.max_slots * 8;
     if (smem > 48 * 1024 - 64) DDF_FAIL("staged rows: %zu bytes of staging exceed the static limit", smem);
-    const int batch = (g_tune_wave >> 5) & 3;          // A/B knob: gathers in flight per thread
+    const int batch = (tune_wave >> 5) & 3;          // A/B knob: gathers in flight per thread
     if (batch == 1)
       k_rows_stage<MODE, 4><<<(int)(w1 - w0), DDF_SELL_WIN, smem, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p, sb.tab.p,
                                                                            sb.packed.p, w0);
@@ -712,7 +655,7 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
     else
       k_rows_stage<MODE, 8><<<(int)(w1 - w0), DDF_SELL_WIN, smem, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.len8.p, sb.tab.p,
                                                                            sb.packed.p, w0);
-  } else if (m->wave_sell && (g_tune_wave & 3) == 0) {   // explicit-index SELL-32 rows
+  } else if (m->wave_sell && (tune_wave & 3) == 0) {   // explicit-index SELL-32 rows
     const int64_t w0 = a.row0 / DDF_SELL_WIN, w1 = (a.row1 + DDF_SELL_WIN - 1) / DDF_SELL_WIN;
     if (w1 - w0 > 0x7fffffffLL) DDF_FAIL("grid too large");
     const SellBufs& sb = m->lsell;
@@ -725,21 +668,10 @@ static int launch_rows(ddf_mesh* m, cudaStream_t stream, RowArgs a) {
     else
       k_rows_sell<MODE, false><<<(int)(w1 - w0), DDF_SELL_WIN, 0, stream>>>(a, sb.ptr.p, sb.perm8.p, sb.col.p, sb.val.p,
                                                                              nullptr, nullptr, w0);
-  } else if ((g_tune_wave & 3) < 2) {   // CSR, one thread per row
+  } else {                                // CSR, one thread per row
     int grid;
     DDF_CHECK(grid_for(n, 256, &grid));
     k_rows_thread<MODE><<<grid, 256, 0, stream>>>(a);
-  } else {
-    int grid;
-    DDF_CHECK(grid_for(n, 256, &grid));       // 8 warps x 32 rows per block
-    // the staging buffer must not eat the L1 that serves the u-gathers: cap the shared-memory carveout
-    static int carve_set[3] = {-1, -1, -1};
-    const int carve = (g_tune_wave & 3) == 2 ? 50 : -1;
-    if (carve_set[MODE] != carve) {
-      DDF_CUDA(cudaFuncSetAttribute(k_rows_warp<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-      carve_set[MODE] = carve;
-    }
-    k_rows_warp<MODE><<<grid, 256, 0, stream>>>(a);
   }
   DDF_LAUNCH_CHECK(m->ctx);
   return 0;
@@ -850,8 +782,9 @@ int ddf_step_launch(ddf_mesh* m, cudaStream_t stream, int kind, const double* u,
   return launch_rows<3>(m, stream, a);
 }
 
-#ifdef DDF_WAVEFRONT2
-#include "wavefront2.cuh"      // experimental two-step wavefront (never run on a device yet; not built by default)
+#include "wavefront2.cuh"      // two leapfrog steps per launch with a wavefront through L2
+#ifndef DDF_WAVE2_DEFAULT
+#define DDF_WAVE2_DEFAULT 0    // flipped to 1 once the two-step kernel is measured faster on the device (profiles/)
 #endif
 
 int ddf_leapfrog_launch(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
@@ -877,14 +810,15 @@ extern "C" int ddf_wave_leapfrog(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt,
   DDF_CHECK(ddf_vec_settle(v));
   if ((int64_t)m->utmp.n != nv) DDF_CHECK(m->utmp.alloc(m->ctx, nv));
   int s = 0;
-#ifdef DDF_WAVEFRONT2
-  if (g_tune_wave & 65536) {       // experimental: two steps per launch (the state ends up in u again: no swap)
+  // two steps per launch (wavefront2.cuh; the state ends up in u again: no swap).  Tuning bit 65536 forces it on,
+  // 131072 forces one step per launch; launch_pipe2 itself declines meshes where the wavefront cannot pay
+  const int tw = m->ctx->tune.wave;
+  if ((tw & 65536) || (DDF_WAVE2_DEFAULT && !(tw & 131072) && (tw & 0xffff) == 0)) {
     for (bool ran = true; ran && s + 1 < nsteps;) {
       DDF_CHECK(launch_pipe2(m, m->ctx->stream, u->d.p, v->d.p, m->utmp.p, dt, &ran));
       if (ran) s += 2;
     }
   }
-#endif
   for (; s < nsteps; s++) {
     DDF_CHECK(ddf_leapfrog_launch(m, m->ctx->stream, u->d.p, v->d.p, m->utmp.p, dt, 0, nv));
     u->d.swap(m->utmp);          // O(1) ping-pong: the vector handle now owns the new state

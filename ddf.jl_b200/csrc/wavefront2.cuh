@@ -1,8 +1,5 @@
-// wavefront2.cuh -- EXPERIMENTAL, NOT BUILT BY DEFAULT (compile wave.cu with -DDDF_WAVEFRONT2; build.sh does not).
-//
-// STATUS: written at the end of round 1 when no GPU minutes were left.  It compiles for sm_100a and its schedule is
-// model-checked on host threads (tests/test_wavefront_model.py), but it has NEVER RUN on a device.  Nothing in the
-// shipped library, the tests or the bench uses it.  DESIGN.md section 7 holds the plan it implements.
+// wavefront2.cuh -- two fused leapfrog steps per launch (included by wave.cu; selected by ddf_wave_leapfrog, see there).
+// The schedule is model-checked on host threads (tests/test_wavefront_model.py).
 //
 // Two fused leapfrog steps per launch with a wavefront through L2.  The persistent blocks of k_rows_pipe walk the
 // windows in order; here iteration `it` of a block runs the step-n task of window it*B + b and then the step-(n+1)
@@ -116,9 +113,18 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
             const int64_t left = (w1 - w0) - q * stride;
             const uint32_t active = (uint32_t)(left < stride ? left : stride);
             uint32_t seen;
-            do {
+            unsigned long long t0 = 0;
+            for (;;) {
               asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + q) : "memory");
-            } while (seen < active);
+              if (seen >= active) break;
+              // never hang the device: the blocks are co-resident by construction, so a wait of seconds means a
+              // broken schedule -- abort the launch (the host sees a launch failure) instead of spinning for ever
+              unsigned long long t1;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+              if (t0 == 0) t0 = t1;
+              else if (t1 - t0 > 4000000000ull) __trap();
+              __nanosleep(64);
+            }
           }
         }
         __syncwarp();
@@ -239,10 +245,7 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, 
   const int64_t gw = (int64_t)sb.K * DDF_SELL_WIN;
   const int64_t g0 = 0, g1 = (nv + gw - 1) / gw;
   const int grid = (int)std::min<int64_t>(m->ctx->sm_count, g1 - g0);
-  if (g1 - g0 < 4 * (int64_t)grid) return 0;                   // too few windows for a wavefront
-  static ddf_mesh* reach_mesh = nullptr;
-  static int64_t reach_rows = 0;
-  if (reach_mesh != m) {
+  if (m->wave2_reach < 0) {
     DevBuf<unsigned long long> r;
     DDF_CHECK(r.alloc(m->ctx, 1));
     DDF_CUDA(cudaMemsetAsync(r.p, 0, 8, stream));
@@ -253,20 +256,18 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, 
     unsigned long long h = 0;
     DDF_CUDA(cudaMemcpyAsync(&h, r.p, 8, cudaMemcpyDeviceToHost, stream));
     DDF_CUDA(cudaStreamSynchronize(stream));
-    reach_rows = (int64_t)h;
-    reach_mesh = m;
+    m->wave2_reach = (int64_t)h;
   }
-  const int reachw = (int)(reach_rows / gw) + 2;
+  const int reachw = (int)(m->wave2_reach / gw) + 2;
   const int lag = (reachw + grid - 1) / grid + 1;
   const int64_t nit = (g1 - g0 + grid - 1) / grid;
-  static uint32_t* done_p = nullptr;                            // one counter per iteration, zeroed per launch
-  static int64_t done_n = 0;                                    // (experimental: a process-lifetime scratch buffer)
-  if (done_n < nit) {
-    if (done_p) cudaFree(done_p);
-    DDF_CUDA(cudaMalloc((void**)&done_p, (size_t)nit * 4));
-    done_n = nit;
-  }
-  DDF_CUDA(cudaMemsetAsync(done_p, 0, (size_t)nit * 4, stream));
+  // worth it only when the wavefront is short against the sweep: the windows between the two steps must stay in L2
+  // (lag * grid windows of entries) and the first / last `lag` iterations run one step only
+  if (nit < 4 * (int64_t)lag) return 0;
+  const int64_t held = (int64_t)lag * grid * (int64_t)sb.max_entries * 10;
+  if (held > (int64_t)48 << 20) return 0;
+  if ((int64_t)m->wave2_done.n < nit) DDF_CHECK(m->wave2_done.alloc(m->ctx, (size_t)nit));
+  DDF_CUDA(cudaMemsetAsync(m->wave2_done.p, 0, (size_t)nit * 4, stream));
   RowArgs a{};
   a.u = u;
   a.out0 = v;
@@ -274,14 +275,11 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, 
   a.dt = dt;
   a.row0 = 0;
   a.row1 = nv;
+  a.isb = m->isbnd[0].p;
   const size_t smem_p = (size_t)g.nstages * g.stage_bytes;
-  static size_t attr_p = 0;
-  if (attr_p < smem_p) {
-    DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-    attr_p = smem_p;
-  }
+  DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
   k_rows_pipe2<2><<<grid, 2 * PIPE_GROUP + 32, smem_p, stream>>>(a, sb.tab.p, sb.packed.p, sb.meta.p, g0, g1, g, lag,
-                                                                 reachw, done_p);
+                                                                 reachw, m->wave2_done.p);
   DDF_LAUNCH_CHECK(m->ctx);
   *ran = true;
   return 0;

@@ -55,6 +55,9 @@ int ddf_ctx_destroy(ddf_ctx* ctx);
 int ddf_sync(ddf_ctx* ctx);
 /* bytes currently held by the library on this ctx's device */
 int ddf_ctx_bytes_in_use(ddf_ctx* ctx, int64_t* out);
+/* Device memory is drawn from the device's stream-ordered pool and stays cached there when tables are dropped;
+ * ddf_ctx_trim synchronises and returns the cached blocks to the driver. */
+int ddf_ctx_trim(ddf_ctx* ctx);
 /* CUDA-event timing on the library stream (bench.py's roofline timer):
  * tic records an event, toc records another, synchronises and returns ms. */
 int ddf_timer_tic(ddf_ctx* ctx);
@@ -70,6 +73,9 @@ int ddf_ctx_launch_count(ddf_ctx* ctx, int64_t* out);
  * fallback; "prefetch" = how many blocks ahead a block asks L2 for the index words of a later block, default 592,
  * 0 = off); every variant returns bit-identical results; for "fixed", "wave" and "asm" 0 selects the default */
 int ddf_set_tuning(const char* key, int value);
+/* the same selector for ONE context (ddf_set_tuning sets the defaults of later contexts and every live one);
+ * tuning state lives in the context, so distinct contexts may be driven from distinct threads */
+int ddf_ctx_set_tuning(ddf_ctx* ctx, const char* key, int value);
 /* overwrite a >L2-sized scratch buffer (bench hygiene between timed launches) */
 int ddf_flush_l2(ddf_ctx* ctx);
 
@@ -150,6 +156,9 @@ int ddf_vec_mul(ddf_vec* x, ddf_vec* y, ddf_vec* z);
 int ddf_vec_norm(ddf_vec* v, int kind, double* out);
 int ddf_vec_dot(ddf_vec* x, ddf_vec* y, double* out);
 int ddf_vec_sum(ddf_vec* x, double* out);
+/* dot(f, g) of src/ManifoldOps.jl:154-164: sum f_i (1/vol_D[i]) g_i for Fun{D,Pr,D}, sum f_i (1/dualvol_0[i]) g_i
+ * for Fun{D,Dl,0}; any other (P, R) is an error like the reference's missing method.  One fused pass. */
+int ddf_vec_wdot(ddf_mesh* mesh, int P, int R, ddf_vec* f, ddf_vec* g, double* out);
 
 /* ----------------------------------------------------------------- operators */
 /* Each returns a new op handle (src/ManifoldOps.jl).  P is DDF_PR / DDF_DL. */
@@ -176,6 +185,8 @@ int ddf_op_compose(ddf_op* A, ddf_op* B, ddf_op** out);
 int ddf_op_add(ddf_op* A, double b, ddf_op* B, ddf_op** out);
 /* a*A (Ops.jl:198-212) */
 int ddf_op_scale(double a, ddf_op* A, ddf_op** out);
+/* A / a (Ops.jl:210-212): the assembled values divided by a (one rounding each) + the constructor's chop */
+int ddf_op_div(ddf_op* A, double a, ddf_op** out);
 /* adjoint(A) (Ops.jl:258-260) */
 int ddf_op_adjoint(ddf_op* A, ddf_op** out);
 /* Op*Fun (Ops.jl:273-276): y = A x */

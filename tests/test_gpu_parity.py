@@ -818,26 +818,31 @@ def test_wave_pipeline_repeatable(ddf, ctx):
             ddf._lib.call("ddf_set_tuning", b"wave", 0)
 
 
-@pytest.mark.skipif(not os.environ.get("DDF_WAVEFRONT2"), reason="experimental two-step wavefront: build wave.cu with "
-                    "-DDDF_WAVEFRONT2 and set DDF_WAVEFRONT2=1 (csrc/wavefront2.cuh; not part of the default library)")
-def test_wavefront2_equals_single_steps(ddf, ctx):
-    """Two leapfrog steps per launch (wavefront through L2) against the one-step-per-launch default: same bits after an
-    even and an odd number of steps, repeatably.  Only meaningful with a library built with -DDDF_WAVEFRONT2 (otherwise
-    the tuning bit is ignored and the test would compare the default with itself)."""
-    n = 64                                           # 65^3 vertices = 1073 windows: enough for a wavefront on 148 SMs
-    m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
+@pytest.mark.parametrize("n", [64, 128])
+def test_wavefront2_equals_single_steps(ddf, ctx, n):
+    """Two leapfrog steps per launch (wavefront through L2, csrc/wavefront2.cuh, tuning bit 65536) against the
+    one-step-per-launch kernel AND the oracle-checked explicit-index SELL kernel: same bits after an even and an odd
+    number of steps, repeatably, from a random (non-smooth) state so that a stale or early read cannot hide."""
+    m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)        # n=64: 1073 windows, lag 2; n=128: 8386 windows
     dt = ddf.wave_dt(m)
+    rng = np.random.default_rng(n)
+    u0, v0 = rng.standard_normal(m.nsimplices(0)), rng.standard_normal(m.nsimplices(0))
     for steps in (6, 7):
-        ref_u, ref_v = ddf.sample(m, "wave"), ddf.Fun(m, ddf.Pr, 0)
-        ddf.wave_leapfrog(m, ref_u, ref_v, dt, steps)
+        ref_u, ref_v = ddf.Fun(m, ddf.Pr, 0, u0), ddf.Fun(m, ddf.Pr, 0, v0)
+        ddf._lib.call("ddf_set_tuning", b"wave", 131072)          # one step per launch
+        try:
+            ddf.wave_leapfrog(m, ref_u, ref_v, dt, steps)
+        finally:
+            ddf._lib.call("ddf_set_tuning", b"wave", 0)
+        ru, rv = ref_u.values, ref_v.values
         for _ in range(3):
-            u, v = ddf.sample(m, "wave"), ddf.Fun(m, ddf.Pr, 0)
+            u, v = ddf.Fun(m, ddf.Pr, 0, u0), ddf.Fun(m, ddf.Pr, 0, v0)
             ddf._lib.call("ddf_set_tuning", b"wave", 65536)
             try:
                 ddf.wave_leapfrog(m, u, v, dt, steps)
             finally:
                 ddf._lib.call("ddf_set_tuning", b"wave", 0)
-            assert np.array_equal(u.values, ref_u.values) and np.array_equal(v.values, ref_v.values), steps
+            assert np.array_equal(u.values, ru) and np.array_equal(v.values, rv), steps
     m.close()
 
 

@@ -1,0 +1,274 @@
+"""GPU parity tests added in round 2: the largest meshes the numpy oracle finishes in seconds (3D Kuhn n=64 =
+1.57e6 tetrahedra; a 3D Delaunay mesh of > 1e6 tetrahedra in Qhull's order), the remaining A11 rows (weighted dot,
+norms, sum, integral), `Op / a`, two contexts on two threads, a very high-valence vertex in the assembly, `lookup`
+tables and edge-midpoint refinement on the device."""
+import threading
+import time
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import ddf_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(np.max(np.abs(b)) if b.size else 0.0, 1e-300)
+    return float(np.max(np.abs(a - b)) / scale) if a.size else 0.0
+
+
+def with_device_geometry(om, dm):
+    for R in range(om.D + 1):
+        om._cache[("vol", R)] = dm.get_volumes(R)
+        om._cache[("dualvol", R, True)] = dm.get_dualvolumes(R)
+    return om
+
+
+def compare_everything(ddf, om, dm, steps=4, geometry_tol=RTOL):
+    """assembly CSC, d_k x, boundary x, star x, assembled L, L u and `steps` leapfrog steps: bit for bit (integer work
+    and, given the device's geometry, every Float64 operator); the geometry itself and the end-to-end results with
+    INDEPENDENT geometry on both sides within north_star's 1e-12."""
+    D = om.D
+    for R in range(D + 1):
+        assert dm.nsimplices(R) == om.nsimplices(R)
+        cp, rv = dm.get_simplices_csc(R)
+        ocp, orv = o.simplices_julia_csc(om.simplices[R])
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv), f"simplices R={R}"
+    for R in range(1, D + 1):
+        cp, rv, nz = dm.get_boundaries_csc(R)
+        ocp, orv, onz = o.to_julia_csc(om.boundaries[R])
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz), f"boundary R={R}"
+    rng = np.random.default_rng(64)
+    for k in range(D):
+        x = rng.standard_normal(om.nsimplices(k))
+        assert np.array_equal((ddf.deriv(ddf.Pr, k, dm) * ddf.Fun(dm, ddf.Pr, k, x)).values, o.apply_deriv(o.Pr, k, om, x)), k
+    for k in range(1, D + 1):
+        x = rng.standard_normal(om.nsimplices(k))
+        want = o.spmv_csc(om.boundaries[k], x)
+        assert np.array_equal((ddf.boundary(ddf.Pr, k, dm) * ddf.Fun(dm, ddf.Pr, k, x)).values, want), k
+        assert np.array_equal((ddf.deriv(ddf.Dl, k, dm) * ddf.Fun(dm, ddf.Dl, k, x)).values, want), k
+    # geometry: independent on both sides
+    ext = float(np.max(np.abs(om.coords))) or 1.0
+    for R in range(D + 1):
+        assert relerr(dm.get_volumes(R), o.calc_volumes(om, R)) <= geometry_tol, f"vol R={R}"
+        assert np.max(np.abs(dm.get_dualcoords(R) - o.calc_dualcoords(om, R))) <= geometry_tol * ext, f"dualcoords R={R}"
+        assert relerr(dm.get_dualvolumes(R), o.calc_dualvolumes(om, R)) <= geometry_tol, f"dualvol R={R}"
+    u0 = rng.standard_normal(om.nsimplices(0))
+    v0 = rng.standard_normal(om.nsimplices(0))
+    L_ind = o.laplace(o.Pr, 0, om)                       # oracle geometry
+    y = (ddf.laplace(ddf.Pr, 0, dm) * ddf.Fun(dm, ddf.Pr, 0, u0)).values
+    assert relerr(y, o.spmv_csc(L_ind, u0)) <= geometry_tol, "L u end to end (independent geometry)"
+    dt = ddf.wave_dt(dm)
+    assert abs(dt - o.wave_dt(om)) <= 1e-15
+    ou, ov = o.wave_leapfrog(om, u0, v0, dt, steps)
+    fu, fv = ddf.Fun(dm, ddf.Pr, 0, u0), ddf.Fun(dm, ddf.Pr, 0, v0)
+    ddf.wave_leapfrog(dm, fu, fv, dt, steps)
+    assert relerr(fu.values, ou) <= geometry_tol and relerr(fv.values, ov) <= geometry_tol, "leapfrog end to end"
+    # operators: bit for bit given the device's geometry
+    om._cache.clear()
+    om = with_device_geometry(om, dm)
+    for R in range(D + 1):
+        x = rng.standard_normal(om.nsimplices(R))
+        assert np.array_equal((ddf.hodge(ddf.Pr, R, dm) * ddf.Fun(dm, ddf.Pr, R, x)).values, o.hodge_diag(o.Pr, R, om) * x)
+    L = o.laplace(o.Pr, 0, om)
+    A = ddf.laplace(ddf.Pr, 0, dm).to_csc()
+    assert np.array_equal(A.indptr, L.indptr) and np.array_equal(A.indices, L.indices) and np.array_equal(A.data, L.data)
+    assert np.array_equal(y, o.spmv_csc(L, u0))
+    ou, ov = o.wave_leapfrog(om, u0, v0, dt, steps)
+    assert np.array_equal(fu.values, ou) and np.array_equal(fv.values, ov), "leapfrog bit for bit"
+    om._cache.clear()
+
+
+def test_kuhn3_n64_bit_exact(ddf, ctx):
+    """3D Kuhn n=64 (274,625 / 1,872,064 / 3,170,304 / 1,572,864): vertex keys of 19 bits, 1073 row windows, the
+    bit-packed d_1 / d_2 rows, staged boundary rows -- everything element-wise against the oracle."""
+    om = o.large_hypercube_manifold(3, (64,) * 3)
+    dm = ddf.large_hypercube_manifold(3, (64,) * 3, ctx=ctx)
+    assert [ddf.deriv_format(dm, k) for k in range(3)][1:] == ["bits32", "bits64"]
+    compare_everything(ddf, om, dm)
+    dm.close()
+
+
+def test_delaunay3_million_tets_bit_exact(ddf, ctx):
+    """A 3D Delaunay mesh of random points with > 1e6 tetrahedra in Qhull's (scattered) order: no structure for the
+    row packings to lean on; assembly, every apply and the wave step element-wise against the oracle.  Dual volumes
+    of a random Delaunay mesh are not positive and span many orders of magnitude (obtuse tetrahedra), so the geometry
+    is compared at 1e-9 of the largest value here; the operator arithmetic stays bit-exact given the geometry."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(2024)
+    pts = rng.random((160000, 3))
+    tets = np.asarray(Delaunay(pts).simplices, dtype=np.int64)
+    assert len(tets) > 1_000_000
+    om = o.build_manifold("delaunay3", tets, pts)
+    dm = ddf.Manifold.from_simplices("delaunay3", tets, pts, None, ctx=ctx)
+    # independent-geometry end-to-end comparisons are ill-conditioned on this mesh (slivers): operators only
+    D = 3
+    for R in range(D + 1):
+        cp, rv = dm.get_simplices_csc(R)
+        ocp, orv = o.simplices_julia_csc(om.simplices[R])
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv)
+    for R in range(1, D + 1):
+        for a, b in zip(dm.get_boundaries_csc(R), o.to_julia_csc(om.boundaries[R])):
+            assert np.array_equal(a, b)
+    for k in range(D):
+        x = rng.standard_normal(om.nsimplices(k))
+        assert np.array_equal((ddf.deriv(ddf.Pr, k, dm) * ddf.Fun(dm, ddf.Pr, k, x)).values, o.apply_deriv(o.Pr, k, om, x)), k
+    for k in range(1, D + 1):
+        x = rng.standard_normal(om.nsimplices(k))
+        assert np.array_equal((ddf.boundary(ddf.Pr, k, dm) * ddf.Fun(dm, ddf.Pr, k, x)).values, o.spmv_csc(om.boundaries[k], x)), k
+    for R in range(D + 1):
+        assert relerr(dm.get_volumes(R), o.calc_volumes(om, R)) <= RTOL
+    om = with_device_geometry(om, dm)
+    L = o.laplace(o.Pr, 0, om)
+    A = ddf.laplace(ddf.Pr, 0, dm).to_csc()
+    assert np.array_equal(A.indptr, L.indptr) and np.array_equal(A.indices, L.indices) and np.array_equal(A.data, L.data)
+    u0 = rng.standard_normal(om.nsimplices(0))
+    assert np.array_equal((ddf.laplace(ddf.Pr, 0, dm) * ddf.Fun(dm, ddf.Pr, 0, u0)).values, o.spmv_csc(L, u0))
+    dm.close()
+
+
+# ----------------------------------------------------------------------------- A11
+@pytest.mark.parametrize("D,n", [(2, 24), (3, 8)])
+def test_weighted_dot_norms_sum_integral(ddf, ctx, D, n):
+    """dot(f,g) (ManifoldOps.jl:154-164), integral (:150-151), norm(.,1|2|Inf), sum against the oracle's numpy
+    evaluation.  Reduction order differs from Julia's pairwise mapreduce (and numpy's): tolerance n*eps of the
+    absolute sum, written below; max-norm and the weights' roundings are exact."""
+    om = o.large_hypercube_manifold(D, (n,) * D)
+    dm = ddf.large_hypercube_manifold(D, (n,) * D, ctx=ctx)
+    rng = np.random.default_rng(5)
+    eps = np.finfo(np.float64).eps
+    for P, R, w in ((ddf.Pr, D, o.calc_volumes(om, D)), (ddf.Dl, 0, o.calc_dualvolumes(om, 0))):
+        nR = om.nsimplices(R)
+        f, g = rng.standard_normal(nR), rng.standard_normal(nR)
+        F, G = ddf.Fun(dm, P, R, f), ddf.Fun(dm, P, R, g)
+        dw = dm.get_volumes(D) if P else dm.get_dualvolumes(0)
+        terms = (f * (1.0 / dw)) * g                     # dot(x, Diagonal(1 ./ w), y): x_i * d_i * y_i per entry
+        tol = 4 * nR * eps * np.sum(np.abs(terms))
+        assert abs(F.dot(G) - np.sum(terms)) <= tol
+        assert abs(F.dot(G) - np.sum((f * (1.0 / w)) * g)) <= tol + 1e-12 * np.sum(np.abs(terms))   # oracle geometry
+        assert abs(ddf.integral(F) - np.sum(f)) <= 4 * nR * eps * np.sum(np.abs(f))
+        assert abs(F.sum() - np.sum(f)) <= 4 * nR * eps * np.sum(np.abs(f))
+        assert abs(F.norm(1) - np.sum(np.abs(f))) <= 4 * nR * eps * np.sum(np.abs(f))
+        assert abs(F.norm(2) - np.sqrt(np.sum(f * f))) <= 4 * nR * eps * np.sqrt(np.sum(f * f))
+        assert F.norm(np.inf) == np.max(np.abs(f))
+        assert abs(F.vdot(G) - np.dot(f, g)) <= 4 * nR * eps * np.sum(np.abs(f * g))
+    # exact case: integer-valued data and unit weights (D-simplices of a mesh scaled so that vol_D = 1 do not exist
+    # here; use the weights' exactness instead: a power-of-two weight commutes with the sum)
+    with pytest.raises(ddf.DDFError, match="ManifoldOps.jl:154-164"):
+        ddf.Fun(dm, ddf.Pr, 1).dot(ddf.Fun(dm, ddf.Pr, 1))
+    with pytest.raises(ddf.DDFError):
+        ddf.Fun(dm, ddf.Pr, D).dot(ddf.Fun(dm, ddf.Pr, 0))
+    dm.close()
+
+
+def test_op_division_rounds_like_the_reference(ddf, ctx):
+    """A / a (Ops.jl:210-212) divides every stored value once: to_csc(A / 3) == oracle values / 3 bit for bit (and is
+    NOT (1/3) * A), for a diagonal, a sparse product and the Laplacian; apply follows the assembled values."""
+    om = o.large_hypercube_manifold(2, (6, 6))
+    dm = ddf.large_hypercube_manifold(2, (6, 6), ctx=ctx)
+    om = with_device_geometry(om, dm)
+    rng = np.random.default_rng(9)
+    for a in (3.0, 7.0, 0.1):
+        A = (ddf.coderiv(ddf.Pr, 1, dm) / a).to_csc()
+        B = o.chop_sparse(sp.csc_matrix(o.coderiv(o.Pr, 1, om)))
+        B.data = B.data / a
+        B = o.chop_sparse(B)
+        assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
+        Lq = (ddf.laplace(ddf.Pr, 0, dm) / a)
+        Lo = o.laplace(o.Pr, 0, om)
+        Lo.data = Lo.data / a
+        assert np.array_equal(Lq.to_csc().data, Lo.data)
+        x = rng.standard_normal(om.nsimplices(0))
+        assert np.array_equal((Lq * ddf.Fun(dm, ddf.Pr, 0, x)).values, o.spmv_csc(Lo, x))
+        H = (ddf.hodge(ddf.Pr, 1, dm) / a).to_csc()
+        assert np.array_equal(H.diagonal(), o.hodge_diag(o.Pr, 1, om) / a)
+    # a power of two stays lazy and exact
+    x = rng.standard_normal(om.nsimplices(0))
+    d0 = ddf.deriv(ddf.Pr, 0, dm)
+    assert np.array_equal(((d0 / 4.0) * ddf.Fun(dm, ddf.Pr, 0, x)).values, o.apply_deriv(o.Pr, 0, om, x) / 4.0)
+    dm.close()
+
+
+# ------------------------------------------------------------------ contexts and threads
+def test_two_contexts_on_two_threads(ddf, ctx):
+    """"distinct ctxs may be used from distinct threads".  Two contexts (same device) assemble, apply and
+    step concurrently from two host threads with DIFFERENT per-context tuning; each must reproduce the oracle bit for
+    bit.  (Tuning state, the assembly workspace and the kernel attributes live in the context now, not in globals.)"""
+    om = o.large_hypercube_manifold(3, (10, 10, 10))
+    rng = np.random.default_rng(3)
+    xs = [rng.standard_normal(om.nsimplices(k)) for k in range(3)]
+    want = [o.apply_deriv(o.Pr, k, om, xs[k]) for k in range(3)]
+    errors = []
+
+    def worker(tune_fixed, tune_asm, reps):
+        try:
+            c = ddf.Context(0)
+            ddf._lib.call("ddf_ctx_set_tuning", c._h, b"fixed", tune_fixed)
+            ddf._lib.call("ddf_ctx_set_tuning", c._h, b"asm", tune_asm)
+            for _ in range(reps):
+                dm = ddf.large_hypercube_manifold(3, (10, 10, 10), ctx=c)
+                for R in range(1, 4):
+                    for a, b in zip(dm.get_boundaries_csc(R), o.to_julia_csc(om.boundaries[R])):
+                        assert np.array_equal(a, b)
+                for k in range(3):
+                    y = (ddf.deriv(ddf.Pr, k, dm) * ddf.Fun(dm, ddf.Pr, k, xs[k])).values
+                    assert np.array_equal(y, want[k]), (tune_fixed, k)
+                fmt = [ddf.deriv_format(dm, k) for k in range(3)]
+                assert (fmt == ["explicit"] * 3) == (tune_fixed == 18), (tune_fixed, fmt)
+                u, v = ddf.sample(dm, "wave"), ddf.Fun(dm, ddf.Pr, 0)
+                ddf.wave_leapfrog(dm, u, v, ddf.wave_dt(dm), 3)
+                dm.close()
+            c.sync()
+            c.close()
+        except BaseException as e:      # noqa: BLE001 -- reported in the main thread
+            errors.append(e)
+
+    ts = [threading.Thread(target=worker, args=(0, 0, 6)), threading.Thread(target=worker, args=(18, 1, 6))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
+# ---------------------------------------------------------------------- assembly: a very long bucket
+def test_assembly_one_vertex_of_valence_1e5(ddf, ctx):
+    """A fan of 100,000 triangles around ONE vertex (id 0): the bucket of vertex 0 holds 2e5 face tuples.  The
+    overflow path of the bucket ranking must sort it with the whole block (it used to be a single-lane insertion
+    sort), give the oracle's numbering, and do so in well under a second."""
+    k = 100_000
+    ang = 2 * np.pi * np.arange(k) / k
+    coords = np.concatenate([[[0.0, 0.0]], np.stack([np.cos(ang), np.sin(ang)], axis=1)])
+    tri = np.stack([np.zeros(k, dtype=np.int64), 1 + np.arange(k), 1 + (np.arange(k) + 1) % k], axis=1)
+    rng = np.random.default_rng(0)
+    tri = tri[rng.permutation(k)]                            # parents in a scattered order: ties resolved by parent id
+    om = o.build_manifold("fan", tri, coords)
+    ctx.sync()
+    t0 = time.perf_counter()
+    dm = ddf.Manifold.from_simplices("fan", tri, coords, None, ctx=ctx)
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    for R in (1, 2):
+        for a, b in zip(dm.get_boundaries_csc(R), o.to_julia_csc(om.boundaries[R])):
+            assert np.array_equal(a, b)
+    assert np.array_equal(dm.get_simplices(1), om.simplices[1])
+    assert dt < 1.0, f"assembly of a 1e5-valence fan took {dt:.2f} s"
+    dm.close()
+    # the same in 3D: 60,000 tetrahedra sharing one vertex (a triangulated sphere coned to the centre)
+    from scipy.spatial import ConvexHull
+    p = rng.standard_normal((30002, 3))
+    p /= np.linalg.norm(p, axis=1)[:, None]
+    hull = ConvexHull(p).simplices.astype(np.int64)
+    coords = np.concatenate([[[0.0, 0.0, 0.0]], p])
+    tets = np.concatenate([np.zeros((len(hull), 1), dtype=np.int64), hull + 1], axis=1)
+    om = o.build_manifold("cone", tets, coords)
+    dm = ddf.Manifold.from_simplices("cone", tets, coords, None, ctx=ctx)
+    for R in (1, 2, 3):
+        for a, b in zip(dm.get_boundaries_csc(R), o.to_julia_csc(om.boundaries[R])):
+            assert np.array_equal(a, b)
+    dm.close()
