@@ -126,24 +126,42 @@ def owned_counts(ddf, ctx, nelts_xy, slab, local_counts):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_reference_pass(n_ref, seconds_target, threads_omp=False):
-    """Time the C restatement of the reference's CPU path on a bounded sample: 3D Kuhn n=n_ref,
-    the same 7 operator applications, reference storage.  Returns dict(value, unit, cores, kind, sample)."""
+_CPU_SETUP = {}
+
+
+def cpu_reference_setup(n_ref):
+    """The reference's storage of BASELINE config 4 at n = n_ref on the host: boundaries[1..3] as 1-based Int64 CSC with
+    Int8 values.  Built entirely on the CPU by the oracle's C twin (Kuhn table + linear-time face ranking, both held
+    against the literal restatement in tests/test_oracle_pins.py) -- nothing of the product is involved."""
+    if n_ref in _CPU_SETUP:
+        return _CPU_SETUP[n_ref]
     import c_oracle
     import ddf_oracle as o
     t0 = time.time()
-    simp, coords, weights = o.large_hypercube_tables(3, (n_ref,) * 3)
-    tables = {3: simp}
+    tab = c_oracle.kuhn3_table(n_ref, o.symmetric_hypercube(3))
+    V = (n_ref + 1) ** 3
+    n = [V, 0, 0, tab.shape[0]]
     csc = {}
     for R in (3, 2, 1):
-        faces, cp, rv, nz = c_oracle.calc_faces_boundaries(tables[R])
-        tables[R - 1] = faces
+        faces, cp, rv, nz = c_oracle.calc_faces_boundaries_linear(tab, V)
         csc[R] = (cp, rv, nz)
-    t_asm = time.time() - t0
-    n = [coords.shape[0]] + [tables[R].shape[0] for R in (1, 2, 3)]
+        n[R - 1] = faces.shape[0]
+        tab = faces
+    del tab
+    assert n[0] == V
+    _CPU_SETUP[n_ref] = (n, csc, time.time() - t0)
+    return _CPU_SETUP[n_ref]
+
+
+def cpu_reference_pass(n_ref, warmup, steps, seconds_cap, threads_omp=False):
+    """Time the C restatement of the reference's CPU path: 3D Kuhn n=n_ref, the same 7 operator applications per step
+    on the reference's storage.  `warmup` untimed + up to `steps` timed passes (fewer if they would exceed
+    `seconds_cap`).  Returns dict(value, unit, cores, kind, sample, ...)."""
+    import c_oracle
+    n, csc, t_asm = cpu_reference_setup(n_ref)
     rng = np.random.default_rng(0)
     x = [rng.random(nk) for nk in n]
-    # the diagonal's values do not change the cost of Diagonal*Vector; use the oracle's real stars where cheap
+    # the diagonal's values do not change the cost of Diagonal * Vector
     star = [rng.random(nk) + 0.5 for nk in n]
     dof = 2 * (n[1] + n[2] + n[3]) + n[0]
 
@@ -154,69 +172,70 @@ def cpu_reference_pass(n_ref, seconds_target, threads_omp=False):
         for k in range(4):
             c_oracle.diag_mul(star[k], x[k])
 
+    t1 = time.time()
     one_pass()
+    first = time.time() - t1
+    for _ in range(max(0, min(warmup - 1, int(seconds_cap / 4 / max(first, 1e-9))))):
+        one_pass()
     t1 = time.time()
     reps = 0
-    while True:
+    while reps < steps:
         one_pass()
         reps += 1
         el = time.time() - t1
-        if el >= seconds_target or reps >= 200:
+        if el >= seconds_cap:
             break
+    el = time.time() - t1
     per = el / reps
-    return {"value": dof / per, "unit": UNIT, "cores": (os.cpu_count() if threads_omp else 1), "kind": "port",
-            "sample": f"3D Kuhn n={n_ref} ({n[3]} tets, {dof} DOF/step), {reps} passes in {el:.1f}s, C restatement of "
-                      f"SparseArrays mul! on Int64-CSC/Int8 storage; assembly restatement took {t_asm:.1f}s",
-            "ms_per_step": per * 1e3, "dof_per_step": dof}
+    cores = os.cpu_count() if threads_omp else 1
+    return {"value": dof / per, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"3D Kuhn n={n_ref} ({n[3]} tets, {dof} DOF/step), {reps} timed passes in {el:.1f}s on {cores} "
+                      f"thread(s), C restatement of SparseArrays mul! on the reference's Int64-CSC/Int8 storage "
+                      f"(storage built on the CPU in {t_asm:.1f}s)",
+            "ms_per_step": per * 1e3, "dof_per_step": dof, "timed_passes": reps, "n": n_ref, "nsimplices": list(n)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # warmup W passes + K timed steps, each step a bounded sample (n=64)
     import c_oracle
     c_oracle.load()
-    single = cpu_reference_pass(args.n_ref, seconds_target=min(60.0, 2.0 * max(args.steps, 1)))
-    omp = cpu_reference_pass(args.n_ref, seconds_target=min(30.0, 1.0 * max(args.steps, 1)), threads_omp=True)
+    # the SAME configuration as the product arm (n = args.n_ref, default = the product's n = 256): W warm-up passes and
+    # K timed passes, each one whole step of the workload, capped so that the run ends within a few minutes
+    single = cpu_reference_pass(args.n_ref, args.warmup, args.steps, seconds_cap=150.0)
+    omp = cpu_reference_pass(args.n_ref, args.warmup, args.steps, seconds_cap=40.0, threads_omp=True)
     # Julia's SparseArrays mul! is single-threaded whatever JULIA_NUM_THREADS says: one thread IS all the
-    # host threads the reference's own implementation can use, so the line's value is the 1-thread loop.  A
-    # row-parallel OpenMP variant on every host core is timed beside it as a cross-check (not what DDF.jl does).
+    # host threads the reference's own implementation can use, so the line's value is the 1-thread loop.  The
+    # row-parallel OpenMP variant on every host core is reported beside it (not what DDF.jl does).
     res = single
-    # second cross-check: scipy.sparse CSR y = A x on the same matrices (Int8 -> Float64 values)
-    scipy_x = None
-    try:
-        import scipy.sparse as sp
-        import ddf_oracle as o
-        om = o.large_hypercube_manifold(3, (args.n_ref,) * 3)
-        mats = [o.deriv(o.Pr, k, om).astype(np.float64).tocsr() for k in range(3)]
-        xs = [np.random.default_rng(k).random(m_.shape[1]) for k, m_ in enumerate(mats)]
-        stars = [np.random.default_rng(9 + k).random(om.nsimplices(k)) for k in range(4)]
-        xd = [np.random.default_rng(5 + k).random(om.nsimplices(k)) for k in range(4)]
-        t0 = time.time()
-        reps = 0
-        while time.time() - t0 < 3.0:
-            for m_, x_ in zip(mats, xs):
-                m_ @ x_
-            for d_, x_ in zip(stars, xd):
-                d_ * x_
-            reps += 1
-        scipy_x = {"value": single["dof_per_step"] * reps / (time.time() - t0), "cores": 1, "what": "scipy.sparse CSR @ x"}
-    except Exception as e:      # the cross-check must never break the arm
-        scipy_x = {"error": repr(e)}
+    cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    cpu["allcores"] = {"value": omp["value"], "unit": UNIT, "cores": omp["cores"], "sample": omp["sample"],
+                       "note": "row-parallel OpenMP restatement; the reference itself cannot thread this path"}
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE config 4 (3D Kuhn large_hypercube: d0,d1,d2 + star0..3 apply, Float64), "
-                                   f"bounded sample n={args.n_ref}", "reference_runnable": False,
-                       "note": "DDF.jl is Julia; no julia binary in the image -> C restatement of its SparseArrays "
-                               "mul! loops on the reference's storage (Int64 CSC, Int8 values)"},
-            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "scipy_csr_crosscheck": scipy_x,
-            "omp_allcores_crosscheck": {"value": omp["value"], "cores": omp["cores"],
-                                        "note": "row-parallel OpenMP restatement; the reference itself cannot thread this path"},
+            "config": workload_config(args.n_ref, 1, False, res["nsimplices"], res["dof_per_step"]),
+            "timed_passes": res["timed_passes"],
+            "reference_runnable": False,
+            "note": "DDF.jl is Julia; no julia binary in the image -> C restatement of its SparseArrays mul! loops on the "
+                    "reference's storage (Int64 CSC, Int8 values), 1 thread like Julia's sparse mul!",
+            "cpu_baseline": cpu,
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print_json(line)
+
+
+def workload_config(n, N, strong, cnt, dof_total):
+    """`config` of the JSON line: identical for the product arm and the reference arm on the same n at N = 1."""
+    wl = (f"BASELINE config 4: 3D Kuhn large_hypercube n={n}"
+          + ((f", ONE cube cut into {N} z-slabs (config 5 strong scaling)" if strong else
+              f" per GPU, z-slabs of {n * N} layers over {N} GPUs (config 5 weak scaling)") if N > 1 else "")
+          + ": y=d_k x (k=0,1,2) and star_k x (k=0..3), Float64")
+    return {"workload": wl, "nsimplices_local": [int(c) for c in cnt], "dof_per_step": int(dof_total),
+            "l2_hygiene": "inputs larger than the last-level cache (index tables 0.9-2.4 GB, vectors 0.14-1.6 GB; "
+                          "B200 L2 = 126 MB)",
+            "parallelism": "none" if N == 1 else f"z-slabs x{N}, no collective in d_k/star_k apply; "
+                                                 "peer-memory / NCCL halo in the wave step"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -497,8 +516,12 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and N == 1 and not args.no_cpu:
-        cpu = cpu_reference_pass(args.n_ref, seconds_target=12.0)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        # bounded sample of the SAME workload (same n): a few whole passes, 1 thread (what Julia's sparse mul! uses),
+        # and the all-core OpenMP variant beside it
+        c1 = cpu_reference_pass(args.n_ref, 1, 8, seconds_cap=14.0)
+        ca = cpu_reference_pass(args.n_ref, 1, 8, seconds_cap=6.0, threads_omp=True)
+        cpu = {k: c1[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu["allcores"] = {"value": ca["value"], "unit": UNIT, "cores": ca["cores"], "sample": ca["sample"]}
 
     if rank == 0:
         d1_bytes = dk_bytes(cnt[2], cnt[1], 1)
@@ -525,15 +548,7 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.strong and N > 1 else "weak",
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE config 4: 3D Kuhn large_hypercube n={n}"
-                                   + ((f", ONE cube cut into {N} z-slabs (config 5 strong scaling)" if args.strong else
-                                       f" per GPU, z-slabs of {n * N} layers over {N} GPUs (config 5 weak scaling)")
-                                      if N > 1 else "")
-                                   + ": y=d_k x (k=0,1,2) and star_k x (k=0..3), Float64",
-                       "nsimplices_local": cnt, "dof_per_step": int(dof_total),
-                       "l2_hygiene": "inputs larger than L2 (index tables 0.9-2.4 GB, vectors 0.14-1.6 GB vs 126 MB L2)",
-                       "parallelism": "none" if N == 1 else f"z-slabs x{N}, no collective in d_k/star_k apply; "
-                                                            "NCCL send/recv halo in the wave step"},
+            "config": workload_config(n, N, args.strong, cnt, dof_total),
             "roofline": {"bound": "hbm", "kernel": d1_kernel + " (y = d1 x" + d1_note,
                          "achieved": d1_bytes / d1_ms * 1e-6,
                          "peak": peak, "unit": "GB/s", "frac": d1_bytes / d1_ms * 1e-6 / peak, "traffic": traffic,
@@ -578,7 +593,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", "--cells", dest="n", type=int, default=256,
                     help="cells per axis (per GPU along z); use --cells under torchrun (its parser rejects --n)")
-    ap.add_argument("--n-ref", type=int, default=64, help="cells per axis of the CPU sample")
+    ap.add_argument("--n-ref", type=int, default=0, help="cells per axis of the CPU arm (default: the same n as the product arm)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -589,6 +604,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.n_ref <= 0:
+        args.n_ref = args.n
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -42,6 +42,10 @@ class Context:
         self.device = device
         self.rank = 0
         self.nranks = 1
+        # manifolds, cochains and operators hold pointers into this context: close() is deferred until the last of
+        # them is gone (their finalizers call _release)
+        self._live = 0
+        self._closing = False
 
     def sync(self):
         call("ddf_sync", self._h)
@@ -97,8 +101,18 @@ class Context:
         call("ddf_comm_allreduce", self._h, C.byref(v), {"sum": 0, "max": 1, "min": 2}[op])
         return v.value
 
+    def _retain(self):
+        self._live += 1
+
+    def _release(self):
+        self._live -= 1
+        if self._closing and self._live <= 0:
+            self.close()
+
     def close(self):
-        if self._h:
+        """Destroy the context; deferred while manifolds / cochains / operators created on it are alive."""
+        self._closing = True
+        if self._h and self._live <= 0:
             _lib.load().ddf_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -125,6 +139,7 @@ class Manifold:
         self._h = handle
         self.ctx = ctx
         self.name = name
+        ctx._retain()
         D, Cc = C.c_int(), C.c_int()
         call("ddf_mesh_dims", self._h, C.byref(D), C.byref(Cc))
         self.D, self.C = D.value, Cc.value
@@ -243,12 +258,14 @@ class Manifold:
         if self._h and self._live_ops <= 0:
             _lib.load().ddf_mesh_destroy(self._h)
             self._h = C.c_void_p()
+            self.ctx._release()
 
     def __del__(self):
         try:
             if self._h and _lib._lib is not None and self.ctx._h:
                 _lib._lib.ddf_mesh_destroy(self._h)
                 self._h = None
+                self.ctx._release()
         except Exception:
             pass
 
@@ -261,13 +278,15 @@ class Fun:
         self.P = bool(P)
         self.R = int(R)
         n = manifold.nsimplices(R)
+        self._ctx = manifold.ctx
         if _handle is not None:
             self._h = _handle
         else:
             self._h = C.c_void_p()
             call("ddf_vec_create", manifold.ctx._h, n, C.byref(self._h))
-            if values is not None:
-                self.upload(values)
+        self._ctx._retain()
+        if _handle is None and values is not None:
+            self.upload(values)
 
     def __len__(self):
         return self.manifold.nsimplices(self.R)
@@ -375,9 +394,10 @@ class Fun:
 
     def __del__(self):
         try:
-            if self._h and _lib._lib is not None:
+            if self._h and _lib._lib is not None and self._ctx._h:
                 _lib._lib.ddf_vec_destroy(self._h)
                 self._h = None
+                self._ctx._release()
         except Exception:
             pass
 
@@ -410,6 +430,8 @@ class Op:
         self.P1, self.R1, self.P2, self.R2 = bool(P1), int(R1), bool(P2), int(R2)
         self._h = handle
         manifold._live_ops += 1
+        self._ctx = manifold.ctx
+        self._ctx._retain()
 
     @property
     def shape(self):
@@ -498,13 +520,14 @@ class Op:
 
     def __del__(self):
         try:
-            if self._h and _lib._lib is not None:
+            if self._h and _lib._lib is not None and self._ctx._h:
                 _lib._lib.ddf_op_destroy(self._h)
                 self._h = None
                 m = self.manifold
                 m._live_ops -= 1
                 if m._closing and m._live_ops <= 0:
                     m.close()
+                self._ctx._release()
         except Exception:
             pass
 

@@ -274,7 +274,7 @@ __device__ __forceinline__ void stage_issue(const uint32_t* __restrict__ wtab, c
   }
 }
 
-#define PIPE_TD 8               // depth of the run-table ring of the persistent pipelines
+#define PIPE_TD 8               // depth of the run-table ring of the persistent pipelines (even: wavefront2 splits it by task parity)
 
 // one TMA bulk copy global -> shared, completion counted on `mbar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* mbar, uint64_t policy) {

@@ -421,7 +421,7 @@ k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* _
 
 #ifdef DDF_PIPE_TRACE
 // block 0 records %globaltimer at: producer armed stage (0), consumer saw data (1), consumer released stage (2)
-__device__ unsigned long long g_pipe_trace[5 * 1024];
+__device__ unsigned long long g_pipe_trace[8 * 1024];
 #define PIPE_TRACE(kind, it)                                                        \
   do {                                                                              \
     if (blockIdx.x == 0 && (it) < 1024 && (threadIdx.x & 31) == 0) {                \
@@ -596,8 +596,8 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
 }
 
 #ifdef DDF_PIPE_TRACE
-extern "C" __attribute__((visibility("default"))) int ddf_debug_pipe_trace(unsigned long long* out /* 3*1024 */) {
-  return cudaMemcpyFromSymbol(out, g_pipe_trace, sizeof(unsigned long long) * 5 * 1024) == cudaSuccess ? 0 : 1;
+extern "C" __attribute__((visibility("default"))) int ddf_debug_pipe_trace(unsigned long long* out /* 8*1024 */) {
+  return cudaMemcpyFromSymbol(out, g_pipe_trace, sizeof(unsigned long long) * 8 * 1024) == cudaSuccess ? 0 : 1;
 }
 #endif
 

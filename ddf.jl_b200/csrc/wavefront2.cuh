@@ -7,10 +7,15 @@
 // L2 the second time (evict_first).  u ping-pong: step n reads U0 = a.u and writes U1 = a.out1, step n+1 reads U1 and
 // writes U0; v = a.out0 is updated in place by both.  A step-(n+1) task of window w may be staged once every
 // step-n window <= w + reach has finished: blocks count their finished step-n tasks per iteration in `done[it]`
-// (threadfence + one atomic per task), the producer warp polls the counters it needs before it arms the stage.
+// (threadfence + one atomic per task); a WATCHER warp per block follows the counters in order and publishes "every
+// iteration <= k is finished" in shared memory, so the producer warp -- whose time per task is the budget of the whole
+// pipeline -- never waits for an L2 round trip: it compares a shared-memory word before it arms a step-(n+1) stage.
 // With lag >= ceil(reach / B) + 1 a block only ever waits for iterations it has armed itself (no deadlock while all
-// blocks are co-resident: one block per SM, grid <= SM count).
+// blocks are co-resident: one block per SM, grid <= SM count); `slack` more iterations of lag let the blocks drift
+// apart by that much before anyone waits (the price: lag * B windows of entries must stay in L2).
 #pragma once
+
+#define W2_RING 16             // > the most step-n tasks of one block that can be in flight (ring stages)
 
 struct Wave2Task {
   int kind;        // 0 = step n, 1 = step n+1
@@ -45,8 +50,8 @@ struct Wave2Enum {
   }
 };
 
-template <int NG>
-__global__ void __launch_bounds__(NG * PIPE_GROUP + 32, 1)
+template <int NG, int NP>
+__global__ void __launch_bounds__(NG * PIPE_GROUP + 32 * (NP + 2), 1)
 k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __restrict__ packed,
              const unsigned char* __restrict__ meta, int64_t w0, int64_t w1, PipeGeom g, int lag, int reachw,
              uint32_t* __restrict__ done) {
@@ -54,9 +59,15 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
   __shared__ __align__(8) uint64_t full[PIPE_MAX_STAGES], empty[PIPE_MAX_STAGES], tfull[PIPE_TD];
   __shared__ __align__(16) uint32_t tabS[PIPE_TD * STAGE_TAB];
   __shared__ uint32_t issued[PIPE_MAX_STAGES];
+  __shared__ int known_done;                         // every step-n iteration <= known_done is finished on ALL blocks
+  // stored[it % W2_RING] = it + 1 once THIS block's step-n task of iteration `it` has issued all its stores (set by
+  // its consumer group behind a group barrier); the publisher warp turns that into the device-wide count
+  __shared__ int stored[W2_RING];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   if (tid < PIPE_MAX_STAGES) issued[tid] = 0u;
+  if (tid < W2_RING) stored[tid] = 0;
   if (tid == 0) {
+    known_done = -1;
     for (int d = 0; d < PIPE_TD; d++)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tfull[d])) : "memory");
     for (int s = 0; s < g.nstages; s++) {
@@ -68,24 +79,77 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
   __syncthreads();
   const int64_t stride = gridDim.x;
   const int64_t nit = (w1 - w0 + stride - 1) / stride;
+  if (warp == NG * PIPE_GROUP / 32 + NP) {
+    // ------------------------------------------------------------ watcher: iteration q is finished when all its
+    // windows (one per block, fewer in the last iteration) have counted themselves in done[q]
+    if (lane == 0) {
+      for (int64_t q = 0; q < nit; q++) {
+        const int64_t left = (w1 - w0) - q * stride;
+        const uint32_t active = (uint32_t)(left < stride ? left : stride);
+        unsigned long long t0 = 0;
+        for (;;) {
+          uint32_t seen;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + q) : "memory");
+          if (seen >= active) break;
+          // never hang the device: the blocks are co-resident by construction, so a wait of seconds means a broken
+          // schedule -- abort the launch (the host sees a launch failure) instead of spinning for ever
+          unsigned long long t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t0 == 0) t0 = t1;
+          else if (t1 - t0 > 4000000000ull) __trap();
+          __nanosleep(200);
+        }
+        asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(&known_done)), "r"((int)q) : "memory");
+      }
+    }
+    return;
+  }
+  if (warp == NG * PIPE_GROUP / 32 + NP + 1) {
+    // ------------------------------------------------------------ publisher: the device-scope fence that makes a
+    // finished task's stores visible costs a round trip to L2; it is paid here, off the consumers' path.  The
+    // consumers' stores happen-before their group barrier, the barrier before the shared-memory release below, and
+    // this thread's fence is cumulative over what it has observed (PTX memory model, causality order).
+    if (lane == 0) {
+      for (int64_t q = 0; q < nit; q++) {
+        if (w0 + blockIdx.x + q * stride >= w1) break;
+        for (;;) {
+          int seen;
+          asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&stored[q % W2_RING])) : "memory");
+          if (seen >= (int)q + 1) break;          // slots only grow: a later task in the slot implies this one
+          __nanosleep(32);
+        }
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(done + q) : "memory");
+      }
+    }
+    return;
+  }
   double* const U0 = const_cast<double*>(a.u);       // step n input, step n+1 output
   double* const U1 = a.out1;                         // step n output, step n+1 input
   double* const V = a.out0;
-  if (warp == NG * PIPE_GROUP / 32) {
-    // ------------------------------------------------------------ producer warp
+  if (warp >= NG * PIPE_GROUP / 32 && warp < NG * PIPE_GROUP / 32 + NP) {
+    // ------------------------------------------------------------ NP producer warps: warp p arms the tasks p mod NP
+    // (one warp spends ~1.3 us per task on its ~7 bulk requests and the bookkeeping around them -- more than the
+    // consumers need for a window; the stages, the table ring slots (NP divides PIPE_TD) and the dependency check of a
+    // task belong to exactly one of the two, so they never touch the same barrier phase)
+    const uint32_t ppar = warp - NG * PIPE_GROUP / 32;
     const uint64_t pol_keep = make_policy_evict_last(), pol_stream = make_policy_evict_first();
     Wave2Enum ahead(nit, lag, w0, w1, stride, blockIdx.x), cur(nit, lag, w0, w1, stride, blockIdx.x);
     Wave2Task t;
+    int64_t aidx = 0;                                  // tasks taken from `ahead` so far
     if (lane == 0) {
       for (int d = 0; d < PIPE_TD; d++) {
         Wave2Task ta;
-        if (ahead.next(ta)) {
+        const bool ok = ahead.next(ta);
+        aidx++;
+        if (ok && (uint32_t)(d % NP) == ppar) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tfull[d])), "r"(STAGE_TAB * 4) : "memory");
           bulk_g2s(tabS + d * STAGE_TAB, tab + ta.win * STAGE_TAB, STAGE_TAB * 4, &tfull[d], pol_keep);
         }
       }
     }
     for (int64_t pit = 0; cur.next(t); pit++) {
+      if ((uint32_t)(pit % NP) != ppar) continue;
       const int td = (int)(pit % PIPE_TD);
       stage_wait(&tfull[td], (uint32_t)(pit / PIPE_TD) & 1u);
       const uint32_t* wt = tabS + td * STAGE_TAB;
@@ -93,45 +157,33 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
       const uint32_t start = lane < STAGE_RMAX ? wt[4 + 2 * lane] : 0u, off = lane < STAGE_RMAX ? wt[5 + 2 * lane] : 0u;
       const uint32_t end = lane + 1 < nruns ? wt[5 + 2 * (lane + 1)] : total;
       __syncwarp();
-      if (lane == 0) {                                                      // refill this table slot
+      if (lane == 0) {                                                      // refill this table slot with task pit + PIPE_TD
         Wave2Task ta;
-        if (ahead.next(ta)) {
+        bool ok = true;
+        while (ok && aidx <= pit + PIPE_TD) { ok = ahead.next(ta); aidx++; }
+        if (ok) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tfull[td])), "r"(STAGE_TAB * 4) : "memory");
           bulk_g2s(tabS + td * STAGE_TAB, tab + ta.win * STAGE_TAB, STAGE_TAB * 4, &tfull[td], pol_keep);
         }
       }
+      PIPE_TRACE(7, pit);
       if (t.kind == 1) {
-        // every step-n window <= win + reachw must be finished.  A block's consumer groups take the tasks alternately,
-        // so its step-n tasks may finish out of order -- but never by more than the ring holds (a task is armed only
-        // after the task nstages before it released its stage): the iteration that holds window win + reachw and the
-        // nstages - 1 before it are checked, everything older is implied.
+        // every step-n window <= win + reachw must be finished (on any block): the watcher says up to which iteration
         int64_t need = ((t.win - w0) + reachw) / stride;
         if (need > nit - 1) need = nit - 1;
-        if (lane == 0) {
-          for (int64_t q = need; q >= 0 && q > need - g.nstages; q--) {
-            const int64_t left = (w1 - w0) - q * stride;
-            const uint32_t active = (uint32_t)(left < stride ? left : stride);
-            uint32_t seen;
-            unsigned long long t0 = 0;
-            for (;;) {
-              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + q) : "memory");
-              if (seen >= active) break;
-              // never hang the device: the blocks are co-resident by construction, so a wait of seconds means a
-              // broken schedule -- abort the launch (the host sees a launch failure) instead of spinning for ever
-              unsigned long long t1;
-              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-              if (t0 == 0) t0 = t1;
-              else if (t1 - t0 > 4000000000ull) __trap();
-              __nanosleep(64);
-            }
-          }
+        for (;;) {
+          int seen;
+          asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&known_done)) : "memory");
+          if ((int64_t)seen >= need) break;
+          __nanosleep(32);
         }
         __syncwarp();
         asm volatile("fence.proxy.async.global;" ::: "memory");             // generic-proxy stores of U1 / V -> our bulk reads
       }
       const int s = (int)(pit % g.nstages);
       const uint32_t j = (uint32_t)(pit / g.nstages);
+      PIPE_TRACE(5, pit);
       if (j > 0) stage_wait(&empty[s], (j - 1) & 1u);
       unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
       const int64_t r0 = t.win * g.K * DDF_SELL_WIN;
@@ -143,6 +195,7 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(tx) : "memory");
         asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&issued[s])), "r"((uint32_t)pit + 1u) : "memory");
       }
+      PIPE_TRACE(0, pit);
       __syncwarp();
       const double* uin = t.kind ? U1 : U0;
       // first touch of a window's entries keeps them in L2 for the second step, the second touch lets them go
@@ -154,6 +207,7 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
         bulk_g2s(sb + g.o_v, V + r0, vbytes, &full[s], pol_stream);
         bulk_g2s(sb + g.o_u, uin + r0, vbytes, &full[s], pol_keep);
       }
+      PIPE_TRACE(6, pit);
     }
   } else {
     // ------------------------------------------------------------ consumer groups: group k takes tasks k, k + NG, ...
@@ -170,7 +224,9 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
         asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&issued[s])) : "memory");
         if (seen >= (uint32_t)pit + 1u) break;
       }
+      PIPE_TRACE(3, pit);
       stage_wait(&full[s], j & 1u);
+      PIPE_TRACE(1, pit);
       const unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
       const double* stage = reinterpret_cast<const double*>(sb);
       double* const uout = t.kind ? U0 : U1;
@@ -208,12 +264,13 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
         }
       }
       __syncwarp();
+      PIPE_TRACE(2, pit);
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
       if (t.kind == 0) {
-        // publish: every thread's stores of this task are visible device-wide before the count moves
-        __threadfence();
+        // hand the task to the publisher: all stores of the group issued (group barrier), then one shared-memory flag
         asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)grp), "r"(PIPE_GROUP) : "memory");
-        if (gtid == 0) atomicAdd(done + t.it, 1u);
+        if (gtid == 0)
+          asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(&stored[t.it % W2_RING])), "r"((int)t.it + 1) : "memory");
       }
     }
   }
@@ -259,13 +316,16 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, 
     m->wave2_reach = (int64_t)h;
   }
   const int reachw = (int)(m->wave2_reach / gw) + 2;
-  const int lag = (reachw + grid - 1) / grid + 1;
+  // tuning bits 18-21 of "wave": extra iterations of lag (default 4)
+  const int slack_t = (m->ctx->tune.wave >> 18) & 15;
+  const int slack = slack_t ? slack_t - 1 : 4;
+  const int lag = (reachw + grid - 1) / grid + 1 + slack;
   const int64_t nit = (g1 - g0 + grid - 1) / grid;
   // worth it only when the wavefront is short against the sweep: the windows between the two steps must stay in L2
   // (lag * grid windows of entries) and the first / last `lag` iterations run one step only
   if (nit < 4 * (int64_t)lag) return 0;
   const int64_t held = (int64_t)lag * grid * (int64_t)sb.max_entries * 10;
-  if (held > (int64_t)48 << 20) return 0;
+  if (held > (int64_t)64 << 20) return 0;
   if ((int64_t)m->wave2_done.n < nit) DDF_CHECK(m->wave2_done.alloc(m->ctx, (size_t)nit));
   DDF_CUDA(cudaMemsetAsync(m->wave2_done.p, 0, (size_t)nit * 4, stream));
   RowArgs a{};
@@ -277,9 +337,21 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, 
   a.row1 = nv;
   a.isb = m->isbnd[0].p;
   const size_t smem_p = (size_t)g.nstages * g.stage_bytes;
-  DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-  k_rows_pipe2<2><<<grid, 2 * PIPE_GROUP + 32, smem_p, stream>>>(a, sb.tab.p, sb.packed.p, sb.meta.p, g0, g1, g, lag,
-                                                                 reachw, m->wave2_done.p);
+  if (getenv("DDF_DEBUG"))
+    fprintf(stderr, "[ddf] k_rows_pipe2: %d stages x %u B (slots %u, entries %u), grid %d, reach %lld rows = %d windows, lag %d, nit %lld\n",
+            g.nstages, g.stage_bytes, sb.max_slots, sb.max_entries, grid, (long long)m->wave2_reach, reachw, lag, (long long)nit);
+  const int np = (m->ctx->tune.wave >> 22) & 7;      // tuning bits 22-24: producer warps (0 = default)
+#define DDF_PIPE2_LAUNCH(NPV)                                                                                          \
+  do {                                                                                                                 \
+    DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe2<2, NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));     \
+    k_rows_pipe2<2, NPV><<<grid, 2 * PIPE_GROUP + 32 * (NPV + 2), smem_p, stream>>>(a, sb.tab.p, sb.packed.p, sb.meta.p, \
+                                                                                   g0, g1, g, lag, reachw,              \
+                                                                                   m->wave2_done.p);                    \
+  } while (0)
+  if (np == 1) DDF_PIPE2_LAUNCH(1);
+  else if (np == 4) DDF_PIPE2_LAUNCH(4);
+  else DDF_PIPE2_LAUNCH(2);
+#undef DDF_PIPE2_LAUNCH
   DDF_LAUNCH_CHECK(m->ctx);
   *ran = true;
   return 0;

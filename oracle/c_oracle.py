@@ -94,3 +94,39 @@ def calc_faces_boundaries(simplices: np.ndarray):
     nf = lib.ddf_calc_faces_boundaries(C.c_int64(n), C.c_int(N), _p(s, C.c_int64), _p(faces, C.c_int64),
                                        _p(colptr, C.c_int64), _p(rowval, C.c_int64), _p(nzval, C.c_int8))
     return faces[:nf].copy(), colptr, rowval, nzval
+
+
+def calc_faces_boundaries_linear(simplices: np.ndarray, nvertices: int):
+    """Same outputs as calc_faces_boundaries (the reference's 1-based CSC) from the linear-time bucket variant
+    (ddf_calc_faces_boundaries_linear): what builds the n = 256 storage of the CPU baseline."""
+    lib = load()
+    lib.ddf_calc_faces_boundaries_linear.restype = C.c_int64
+    s = np.ascontiguousarray(simplices, dtype=np.int64)
+    n, N = s.shape
+    faces = np.empty((n * N, N - 1), dtype=np.int64)
+    colptr = np.empty(n + 1, dtype=np.int64)
+    rowval = np.empty(n * N, dtype=np.int64)
+    nzval = np.empty(n * N, dtype=np.int8)
+    nf = lib.ddf_calc_faces_boundaries_linear(C.c_int64(n), C.c_int(N), C.c_int64(nvertices), _p(s, C.c_int64),
+                                              _p(faces, C.c_int64), _p(colptr, C.c_int64), _p(rowval, C.c_int64),
+                                              _p(nzval, C.c_int8))
+    if nf == -1:
+        return calc_faces_boundaries(simplices)
+    if nf < 0:
+        raise MemoryError("ddf_calc_faces_boundaries_linear: out of memory")
+    out = np.empty((nf, N - 1), dtype=np.int64)
+    out[:] = faces[:nf]
+    del faces
+    return out, colptr, rowval, nzval
+
+
+def kuhn3_table(n: int, block: np.ndarray) -> np.ndarray:
+    """Simplex table of large_hypercube_manifold(Val(3); nelts = (n, n, n)) from the 48-tetrahedron mirrored Kuhn
+    block (corner offsets in {0, 1, 2}; taken from the oracle's own generator, ddf_oracle.symmetric_hypercube)."""
+    lib = load()
+    lib.ddf_kuhn3_table.restype = None
+    b = np.ascontiguousarray(block, dtype=np.int8)
+    assert b.shape == (48, 4, 3) and n % 2 == 0
+    out = np.empty((6 * n ** 3, 4), dtype=np.int64)
+    lib.ddf_kuhn3_table(C.c_int64(n), _p(b, C.c_int8), _p(out, C.c_int64))
+    return out

@@ -512,3 +512,70 @@ def test_poisson_exact_solution_reference_notebook():
     r = 3e-3
     ser = r ** 2 / (8 * np.pi * sigma ** 2) - r ** 4 / (64 * np.pi * sigma ** 4)
     assert abs(o.poisson_u_exact(x)[0] - ser) < 1e-9 * abs(ser) + (r / sigma) ** 6
+
+
+def test_handwritten_cube_of_24_tetrahedra():
+    """test/test-topologies.jl:78-107: the cube cut into 24 tetrahedra around its centre (8 corners, 6 face centres,
+    the body centre; vertex names p000 ... p111 are 1..15 in the order written there).  Counts by Euler's formula,
+    boundary o boundary = 0 (checkboundary2), every interior triangle shared by two tetrahedra, the boundary the 24
+    triangles of the 6 faces."""
+    p000, p002, p020, p022, p200, p202, p220, p222, p110, p112, p101, p121, p011, p211, p111 = range(15)
+    tets = np.array([(p000, p020, p110, p111), (p020, p220, p110, p111), (p220, p200, p110, p111), (p200, p000, p110, p111),
+                     (p002, p022, p112, p111), (p022, p222, p112, p111), (p222, p202, p112, p111), (p202, p002, p112, p111),
+                     (p000, p002, p101, p111), (p002, p202, p101, p111), (p202, p200, p101, p111), (p200, p000, p101, p111),
+                     (p020, p022, p121, p111), (p022, p222, p121, p111), (p222, p220, p121, p111), (p220, p020, p121, p111),
+                     (p000, p002, p011, p111), (p002, p022, p011, p111), (p022, p020, p011, p111), (p020, p000, p011, p111),
+                     (p200, p202, p211, p111), (p202, p222, p211, p111), (p222, p220, p211, p111), (p220, p200, p211, p111)])
+    xyz = {"0": 0.0, "1": 0.5, "2": 1.0}
+    names = ["000", "002", "020", "022", "200", "202", "220", "222", "110", "112", "101", "121", "011", "211", "111"]
+    coords = np.array([[xyz[c] for c in nm] for nm in names])
+    m = o.build_manifold("cube", tets, coords)
+    n = [m.nsimplices(R) for R in range(4)]
+    assert n[0] == 15 and n[3] == 24
+    assert n[0] - n[1] + n[2] - n[3] == 1                      # Euler characteristic of a ball
+    assert n[2] == (4 * 24 + 24) // 2 and n[1] == 50           # 24 boundary triangles; 12 cube edges + 24 face diagonals + 8 + 6
+    for R in (2, 3):
+        z = m.boundaries[R - 1].astype(np.int64) @ m.boundaries[R].astype(np.int64)
+        assert z.nnz == 0 or np.abs(z.data).max() == 0
+    per_face = np.asarray(abs(m.boundaries[3]).sum(axis=1)).reshape(-1)
+    assert sorted(set(per_face.tolist())) == [1, 2] and int((per_face == 1).sum()) == 24
+    assert o.calc_isboundary(m, 2).sum() == 24 and o.calc_isboundary(m, 0).sum() == 14     # all but the body centre
+    assert abs(o.calc_volumes(m, 3).sum() - 1.0) < 1e-15 and np.allclose(o.calc_volumes(m, 3), 1.0 / 24)
+    # the C twin and its linear-time variant give the same matrices
+    import c_oracle
+    tab = m.simplices[3]
+    for R in (3, 2, 1):
+        a = c_oracle.calc_faces_boundaries(tab)
+        b = c_oracle.calc_faces_boundaries_linear(tab, 15)
+        ref = o.to_julia_csc(m.boundaries[R])
+        for x, y, zz in zip(a[1:], b[1:], ref):
+            assert np.array_equal(x, y) and np.array_equal(x, zz)
+        assert np.array_equal(a[0], m.simplices[R - 1]) and np.array_equal(b[0], m.simplices[R - 1])
+        tab = a[0]
+
+
+def test_linear_assembly_equals_literal_restatement():
+    """oracle/ddf_oracle.c: the linear-time face ranking that builds the CPU baseline's n = 256 storage against the
+    literal comparison-sort restatement of Manifolds.jl:717-768 and the numpy oracle -- Kuhn, Delaunay (scattered
+    numbering, long buckets) and a fan with one very high-valence vertex; and the C Kuhn table against the oracle's."""
+    import c_oracle
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(11)
+    pts = rng.random((3000, 3))
+    k = 3000
+    fan = np.stack([np.zeros(k, dtype=np.int64), 1 + np.arange(k), 1 + (np.arange(k) + 1) % k], axis=1)[rng.permutation(k)]
+    cases = [(o.large_hypercube_tables(3, (6, 6, 6))[0], 7 ** 3), (o.large_hypercube_tables(2, (10, 10))[0], 121),
+             (np.sort(np.asarray(Delaunay(pts).simplices, dtype=np.int64), axis=1), 3000), (np.sort(fan, axis=1), k + 1)]
+    for tab, V in cases:
+        while tab.shape[1] >= 2:
+            a = c_oracle.calc_faces_boundaries(tab)
+            b = c_oracle.calc_faces_boundaries_linear(tab, V)
+            faces, B = o.calc_faces_boundaries(tab, V)
+            for x, y, zz in zip(a[1:], b[1:], o.to_julia_csc(B)):
+                assert np.array_equal(x, y) and np.array_equal(x, zz)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[0], faces)
+            tab = a[0]
+            if tab.shape[1] == 1:
+                break
+    for n in (2, 6):
+        assert np.array_equal(c_oracle.kuhn3_table(n, o.symmetric_hypercube(3)), o.large_hypercube_tables(3, (n,) * 3)[0])
