@@ -54,6 +54,8 @@ SIGNATURES = {
     "ddf_mesh_dims": [_P, _intp, _intp],
     "ddf_mesh_get_simplices_csc": [_P, _int, _i64p, _i64p],
     "ddf_mesh_get_boundary_csc": [_P, _int, _i64p, _i64p, _i8p],
+    "ddf_mesh_get_lookup_csc": [_P, _int, _int, _i64p, _i64p, _i64p],
+    "ddf_mesh_refine_coords": [_P, _f64p],
     "ddf_mesh_geometry": [_P, _int, _int],
     "ddf_mesh_get_coords": [_P, _f64p],
     "ddf_mesh_get_weights": [_P, _f64p],

@@ -210,6 +210,23 @@ class Manifold:
         return sp.csc_matrix((nzval, rowval - 1, colptr - 1),
                              shape=(self.nsimplices(R - 1), self.nsimplices(R)))
 
+    def get_lookup(self, Ri: int, Rj: int):
+        """get_lookup(mfd, Ri, Rj) (Manifolds.jl:455-498) as a scipy CSC pattern matrix (n_Ri x n_Rj, values 1)."""
+        import scipy.sparse as sp
+        nnz = C.c_int64()
+        call("ddf_mesh_get_lookup_csc", self._h, int(Ri), int(Rj), C.byref(nnz), None, None)
+        colptr = np.empty(self.nsimplices(Rj) + 1, dtype=np.int64)
+        rowval = np.empty(nnz.value, dtype=np.int64)
+        call("ddf_mesh_get_lookup_csc", self._h, int(Ri), int(Rj), C.byref(nnz), _i64p(colptr), _i64p(rowval))
+        return sp.csc_matrix((np.ones(nnz.value, dtype=np.int8), rowval - 1, colptr - 1),
+                             shape=(self.nsimplices(Ri), self.nsimplices(Rj)))
+
+    def refine_coords(self) -> np.ndarray:
+        """refine_coords(get_lookup(mfd, 0, 1), get_coords(mfd)) (Meshing.jl:127-146), computed on the device."""
+        out = np.empty((self.nsimplices(0) + self.nsimplices(1), self.C))
+        call("ddf_mesh_refine_coords", self._h, _f64p(out))
+        return out
+
     def _geometry(self):
         call("ddf_mesh_geometry", self._h, 1, 1 if self.use_weighted_duals else 0)
 

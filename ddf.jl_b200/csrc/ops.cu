@@ -2472,7 +2472,8 @@ static int materialise(OpNode* n, Coo& c) {
     return coo_chop(ctx, c);
   }
   if (n->kind == OPK_LAPLACE0) {
-    DDF_CHECK(ddf_laplace0_to_coo(m, c.row, c.col, c.val, &c.nnz));
+    DDF_CHECK(ddf_laplace0_to_coo(m, c.row, c.col, c.val, &c.nnz));      // row order
+    DDF_CHECK(coo_sort_by_col(ctx, c, n->ncols));                          // stable: rows stay ascending inside a column
     return coo_chop(ctx, c);
   }
   if (n->kind == OPK_CHAIN && !n->tree_ops.empty()) {

@@ -687,21 +687,16 @@ int ddf_laplace0_apply(ddf_mesh* m, const double* x, double* y) {
   return launch_rows<0>(m, m->ctx->stream, a);
 }
 
-// assembled L as COO in CSC order.  Column j of L holds L[i,j] for the neighbours i of j:
-// the value stored in ROW i at column j.
+// assembled L as COO in ROW order (row i: its stored entries, columns ascending); the caller sorts by column.
+// (Taking column j's entries from row j's neighbour list -- "the pattern is symmetric" -- loses L[i,j] when the chop
+// removed L[j,i] but kept L[i,j]: the two are different products ih0[i] * star1[e], ih0[j] * star1[e].)
 __global__ void k_laplace0_coo(const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
                                const double* __restrict__ lval, int64_t nv, int32_t* __restrict__ row,
                                int32_t* __restrict__ col, double* __restrict__ val) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nv) return;
-  // the pattern is symmetric (L[i,j] kept <=> L[j,i] kept only if both ih are kept; handle the general
-  // case by searching row i for column j and writing 0 when it is absent -- chopped later)
-  for (uint32_t p = rowptr[j]; p < rowptr[j + 1]; p++) {
-    const int32_t i = nbr[p];
-    double v = 0.0;
-    for (uint32_t q = rowptr[i]; q < rowptr[i + 1]; q++)
-      if (nbr[q] == (int32_t)j) { v = lval[q]; break; }
-    row[p] = i; col[p] = (int32_t)j; val[p] = v;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  for (uint32_t p = rowptr[i]; p < rowptr[i + 1]; p++) {
+    row[p] = (int32_t)i; col[p] = nbr[p]; val[p] = lval[p];
   }
 }
 
@@ -784,7 +779,7 @@ int ddf_step_launch(ddf_mesh* m, cudaStream_t stream, int kind, const double* u,
 
 #include "wavefront2.cuh"      // two leapfrog steps per launch with a wavefront through L2
 #ifndef DDF_WAVE2_DEFAULT
-#define DDF_WAVE2_DEFAULT 0    // flipped to 1 once the two-step kernel is measured faster on the device (profiles/)
+#define DDF_WAVE2_DEFAULT 1    // measured at C4: 0.464 ms per step against 0.490 ms with one step per launch (profiles/r02_tuning.md)
 #endif
 
 int ddf_leapfrog_launch(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,

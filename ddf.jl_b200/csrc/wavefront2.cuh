@@ -184,7 +184,17 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
       const int s = (int)(pit % g.nstages);
       const uint32_t j = (uint32_t)(pit / g.nstages);
       PIPE_TRACE(5, pit);
-      if (j > 0) stage_wait(&empty[s], (j - 1) & 1u);
+      if (j > 0) {
+        // The previous use of this stage was armed by ANOTHER producer warp.  A parity wait entered before that use
+        // has even been armed would look at the phase before it and pass at once (same aliasing as on the consumer
+        // side): first see the previous use armed, then wait for its release.
+        for (;;) {
+          uint32_t seen;
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&issued[s])) : "memory");
+          if (seen >= (uint32_t)(pit - g.nstages) + 1u) break;
+        }
+        stage_wait(&empty[s], (j - 1) & 1u);
+      }
       unsigned char* sb = pipe_smem + (size_t)s * g.stage_bytes;
       const int64_t r0 = t.win * g.K * DDF_SELL_WIN;
       const uint32_t nr = (uint32_t)min((int64_t)g.K * DDF_SELL_WIN, g.nrows - r0);
@@ -316,7 +326,7 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, 
     m->wave2_reach = (int64_t)h;
   }
   const int reachw = (int)(m->wave2_reach / gw) + 2;
-  // tuning bits 18-21 of "wave": extra iterations of lag (default 4)
+  // tuning bits 18-21 of "wave": extra iterations of lag (default 4: measured best at C4, profiles/r02_tuning.md)
   const int slack_t = (m->ctx->tune.wave >> 18) & 15;
   const int slack = slack_t ? slack_t - 1 : 4;
   const int lag = (reachw + grid - 1) / grid + 1 + slack;
@@ -341,12 +351,22 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, 
     fprintf(stderr, "[ddf] k_rows_pipe2: %d stages x %u B (slots %u, entries %u), grid %d, reach %lld rows = %d windows, lag %d, nit %lld\n",
             g.nstages, g.stage_bytes, sb.max_slots, sb.max_entries, grid, (long long)m->wave2_reach, reachw, lag, (long long)nit);
   const int np = (m->ctx->tune.wave >> 22) & 7;      // tuning bits 22-24: producer warps (0 = default)
+  // COOPERATIVE launch: the blocks wait for each other's step-n windows, so all of them must be resident at once.
+  // One block per SM and grid <= SM count make that true on an idle device; the cooperative launch makes the driver
+  // guarantee it (or refuse the launch) when other work shares the GPU.  A refused launch falls back to one step per
+  // launch (*ran stays false).
+  const uint32_t* tab_p = sb.tab.p;
+  const unsigned char *packed_p = sb.packed.p, *meta_p = sb.meta.p;
+  int64_t g0v = g0, g1v = g1;
+  int lagv = lag, reachv = reachw;
+  uint32_t* done_p = m->wave2_done.p;
+  void* kargs[] = {&a, &tab_p, &packed_p, &meta_p, &g0v, &g1v, &g, &lagv, &reachv, &done_p};
 #define DDF_PIPE2_LAUNCH(NPV)                                                                                          \
   do {                                                                                                                 \
     DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe2<2, NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));     \
-    k_rows_pipe2<2, NPV><<<grid, 2 * PIPE_GROUP + 32 * (NPV + 2), smem_p, stream>>>(a, sb.tab.p, sb.packed.p, sb.meta.p, \
-                                                                                   g0, g1, g, lag, reachw,              \
-                                                                                   m->wave2_done.p);                    \
+    cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_rows_pipe2<2, NPV>, dim3(grid),                        \
+                                                 dim3(2 * PIPE_GROUP + 32 * (NPV + 2)), kargs, smem_p, stream);         \
+    if (le != cudaSuccess) { cudaGetLastError(); return 0; }                                                           \
   } while (0)
   if (np == 1) DDF_PIPE2_LAUNCH(1);
   else if (np == 4) DDF_PIPE2_LAUNCH(4);

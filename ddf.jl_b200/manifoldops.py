@@ -178,14 +178,12 @@ def delaunay_mesh(coords: np.ndarray) -> np.ndarray:
 
 def refined_manifold(mfd0: Manifold) -> Manifold:
     """refined_manifold(mfd0; optimize_mesh=false) (ManifoldConstructors.jl:521-529):
-    old vertices + edge midpoints in edge-id order (Meshing.jl:127-146), Delaunay,
-    zero weights.  Host-side mesh input; the face assembly runs on the device."""
+    old vertices + edge midpoints in edge-id order (Meshing.jl:127-146, on the device), Delaunay (scipy Qhull on the
+    host, exactly the reference's Delaunay.jl -> PyCall -> scipy backend), zero weights; the face assembly runs on the
+    device."""
     if mfd0.D == 0:
         return mfd0
-    coords = mfd0.get_coords()
-    edges = mfd0.get_simplices(1)
-    mid = (coords[edges[:, 0]] + coords[edges[:, 1]]) / 2
-    newc = np.concatenate([coords, mid], axis=0)
+    newc = mfd0.refine_coords()          # device: old vertices + edge midpoints in edge-id order
     return Manifold.from_simplices("refined " + mfd0.name, delaunay_mesh(newc), newc, ctx=mfd0.ctx)
 
 

@@ -109,6 +109,13 @@ int ddf_mesh_get_simplices_csc(ddf_mesh* mesh, int R, int64_t* colptr, int64_t* 
 /* get_boundaries(mfd, R).op (src/Manifolds.jl:443-450): n_{R-1} x n_R, Int8 values */
 int ddf_mesh_get_boundary_csc(ddf_mesh* mesh, int R, int64_t* colptr,
                               int64_t* rowval, int8_t* nzval);
+/* get_lookup(mfd, Ri, Rj).op (src/Manifolds.jl:455-498): the n_Ri x n_Rj index-only (`One`) incidence pattern --
+ * Ri == 0: the vertex tables, Ri == Rj: identity, Ri < Rj: sub-simplices (|boundaries| and its chains), Ri > Rj: the
+ * transpose -- as 1-based Int64 CSC with rows ascending.  Call with colptr == NULL to query nnz. */
+int ddf_mesh_get_lookup_csc(ddf_mesh* mesh, int Ri, int Rj, int64_t* nnz, int64_t* colptr, int64_t* rowval);
+/* refine_coords(get_lookup(mfd,0,1), get_coords(mfd)) (src/Meshing.jl:127-146; ManifoldConstructors.jl:523): the old
+ * vertices followed by the edge midpoints in edge-id order, (n_0 + n_1) rows of C doubles */
+int ddf_mesh_refine_coords(ddf_mesh* mesh, double* out);
 /* calc_volumes / weighted calc_dualcoords / circumcentric calc_dualvolumes
  * (src/Manifolds.jl:834-855, :896-913, :1160-1223) for all R. */
 int ddf_mesh_geometry(ddf_mesh* mesh, int dualkind, int use_weighted_duals);

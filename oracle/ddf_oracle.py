@@ -538,6 +538,33 @@ def calc_isboundary(mfd: Manifold, R: int) -> np.ndarray:
 # --------------------------------------------------------------------------- #
 # chop / dnz  (src/Ops.jl:36-58)
 # --------------------------------------------------------------------------- #
+def calc_lookup(mfd: Manifold, Ri: int, Rj: int) -> sp.csc_matrix:
+    """get_lookup(mfd, Ri, Rj) (Manifolds.jl:455-498) as an n_Ri x n_Rj int8 pattern matrix: the reference's own chain
+    -- Ri == 0: the simplex definitions (:479-481); Ri == Rj: identity (:482-485); Ri == Rj - 1: |boundaries[Rj]|
+    (:486-488); Ri < Rj - 1: pattern of lookup(Ri, Rj-1) * lookup(Rj-1, Rj) (:489-493); else the transpose (:494-496)."""
+    assert 0 <= Ri <= mfd.D and 0 <= Rj <= mfd.D
+    key = ("lookup", Ri, Rj)
+    if key in mfd._cache:
+        return mfd._cache[key]
+    ni, nj = mfd.nsimplices(Ri), mfd.nsimplices(Rj)
+    if Ri == 0:
+        S = mfd.simplices[Rj]
+        A = sp.csc_matrix((np.ones(S.size, dtype=np.int8), S.reshape(-1), (Rj + 1) * np.arange(nj + 1)), shape=(ni, nj))
+    elif Ri == Rj:
+        A = sp.identity(ni, dtype=np.int8, format="csc")
+    elif Ri == Rj - 1:
+        A = abs(mfd.boundaries[Rj]).astype(np.int8).tocsc()
+    elif Ri < Rj - 1:
+        P = (calc_lookup(mfd, Ri, Rj - 1).astype(np.int64) @ calc_lookup(mfd, Rj - 1, Rj).astype(np.int64)).tocsc()
+        P.data = np.ones_like(P.data)
+        A = P.astype(np.int8)
+    else:
+        A = calc_lookup(mfd, Rj, Ri).T.tocsc()
+    A.sort_indices()
+    mfd._cache[key] = A
+    return A
+
+
 def chop_sparse(A: sp.spmatrix) -> sp.csc_matrix:
     """dnz for float sparse matrices: zero entries with abs2 < sqrt(eps^3),
     then dropzeros! (Ops.jl:44-46)."""

@@ -493,7 +493,7 @@ def test_op_fun_algebra(ddf, pairs):
     assert d0.adjoint().shape == (om.nsimplices(0), om.nsimplices(1))
     h = ddf.Fun(dm, ddf.Pr, 1, rng.integers(-9, 9, om.nsimplices(1)).astype(float))
     # <d0 f, h> == <f, d0' h> exactly on integers
-    assert (d0 * f).dot(h) == f.dot(d0.adjoint() * h)
+    assert (d0 * f).vdot(h) == f.vdot(d0.adjoint() * h)      # plain Euclidean products (Fun.dot is the weighted one)
     E, B = ddf.one(ddf.Pr, 0, dm), ddf.isboundary(ddf.Pr, 0, dm)
     m = 1.0 - om_isb(om)
     assert np.array_equal(((E - B) * f).values, m * f.values)   # wave.jl:93

@@ -17,6 +17,15 @@ import torch.distributed as dist  # noqa: E402
 import ddf.jl_b200 as ddf  # noqa: E402
 
 
+def global_field(seed, slab, nelts, D):
+    """This slab's part of ONE random vertex field of the undivided mesh (same numbers on every rank for a given
+    seed): non-symmetric and non-zero on the interface planes, unlike prod sin(pi x) whose zeros sit exactly there."""
+    total = int(np.prod([n + 1 for n in nelts]))
+    g = np.random.default_rng(seed).standard_normal(total)
+    lo = slab.z_cell_lo * slab.plane
+    return g[lo:lo + slab.n_local_planes * slab.plane].copy(), g
+
+
 def main():
     rank = int(os.environ["RANK"])
     local = int(os.environ["LOCAL_RANK"])
@@ -31,8 +40,10 @@ def main():
     for tune, (D, nelts, nsteps) in [(t, c) for t in (0, 1024) for c in cases]:
         ddf._lib.call("ddf_set_tuning", b"wave", tune)       # 0: fused peer-memory halo, 1024: NCCL send/recv
         mfd, slab = ddf.dist.slab_hypercube(D, nelts, ctx)
-        u = ddf.sample(mfd, "wave")
-        v = ddf.Fun(mfd, ddf.Pr, 0)
+        lu, gu = global_field(100 + D, slab, nelts, D)
+        lv, gv = global_field(200 + D, slab, nelts, D)
+        u = ddf.Fun(mfd, ddf.Pr, 0, lu)
+        v = ddf.Fun(mfd, ddf.Pr, 0, lv)
         dt = ctx.allreduce(ddf.wave_dt(mfd), "min")
         # several calls with odd and even step counts: the ping-pong buffers swap roles between calls
         done = 0
@@ -47,8 +58,8 @@ def main():
         dist.all_gather_object(parts, mine)
         if rank == 0:
             full = ddf.large_hypercube_manifold(D, nelts, ctx=ctx, hdiv=nelts[0])
-            fu = ddf.sample(full, "wave")
-            fv = ddf.Fun(full, ddf.Pr, 0)
+            fu = ddf.Fun(full, ddf.Pr, 0, gu)
+            fv = ddf.Fun(full, ddf.Pr, 0, gv)
             fdt = ddf.wave_dt(full)
             ddf.wave_leapfrog_single = None
             ddf._lib.call("ddf_wave_leapfrog", full._h, fu._h, fv._h, float(dt), int(nsteps))
@@ -67,7 +78,9 @@ def main():
     for tune, (D, nelts, nsw) in [(t, c) for t in (0, 1024) for c in ((3, (8, 8, 8 * world), 7), (3, (32, 32, 8 * world), 4))]:
         ddf._lib.call("ddf_set_tuning", b"wave", tune)
         mfd, slab = ddf.dist.slab_hypercube(D, nelts, ctx)
-        u, rho = ddf.sample(mfd, "wave"), ddf.sample(mfd, "poisson_rho")
+        lu, gu = global_field(300 + D, slab, nelts, D)
+        lr, gr = global_field(400 + D, slab, nelts, D)
+        u, rho = ddf.Fun(mfd, ddf.Pr, 0, lu), ddf.Fun(mfd, ddf.Pr, 0, lr)
         for part in (1, 2, nsw - 3):
             ddf.poisson_jacobi(mfd, u, rho, 2.0 / 3.0, part)
         mode = ddf.dist.halo_mode(mfd)
@@ -76,7 +89,7 @@ def main():
         dist.all_gather_object(parts, (slab.z_own_lo, u.values[lo:hi].copy()))
         if rank == 0:
             full = ddf.large_hypercube_manifold(D, nelts, ctx=ctx, hdiv=nelts[0])
-            fu, frho = ddf.sample(full, "wave"), ddf.sample(full, "poisson_rho")
+            fu, frho = ddf.Fun(full, ddf.Pr, 0, gu), ddf.Fun(full, ddf.Pr, 0, gr)
             ddf._lib.call("ddf_poisson_jacobi", full._h, fu._h, frho._h, 2.0 / 3.0, int(nsw))
             ru = fu.values
             same = True
@@ -92,7 +105,9 @@ def main():
     # the reference's integrator on slabs: fixed-step Tsit5 with a ghost-plane exchange before every right-hand side
     for D, nelts, nsteps in ((3, (8, 8, 8 * world), 3), (2, (16, 16 * world), 4)):
         mfd, slab = ddf.dist.slab_hypercube(D, nelts, ctx)
-        u, v = ddf.sample(mfd, "wave"), ddf.Fun(mfd, ddf.Pr, 0)
+        lu, gu = global_field(500 + D, slab, nelts, D)
+        lv, gv = global_field(600 + D, slab, nelts, D)
+        u, v = ddf.Fun(mfd, ddf.Pr, 0, lu), ddf.Fun(mfd, ddf.Pr, 0, lv)
         dt = ctx.allreduce(ddf.wave_dt(mfd), "min")
         ddf.wave_tsit5(mfd, u, v, dt, nsteps)
         lo, hi = slab.own_rows
@@ -100,7 +115,7 @@ def main():
         dist.all_gather_object(parts, (slab.z_own_lo, u.values[lo:hi].copy(), v.values[lo:hi].copy()))
         if rank == 0:
             full = ddf.large_hypercube_manifold(D, nelts, ctx=ctx, hdiv=nelts[0])
-            fu, fv = ddf.sample(full, "wave"), ddf.Fun(full, ddf.Pr, 0)
+            fu, fv = ddf.Fun(full, ddf.Pr, 0, gu), ddf.Fun(full, ddf.Pr, 0, gv)
             ctx.nranks_save = None
             ddf._lib.call("ddf_wave_tsit5", full._h, fu._h, fv._h, float(dt), int(nsteps))
             ru, rv = fu.values, fv.values
