@@ -556,7 +556,40 @@ def run_b200(args):
         barrier()
         h2d = 8 * sum(cnt)
         d2h = 8 * (cnt[1] + cnt[2] + cnt[3] + sum(cnt))
-        e2e = {"value": dof_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        # What the platform's host link can do at this N: the same pinned buffers copied up and down CONCURRENTLY on two
+        # streams by every rank at once (no kernels) -- the ceiling of any end-to-end path on this box.  The e2e step
+        # above is bound by it (D2H carries twice the bytes of H2D), and on a multi-GPU box the ranks share host links /
+        # root ports, so the ceiling per rank drops with N: `frac_of_platform` separates that from the library.
+        platform = None
+        try:
+            s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+            nb = min(int(cnt[2]), 1 << 27)                       # up to 1 GiB per direction
+            dsrc = torch.empty(nb, dtype=torch.float64, device="cuda")
+            ddst = torch.empty(nb, dtype=torch.float64, device="cuda")
+            hsrc, hdst = hx[2][:nb], hz[2][:nb]
+
+            def duplex(reps):
+                for _ in range(reps):
+                    with torch.cuda.stream(s_up):
+                        ddst.copy_(hsrc, non_blocking=True)
+                    with torch.cuda.stream(s_dn):
+                        hdst.copy_(dsrc, non_blocking=True)
+                torch.cuda.synchronize()
+            duplex(1)
+            barrier()
+            t0 = time.perf_counter()
+            duplex(4)
+            dt_p = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            per_dir = 4 * nb * 8 / dt_p * 1e-9                    # GB/s per direction per rank, all ranks at once
+            t_plat = max(h2d, d2h) / (per_dir * 1e9) * 1e3        # ms this step's bytes need at that rate (duplex)
+            platform = {"duplex_GBps_per_direction_per_rank": per_dir, "ranks_at_once": N, "ms_for_this_steps_bytes": t_plat,
+                        "frac_of_platform": t_plat / e2e_ms,
+                        "how": "torch pinned<->device copy_ of 1 GiB up and 1 GiB down concurrently on two streams, all ranks at once"}
+            del dsrc, ddst
+        except Exception as e:      # the probe must never break the bench
+            platform = {"error": repr(e)}
+        e2e = {"value": dof_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "platform": platform,
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": Ke,
                "api": "ddf_vec_upload_async -> ddf_op_apply -> ddf_vec_download_async -> ddf_sync "
                       "(pinned host buffers; H2D, compute and D2H on separate streams)"}

@@ -19,6 +19,7 @@
 //        with SparseArrays' CSC `mul!`).
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <memory>
 
 #include "mesh.cuh"
@@ -837,29 +838,50 @@ template <int W>
 __global__ void __launch_bounds__(256)
 k_bits_scan(const int32_t* __restrict__ tab, int64_t nrows, uint32_t* __restrict__ base, uint32_t* __restrict__ maxd,
             uint32_t* __restrict__ bad) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // a warp = one aligned group of 32 rows
-  const bool ok = r < nrows;
-  uint32_t idx[W];
+  // Persistent grid: a warp walks aligned groups of 32 rows with a grid stride and keeps the running maxima of the
+  // W difference fields in registers; one block-level reduction and W atomics per BLOCK at the end.  (One atomic --
+  // or even one filtered read -- per warp on the same four words is an L2 hot spot: 13 ms, then 5 ms at C4 for a
+  // 2.4 GB table that streams in under a millisecond.)
+  __shared__ uint32_t smax[8][W];
+  __shared__ uint32_t sbad;
+  const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) sbad = 0u;
+  __syncthreads();
+  uint32_t mx[W];
 #pragma unroll
-  for (int p = 0; p < W; p++) idx[p] = ok ? (uint32_t)tab[r * W + p] : 0xffffffffu;
-  const uint32_t b = __reduce_min_sync(0xffffffffu, idx[0]);
-  if (ok && (threadIdx.x & 31) == 0) base[r >> 5] = b;
-  uint32_t d[W];
-  d[0] = ok ? idx[0] - b : 0u;
+  for (int p = 0; p < W; p++) mx[p] = 0u;
   bool unsorted = false;
+  const int64_t ngroups = (nrows + 31) >> 5;
+  for (int64_t grp = (int64_t)blockIdx.x * 8 + w; grp < ngroups; grp += (int64_t)gridDim.x * 8) {
+    const int64_t r = grp * 32 + lane;
+    const bool ok = r < nrows;
+    uint32_t idx[W];
 #pragma unroll
-  for (int p = 1; p < W; p++) {
-    d[p] = ok ? idx[p] - idx[p - 1] : 0u;
-    unsorted |= ok && idx[p] <= idx[p - 1];
+    for (int p = 0; p < W; p++) idx[p] = ok ? (uint32_t)tab[r * W + p] : 0xffffffffu;
+    const uint32_t b = __reduce_min_sync(0xffffffffu, idx[0]);
+    if (lane == 0) base[grp] = b;
+    if (ok) {
+      mx[0] = max(mx[0], idx[0] - b);
+#pragma unroll
+      for (int p = 1; p < W; p++) {
+        mx[p] = max(mx[p], idx[p] - idx[p - 1]);
+        unsorted |= idx[p] <= idx[p - 1];
+      }
+    }
   }
-  if (unsorted) atomicOr(bad, 1u);
 #pragma unroll
   for (int p = 0; p < W; p++) {
-    const uint32_t mx = __reduce_max_sync(0xffffffffu, d[p]);
-    // read before the atomic: after the first few warps almost none raises the maximum (millions of atomics on four
-    // addresses cost 13 ms at C4, the filtered version runs at the speed of the table read)
-    if ((threadIdx.x & 31) == 0 && mx > *reinterpret_cast<volatile uint32_t*>(maxd + p)) atomicMax(maxd + p, mx);
+    const uint32_t m = __reduce_max_sync(0xffffffffu, mx[p]);
+    if (lane == 0) smax[w][p] = m;
   }
+  if (unsorted) atomicOr(&sbad, 1u);
+  __syncthreads();
+  if (threadIdx.x < W) {
+    uint32_t m = 0u;
+    for (int k = 0; k < 8; k++) m = max(m, smax[k][threadIdx.x]);
+    atomicMax(maxd + threadIdx.x, m);
+  }
+  if (threadIdx.x == 0 && sbad) atomicOr(bad, 1u);
 }
 
 template <int W, int WB>
@@ -963,8 +985,9 @@ static int bits_build(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, Bi
   DDF_CHECK(br.base.alloc(ctx, (size_t)ceil_div64(nrows, 32)));
   int grid;
   DDF_CHECK(grid_for(nrows, 256, &grid));
-  if (W == 3) k_bits_scan<3><<<grid, 256, 0, ctx->stream>>>(tab, nrows, br.base.p, stat.p, stat.p + 4);
-  else k_bits_scan<4><<<grid, 256, 0, ctx->stream>>>(tab, nrows, br.base.p, stat.p, stat.p + 4);
+  const int sgrid = std::min(grid, ctx->sm_count * 8);          // persistent: 8 resident blocks per SM
+  if (W == 3) k_bits_scan<3><<<sgrid, 256, 0, ctx->stream>>>(tab, nrows, br.base.p, stat.p, stat.p + 4);
+  else k_bits_scan<4><<<sgrid, 256, 0, ctx->stream>>>(tab, nrows, br.base.p, stat.p, stat.p + 4);
   DDF_LAUNCH_CHECK(ctx);
   uint32_t h[5] = {0, 0, 0, 0, 0};
   DDF_CUDA(cudaMemcpyAsync(h, stat.p, 5 * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -779,7 +779,7 @@ int ddf_step_launch(ddf_mesh* m, cudaStream_t stream, int kind, const double* u,
 
 #include "wavefront2.cuh"      // two leapfrog steps per launch with a wavefront through L2
 #ifndef DDF_WAVE2_DEFAULT
-#define DDF_WAVE2_DEFAULT 1    // measured at C4: 0.464 ms per step against 0.490 ms with one step per launch (profiles/r02_tuning.md)
+#define DDF_WAVE2_DEFAULT 1    // measured at C4: 0.451 ms per step against 0.490 ms with one step per launch (profiles/r02_tuning.md)
 #endif
 
 int ddf_leapfrog_launch(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,

@@ -51,10 +51,10 @@ struct Wave2Enum {
 };
 
 template <int NG, int NP>
-__global__ void __launch_bounds__(NG * PIPE_GROUP + 32 * (NP + 2), 1)
+__global__ void __launch_bounds__(NG * PIPE_GROUP + 32 * (NP + 3), 1)
 k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __restrict__ packed,
              const unsigned char* __restrict__ meta, int64_t w0, int64_t w1, PipeGeom g, int lag, int reachw,
-             uint32_t* __restrict__ done) {
+             uint32_t* __restrict__ done, int pf) {
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   __shared__ __align__(8) uint64_t full[PIPE_MAX_STAGES], empty[PIPE_MAX_STAGES], tfull[PIPE_TD];
   __shared__ __align__(16) uint32_t tabS[PIPE_TD * STAGE_TAB];
@@ -63,11 +63,13 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
   // stored[it % W2_RING] = it + 1 once THIS block's step-n task of iteration `it` has issued all its stores (set by
   // its consumer group behind a group barrier); the publisher warp turns that into the device-wide count
   __shared__ int stored[W2_RING];
+  __shared__ int prod_it;                            // the latest step-n iteration a producer has armed (prefetch throttle)
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   if (tid < PIPE_MAX_STAGES) issued[tid] = 0u;
   if (tid < W2_RING) stored[tid] = 0;
   if (tid == 0) {
     known_done = -1;
+    prod_it = 0;
     for (int d = 0; d < PIPE_TD; d++)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tfull[d])) : "memory");
     for (int s = 0; s < g.nstages; s++) {
@@ -100,6 +102,32 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
           __nanosleep(200);
         }
         asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(&known_done)), "r"((int)q) : "memory");
+      }
+    }
+    return;
+  }
+  if (warp == NG * PIPE_GROUP / 32 + NP + 2) {
+    // ------------------------------------------------------------ L2 prefetcher: the first read of a window's entries
+    // comes from HBM and takes ~2 us from arming to data; with three stages in shared memory that latency bounds the
+    // pipeline.  This warp runs `pf` iterations ahead of the producers and asks L2 for the entries + meta records
+    // of the step-n windows (its own table loads may take their time: nobody waits for this warp).
+    if (lane == 0 && pf > 0) {
+      const uint64_t pol_keep = make_policy_evict_last();
+      for (int64_t q = 0; q < nit; q++) {
+        const int64_t win = w0 + blockIdx.x + q * stride;
+        if (win >= w1) break;
+        for (;;) {
+          int seen;
+          asm volatile("ld.relaxed.cta.shared.s32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(&prod_it)) : "memory");
+          if ((int64_t)seen + pf >= q) break;
+          __nanosleep(200);
+        }
+        const uint32_t e0 = __ldg(tab + win * STAGE_TAB + 2), nent = __ldg(tab + win * STAGE_TAB + 3);
+        if (nent)
+          asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(packed + (size_t)e0 * 10),
+                       "r"(nent * 10u), "l"(pol_keep) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(meta + win * g.K * STAGE_META),
+                     "r"((uint32_t)g.K * STAGE_META), "l"(pol_keep) : "memory");
       }
     }
     return;
@@ -204,6 +232,7 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
       if (lane == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(tx) : "memory");
         asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&issued[s])), "r"((uint32_t)pit + 1u) : "memory");
+        if (t.kind == 0) asm volatile("st.relaxed.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(&prod_it)), "r"((int)t.it) : "memory");
       }
       PIPE_TRACE(0, pit);
       __syncwarp();
@@ -326,9 +355,9 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, 
     m->wave2_reach = (int64_t)h;
   }
   const int reachw = (int)(m->wave2_reach / gw) + 2;
-  // tuning bits 18-21 of "wave": extra iterations of lag (default 4: measured best at C4, profiles/r02_tuning.md)
+  // tuning bits 18-21 of "wave": extra iterations of lag (default 3: measured best at C4 together with prefetch distance 2, profiles/r02_tuning.md)
   const int slack_t = (m->ctx->tune.wave >> 18) & 15;
-  const int slack = slack_t ? slack_t - 1 : 4;
+  const int slack = slack_t ? slack_t - 1 : 3;
   const int lag = (reachw + grid - 1) / grid + 1 + slack;
   const int64_t nit = (g1 - g0 + grid - 1) / grid;
   // worth it only when the wavefront is short against the sweep: the windows between the two steps must stay in L2
@@ -360,12 +389,14 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, 
   int64_t g0v = g0, g1v = g1;
   int lagv = lag, reachv = reachw;
   uint32_t* done_p = m->wave2_done.p;
-  void* kargs[] = {&a, &tab_p, &packed_p, &meta_p, &g0v, &g1v, &g, &lagv, &reachv, &done_p};
+  const int pf_t = (m->ctx->tune.wave >> 25) & 15;    // tuning bits 25-28: L2 prefetch distance + 1 (0 = default)
+  int pfv = pf_t ? pf_t - 1 : 2;
+  void* kargs[] = {&a, &tab_p, &packed_p, &meta_p, &g0v, &g1v, &g, &lagv, &reachv, &done_p, &pfv};
 #define DDF_PIPE2_LAUNCH(NPV)                                                                                          \
   do {                                                                                                                 \
     DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe2<2, NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));     \
     cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_rows_pipe2<2, NPV>, dim3(grid),                        \
-                                                 dim3(2 * PIPE_GROUP + 32 * (NPV + 2)), kargs, smem_p, stream);         \
+                                                 dim3(2 * PIPE_GROUP + 32 * (NPV + 3)), kargs, smem_p, stream);         \
     if (le != cudaSuccess) { cudaGetLastError(); return 0; }                                                           \
   } while (0)
   if (np == 1) DDF_PIPE2_LAUNCH(1);

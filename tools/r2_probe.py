@@ -79,8 +79,8 @@ if "wave" in what:
     u0, v0 = rng.standard_normal(m.nsimplices(0)), rng.standard_normal(m.nsimplices(0))
     res = {}
     ref = None
-    cases = [("single", 131072)] + [(f"two_step_slack{sl}_np{np_}", 65536 | ((sl + 1) << 18) | (np_ << 22))
-                                    for np_ in (1, 2, 4) for sl in (2, 4, 6)]
+    cases = [("single", 131072)] + [(f"two_step_slack{sl}_np2_pf{pf}", 65536 | ((sl + 1) << 18) | (2 << 22) | ((pf + 1) << 25))
+                                    for pf in (0, 2, 3, 5) for sl in (3, 4)]
     for name, tune in cases:
         ddf._lib.call("ddf_set_tuning", b"wave", tune)
         u, v = ddf.Fun(m, ddf.Pr, 0, u0), ddf.Fun(m, ddf.Pr, 0, v0)
