@@ -615,7 +615,7 @@ def run_b200(args):
         # algorithmic bytes when this run's slab differs slightly from the captured n=256 cube
         traffic, traffic_src = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 tj = json.load(f)
             if tj.get("n") == n:
                 e = tj[d1_kernel]

@@ -160,6 +160,34 @@ function Base.:+(A::DeviceOp, B::DeviceOp)                       # Ops.jl:186-19
     return own(DeviceOp(r[], A.m))
 end
 Base.:-(A::DeviceOp, B::DeviceOp) = A + (-1.0) * B
+function Base.:/(A::DeviceOp, a::Number)                         # Ops.jl:210-212: values ./ a, ONE rounding per entry
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ddf_op_div, lib), Cint, (Ptr{Cvoid}, Cdouble, Ref{Ptr{Cvoid}}), A.h, Float64(a), r))
+    return own(DeviceOp(r[], A.m))
+end
+
+# dot(f, g) of src/ManifoldOps.jl:154-164 (Fun{D,Pr,D}: 1 ./ vol_D, Fun{D,Dl,0}: 1 ./ dualvol_0), one fused pass
+function wdot(m::DeviceManifold, P::Bool, R::Int, f::DeviceVector, g::DeviceVector)
+    out = Ref{Float64}(0.0)
+    check(ccall((:ddf_vec_wdot, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Float64}),
+                m.h, P ? 1 : 0, R, f.h, g.h, out))
+    return out[]
+end
+
+# get_lookup(mfd, Ri, Rj).op (src/Manifolds.jl:455-498) as an index-only CSC found on the device
+function lookup(m::DeviceManifold, Ri::Int, Rj::Int)
+    nnz = Ref{Int64}(0)
+    check(ccall((:ddf_mesh_get_lookup_csc, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Int64}, Ptr{Int64}, Ptr{Int64}),
+                m.h, Ri, Rj, nnz, C_NULL, C_NULL))
+    nj = Ref{Int64}(0)
+    check(ccall((:ddf_mesh_nsimplices, lib), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}), m.h, Rj, nj))
+    ni = Ref{Int64}(0)
+    check(ccall((:ddf_mesh_nsimplices, lib), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}), m.h, Ri, ni))
+    colptr = Vector{Int64}(undef, nj[] + 1); rowval = Vector{Int64}(undef, nnz[])
+    check(ccall((:ddf_mesh_get_lookup_csc, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Int64}, Ptr{Int64}, Ptr{Int64}),
+                m.h, Ri, Rj, nnz, colptr, rowval))
+    return SparseMatrixCSC{Bool,Int}(ni[], nj[], colptr, rowval, fill(true, nnz[]))
+end
 
 # Op*Fun (src/Ops.jl:273-276) ends in `A.values * f.values.vec`:
 function Base.:*(A::DeviceOp, x::DeviceVector)
