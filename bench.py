@@ -358,6 +358,13 @@ def run_b200(args):
     own = owned_counts(ddf, ctx, (n, n), slab, cnt)
     d = [ddf.deriv(ddf.Pr, k, mfd) for k in range(3)]
     h = [ddf.hodge(ddf.Pr, k, mfd) for k in range(4)]
+    if slab is not None:
+        # a slab rank applies d_k / star_k to the rows it OWNS (one contiguous range per rank by the lexicographic
+        # numbering); the rows of ghost simplices belong to the neighbour rank and are neither computed nor counted
+        rng_ = [mfd.owned_rows(k) for k in range(4)]
+        assert [hi_ - lo_ for lo_, hi_ in rng_] == [int(c) for c in own], (rng_, own)
+        d = [d[k].restrict_rows(*rng_[k + 1]) for k in range(3)]
+        h = [h[k].restrict_rows(*rng_[k]) for k in range(4)]
     x = [ddf.rand_fun(mfd, ddf.Pr, k, seed=k + 1) for k in range(4)]
     y = [ddf.Fun(mfd, ddf.Pr, k + 1) for k in range(3)]
     z = [ddf.Fun(mfd, ddf.Dl, k) for k in range(4)]

@@ -98,6 +98,8 @@ SIGNATURES = {
     "ddf_op_add": [_P, _f64, _P, _PP],
     "ddf_op_scale": [_f64, _P, _PP],
     "ddf_op_div": [_P, _f64, _PP],
+    "ddf_op_restrict_rows": [_P, _i64, _i64, _PP],
+    "ddf_mesh_owned_rows": [_P, _int, _i64p, _i64p],
     "ddf_op_adjoint": [_P, _PP],
     "ddf_op_apply": [_P, _P, _P],
     "ddf_op_assemble": [_P, _PP],

@@ -265,6 +265,12 @@ class Manifold:
         call("ddf_mesh_get_isboundary", self._h, int(R), out.ctypes.data_as(C.POINTER(C.c_uint8)))
         return out.astype(bool)
 
+    def owned_rows(self, R: int):
+        """(lo, hi): the local R-simplices this rank owns as one row range (everything on a mesh without a halo)."""
+        lo, hi = C.c_int64(), C.c_int64()
+        call("ddf_mesh_owned_rows", self._h, int(R), C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
     def set_halo(self, plane: int, ghost_lo: int, ghost_hi: int):
         call("ddf_mesh_set_halo", self._h, int(plane), int(ghost_lo), int(ghost_hi))
 
@@ -504,6 +510,11 @@ class Op:
     def __sub__(self, B):
         self._check(B)
         return self._new("ddf_op_add", self._h, -1.0, B._h)
+
+    def restrict_rows(self, lo: int, hi: int) -> "Op":
+        """The same operator writing rows [lo, hi) only (leaf operators: deriv(Pr,k), hodge, invhodge, isboundary) --
+        what a slab rank applies to the simplices it owns."""
+        return self._new("ddf_op_restrict_rows", self._h, int(lo), int(hi))
 
     def adjoint(self):
         """adjoint(A) (Ops.jl:258-260)."""

@@ -132,6 +132,68 @@ extern "C" int ddf_mesh_set_halo(ddf_mesh* m, int64_t plane, int64_t ghost_lo, i
   return 0;
 }
 
+// rows of the rank-R tables this rank OWNS (smallest vertex in an owned plane), as one range [lo, hi):
+// below the top rank the tables are sorted lexicographically, so the owned rows are the lower-bound range of the first
+// column; the top-level table is in the caller's order, where the range is measured (and must be contiguous, which it is
+// for the generator's block order -- otherwise the whole table is returned).
+__global__ void k_owned_top(const int32_t* __restrict__ simp, int N, int64_t n, int32_t vlo, int32_t vhi,
+                            unsigned long long* __restrict__ st /* min, max, count */) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool own = j < n && simp[j * N] >= vlo && simp[j * N] < vhi;
+  const unsigned mask = __ballot_sync(0xffffffffu, own);
+  if (!mask) return;
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(mask) - 1)) atomicMin(st, (unsigned long long)j);
+  if ((threadIdx.x & 31) == (unsigned)(31 - __clz(mask))) atomicMax(st + 1, (unsigned long long)j);
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(mask) - 1)) atomicAdd(st + 2, (unsigned long long)__popc(mask));
+}
+
+extern "C" int ddf_mesh_owned_rows(ddf_mesh* m, int R, int64_t* lo, int64_t* hi) {
+  DDF_TRY_BEGIN
+  if (R < 0 || R > m->D) DDF_FAIL("owned_rows: R=%d out of range", R);
+  DDF_CHECK(ddf_mesh_require_assembled(m));
+  ddf_ctx* ctx = m->ctx;
+  DDF_CUDA(cudaSetDevice(ctx->device));
+  const int64_t nv = m->n[0], n = m->n[R];
+  *lo = 0;
+  *hi = n;
+  if (m->halo_plane <= 0 || n == 0) return 0;                 // not a slab: everything is owned
+  const int64_t vlo = m->halo_lo * m->halo_plane, vhi = nv - m->halo_hi * m->halo_plane;
+  if (R == 0) { *lo = vlo; *hi = vhi; return 0; }
+  const int N = R + 1;
+  if (R < m->D) {
+    auto lower_bound = [&](int64_t v, int64_t* out) -> int {   // first row whose smallest vertex is >= v
+      int64_t a = 0, b = n;
+      while (a < b) {
+        const int64_t mid = (a + b) >> 1;
+        int32_t first = 0;
+        DDF_CUDA(cudaMemcpyAsync(&first, m->simp[R].p + mid * N, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (first < v) a = mid + 1; else b = mid;
+      }
+      *out = a;
+      return 0;
+    };
+    DDF_CHECK(lower_bound(vlo, lo));
+    DDF_CHECK(lower_bound(vhi, hi));
+    return 0;
+  }
+  DevBuf<unsigned long long> st;
+  DDF_CHECK(st.alloc(ctx, 3));
+  const unsigned long long init[3] = {~0ull, 0ull, 0ull};
+  DDF_CUDA(cudaMemcpyAsync(st.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  int grid;
+  DDF_CHECK(grid_for(n, 256, &grid));
+  k_owned_top<<<grid, 256, 0, ctx->stream>>>(m->simp[R].p, N, n, (int32_t)vlo, (int32_t)vhi, st.p);
+  DDF_LAUNCH_CHECK(ctx);
+  unsigned long long h[3] = {0, 0, 0};
+  DDF_CUDA(cudaMemcpyAsync(h, st.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h[2] == 0) { *lo = 0; *hi = 0; return 0; }
+  if (h[1] - h[0] + 1 == h[2]) { *lo = (int64_t)h[0]; *hi = (int64_t)h[1] + 1; }
+  return 0;
+  DDF_TRY_END
+}
+
 // exchange on `stream`: my lowest owned plane -> rank-1 (into its first upper ghost plane),
 // my highest owned plane -> rank+1 (into its last lower ghost plane), and the converse receives.
 static int halo_exchange_on(ddf_mesh* m, double* u, cudaStream_t stream) {

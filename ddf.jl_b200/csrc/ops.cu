@@ -66,6 +66,9 @@ struct OpNode {
   std::vector<double> tree_coefs;    // SUM: coefficient of every term
   double tree_scale = 1.0;           // CHAIN: scalar applied to the assembled product (a * A, Ops.jl:240-243)
   OpRef adj_of;                      // this node is adjoint(adj_of)
+  // ddf_op_restrict_rows: apply writes rows [row_lo, row_hi) only (row_hi < 0: all rows).  Slab meshes apply d_k /
+  // star_k to the rows they OWN; the ghost rows belong to the neighbour rank.
+  int64_t row_lo = 0, row_hi = -1;
 };
 
 struct ddf_op {
@@ -801,16 +804,19 @@ static int packed_build(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, 
 }
 
 static int launch_packed(ddf_ctx* ctx, const PackedBufs& pb, int W, int64_t nrows, int first_negative, const double* x,
-                         const double* pre, const double* post, double alpha, double* y) {
+                         const double* pre, const double* post, double alpha, double* y, int64_t row0 = 0) {
   const DdfTune& tn = ctx->tune;
+  const uint32_t *pw = pb.words.p + row0 * (W - 1), *pbase = pb.base.p + row0 / 32;     // row range: see launch_bits_w
+  y += row0;
+  if (post) post += row0;
   const int g4 = (int)ceil_div64(ceil_div64(nrows, 4), 256), g3 = (int)ceil_div64(ceil_div64(nrows, 3), 256);
   const bool quad = W == 2 && tn.fixed != 19;
 #define DDF_PACKED_CASE(PRE_, POST_)                                                                                 \
   do {                                                                                                               \
-    if (quad) k_apply_packed_quad<PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha, tn.prefetch); \
-    else if (W == 2) k_apply_packed_rows<2, 4, PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha); \
-    else if (W == 3) k_apply_packed_rows<3, 4, PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha); \
-    else k_apply_packed_rows<4, 3, PRE_, POST_><<<g3, 256, 0, ctx->stream>>>(pb.words.p, pb.base.p, nrows, first_negative, x, y, pre, post, alpha);             \
+    if (quad) k_apply_packed_quad<PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pw, pbase, nrows, first_negative, x, y, pre, post, alpha, tn.prefetch); \
+    else if (W == 2) k_apply_packed_rows<2, 4, PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pw, pbase, nrows, first_negative, x, y, pre, post, alpha); \
+    else if (W == 3) k_apply_packed_rows<3, 4, PRE_, POST_><<<g4, 256, 0, ctx->stream>>>(pw, pbase, nrows, first_negative, x, y, pre, post, alpha); \
+    else k_apply_packed_rows<4, 3, PRE_, POST_><<<g3, 256, 0, ctx->stream>>>(pw, pbase, nrows, first_negative, x, y, pre, post, alpha);             \
   } while (0)
   if (pre && post) DDF_PACKED_CASE(true, true);
   else if (pre) DDF_PACKED_CASE(true, false);
@@ -1014,11 +1020,17 @@ static int bits_build(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, Bi
 
 template <int W, int WB>
 static void launch_bits_w(ddf_ctx* ctx, const BitRows& br, const BitFmt& f, int64_t nrows, int first_negative,
-                          const double* x, const double* pre, const double* post, double alpha, double* y) {
+                          const double* x, const double* pre, const double* post, double alpha, double* y,
+                          int64_t row0 = 0) {
   const DdfTune& tn = ctx->tune;
   constexpr int RPW = W == 3 ? 4 : 3;
+  // a row range [row0, row0 + nrows): row0 is a multiple of 32, so the kernel sees shifted tables (the base word of
+  // a 32-row group, the per-row words, y and the per-row output diagonal all move by row0; x and the input diagonal
+  // are indexed by column and stay)
   const int g = (int)ceil_div64(ceil_div64(nrows, RPW), 256);
-  const uint32_t *w = br.words.p, *b = br.base.p;
+  const uint32_t *w = br.words.p + row0 * (WB / 4), *b = br.base.p + row0 / 32;
+  y += row0;
+  if (post) post += row0;
   if (!pre && !post && (tn.fixed == 21 || tn.fixed == 22)) {      // A/B: other rows-per-lane counts
     constexpr int RA = W == 3 ? 8 : 4, RB = 2;
     if (tn.fixed == 21)
@@ -1034,12 +1046,12 @@ static void launch_bits_w(ddf_ctx* ctx, const BitRows& br, const BitFmt& f, int6
 }
 
 static int launch_bits(ddf_ctx* ctx, const BitRows& br, int W, int64_t nrows, int first_negative, const double* x,
-                       const double* pre, const double* post, double alpha, double* y) {
+                       const double* pre, const double* post, double alpha, double* y, int64_t row0 = 0) {
   const BitFmt f = bits_fmt(br);
-  if (W == 3 && br.wbytes == 4) launch_bits_w<3, 4>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y);
-  else if (W == 3) launch_bits_w<3, 8>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y);
-  else if (br.wbytes == 4) launch_bits_w<4, 4>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y);
-  else launch_bits_w<4, 8>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y);
+  if (W == 3 && br.wbytes == 4) launch_bits_w<3, 4>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y, row0);
+  else if (W == 3) launch_bits_w<3, 8>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y, row0);
+  else if (br.wbytes == 4) launch_bits_w<4, 4>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y, row0);
+  else launch_bits_w<4, 8>(ctx, br, f, nrows, first_negative, x, pre, post, alpha, y, row0);
   DDF_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -1091,9 +1103,12 @@ static void launch_fixed_x(ddf_ctx* ctx, int var, const int32_t* tab, int64_t nr
 
 // ================================================================ kernel launchers
 static int launch_fixed(ddf_ctx* ctx, const int32_t* tab, int W, int64_t nrows, int first_negative, const double* x,
-                        const double* pre, const double* post, double alpha, double* y) {
+                        const double* pre, const double* post, double alpha, double* y, int64_t row0 = 0) {
   const DdfTune& tn = ctx->tune;
   if (nrows == 0) return 0;
+  tab += row0 * W;                         // row range: see launch_bits_w
+  y += row0;
+  if (post) post += row0;
   int grid;
   DDF_CHECK(grid_for(ceil_div64(nrows, 4), 256, &grid));
   if (tn.fixed > 0 && tn.fixed < 16 && tn.fixed != 9 && !pre && !post && alpha == 1.0 && W >= 2 && W <= 4) {
@@ -1813,13 +1828,22 @@ static int apply_sparse(OpNode* f, const double* x, const OpNode* pre, const OpN
   if (f->kind == OPK_FIXED) {
     const int W = f->R + 1;
     // default: prefix-packed rows (4 bytes less index data per row); tuning 18 keeps the explicit table
+    // row range (ddf_op_restrict_rows), rounded outward to whole 1024-row blocks so that every storage keeps its
+    // 32-row groups and vector widths; the few extra rows are correct values of rows next to the range
+    int64_t r0 = 0, nr = f->nrows;
+    if (f->row_hi >= 0) {
+      r0 = f->row_lo / 1024 * 1024;
+      const int64_t r1 = std::min<int64_t>((f->row_hi + 1023) / 1024 * 1024, f->nrows);
+      nr = r1 > r0 ? r1 - r0 : 0;
+      if (nr == 0) return 0;
+    }
     {
       int fmt = 0;
       DDF_CHECK(dk_rows_format(m, f->R, &fmt));
-      if (fmt >= 2) return launch_bits(f->ctx, m->bbits[f->R], W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
-      if (fmt == 1) return launch_packed(f->ctx, m->bpack[f->R], W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
+      if (fmt >= 2) return launch_bits(f->ctx, m->bbits[f->R], W, nr, (f->R & 1), x, pre_d, post_d, a, y, r0);
+      if (fmt == 1) return launch_packed(f->ctx, m->bpack[f->R], W, nr, (f->R & 1), x, pre_d, post_d, a, y, r0);
     }
-    return launch_fixed(f->ctx, m->bnd_table(f->R), W, f->nrows, (f->R & 1), x, pre_d, post_d, a, y);
+    return launch_fixed(f->ctx, m->bnd_table(f->R), W, nr, (f->R & 1), x, pre_d, post_d, a, y, r0);
   }
   // boundary / dual derivative: SELL-32 copy of the row-CSR when its padding is small, else CSR
   const int R = f->R;
@@ -1971,7 +1995,12 @@ static int apply_node(OpNode* n, const double* x, double* y) {
       return 0;
     case OPK_FIXED:
     case OPK_CSRSIGN: return apply_sparse(n, x, nullptr, nullptr, 1.0, y);
-    case OPK_DIAG: return launch_diag(ctx, n->diag, n->scale, x, y, n->nrows);
+    case OPK_DIAG: {
+      if (n->row_hi < 0) return launch_diag(ctx, n->diag, n->scale, x, y, n->nrows);
+      const int64_t r0 = n->row_lo / 4 * 4;                      // 128-bit accesses: keep the 32-byte phase of the vectors
+      const int64_t r1 = std::min<int64_t>((n->row_hi + 3) / 4 * 4, n->nrows);
+      return r1 > r0 ? launch_diag(ctx, n->diag ? n->diag + r0 : nullptr, n->scale, x + r0, y + r0, r1 - r0) : 0;
+    }
     case OPK_CSRF64: {
       if (!n->nrows) return 0;
       if (n->sell_state == 0) {                  // large operators: SELL copy of the rows, once
@@ -2016,6 +2045,24 @@ static int apply_node(OpNode* n, const double* x, double* y) {
     }
   }
   return 1;
+}
+
+// An operator that writes rows [row0, row1) only -- what a rank of a slab-decomposed mesh OWNS (rows of
+// ghost simplices belong to the neighbour and are never used).  Leaf operators of the hot path: deriv(Pr,k) and the
+// diagonal operators; the range may be widened to the storage's block size (rows next to the range, correct values).
+extern "C" int ddf_op_restrict_rows(ddf_op* A, int64_t row0, int64_t row1, ddf_op** out) {
+  DDF_TRY_BEGIN
+  *out = nullptr;
+  OpRef n = A->node;
+  if (n->kind != OPK_FIXED && n->kind != OPK_DIAG)
+    DDF_FAIL("restrict_rows: supported for deriv(Pr,k) and diagonal operators (hodge, invhodge, isboundary)");
+  if (row0 < 0 || row1 < row0 || row1 > n->nrows) DDF_FAIL("restrict_rows: need 0 <= row0 <= row1 <= %lld", (long long)n->nrows);
+  OpRef o = clone_leaf(n);
+  o->row_lo = row0;
+  o->row_hi = row1;
+  *out = wrap(o);
+  return 0;
+  DDF_TRY_END
 }
 
 extern "C" int ddf_op_apply(ddf_op* A, ddf_vec* x, ddf_vec* y) {

@@ -256,6 +256,12 @@ int ddf_comm_destroy(ddf_ctx* ctx);
  * `ghost_lo` and last `ghost_hi` vertex planes are ghosts owned by rank-1 / rank+1
  * (0 at the domain ends).  Owned rows are the planes in between. */
 int ddf_mesh_set_halo(ddf_mesh* mesh, int64_t plane, int64_t ghost_lo, int64_t ghost_hi);
+/* The rank-R simplices this rank owns (smallest vertex in an owned plane) as ONE row range [lo, hi) of its local
+ * tables (lexicographic numbering makes them contiguous); a mesh without a halo owns everything. */
+int ddf_mesh_owned_rows(ddf_mesh* mesh, int R, int64_t* lo, int64_t* hi);
+/* A copy of a leaf operator (deriv(Pr,k), hodge / invhodge / isboundary) whose apply writes rows [row0, row1) only:
+ * a slab rank applies d_k / star_k to the rows it owns and leaves the ghost rows to their owner. */
+int ddf_op_restrict_rows(ddf_op* A, int64_t row0, int64_t row1, ddf_op** out);
 /* fused leapfrog on the owned rows + one-plane halo exchange of u per step with
  * ncclSend/ncclRecv to rank-1 / rank+1, overlapped with the interior rows. */
 int ddf_wave_leapfrog_dist(ddf_mesh* mesh, ddf_vec* u, ddf_vec* v, double dt, int nsteps);

@@ -357,3 +357,43 @@ def test_refine_coords_on_device(ddf, ctx):
         for a, b in zip(dm.get_boundaries_csc(R), o.to_julia_csc(om.boundaries[R])):
             assert np.array_equal(a, b)
     dm.close()
+
+
+# ------------------------------------------------------------------ owned rows of a slab
+def test_owned_row_ranges_and_restricted_apply(ddf, ctx):
+    """A slab rank owns the simplices whose smallest vertex lies in an owned plane: one contiguous row range per rank
+    (lexicographic numbering; measured for the top level).  `restrict_rows` applies d_k / star_k to that range only:
+    the owned rows carry the full apply's bits, rows beyond the (block-rounded) range are never written."""
+    nx, nz = 24, 20
+    dm = ddf.large_hypercube_manifold(3, (nx, nx, nz), ctx=ctx, hdiv=nx)
+    plane = (nx + 1) ** 2
+    dm.set_halo(plane, 2, 3)
+    nv = dm.nsimplices(0)
+    vlo, vhi = 2 * plane, nv - 3 * plane
+    rng = np.random.default_rng(12)
+    for R in range(4):
+        first = np.arange(nv) if R == 0 else dm.get_simplices(R)[:, 0]
+        own = (first >= vlo) & (first < vhi)
+        lo, hi = dm.owned_rows(R)
+        assert hi - lo == int(own.sum()) and own[lo:hi].all(), (R, lo, hi, int(own.sum()))
+        x = rng.standard_normal(dm.nsimplices(R))
+        fx = ddf.Fun(dm, ddf.Pr, R, x)
+        full = (ddf.hodge(ddf.Pr, R, dm) * fx).values
+        y = ddf.Fun(dm, ddf.Dl, R, np.full(dm.nsimplices(R), -7.0))
+        ddf.hodge(ddf.Pr, R, dm).restrict_rows(lo, hi).apply(fx, y)
+        got = y.values
+        assert np.array_equal(got[lo:hi], full[lo:hi])
+        assert np.all(got[:max(lo - 4, 0)] == -7.0) and np.all(got[hi + 4:] == -7.0)
+        if R < 3:
+            lo1, hi1 = dm.owned_rows(R + 1)
+            full = (ddf.deriv(ddf.Pr, R, dm) * fx).values
+            y = ddf.Fun(dm, ddf.Pr, R + 1, np.full(dm.nsimplices(R + 1), -7.0))
+            ddf.deriv(ddf.Pr, R, dm).restrict_rows(lo1, hi1).apply(fx, y)
+            got = y.values
+            assert np.array_equal(got[lo1:hi1], full[lo1:hi1]), R
+            assert np.all(got[:max(lo1 - 1024, 0)] == -7.0) and np.all(got[hi1 + 1024:] == -7.0), R
+    # a mesh without a halo owns everything
+    m2 = ddf.large_hypercube_manifold(2, (6, 6), ctx=ctx)
+    assert [m2.owned_rows(R) for R in range(3)] == [(0, m2.nsimplices(R)) for R in range(3)]
+    m2.close()
+    dm.close()
