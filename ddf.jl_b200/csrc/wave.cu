@@ -810,7 +810,7 @@ extern "C" int ddf_wave_leapfrog(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt,
   const int tw = m->ctx->tune.wave;
   if ((tw & 65536) || (DDF_WAVE2_DEFAULT && !(tw & 131072) && (tw & 0xffff) == 0)) {
     for (bool ran = true; ran && s + 1 < nsteps;) {
-      DDF_CHECK(launch_pipe2(m, m->ctx->stream, u->d.p, v->d.p, m->utmp.p, dt, &ran));
+      DDF_CHECK(launch_pipe2(m, m->ctx->stream, 0, u->d.p, v->d.p, m->utmp.p, dt, &ran));
       if (ran) s += 2;
     }
   }
@@ -936,7 +936,18 @@ extern "C" int ddf_poisson_jacobi(ddf_mesh* m, ddf_vec* u, ddf_vec* rho, double 
   DDF_CHECK(ddf_vec_settle(rho));
   DDF_CHECK(ddf_mesh_require_dinv(m));
   if ((int64_t)m->utmp.n != nv) DDF_CHECK(m->utmp.alloc(ctx, nv));
-  for (int s = 0; s < nsweeps; s++) {
+  int s = 0;
+  {
+    // two sweeps per launch with the wavefront through L2 (wavefront2.cuh), like the leapfrog step
+    const int tw = ctx->tune.wave;
+    if ((tw & 65536) || (DDF_WAVE2_DEFAULT && !(tw & 131072) && (tw & 0xffff) == 0)) {
+      for (bool ran = true; ran && s + 1 < nsweeps;) {
+        DDF_CHECK(launch_pipe2(m, ctx->stream, 1, u->d.p, rho->d.p, m->utmp.p, theta, &ran));
+        if (ran) s += 2;
+      }
+    }
+  }
+  for (; s < nsweeps; s++) {
     RowArgs a{};
     a.u = u->d.p;
     a.out1 = m->utmp.p;

@@ -50,7 +50,8 @@ struct Wave2Enum {
   }
 };
 
-template <int NG, int NP>
+// MODE 2: leapfrog (a.out0 = v in/out, a.dt);  MODE 3: Poisson relaxation sweep (a.rho, a.dinv, a.theta; no v)
+template <int MODE, int NG, int NP>
 __global__ void __launch_bounds__(NG * PIPE_GROUP + 32 * (NP + 3), 1)
 k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __restrict__ packed,
              const unsigned char* __restrict__ meta, int64_t w0, int64_t w1, PipeGeom g, int lag, int reachw,
@@ -154,7 +155,8 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
   }
   double* const U0 = const_cast<double*>(a.u);       // step n input, step n+1 output
   double* const U1 = a.out1;                         // step n output, step n+1 input
-  double* const V = a.out0;
+  double* const V = a.out0;                          // MODE 2 only
+  const double* const AUX = MODE == 3 ? a.rho : a.out0;   // what travels in the stage's "v" slot
   if (warp >= NG * PIPE_GROUP / 32 && warp < NG * PIPE_GROUP / 32 + NP) {
     // ------------------------------------------------------------ NP producer warps: warp p arms the tasks p mod NP
     // (one warp spends ~1.3 us per task on its ~7 bulk requests and the bookkeeping around them -- more than the
@@ -243,7 +245,7 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
       if (lane == 31 && nent) bulk_g2s(sb + g.o_ent, packed + (size_t)e0 * 10, nent * 10u, &full[s], pol_ent);
       if (lane == 30) bulk_g2s(sb + g.o_meta, meta + t.win * g.K * STAGE_META, mbytes, &full[s], pol_ent);
       if (lane == 29) {
-        bulk_g2s(sb + g.o_v, V + r0, vbytes, &full[s], pol_stream);
+        bulk_g2s(sb + g.o_v, AUX + r0, vbytes, &full[s], MODE == 3 ? pol_keep : pol_stream);
         bulk_g2s(sb + g.o_u, uin + r0, vbytes, &full[s], pol_keep);
       }
       PIPE_TRACE(6, pit);
@@ -281,6 +283,10 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
         const uint32_t p = (metaS + STAGE_META_HDR)[gtid];
         const uint32_t part = reinterpret_cast<const uint32_t*>(metaS)[4 + gwarp];
         const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
+        const uint32_t pl = (uint32_t)kk * DDF_SELL_WIN + p;
+        const int64_t i = t.win * g.K * DDF_SELL_WIN + pl;
+        double dinv_i = 0.0;                                 // MODE 3: requested now, needed after the row sum
+        if (MODE == 3 && i >= a.row0 && i < a.row1) dinv_i = __ldg(a.dinv + i);
         uint32_t e = part + lane, q = 0;
         double acc = 0.0;
         while (q < maxlen) {
@@ -292,14 +298,16 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
           }
           q = qend;
         }
-        const uint32_t pl = (uint32_t)kk * DDF_SELL_WIN + p;
-        const int64_t i = t.win * g.K * DDF_SELL_WIN + pl;
         if (i >= a.row0 && i < a.row1) {
           const double m = (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
           const double ev = reinterpret_cast<const double*>(sb + g.o_v)[pl];
-          const double vn = __dadd_rn(ev, __dmul_rn(a.dt, __dmul_rn(m, acc)));
-          V[i] = vn;
-          uout[i] = __dadd_rn(reinterpret_cast<const double*>(sb + g.o_u)[pl], __dmul_rn(a.dt, __dmul_rn(m, vn)));
+          if (MODE == 3) {
+            uout[i] = jacobi_update(reinterpret_cast<const double*>(sb + g.o_u)[pl], acc, ev, dinv_i, m, a.theta);
+          } else {
+            const double vn = __dadd_rn(ev, __dmul_rn(a.dt, __dmul_rn(m, acc)));
+            V[i] = vn;
+            uout[i] = __dadd_rn(reinterpret_cast<const double*>(sb + g.o_u)[pl], __dmul_rn(a.dt, __dmul_rn(m, vn)));
+          }
         }
       }
       __syncwarp();
@@ -331,7 +339,8 @@ __global__ void k_row_reach(const uint32_t* __restrict__ rowptr, const int32_t* 
 }
 
 // Two leapfrog steps in one launch: on return u (U0) holds the state after both steps, utmp the one in between.
-static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, double* utmp, double dt, bool* ran) {
+// kind 0: leapfrog (aux = v in/out, coef = dt);  kind 1: Poisson relaxation sweep (aux = rho read-only, coef = theta)
+static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, int kind, double* u, double* aux, double* utmp, double coef, bool* ran) {
   *ran = false;
   const StageBufs& sb = m->lstage;
   if (!sb.ok || m->ctx->nranks > 1) return 0;
@@ -369,12 +378,12 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, 
   DDF_CUDA(cudaMemsetAsync(m->wave2_done.p, 0, (size_t)nit * 4, stream));
   RowArgs a{};
   a.u = u;
-  a.out0 = v;
   a.out1 = utmp;
-  a.dt = dt;
   a.row0 = 0;
   a.row1 = nv;
   a.isb = m->isbnd[0].p;
+  if (kind == 0) { a.out0 = aux; a.dt = coef; }
+  else { a.rho = aux; a.dinv = m->ldinv.p; a.theta = coef; }
   const size_t smem_p = (size_t)g.nstages * g.stage_bytes;
   if (getenv("DDF_DEBUG"))
     fprintf(stderr, "[ddf] k_rows_pipe2: %d stages x %u B (slots %u, entries %u), grid %d, reach %lld rows = %d windows, lag %d, nit %lld\n",
@@ -392,16 +401,17 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, double* u, double* v, 
   const int pf_t = (m->ctx->tune.wave >> 25) & 15;    // tuning bits 25-28: L2 prefetch distance + 1 (0 = default)
   int pfv = pf_t ? pf_t - 1 : 2;
   void* kargs[] = {&a, &tab_p, &packed_p, &meta_p, &g0v, &g1v, &g, &lagv, &reachv, &done_p, &pfv};
-#define DDF_PIPE2_LAUNCH(NPV)                                                                                          \
+#define DDF_PIPE2_LAUNCH(MODEV, NPV)                                                                                   \
   do {                                                                                                                 \
-    DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe2<2, NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));     \
-    cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_rows_pipe2<2, NPV>, dim3(grid),                        \
+    DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe2<MODEV, 2, NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); \
+    cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_rows_pipe2<MODEV, 2, NPV>, dim3(grid),                 \
                                                  dim3(2 * PIPE_GROUP + 32 * (NPV + 3)), kargs, smem_p, stream);         \
     if (le != cudaSuccess) { cudaGetLastError(); return 0; }                                                           \
   } while (0)
-  if (np == 1) DDF_PIPE2_LAUNCH(1);
-  else if (np == 4) DDF_PIPE2_LAUNCH(4);
-  else DDF_PIPE2_LAUNCH(2);
+  if (kind == 1) DDF_PIPE2_LAUNCH(3, 2);
+  else if (np == 1) DDF_PIPE2_LAUNCH(2, 1);
+  else if (np == 4) DDF_PIPE2_LAUNCH(2, 4);
+  else DDF_PIPE2_LAUNCH(2, 2);
 #undef DDF_PIPE2_LAUNCH
   DDF_LAUNCH_CHECK(m->ctx);
   *ran = true;

@@ -397,3 +397,32 @@ def test_owned_row_ranges_and_restricted_apply(ddf, ctx):
     assert [m2.owned_rows(R) for R in range(3)] == [(0, m2.nsimplices(R)) for R in range(3)]
     m2.close()
     dm.close()
+
+
+def test_wavefront2_poisson_sweeps_equal_single_sweeps(ddf, ctx):
+    """The fused Poisson relaxation sweep also runs two sweeps per launch (wavefront through L2): same bits as one
+    sweep per launch for even and odd sweep counts, from random u and rho."""
+    n = 96
+    m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
+    rng = np.random.default_rng(3)
+    u0, rho = rng.standard_normal(m.nsimplices(0)), rng.standard_normal(m.nsimplices(0))
+    frho = ddf.Fun(m, ddf.Pr, 0, rho)
+    for sweeps in (4, 5):
+        ref = ddf.Fun(m, ddf.Pr, 0, u0)
+        ddf._lib.call("ddf_set_tuning", b"wave", 131072)              # one sweep per launch
+        try:
+            ddf.poisson_jacobi(m, ref, frho, 2.0 / 3.0, sweeps)
+        finally:
+            ddf._lib.call("ddf_set_tuning", b"wave", 0)
+        for tune in (0, 65536 | (1 << 18)):                           # default; forced with slack 0
+            u = ddf.Fun(m, ddf.Pr, 0, u0)
+            ctx.sync()
+            l0 = ctx.launch_count()
+            ddf._lib.call("ddf_set_tuning", b"wave", tune)
+            try:
+                ddf.poisson_jacobi(m, u, frho, 2.0 / 3.0, sweeps)
+            finally:
+                ddf._lib.call("ddf_set_tuning", b"wave", 0)
+            assert ctx.launch_count() - l0 <= sweeps // 2 + (sweeps % 2) + 2, (ctx.launch_count() - l0, sweeps)
+            assert np.array_equal(u.values, ref.values), (sweeps, tune)
+    m.close()
