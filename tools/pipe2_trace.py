@@ -21,7 +21,7 @@ ctx = ddf.Context(0)
 m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
 u, v = ddf.sample(m, "wave"), ddf.Fun(m, ddf.Pr, 0)
 dt = ddf.wave_dt(m)
-ddf._lib.call("ddf_set_tuning", b"wave", 65536 | ((slack + 1) << 18))
+ddf._lib.call("ddf_set_tuning", b"wave", int(os.environ.get("W2_TUNE", str(65536 | ((slack + 1) << 18)))))
 ddf.wave_leapfrog(m, u, v, dt, 4)
 ctx.sync()
 lib = C.CDLL(L.LIB_PATH)
@@ -41,6 +41,11 @@ for kind, name in ((0, "even tasks"), (1, "odd tasks")):
           "| issue", med(issued[sel] - armed[sel]))
     print("  fill (armed -> data visible)", med(ready[sel] - armed[sel]), "| consumer waited for data", med(ready[sel] - creach[sel]))
     print("  consume", med(done[sel] - ready[sel]), "| consumer idle before the task", med(creach[sel][1:] - done[sel - 2][1:]))
+if os.environ.get("W2_VGTRACE"):
+    ld0, ld1 = t[4][:nt], t[5][:nt]
+    sel = np.arange(lo, hi)
+    print("VG consumer: consume (data visible -> released)", np.median(done[sel] - ready[sel]), "| released -> loads start",
+          np.median(ld0[sel] - done[sel]), "| issuing the loads", np.median(ld1[sel] - ld0[sel]))
 for k in range(lo, lo + 8):
     b = reach[lo]
     print(f"  task {k}: reach +{reach[k]-b} waitfree +{wait_free[k]-b} armed +{armed[k]-b} issued +{issued[k]-b} | creach +{creach[k]-b} ready +{ready[k]-b} done +{done[k]-b}")
