@@ -120,6 +120,7 @@ SIGNATURES = {
     "ddf_comm_init": [_P, _int, _int, _P],
     "ddf_comm_destroy": [_P],
     "ddf_mesh_set_halo": [_P, _i64, _i64, _i64],
+    "ddf_mesh_set_halo_lists": [_P, _i64, _i64, _int, C.POINTER(C.c_int32), _i64p, _i64p, _i64p, _i64p],
     "ddf_wave_leapfrog_dist": [_P, _P, _P, _f64, _int],
     "ddf_halo_exchange": [_P, _P],
     "ddf_halo_exchange_k": [_P, _P, _int],

@@ -274,6 +274,13 @@ class Manifold:
     def set_halo(self, plane: int, ghost_lo: int, ghost_hi: int):
         call("ddf_mesh_set_halo", self._h, int(plane), int(ghost_lo), int(ghost_hi))
 
+    def set_halo_lists(self, part):
+        """Ghost lists of a mesh partitioned by vertex ranges (`ddf.dist.partition_mesh`)."""
+        peers = np.ascontiguousarray(part.peers, dtype=np.int32)
+        arrs = [np.ascontiguousarray(a, dtype=np.int64) for a in (part.send_ptr, part.send_idx, part.recv_ptr, part.recv_idx)]
+        call("ddf_mesh_set_halo_lists", self._h, int(part.own_lo), int(part.own_hi), int(peers.shape[0]),
+             peers.ctypes.data_as(C.POINTER(C.c_int32)), *[_i64p(a) for a in arrs])
+
     def close(self):
         """Release the device tables.  Operators built on this manifold borrow its tables, so while any of them is
         alive the release is deferred to the moment the last one is dropped (Op.__del__)."""

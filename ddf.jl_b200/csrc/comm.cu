@@ -132,6 +132,105 @@ extern "C" int ddf_mesh_set_halo(ddf_mesh* m, int64_t plane, int64_t ghost_lo, i
   return 0;
 }
 
+// =====================================================================================
+// General halo: a mesh of ANY origin (uploaded, refined, Delaunay) partitioned by contiguous ranges of the global
+// vertex numbering (north_star: "large refined meshes are partitioned by simplex ranges").  The host side
+// (ddf.dist.partition_mesh) gives every rank the closed star of its owned vertices, renumbered monotonically, so the
+// local face ranks keep the global order and every owned row (geometry, star values, L) is bit-identical to the
+// undivided mesh; ghost vertices get their values from their owners through explicit index lists, one grouped
+// ncclSend/ncclRecv per exchange, peers in any number and order.
+// =====================================================================================
+struct HaloGeneral {
+  std::vector<int> peers;
+  std::vector<int64_t> send_ptr, recv_ptr;      // npeers + 1 offsets into the index lists
+  DevBuf<uint32_t> send_idx, recv_idx;          // local vertex ids
+  DevBuf<double> send_buf, recv_buf;
+};
+__global__ void k_gen_pack(const uint32_t* __restrict__ idx, const double* __restrict__ src, int64_t n, double* __restrict__ dst) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[p] = src[idx[p]];
+}
+__global__ void k_gen_unpack(const uint32_t* __restrict__ idx, const double* __restrict__ src, int64_t n, double* __restrict__ dst) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[idx[p]] = src[p];
+}
+void ddf_halo_gen_release(ddf_mesh* m) {
+  delete (HaloGeneral*)m->halo_gen;
+  m->halo_gen = nullptr;
+}
+// own_lo / own_hi: the owned local vertex range; peers[k] exchanges send_idx[send_ptr[k] .. send_ptr[k+1]) (values this
+// rank owns and peer k holds as ghosts) against recv_idx[recv_ptr[k] .. recv_ptr[k+1]) (this rank's ghosts owned by
+// peer k); both sides list a pair's vertices in ascending GLOBAL id, so positions match.  0-based local ids.
+extern "C" int ddf_mesh_set_halo_lists(ddf_mesh* m, int64_t own_lo, int64_t own_hi, int npeers, const int32_t* peers,
+                                       const int64_t* send_ptr, const int64_t* send_idx, const int64_t* recv_ptr,
+                                       const int64_t* recv_idx) {
+  DDF_TRY_BEGIN
+  ddf_ctx* ctx = m->ctx;
+  if (own_lo < 0 || own_hi < own_lo || own_hi > m->n[0]) DDF_FAIL("set_halo_lists: owned range [%lld, %lld) outside 0..%lld", (long long)own_lo, (long long)own_hi, (long long)m->n[0]);
+  if (npeers < 0) DDF_FAIL("set_halo_lists: npeers < 0");
+  ddf_halo_gen_release(m);
+  HaloGeneral* hg = new HaloGeneral();
+  m->halo_gen = hg;
+  m->gen_own_lo = own_lo;
+  m->gen_own_hi = own_hi;
+  m->halo_plane = 0;
+  hg->peers.assign(peers, peers + npeers);
+  hg->send_ptr.assign(send_ptr, send_ptr + npeers + 1);
+  hg->recv_ptr.assign(recv_ptr, recv_ptr + npeers + 1);
+  for (int k = 0; k < npeers; k++)
+    if (peers[k] < 0 || peers[k] >= ctx->nranks || peers[k] == ctx->rank || send_ptr[k + 1] < send_ptr[k] || recv_ptr[k + 1] < recv_ptr[k])
+      DDF_FAIL("set_halo_lists: bad peer %d", k);
+  const int64_t ns = npeers ? send_ptr[npeers] : 0, nr = npeers ? recv_ptr[npeers] : 0;
+  std::vector<uint32_t> hs(ns), hr(nr);
+  for (int64_t q = 0; q < ns; q++) {
+    if (send_idx[q] < own_lo || send_idx[q] >= own_hi) DDF_FAIL("set_halo_lists: send entry %lld is not an owned vertex", (long long)q);
+    hs[q] = (uint32_t)send_idx[q];
+  }
+  for (int64_t q = 0; q < nr; q++) {
+    if (recv_idx[q] < 0 || recv_idx[q] >= m->n[0] || (recv_idx[q] >= own_lo && recv_idx[q] < own_hi)) DDF_FAIL("set_halo_lists: recv entry %lld is not a ghost vertex", (long long)q);
+    hr[q] = (uint32_t)recv_idx[q];
+  }
+  DDF_CHECK(hg->send_idx.alloc(ctx, ns));
+  DDF_CHECK(hg->recv_idx.alloc(ctx, nr));
+  DDF_CHECK(hg->send_buf.alloc(ctx, ns));
+  DDF_CHECK(hg->recv_buf.alloc(ctx, nr));
+  if (ns) DDF_CUDA(cudaMemcpyAsync(hg->send_idx.p, hs.data(), ns * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (nr) DDF_CUDA(cudaMemcpyAsync(hg->recv_idx.p, hr.data(), nr * 4, cudaMemcpyHostToDevice, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+  DDF_TRY_END
+}
+
+static int halo_exchange_general(ddf_mesh* m, double* u, cudaStream_t stream) {
+  ddf_ctx* ctx = m->ctx;
+  HaloGeneral* hg = (HaloGeneral*)m->halo_gen;
+  if (ctx->nranks == 1 || hg->peers.empty()) return 0;
+  if (!ctx->nccl_comm) DDF_FAIL("halo: communicator not initialised (ddf_comm_init)");
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  const int np = (int)hg->peers.size();
+  const int64_t ns = hg->send_ptr[np], nr = hg->recv_ptr[np];
+  int grid;
+  if (ns) {
+    DDF_CHECK(grid_for(ns, 256, &grid));
+    k_gen_pack<<<grid, 256, 0, stream>>>(hg->send_idx.p, u, ns, hg->send_buf.p);
+    DDF_LAUNCH_CHECK(ctx);
+  }
+  DDF_NCCL(g_nccl.GroupStart());
+  for (int k = 0; k < np; k++) {
+    const int64_t s0 = hg->send_ptr[k], s1 = hg->send_ptr[k + 1], r0 = hg->recv_ptr[k], r1 = hg->recv_ptr[k + 1];
+    if (s1 > s0) DDF_NCCL(g_nccl.Send(hg->send_buf.p + s0, s1 - s0, ncclDouble, hg->peers[k], comm, stream));
+    if (r1 > r0) DDF_NCCL(g_nccl.Recv(hg->recv_buf.p + r0, r1 - r0, ncclDouble, hg->peers[k], comm, stream));
+  }
+  DDF_NCCL(g_nccl.GroupEnd());
+  ctx->launches++;
+  if (nr) {
+    DDF_CHECK(grid_for(nr, 256, &grid));
+    k_gen_unpack<<<grid, 256, 0, stream>>>(hg->recv_idx.p, hg->recv_buf.p, nr, u);
+    DDF_LAUNCH_CHECK(ctx);
+  }
+  return 0;
+}
+
 // rows of the rank-R tables this rank OWNS (smallest vertex in an owned plane), as one range [lo, hi):
 // below the top rank the tables are sorted lexicographically, so the owned rows are the lower-bound range of the first
 // column; the top-level table is in the caller's order, where the range is measured (and must be contiguous, which it is
@@ -156,8 +255,9 @@ extern "C" int ddf_mesh_owned_rows(ddf_mesh* m, int R, int64_t* lo, int64_t* hi)
   const int64_t nv = m->n[0], n = m->n[R];
   *lo = 0;
   *hi = n;
-  if (m->halo_plane <= 0 || n == 0) return 0;                 // not a slab: everything is owned
-  const int64_t vlo = m->halo_lo * m->halo_plane, vhi = nv - m->halo_hi * m->halo_plane;
+  if ((m->halo_plane <= 0 && !m->halo_gen) || n == 0) return 0;        // no halo: everything is owned
+  const int64_t vlo = m->halo_gen ? m->gen_own_lo : m->halo_lo * m->halo_plane;
+  const int64_t vhi = m->halo_gen ? m->gen_own_hi : nv - m->halo_hi * m->halo_plane;
   if (R == 0) { *lo = vlo; *hi = vhi; return 0; }
   const int N = R + 1;
   if (R < m->D) {
@@ -198,6 +298,7 @@ extern "C" int ddf_mesh_owned_rows(ddf_mesh* m, int R, int64_t* lo, int64_t* hi)
 // my highest owned plane -> rank+1 (into its last lower ghost plane), and the converse receives.
 static int halo_exchange_on(ddf_mesh* m, double* u, cudaStream_t stream) {
   ddf_ctx* ctx = m->ctx;
+  if (m->halo_gen) return halo_exchange_general(m, u, stream);
   if (ctx->nranks == 1) return 0;
   if (!ctx->nccl_comm) DDF_FAIL("halo: communicator not initialised (ddf_comm_init)");
   if (!m->halo_plane) DDF_FAIL("halo: slab not described (ddf_mesh_set_halo)");
@@ -307,6 +408,7 @@ __global__ void k_halo_signal(unsigned long long* to_lower, unsigned long long* 
 void ddf_halo_lists_release(ddf_mesh* m);
 void ddf_halo_release(ddf_mesh* m) {
   ddf_halo_lists_release(m);
+  ddf_halo_gen_release(m);
   HaloP2P* hp = (HaloP2P*)m->halo_p2p;
   if (!hp) return;
   if (hp->lo_base) cudaIpcCloseMemHandle(hp->lo_base);
@@ -583,6 +685,12 @@ extern "C" int ddf_halo_exchange_k(ddf_mesh* m, ddf_vec* x, int R) {
   ddf_ctx* ctx = m->ctx;
   if (R < 0 || R > m->D) DDF_FAIL("halo_exchange_k: 0 <= R <= D");
   if (x->n != m->n[R]) DDF_FAIL("halo_exchange_k: vector has length %lld, the mesh has %lld %d-simplices", (long long)x->n, (long long)m->n[R], R);
+  if (m->halo_gen) {
+    // vertex-range partition of a general mesh: ghost lists exist for vertices only
+    if (R != 0) DDF_FAIL("halo_exchange_k: a mesh partitioned by vertex ranges exchanges 0-cochains only (R = %d)", R);
+    DDF_CHECK(ddf_vec_settle(x));
+    return halo_exchange_general(m, x->d.p, ctx->stream);
+  }
   if (ctx->nranks == 1) return 0;
   if (!ctx->nccl_comm) DDF_FAIL("halo: communicator not initialised (ddf_comm_init)");
   if (!m->halo_plane) DDF_FAIL("halo: slab not described (ddf_mesh_set_halo)");
@@ -631,13 +739,24 @@ static int steps_dist(ddf_mesh* m, int kind, ddf_vec* u, ddf_vec* v, double dt, 
   const int64_t nv = m->n[0];
   if (u->n != nv || v->n != nv) DDF_FAIL("distributed step: vectors must have length n0");
   if (u == v) DDF_FAIL("distributed step: the two vectors must not alias");
-  if (!m->halo_plane) DDF_FAIL("distributed step: slab not described (ddf_mesh_set_halo)");
+  if (!m->halo_plane && !m->halo_gen) DDF_FAIL("distributed step: partition not described (ddf_mesh_set_halo / ddf_mesh_set_halo_lists)");
   DDF_CHECK(ddf_vec_settle(u));
   DDF_CHECK(ddf_vec_settle(v));
   if ((int64_t)m->utmp.n != nv) {
     DDF_CHECK(m->utmp.alloc(ctx, nv));
     // ghost planes that are never written must still hold finite data
     DDF_CUDA(cudaMemcpyAsync(m->utmp.p, u->d.p, nv * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  if (m->halo_gen) {
+    // general partition: the owned rows in one launch, then the list-driven ghost exchange of the new u
+    m->halo_last = 2;
+    for (int s = 0; s < nsteps; s++) {
+      DDF_CHECK(ddf_step_launch(m, ctx->stream, kind, u->d.p, v->d.p, m->utmp.p, dt, m->gen_own_lo, m->gen_own_hi, nullptr,
+                                nullptr, 0));
+      DDF_CHECK(halo_exchange_general(m, m->utmp.p, ctx->stream));
+      u->d.swap(m->utmp);
+    }
+    return 0;
   }
   const int64_t P = m->halo_plane;
   const int64_t own_lo = m->halo_lo * P, own_hi = nv - m->halo_hi * P;
@@ -681,7 +800,7 @@ static int steps_dist(ddf_mesh* m, int kind, ddf_vec* u, ddf_vec* v, double dt, 
 
 extern "C" int ddf_wave_leapfrog_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* v, double dt, int nsteps) {
   DDF_TRY_BEGIN
-  if (m->ctx->nranks == 1 && !m->halo_plane) return ddf_wave_leapfrog(m, u, v, dt, nsteps);
+  if (m->ctx->nranks == 1 && !m->halo_plane && !m->halo_gen) return ddf_wave_leapfrog(m, u, v, dt, nsteps);
   return steps_dist(m, 0, u, v, dt, nsteps);
   DDF_TRY_END
 }
@@ -690,7 +809,7 @@ extern "C" int ddf_wave_leapfrog_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* v, doubl
 // interface planes + step flags, or NCCL send/recv), u ping-pong, rho read-only
 extern "C" int ddf_poisson_jacobi_dist(ddf_mesh* m, ddf_vec* u, ddf_vec* rho, double theta, int nsweeps) {
   DDF_TRY_BEGIN
-  if (m->ctx->nranks == 1 && !m->halo_plane) return ddf_poisson_jacobi(m, u, rho, theta, nsweeps);
+  if (m->ctx->nranks == 1 && !m->halo_plane && !m->halo_gen) return ddf_poisson_jacobi(m, u, rho, theta, nsweeps);
   return steps_dist(m, 1, u, rho, theta, nsweeps);
   DDF_TRY_END
 }

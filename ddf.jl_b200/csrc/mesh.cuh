@@ -133,6 +133,10 @@ struct ddf_mesh {
   // slab halo of the distributed wave step (comm.cu): vertex planes along the
   // slowest axis; the first halo_lo / last halo_hi planes are ghosts owned by rank-1 / rank+1
   int64_t halo_plane = 0, halo_lo = 0, halo_hi = 0;
+  // general halo of a mesh partitioned by vertex ranges (comm.cu, ddf_mesh_set_halo_lists): owned local vertices are
+  // the contiguous range [gen_own_lo, gen_own_hi); ghost vertices are filled from explicit per-peer index lists
+  void* halo_gen = nullptr;
+  int64_t gen_own_lo = 0, gen_own_hi = -1;
   // fused peer-memory halo (comm.cu): arena + peer mappings, the step counter the flags carry;
   // state 0 = untried, 1 = in use, 2 = unavailable (NCCL send/recv is used instead)
   void* halo_p2p = nullptr;

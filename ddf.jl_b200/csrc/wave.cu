@@ -872,7 +872,7 @@ extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt,
   double* U[2] = {u->d.p, udot->d.p};
   // slab meshes (one rank per GPU): the ghost planes of the state every right-hand side reads are refreshed from
   // their owners first; ghost rows of the derivatives are scratch and never reach an owned row
-  const bool dist = ctx->nranks > 1 && m->halo_plane > 0;
+  const bool dist = ctx->nranks > 1 && (m->halo_plane > 0 || m->halo_gen);
   if (dist) DDF_CHECK(ddf_halo_exchange_raw(m, U[0]));
   DDF_CHECK(wave_rhs_launch(m, U[0], U[1], kp[0][0], kp[0][1]));
   for (int step = 0; step < nsteps; step++) {

@@ -159,3 +159,113 @@ def global_ids(mfd, slab: "Slab", R: int, counts: Optional[Sequence[int]] = None
     if (out < 0).any():
         raise RuntimeError(f"{int((out < 0).sum())} local {R}-simplices have no owner among the neighbouring slabs")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# General meshes (uploaded, refined, Delaunay): partition by contiguous ranges of the global vertex numbering.
+# north_star: "large refined meshes are partitioned by simplex ranges".  A simplex of any rank belongs to the rank
+# owning its smallest vertex, and face ids are lexicographic ranks (Manifolds.jl:735-757), so contiguous vertex ranges
+# give every rank contiguous ranges of simplices of every rank below the top one.
+# ----------------------------------------------------------------------------------------------------------------
+@dataclass
+class MeshPart:
+    """One rank's share of a mesh partitioned by vertex ranges (`partition_mesh`)."""
+    rank: int
+    nranks: int
+    cuts: np.ndarray            # nranks + 1 global vertex cuts: rank r owns [cuts[r], cuts[r+1])
+    local_to_global: np.ndarray  # ascending global ids of the local vertices (owned and ghost)
+    top_global: np.ndarray       # ascending rows of the global top-level table that are local
+    simplices: np.ndarray        # local top-level table in LOCAL vertex ids, rows in the global order
+    own_lo: int                  # owned local vertices are the contiguous local range [own_lo, own_hi)
+    own_hi: int
+    peers: np.ndarray            # ranks this one exchanges with, ascending
+    send_ptr: np.ndarray         # len(peers) + 1
+    send_idx: np.ndarray         # local ids of owned vertices that peers[k] holds as ghosts, ascending global id
+    recv_ptr: np.ndarray
+    recv_idx: np.ndarray         # local ids of this rank's ghosts owned by peers[k], ascending global id
+
+    @property
+    def nverts(self) -> int:
+        return int(self.local_to_global.shape[0])
+
+
+def vertex_cuts(nverts: int, nranks: int) -> np.ndarray:
+    """Balanced contiguous vertex ranges."""
+    return (np.arange(nranks + 1, dtype=np.int64) * int(nverts)) // int(nranks)
+
+
+def partition_mesh(simplices: np.ndarray, nverts: int, nranks: int, cuts: Optional[Sequence[int]] = None,
+                   ranks: Optional[Sequence[int]] = None) -> List[MeshPart]:
+    """Cut a mesh given by its 0-based top-level table (n_D, D+1) into `nranks` parts by vertex ranges.
+
+    Rank r's local mesh is the CLOSED STAR of its owned vertices -- every top-level simplex with at least one owned
+    vertex -- renumbered by the monotone map global -> local, rows kept in the global order.  Then every simplex of any
+    rank that contains an owned vertex is local together with ALL its cofaces, local face ids keep the global relative
+    order (lexicographic ranks under a monotone renumbering), and so the volumes, circumcentric dual volumes (sums
+    over ascending parents, Manifolds.jl:1187), star values, boundary flags and rows of L = laplace(Pr, 0) of the
+    owned vertices are bit-identical to the undivided mesh's.  Ghost vertices (local, not owned) are refreshed from
+    their owners through the index lists returned here; both sides of a pair list the shared vertices in ascending
+    global id, so the i-th value sent is the i-th value received.
+
+    The vertex numbering should have locality (a space-filling or generator order); with a random numbering the
+    closed stars cover most of the mesh.  `ranks` limits the returned parts (each rank usually wants its own)."""
+    simplices = np.sort(np.ascontiguousarray(simplices, dtype=np.int64), axis=1)
+    cuts = vertex_cuts(nverts, nranks) if cuts is None else np.asarray(cuts, dtype=np.int64)
+    if cuts.shape != (nranks + 1,) or cuts[0] != 0 or cuts[-1] != nverts or (np.diff(cuts) < 0).any():
+        raise ValueError("cuts must be nranks + 1 non-decreasing vertex ids from 0 to nverts")
+    if simplices.size and (simplices.min() < 0 or simplices.max() >= nverts):
+        raise ValueError("simplex table names a vertex outside 0..nverts")
+    # local vertex sets of every rank (needed by its neighbours for their send lists)
+    local_rows, local_verts = [], []
+    for r in range(nranks):
+        touch = ((simplices >= cuts[r]) & (simplices < cuts[r + 1])).any(axis=1)
+        rows = np.nonzero(touch)[0]
+        local_rows.append(rows)
+        verts = np.unique(simplices[rows])
+        # owned vertices that no simplex touches still belong to the rank (the reference keeps isolated vertices)
+        local_verts.append(np.union1d(verts, np.arange(cuts[r], cuts[r + 1], dtype=np.int64)))
+    parts = []
+    for r in (range(nranks) if ranks is None else ranks):
+        l2g = local_verts[r]
+        own_lo = int(np.searchsorted(l2g, cuts[r]))
+        own_hi = int(np.searchsorted(l2g, cuts[r + 1]))
+        ghost_g = np.concatenate([l2g[:own_lo], l2g[own_hi:]])
+        ghost_l = np.concatenate([np.arange(own_lo), np.arange(own_hi, l2g.shape[0])]).astype(np.int64)
+        owner = np.searchsorted(cuts, ghost_g, side="right") - 1
+        # an empty range can share its cut with the next one: the owner is the rank whose range really holds the vertex
+        peers, send_ptr, send_idx, recv_ptr, recv_idx = [], [0], [], [0], []
+        for p in range(nranks):
+            if p == r:
+                continue
+            rcv = ghost_l[owner == p]                                        # ascending local == ascending global
+            mine_on_p = local_verts[p][(local_verts[p] >= cuts[r]) & (local_verts[p] < cuts[r + 1])]
+            snd = np.searchsorted(l2g, mine_on_p)
+            if rcv.size == 0 and snd.size == 0:
+                continue
+            peers.append(p)
+            send_idx.append(snd)
+            recv_idx.append(rcv)
+            send_ptr.append(send_ptr[-1] + snd.size)
+            recv_ptr.append(recv_ptr[-1] + rcv.size)
+        cat = lambda xs: np.concatenate(xs).astype(np.int64) if xs else np.zeros(0, dtype=np.int64)
+        parts.append(MeshPart(rank=r, nranks=nranks, cuts=cuts, local_to_global=l2g, top_global=local_rows[r],
+                              simplices=np.searchsorted(l2g, simplices[local_rows[r]]), own_lo=own_lo, own_hi=own_hi,
+                              peers=np.asarray(peers, dtype=np.int32), send_ptr=np.asarray(send_ptr, dtype=np.int64),
+                              send_idx=cat(send_idx), recv_ptr=np.asarray(recv_ptr, dtype=np.int64),
+                              recv_idx=cat(recv_idx)))
+    return parts
+
+
+def distribute_mesh(name: str, simplices: np.ndarray, coords: np.ndarray, weights: Optional[np.ndarray], ctx,
+                    cuts: Optional[Sequence[int]] = None, use_weighted_duals: bool = True):
+    """This rank's part of `Manifold(name, simplices, coords, weights)` as a device mesh with its ghost lists set
+    (`ddf_mesh_set_halo_lists`).  Every rank passes the same global tables.  Returns (Manifold, MeshPart);
+    `ddf.wave.leapfrog_dist`, `poisson_jacobi_dist`, `tsit5` and `halo_exchange` (0-cochains) then work on it exactly
+    as on a generator slab, and `Manifold.owned_rows(R)` gives the owned row range of every rank below the top one."""
+    from .core import Manifold
+    part = partition_mesh(simplices, coords.shape[0], ctx.nranks, cuts, ranks=[ctx.rank])[0]
+    w = None if weights is None else np.asarray(weights, dtype=np.float64)[part.local_to_global]
+    mfd = Manifold.from_simplices(name, part.simplices, np.asarray(coords, dtype=np.float64)[part.local_to_global], w,
+                                  ctx=ctx, use_weighted_duals=use_weighted_duals)
+    mfd.set_halo_lists(part)
+    return mfd, part

@@ -256,6 +256,17 @@ int ddf_comm_destroy(ddf_ctx* ctx);
  * `ghost_lo` and last `ghost_hi` vertex planes are ghosts owned by rank-1 / rank+1
  * (0 at the domain ends).  Owned rows are the planes in between. */
 int ddf_mesh_set_halo(ddf_mesh* mesh, int64_t plane, int64_t ghost_lo, int64_t ghost_hi);
+/* Partition of a mesh of ANY origin (uploaded, refined, Delaunay) by contiguous ranges of the global vertex numbering
+ * (north_star: "large refined meshes are partitioned by simplex ranges"; the reference has no parallel code).  The
+ * local mesh is the closed star of the owned vertices, renumbered monotonically (host side: ddf.dist.partition_mesh),
+ * so owned local vertices are the range [own_lo, own_hi) and every owned row of the geometry / star / L tables equals
+ * the undivided mesh's bit for bit.  peers[k] (k < npeers) receives the owned values send_idx[send_ptr[k] ..
+ * send_ptr[k+1]) and fills the ghosts recv_idx[recv_ptr[k] .. recv_ptr[k+1]); 0-based local vertex ids, both sides of
+ * a pair in ascending global id.  After this call ddf_wave_leapfrog_dist, ddf_poisson_jacobi_dist, ddf_wave_tsit5,
+ * ddf_halo_exchange and ddf_mesh_owned_rows work as on a slab (one grouped ncclSend/ncclRecv per exchange). */
+int ddf_mesh_set_halo_lists(ddf_mesh* mesh, int64_t own_lo, int64_t own_hi, int npeers, const int32_t* peers,
+                            const int64_t* send_ptr, const int64_t* send_idx, const int64_t* recv_ptr,
+                            const int64_t* recv_idx);
 /* The rank-R simplices this rank owns (smallest vertex in an owned plane) as ONE row range [lo, hi) of its local
  * tables (lexicographic numbering makes them contiguous); a mesh without a halo owns everything. */
 int ddf_mesh_owned_rows(ddf_mesh* mesh, int R, int64_t* lo, int64_t* hi);

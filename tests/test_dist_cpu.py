@@ -291,3 +291,142 @@ def test_global_numbering_of_owned_simplices():
                 assert np.array_equal(glob, ftab[offset:offset + cnt]), (D, R, s.rank)
                 offset += cnt
             assert offset == ftab.shape[0], (D, R)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# General meshes partitioned by vertex ranges (ddf.dist.partition_mesh; device side ddf_mesh_set_halo_lists)
+# ------------------------------------------------------------------------------------------------------------------
+def _general_meshes():
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import ddf_oracle as o
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(11)
+    pts = rng.random((400, 2))
+    pts = pts[np.argsort(pts[:, 0])]                     # a numbering with locality: sorted along x
+    yield "delaunay2d", np.sort(Delaunay(pts).simplices.astype(np.int64), axis=1), pts, np.zeros(len(pts))
+    pts3 = rng.random((250, 3))
+    pts3 = pts3[np.argsort(pts3[:, 2])]
+    yield "delaunay3d", np.sort(Delaunay(pts3).simplices.astype(np.int64), axis=1), pts3, np.zeros(len(pts3))
+    simp, coords, weights = o.large_hypercube_tables(3, (4, 4, 4))
+    yield "kuhn3", simp, coords, weights                 # non-zero weights
+
+
+def test_general_partition_owned_rows_equal_undivided():
+    """Closed star of a vertex range, renumbered monotonically: the owned rows of the boundary mask, star_0 and
+    L = laplace(Pr,0) (values AND order of the entries) equal the undivided oracle's bit for bit; the ghost lists
+    of a pair match by position; every ghost is received exactly once."""
+    import ddf_oracle as o
+    from importlib import import_module
+    dd = import_module("ddf.jl_b200.dist")
+    for name, simp, coords, weights in _general_meshes():
+        full = o.build_manifold(name, simp, coords, weights)
+        fb, fL = o.wave_operators(full)
+        fL = fL.tocsr()
+        fL.sort_indices()
+        nv = coords.shape[0]
+        for world in (2, 3, 5):
+            parts = dd.partition_mesh(simp, nv, world)
+            assert sum(p.own_hi - p.own_lo for p in parts) == nv
+            for p in parts:
+                l2g = p.local_to_global
+                assert np.array_equal(l2g[p.own_lo:p.own_hi], np.arange(p.cuts[p.rank], p.cuts[p.rank + 1]))
+                assert np.array_equal(l2g[p.simplices], simp[p.top_global])
+                m = o.build_manifold(name, p.simplices, coords[l2g], weights[l2g])
+                b, L = o.wave_operators(m)
+                L = L.tocsr()
+                L.sort_indices()
+                for i in range(p.own_lo, p.own_hi):
+                    g = l2g[i]
+                    assert b[i] == fb[g]
+                    a0, a1 = L.indptr[i], L.indptr[i + 1]
+                    g0, g1 = fL.indptr[g], fL.indptr[g + 1]
+                    assert np.array_equal(l2g[L.indices[a0:a1]], fL.indices[g0:g1])
+                    assert np.array_equal(L.data[a0:a1], fL.data[g0:g1]), (name, world, p.rank, i)
+                # ghosts: each exactly once
+                nghost = p.nverts - (p.own_hi - p.own_lo)
+                assert p.recv_idx.shape[0] == nghost and np.unique(p.recv_idx).shape[0] == nghost
+                assert ((p.recv_idx < p.own_lo) | (p.recv_idx >= p.own_hi)).all()
+                assert ((p.send_idx >= p.own_lo) & (p.send_idx < p.own_hi)).all()
+            for p in parts:
+                for k, q in enumerate(p.peers):
+                    other = parts[q]
+                    kk = list(other.peers).index(p.rank)
+                    mine = p.local_to_global[p.send_idx[p.send_ptr[k]:p.send_ptr[k + 1]]]
+                    theirs = other.local_to_global[other.recv_idx[other.recv_ptr[kk]:other.recv_ptr[kk + 1]]]
+                    assert np.array_equal(mine, theirs)
+
+
+def _general_worker(rank, world, port, nsteps, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ddf_oracle as o
+    from importlib import import_module
+    dd = import_module("ddf.jl_b200.dist")
+    name, simp, coords, weights = next(iter(_general_meshes()))
+    part = dd.partition_mesh(simp, coords.shape[0], world, ranks=[rank])[0]
+    l2g = part.local_to_global
+    m = o.build_manifold(name, part.simplices, coords[l2g], weights[l2g])
+    b, L = o.wave_operators(m)
+    mask = 1.0 - b.astype(np.float64)
+    lo, hi = part.own_lo, part.own_hi
+    rng = np.random.default_rng(5)
+    u = rng.standard_normal(coords.shape[0])[l2g]
+    v = rng.standard_normal(coords.shape[0])[l2g]
+    dt = 1e-3
+    Lr = L.tocsr()
+    Lr.sort_indices()
+    for _ in range(nsteps):
+        lu = o._segment_sum_sequential(Lr.data * u[Lr.indices], Lr.indptr)
+        vn, un = v.copy(), u.copy()
+        vn[lo:hi] = v[lo:hi] + dt * (mask[lo:hi] * lu[lo:hi])
+        un[lo:hi] = u[lo:hi] + dt * (mask[lo:hi] * vn[lo:hi])
+        reqs, bufs = [], []
+        for k, peer in enumerate(part.peers):
+            s = part.send_idx[part.send_ptr[k]:part.send_ptr[k + 1]]
+            r = part.recv_idx[part.recv_ptr[k]:part.recv_ptr[k + 1]]
+            if s.size:
+                reqs.append(dist.isend(torch.from_numpy(un[s].copy()), int(peer)))
+            if r.size:
+                buf = torch.empty(r.size, dtype=torch.float64)
+                bufs.append((r, buf))
+                reqs.append(dist.irecv(buf, int(peer)))
+        for r in reqs:
+            r.wait()
+        for r, buf in bufs:
+            un[r] = buf.numpy()
+        u, v = un, vn
+    q.put((rank, int(part.cuts[rank]), int(part.cuts[rank + 1]), u[lo:hi].copy(), v[lo:hi].copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_general_partition_wave_equals_undivided():
+    """World-size-2 leapfrog on a vertex-range partition of a 2D Delaunay mesh (gloo send/recv along the ghost lists)
+    == the undivided oracle, bit for bit, from a random state."""
+    import ddf_oracle as o
+    world, nsteps = 2, 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_general_worker, args=(r, world, port, nsteps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    name, simp, coords, weights = next(iter(_general_meshes()))
+    m = o.build_manifold(name, simp, coords, weights)
+    rng = np.random.default_rng(5)
+    u0 = rng.standard_normal(coords.shape[0])
+    v0 = rng.standard_normal(coords.shape[0])
+    ou, ov = o.wave_leapfrog(m, u0, v0, 1e-3, nsteps)
+    for rank, glo, ghi, u, v in sorted(res):
+        assert np.array_equal(u, ou[glo:ghi]), f"rank {rank} u"
+        assert np.array_equal(v, ov[glo:ghi]), f"rank {rank} v"
