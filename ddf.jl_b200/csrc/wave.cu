@@ -198,7 +198,84 @@ struct RowArgs {
   const double* rho;
   const double* dinv;
   double theta;
+  // MODE 4 (one fused Tsit5 stage, ddf_wave_tsit5): the row sum is L * su_J (a.u = su_J); the epilogue forms
+  // k^v_J = (1-b) .* (L su_J) and the NEXT stage input su_{J+1} -- and, for J = 6, the new udot -- pointwise from the
+  // step's base state and the stored k^v_1 .. k^v_{J-1} (see tsit5_stage below)
+  const double* kv[5];
+  const double* base_u;
+  const double* base_v;
+  double* out_kv;       // k^v_J (null for J = 6: nobody reads it)
+  double* out_su;       // su_{J+1}; for J = 6 the new u (may be base_u: every thread reads its own row first)
+  double* out_sv;       // J = 6: the new udot (may be base_v)
+  int J;
 };
+
+// Tsitouras 5(4) tableau (OrdinaryDiffEq's Tsit5ConstantCache; pinned by its order conditions in tests/test_oracle_pins.py)
+__constant__ double c_tsit5_a[6][6] = {
+    {0.161, 0, 0, 0, 0, 0},
+    {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+    {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+    {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
+    {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+
+// One row of a fused Tsit5 stage.  The unfused sequence (six k_lincomb passes + six wave right-hand sides per step)
+// computes, per stage l, the input (su_l, sv_l) = U + dt * (a_l1 k_1 + ... ) with every product and sum rounded
+// separately, left to right, and k_l = ((1-b) .* sv_l, (1-b) .* (L su_l)).  Only k^v_l = (1-b) .* (L su_l) needs other
+// rows; k^u_l = m * sv_l and sv_l itself are functions of THIS row's base state and k^v_1 .. k^v_{l-1}.  So a stage
+// kernel recomputes them in registers with the same operations in the same order -- identical bits, and the 2 x 6
+// lincomb passes over up to 8 vectors disappear (the stored state per step shrinks from 16 vectors to 7).
+template <int J>
+__device__ __forceinline__ void tsit5_stage(double m, double lu, double (&kv)[6], double u0, double v0, double dt,
+                                            double& kv_new, double& su_next, double& sv_next) {
+  kv[J - 1] = kv_new = __dmul_rn(m, lu);
+  double ku[6];
+  ku[0] = __dmul_rn(m, v0);
+#pragma unroll
+  for (int l = 2; l <= J; l++) {
+    double s = __dmul_rn(c_tsit5_a[l - 2][0], kv[0]);
+#pragma unroll
+    for (int q = 1; q <= l - 2; q++) s = __dadd_rn(s, __dmul_rn(c_tsit5_a[l - 2][q], kv[q]));
+    ku[l - 1] = __dmul_rn(m, __dadd_rn(v0, __dmul_rn(dt, s)));
+  }
+  double s = __dmul_rn(c_tsit5_a[J - 1][0], ku[0]);
+#pragma unroll
+  for (int q = 1; q <= J - 1; q++) s = __dadd_rn(s, __dmul_rn(c_tsit5_a[J - 1][q], ku[q]));
+  su_next = __dadd_rn(u0, __dmul_rn(dt, s));
+  sv_next = 0.0;
+  if (J == 6) {
+    double t = __dmul_rn(c_tsit5_a[5][0], kv[0]);
+#pragma unroll
+    for (int q = 1; q <= 5; q++) t = __dadd_rn(t, __dmul_rn(c_tsit5_a[5][q], kv[q]));
+    sv_next = __dadd_rn(v0, __dmul_rn(dt, t));
+  }
+}
+
+// operands of row i requested up front (their latency overlaps the row sum), finished after it
+struct Tsit5Row {
+  double kv[6], u0, v0;
+};
+__device__ __forceinline__ void tsit5_load(const RowArgs& a, int64_t i, Tsit5Row& r) {
+#pragma unroll
+  for (int q = 0; q < 5; q++) r.kv[q] = q < a.J - 1 ? __ldg(a.kv[q] + i) : 0.0;
+  r.kv[5] = 0.0;
+  r.u0 = a.base_u[i];       // plain loads: for J = 6 these vectors are also written by this kernel (own row only)
+  r.v0 = a.base_v[i];
+}
+__device__ __forceinline__ void tsit5_finish(const RowArgs& a, int64_t i, double m, double lu, Tsit5Row& r) {
+  double kn, su, sv;
+  switch (a.J) {
+    case 1: tsit5_stage<1>(m, lu, r.kv, r.u0, r.v0, a.dt, kn, su, sv); break;
+    case 2: tsit5_stage<2>(m, lu, r.kv, r.u0, r.v0, a.dt, kn, su, sv); break;
+    case 3: tsit5_stage<3>(m, lu, r.kv, r.u0, r.v0, a.dt, kn, su, sv); break;
+    case 4: tsit5_stage<4>(m, lu, r.kv, r.u0, r.v0, a.dt, kn, su, sv); break;
+    case 5: tsit5_stage<5>(m, lu, r.kv, r.u0, r.v0, a.dt, kn, su, sv); break;
+    default: tsit5_stage<6>(m, lu, r.kv, r.u0, r.v0, a.dt, kn, su, sv); break;
+  }
+  if (a.out_kv) a.out_kv[i] = kn;
+  a.out_su[i] = su;
+  if (a.J == 6) a.out_sv[i] = sv;
+}
 
 // the epilogue of MODE 3, shared by every row kernel: one rounding per operation, in this order
 __device__ __forceinline__ double jacobi_update(double u_i, double lu, double rho_i, double dinv_i, double m, double theta) {
@@ -224,6 +301,10 @@ __device__ __forceinline__ void row_epilogue(const RowArgs& a, int64_t i, double
     const double w = jacobi_update(a.u[i], lu, a.rho[i], a.dinv[i], m, a.theta);
     a.out1[i] = w;
     peer_store(a, i, w);
+  } else if (MODE == 4) {
+    Tsit5Row r;
+    tsit5_load(a, i, r);
+    tsit5_finish(a, i, a.isb[i] ? 0.0 : 1.0, lu, r);
   } else {
     const double m = a.isb[i] ? 0.0 : 1.0;
     const double vn = __dadd_rn(a.out0[i], __dmul_rn(a.dt, __dmul_rn(m, lu)));
@@ -400,6 +481,10 @@ k_rows_stage(RowArgs a, const uint32_t* __restrict__ slice_ptr, const uint8_t* _
     const double w = jacobi_update(e1, lu, e0, e2, eb ? 0.0 : 1.0, a.theta);
     a.out1[i] = w;
     peer_store(a, i, w);
+  } else if (MODE == 4) {
+    Tsit5Row r;
+    tsit5_load(a, i, r);
+    tsit5_finish(a, i, eb ? 0.0 : 1.0, lu, r);
   } else {
     const double m = eb ? 0.0 : 1.0;
     const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, lu)));
@@ -508,7 +593,7 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
       if (lane < nruns) bulk_g2s(sb + (size_t)off * 8, a.u + start, (end - off) * 8u, &full[s], pol_keep);
       if (lane == 31 && nent) bulk_g2s(sb + g.o_ent, packed + (size_t)e0 * 10, nent * 10u, &full[s], pol_stream);
       if (lane == 30) bulk_g2s(sb + g.o_meta, meta + win * g.K * STAGE_META, mbytes, &full[s], pol_stream);
-      if (lane == 29 && MODE != 0) {
+      if (lane == 29 && MODE != 0 && MODE != 4) {
         bulk_g2s(sb + g.o_v, (MODE == 1 ? a.udot : (MODE == 3 ? a.rho : a.out0)) + r0, vbytes, &full[s], pol_stream);
         if (MODE == 2 || MODE == 3) bulk_g2s(sb + g.o_u, a.u + r0, vbytes, &full[s], pol_keep);
       }
@@ -547,6 +632,11 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
           const int64_t ip = win * g.K * DDF_SELL_WIN + (int64_t)kk * DDF_SELL_WIN + p;
           if (ip >= a.row0 && ip < a.row1) dinv_i = __ldg(a.dinv + ip);
         }
+        Tsit5Row trow;                                       // MODE 4: likewise
+        if (MODE == 4) {
+          const int64_t ip = win * g.K * DDF_SELL_WIN + (int64_t)kk * DDF_SELL_WIN + p;
+          if (ip >= a.row0 && ip < a.row1) tsit5_load(a, ip, trow);
+        }
         // entry offset of this slice inside the window's record: precomputed in the meta header
         const uint32_t part = reinterpret_cast<const uint32_t*>(metaS)[4 + gwarp];
         const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
@@ -568,6 +658,8 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
         if (i >= a.row0 && i < a.row1) {
           if (MODE == 0) {
             st_hint_f64(a.out0 + i, acc, pol_stream);
+          } else if (MODE == 4) {
+            tsit5_finish(a, i, (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0, acc, trow);
           } else {
             const double m = (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
             const double e0 = reinterpret_cast<const double*>(sb + g.o_v)[pl];
@@ -852,16 +944,11 @@ static int wave_rhs_launch(ddf_mesh* m, const double* u, const double* udot, dou
   return launch_rows<1>(m, m->ctx->stream, a);
 }
 
-extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt, int nsteps) {
-  DDF_TRY_BEGIN
-  DDF_CHECK(ddf_mesh_require_wave(m));
+// The unfused sequence (one k_lincomb pass per stage and component + one wave right-hand side per stage): kept as the
+// cross-check of the fused stages (ddf_set_tuning("wave", 1 << 29)); same bits.
+static int tsit5_unfused(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt, int nsteps, bool dist) {
   ddf_ctx* ctx = m->ctx;
   const int64_t nv = m->n[0];
-  if (u->n != nv || udot->n != nv) DDF_FAIL("wave_tsit5: vectors must have length n0=%lld", (long long)nv);
-  if (u == udot) DDF_FAIL("wave_tsit5: u and udot must not alias");
-  if (!nv || nsteps <= 0) return 0;
-  DDF_CHECK(ddf_vec_settle(u));
-  DDF_CHECK(ddf_vec_settle(udot));
   // work space: k1..k7 and tmp, each for (u, udot): 16 vertex vectors, kept with the mesh between calls
   const size_t nvp = ((size_t)nv + 1) & ~(size_t)1;       // even stride: every sub-vector stays 16-byte aligned (TMA, 128-bit loads)
   if (m->tsit_work.n != 16 * nvp) DDF_CHECK(m->tsit_work.alloc(ctx, 16 * nvp));
@@ -870,9 +957,6 @@ extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt,
     for (int c = 0; c < 2; c++) kp[s][c] = m->tsit_work.p + (size_t)(2 * s + c) * nvp;
   struct { double* p; } tmp[2] = {{m->tsit_work.p + 14 * nvp}, {m->tsit_work.p + 15 * nvp}};
   double* U[2] = {u->d.p, udot->d.p};
-  // slab meshes (one rank per GPU): the ghost planes of the state every right-hand side reads are refreshed from
-  // their owners first; ghost rows of the derivatives are scratch and never reach an owned row
-  const bool dist = ctx->nranks > 1 && (m->halo_plane > 0 || m->halo_gen);
   if (dist) DDF_CHECK(ddf_halo_exchange_raw(m, U[0]));
   DDF_CHECK(wave_rhs_launch(m, U[0], U[1], kp[0][0], kp[0][1]));
   for (int step = 0; step < nsteps; step++) {
@@ -891,7 +975,55 @@ extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt,
     }
     for (int c = 0; c < 2; c++) std::swap(kp[0][c], kp[6][c]);     // FSAL
   }
-  DDF_CUDA(cudaStreamSynchronize(ctx->stream));    // the work space is freed on return
+  return 0;
+}
+
+extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt, int nsteps) {
+  DDF_TRY_BEGIN
+  DDF_CHECK(ddf_mesh_require_wave(m));
+  ddf_ctx* ctx = m->ctx;
+  const int64_t nv = m->n[0];
+  if (u->n != nv || udot->n != nv) DDF_FAIL("wave_tsit5: vectors must have length n0=%lld", (long long)nv);
+  if (u == udot) DDF_FAIL("wave_tsit5: u and udot must not alias");
+  if (!nv || nsteps <= 0) return 0;
+  DDF_CHECK(ddf_vec_settle(u));
+  DDF_CHECK(ddf_vec_settle(udot));
+  // partitioned meshes (one rank per GPU): the ghost entries of the state every right-hand side reads are refreshed
+  // from their owners first; ghost rows of the derivatives are scratch and never reach an owned row
+  const bool dist = ctx->nranks > 1 && (m->halo_plane > 0 || m->halo_gen);
+  if (ctx->tune.wave & (1 << 29)) {
+    DDF_CHECK(tsit5_unfused(m, u, udot, dt, nsteps, dist));
+    DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  // Fused stages: SIX launches per step.  Stage kernel J gathers su_J (su_1 = u), stores k^v_J and the next stage
+  // input su_{J+1}; kernel 6 stores the new state over (u, udot).  FSAL is implicit: k_1 of the next step is what its
+  // kernel 1 computes from the new u.  Work space: k^v_1..k^v_5 and two stage inputs (ping-pong) = 7 vertex vectors.
+  const size_t nvp = ((size_t)nv + 1) & ~(size_t)1;       // even stride: every sub-vector stays 16-byte aligned (TMA)
+  if (m->tsit_work.n != 7 * nvp) DDF_CHECK(m->tsit_work.alloc(ctx, 7 * nvp));
+  double* kvp[5];
+  for (int q = 0; q < 5; q++) kvp[q] = m->tsit_work.p + (size_t)q * nvp;
+  double* su[2] = {m->tsit_work.p + 5 * nvp, m->tsit_work.p + 6 * nvp};
+  if (dist) DDF_CHECK(ddf_halo_exchange_raw(m, u->d.p));
+  for (int step = 0; step < nsteps; step++) {
+    for (int J = 1; J <= 6; J++) {
+      RowArgs a{};
+      a.u = J == 1 ? u->d.p : su[J & 1];                   // su_2 -> su[0], su_3 -> su[1], ...
+      for (int q = 0; q < J - 1; q++) a.kv[q] = kvp[q];
+      a.base_u = u->d.p;
+      a.base_v = udot->d.p;
+      a.out_kv = J < 6 ? kvp[J - 1] : nullptr;
+      a.out_su = J < 6 ? su[(J + 1) & 1] : u->d.p;
+      a.out_sv = J < 6 ? nullptr : udot->d.p;
+      a.J = J;
+      a.dt = dt;
+      a.row0 = 0;
+      a.row1 = nv;
+      DDF_CHECK(launch_rows<4>(m, ctx->stream, a));
+      if (dist) DDF_CHECK(ddf_halo_exchange_raw(m, a.out_su));
+    }
+  }
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
   DDF_TRY_END
 }

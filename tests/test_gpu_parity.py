@@ -762,6 +762,36 @@ def test_wave_tsit5_bit_exact(ddf, pairs, kind):
     assert np.array_equal(ddf.lincomb(base, dt, cs, ks, out=base).values, ref)
 
 
+@pytest.mark.parametrize("shape,tune", [((3, 40), 0), ((3, 40), 128), ((3, 12), 16), ((3, 12), 17), ((2, 96), 0), ((2, 96), 16)])
+def test_wave_tsit5_fused_stages_equal_unfused(ddf, ctx, shape, tune):
+    """The fused stage kernels of ddf_wave_tsit5 (six launches per step: row sum + the pointwise recomputation of the
+    stage inputs, csrc/wave.cu tsit5_stage) against the unfused sequence of k_lincomb passes and wave right-hand sides
+    (tuning bit 1 << 29) that test_wave_tsit5_bit_exact historically pinned to the oracle: same bits from a random
+    state, odd and even step counts, on every row storage (persistent pipeline, per-window staged kernel 128, SELL 16,
+    CSR 17; 2D rows in groups of two windows)."""
+    D, n = shape
+    ddf._lib.call("ddf_set_tuning", b"wave", tune)
+    try:
+        m = ddf.large_hypercube_manifold(D, (n,) * D, ctx=ctx)
+        dt = ddf.wave_dt(m)
+        rng = np.random.default_rng(n + tune)
+        u0, v0 = rng.standard_normal(m.nsimplices(0)), rng.standard_normal(m.nsimplices(0))
+        for steps in (1, 4):
+            ru, rv = ddf.Fun(m, ddf.Pr, 0, u0), ddf.Fun(m, ddf.Pr, 0, v0)
+            ddf._lib.call("ddf_set_tuning", b"wave", tune | (1 << 29))
+            ddf.wave_tsit5(m, ru, rv, dt, steps)
+            ddf._lib.call("ddf_set_tuning", b"wave", tune)
+            u, v = ddf.Fun(m, ddf.Pr, 0, u0), ddf.Fun(m, ddf.Pr, 0, v0)
+            ctx.sync()
+            l0 = ctx.launch_count()
+            ddf.wave_tsit5(m, u, v, dt, steps)
+            assert ctx.launch_count() - l0 == 6 * steps, (ctx.launch_count() - l0, steps)
+            assert np.array_equal(u.values, ru.values) and np.array_equal(v.values, rv.values), (shape, tune, steps)
+        m.close()
+    finally:
+        ddf._lib.call("ddf_set_tuning", b"wave", 0)
+
+
 def test_wave_tsit5_converges_to_exact_solution(ddf, ctx):
     """Wave.wave(Val(2), levels) with the reference's integrator: the error against
     cos(sqrt(2) pi t) prod sin(pi x) (wave.jl:150-163) falls at the same rate as with the leapfrog step
