@@ -33,6 +33,9 @@ int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n
 // windows per pipeline group the builder tries first for short rows (2D meshes); 0 = SELL with 16-bit offsets
 #define DDF_STAGE_K_SHORT 2
 
+#ifndef DDF_PIPE_UNR
+#define DDF_PIPE_UNR 4          // unroll factor of the consumers' row sum
+#endif
 #define PIPE_GROUP 256          // threads of one consumer group (= rows of a window)
 #define PIPE_MAX_STAGES 6
 // geometry of one stage of the persistent pipeline (k_rows_pipe below)
@@ -519,6 +522,28 @@ __device__ unsigned long long g_pipe_trace[8 * 1024];
 #define PIPE_TRACE(kind, it)
 #endif
 
+// The row sum of the pipeline consumers: a row's entries live in the stage's record as jagged diagonals (segments of
+// constant active-lane count, entries of a row `nact` apart); the adds are sequential in entry order.  Unrolled by 4
+// with a peeled remainder: fully unrolled, predicated blocks of 8 or 16 entries (all loads of a block up front) were
+// measured SLOWER at C4 (two steps per launch 0.454 -> 0.499 / 0.610 ms, profiles/r02_tuning.md).
+template <int UNR>
+__device__ __forceinline__ double pipe_row_sum(const double* __restrict__ valS, const uint16_t* __restrict__ slotS,
+                                               const double* __restrict__ stage, uint32_t part, uint32_t lane,
+                                               uint32_t mylen, uint32_t maxlen) {
+  uint32_t e = part + lane, q = 0;
+  double acc = 0.0;
+  while (q < maxlen) {                                                   // segments of constant active-lane count
+    const uint32_t nact = __popc(__ballot_sync(0xffffffffu, q < mylen));
+    const uint32_t qend = __shfl_sync(0xffffffffu, mylen, nact - 1);
+    if (lane < nact) {
+#pragma unroll UNR
+      for (uint32_t k = q; k < qend; k++, e += nact) acc = __dadd_rn(acc, __dmul_rn(valS[e], stage[slotS[e]]));
+    }
+    q = qend;
+  }
+  return acc;
+}
+
 template <int MODE, int NG>
 __global__ void __launch_bounds__(NG * PIPE_GROUP + 32, 1)
 k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __restrict__ packed,
@@ -640,18 +665,8 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
         // entry offset of this slice inside the window's record: precomputed in the meta header
         const uint32_t part = reinterpret_cast<const uint32_t*>(metaS)[4 + gwarp];
         const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
-        uint32_t e = part + lane, q = 0;
-        double acc = 0.0;
         PIPE_TRACE(3, it);
-        while (q < maxlen) {                                                   // segments of constant active-lane count
-          const uint32_t nact = __popc(__ballot_sync(0xffffffffu, q < mylen));
-          const uint32_t qend = __shfl_sync(0xffffffffu, mylen, nact - 1);
-          if (lane < nact) {
-#pragma unroll 4
-            for (uint32_t k = q; k < qend; k++, e += nact) acc = __dadd_rn(acc, __dmul_rn(valS[e], stage[slotS[e]]));
-          }
-          q = qend;
-        }
+        const double acc = pipe_row_sum<DDF_PIPE_UNR>(valS, slotS, stage, part, lane, mylen, maxlen);
         PIPE_TRACE(4, it);
         const uint32_t pl = (uint32_t)kk * DDF_SELL_WIN + p;                  // row offset inside the group
         const int64_t i = win * g.K * DDF_SELL_WIN + pl;

@@ -287,17 +287,7 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
         const int64_t i = t.win * g.K * DDF_SELL_WIN + pl;
         double dinv_i = 0.0;                                 // MODE 3: requested now, needed after the row sum
         if (MODE == 3 && i >= a.row0 && i < a.row1) dinv_i = __ldg(a.dinv + i);
-        uint32_t e = part + lane, q = 0;
-        double acc = 0.0;
-        while (q < maxlen) {
-          const uint32_t nact = __popc(__ballot_sync(0xffffffffu, q < mylen));
-          const uint32_t qend = __shfl_sync(0xffffffffu, mylen, nact - 1);
-          if (lane < nact) {
-#pragma unroll 4
-            for (uint32_t k = q; k < qend; k++, e += nact) acc = __dadd_rn(acc, __dmul_rn(valS[e], stage[slotS[e]]));
-          }
-          q = qend;
-        }
+        const double acc = pipe_row_sum<DDF_PIPE_UNR>(valS, slotS, stage, part, lane, mylen, maxlen);
         if (i >= a.row0 && i < a.row1) {
           const double m = (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
           const double ev = reinterpret_cast<const double*>(sb + g.o_v)[pl];
