@@ -274,4 +274,37 @@ function leapfrog!(m::DeviceManifold, u::DeviceVector, v::DeviceVector, dt::Floa
     return u, v
 end
 
+# ---------------------------------------------------------------------------------- one process per GPU
+# The host process (MPI.jl / Distributed) broadcasts the 128-byte id of rank 0 itself.
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    GC.@preserve id check(ccall((:ddf_comm_unique_id, lib), Cint, (Ptr{UInt8},), id))
+    return id
+end
+comm_init!(ctx::Ptr{Cvoid}, nranks::Int, rank::Int, id::Vector{UInt8}) =
+    GC.@preserve id check(ccall((:ddf_comm_init, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx, nranks, rank, id))
+
+# A mesh cut by vertex ranges (this rank's closed star of its owned vertices, renumbered monotonically): owned local
+# vertices are own_lo:own_hi-1 (0-based), peers[k] gets send_idx[send_ptr[k]+1:send_ptr[k+1]] and fills
+# recv_idx[recv_ptr[k]+1:recv_ptr[k+1]] (0-based local ids, both sides in ascending global id).
+function set_halo_lists!(m::DeviceManifold, own_lo::Int, own_hi::Int, peers::Vector{Int32}, send_ptr::Vector{Int64},
+                         send_idx::Vector{Int64}, recv_ptr::Vector{Int64}, recv_idx::Vector{Int64})
+    GC.@preserve peers send_ptr send_idx recv_ptr recv_idx check(ccall(
+        (:ddf_mesh_set_halo_lists, lib), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Cint, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+        m.h, own_lo, own_hi, length(peers), peers, send_ptr, send_idx, recv_ptr, recv_idx))
+    return m
+end
+
+# generator slab along the slowest axis: `plane` vertices per plane, ghost planes below / above the owned ones
+set_halo!(m::DeviceManifold, plane::Int, ghost_lo::Int, ghost_hi::Int) =
+    check(ccall((:ddf_mesh_set_halo, lib), Cint, (Ptr{Cvoid}, Int64, Int64, Int64), m.h, plane, ghost_lo, ghost_hi))
+
+# the fused step on a partitioned mesh: owned rows + ghost exchange per step (peer-memory halo on slabs, NCCL lists otherwise)
+function leapfrog_dist!(m::DeviceManifold, u::DeviceVector, v::DeviceVector, dt::Float64, nsteps::Int)
+    check(ccall((:ddf_wave_leapfrog_dist, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint),
+                m.h, u.h, v.h, dt, nsteps))
+    return u, v
+end
+
 end # module
