@@ -122,10 +122,12 @@ extern "C" int ddf_comm_allreduce(ddf_ctx* ctx, double* value, int op) {
   DDF_TRY_END
 }
 
+void ddf_halo_gen_release(ddf_mesh* m);
 extern "C" int ddf_mesh_set_halo(ddf_mesh* m, int64_t plane, int64_t ghost_lo, int64_t ghost_hi) {
   if (plane <= 0 || ghost_lo < 0 || ghost_hi < 0 || (ghost_lo + ghost_hi + 1) * plane > m->n[0] || m->n[0] % plane)
     DDF_FAIL("set_halo: inconsistent slab description (plane=%lld, lo=%lld, hi=%lld, V=%lld)", (long long)plane,
              (long long)ghost_lo, (long long)ghost_hi, (long long)m->n[0]);
+  ddf_halo_gen_release(m);            // a slab description replaces a vertex-range partition and vice versa
   m->halo_plane = plane;
   m->halo_lo = ghost_lo;
   m->halo_hi = ghost_hi;
@@ -168,15 +170,7 @@ extern "C" int ddf_mesh_set_halo_lists(ddf_mesh* m, int64_t own_lo, int64_t own_
   ddf_ctx* ctx = m->ctx;
   if (own_lo < 0 || own_hi < own_lo || own_hi > m->n[0]) DDF_FAIL("set_halo_lists: owned range [%lld, %lld) outside 0..%lld", (long long)own_lo, (long long)own_hi, (long long)m->n[0]);
   if (npeers < 0) DDF_FAIL("set_halo_lists: npeers < 0");
-  ddf_halo_gen_release(m);
-  HaloGeneral* hg = new HaloGeneral();
-  m->halo_gen = hg;
-  m->gen_own_lo = own_lo;
-  m->gen_own_hi = own_hi;
-  m->halo_plane = 0;
-  hg->peers.assign(peers, peers + npeers);
-  hg->send_ptr.assign(send_ptr, send_ptr + npeers + 1);
-  hg->recv_ptr.assign(recv_ptr, recv_ptr + npeers + 1);
+  // validate everything before the mesh's current description is replaced
   for (int k = 0; k < npeers; k++)
     if (peers[k] < 0 || peers[k] >= ctx->nranks || peers[k] == ctx->rank || send_ptr[k + 1] < send_ptr[k] || recv_ptr[k + 1] < recv_ptr[k])
       DDF_FAIL("set_halo_lists: bad peer %d", k);
@@ -190,6 +184,15 @@ extern "C" int ddf_mesh_set_halo_lists(ddf_mesh* m, int64_t own_lo, int64_t own_
     if (recv_idx[q] < 0 || recv_idx[q] >= m->n[0] || (recv_idx[q] >= own_lo && recv_idx[q] < own_hi)) DDF_FAIL("set_halo_lists: recv entry %lld is not a ghost vertex", (long long)q);
     hr[q] = (uint32_t)recv_idx[q];
   }
+  ddf_halo_gen_release(m);
+  HaloGeneral* hg = new HaloGeneral();
+  m->halo_gen = hg;
+  m->gen_own_lo = own_lo;
+  m->gen_own_hi = own_hi;
+  m->halo_plane = 0;
+  hg->peers.assign(peers, peers + npeers);
+  hg->send_ptr.assign(send_ptr, send_ptr + npeers + 1);
+  hg->recv_ptr.assign(recv_ptr, recv_ptr + npeers + 1);
   DDF_CHECK(hg->send_idx.alloc(ctx, ns));
   DDF_CHECK(hg->recv_idx.alloc(ctx, nr));
   DDF_CHECK(hg->send_buf.alloc(ctx, ns));

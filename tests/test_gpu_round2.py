@@ -426,3 +426,86 @@ def test_wavefront2_poisson_sweeps_equal_single_sweeps(ddf, ctx):
             assert ctx.launch_count() - l0 <= sweeps // 2 + (sweeps % 2) + 2, (ctx.launch_count() - l0, sweeps)
             assert np.array_equal(u.values, ref.values), (sweeps, tune)
     m.close()
+
+
+# ------------------------------------------------------------------ meshes of any origin, partitioned by vertex ranges
+def test_vertex_range_partition_emulated_on_one_gpu(ddf, ctx):
+    """ddf.dist.partition_mesh + ddf_mesh_set_halo_lists on ONE GPU (the 2-GPU run is tests/test_gpu_multi.py): the three
+    parts of a 2D Delaunay mesh live side by side as three device meshes, every part advances its OWNED rows with
+    ddf_wave_leapfrog_dist / ddf_poisson_jacobi_dist, and the ghost exchange between them is done through the host along
+    the partition's own send / receive lists.  Owned rows must equal the undivided mesh bit for bit -- geometry, star
+    values, L rows and the row-range launch are all in that comparison.  Then the argument checks of the C entry."""
+    import ctypes as C
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(31)
+    npts, world, nsteps = 6000, 3, 5
+    pts = rng.random((npts, 2))
+    pts = pts[np.argsort(pts[:, 0])]
+    simp = np.sort(Delaunay(pts).simplices.astype(np.int64), axis=1)
+    wts = np.zeros(npts)
+    gu, gv, gr = rng.standard_normal(npts), rng.standard_normal(npts), rng.standard_normal(npts)
+    dt = 1e-4
+    full = ddf.Manifold.from_simplices("full", simp, pts, wts, ctx=ctx)
+    full._geometry()
+    fu, fv = ddf.Fun(full, ddf.Pr, 0, gu), ddf.Fun(full, ddf.Pr, 0, gv)
+    ddf._lib.call("ddf_wave_leapfrog", full._h, fu._h, fv._h, dt, nsteps)
+    fp, frho = ddf.Fun(full, ddf.Pr, 0, gu), ddf.Fun(full, ddf.Pr, 0, gr)
+    ddf._lib.call("ddf_poisson_jacobi", full._h, fp._h, frho._h, 2.0 / 3.0, nsteps)
+    parts = ddf.dist.partition_mesh(simp, npts, world)
+    empty = np.zeros(0, dtype=np.int64)
+    meshes = []
+    for p in parts:
+        l2g = p.local_to_global
+        m = ddf.Manifold.from_simplices(f"part{p.rank}", p.simplices, pts[l2g], wts[l2g], ctx=ctx)
+        m._geometry()
+        # one process: no peers in the device lists, the exchange below goes through the host
+        ddf._lib.call("ddf_mesh_set_halo_lists", m._h, p.own_lo, p.own_hi, 0, None, ddf.core._i64p(np.zeros(1, dtype=np.int64)),
+                      ddf.core._i64p(empty), ddf.core._i64p(np.zeros(1, dtype=np.int64)), ddf.core._i64p(empty))
+        assert m.owned_rows(0) == (p.own_lo, p.own_hi)
+        meshes.append(m)
+
+    def exchange(funs):
+        vals = [f.values for f in funs]
+        for p, v in zip(parts, vals):
+            for k, q in enumerate(p.peers):
+                other = parts[q]
+                kk = list(other.peers).index(p.rank)
+                send = v[p.send_idx[p.send_ptr[k]:p.send_ptr[k + 1]]]
+                vals[q][other.recv_idx[other.recv_ptr[kk]:other.recv_ptr[kk + 1]]] = send
+        for f, v in zip(funs, vals):
+            f.upload(v)
+
+    for fn, ref, aux_g, coef in (("ddf_wave_leapfrog_dist", fu, gv, dt), ("ddf_poisson_jacobi_dist", fp, gr, 2.0 / 3.0)):
+        us = [ddf.Fun(m, ddf.Pr, 0, gu[p.local_to_global]) for m, p in zip(meshes, parts)]
+        auxs = [ddf.Fun(m, ddf.Pr, 0, aux_g[p.local_to_global]) for m, p in zip(meshes, parts)]
+        for _ in range(nsteps):
+            for m, u, a in zip(meshes, us, auxs):
+                ddf._lib.call(fn, m._h, u._h, a._h, coef, 1)
+            exchange(us)
+        want = ref.values
+        for p, u in zip(parts, us):
+            got = u.values[p.own_lo:p.own_hi]
+            assert np.array_equal(got, want[p.cuts[p.rank]:p.cuts[p.rank + 1]]), (fn, p.rank)
+        if fn == "ddf_wave_leapfrog_dist":
+            for p, a in zip(parts, auxs):
+                assert np.array_equal(a.values[p.own_lo:p.own_hi], fv.values[p.cuts[p.rank]:p.cuts[p.rank + 1]]), p.rank
+    # owned edges: one contiguous range per part, together the undivided mesh's edge table in order
+    fedges, off = full.get_simplices(1), 0
+    for m, p in zip(meshes, parts):
+        lo, hi = m.owned_rows(1)
+        e = p.local_to_global[m.get_simplices(1)[lo:hi]]
+        assert np.array_equal(e, fedges[off:off + len(e)])
+        off += len(e)
+    assert off == full.nsimplices(1)
+    # argument checks of ddf_mesh_set_halo_lists
+    m, p = meshes[1], parts[1]
+    one = np.zeros(2, dtype=np.int64)
+    peers = (C.c_int32 * 1)(0)
+    for args in ((-1, p.own_hi, 0, None, one[:1], empty, one[:1], empty),                    # range below 0
+                 (p.own_lo, m.nsimplices(0) + 1, 0, None, one[:1], empty, one[:1], empty),   # range above n0
+                 (p.own_lo, p.own_hi, 1, peers, one, empty, one, empty)):                    # peer 0 does not exist on 1 rank ... or is this rank
+        with pytest.raises(ddf.DDFError):
+            ddf._lib.call("ddf_mesh_set_halo_lists", m._h, args[0], args[1], args[2], args[3], *[ddf.core._i64p(np.ascontiguousarray(a)) for a in args[4:]])
+    for m in meshes:
+        m.close()
+    full.close()
