@@ -41,19 +41,22 @@ int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n
 // geometry of one stage of the persistent pipeline (k_rows_pipe below)
 struct PipeGeom {
   uint32_t o_ent, o_v, o_u, o_meta, stage_bytes;   // byte offsets inside a stage (x16): entries records, v, u, meta
+  uint32_t o_run2;                                 // MODE 5: the staged runs of the SECOND gathered vector (0 otherwise)
   int nstages;
   int K;                                           // windows per group (= per stage)
   int64_t nrows;
 };
 
-static int pipe_geometry(const ddf_mesh* m, PipeGeom* g) {
+// pair: two gathered vectors per stage and no v / u slices (the paired Tsit5 stages, MODE 5)
+static int pipe_geometry(const ddf_mesh* m, PipeGeom* g, bool pair = false) {
   const StageBufs& sb = m->lstage;
   auto up = [](uint32_t x, uint32_t a) { return (x + a - 1) / a * a; };
   g->K = sb.K;
-  g->o_ent = up(sb.max_slots * 8u, 16);
+  g->o_run2 = pair ? up(sb.max_slots * 8u, 16) : 0u;
+  g->o_ent = (pair ? 2u : 1u) * up(sb.max_slots * 8u, 16);
   g->o_v = g->o_ent + up(sb.max_entries * 10u, 16);
-  g->o_u = g->o_v + (uint32_t)sb.K * DDF_SELL_WIN * 8;
-  g->o_meta = g->o_u + (uint32_t)sb.K * DDF_SELL_WIN * 8;
+  g->o_u = g->o_v + (pair ? 0u : (uint32_t)sb.K * DDF_SELL_WIN * 8);
+  g->o_meta = g->o_u + (pair ? 0u : (uint32_t)sb.K * DDF_SELL_WIN * 8);
   g->stage_bytes = up(g->o_meta + (uint32_t)sb.K * STAGE_META, 128);
   const uint32_t budget = 227u * 1024u - 4096u;
   g->nstages = (int)(budget / g->stage_bytes);
@@ -211,6 +214,12 @@ struct RowArgs {
   double* out_su;       // su_{J+1}; for J = 6 the new u (may be base_u: every thread reads its own row first)
   double* out_sv;       // J = 6: the new udot (may be base_v)
   int J;
+  // MODE 5 (TWO Tsit5 stages per pass over L, tsit5_pair below): J = 1, 3, 5; a.u = su_J and u2 = su_{J+1} are gathered
+  // with the same entries; out_kv / out_kv2 = k^v_J / k^v_{J+1} (J < 5), out_su / out_su2 = su_{J+2} / su_{J+3};
+  // for J = 5: out_su = new u (may be base_u), out_sv = new udot (may be base_v), out_su2 = su_2 of the NEXT step
+  const double* u2;
+  double* out_kv2;
+  double* out_su2;
 };
 
 // Tsitouras 5(4) tableau (OrdinaryDiffEq's Tsit5ConstantCache; pinned by its order conditions in tests/test_oracle_pins.py)
@@ -278,6 +287,76 @@ __device__ __forceinline__ void tsit5_finish(const RowArgs& a, int64_t i, double
   if (a.out_kv) a.out_kv[i] = kn;
   a.out_su[i] = su;
   if (a.J == 6) a.out_sv[i] = sv;
+}
+
+// TWO stages per pass over L.  In dU = F U with F = [0, M; M L, 0] the stage input su_l depends on k^u_q = M sv_q
+// (q < l) only, and sv_q on k^v_r (r < q): su_l needs k^v_1 .. k^v_{l-2}, NOT k^v_{l-1}.  So su_J and su_{J+1} are both
+// known before stage J runs, the two row sums L su_J and L su_{J+1} share one read of the entries of L, and a Tsit5 step
+// is THREE passes over L instead of six: (1,2) -> su_3, su_4;  (3,4) -> su_5, su_6;  (5,6) -> the new state and su_2 of
+// the next step.  Every stage input / derivative is formed by the same operations in the same order as the unfused
+// sequence: same bits.
+template <int J>
+__device__ __forceinline__ void tsit5_pair(double m, double lu_a, double lu_b, double (&kv)[6], double u0, double v0, double dt,
+                                           double& kv_a, double& kv_b, double& o1, double& o2, double& o3) {
+  kv[J - 1] = kv_a = __dmul_rn(m, lu_a);
+  kv[J] = kv_b = __dmul_rn(m, lu_b);
+  constexpr int LMAX = J + 2 < 6 ? J + 2 : 6;           // k^u_1 .. k^u_LMAX are needed
+  double ku[6];
+  ku[0] = __dmul_rn(m, v0);
+#pragma unroll
+  for (int l = 2; l <= LMAX; l++) {
+    double s = __dmul_rn(c_tsit5_a[l - 2][0], kv[0]);
+#pragma unroll
+    for (int q = 1; q <= l - 2; q++) s = __dadd_rn(s, __dmul_rn(c_tsit5_a[l - 2][q], kv[q]));
+    ku[l - 1] = __dmul_rn(m, __dadd_rn(v0, __dmul_rn(dt, s)));
+  }
+  // su_l = u0 + dt * (a_{l,1} k^u_1 + ... + a_{l,l-1} k^u_{l-1}),  tableau row l - 2
+  {
+    constexpr int l = J + 2;
+    double s = __dmul_rn(c_tsit5_a[l - 2][0], ku[0]);
+#pragma unroll
+    for (int q = 1; q <= l - 2; q++) s = __dadd_rn(s, __dmul_rn(c_tsit5_a[l - 2][q], ku[q]));
+    o1 = __dadd_rn(u0, __dmul_rn(dt, s));
+  }
+  o3 = 0.0;
+  if (J < 5) {
+    constexpr int l = J < 5 ? J + 3 : 7;
+    double s = __dmul_rn(c_tsit5_a[l - 2][0], ku[0]);
+#pragma unroll
+    for (int q = 1; q <= l - 2; q++) s = __dadd_rn(s, __dmul_rn(c_tsit5_a[l - 2][q], ku[q]));
+    o2 = __dadd_rn(u0, __dmul_rn(dt, s));
+  } else {
+    // o1 is the new u; o2 = the new udot; o3 = su_2 of the next step = u' + dt * (a_21 * (m * udot'))
+    double t = __dmul_rn(c_tsit5_a[5][0], kv[0]);
+#pragma unroll
+    for (int q = 1; q <= 5; q++) t = __dadd_rn(t, __dmul_rn(c_tsit5_a[5][q], kv[q]));
+    o2 = __dadd_rn(v0, __dmul_rn(dt, t));
+    o3 = __dadd_rn(o1, __dmul_rn(dt, __dmul_rn(c_tsit5_a[0][0], __dmul_rn(m, o2))));
+  }
+}
+__device__ __forceinline__ void tsit5_pair_finish(const RowArgs& a, int64_t i, double m, double lu_a, double lu_b, Tsit5Row& r) {
+  double ka, kb, o1, o2, o3;
+  if (a.J == 1) tsit5_pair<1>(m, lu_a, lu_b, r.kv, r.u0, r.v0, a.dt, ka, kb, o1, o2, o3);
+  else if (a.J == 3) tsit5_pair<3>(m, lu_a, lu_b, r.kv, r.u0, r.v0, a.dt, ka, kb, o1, o2, o3);
+  else tsit5_pair<5>(m, lu_a, lu_b, r.kv, r.u0, r.v0, a.dt, ka, kb, o1, o2, o3);
+  if (a.J < 5) {
+    a.out_kv[i] = ka;
+    a.out_kv2[i] = kb;
+    a.out_su[i] = o1;
+    a.out_su2[i] = o2;
+  } else {
+    a.out_su[i] = o1;
+    a.out_sv[i] = o2;
+    a.out_su2[i] = o3;
+  }
+}
+// su_2 of the first step: u + dt * (a_21 * ((1-b) .* udot))
+__global__ void k_tsit5_first(const double* __restrict__ u, const double* __restrict__ udot, const uint8_t* __restrict__ isb,
+                              double dt, int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double m = isb[i] ? 0.0 : 1.0;
+  out[i] = __dadd_rn(u[i], __dmul_rn(dt, __dmul_rn(c_tsit5_a[0][0], __dmul_rn(m, udot[i]))));
 }
 
 // the epilogue of MODE 3, shared by every row kernel: one rounding per operation, in this order
@@ -544,6 +623,32 @@ __device__ __forceinline__ double pipe_row_sum(const double* __restrict__ valS, 
   return acc;
 }
 
+// the same walk with TWO gathered vectors (stage and stage2 share the slots): two independent sums, each in entry order
+template <int UNR>
+__device__ __forceinline__ void pipe_row_sum2(const double* __restrict__ valS, const uint16_t* __restrict__ slotS,
+                                              const double* __restrict__ stage, const double* __restrict__ stage2,
+                                              uint32_t part, uint32_t lane, uint32_t mylen, uint32_t maxlen, double& acc_a,
+                                              double& acc_b) {
+  uint32_t e = part + lane, q = 0;
+  double a0 = 0.0, a1 = 0.0;
+  while (q < maxlen) {
+    const uint32_t nact = __popc(__ballot_sync(0xffffffffu, q < mylen));
+    const uint32_t qend = __shfl_sync(0xffffffffu, mylen, nact - 1);
+    if (lane < nact) {
+#pragma unroll UNR
+      for (uint32_t k = q; k < qend; k++, e += nact) {
+        const double v = valS[e];
+        const uint32_t sl = slotS[e];
+        a0 = __dadd_rn(a0, __dmul_rn(v, stage[sl]));
+        a1 = __dadd_rn(a1, __dmul_rn(v, stage2[sl]));
+      }
+    }
+    q = qend;
+  }
+  acc_a = a0;
+  acc_b = a1;
+}
+
 template <int MODE, int NG>
 __global__ void __launch_bounds__(NG * PIPE_GROUP + 32, 1)
 k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __restrict__ packed,
@@ -607,6 +712,7 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
       const uint32_t mbytes = (uint32_t)g.K * STAGE_META;
       // requests per group: the runs of u, ONE range of entries records, ONE range of meta records, v (or udot), u
       uint32_t tx = total * 8u + nent * 10u + mbytes;
+      if (MODE == 5) tx += total * 8u;
       if (MODE == 1) tx += vbytes;
       if (MODE == 2 || MODE == 3) tx += 2u * vbytes;
       if (lane == 0) {
@@ -616,9 +722,10 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
       PIPE_TRACE(0, it);
       __syncwarp();
       if (lane < nruns) bulk_g2s(sb + (size_t)off * 8, a.u + start, (end - off) * 8u, &full[s], pol_keep);
+      if (MODE == 5 && lane < nruns) bulk_g2s(sb + g.o_run2 + (size_t)off * 8, a.u2 + start, (end - off) * 8u, &full[s], pol_keep);
       if (lane == 31 && nent) bulk_g2s(sb + g.o_ent, packed + (size_t)e0 * 10, nent * 10u, &full[s], pol_stream);
       if (lane == 30) bulk_g2s(sb + g.o_meta, meta + win * g.K * STAGE_META, mbytes, &full[s], pol_stream);
-      if (lane == 29 && MODE != 0 && MODE != 4) {
+      if (lane == 29 && MODE != 0 && MODE != 4 && MODE != 5) {
         bulk_g2s(sb + g.o_v, (MODE == 1 ? a.udot : (MODE == 3 ? a.rho : a.out0)) + r0, vbytes, &full[s], pol_stream);
         if (MODE == 2 || MODE == 3) bulk_g2s(sb + g.o_u, a.u + r0, vbytes, &full[s], pol_keep);
       }
@@ -658,7 +765,7 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
           if (ip >= a.row0 && ip < a.row1) dinv_i = __ldg(a.dinv + ip);
         }
         Tsit5Row trow;                                       // MODE 4: likewise
-        if (MODE == 4) {
+        if (MODE == 4 || MODE == 5) {
           const int64_t ip = win * g.K * DDF_SELL_WIN + (int64_t)kk * DDF_SELL_WIN + p;
           if (ip >= a.row0 && ip < a.row1) tsit5_load(a, ip, trow);
         }
@@ -666,7 +773,9 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
         const uint32_t part = reinterpret_cast<const uint32_t*>(metaS)[4 + gwarp];
         const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
         PIPE_TRACE(3, it);
-        const double acc = pipe_row_sum<DDF_PIPE_UNR>(valS, slotS, stage, part, lane, mylen, maxlen);
+        double acc, acc2 = 0.0;
+        if (MODE == 5) pipe_row_sum2<DDF_PIPE_UNR>(valS, slotS, stage, reinterpret_cast<const double*>(sb + g.o_run2), part, lane, mylen, maxlen, acc, acc2);
+        else acc = pipe_row_sum<DDF_PIPE_UNR>(valS, slotS, stage, part, lane, mylen, maxlen);
         PIPE_TRACE(4, it);
         const uint32_t pl = (uint32_t)kk * DDF_SELL_WIN + p;                  // row offset inside the group
         const int64_t i = win * g.K * DDF_SELL_WIN + pl;
@@ -675,6 +784,8 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
             st_hint_f64(a.out0 + i, acc, pol_stream);
           } else if (MODE == 4) {
             tsit5_finish(a, i, (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0, acc, trow);
+          } else if (MODE == 5) {
+            tsit5_pair_finish(a, i, (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0, acc, acc2, trow);
           } else {
             const double m = (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
             const double e0 = reinterpret_cast<const double*>(sb + g.o_v)[pl];
@@ -993,6 +1104,60 @@ static int tsit5_unfused(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt, int 
   return 0;
 }
 
+// Three launches of k_rows_pipe<5,2> per step (two stages each); tuning bit 1 << 30 selects one stage per launch.
+static int tsit5_paired(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt, int nsteps, bool dist, const PipeGeom& g) {
+  ddf_ctx* ctx = m->ctx;
+  const int64_t nv = m->n[0];
+  const StageBufs& sb = m->lstage;
+  const size_t nvp = ((size_t)nv + 1) & ~(size_t)1;       // even stride: every sub-vector stays 16-byte aligned (TMA)
+  // work space: k^v_1 .. k^v_4 and four stage inputs (su_2 | su_3, su_4 | su_5, su_6 rotate through them)
+  if (m->tsit_work.n != 8 * nvp) DDF_CHECK(m->tsit_work.alloc(ctx, 8 * nvp));
+  double* kvp[4];
+  double* X[4];
+  for (int q = 0; q < 4; q++) { kvp[q] = m->tsit_work.p + (size_t)q * nvp; X[q] = m->tsit_work.p + (size_t)(4 + q) * nvp; }
+  const int64_t gw = (int64_t)sb.K * DDF_SELL_WIN;
+  const int64_t g1 = (nv + gw - 1) / gw;
+  const size_t smem_p = (size_t)g.nstages * g.stage_bytes;
+  const int grid = (int)std::min<int64_t>(ctx->sm_count, g1);
+  DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+  auto pass = [&](int J, const double* ga, const double* gb, double* o1, double* o2, double* o3) -> int {
+    RowArgs a{};
+    a.isb = m->isbnd[0].p;
+    a.u = ga;
+    a.u2 = gb;
+    for (int q = 0; q < J - 1; q++) a.kv[q] = kvp[q];
+    a.base_u = u->d.p;
+    a.base_v = udot->d.p;
+    a.J = J;
+    a.dt = dt;
+    a.row0 = 0;
+    a.row1 = nv;
+    if (J < 5) { a.out_kv = kvp[J - 1]; a.out_kv2 = kvp[J]; a.out_su = o1; a.out_su2 = o2; }
+    else { a.out_su = o1; a.out_sv = o2; a.out_su2 = o3; }
+    k_rows_pipe<5, 2><<<grid, 2 * PIPE_GROUP + 32, smem_p, ctx->stream>>>(a, sb.tab.p, sb.packed.p, sb.meta.p, 0, g1, g);
+    DDF_LAUNCH_CHECK(ctx);
+    return 0;
+  };
+  int gridp;
+  DDF_CHECK(grid_for(nv, 256, &gridp));
+  if (dist) DDF_CHECK(ddf_halo_exchange_raw(m, u->d.p));
+  k_tsit5_first<<<gridp, 256, 0, ctx->stream>>>(u->d.p, udot->d.p, m->isbnd[0].p, dt, nv, X[0]);
+  DDF_LAUNCH_CHECK(ctx);
+  if (dist) DDF_CHECK(ddf_halo_exchange_raw(m, X[0]));
+  int c = 0;                                               // X[c] holds su_2 of the current step
+  for (int step = 0; step < nsteps; step++) {
+    double *s2 = X[c], *s3 = X[(c + 1) & 3], *s4 = X[(c + 2) & 3], *s5 = X[(c + 3) & 3], *s6 = X[c], *n2 = X[(c + 1) & 3];
+    DDF_CHECK(pass(1, u->d.p, s2, s3, s4, nullptr));
+    if (dist) { DDF_CHECK(ddf_halo_exchange_raw(m, s3)); DDF_CHECK(ddf_halo_exchange_raw(m, s4)); }
+    DDF_CHECK(pass(3, s3, s4, s5, s6, nullptr));           // su_6 overwrites su_2, which nobody reads any more
+    if (dist) { DDF_CHECK(ddf_halo_exchange_raw(m, s5)); DDF_CHECK(ddf_halo_exchange_raw(m, s6)); }
+    DDF_CHECK(pass(5, s5, s6, u->d.p, udot->d.p, n2));     // in place: a row reads its own u, udot before it stores them
+    if (dist) { DDF_CHECK(ddf_halo_exchange_raw(m, u->d.p)); DDF_CHECK(ddf_halo_exchange_raw(m, n2)); }
+    c = (c + 1) & 3;
+  }
+  return 0;
+}
+
 extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt, int nsteps) {
   DDF_TRY_BEGIN
   DDF_CHECK(ddf_mesh_require_wave(m));
@@ -1010,6 +1175,16 @@ extern "C" int ddf_wave_tsit5(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt,
     DDF_CHECK(tsit5_unfused(m, u, udot, dt, nsteps, dist));
     DDF_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
+  }
+  // Paired stages (default on meshes whose rows are staged): THREE passes over L per step, see tsit5_pair.
+  {
+    PipeGeom gp;
+    const int tw = ctx->tune.wave;
+    if (m->lstage.ok && (tw & 3) == 0 && !(tw & 128) && !(tw & (1 << 30)) && pipe_geometry(m, &gp, true)) {
+      DDF_CHECK(tsit5_paired(m, u, udot, dt, nsteps, dist, gp));
+      DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+      return 0;
+    }
   }
   // Fused stages: SIX launches per step.  Stage kernel J gathers su_J (su_1 = u), stores k^v_J and the next stage
   // input su_{J+1}; kernel 6 stores the new state over (u, udot).  FSAL is implicit: k_1 of the next step is what its

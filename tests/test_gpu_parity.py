@@ -762,21 +762,22 @@ def test_wave_tsit5_bit_exact(ddf, pairs, kind):
     assert np.array_equal(ddf.lincomb(base, dt, cs, ks, out=base).values, ref)
 
 
-@pytest.mark.parametrize("shape,tune", [((3, 40), 0), ((3, 40), 128), ((3, 12), 16), ((3, 12), 17), ((2, 96), 0), ((2, 96), 16)])
+@pytest.mark.parametrize("shape,tune", [((3, 40), 0), ((3, 40), 1 << 30), ((3, 40), 128), ((3, 12), 16), ((3, 12), 17),
+                                        ((2, 96), 0), ((2, 96), 1 << 30), ((2, 96), 16), ((3, 72), 0)])
 def test_wave_tsit5_fused_stages_equal_unfused(ddf, ctx, shape, tune):
-    """The fused stage kernels of ddf_wave_tsit5 (six launches per step: row sum + the pointwise recomputation of the
-    stage inputs, csrc/wave.cu tsit5_stage) against the unfused sequence of k_lincomb passes and wave right-hand sides
-    (tuning bit 1 << 29) that test_wave_tsit5_bit_exact historically pinned to the oracle: same bits from a random
-    state, odd and even step counts, on every row storage (persistent pipeline, per-window staged kernel 128, SELL 16,
-    CSR 17; 2D rows in groups of two windows)."""
+    """ddf_wave_tsit5 against the unfused sequence of k_lincomb passes and wave right-hand sides (tuning bit 1 << 29) that
+    test_wave_tsit5_bit_exact pins to the oracle: same bits from a random state, odd and even step counts, on every row
+    storage.  Default on staged rows: THREE passes over L per step, two stages each (csrc/wave.cu tsit5_pair: su_l does
+    not depend on k^v_{l-1}, so stages J and J+1 share one read of L); 1 << 30, the per-window staged kernel (128), SELL
+    (16) and CSR (17): six fused single-stage launches (row sum + pointwise recomputation of the stage inputs)."""
     D, n = shape
     ddf._lib.call("ddf_set_tuning", b"wave", tune)
     try:
         m = ddf.large_hypercube_manifold(D, (n,) * D, ctx=ctx)
         dt = ddf.wave_dt(m)
-        rng = np.random.default_rng(n + tune)
+        rng = np.random.default_rng(n + (tune & 0xffff))
         u0, v0 = rng.standard_normal(m.nsimplices(0)), rng.standard_normal(m.nsimplices(0))
-        for steps in (1, 4):
+        for steps in (1, 4, 5):
             ru, rv = ddf.Fun(m, ddf.Pr, 0, u0), ddf.Fun(m, ddf.Pr, 0, v0)
             ddf._lib.call("ddf_set_tuning", b"wave", tune | (1 << 29))
             ddf.wave_tsit5(m, ru, rv, dt, steps)
@@ -785,8 +786,10 @@ def test_wave_tsit5_fused_stages_equal_unfused(ddf, ctx, shape, tune):
             ctx.sync()
             l0 = ctx.launch_count()
             ddf.wave_tsit5(m, u, v, dt, steps)
-            assert ctx.launch_count() - l0 == 6 * steps, (ctx.launch_count() - l0, steps)
+            paired = tune == 0 and ddf.wave_format(m) == "staged"
+            assert ctx.launch_count() - l0 == (3 * steps + 1 if paired else 6 * steps), (ctx.launch_count() - l0, steps)
             assert np.array_equal(u.values, ru.values) and np.array_equal(v.values, rv.values), (shape, tune, steps)
+        assert ddf.wave_format(m) == ("staged" if tune in (0, 1 << 30, 128) else "sell")
         m.close()
     finally:
         ddf._lib.call("ddf_set_tuning", b"wave", 0)

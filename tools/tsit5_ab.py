@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""A/B of the Tsit5 step at C4 (or argv[1]): the fused stage kernels (default) against the unfused sequence of k_lincomb
-passes and right-hand sides (tuning bit 1 << 29); bits compared."""
+"""A/B of the Tsit5 step at C4 (or argv[1]): three paired-stage passes over L (default), six fused single-stage launches
+(tuning bit 1 << 30) and the unfused sequence of k_lincomb passes and right-hand sides (1 << 29); bits compared."""
 import os
 import sys
 
@@ -15,7 +15,7 @@ dt = ddf.wave_dt(m)
 rng = np.random.default_rng(3)
 u0, v0 = rng.standard_normal(m.nsimplices(0)), rng.standard_normal(m.nsimplices(0))
 ref = None
-for name, tune in (("unfused", 1 << 29), ("fused stage kernels", 0)):
+for name, tune in (("unfused", 1 << 29), ("six fused single-stage launches", 1 << 30), ("three paired-stage passes over L", 0)):
     ddf._lib.call("ddf_set_tuning", b"wave", tune)
     u, v = ddf.Fun(m, ddf.Pr, 0, u0), ddf.Fun(m, ddf.Pr, 0, v0)
     ddf.wave_tsit5(m, u, v, dt, 2)
