@@ -779,36 +779,40 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
         PIPE_TRACE(4, it);
         const uint32_t pl = (uint32_t)kk * DDF_SELL_WIN + p;                  // row offset inside the group
         const int64_t i = win * g.K * DDF_SELL_WIN + pl;
+        // what the epilogue needs from the stage goes to registers first; after the LAST window of the group the stage
+        // is handed back to the producer BEFORE the epilogue (global loads consumed, arithmetic, stores) runs
+        const double m = (MODE != 0 && (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p]) ? 0.0 : 1.0;
+        double e0 = 0.0, eu = 0.0;
+        if (MODE == 1 || MODE == 2 || MODE == 3) e0 = reinterpret_cast<const double*>(sb + g.o_v)[pl];
+        if (MODE == 2 || MODE == 3) eu = reinterpret_cast<const double*>(sb + g.o_u)[pl];
+        if (kk == g.K - 1) {
+          __syncwarp();
+          PIPE_TRACE(2, it);
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+        }
         if (i >= a.row0 && i < a.row1) {
           if (MODE == 0) {
             st_hint_f64(a.out0 + i, acc, pol_stream);
           } else if (MODE == 4) {
-            tsit5_finish(a, i, (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0, acc, trow);
+            tsit5_finish(a, i, m, acc, trow);
           } else if (MODE == 5) {
-            tsit5_pair_finish(a, i, (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0, acc, acc2, trow);
+            tsit5_pair_finish(a, i, m, acc, acc2, trow);
+          } else if (MODE == 1) {
+            a.out0[i] = __dmul_rn(m, e0);
+            a.out1[i] = __dmul_rn(m, acc);
+          } else if (MODE == 3) {
+            const double w = jacobi_update(eu, acc, e0, dinv_i, m, a.theta);
+            a.out1[i] = w;
+            peer_store(a, i, w);
           } else {
-            const double m = (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
-            const double e0 = reinterpret_cast<const double*>(sb + g.o_v)[pl];
-            if (MODE == 1) {
-              a.out0[i] = __dmul_rn(m, e0);
-              a.out1[i] = __dmul_rn(m, acc);
-            } else if (MODE == 3) {
-              const double w = jacobi_update(reinterpret_cast<const double*>(sb + g.o_u)[pl], acc, e0, dinv_i, m, a.theta);
-              a.out1[i] = w;
-              peer_store(a, i, w);
-            } else {
-              const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, acc)));
-              a.out0[i] = vn;
-              const double w = __dadd_rn(reinterpret_cast<const double*>(sb + g.o_u)[pl], __dmul_rn(a.dt, __dmul_rn(m, vn)));
-              a.out1[i] = w;
-              peer_store(a, i, w);
-            }
+            const double vn = __dadd_rn(e0, __dmul_rn(a.dt, __dmul_rn(m, acc)));
+            a.out0[i] = vn;
+            const double w = __dadd_rn(eu, __dmul_rn(a.dt, __dmul_rn(m, vn)));
+            a.out1[i] = w;
+            peer_store(a, i, w);
           }
         }
       }
-      __syncwarp();
-      PIPE_TRACE(2, it);
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
     }
   }
 }
