@@ -36,6 +36,11 @@ int ddf_reduce(ddf_ctx* c, int mode, const double* x, const double* y, int64_t n
 #ifndef DDF_PIPE_UNR
 #define DDF_PIPE_UNR 4          // unroll factor of the consumers' row sum
 #endif
+#ifndef PIPE_PF
+#define PIPE_PF 2               // L2 prefetch distance (iterations) of the entries in the Tsit5 stage kernels; 0 = off.
+                                // Measured at C4 (paired stages): 0 / 2 / 3 / 5 -> 2.27 / 2.05 / 2.06 / 2.12 ms per step; the
+                                // same prefetch in the HBM-bound one-step leapfrog kernel LOSES (0.482 -> 0.546 ms): Tsit5 only
+#endif
 #define PIPE_GROUP 256          // threads of one consumer group (= rows of a window)
 #define PIPE_MAX_STAGES 6
 // geometry of one stage of the persistent pipeline (k_rows_pipe below)
@@ -700,6 +705,17 @@ k_rows_pipe(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* __
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tfull[td])), "r"(STAGE_TAB * 4) : "memory");
         bulk_g2s(tabS + td * STAGE_TAB, tab + (win + PIPE_TD * stride) * STAGE_TAB, STAGE_TAB * 4, &tfull[td], pol_stream);
+      }
+      if (PIPE_PF > 0 && (MODE == 4 || MODE == 5) && win + PIPE_PF * stride < w1) {
+        // ask L2 for the entries + meta records of the window PIPE_PF iterations ahead (its table arrived long ago): the
+        // fill of that stage then costs an L2 round trip instead of an HBM one -- it matters where few stages fit
+        const int tp = (int)((it + PIPE_PF) % PIPE_TD);
+        stage_wait(&tfull[tp], (uint32_t)((it + PIPE_PF) / PIPE_TD) & 1u);
+        if (lane == 0) {
+          const uint32_t pe0 = tabS[tp * STAGE_TAB + 2], pn = tabS[tp * STAGE_TAB + 3];
+          if (pn) bulk_prefetch_l2(packed + (size_t)pe0 * 10, pn * 10u);
+          bulk_prefetch_l2(meta + (win + PIPE_PF * stride) * g.K * STAGE_META, (uint32_t)g.K * STAGE_META);
+        }
       }
       const int s = (int)(it % g.nstages);
       const uint32_t j = (uint32_t)(it / g.nstages);
