@@ -503,12 +503,14 @@ def run_b200(args):
         ctx.tic()
         ddf.wave_tsit5(mfd, ut, vt, dt, 5)
         t5 = ctx.toc() / 5
-        # bytes of one Tsit5 step in this library's format: six reads of the staged rows of L (the integrator needs six
-        # right-hand sides by construction) + the 45 vertex-vector passes of the fused stage kernels (csrc/wave.cu)
+        # bytes of one Tsit5 step in this library's format: THREE reads of the staged rows of L (two stages share one
+        # read: csrc/wave.cu tsit5_pair; the unfused integrator needs six) + the 29 vertex-vector passes of the three
+        # paired-stage kernels (gathered stage inputs, base state, stored k's, outputs)
         _, fmt_b = ddf.wave_step_bytes(mfd)
-        t5_bytes = 6 * (fmt_b - 32 * cnt[0]) + 45 * 8 * cnt[0]
-        tsit5 = {"ms_per_step": t5, "rhs_per_step": 6, "launches_per_step": 6, "vertex_updates_per_s": cnt[0] / (t5 * 1e-3),
-                 "format_bytes": int(t5_bytes), "GBps": t5_bytes / t5 * 1e-6, "frac": t5_bytes / t5 * 1e-6 / peak}
+        t5_bytes = 3 * (fmt_b - 32 * cnt[0]) + 29 * 8 * cnt[0]
+        tsit5 = {"ms_per_step": t5, "rhs_per_step": 6, "launches_per_step": 3, "vertex_updates_per_s": cnt[0] / (t5 * 1e-3),
+                 "format_bytes": int(t5_bytes), "GBps": t5_bytes / t5 * 1e-6, "frac": t5_bytes / t5 * 1e-6 / peak,
+                 "reads_of_L_per_step": 3}
         del ut, vt
     # BASELINE config 2: the Laplacian of examples/poisson.jl on the 2D simplex refined 10x (1,048,576 triangles;
     # Delaunay through scipy like the reference): y = L rho
