@@ -225,7 +225,9 @@ int ddf_wave_dt(ddf_mesh* mesh, double* dt);
  * one kernel per step, L applied matrix-free from the vertex adjacency. */
 int ddf_wave_leapfrog(ddf_mesh* mesh, ddf_vec* u, ddf_vec* v, double dt, int nsteps);
 /* `nsteps` fixed steps of Tsit5 on dU = F U, U = [u; udot] -- what examples/wave.jl:134 runs
- * (`solve(prob, Tsit5(); adaptive=false, dt=dt)`); in place. */
+ * (`solve(prob, Tsit5(); adaptive=false, dt=dt)`); in place.  Same roundings as the unfused perform_step! (stage
+ * broadcasts with separately rounded products and sums, left to right); on meshes whose rows are staged a step is three
+ * passes over L, two stages each (a stage input of u does not depend on the previous stage's derivative of udot). */
 int ddf_wave_tsit5(ddf_mesh* mesh, ddf_vec* u, ddf_vec* udot, double dt, int nsteps);
 /* Fused Poisson relaxation sweep (weighted Jacobi on L u = rho with the boundary values of u held fixed --
  * the Dirichlet problem of examples/poisson.jl:75-81): u <- u + theta * ((1-b) .* ((rho - L u) ./ diag(L))),
