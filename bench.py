@@ -343,15 +343,17 @@ def run_b200(args):
     ctx.tic()
     ddf._lib.call("ddf_mesh_assemble", mfd._h)
     asm_first_ms = ctx.toc()
-    mfd.close()
-    if N == 1:
-        mfd = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx, assemble=False)
-    else:
-        mfd, slab = ddf.dist.slab_hypercube(3, (n, n, n if args.strong else n * N), ctx, assemble=False)
-    ctx.sync()
-    ctx.tic()
-    ddf._lib.call("ddf_mesh_assemble", mfd._h)
-    asm_ms = ctx.toc()
+    asm_ms = float("inf")
+    for _ in range(2):                   # best of two further assemblies (the pool is warm now)
+        mfd.close()
+        if N == 1:
+            mfd = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx, assemble=False)
+        else:
+            mfd, slab = ddf.dist.slab_hypercube(3, (n, n, n if args.strong else n * N), ctx, assemble=False)
+        ctx.sync()
+        ctx.tic()
+        ddf._lib.call("ddf_mesh_assemble", mfd._h)
+        asm_ms = min(asm_ms, ctx.toc())
     mfd._geometry()
     ctx.sync()
     cnt = [mfd.nsimplices(k) for k in range(4)]
