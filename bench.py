@@ -498,19 +498,24 @@ def run_b200(args):
             del A, xd, yd
     # the reference's own integrator on the same mesh: fixed-step Tsit5 (wave.jl:134), 6 right-hand sides per step
     tsit5 = None
-    if N == 1 and not args.no_extras:
+    if not args.no_extras:
+        # at N > 1 on the slab meshes: the ghost planes of the two new stage inputs travel after every pass (one grouped
+        # ncclSend/ncclRecv per pass), timed like the wave step (barrier, max over ranks)
         ut, vt = ddf.sample(mfd, "wave"), ddf.Fun(mfd, ddf.Pr, 0)
         ddf.wave_tsit5(mfd, ut, vt, dt, 1)
         ctx.sync()
+        barrier()
         ctx.tic()
         ddf.wave_tsit5(mfd, ut, vt, dt, 5)
-        t5 = ctx.toc() / 5
+        t5 = max_over_ranks(ctx.toc() / 5)
+        barrier()
         # bytes of one Tsit5 step in this library's format: THREE reads of the staged rows of L (two stages share one
         # read: csrc/wave.cu tsit5_pair; the unfused integrator needs six) + the 29 vertex-vector passes of the three
         # paired-stage kernels (gathered stage inputs, base state, stored k's, outputs)
         _, fmt_b = ddf.wave_step_bytes(mfd)
         t5_bytes = 3 * (fmt_b - 32 * cnt[0]) + 29 * 8 * cnt[0]
-        tsit5 = {"ms_per_step": t5, "rhs_per_step": 6, "launches_per_step": 3, "vertex_updates_per_s": cnt[0] / (t5 * 1e-3),
+        tsit5 = {"ms_per_step": t5, "rhs_per_step": 6, "launches_per_step": 3,
+                 "vertex_updates_per_s": sum_over_ranks(float(own[0])) / (t5 * 1e-3),
                  "format_bytes": int(t5_bytes), "GBps": t5_bytes / t5 * 1e-6, "frac": t5_bytes / t5 * 1e-6 / peak,
                  "reads_of_L_per_step": 3}
         del ut, vt
@@ -663,6 +668,8 @@ def run_b200(args):
             # the one path with an exchange step: the fused wave step (per-N value for the scaling table)
             "wave_ms_per_step": wave["ms_per_step"], "wave_vertex_updates_per_s": wave["vertex_updates_per_s"],
             "wave_frac": wave["frac"], "wave_halo": wave["halo"], "parity_n": parity_n,
+            # the integrator the reference itself runs (examples/wave.jl:134), same mesh / slabs: per-N value
+            "wave_tsit5_ms_per_step": tsit5["ms_per_step"] if tsit5 else None,
             "breakdown": breakdown, "wave": wave, "wave2d": wave2d, "poisson_step": poisson_step, "dual_deriv": dual, "wave_tsit5": tsit5, "poisson2d": poisson2d,
             "assembly_ms": asm_ms,
             # assembly of d_3, d_2, d_1 on the device from the tet table (bit-exact; no roofline target):

@@ -13,6 +13,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <initializer_list>
 #include <vector>
 
 #include "mesh.cuh"
@@ -324,6 +325,34 @@ static int halo_exchange_on(ddf_mesh* m, double* u, cudaStream_t stream) {
 
 // raw-pointer variant for the integrators of wave.cu (vertex cochain on the compute stream)
 int ddf_halo_exchange_raw(ddf_mesh* m, double* u) { return halo_exchange_on(m, u, m->ctx->stream); }
+
+// two vertex cochains at once (the two stage inputs a paired Tsit5 pass produces): on slabs ONE grouped
+// ncclSend/ncclRecv carries the interface planes of both
+int ddf_halo_exchange_raw2(ddf_mesh* m, double* a, double* b) {
+  ddf_ctx* ctx = m->ctx;
+  cudaStream_t stream = ctx->stream;
+  if (m->halo_gen || ctx->nranks == 1 || !ctx->nccl_comm || !m->halo_plane) {
+    DDF_CHECK(halo_exchange_on(m, a, stream));
+    return halo_exchange_on(m, b, stream);
+  }
+  const int64_t P = m->halo_plane, V = m->n[0];
+  const int64_t own_lo = m->halo_lo * P, own_hi = V - m->halo_hi * P;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  DDF_NCCL(g_nccl.GroupStart());
+  for (double* u : {a, b}) {
+    if (m->halo_lo > 0) {
+      DDF_NCCL(g_nccl.Send(u + own_lo, P, ncclDouble, ctx->rank - 1, comm, stream));
+      DDF_NCCL(g_nccl.Recv(u + own_lo - P, P, ncclDouble, ctx->rank - 1, comm, stream));
+    }
+    if (m->halo_hi > 0) {
+      DDF_NCCL(g_nccl.Send(u + own_hi - P, P, ncclDouble, ctx->rank + 1, comm, stream));
+      DDF_NCCL(g_nccl.Recv(u + own_hi, P, ncclDouble, ctx->rank + 1, comm, stream));
+    }
+  }
+  DDF_NCCL(g_nccl.GroupEnd());
+  ctx->launches += (m->halo_lo > 0) + (m->halo_hi > 0);
+  return 0;
+}
 
 extern "C" int ddf_halo_exchange(ddf_mesh* m, ddf_vec* u) {
   DDF_TRY_BEGIN

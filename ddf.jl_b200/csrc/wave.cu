@@ -1070,6 +1070,7 @@ int ddf_lincomb_launch(ddf_ctx* ctx, const double* base, double dt, int nk, cons
                        double* out, int64_t n);   // core.cu
 
 int ddf_halo_exchange_raw(ddf_mesh* m, double* u);     // comm.cu
+int ddf_halo_exchange_raw2(ddf_mesh* m, double* a, double* b);
 
 static const double TSIT5_A[6][6] = {
     {0.161, 0, 0, 0, 0, 0},
@@ -1168,11 +1169,11 @@ static int tsit5_paired(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt, int n
   for (int step = 0; step < nsteps; step++) {
     double *s2 = X[c], *s3 = X[(c + 1) & 3], *s4 = X[(c + 2) & 3], *s5 = X[(c + 3) & 3], *s6 = X[c], *n2 = X[(c + 1) & 3];
     DDF_CHECK(pass(1, u->d.p, s2, s3, s4, nullptr));
-    if (dist) { DDF_CHECK(ddf_halo_exchange_raw(m, s3)); DDF_CHECK(ddf_halo_exchange_raw(m, s4)); }
+    if (dist) DDF_CHECK(ddf_halo_exchange_raw2(m, s3, s4));
     DDF_CHECK(pass(3, s3, s4, s5, s6, nullptr));           // su_6 overwrites su_2, which nobody reads any more
-    if (dist) { DDF_CHECK(ddf_halo_exchange_raw(m, s5)); DDF_CHECK(ddf_halo_exchange_raw(m, s6)); }
+    if (dist) DDF_CHECK(ddf_halo_exchange_raw2(m, s5, s6));
     DDF_CHECK(pass(5, s5, s6, u->d.p, udot->d.p, n2));     // in place: a row reads its own u, udot before it stores them
-    if (dist) { DDF_CHECK(ddf_halo_exchange_raw(m, u->d.p)); DDF_CHECK(ddf_halo_exchange_raw(m, n2)); }
+    if (dist) DDF_CHECK(ddf_halo_exchange_raw2(m, u->d.p, n2));
     c = (c + 1) & 3;
   }
   return 0;
