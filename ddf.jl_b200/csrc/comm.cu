@@ -331,6 +331,7 @@ int ddf_halo_exchange_raw(ddf_mesh* m, double* u) { return halo_exchange_on(m, u
 int ddf_halo_exchange_raw2(ddf_mesh* m, double* a, double* b) {
   ddf_ctx* ctx = m->ctx;
   cudaStream_t stream = ctx->stream;
+  m->halo_last = 2;
   if (m->halo_gen || ctx->nranks == 1 || !ctx->nccl_comm || !m->halo_plane) {
     DDF_CHECK(halo_exchange_on(m, a, stream));
     return halo_exchange_on(m, b, stream);
@@ -396,8 +397,10 @@ struct HaloP2P {
   unsigned char* lo_base = nullptr;    // mapped arena of rank-1 / rank+1
   unsigned char* hi_base = nullptr;
   unsigned long long* flags() { return reinterpret_cast<unsigned long long*>(arena.p); }
-  static double* landing(unsigned char* base, int from_upper, int parity, int64_t P) {
-    return reinterpret_cast<double*>(base + 256) + ((int64_t)from_upper * 2 + parity) * P;
+  // slot 0: the vector of the fused leapfrog / Poisson steps and the FIRST output of a paired Tsit5 pass; slot 1: its
+  // second output
+  static double* landing(unsigned char* base, int from_upper, int parity, int64_t P, int slot = 0) {
+    return reinterpret_cast<double*>(base + 256) + (((int64_t)slot * 2 + from_upper) * 2 + parity) * P;
   }
 };
 
@@ -459,7 +462,7 @@ static int halo_handshake_local(ddf_mesh* m, int* ok_out) {
   m->halo_p2p = hp;
   // a dedicated allocation of whole 2 MiB pages: cudaMalloc never shares those with other buffers, so the
   // IPC handle maps exactly this arena at offset 0
-  const size_t need = 256 + 4 * (size_t)P * sizeof(double);
+  const size_t need = 256 + 8 * (size_t)P * sizeof(double);
   const size_t bytes = (need + (2u << 20) - 1) / (2u << 20) * (2u << 20);
   hp->arena.plain = true;                 // cudaMalloc: pool memory cannot be exported with cudaIpcGetMemHandle
   DDF_CHECK(hp->arena.alloc(ctx, bytes));
@@ -561,6 +564,89 @@ static int steps_dist_p2p(ddf_mesh* m, int kind, ddf_vec* u, ddf_vec* v, double 
   DDF_LAUNCH_CHECK(ctx);
   // a wait that timed out inside THIS call left stale ghost planes behind: report it now, not in the next call
   DDF_CUDA(cudaMemcpyAsync(&err, flags + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (err) DDF_FAIL("halo: timed out (20 s) waiting for a neighbour's step flag; the ghost planes are stale");
+  return 0;
+}
+
+// ---- the same protocol, pass by pass, for the paired Tsit5 stages of wave.cu: a pass gathers TWO vertex vectors and
+// stores two (slots 0 / 1 of the landing arenas).  begin: wait for the neighbours' flags >= k - 1 and (copy != 0) move what
+// they landed in their pass k - 1 into the ghost planes of this pass's inputs; the caller then runs the pass on the owned
+// rows with the returned peer pointers and calls end (flag = k).  finish leaves valid ghost planes in a / b.
+int ddf_p2p_usable(ddf_mesh* m, int* usable) {
+  ddf_ctx* ctx = m->ctx;
+  *usable = 0;
+  if (ctx->nranks == 1 || !m->halo_plane || m->halo_gen || (ctx->tune.wave & 1024)) return 0;
+  if (m->halo_p2p_state == 0) {
+    int ok = 0;
+    DDF_CHECK(halo_handshake(m, &ok));
+    m->halo_p2p_state = ok ? 1 : 2;
+  }
+  if (m->halo_p2p_state != 1) return 0;
+  unsigned long long err = 0;
+  DDF_CUDA(cudaMemcpyAsync(&err, ((HaloP2P*)m->halo_p2p)->flags() + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DDF_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (err) DDF_FAIL("halo: timed out waiting for a neighbour's step flag in an earlier call");
+  *usable = 1;
+  return 0;
+}
+int ddf_p2p_pass_begin(ddf_mesh* m, double* in_a, double* in_b, int copy, double** peers /* lo_a, hi_a, lo_b, hi_b */,
+                       int64_t* own_lo_out, int64_t* own_hi_out) {
+  ddf_ctx* ctx = m->ctx;
+  HaloP2P* hp = (HaloP2P*)m->halo_p2p;
+  const int64_t nv = m->n[0], P = m->halo_plane;
+  const int64_t own_lo = m->halo_lo * P, own_hi = nv - m->halo_hi * P;
+  const bool has_lo = m->halo_lo > 0, has_hi = m->halo_hi > 0;
+  const int cgrid = (int)std::min<int64_t>(32, ceil_div64(P, 256));
+  const unsigned long long k = ++m->halo_step;
+  const int par_in = (int)((k - 1) & 1), par_out = (int)(k & 1);
+  double* in[2] = {in_a, in_b};
+  for (int slot = 0; slot < 2; slot++) {
+    k_halo_wait_copy<<<cgrid, 256, 0, ctx->stream>>>(
+        hp->flags(), has_lo ? k - 1 : 0ull, has_hi ? k - 1 : 0ull,
+        copy && has_lo ? HaloP2P::landing(hp->arena.p, 0, par_in, P, slot) : nullptr, in[slot] + own_lo - P,
+        copy && has_hi ? HaloP2P::landing(hp->arena.p, 1, par_in, P, slot) : nullptr, in[slot] + own_hi, P);
+    DDF_LAUNCH_CHECK(ctx);
+    if (!copy) break;                       // the first launch has waited; nothing to copy
+  }
+  // I am the UPPER neighbour of rank-1 and the LOWER neighbour of rank+1
+  for (int slot = 0; slot < 2; slot++) {
+    peers[2 * slot + 0] = has_lo ? HaloP2P::landing(hp->lo_base, 1, par_out, P, slot) : nullptr;
+    peers[2 * slot + 1] = has_hi ? HaloP2P::landing(hp->hi_base, 0, par_out, P, slot) : nullptr;
+  }
+  *own_lo_out = own_lo;
+  *own_hi_out = own_hi;
+  m->halo_last = 1;
+  return 0;
+}
+int ddf_p2p_pass_end(ddf_mesh* m) {
+  ddf_ctx* ctx = m->ctx;
+  HaloP2P* hp = (HaloP2P*)m->halo_p2p;
+  const bool has_lo = m->halo_lo > 0, has_hi = m->halo_hi > 0;
+  k_halo_signal<<<1, 1, 0, ctx->stream>>>(has_lo ? reinterpret_cast<unsigned long long*>(hp->lo_base) + 1 : nullptr,
+                                          has_hi ? reinterpret_cast<unsigned long long*>(hp->hi_base) + 0 : nullptr, m->halo_step);
+  DDF_LAUNCH_CHECK(ctx);
+  return 0;
+}
+int ddf_p2p_finish(ddf_mesh* m, double* a, double* b) {
+  ddf_ctx* ctx = m->ctx;
+  HaloP2P* hp = (HaloP2P*)m->halo_p2p;
+  const int64_t nv = m->n[0], P = m->halo_plane;
+  const int64_t own_lo = m->halo_lo * P, own_hi = nv - m->halo_hi * P;
+  const bool has_lo = m->halo_lo > 0, has_hi = m->halo_hi > 0;
+  const int cgrid = (int)std::min<int64_t>(32, ceil_div64(P, 256));
+  const unsigned long long k = m->halo_step;
+  double* out[2] = {a, b};
+  for (int slot = 0; slot < 2; slot++) {
+    if (!out[slot]) continue;
+    k_halo_wait_copy<<<cgrid, 256, 0, ctx->stream>>>(
+        hp->flags(), has_lo ? k : 0ull, has_hi ? k : 0ull,
+        has_lo ? HaloP2P::landing(hp->arena.p, 0, (int)(k & 1), P, slot) : nullptr, out[slot] + own_lo - P,
+        has_hi ? HaloP2P::landing(hp->arena.p, 1, (int)(k & 1), P, slot) : nullptr, out[slot] + own_hi, P);
+    DDF_LAUNCH_CHECK(ctx);
+  }
+  unsigned long long err = 0;
+  DDF_CUDA(cudaMemcpyAsync(&err, hp->flags() + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
   DDF_CUDA(cudaStreamSynchronize(ctx->stream));
   if (err) DDF_FAIL("halo: timed out (20 s) waiting for a neighbour's step flag; the ghost planes are stale");
   return 0;

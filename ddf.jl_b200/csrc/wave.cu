@@ -225,6 +225,8 @@ struct RowArgs {
   const double* u2;
   double* out_kv2;
   double* out_su2;
+  double* peer_lo2;     // fused halo of the SECOND stored stage input (out_su2), like peer_lo / peer_hi for out_su
+  double* peer_hi2;
 };
 
 // Tsitouras 5(4) tableau (OrdinaryDiffEq's Tsit5ConstantCache; pinned by its order conditions in tests/test_oracle_pins.py)
@@ -339,6 +341,15 @@ __device__ __forceinline__ void tsit5_pair(double m, double lu_a, double lu_b, d
     o3 = __dadd_rn(o1, __dmul_rn(dt, __dmul_rn(c_tsit5_a[0][0], __dmul_rn(m, o2))));
   }
 }
+// fused halo (comm.cu): interface-plane rows are ALSO stored into the neighbours' landing arenas over NVLink
+__device__ __forceinline__ void peer_store(const RowArgs& a, int64_t i, double w) {
+  if (a.peer_lo && i < a.send_lo_end) a.peer_lo[i - a.row0] = w;
+  if (a.peer_hi && i >= a.send_hi_beg) a.peer_hi[i - a.send_hi_beg] = w;
+}
+__device__ __forceinline__ void peer_store2(const RowArgs& a, int64_t i, double w) {
+  if (a.peer_lo2 && i < a.send_lo_end) a.peer_lo2[i - a.row0] = w;
+  if (a.peer_hi2 && i >= a.send_hi_beg) a.peer_hi2[i - a.send_hi_beg] = w;
+}
 __device__ __forceinline__ void tsit5_pair_finish(const RowArgs& a, int64_t i, double m, double lu_a, double lu_b, Tsit5Row& r) {
   double ka, kb, o1, o2, o3;
   if (a.J == 1) tsit5_pair<1>(m, lu_a, lu_b, r.kv, r.u0, r.v0, a.dt, ka, kb, o1, o2, o3);
@@ -349,10 +360,14 @@ __device__ __forceinline__ void tsit5_pair_finish(const RowArgs& a, int64_t i, d
     a.out_kv2[i] = kb;
     a.out_su[i] = o1;
     a.out_su2[i] = o2;
+    peer_store(a, i, o1);
+    peer_store2(a, i, o2);
   } else {
     a.out_su[i] = o1;
     a.out_sv[i] = o2;
     a.out_su2[i] = o3;
+    peer_store(a, i, o1);
+    peer_store2(a, i, o3);
   }
 }
 // su_2 of the first step: u + dt * (a_21 * ((1-b) .* udot))
@@ -370,10 +385,6 @@ __device__ __forceinline__ double jacobi_update(double u_i, double lu, double rh
   return __dadd_rn(u_i, __dmul_rn(theta, __dmul_rn(m, c)));
 }
 
-__device__ __forceinline__ void peer_store(const RowArgs& a, int64_t i, double w) {
-  if (a.peer_lo && i < a.send_lo_end) a.peer_lo[i - a.row0] = w;
-  if (a.peer_hi && i >= a.send_hi_beg) a.peer_hi[i - a.send_hi_beg] = w;
-}
 
 template <int MODE>
 __device__ __forceinline__ void row_epilogue(const RowArgs& a, int64_t i, double lu, uint64_t pol_stream) {
@@ -1071,6 +1082,10 @@ int ddf_lincomb_launch(ddf_ctx* ctx, const double* base, double dt, int nk, cons
 
 int ddf_halo_exchange_raw(ddf_mesh* m, double* u);     // comm.cu
 int ddf_halo_exchange_raw2(ddf_mesh* m, double* a, double* b);
+int ddf_p2p_usable(ddf_mesh* m, int* usable);           // comm.cu: the fused peer-memory halo, pass by pass
+int ddf_p2p_pass_begin(ddf_mesh* m, double* in_a, double* in_b, int copy, double** peers, int64_t* own_lo, int64_t* own_hi);
+int ddf_p2p_pass_end(ddf_mesh* m);
+int ddf_p2p_finish(ddf_mesh* m, double* a, double* b);
 
 static const double TSIT5_A[6][6] = {
     {0.161, 0, 0, 0, 0, 0},
@@ -1141,7 +1156,11 @@ static int tsit5_paired(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt, int n
   const size_t smem_p = (size_t)g.nstages * g.stage_bytes;
   const int grid = (int)std::min<int64_t>(ctx->sm_count, g1);
   DDF_CUDA(cudaFuncSetAttribute(k_rows_pipe<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
-  auto pass = [&](int J, const double* ga, const double* gb, double* o1, double* o2, double* o3) -> int {
+  // slab meshes: the fused peer-memory halo when the ranks can map each other (comm.cu), else grouped ncclSend/ncclRecv
+  int p2p = 0;
+  if (dist) DDF_CHECK(ddf_p2p_usable(m, &p2p));
+  bool first_pass = true;
+  auto pass = [&](int J, double* ga, double* gb, double* o1, double* o2, double* o3) -> int {
     RowArgs a{};
     a.isb = m->isbnd[0].p;
     a.u = ga;
@@ -1153,10 +1172,25 @@ static int tsit5_paired(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt, int n
     a.dt = dt;
     a.row0 = 0;
     a.row1 = nv;
+    int64_t gg0 = 0, gg1 = g1;
+    if (p2p) {
+      // wait for the neighbours' previous pass, take over what they landed (not before the first pass of a call: the
+      // ghost planes of its inputs come from the NCCL exchange below), then run the owned rows only
+      double* peers[4];
+      DDF_CHECK(ddf_p2p_pass_begin(m, ga, gb, first_pass ? 0 : 1, peers, &a.row0, &a.row1));
+      first_pass = false;
+      a.peer_lo = peers[0]; a.peer_hi = peers[1]; a.peer_lo2 = peers[2]; a.peer_hi2 = peers[3];
+      a.send_lo_end = a.row0 + m->halo_plane;
+      a.send_hi_beg = a.row1 - m->halo_plane;
+      gg0 = a.row0 / gw;
+      gg1 = (a.row1 + gw - 1) / gw;
+    }
     if (J < 5) { a.out_kv = kvp[J - 1]; a.out_kv2 = kvp[J]; a.out_su = o1; a.out_su2 = o2; }
     else { a.out_su = o1; a.out_sv = o2; a.out_su2 = o3; }
-    k_rows_pipe<5, 2><<<grid, 2 * PIPE_GROUP + 32, smem_p, ctx->stream>>>(a, sb.tab.p, sb.packed.p, sb.meta.p, 0, g1, g);
+    const int gridj = (int)std::min<int64_t>(ctx->sm_count, gg1 - gg0);
+    k_rows_pipe<5, 2><<<gridj, 2 * PIPE_GROUP + 32, smem_p, ctx->stream>>>(a, sb.tab.p, sb.packed.p, sb.meta.p, gg0, gg1, g);
     DDF_LAUNCH_CHECK(ctx);
+    if (p2p) DDF_CHECK(ddf_p2p_pass_end(m));
     return 0;
   };
   int gridp;
@@ -1169,13 +1203,14 @@ static int tsit5_paired(ddf_mesh* m, ddf_vec* u, ddf_vec* udot, double dt, int n
   for (int step = 0; step < nsteps; step++) {
     double *s2 = X[c], *s3 = X[(c + 1) & 3], *s4 = X[(c + 2) & 3], *s5 = X[(c + 3) & 3], *s6 = X[c], *n2 = X[(c + 1) & 3];
     DDF_CHECK(pass(1, u->d.p, s2, s3, s4, nullptr));
-    if (dist) DDF_CHECK(ddf_halo_exchange_raw2(m, s3, s4));
+    if (dist && !p2p) DDF_CHECK(ddf_halo_exchange_raw2(m, s3, s4));
     DDF_CHECK(pass(3, s3, s4, s5, s6, nullptr));           // su_6 overwrites su_2, which nobody reads any more
-    if (dist) DDF_CHECK(ddf_halo_exchange_raw2(m, s5, s6));
+    if (dist && !p2p) DDF_CHECK(ddf_halo_exchange_raw2(m, s5, s6));
     DDF_CHECK(pass(5, s5, s6, u->d.p, udot->d.p, n2));     // in place: a row reads its own u, udot before it stores them
-    if (dist) DDF_CHECK(ddf_halo_exchange_raw2(m, u->d.p, n2));
+    if (dist && !p2p) DDF_CHECK(ddf_halo_exchange_raw2(m, u->d.p, n2));
     c = (c + 1) & 3;
   }
+  if (p2p && nsteps > 0) DDF_CHECK(ddf_p2p_finish(m, u->d.p, nullptr));   // leave with valid ghost planes of u
   return 0;
 }
 

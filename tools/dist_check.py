@@ -103,13 +103,19 @@ def main():
         mfd.close()
     ddf._lib.call("ddf_set_tuning", b"wave", 0)
     # the reference's integrator on slabs: fixed-step Tsit5 with a ghost-plane exchange before every right-hand side
-    for D, nelts, nsteps in ((3, (8, 8, 8 * world), 3), (2, (16, 16 * world), 4)):
+    # (paired stages: peer-memory halo pass by pass -- tuning 0 -- or one grouped ncclSend/ncclRecv per pass -- 1024;
+    # several calls, so the step counter of the halo protocol runs across calls and mixes with the leapfrog's)
+    for tune, (D, nelts, nsteps) in [(t, c) for t in (0, 1024) for c in ((3, (8, 8, 8 * world), 3), (2, (16, 16 * world), 4),
+                                                                         (3, (24, 24, 8 * world + 2), 4))]:
+        ddf._lib.call("ddf_set_tuning", b"wave", tune)
         mfd, slab = ddf.dist.slab_hypercube(D, nelts, ctx)
         lu, gu = global_field(500 + D, slab, nelts, D)
         lv, gv = global_field(600 + D, slab, nelts, D)
         u, v = ddf.Fun(mfd, ddf.Pr, 0, lu), ddf.Fun(mfd, ddf.Pr, 0, lv)
         dt = ctx.allreduce(ddf.wave_dt(mfd), "min")
-        ddf.wave_tsit5(mfd, u, v, dt, nsteps)
+        ddf.wave_tsit5(mfd, u, v, dt, 1)
+        ddf.wave_tsit5(mfd, u, v, dt, nsteps - 1)
+        t5mode = ddf.dist.halo_mode(mfd)
         lo, hi = slab.own_rows
         parts = [None] * world
         dist.all_gather_object(parts, (slab.z_own_lo, u.values[lo:hi].copy(), v.values[lo:hi].copy()))
@@ -123,11 +129,12 @@ def main():
             for zlo, pu, pv in sorted(parts, key=lambda t: t[0]):
                 a = zlo * slab.plane
                 same = same and np.array_equal(pu, ru[a:a + len(pu)]) and np.array_equal(pv, rv[a:a + len(pv)])
-            print(f"dist_check tsit5 D={D} nelts={nelts} world={world} steps={nsteps}: {'BIT-EXACT' if same else 'MISMATCH'}",
+            print(f"dist_check tsit5 halo={t5mode} D={D} nelts={nelts} world={world} steps={nsteps}: {'BIT-EXACT' if same else 'MISMATCH'}",
                   flush=True)
             ok = ok and same
             full.close()
         mfd.close()
+    ddf._lib.call("ddf_set_tuning", b"wave", 0)
     # ghost exchange of cochains of every rank: a globally consistent R-cochain (a function of the simplex's
     # global vertex coordinates), ghost entries wiped, exchanged, must come back bit for bit
     ddf._lib.call("ddf_set_tuning", b"wave", 0)
