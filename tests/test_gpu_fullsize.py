@@ -92,6 +92,40 @@ def run_full_checks(ddf, ctx, D, n, steps=4):
         v = v + dt * (mk * laplace_apply(rls[1], other, l, diag, nlower, u))
         u = u + dt * (mk * v)
     assert np.array_equal(fu.values, u.cpu().numpy()) and np.array_equal(fv.values, v.cpu().numpy()), "leapfrog at full size"
+    # ---- N1: fixed-step Tsit5 (examples/wave.jl:134) restated here stage by stage in perform_step!'s order -- stage
+    # broadcasts with separately rounded products and sums, left to right, FSAL across steps -- against ddf_wave_tsit5,
+    # which at this size runs THREE paired-stage passes over L per step (csrc/wave.cu tsit5_pair): bit for bit
+    A = ((0.161,),
+         (-0.008480655492356989, 0.335480655492357),
+         (2.8971530571054935, -6.359448489975075, 4.3622954328695815),
+         (5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525),
+         (5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383),
+         (0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774))
+
+    def rhs(U):
+        return mk * U[1], mk * laplace_apply(rls[1], other, l, diag, nlower, U[0])
+
+    def broadcast(base, coefs, ks):
+        acc = coefs[0] * ks[0]
+        for c, kk in zip(coefs[1:], ks[1:]):
+            acc = acc + c * kk
+        return base + dt * acc
+
+    tu = torch.rand(tb.n[0], dtype=torch.float64, device="cuda", generator=g) - 0.5
+    tv = torch.rand(tb.n[0], dtype=torch.float64, device="cuda", generator=g) - 0.5
+    gu, gv = ddf.Fun(m, ddf.Pr, 0, tu.cpu().numpy()), ddf.Fun(m, ddf.Pr, 0, tv.cpu().numpy())
+    tsteps = 2
+    ddf.wave_tsit5(m, gu, gv, dt, tsteps)
+    U = (tu, tv)
+    ks = [rhs(U)]
+    for _ in range(tsteps):
+        for st in range(6):
+            tmp = tuple(broadcast(U[c], A[st], [kk[c] for kk in ks]) for c in range(2))
+            ks.append(rhs(tmp))
+        U = tmp
+        ks = [ks[6]]
+    assert np.array_equal(gu.values, U[0].cpu().numpy()) and np.array_equal(gv.values, U[1].cpu().numpy()), "Tsit5 at full size"
+    del tu, tv, U, ks, tmp
     del tb, rls, vol, dvol, other, l, diag, nlower, u, v
     torch.cuda.empty_cache()
     m.close()
