@@ -9,8 +9,9 @@ import numpy as np  # noqa: E402
 import ddf.jl_b200 as ddf  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+D = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ctx = ddf.Context(0)
-m = ddf.large_hypercube_manifold(3, (n, n, n), ctx=ctx)
+m = ddf.large_hypercube_manifold(D, (n,) * D, ctx=ctx)
 dt = ddf.wave_dt(m)
 rng = np.random.default_rng(3)
 u0, v0 = rng.standard_normal(m.nsimplices(0)), rng.standard_normal(m.nsimplices(0))
@@ -29,5 +30,5 @@ for name, tune in (("unfused", 1 << 29), ("six fused single-stage launches", 1 <
         ctx.tic()
         ddf.wave_tsit5(m, u, v, dt, 5)
         ts.append(ctx.toc() / 5)
-    print(f"tsit5_ab n={n} {name}: {min(ts):.3f} ms per step, same bits: {same}", flush=True)
+    print(f"tsit5_ab D={D} n={n} {name}: {min(ts):.3f} ms per step, same bits: {same}", flush=True)
 ddf._lib.call("ddf_set_tuning", b"wave", 0)
