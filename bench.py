@@ -468,6 +468,12 @@ def run_b200(args):
                   "vertex_updates_per_s": m2.nsimplices(0) / (ms2 * 1e-3), "algorithmic_bytes": alg2,
                   "format_bytes": fmt2, "GBps": alg2 / ms2 * 1e-6, "frac": alg2 / ms2 * 1e-6 / peak,
                   "row_format": ddf.wave_format(m2), "steps": 200}
+        # the integrator examples/wave.jl runs on this very configuration (levels = 11): fixed-step Tsit5
+        ddf.wave_tsit5(m2, u2, v2, dt2, 2)
+        ctx.sync()
+        ctx.tic()
+        ddf.wave_tsit5(m2, u2, v2, dt2, 50)
+        wave2d["tsit5_ms_per_step"] = ctx.toc() / 50
         m2.close()
     # north_star kernel (3), Poisson flavour: one fused weighted-Jacobi sweep on the same mesh
     # algorithmic bytes (SURVEY 8d counting): E*(2*4+8) + V*(u r/w 16 + rho 8 + 1/diag 8 + mask 1)
