@@ -134,6 +134,41 @@ def main():
             ok = ok and same
             full.close()
         mfd.close()
+    # the two integrators interleaved on ONE slab mesh: leapfrog, Tsit5, leapfrog again -- the step counter and the
+    # landing parities of the peer-memory protocol run through both (and through the NCCL fallback)
+    for tune in (0, 1024):
+        ddf._lib.call("ddf_set_tuning", b"wave", tune)
+        D, nelts = 3, (16, 16, 8 * world + 2)
+        mfd, slab = ddf.dist.slab_hypercube(D, nelts, ctx)
+        lu, gu = global_field(650 + D, slab, nelts, D)
+        lv, gv = global_field(660 + D, slab, nelts, D)
+        u, v = ddf.Fun(mfd, ddf.Pr, 0, lu), ddf.Fun(mfd, ddf.Pr, 0, lv)
+        dt = ctx.allreduce(ddf.wave_dt(mfd), "min")
+        ddf.wave_leapfrog(mfd, u, v, dt, 3)
+        ddf.wave_tsit5(mfd, u, v, dt, 2)
+        ddf.wave_leapfrog(mfd, u, v, dt, 2)
+        ddf.wave_tsit5(mfd, u, v, dt, 1)
+        mmode = ddf.dist.halo_mode(mfd)
+        lo, hi = slab.own_rows
+        parts = [None] * world
+        dist.all_gather_object(parts, (slab.z_own_lo, u.values[lo:hi].copy(), v.values[lo:hi].copy()))
+        if rank == 0:
+            full = ddf.large_hypercube_manifold(D, nelts, ctx=ctx, hdiv=nelts[0])
+            fu, fv = ddf.Fun(full, ddf.Pr, 0, gu), ddf.Fun(full, ddf.Pr, 0, gv)
+            ddf._lib.call("ddf_wave_leapfrog", full._h, fu._h, fv._h, float(dt), 3)
+            ddf._lib.call("ddf_wave_tsit5", full._h, fu._h, fv._h, float(dt), 2)
+            ddf._lib.call("ddf_wave_leapfrog", full._h, fu._h, fv._h, float(dt), 2)
+            ddf._lib.call("ddf_wave_tsit5", full._h, fu._h, fv._h, float(dt), 1)
+            ru, rv = fu.values, fv.values
+            same = True
+            for zlo, pu, pv in sorted(parts, key=lambda t: t[0]):
+                a = zlo * slab.plane
+                same = same and np.array_equal(pu, ru[a:a + len(pu)]) and np.array_equal(pv, rv[a:a + len(pv)])
+            print(f"dist_check leapfrog+tsit5 interleaved halo={mmode} D={D} nelts={nelts} world={world}: "
+                  f"{'BIT-EXACT' if same else 'MISMATCH'}", flush=True)
+            ok = ok and same
+            full.close()
+        mfd.close()
     ddf._lib.call("ddf_set_tuning", b"wave", 0)
     # ghost exchange of cochains of every rank: a globally consistent R-cochain (a function of the simplex's
     # global vertex coordinates), ghost entries wiped, exchanged, must come back bit for bit
