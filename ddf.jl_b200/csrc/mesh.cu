@@ -468,6 +468,47 @@ __device__ __forceinline__ bool bk_less(unsigned long long ra, uint32_t ta, unsi
 }
 
 // warp per bucket: sort by (rest, tuple id), count the distinct faces
+// rank by counting, EL elements per lane: one walk over the bucket's shared-memory copy, sorted tuples written back
+template <int EL>
+__device__ __forceinline__ uint32_t bucket_rank_walk(const unsigned long long* __restrict__ sr, const uint32_t* __restrict__ st,
+                                                     uint32_t sz, uint32_t lo, int lane, unsigned long long* __restrict__ rest,
+                                                     uint32_t* __restrict__ tup) {
+  unsigned long long myr[EL];
+  uint32_t myt[EL], rank[EL], eq_lower[EL];
+#pragma unroll
+  for (int e = 0; e < EL; e++) {
+    const uint32_t i = (uint32_t)e * 32u + (uint32_t)lane;
+    myr[e] = i < sz ? sr[i] : ~0ull;
+    myt[e] = i < sz ? st[i] : ~0u;
+    rank[e] = 0;
+    eq_lower[e] = 0;
+  }
+  for (uint32_t j = 0; j < sz; j++) {
+    const unsigned long long rj = sr[j];
+    const uint32_t tj = st[j];
+#pragma unroll
+    for (int e = 0; e < EL; e++) {
+      const bool same = rj == myr[e];
+      const bool lower = same && tj < myt[e];
+      rank[e] += (rj < myr[e]) || lower;
+      eq_lower[e] += lower;
+    }
+  }
+  uint32_t u = 0;
+#pragma unroll
+  for (int e = 0; e < EL; e++) {
+    const uint32_t i = (uint32_t)e * 32u + (uint32_t)lane;
+    bool head = false;
+    if (i < sz) {
+      rest[lo + rank[e]] = myr[e];
+      tup[lo + rank[e]] = myt[e];
+      head = eq_lower[e] == 0;                            // first (smallest parent) of its face
+    }
+    u += __popc(__ballot_sync(0xffffffffu, head));
+  }
+  return u;
+}
+
 __global__ void __launch_bounds__(256)
 k_bucket_sort(const uint32_t* __restrict__ start, int64_t nbuckets, unsigned long long* __restrict__ rest,
               uint32_t* __restrict__ tup, uint32_t* __restrict__ ucnt, uint32_t* __restrict__ big /* [0] = count, then ids */) {
@@ -489,26 +530,15 @@ k_bucket_sort(const uint32_t* __restrict__ start, int64_t nbuckets, unsigned lon
     st[w][i] = tup[lo + i];
   }
   __syncwarp();
-  uint32_t u = 0;
-  for (uint32_t i0 = 0; i0 < sz; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    bool head = false;
-    if (i < sz) {
-      const unsigned long long myr = sr[w][i];
-      const uint32_t myt = st[w][i];
-      uint32_t rank = 0, eq_lower = 0;
-      for (uint32_t j = 0; j < sz; j++) {
-        const unsigned long long rj = sr[w][j];
-        const uint32_t tj = st[w][j];
-        const bool same = rj == myr;
-        rank += (rj < myr) || (same && tj < myt);
-        eq_lower += same && tj < myt;
-      }
-      rest[lo + rank] = myr;
-      tup[lo + rank] = myt;
-      head = eq_lower == 0;                     // first (smallest parent) of its face
-    }
-    u += __popc(__ballot_sync(0xffffffffu, head));
+  // a lane ranks ALL its elements (lane, lane + 32, ...: up to BK_MAX / 32 = 4) in ONE walk over the bucket -- the
+  // bucket's entries are read from shared memory once per walk, not once per round of 32 elements (most buckets of the
+  // triangle level hold 33..64 tuples, where a second round used to cost as much as the first for a handful of lanes)
+  uint32_t u;
+  switch ((sz + 31u) >> 5) {                             // warp-uniform: elements per lane in this bucket
+    case 1: u = bucket_rank_walk<1>(sr[w], st[w], sz, lo, lane, rest, tup); break;
+    case 2: u = bucket_rank_walk<2>(sr[w], st[w], sz, lo, lane, rest, tup); break;
+    case 3: u = bucket_rank_walk<3>(sr[w], st[w], sz, lo, lane, rest, tup); break;
+    default: u = bucket_rank_walk<4>(sr[w], st[w], sz, lo, lane, rest, tup); break;
   }
   if (lane == 0) ucnt[b] = u;
 }
