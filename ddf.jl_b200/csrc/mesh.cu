@@ -468,52 +468,58 @@ __device__ __forceinline__ bool bk_less(unsigned long long ra, uint32_t ta, unsi
 }
 
 // warp per bucket: sort by (rest, tuple id), count the distinct faces
-// rank by counting, EL elements per lane: one walk over the bucket's shared-memory copy, sorted tuples written back
-template <int EL>
-__device__ __forceinline__ uint32_t bucket_rank_walk(const unsigned long long* __restrict__ sr, const uint32_t* __restrict__ st,
+// Rank by counting, EL elements per lane: ONE walk over the bucket's shared-memory copy for all of a lane's elements.
+// NARROW (the rest of the tuple fits 32 bits: every level but the first of a 3D mesh): rest and tuple id form ONE
+// 64-bit key, a comparison is one 64-bit compare; otherwise (rest, tuple id) lexicographically.  The distinct faces of
+// the bucket are counted AFTER the ranking from the sorted keys (a head differs from its predecessor) instead of by a
+// second counter inside the O(size^2) walk.
+template <int EL, bool NARROW>
+__device__ __forceinline__ uint32_t bucket_rank_walk(unsigned long long* __restrict__ sk, const uint32_t* __restrict__ st,
                                                      uint32_t sz, uint32_t lo, int lane, unsigned long long* __restrict__ rest,
                                                      uint32_t* __restrict__ tup) {
-  unsigned long long myr[EL];
-  uint32_t myt[EL], rank[EL], eq_lower[EL];
+  unsigned long long myk[EL];
+  uint32_t myt[EL], rank[EL];
 #pragma unroll
   for (int e = 0; e < EL; e++) {
     const uint32_t i = (uint32_t)e * 32u + (uint32_t)lane;
-    myr[e] = i < sz ? sr[i] : ~0ull;
-    myt[e] = i < sz ? st[i] : ~0u;
+    myk[e] = i < sz ? sk[i] : ~0ull;
+    myt[e] = (!NARROW && i < sz) ? st[i] : ~0u;
     rank[e] = 0;
-    eq_lower[e] = 0;
   }
   for (uint32_t j = 0; j < sz; j++) {
-    const unsigned long long rj = sr[j];
-    const uint32_t tj = st[j];
+    const unsigned long long kj = sk[j];
+    const uint32_t tj = NARROW ? 0u : st[j];
 #pragma unroll
-    for (int e = 0; e < EL; e++) {
-      const bool same = rj == myr[e];
-      const bool lower = same && tj < myt[e];
-      rank[e] += (rj < myr[e]) || lower;
-      eq_lower[e] += lower;
+    for (int e = 0; e < EL; e++) rank[e] += NARROW ? (kj < myk[e]) : ((kj < myk[e]) || (kj == myk[e] && tj < myt[e]));
+  }
+  __syncwarp();                                           // every lane has finished reading the unsorted bucket
+#pragma unroll
+  for (int e = 0; e < EL; e++) {
+    const uint32_t i = (uint32_t)e * 32u + (uint32_t)lane;
+    if (i < sz) {
+      const unsigned long long r = NARROW ? (myk[e] >> 32) : myk[e];
+      rest[lo + rank[e]] = r;
+      tup[lo + rank[e]] = NARROW ? (uint32_t)myk[e] : myt[e];
+      sk[rank[e]] = r;                                    // sorted rests, for the head count
     }
   }
+  __syncwarp();
   uint32_t u = 0;
 #pragma unroll
   for (int e = 0; e < EL; e++) {
     const uint32_t i = (uint32_t)e * 32u + (uint32_t)lane;
-    bool head = false;
-    if (i < sz) {
-      rest[lo + rank[e]] = myr[e];
-      tup[lo + rank[e]] = myt[e];
-      head = eq_lower[e] == 0;                            // first (smallest parent) of its face
-    }
+    const bool head = i < sz && (i == 0 || sk[i] != sk[i - 1]);       // first (smallest parent) of its face
     u += __popc(__ballot_sync(0xffffffffu, head));
   }
   return u;
 }
 
+template <bool NARROW>
 __global__ void __launch_bounds__(256)
 k_bucket_sort(const uint32_t* __restrict__ start, int64_t nbuckets, unsigned long long* __restrict__ rest,
               uint32_t* __restrict__ tup, uint32_t* __restrict__ ucnt, uint32_t* __restrict__ big /* [0] = count, then ids */) {
   __shared__ unsigned long long sr[8][BK_MAX];
-  __shared__ uint32_t st[8][BK_MAX];
+  __shared__ uint32_t st[NARROW ? 1 : 8][NARROW ? 1 : BK_MAX];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * 8 + w;
   if (b >= nbuckets) return;
@@ -523,22 +529,24 @@ k_bucket_sort(const uint32_t* __restrict__ start, int64_t nbuckets, unsigned lon
     if (lane == 0) big[1 + atomicAdd(&big[0], 1u)] = (uint32_t)b;
     return;
   }
-  // rank by counting: every lane compares its element(s) with all sz elements of the bucket (broadcast reads of
-  // shared memory, no barriers) -- cheaper than a bitonic network for the few dozen faces above one vertex
+  // every lane compares its element(s) with all sz elements of the bucket (broadcast reads of shared memory, no
+  // barriers) -- cheaper than a bitonic network for the few dozen faces above one vertex
   for (uint32_t i = lane; i < sz; i += 32) {
-    sr[w][i] = rest[lo + i];
-    st[w][i] = tup[lo + i];
+    if (NARROW) {
+      sr[w][i] = (rest[lo + i] << 32) | (unsigned long long)tup[lo + i];
+    } else {
+      sr[w][i] = rest[lo + i];
+      st[NARROW ? 0 : w][i] = tup[lo + i];
+    }
   }
   __syncwarp();
-  // a lane ranks ALL its elements (lane, lane + 32, ...: up to BK_MAX / 32 = 4) in ONE walk over the bucket -- the
-  // bucket's entries are read from shared memory once per walk, not once per round of 32 elements (most buckets of the
-  // triangle level hold 33..64 tuples, where a second round used to cost as much as the first for a handful of lanes)
+  // (most buckets of the triangle level hold 33..64 tuples: two elements per lane in one walk)
   uint32_t u;
   switch ((sz + 31u) >> 5) {                             // warp-uniform: elements per lane in this bucket
-    case 1: u = bucket_rank_walk<1>(sr[w], st[w], sz, lo, lane, rest, tup); break;
-    case 2: u = bucket_rank_walk<2>(sr[w], st[w], sz, lo, lane, rest, tup); break;
-    case 3: u = bucket_rank_walk<3>(sr[w], st[w], sz, lo, lane, rest, tup); break;
-    default: u = bucket_rank_walk<4>(sr[w], st[w], sz, lo, lane, rest, tup); break;
+    case 1: u = bucket_rank_walk<1, NARROW>(sr[w], st[NARROW ? 0 : w], sz, lo, lane, rest, tup); break;
+    case 2: u = bucket_rank_walk<2, NARROW>(sr[w], st[NARROW ? 0 : w], sz, lo, lane, rest, tup); break;
+    case 3: u = bucket_rank_walk<3, NARROW>(sr[w], st[NARROW ? 0 : w], sz, lo, lane, rest, tup); break;
+    default: u = bucket_rank_walk<4, NARROW>(sr[w], st[NARROW ? 0 : w], sz, lo, lane, rest, tup); break;
   }
   if (lane == 0) ucnt[b] = u;
 }
@@ -780,7 +788,9 @@ static int assemble_level_bucket(ddf_mesh* m, int vbits) {
   k_bucket_scatter<N><<<gs, 256, 0, ctx->stream>>>(m->simp[R].p, nsimp, vbits, cursor, rest, tup);
   DDF_LAUNCH_CHECK(ctx);
   DDF_CUDA(cudaMemsetAsync(ucnt + nv, 0, 4, ctx->stream));
-  k_bucket_sort<<<gb, 256, 0, ctx->stream>>>(start, nv, rest, tup, ucnt, big);
+  // the rest of a face tuple (its N - 2 larger vertices) fits 32 bits at every level but the first of a 3D mesh
+  if ((N - 2) * vbits <= 32) k_bucket_sort<true><<<gb, 256, 0, ctx->stream>>>(start, nv, rest, tup, ucnt, big);
+  else k_bucket_sort<false><<<gb, 256, 0, ctx->stream>>>(start, nv, rest, tup, ucnt, big);
   DDF_LAUNCH_CHECK(ctx);
   k_bucket_sort_big<<<2 * ctx->sm_count, 1024, 0, ctx->stream>>>(start, rest, tup, ucnt, big);   // no-op without big buckets
   DDF_LAUNCH_CHECK(ctx);
