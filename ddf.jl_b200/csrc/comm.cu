@@ -18,6 +18,9 @@
 
 #include "mesh.cuh"
 
+int ddf_pipe2_feasible(ddf_mesh* m, int* ok);           // wave.cu
+int ddf_leapfrog_pair_launch(ddf_mesh* m, cudaStream_t stream, double* u, double* v, double* utmp, double dt, int64_t row0,
+                             int64_t row1, int64_t row0b, int64_t row1b, int64_t plane, double* const* peers6, int* ran);
 int ddf_step_launch(ddf_mesh* m, cudaStream_t stream, int kind, const double* u, double* aux, double* unew, double coef,
                     int64_t row0, int64_t row1, double* peer_lo, double* peer_hi, int64_t plane);           // wave.cu
 int ddf_mesh_require_dinv(ddf_mesh* m);                                                                      // wave.cu
@@ -397,8 +400,9 @@ struct HaloP2P {
   unsigned char* lo_base = nullptr;    // mapped arena of rank-1 / rank+1
   unsigned char* hi_base = nullptr;
   unsigned long long* flags() { return reinterpret_cast<unsigned long long*>(arena.p); }
-  // slot 0: the vector of the fused leapfrog / Poisson steps and the FIRST output of a paired Tsit5 pass; slot 1: its
-  // second output
+  // slot 0: the vector of the fused leapfrog / Poisson steps (the plane next to the interface) and the FIRST output of a
+  // paired Tsit5 pass; slot 1: its second output, or the second plane of u of a two-step leapfrog launch; slot 2: the
+  // plane of v of a two-step leapfrog launch
   static double* landing(unsigned char* base, int from_upper, int parity, int64_t P, int slot = 0) {
     return reinterpret_cast<double*>(base + 256) + (((int64_t)slot * 2 + from_upper) * 2 + parity) * P;
   }
@@ -462,7 +466,7 @@ static int halo_handshake_local(ddf_mesh* m, int* ok_out) {
   m->halo_p2p = hp;
   // a dedicated allocation of whole 2 MiB pages: cudaMalloc never shares those with other buffers, so the
   // IPC handle maps exactly this arena at offset 0
-  const size_t need = 256 + 8 * (size_t)P * sizeof(double);
+  const size_t need = 256 + 12 * (size_t)P * sizeof(double);      // 3 slots x 2 sides x 2 parities
   const size_t bytes = (need + (2u << 20) - 1) / (2u << 20) * (2u << 20);
   hp->arena.plain = true;                 // cudaMalloc: pool memory cannot be exported with cudaIpcGetMemHandle
   DDF_CHECK(hp->arena.alloc(ctx, bytes));
@@ -536,7 +540,83 @@ static int steps_dist_p2p(ddf_mesh* m, int kind, ddf_vec* u, ddf_vec* v, double 
   DDF_CUDA(cudaMemcpyAsync(&err, flags + 2, 8, cudaMemcpyDeviceToHost, ctx->stream));
   DDF_CUDA(cudaStreamSynchronize(ctx->stream));
   if (err) DDF_FAIL("halo: timed out waiting for a neighbour's step flag in an earlier call");
-  for (int s = 0; s < nsteps; s++) {
+  int s = 0;
+  // ---- two steps per launch with a deep halo (leapfrog only; every rank must be able to: agreed once per mesh)
+  if (kind == 0 && nsteps >= 2 && m->wave2_dist_state == 0) {
+    int ok = 0;
+    const int rc = ddf_pipe2_feasible(m, &ok);
+    if (rc != 0) { ok = 0; cudaGetLastError(); }
+    // the deep halo needs two ghost planes per interior side and two owned planes to send
+    if ((has_lo && m->halo_lo < 2) || (has_hi && m->halo_hi < 2) || own_hi - own_lo < 2 * P) ok = 0;
+    double agreed = ok ? 1.0 : 0.0;
+    DDF_CHECK(ddf_comm_allreduce(ctx, &agreed, 2));     // min over ranks
+    m->wave2_dist_state = agreed > 0.5 ? 1 : 2;
+    m->wave2_dist_tune = ctx->tune.wave;
+  }
+  if (kind == 0 && nsteps >= 2 && m->wave2_dist_state != 0 && m->wave2_dist_tune != ctx->tune.wave) {
+    int ok = 0;                                          // the tuning changed since the agreement: ask again
+    const int rc = ddf_pipe2_feasible(m, &ok);
+    if (rc != 0) { ok = 0; cudaGetLastError(); }
+    if ((has_lo && m->halo_lo < 2) || (has_hi && m->halo_hi < 2) || own_hi - own_lo < 2 * P) ok = 0;
+    double agreed = ok ? 1.0 : 0.0;
+    DDF_CHECK(ddf_comm_allreduce(ctx, &agreed, 2));
+    m->wave2_dist_state = agreed > 0.5 ? 1 : 2;
+    m->wave2_dist_tune = ctx->tune.wave;
+  }
+  if (kind == 0 && m->wave2_dist_state == 1 && nsteps >= 2) {
+    {
+      // the ghost planes the pairs read -- two of u, one of v -- are refreshed from their owners once per call
+      ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+      double *uu = u->d.p, *vv = v->d.p;
+      DDF_NCCL(g_nccl.GroupStart());
+      if (has_lo) {
+        DDF_NCCL(g_nccl.Send(uu + own_lo, 2 * P, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+        DDF_NCCL(g_nccl.Recv(uu + own_lo - 2 * P, 2 * P, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+        DDF_NCCL(g_nccl.Send(vv + own_lo, P, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+        DDF_NCCL(g_nccl.Recv(vv + own_lo - P, P, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+      }
+      if (has_hi) {
+        DDF_NCCL(g_nccl.Send(uu + own_hi - 2 * P, 2 * P, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+        DDF_NCCL(g_nccl.Recv(uu + own_hi, 2 * P, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+        DDF_NCCL(g_nccl.Send(vv + own_hi - P, P, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+        DDF_NCCL(g_nccl.Recv(vv + own_hi, P, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+      }
+      DDF_NCCL(g_nccl.GroupEnd());
+      ctx->launches += (has_lo ? 1 : 0) + (has_hi ? 1 : 0);
+      bool first = true;
+      while (nsteps - s >= 2) {
+        const unsigned long long k = ++m->halo_step;
+        const int par_in = (int)((k - 1) & 1), par_out = (int)(k & 1);
+        uu = u->d.p;
+        // wait for the neighbours' previous event; after the first pair take over the three planes they landed
+        for (int slot = 0; slot < 3; slot++) {
+          double* dst_lo = slot == 0 ? uu + own_lo - P : (slot == 1 ? uu + own_lo - 2 * P : vv + own_lo - P);
+          double* dst_hi = slot == 0 ? uu + own_hi : (slot == 1 ? uu + own_hi + P : vv + own_hi);
+          k_halo_wait_copy<<<cgrid, 256, 0, ctx->stream>>>(
+              flags, has_lo ? k - 1 : 0ull, has_hi ? k - 1 : 0ull,
+              !first && has_lo ? HaloP2P::landing(hp->arena.p, 0, par_in, P, slot) : nullptr, dst_lo,
+              !first && has_hi ? HaloP2P::landing(hp->arena.p, 1, par_in, P, slot) : nullptr, dst_hi, P);
+          DDF_LAUNCH_CHECK(ctx);
+          if (first) break;                              // the one launch has waited; nothing to copy yet
+        }
+        double* peers[6];
+        for (int slot = 0; slot < 3; slot++) {
+          peers[slot] = has_lo ? HaloP2P::landing(hp->lo_base, 1, par_out, P, slot) : nullptr;
+          peers[3 + slot] = has_hi ? HaloP2P::landing(hp->hi_base, 0, par_out, P, slot) : nullptr;
+        }
+        int ran = 0;
+        DDF_CHECK(ddf_leapfrog_pair_launch(m, ctx->stream, uu, vv, m->utmp.p, dt, own_lo - (has_lo ? P : 0),
+                                           own_hi + (has_hi ? P : 0), own_lo, own_hi, P, peers, &ran));
+        if (!ran) DDF_FAIL("distributed step: the two-step launch all ranks agreed on was refused on this one");
+        k_halo_signal<<<1, 1, 0, ctx->stream>>>(has_lo ? reinterpret_cast<unsigned long long*>(hp->lo_base) + 1 : nullptr,
+                                                has_hi ? reinterpret_cast<unsigned long long*>(hp->hi_base) + 0 : nullptr, k);
+        DDF_LAUNCH_CHECK(ctx);
+        s += 2;
+        first = false;
+      }
+    }
+  }
+  for (; s < nsteps; s++) {
     const unsigned long long k = ++m->halo_step;
     const int par_in = (int)((k - 1) & 1), par_out = (int)(k & 1);
     // the ghost planes are valid on entry (caller's contract); later steps take what the neighbours landed

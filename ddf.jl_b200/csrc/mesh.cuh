@@ -143,6 +143,8 @@ struct ddf_mesh {
   void* halo_lists = nullptr;            // per-rank-R pack / unpack index lists of ddf_halo_exchange_k (comm.cu)
   unsigned long long halo_step = 0;
   int halo_p2p_state = 0;
+  int wave2_dist_tune = 0;               // the "wave" tuning value that agreement was made under
+  int wave2_dist_state = 0;              // two leapfrog steps per launch on this slab: 0 = not asked yet, 1 = every rank can, 2 = no
   int halo_last = 0;                     // what the last distributed step used: 1 = peer memory, 2 = NCCL
 
   // hypercube generator parameters (slab meshes of the distributed wave step)

@@ -227,6 +227,13 @@ struct RowArgs {
   double* out_su2;
   double* peer_lo2;     // fused halo of the SECOND stored stage input (out_su2), like peer_lo / peer_hi for out_su
   double* peer_hi2;
+  // two leapfrog steps per launch on a slab (wavefront2.cuh, deep halo): the step-n tasks cover rows [row0, row1) = the
+  // owned rows + one ghost plane on either side, the step-(n+1) tasks the owned rows [row0b, row1b) and store the two
+  // outermost owned planes of the new u (peer_lo / peer_lo2 towards rank-1, peer_hi / peer_hi2 towards rank+1; the
+  // plane next to the interface first) and the outermost plane of the new v (peer_lo3 / peer_hi3) into the neighbours
+  int64_t row0b, row1b, plane;
+  double* peer_lo3;
+  double* peer_hi3;
 };
 
 // Tsitouras 5(4) tableau (OrdinaryDiffEq's Tsit5ConstantCache; pinned by its order conditions in tests/test_oracle_pins.py)
@@ -1030,6 +1037,31 @@ int ddf_step_launch(ddf_mesh* m, cudaStream_t stream, int kind, const double* u,
 #ifndef DDF_WAVE2_DEFAULT
 #define DDF_WAVE2_DEFAULT 1    // measured at C4: 0.451 ms per step against 0.490 ms with one step per launch (profiles/r02_tuning.md)
 #endif
+
+// ---- for the slab driver of comm.cu: two leapfrog steps per launch with a DEEP halo (step n on the owned rows + one
+// ghost plane per side, step n+1 on the owned rows; the state after both steps of the outermost owned planes is stored
+// into the neighbours' landing arenas).  feasible: this rank's verdict (the ranks agree on it before using it).
+int ddf_pipe2_feasible(ddf_mesh* m, int* ok) {
+  *ok = 0;
+  const int tw = m->ctx->tune.wave;
+  if (!((tw & 65536) || (DDF_WAVE2_DEFAULT && !(tw & 131072) && (tw & 0xffff) == 0))) return 0;
+  DDF_CHECK(ddf_mesh_require_wave(m));
+  Pipe2Plan pl;
+  bool good = false;
+  DDF_CHECK(pipe2_plan(m, m->ctx->stream, &pl, &good));
+  *ok = good ? 1 : 0;
+  return 0;
+}
+int ddf_leapfrog_pair_launch(ddf_mesh* m, cudaStream_t stream, double* u, double* v, double* utmp, double dt, int64_t row0,
+                             int64_t row1, int64_t row0b, int64_t row1b, int64_t plane, double* const* peers6, int* ran) {
+  Pipe2Deep d;
+  d.row0 = row0; d.row1 = row1; d.row0b = row0b; d.row1b = row1b; d.plane = plane;
+  for (int q = 0; q < 6; q++) d.peers[q] = peers6[q];
+  bool r = false;
+  DDF_CHECK(launch_pipe2(m, stream, 0, u, v, utmp, dt, &r, &d));
+  *ran = r ? 1 : 0;
+  return 0;
+}
 
 int ddf_leapfrog_launch(ddf_mesh* m, cudaStream_t stream, const double* u, double* v, double* unew, double dt,
                         int64_t row0, int64_t row1) {

@@ -285,10 +285,13 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
         const uint32_t maxlen = __shfl_sync(0xffffffffu, mylen, 0);
         const uint32_t pl = (uint32_t)kk * DDF_SELL_WIN + p;
         const int64_t i = t.win * g.K * DDF_SELL_WIN + pl;
+        // deep halo (a.plane > 0, MODE 2): the step-(n+1) tasks cover the owned rows only
+        const int64_t r0 = (MODE == 2 && t.kind && a.plane > 0) ? a.row0b : a.row0;
+        const int64_t r1 = (MODE == 2 && t.kind && a.plane > 0) ? a.row1b : a.row1;
         double dinv_i = 0.0;                                 // MODE 3: requested now, needed after the row sum
-        if (MODE == 3 && i >= a.row0 && i < a.row1) dinv_i = __ldg(a.dinv + i);
+        if (MODE == 3 && i >= r0 && i < r1) dinv_i = __ldg(a.dinv + i);
         const double acc = pipe_row_sum<DDF_PIPE_UNR>(valS, slotS, stage, part, lane, mylen, maxlen);
-        if (i >= a.row0 && i < a.row1) {
+        if (i >= r0 && i < r1) {
           const double m = (metaS + STAGE_META_HDR + 2 * DDF_SELL_WIN)[p] ? 0.0 : 1.0;
           const double ev = reinterpret_cast<const double*>(sb + g.o_v)[pl];
           if (MODE == 3) {
@@ -296,7 +299,20 @@ k_rows_pipe2(RowArgs a, const uint32_t* __restrict__ tab, const unsigned char* _
           } else {
             const double vn = __dadd_rn(ev, __dmul_rn(a.dt, __dmul_rn(m, acc)));
             V[i] = vn;
-            uout[i] = __dadd_rn(reinterpret_cast<const double*>(sb + g.o_u)[pl], __dmul_rn(a.dt, __dmul_rn(m, vn)));
+            const double un = __dadd_rn(reinterpret_cast<const double*>(sb + g.o_u)[pl], __dmul_rn(a.dt, __dmul_rn(m, vn)));
+            uout[i] = un;
+            if (MODE == 2 && t.kind && a.plane > 0) {
+              // the state after BOTH steps of my outermost owned planes goes straight into the neighbours' landing arenas
+              const int64_t P = a.plane;
+              if (a.peer_lo) {
+                if (i < r0 + P) { a.peer_lo[i - r0] = un; a.peer_lo3[i - r0] = vn; }
+                else if (i < r0 + 2 * P) a.peer_lo2[i - r0 - P] = un;
+              }
+              if (a.peer_hi) {
+                if (i >= r1 - P) { a.peer_hi[i - (r1 - P)] = un; a.peer_hi3[i - (r1 - P)] = vn; }
+                else if (i >= r1 - 2 * P) a.peer_hi2[i - (r1 - 2 * P)] = un;
+              }
+            }
           }
         }
       }
@@ -330,16 +346,30 @@ __global__ void k_row_reach(const uint32_t* __restrict__ rowptr, const int32_t* 
 
 // Two leapfrog steps in one launch: on return u (U0) holds the state after both steps, utmp the one in between.
 // kind 0: leapfrog (aux = v in/out, coef = dt);  kind 1: Poisson relaxation sweep (aux = rho read-only, coef = theta)
-static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, int kind, double* u, double* aux, double* utmp, double coef, bool* ran) {
-  *ran = false;
-  const StageBufs& sb = m->lstage;
-  if (!sb.ok || m->ctx->nranks > 1) return 0;
+// deep halo of a slab (comm.cu): row ranges of the two steps and where the outermost owned planes go
+struct Pipe2Deep {
+  int64_t row0, row1;      // step n: owned rows + one ghost plane on either side that has one
+  int64_t row0b, row1b;    // step n + 1: owned rows
+  int64_t plane;
+  double* peers[6];        // lo: u nearest plane, u second plane, v nearest plane; hi: the same
+};
+
+// geometry and schedule of the two-step launch on this mesh; *ok = false when the wavefront cannot pay
+struct Pipe2Plan {
   PipeGeom g;
-  if (!pipe_geometry(m, &g)) return 0;
+  int64_t g0, g1, nit;
+  int grid, lag, reachw;
+};
+static int pipe2_plan(ddf_mesh* m, cudaStream_t stream, Pipe2Plan* pl, bool* ok) {
+  *ok = false;
+  const StageBufs& sb = m->lstage;
+  if (!sb.ok) return 0;
+  if (!pipe_geometry(m, &pl->g)) return 0;
   const int64_t nv = m->n[0];
   const int64_t gw = (int64_t)sb.K * DDF_SELL_WIN;
-  const int64_t g0 = 0, g1 = (nv + gw - 1) / gw;
-  const int grid = (int)std::min<int64_t>(m->ctx->sm_count, g1 - g0);
+  pl->g0 = 0;
+  pl->g1 = (nv + gw - 1) / gw;
+  pl->grid = (int)std::min<int64_t>(m->ctx->sm_count, pl->g1 - pl->g0);
   if (m->wave2_reach < 0) {
     DevBuf<unsigned long long> r;
     DDF_CHECK(r.alloc(m->ctx, 1));
@@ -353,17 +383,33 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, int kind, double* u, d
     DDF_CUDA(cudaStreamSynchronize(stream));
     m->wave2_reach = (int64_t)h;
   }
-  const int reachw = (int)(m->wave2_reach / gw) + 2;
+  pl->reachw = (int)(m->wave2_reach / gw) + 2;
   // tuning bits 18-21 of "wave": extra iterations of lag (default 3: measured best at C4 together with prefetch distance 2, profiles/r02_tuning.md)
   const int slack_t = (m->ctx->tune.wave >> 18) & 15;
   const int slack = slack_t ? slack_t - 1 : 3;
-  const int lag = (reachw + grid - 1) / grid + 1 + slack;
-  const int64_t nit = (g1 - g0 + grid - 1) / grid;
+  pl->lag = (pl->reachw + pl->grid - 1) / pl->grid + 1 + slack;
+  pl->nit = (pl->g1 - pl->g0 + pl->grid - 1) / pl->grid;
   // worth it only when the wavefront is short against the sweep: the windows between the two steps must stay in L2
   // (lag * grid windows of entries) and the first / last `lag` iterations run one step only
-  if (nit < 4 * (int64_t)lag) return 0;
-  const int64_t held = (int64_t)lag * grid * (int64_t)sb.max_entries * 10;
+  if (pl->nit < 4 * (int64_t)pl->lag) return 0;
+  const int64_t held = (int64_t)pl->lag * pl->grid * (int64_t)sb.max_entries * 10;
   if (held > (int64_t)64 << 20) return 0;
+  *ok = true;
+  return 0;
+}
+
+static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, int kind, double* u, double* aux, double* utmp, double coef, bool* ran,
+                        const Pipe2Deep* deep = nullptr) {
+  *ran = false;
+  const StageBufs& sb = m->lstage;
+  if (!sb.ok || (m->ctx->nranks > 1 && !deep)) return 0;
+  Pipe2Plan pl;
+  bool ok = false;
+  DDF_CHECK(pipe2_plan(m, stream, &pl, &ok));
+  if (!ok) return 0;
+  PipeGeom g = pl.g;
+  const int64_t nv = m->n[0], g0 = pl.g0, g1 = pl.g1, nit = pl.nit;
+  const int grid = pl.grid, lag = pl.lag, reachw = pl.reachw;
   if ((int64_t)m->wave2_done.n < nit) DDF_CHECK(m->wave2_done.alloc(m->ctx, (size_t)nit));
   DDF_CUDA(cudaMemsetAsync(m->wave2_done.p, 0, (size_t)nit * 4, stream));
   RowArgs a{};
@@ -372,6 +418,11 @@ static int launch_pipe2(ddf_mesh* m, cudaStream_t stream, int kind, double* u, d
   a.row0 = 0;
   a.row1 = nv;
   a.isb = m->isbnd[0].p;
+  if (deep) {
+    a.row0 = deep->row0; a.row1 = deep->row1; a.row0b = deep->row0b; a.row1b = deep->row1b; a.plane = deep->plane;
+    a.peer_lo = deep->peers[0]; a.peer_lo2 = deep->peers[1]; a.peer_lo3 = deep->peers[2];
+    a.peer_hi = deep->peers[3]; a.peer_hi2 = deep->peers[4]; a.peer_hi3 = deep->peers[5];
+  }
   if (kind == 0) { a.out0 = aux; a.dt = coef; }
   else { a.rho = aux; a.dinv = m->ldinv.p; a.theta = coef; }
   const size_t smem_p = (size_t)g.nstages * g.stage_bytes;

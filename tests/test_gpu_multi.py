@@ -26,7 +26,7 @@ def test_slab_decomposition_bit_exact_on_all_visible_gpus():
     out = res.stdout + res.stderr
     lines = [ln for ln in out.splitlines() if ln.startswith("dist_check")]
     assert res.returncode == 0, out[-4000:]
-    assert len(lines) >= 28 and all("BIT-EXACT" in ln for ln in lines), "\n".join(lines)
+    assert len(lines) >= 30 and all("BIT-EXACT" in ln for ln in lines), "\n".join(lines)
     assert sum("general partition" in ln for ln in lines) == 2, "\n".join(lines)
     assert any("halo=p2p" in ln for ln in lines) and any("halo=nccl" in ln for ln in lines), "\n".join(lines)
     t5 = [ln for ln in lines if ln.startswith("dist_check tsit5")]

@@ -35,8 +35,10 @@ def main():
     ctx = ddf.Context(local)
     ddf.dist.init_comm(ctx)
     ok = True
+    # the last case is large enough per rank (3200 row windows) for TWO steps per launch with the deep halo: 10 steps in
+    # calls of 1, 2 and 7 = single step, one pair, three pairs + a single step
     cases = ((3, (8, 8, 8 * world), 9), (2, (16, 16 * world), 12), (3, (16, 16, 4 * world + 4), 5),
-             (3, (48, 48, 16 * world), 7))
+             (3, (48, 48, 16 * world), 7), (3, (96, 96, 80 * world), 10))
     for tune, (D, nelts, nsteps) in [(t, c) for t in (0, 1024) for c in cases]:
         ddf._lib.call("ddf_set_tuning", b"wave", tune)       # 0: fused peer-memory halo, 1024: NCCL send/recv
         mfd, slab = ddf.dist.slab_hypercube(D, nelts, ctx)
@@ -47,8 +49,13 @@ def main():
         dt = ctx.allreduce(ddf.wave_dt(mfd), "min")
         # several calls with odd and even step counts: the ping-pong buffers swap roles between calls
         done = 0
+        launches = []
         for part in (1, 2, nsteps - 3):
+            ctx.sync()
+            l0 = ctx.launch_count()
             ddf.wave_leapfrog(mfd, u, v, dt, part)
+            ctx.sync()
+            launches.append(ctx.launch_count() - l0)
             done += part
         assert done == nsteps
         mode = ddf.dist.halo_mode(mfd)
@@ -70,7 +77,7 @@ def main():
                 a = zlo * plane
                 same = same and np.array_equal(pu, ru[a:a + len(pu)]) and np.array_equal(pv, rv[a:a + len(pv)])
             print(f"dist_check halo={mode} D={D} nelts={nelts} world={world} steps={nsteps}: "
-                  f"{'BIT-EXACT' if same else 'MISMATCH'}  |u|inf={np.max(np.abs(ru)):.6f}", flush=True)
+                  f"{'BIT-EXACT' if same else 'MISMATCH'}  |u|inf={np.max(np.abs(ru)):.6f}  launches per call {launches}", flush=True)
             ok = ok and same
             full.close()
         mfd.close()
