@@ -430,3 +430,92 @@ def test_general_partition_wave_equals_undivided():
     for rank, glo, ghi, u, v in sorted(res):
         assert np.array_equal(u, ou[glo:ghi]), f"rank {rank} u"
         assert np.array_equal(v, ov[glo:ghi]), f"rank {rank} v"
+
+
+def test_deep_halo_two_steps_per_exchange_model():
+    """Host model of the deep halo of csrc/comm.cu (steps_dist_p2p, two leapfrog steps per launch on slabs): a rank runs
+    step n on its owned rows PLUS one ghost plane per interior side (the slabs carry two ghost cell layers, so the
+    Laplacian rows, masks and geometry of that plane are complete locally), step n+1 on the owned rows, and only then
+    exchanges: the two outermost owned planes of u and the outermost plane of v per neighbour.  Lockstep emulation of
+    three ranks on the oracle's slab meshes; owned rows must equal the undivided oracle bit for bit, also with a single
+    step (one-plane exchange) mixed in."""
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import ddf_oracle as o
+    from importlib import import_module
+    dd = import_module("ddf.jl_b200.dist")
+    D, nxy, nz, world = 3, 2, 12, 3
+    plane = (nxy + 1) ** (D - 1)
+    slabs = dd.partition_slabs(nz, world, plane)
+    full = o.large_hypercube_manifold(D, (nxy,) * (D - 1) + (nz,), h_div=nxy)
+    rng = np.random.default_rng(8)
+    gu, gv = rng.standard_normal(full.nsimplices(0)), rng.standard_normal(full.nsimplices(0))
+    dt = 1.0 / (2 * nxy)
+    ranks = []
+    for s in slabs:
+        simp, coords, weights = o.large_hypercube_tables(D, (nxy,) * (D - 1) + (s.nz_cells,), h_div=nxy)
+        coords = coords.copy()
+        coords[:, -1] += s.z_cell_lo / nxy
+        m = o.build_manifold("slab", simp, coords, weights)
+        b, L = o.wave_operators(m)
+        Lr = L.tocsr()
+        Lr.sort_indices()
+        g0 = s.z_cell_lo * plane
+        n = m.nsimplices(0)
+        lo, hi = s.own_rows
+        ranks.append(dict(s=s, Lr=Lr, mask=1.0 - b.astype(np.float64), u=gu[g0:g0 + n].copy(), v=gv[g0:g0 + n].copy(),
+                          lo=lo, hi=hi, has_lo=s.ghost_lo > 0, has_hi=s.ghost_hi > 0))
+
+    def step(r, a, b_):                                   # one leapfrog step on rows [a, b_)
+        lu = o._segment_sum_sequential(r["Lr"].data * r["u"][r["Lr"].indices], r["Lr"].indptr)
+        vn, un = r["v"].copy(), r["u"].copy()
+        vn[a:b_] = r["v"][a:b_] + dt * (r["mask"][a:b_] * lu[a:b_])
+        un[a:b_] = r["u"][a:b_] + dt * (r["mask"][a:b_] * vn[a:b_])
+        r["u"], r["v"] = un, vn
+
+    def exchange(planes_u, planes_v):
+        snap = [(r["u"].copy(), r["v"].copy()) for r in ranks]
+        for k, r in enumerate(ranks):
+            lo, hi, P = r["lo"], r["hi"], plane
+            if r["has_lo"]:                               # from rank k-1: its top owned planes
+                pu, pv = snap[k - 1]
+                phi = ranks[k - 1]["hi"]
+                r["u"][lo - planes_u * P:lo] = pu[phi - planes_u * P:phi]
+                if planes_v:
+                    r["v"][lo - P:lo] = pv[phi - P:phi]
+            if r["has_hi"]:                               # from rank k+1: its lowest owned planes
+                pu, pv = snap[k + 1]
+                plo = ranks[k + 1]["lo"]
+                r["u"][hi:hi + planes_u * P] = pu[plo:plo + planes_u * P]
+                if planes_v:
+                    r["v"][hi:hi + P] = pv[plo:plo + P]
+
+    def pair():
+        for r in ranks:
+            P = plane
+            step(r, r["lo"] - (P if r["has_lo"] else 0), r["hi"] + (P if r["has_hi"] else 0))
+            step(r, r["lo"], r["hi"])
+        exchange(2, 1)
+
+    def single():
+        for r in ranks:
+            step(r, r["lo"], r["hi"])
+        exchange(1, 0)
+
+    nsteps = 0
+    exchange(2, 1)                                        # the refresh at the start of a pair segment
+    for _ in range(3):
+        pair()
+        nsteps += 2
+    single()
+    nsteps += 1
+    exchange(2, 1)                                        # a new pair segment after a single step
+    pair()
+    nsteps += 2
+    ou, ov = o.wave_leapfrog(full, gu, gv, dt, nsteps)
+    for r in ranks:
+        s = r["s"]
+        a, b_ = s.z_own_lo * plane, s.z_own_hi * plane
+        assert np.array_equal(r["u"][r["lo"]:r["hi"]], ou[a:b_]), s.rank
+        assert np.array_equal(r["v"][r["lo"]:r["hi"]], ov[a:b_]), s.rank
