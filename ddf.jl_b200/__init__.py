@@ -8,9 +8,11 @@ the dotted name onto this directory).  All compute runs in libddf_b200.so
 from ._lib import DDFError, LIB_PATH, load  # noqa: F401
 from .core import (Context, Dl, Fun, Manifold, Op, Pr, default_context, op_from_csc, op_from_diag,  # noqa: F401
                    rand_fun, set_default_context, unit_fun, zero_fun)
-from .manifoldops import (boundary, boundary_of, coderiv, coderiv_of, delaunay_mesh, deriv, deriv_format, deriv_index_bytes, deriv_of,  # noqa: F401
-                          hodge, hodge_of, integral, invhodge, invhodge_of, isboundary,
-                          large_hypercube_manifold, laplace, laplace_of, one, refined_manifold,
+from .manifoldops import (boundary, boundary_manifold, boundary_of, boundary_simplex_manifold, boundary_tables, coderiv,  # noqa: F401
+                          coderiv_of, delaunay_mesh, deriv, deriv_format, deriv_index_bytes, deriv_of,
+                          hodge, hodge_of, hypercube_manifold, hypercube_tables, integral, invhodge, invhodge_of, isboundary,
+                          large_hypercube_manifold, laplace, laplace_of, one, orthogonal_simplex_manifold,
+                          orthogonal_simplex_tables, refined_manifold,
                           refined_simplex_manifold, regular_simplex, sample, simplex_manifold, zero)
 from .wave import (lincomb, wave, wave_dt, wave_format, wave_leapfrog, wave_rhs, wave_step_bytes,  # noqa: F401
                    wave_tsit5)  # noqa: F401

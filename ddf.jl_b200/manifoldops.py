@@ -166,6 +166,92 @@ def simplex_manifold(D: int, ctx: Optional[Context] = None) -> Manifold:
     return Manifold.from_simplices("simplex manifold", simp, coords, ctx=ctx)
 
 
+def orthogonal_simplex_tables(D: int):
+    """(simplices, coords, weights) of the orthogonal D-simplex with unit legs (ManifoldConstructors.jl:82-113):
+    the origin and the D unit points; the origin carries the weight -1 + 1/D, the other vertices 0."""
+    if D < 0:
+        raise DDFError("orthogonal_simplex_manifold: D >= 0")
+    coords = np.zeros((D + 1, D))
+    coords[1:, :] = np.eye(D)
+    weights = np.zeros(D + 1)
+    if D > 0:
+        weights[0] = -1 + 1.0 / D
+    return np.arange(D + 1, dtype=np.int64)[None, :], coords, weights
+
+
+def orthogonal_simplex_manifold(D: int, ctx: Optional[Context] = None) -> Manifold:
+    """orthogonal_simplex_manifold(Val(D), Float64; optimize_mesh=false) (ManifoldConstructors.jl:82-96)."""
+    simp, coords, weights = orthogonal_simplex_tables(D)
+    return Manifold.from_simplices("orthogonal simplex manifold", simp, coords, weights, ctx=ctx)
+
+
+def hypercube_tables(D: int):
+    """(simplices, coords, weights) of the standard tesselation of the unit D-cube into D! simplices
+    (ManifoldConstructors.jl:121-190): every monotone lattice path from corner 0...0 to corner 1...1 is one simplex;
+    the paths are enumerated depth first, at every corner over the axes not yet taken in ascending order; a corner's
+    vertex number is the binary number of its coordinates with axis 1 as the lowest bit; all weights are zero."""
+    if D < 0:
+        raise DDFError("hypercube_manifold: D >= 0")
+    paths = []
+
+    def walk(corner: int, verts):
+        if len(verts) == D + 1:
+            paths.append(list(verts))
+            return
+        for d in range(D):
+            if not (corner >> d) & 1:
+                nxt = corner | (1 << d)
+                walk(nxt, verts + [nxt])
+
+    walk(0, [0])
+    assert len(paths) == math.factorial(D)
+    simp = np.array(paths, dtype=np.int64).reshape(len(paths), D + 1)
+    corners = np.arange(2 ** D, dtype=np.int64)
+    coords = ((corners[:, None] >> np.arange(D, dtype=np.int64)[None, :]) & 1).astype(np.float64).reshape(2 ** D, D)
+    return simp, coords, np.zeros(2 ** D)
+
+
+def hypercube_manifold(D: int, ctx: Optional[Context] = None) -> Manifold:
+    """hypercube_manifold(Val(D), Float64; optimize_mesh=false) (ManifoldConstructors.jl:121-154): the fixture of the
+    reference's own test-funs.jl / test-ops.jl."""
+    simp, coords, weights = hypercube_tables(D)
+    return Manifold.from_simplices("hypercube manifold", simp, coords, weights, ctx=ctx)
+
+
+def boundary_tables(nzval_rows: np.ndarray, faces: np.ndarray, coords: np.ndarray, weights: np.ndarray):
+    """The tables of boundary_manifold (ManifoldConstructors.jl:549-598) from `keep_face = B * ones` (row sums of the
+    top boundary matrix), the (D-1)-simplex table and the vertex data: the faces with a non-zero sum, their vertices
+    renumbered in ascending order of the old ids."""
+    keep = np.asarray(nzval_rows).reshape(-1)
+    if np.any(np.abs(keep) > 1):
+        raise DDFError("boundary_manifold: a face appears with total orientation beyond +-1 (ManifoldConstructors.jl:556)")
+    F = np.asarray(faces, dtype=np.int64)[keep != 0]
+    used = np.zeros(coords.shape[0], dtype=bool)
+    used[F.reshape(-1)] = True
+    old2new = np.cumsum(used) - 1
+    return old2new[F], np.asarray(coords)[used], np.asarray(weights)[used]
+
+
+def boundary_manifold(mfd0: Manifold) -> Manifold:
+    """boundary_manifold(mfd0; optimize_mesh=false) (ManifoldConstructors.jl:549-598): the (D-1)-dimensional manifold
+    of the faces whose boundary-matrix row does not cancel.  The face tables come from the device assembly; the
+    selection is host-side mesh input like the reference's."""
+    D = mfd0.D
+    if D <= 0:
+        raise DDFError("boundary_manifold: D > 0 (ManifoldConstructors.jl:550)")
+    B = mfd0.get_boundaries(D)
+    rows = np.asarray(B.astype(np.int64).sum(axis=1)).reshape(-1)
+    faces = mfd0.get_simplices(D - 1) if D - 1 >= 1 else np.arange(mfd0.nsimplices(0), dtype=np.int64)[:, None]
+    simp, coords, weights = boundary_tables(rows, faces, mfd0.get_coords(), mfd0.get_weights())
+    return Manifold.from_simplices("boundary " + mfd0.name, simp, coords, weights, ctx=mfd0.ctx)
+
+
+def boundary_simplex_manifold(D: int, ctx: Optional[Context] = None) -> Manifold:
+    """boundary_simplex_manifold(Val(D), Float64) (ManifoldConstructors.jl:606-610): the boundary of the regular
+    (D+1)-simplex -- a closed D-manifold embedded in D+1 coordinates."""
+    return boundary_manifold(simplex_manifold(D + 1, ctx))
+
+
 def delaunay_mesh(coords: np.ndarray) -> np.ndarray:
     """delaunay_mesh(coords) (Meshing.jl:19-49): the reference calls
     scipy.spatial.Delaunay through Delaunay.jl/PyCall; so does this."""

@@ -509,3 +509,33 @@ def test_vertex_range_partition_emulated_on_one_gpu(ddf, ctx):
     for m in meshes:
         m.close()
     full.close()
+
+
+# ------------------------------------------------------------------ A12: the reference's other fixtures as host constructors
+@pytest.mark.parametrize("D", [1, 2, 3, 4])
+def test_fixture_constructors_match_the_oracle(ddf, ctx, D):
+    """hypercube_manifold (the fixture of test-funs.jl / test-ops.jl), orthogonal_simplex_manifold and
+    boundary_simplex_manifold (test-manifolds.jl:277-299) built through the host mirror + device assembly: counts,
+    vertex tables, boundary matrices bit-exact, volumes / dual volumes at 1e-12 against the oracle's constructors."""
+    for make, omake in ((lambda: ddf.hypercube_manifold(D, ctx=ctx), lambda: o.hypercube_manifold(D)),
+                        (lambda: ddf.orthogonal_simplex_manifold(D, ctx=ctx), lambda: o.orthogonal_simplex_manifold(D)),
+                        (lambda: ddf.boundary_simplex_manifold(D, ctx=ctx), lambda: o.boundary_manifold(o.simplex_manifold(D + 1)))):
+        dm, om = make(), omake()
+        assert dm.D == om.D and dm.get_coords().shape == om.coords.shape
+        assert np.array_equal(dm.get_coords(), om.coords) and np.array_equal(dm.get_weights(), om.weights)
+        for R in range(om.D + 1):
+            assert dm.nsimplices(R) == om.nsimplices(R)
+            if R >= 1:
+                assert np.array_equal(dm.get_simplices(R), om.simplices[R])
+                cp, rv, nz = dm.get_boundaries_csc(R)
+                ocp, orv, onz = o.to_julia_csc(om.boundaries[R])
+                assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz)
+            if om.coords.shape[1] <= 3:                 # the device geometry covers D <= C <= 3 (DESIGN section 6)
+                v, ov = dm.get_volumes(R), o.calc_volumes(om, R)
+                assert np.max(np.abs(v - ov)) <= 1e-12 * max(1.0, float(np.max(np.abs(ov))))
+        dm.close()
+    with pytest.raises(ddf.DDFError):                    # the reference's own assertion on an unoriented mesh
+        if D >= 2:
+            ddf.boundary_manifold(ddf.hypercube_manifold(D, ctx=ctx))
+        else:
+            raise ddf.DDFError("D = 1: the hypercube is one edge, consistently oriented")
