@@ -262,6 +262,53 @@ def delaunay_mesh(coords: np.ndarray) -> np.ndarray:
     return np.asarray(Delaunay(coords).simplices, dtype=np.int64)
 
 
+def delaunay_hypercube_tables(D: int):
+    """Coordinates of delaunay_hypercube_manifold (ManifoldConstructors.jl:372-393): the 2^D corners of a unit cube moved
+    to [5/2, 7/2]^D ("re-map coordinates to avoid round-off errors"), first axis fastest; zero weights."""
+    corners = np.arange(2 ** D, dtype=np.int64)
+    coords = ((corners[:, None] >> np.arange(D, dtype=np.int64)[None, :]) & 1).astype(np.float64).reshape(2 ** D, D) + 2.5
+    return coords, np.zeros(2 ** D)
+
+
+def delaunay_hypercube_manifold(D: int, ctx: Optional[Context] = None) -> Manifold:
+    """delaunay_hypercube_manifold(Val(D), Float64; optimize_mesh=false): Delaunay triangulation (scipy Qhull, as in the
+    reference) of the cube's corners."""
+    coords, weights = delaunay_hypercube_tables(D)
+    return Manifold.from_simplices("delaunay hypercube manifold", delaunay_mesh(coords), coords, weights, ctx=ctx)
+
+
+LARGE_DELAUNAY_DEFAULT_NELTS = {0: 1, 1: 1024, 2: 32, 3: 16, 4: 4, 5: 2}
+
+
+def large_delaunay_hypercube_tables(D: int, nelts: Optional[int] = None):
+    """Coordinates of large_delaunay_hypercube_manifold (ManifoldConstructors.jl:401-470): the (nelts+1)^D grid points
+    i / nelts, first axis fastest, where for every axis d the coordinates of the LOWER axes d' < d that are not on the
+    boundary are squeezed by nelts / (nelts + di), di = (1/2) / sqrt(d - 1), and shifted by di / (nelts + di) on the odd
+    layers of axis d ("stagger every second point, except boundary points"); zero weights.  nelts must be a power of 2."""
+    if nelts is None:
+        nelts = LARGE_DELAUNAY_DEFAULT_NELTS[D]
+    if nelts < 1 or (nelts & (nelts - 1)):
+        raise DDFError("large_delaunay_hypercube_manifold: nelts must be a power of 2 (ManifoldConstructors.jl:413)")
+    n1 = nelts + 1
+    idx = np.indices((n1,) * D).reshape(D, -1, order="F").T if D > 0 else np.zeros((1, 0), dtype=np.int64)   # first axis fastest
+    coords = idx.astype(np.float64) / nelts
+    for d in range(1, D):                                    # 0-based axis d >= 1 (the reference's d = 2..D)
+        di = 0.5 / math.sqrt(float(d))
+        odd = (idx[:, d] & 1) == 1
+        for dp in range(d):
+            interior = (idx[:, dp] != 0) & (idx[:, dp] != nelts)
+            x1 = coords[:, dp] * nelts / (nelts + di)
+            x1 = np.where(odd, x1 + di / (nelts + di), x1)
+            coords[:, dp] = np.where(interior, x1, coords[:, dp])
+    return coords, np.zeros(coords.shape[0])
+
+
+def large_delaunay_hypercube_manifold(D: int, nelts: Optional[int] = None, ctx: Optional[Context] = None) -> Manifold:
+    """large_delaunay_hypercube_manifold(Val(D), Float64; nelts, optimize_mesh=false)."""
+    coords, weights = large_delaunay_hypercube_tables(D, nelts)
+    return Manifold.from_simplices("large delaunay hypercube manifold", delaunay_mesh(coords), coords, weights, ctx=ctx)
+
+
 def refined_manifold(mfd0: Manifold) -> Manifold:
     """refined_manifold(mfd0; optimize_mesh=false) (ManifoldConstructors.jl:521-529):
     old vertices + edge midpoints in edge-id order (Meshing.jl:127-146, on the device), Delaunay (scipy Qhull on the

@@ -52,3 +52,42 @@ def test_boundary_of_an_unoriented_mesh_is_rejected_like_the_reference():
     assert np.abs(rows).max() == 2
     with pytest.raises(mo.DDFError):
         mo.boundary_tables(rows, om.simplices[1], om.coords, om.weights)
+
+
+def _staggered_grid_literal(D, n):
+    """ManifoldConstructors.jl:436-451 transcribed point by point (0-based CartesianIndex from 0 to nelts, first axis
+    fastest; the loops over d and d' update x in place in that order)."""
+    import math
+    pts = []
+    for flat in range((n + 1) ** D):
+        i = [(flat // (n + 1) ** d) % (n + 1) for d in range(D)]
+        x = [i[d] / n for d in range(D)]
+        for d in range(1, D + 1):
+            for dp in range(1, d):
+                if i[dp - 1] in (0, n):
+                    continue
+                di = 0.5 / math.sqrt(d - 1)
+                x1 = x[dp - 1] * n / (n + di)
+                if i[d - 1] % 2 == 1:
+                    x1 = x1 + di / (n + di)
+                x[dp - 1] = x1
+        pts.append(x)
+    return np.array(pts).reshape(-1, D)
+
+
+@pytest.mark.parametrize("D,n", [(1, 8), (2, 8), (3, 4), (4, 2)])
+def test_delaunay_hypercube_tables(D, n):
+    """large_delaunay_hypercube_manifold: the vectorised coordinates equal the literal loop, boundary points stay on
+    the cube, and the Delaunay triangulation (scipy, the reference's backend) fills the unit cube (test-manifolds.jl
+    checks sum(volumes) on every fixture).  delaunay_hypercube_manifold: the 2^D corners shifted by 5/2."""
+    coords, weights = mo.large_delaunay_hypercube_tables(D, n)
+    assert np.array_equal(coords, _staggered_grid_literal(D, n)) and not weights.any()
+    assert coords.min() == 0.0 and coords.max() == 1.0
+    m = o.build_manifold("ld", mo.delaunay_mesh(coords), coords, weights)
+    assert abs(o.calc_volumes(m, D).sum() - 1.0) <= 1e-12
+    c2, w2 = mo.delaunay_hypercube_tables(D)
+    assert c2.shape == (2 ** D, D) and c2.min() == 2.5 and c2.max() == 3.5 and not w2.any()
+    m2 = o.build_manifold("dh", mo.delaunay_mesh(c2), c2, w2)
+    assert abs(o.calc_volumes(m2, D).sum() - 1.0) <= 1e-12
+    with pytest.raises(mo.DDFError):
+        mo.large_delaunay_hypercube_tables(D, 3)
